@@ -1,0 +1,110 @@
+/*
+ * hydrocore.h — C ABI of libhydrocore.so (hand-written sm_100a CUDA, no torch types).
+ *
+ * This is the drop-in boundary for pydrodem's depression-fill / D8 / flat-resolution /
+ * accumulation / labelling path.  pydrodem itself reaches that arithmetic by
+ * writing GeoTIFFs and spawning WhiteboxTools / TauDEM executables; each entry point below
+ * names the reference call site (file:line under /root/reference) whose native work it
+ * replaces.  Python binds these with ctypes (pydrodem_b200/_lib.py); INTEGRATION.md shows the
+ * stub a pydrodem maintainer would add.
+ *
+ * Conventions
+ *   - rasters are row-major, north-up, ny rows x nx columns, ny*nx < 2^31;
+ *   - a cell is "nodata" when z == nodata or z is NaN;
+ *   - every function returns 0 on success, a negative hc_status otherwise, and
+ *     hc_last_error() then returns a static thread-local message;
+ *   - *_dev entry points take DEVICE pointers and a cudaStream_t (as void*) and are
+ *     asynchronous apart from a few 4-byte read-backs; *_host entry points take HOST pointers
+ *     and do the H2D / D2H copies themselves;
+ *   - there is no CPU fallback: without a CUDA device hc_create fails.
+ */
+#ifndef HYDROCORE_H
+#define HYDROCORE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hc_ctx hc_ctx;
+
+enum hc_status {
+  HC_OK = 0,
+  HC_ERR_CUDA = -1,
+  HC_ERR_ARG = -2,
+  HC_ERR_NOMEM = -3,
+  HC_ERR_TOO_LARGE = -4,
+  HC_ERR_INTERNAL = -5
+};
+
+/* seed conventions of the two fills pydrodem calls */
+#define HC_SEED_WBT 0    /* wbt.fill_depressions_wang_and_liu: tools/depressions.py:1284 */
+#define HC_SEED_TAUDEM 1 /* TauDEM PitRemove: run_aws.py:582-588 */
+/* D8 code tables */
+#define HC_TABLE_WBT 0    /* wbt.d8_pointer: run_aws.py:539 (NE=1,E=2,SE=4,...,N=128; 0 none) */
+#define HC_TABLE_TAUDEM 1 /* TauDEM D8FlowDir -p: run_aws.py:594-603 (1=E .. 8=SE, ccw)      */
+#define HC_DIR_NOFLOW 0
+#define HC_DIR_NODATA 255
+
+const char *hc_last_error(void);
+int hc_version(void);
+
+/* one context per (process, device): owns the workspace arena and scratch events */
+int hc_create(hc_ctx **ctx, int device);
+int hc_destroy(hc_ctx *ctx);
+/* bytes of device workspace currently held */
+int64_t hc_workspace_bytes(const hc_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py "gpu_launches") */
+int64_t hc_launch_count(const hc_ctx *ctx);
+
+/* Depression fill, epsilon = 0: out = max(z, lowest spill level to a seed).
+ * Replaces wbt.fill_depressions_wang_and_liu / wbt.fill_depressions behind dep.fill_pits
+ * (tools/depressions.py:1236-1316, :1277, :1284; final fill models/depression_handling.py:480)
+ * and TauDEM PitRemove (run_aws.py:582-588).  z and out may not alias. */
+int hc_fill_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
+                int seed_mode, void *stream);
+
+/* D8 direction (uint8 code, HC_DIR_NODATA on nodata / TauDEM-contaminated cells) and optional
+ * slope (float32, may be NULL).  Replaces wbt.d8_pointer (run_aws.py:539) and the steepest-
+ * descent half of TauDEM D8FlowDir -p -sd8 (run_aws.py:594-603). */
+int hc_d8_dev(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx,
+              float nodata, double dx, double dy, int table, void *stream);
+
+/* Flat resolution (Barnes et al. 2014 two-gradient mask; the job TauDEM D8FlowDir does on
+ * filled pits, run_aws.py:594-603).  Rewrites HC_DIR_NOFLOW cells of drainable flats in place. */
+int hc_resolve_flats_dev(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx,
+                         float nodata, int table, void *stream);
+
+/* D8 flow accumulation in cells, self-inclusive, uint32.  Replaces wbt.d8_flow_accumulation
+ * (pntr=True, run_aws.py:544) and TauDEM AreaD8 -nc (run_aws.py:608-617). */
+int hc_accum_dev(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_t nx,
+                 int table, void *stream);
+
+/* The north-star chain fill -> D8(+slope) -> flats -> accumulation on one raster.
+ * filled / dir / acc are required, slope may be NULL; resolve_flats is a flag. */
+int hc_fill_d8_accum_dev(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope,
+                         uint32_t *acc, int64_t ny, int64_t nx, float nodata, double dx, double dy,
+                         int seed_mode, int table, int resolve_flats, void *stream);
+
+/* Connected-component labels of mask != 0, conn = 4 or 8, ids 1..n in raster-scan order of each
+ * component's first cell (exactly scipy.ndimage.label, tools/depressions.py:1646-1669,
+ * tools/endo.py:323).  *nlab receives n (host pointer, may be NULL). */
+int hc_label_dev(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn,
+                 int32_t *nlab, void *stream);
+
+/* HOST-buffer variants (H2D + kernels + D2H inside the call; synchronous). */
+int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
+                 int seed_mode);
+int hc_fill_d8_accum_host(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope,
+                          uint32_t *acc, int64_t ny, int64_t nx, float nodata, double dx, double dy,
+                          int seed_mode, int table, int resolve_flats);
+int hc_label_host(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn,
+                  int32_t *nlab);
+
+/* Diagnostics of the last fill on this context: basins found, Boruvka rounds run. */
+int hc_fill_stats(const hc_ctx *ctx, int64_t *n_basins, int32_t *n_rounds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDROCORE_H */

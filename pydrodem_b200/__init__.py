@@ -1,0 +1,11 @@
+"""pydrodem_b200 — B200-native (sm_100a) DEM hydro-conditioning core behind pydrodem's call boundary.
+
+Hot path: depression fill -> D8 direction/slope -> flat resolution -> D8 accumulation, plus
+connected-component labelling, all hand-written CUDA in libhydrocore.so reached through the C ABI of
+include/hydrocore.h.  No CPU fallback.
+"""
+from ._lib import (DIR_NODATA, DIR_NOFLOW, SEED_TAUDEM, SEED_WBT, TABLE_TAUDEM, TABLE_WBT,  # noqa: F401
+                   HydrocoreError)
+from .core import accum, d8, fill, fill_d8_accum, label, resolve_flats  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,94 @@
+"""ctypes binding of libhydrocore.so (the C ABI in include/hydrocore.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is present when a
+context is requested, this module raises.  Nothing here imports oracle/.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhydrocore.so")
+
+SEED_WBT, SEED_TAUDEM = 0, 1
+TABLE_WBT, TABLE_TAUDEM = 0, 1
+DIR_NOFLOW, DIR_NODATA = 0, 255
+
+c_i64, c_i32, c_f32, c_f64, c_vp = (ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_double,
+                                    ctypes.c_void_p)
+
+# name -> (restype, argtypes); every symbol include/hydrocore.h declares
+SIGNATURES = {
+    "hc_last_error": (ctypes.c_char_p, []),
+    "hc_version": (ctypes.c_int, []),
+    "hc_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int]),
+    "hc_destroy": (ctypes.c_int, [c_vp]),
+    "hc_workspace_bytes": (c_i64, [c_vp]),
+    "hc_launch_count": (c_i64, [c_vp]),
+    "hc_fill_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, c_vp]),
+    "hc_d8_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64, c_f64, ctypes.c_int, c_vp]),
+    "hc_resolve_flats_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, c_vp]),
+    "hc_accum_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_vp]),
+    "hc_fill_d8_accum_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64,
+                                            c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
+    "hc_label_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32), c_vp]),
+    "hc_fill_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int]),
+    "hc_fill_d8_accum_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64,
+                                             c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "hc_label_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32)]),
+    "hc_fill_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i32)]),
+}
+
+
+class HydrocoreError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """dlopen libhydrocore.so and type every entry point.  Raises if the extension is not built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise HydrocoreError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(or `make -C pydrodem_b200/csrc`). pydrodem_b200 has no CPU fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError if the ABI drifted
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().hc_last_error().decode("utf-8", "replace")
+        raise HydrocoreError(f"{what} failed (rc={rc}): {msg}")
+
+
+_ctxs = {}
+
+
+def context(device=0):
+    """One hc_ctx per device per process (owns the device workspace arena)."""
+    lib = load()
+    with _lock:
+        h = _ctxs.get(device)
+        if h is None:
+            p = c_vp()
+            rc = lib.hc_create(ctypes.byref(p), int(device))
+            if rc != 0:
+                raise HydrocoreError(f"hc_create(device={device}) failed (rc={rc}): "
+                                     f"{lib.hc_last_error().decode('utf-8', 'replace')}")
+            h = _ctxs[device] = p
+    return h
+
+
+def launch_count(device=0):
+    return int(load().hc_launch_count(context(device)))

@@ -1,0 +1,253 @@
+// api.cu — the extern "C" surface declared in include/hydrocore.h, the context and its arena.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void hc_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *hc_last_error(void) { return g_err; }
+extern "C" int hc_version(void) { return 100; }
+
+// ---- arena ------------------------------------------------------------------------------------
+int arena_reset(hc_ctx *ctx) {
+  if (ctx->n_blocks > 1) {
+    // coalesce: next time the same workload fits one block and allocates nothing
+    size_t total = 0;
+    HC_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < ctx->n_blocks; i++) {
+      total += ctx->blocks[i].cap;
+      cudaFree(ctx->blocks[i].p);
+    }
+    ctx->n_blocks = 0;
+    char *p = nullptr;
+    if (cudaMalloc(&p, total) == cudaSuccess) {
+      ctx->blocks[0].p = p;
+      ctx->blocks[0].cap = total;
+      ctx->blocks[0].off = 0;
+      ctx->n_blocks = 1;
+    } else {
+      cudaGetLastError();  // fall back to on-demand blocks
+    }
+  }
+  for (int i = 0; i < ctx->n_blocks; i++) ctx->blocks[i].off = 0;
+  return HC_OK;
+}
+
+void *arena_take(hc_ctx *ctx, size_t bytes) {
+  size_t b = hc_align(bytes ? bytes : 1);
+  for (int i = 0; i < ctx->n_blocks; i++) {
+    hc_block *k = &ctx->blocks[i];
+    if (k->cap - k->off >= b) {
+      void *p = k->p + k->off;
+      k->off += b;
+      return p;
+    }
+  }
+  if (ctx->n_blocks == HC_MAX_BLOCKS) { hc_set_error("arena: too many blocks"); return nullptr; }
+  char *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, b);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    hc_set_error("arena: cudaMalloc(%zu) -> %s", b, cudaGetErrorString(e));
+    return nullptr;
+  }
+  hc_block *k = &ctx->blocks[ctx->n_blocks++];
+  k->p = p; k->cap = b; k->off = b;
+  return p;
+}
+
+// ---- context ----------------------------------------------------------------------------------
+extern "C" int hc_create(hc_ctx **out, int device) {
+  if (!out) { hc_set_error("hc_create: null out"); return HC_ERR_ARG; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    hc_set_error("hc_create: no CUDA device (%s) - libhydrocore has no CPU path", cudaGetErrorString(e));
+    cudaGetLastError();
+    return HC_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { hc_set_error("hc_create: device %d out of range", device); return HC_ERR_ARG; }
+  HC_CUDA(cudaSetDevice(device));
+  hc_ctx *ctx = (hc_ctx *)calloc(1, sizeof(hc_ctx));
+  if (!ctx) return HC_ERR_NOMEM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  HC_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  HC_CUDA(cudaMallocHost(&ctx->h_mail, 256));
+  *out = ctx;
+  return HC_OK;
+}
+
+extern "C" int hc_destroy(hc_ctx *ctx) {
+  if (!ctx) return HC_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < ctx->n_blocks; i++) cudaFree(ctx->blocks[i].p);
+  if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+  free(ctx);
+  return HC_OK;
+}
+
+extern "C" int64_t hc_workspace_bytes(const hc_ctx *ctx) {
+  int64_t t = 0;
+  for (int i = 0; i < ctx->n_blocks; i++) t += (int64_t)ctx->blocks[i].cap;
+  return t;
+}
+extern "C" int64_t hc_launch_count(const hc_ctx *ctx) { return ctx->launches; }
+extern "C" int hc_fill_stats(const hc_ctx *ctx, int64_t *n_basins, int32_t *n_rounds) {
+  if (n_basins) *n_basins = ctx->fill_basins;
+  if (n_rounds) *n_rounds = ctx->fill_rounds;
+  return HC_OK;
+}
+
+#define CHECK_CTX(ctx)                                             \
+  do {                                                             \
+    if (!(ctx)) { hc_set_error("null context"); return HC_ERR_ARG; } \
+    HC_CUDA(cudaSetDevice((ctx)->device));                         \
+  } while (0)
+
+static int check_shape(int64_t ny, int64_t nx) {
+  if (ny < 0 || nx < 0) { hc_set_error("negative shape"); return HC_ERR_ARG; }
+  if (ny > 0 && nx > 0 && (double)ny * (double)nx >= 2147483632.0) {
+    hc_set_error("raster of %lld x %lld cells exceeds the 31-bit cell index", (long long)ny, (long long)nx);
+    return HC_ERR_TOO_LARGE;
+  }
+  return HC_OK;
+}
+
+// ---- device entry points ------------------------------------------------------------------------
+extern "C" int hc_fill_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
+                           int seed_mode, void *stream) {
+  CHECK_CTX(ctx);
+  HC_TRY(check_shape(ny, nx));
+  if (ny && nx && (!z || !out)) { hc_set_error("hc_fill: null pointer"); return HC_ERR_ARG; }
+  if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("hc_fill: bad seed_mode"); return HC_ERR_ARG; }
+  return fill_run(ctx, z, out, ny, nx, nodata, seed_mode, (cudaStream_t)stream);
+}
+
+extern "C" int hc_d8_dev(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx,
+                         float nodata, double dx, double dy, int table, void *stream) {
+  CHECK_CTX(ctx);
+  HC_TRY(check_shape(ny, nx));
+  if (ny && nx && (!z || !dir)) { hc_set_error("hc_d8: null pointer"); return HC_ERR_ARG; }
+  return d8_run(ctx, z, dir, slope, ny, nx, nodata, dx, dy, table, (cudaStream_t)stream);
+}
+
+extern "C" int hc_resolve_flats_dev(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx,
+                                    float nodata, int table, void *stream) {
+  CHECK_CTX(ctx);
+  HC_TRY(check_shape(ny, nx));
+  if (ny && nx && (!z || !dir)) { hc_set_error("hc_resolve_flats: null pointer"); return HC_ERR_ARG; }
+  return flats_run(ctx, z, dir, ny, nx, nodata, table, (cudaStream_t)stream);
+}
+
+extern "C" int hc_accum_dev(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_t nx, int table,
+                            void *stream) {
+  CHECK_CTX(ctx);
+  HC_TRY(check_shape(ny, nx));
+  if (ny && nx && (!dir || !acc)) { hc_set_error("hc_accum: null pointer"); return HC_ERR_ARG; }
+  return accum_run(ctx, dir, acc, ny, nx, table, (cudaStream_t)stream);
+}
+
+extern "C" int hc_fill_d8_accum_dev(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope,
+                                    uint32_t *acc, int64_t ny, int64_t nx, float nodata, double dx, double dy,
+                                    int seed_mode, int table, int resolve_flats, void *stream) {
+  CHECK_CTX(ctx);
+  HC_TRY(check_shape(ny, nx));
+  if (ny && nx && (!z || !filled || !dir || !acc)) { hc_set_error("hc_fill_d8_accum: null pointer"); return HC_ERR_ARG; }
+  if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("bad seed_mode"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_TRY(fill_run(ctx, z, filled, ny, nx, nodata, seed_mode, st));
+  HC_TRY(d8_run(ctx, filled, dir, slope, ny, nx, nodata, dx, dy, table, st));
+  if (resolve_flats) HC_TRY(flats_run(ctx, filled, dir, ny, nx, nodata, table, st));
+  HC_TRY(accum_run(ctx, dir, acc, ny, nx, table, st));
+  return HC_OK;
+}
+
+extern "C" int hc_label_dev(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn,
+                            int32_t *nlab, void *stream) {
+  CHECK_CTX(ctx);
+  HC_TRY(check_shape(ny, nx));
+  if (ny && nx && (!mask || !lab)) { hc_set_error("hc_label: null pointer"); return HC_ERR_ARG; }
+  return label_run(ctx, mask, lab, ny, nx, conn, nlab, (cudaStream_t)stream);
+}
+
+// ---- host entry points --------------------------------------------------------------------------
+struct dev_buf {
+  void *p = nullptr;
+  ~dev_buf() { if (p) cudaFree(p); }
+  int alloc(size_t b) {
+    cudaError_t e = cudaMalloc(&p, b ? b : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); hc_set_error("cudaMalloc(%zu) -> %s", b, cudaGetErrorString(e)); p = nullptr; return HC_ERR_NOMEM; }
+    return HC_OK;
+  }
+};
+
+extern "C" int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
+                            int seed_mode) {
+  CHECK_CTX(ctx);
+  HC_TRY(check_shape(ny, nx));
+  size_t n = (size_t)ny * nx;
+  if (!n) return HC_OK;
+  if (!z || !out) { hc_set_error("hc_fill_host: null pointer"); return HC_ERR_ARG; }
+  dev_buf dz, dout;
+  HC_TRY(dz.alloc(n * 4));
+  HC_TRY(dout.alloc(n * 4));
+  HC_CUDA(cudaMemcpyAsync(dz.p, z, n * 4, cudaMemcpyHostToDevice, 0));
+  HC_TRY(hc_fill_dev(ctx, (const float *)dz.p, (float *)dout.p, ny, nx, nodata, seed_mode, nullptr));
+  HC_CUDA(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, 0));
+  HC_CUDA(cudaStreamSynchronize(0));
+  return HC_OK;
+}
+
+extern "C" int hc_fill_d8_accum_host(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope,
+                                     uint32_t *acc, int64_t ny, int64_t nx, float nodata, double dx, double dy,
+                                     int seed_mode, int table, int resolve_flats) {
+  CHECK_CTX(ctx);
+  HC_TRY(check_shape(ny, nx));
+  size_t n = (size_t)ny * nx;
+  if (!n) return HC_OK;
+  if (!z || !filled || !dir || !acc) { hc_set_error("hc_fill_d8_accum_host: null pointer"); return HC_ERR_ARG; }
+  dev_buf dz, df, dd, ds, da;
+  HC_TRY(dz.alloc(n * 4));
+  HC_TRY(df.alloc(n * 4));
+  HC_TRY(dd.alloc(n));
+  if (slope) HC_TRY(ds.alloc(n * 4));
+  HC_TRY(da.alloc(n * 4));
+  HC_CUDA(cudaMemcpyAsync(dz.p, z, n * 4, cudaMemcpyHostToDevice, 0));
+  HC_TRY(hc_fill_d8_accum_dev(ctx, (const float *)dz.p, (float *)df.p, (uint8_t *)dd.p, (float *)ds.p,
+                              (uint32_t *)da.p, ny, nx, nodata, dx, dy, seed_mode, table, resolve_flats, nullptr));
+  HC_CUDA(cudaMemcpyAsync(filled, df.p, n * 4, cudaMemcpyDeviceToHost, 0));
+  HC_CUDA(cudaMemcpyAsync(dir, dd.p, n, cudaMemcpyDeviceToHost, 0));
+  if (slope) HC_CUDA(cudaMemcpyAsync(slope, ds.p, n * 4, cudaMemcpyDeviceToHost, 0));
+  HC_CUDA(cudaMemcpyAsync(acc, da.p, n * 4, cudaMemcpyDeviceToHost, 0));
+  HC_CUDA(cudaStreamSynchronize(0));
+  return HC_OK;
+}
+
+extern "C" int hc_label_host(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn,
+                             int32_t *nlab) {
+  CHECK_CTX(ctx);
+  HC_TRY(check_shape(ny, nx));
+  size_t n = (size_t)ny * nx;
+  if (nlab) *nlab = 0;
+  if (!n) return HC_OK;
+  if (!mask || !lab) { hc_set_error("hc_label_host: null pointer"); return HC_ERR_ARG; }
+  dev_buf dm, dl;
+  HC_TRY(dm.alloc(n));
+  HC_TRY(dl.alloc(n * 4));
+  HC_CUDA(cudaMemcpyAsync(dm.p, mask, n, cudaMemcpyHostToDevice, 0));
+  HC_TRY(hc_label_dev(ctx, (const uint8_t *)dm.p, (int32_t *)dl.p, ny, nx, conn, nlab, nullptr));
+  HC_CUDA(cudaMemcpyAsync(lab, dl.p, n * 4, cudaMemcpyDeviceToHost, 0));
+  HC_CUDA(cudaStreamSynchronize(0));
+  return HC_OK;
+}

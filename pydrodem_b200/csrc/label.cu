@@ -1,0 +1,257 @@
+// label.cu — connected-component labelling with scipy.ndimage.label's numbering, and the
+// exterior-nodata mask the WBT seed rule needs.
+//
+// Replaces scipy.ndimage.label as called by dep.create_clump_array (tools/depressions.py:1646-1669)
+// and endo.find_sink (tools/endo.py:323): 8- or 4-connectivity, ids 1..n in raster-scan order of
+// each component's first cell.
+//
+// Union-find on the pixel grid (each cell links to the smaller root, so a component's root is its
+// first cell in raster order), then the roots are ranked by a three-kernel exclusive scan.
+#include "common.cuh"
+
+__device__ __forceinline__ u32 uf_find(volatile u32 *L, u32 i) {
+  u32 p = L[i];
+  while (p != i) { i = p; p = L[i]; }
+  return i;
+}
+
+__device__ __forceinline__ void uf_union(u32 *L, u32 a, u32 b) {
+  volatile u32 *VL = L;
+  for (;;) {
+    a = uf_find(VL, a);
+    b = uf_find(VL, b);
+    if (a == b) return;
+    if (a < b) { u32 t = a; a = b; b = t; }  // a > b: hang a under b
+    u32 old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_lab_init(const uint8_t *__restrict__ mask, u32 *__restrict__ L, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) L[i] = mask[i] ? (u32)i : HC_NONE;
+}
+
+__global__ void __launch_bounds__(256)
+k_lab_merge(const uint8_t *__restrict__ mask, u32 *L, int ny, int nx, int conn8) {
+  size_t n = (size_t)ny * nx;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !mask[i]) return;
+  int r = (int)(i / (size_t)nx), c = (int)(i - (size_t)r * nx);
+  if (c > 0 && mask[i - 1]) uf_union(L, (u32)i, (u32)(i - 1));
+  if (r > 0) {
+    if (mask[i - nx]) uf_union(L, (u32)i, (u32)(i - nx));
+    if (conn8) {
+      if (c > 0 && mask[i - nx - 1]) uf_union(L, (u32)i, (u32)(i - nx - 1));
+      if (c < nx - 1 && mask[i - nx + 1]) uf_union(L, (u32)i, (u32)(i - nx + 1));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_lab_compress(u32 *L, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 p = L[i];
+  if (p == HC_NONE) return;
+  L[i] = uf_find((volatile u32 *)L, p);
+}
+
+// ---- rank the roots: exclusive scan of (L[i] == i) ------------------------------------------------
+#define SCAN_CHUNK 4096  // cells per block
+
+__global__ void __launch_bounds__(256)
+k_root_count(const u32 *__restrict__ L, u32 *__restrict__ bsum, size_t n) {
+  __shared__ u32 s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  size_t base = (size_t)blockIdx.x * SCAN_CHUNK;
+  u32 cnt = 0;
+  for (int j = threadIdx.x; j < SCAN_CHUNK; j += 256) {
+    size_t i = base + j;
+    if (i < n && L[i] == (u32)i) cnt++;
+  }
+  atomicAdd(&s, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) bsum[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_blocks(u32 *bsum, u32 nb, u32 *total) {
+  // single block, sequential over chunks of 1024 with a running carry
+  __shared__ u32 sh[1024];
+  __shared__ u32 carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (u32 base = 0; base < nb; base += 1024) {
+    u32 i = base + threadIdx.x;
+    u32 v = i < nb ? bsum[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      u32 t = threadIdx.x >= (u32)off ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    u32 incl = sh[threadIdx.x];
+    if (i < nb) bsum[i] = carry + incl - v;  // exclusive
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(256)
+k_root_rank(const u32 *__restrict__ L, const u32 *__restrict__ bsum, u32 *__restrict__ R, size_t n) {
+  // in-block exclusive scan of root flags, 16 consecutive cells per thread
+  __shared__ u32 sh[256];
+  size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * 16;
+  u32 cnt = 0;
+  u32 flags = 0;
+  for (int j = 0; j < 16; j++) {
+    size_t i = base + j;
+    if (i < n && L[i] == (u32)i) { cnt++; flags |= 1u << j; }
+  }
+  sh[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    u32 t = threadIdx.x >= (u32)off ? sh[threadIdx.x - off] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  u32 run = bsum[blockIdx.x] + sh[threadIdx.x] - cnt;
+  for (int j = 0; j < 16; j++)
+    if (flags & (1u << j)) R[base + j] = ++run;  // 1-based id
+}
+
+__global__ void __launch_bounds__(256)
+k_lab_out(const u32 *__restrict__ L, const u32 *__restrict__ R, int32_t *__restrict__ lab, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    u32 p = L[i];
+    lab[i] = p == HC_NONE ? 0 : (int32_t)__ldg(&R[p]);
+  }
+}
+
+size_t label_workspace(int64_t ny, int64_t nx) {
+  size_t n = (size_t)ny * nx;
+  return 2 * hc_align(n * 4) + hc_align(((n + SCAN_CHUNK - 1) / SCAN_CHUNK) * 4) + hc_align(256);
+}
+
+static int label_roots(hc_ctx *ctx, const uint8_t *mask, u32 *L, int64_t ny, int64_t nx, int conn, cudaStream_t st) {
+  size_t n = (size_t)ny * nx;
+  unsigned nb = (unsigned)((n + 255) / 256);
+  k_lab_init<<<ctx->sm_count * 8, 256, 0, st>>>(mask, L, n);
+  HC_LAUNCH_CHECK(ctx);
+  k_lab_merge<<<nb, 256, 0, st>>>(mask, L, (int)ny, (int)nx, conn == 8);
+  HC_LAUNCH_CHECK(ctx);
+  k_lab_compress<<<nb, 256, 0, st>>>(L, n);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+int label_run(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn, int32_t *nlab,
+              cudaStream_t st) {
+  if (nlab) *nlab = 0;
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (conn != 4 && conn != 8) { hc_set_error("label: conn must be 4 or 8"); return HC_ERR_ARG; }
+  size_t n = (size_t)ny * nx;
+  if (n >= 0x7FFFFFF0ull) { hc_set_error("raster too large"); return HC_ERR_TOO_LARGE; }
+  HC_TRY(arena_reset(ctx));
+  u32 nchunks = (u32)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  u32 *L = (u32 *)arena_take(ctx, n * 4);
+  u32 *R = (u32 *)arena_take(ctx, n * 4);
+  u32 *bsum = (u32 *)arena_take(ctx, (size_t)nchunks * 4);
+  u32 *total = (u32 *)arena_take(ctx, 256);
+  if (!L || !R || !bsum || !total) return HC_ERR_NOMEM;
+  HC_TRY(label_roots(ctx, mask, L, ny, nx, conn, st));
+  k_root_count<<<nchunks, 256, 0, st>>>(L, bsum, n);
+  HC_LAUNCH_CHECK(ctx);
+  k_scan_blocks<<<1, 1024, 0, st>>>(bsum, nchunks, total);
+  HC_LAUNCH_CHECK(ctx);
+  k_root_rank<<<nchunks, 256, 0, st>>>(L, bsum, R, n);
+  HC_LAUNCH_CHECK(ctx);
+  k_lab_out<<<ctx->sm_count * 8, 256, 0, st>>>(L, R, lab, n);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, total, 4, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  if (nlab) *nlab = (int32_t)ctx->h_mail[0];
+  return HC_OK;
+}
+
+// ---- exterior nodata (WBT seed rule) ------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_nodata_mask(const float *__restrict__ z, uint8_t *__restrict__ m, int ny, int nx, float nodata, u32 *interior) {
+  size_t n = (size_t)ny * nx;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  u32 any = 0;
+  for (; i < n; i += stride) {
+    float v = z[i];
+    uint8_t nd = d_is_nodata(v, nodata);
+    m[i] = nd;
+    if (nd) {
+      int r = (int)(i / (size_t)nx), c = (int)(i - (size_t)r * nx);
+      if (r > 0 && c > 0 && r < ny - 1 && c < nx - 1) any = 1;
+    }
+  }
+  if (any) *interior = 1u;
+}
+
+__global__ void __launch_bounds__(256)
+k_ext_flag_border(const u32 *__restrict__ L, uint8_t *__restrict__ flag, int ny, int nx) {
+  // threads over the 2*nx + 2*ny border cells
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int r, c;
+  if (t < nx) { r = 0; c = t; }
+  else if (t < 2 * nx) { r = ny - 1; c = t - nx; }
+  else if (t < 2 * nx + ny) { r = t - 2 * nx; c = 0; }
+  else if (t < 2 * nx + 2 * ny) { r = t - 2 * nx - ny; c = nx - 1; }
+  else return;
+  u32 p = L[(size_t)r * nx + c];
+  if (p != HC_NONE) flag[p] = 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_ext_out(const u32 *__restrict__ L, const uint8_t *__restrict__ flag, uint8_t *__restrict__ ext, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    u32 p = L[i];
+    ext[i] = p == HC_NONE ? 0 : flag[p];
+  }
+}
+
+// ext[i] = 1 iff cell i is nodata and 8-connected through nodata to the raster border.
+// ext must have been taken from the arena by the caller (no arena_reset here).
+int ext_nodata_mask(hc_ctx *ctx, const float *z, uint8_t *ext, int64_t ny, int64_t nx, float nodata,
+                    int *has_interior, cudaStream_t st) {
+  size_t n = (size_t)ny * nx;
+  u32 *flagw = (u32 *)arena_take(ctx, 256);
+  if (!flagw) return HC_ERR_NOMEM;
+  HC_CUDA(cudaMemsetAsync(flagw, 0, 4, st));
+  k_nodata_mask<<<ctx->sm_count * 8, 256, 0, st>>>(z, ext, (int)ny, (int)nx, nodata, flagw);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, flagw, 4, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  *has_interior = ctx->h_mail[0] != 0;
+  if (!*has_interior) return HC_OK;
+  u32 *L = (u32 *)arena_take(ctx, n * 4);
+  uint8_t *flag = (uint8_t *)arena_take(ctx, n);
+  if (!L || !flag) return HC_ERR_NOMEM;
+  HC_TRY(label_roots(ctx, ext, L, ny, nx, 8, st));
+  HC_CUDA(cudaMemsetAsync(flag, 0, n, st));
+  int nbord = (int)(2 * nx + 2 * ny);
+  k_ext_flag_border<<<(nbord + 255) / 256, 256, 0, st>>>(L, flag, (int)ny, (int)nx);
+  HC_LAUNCH_CHECK(ctx);
+  k_ext_out<<<ctx->sm_count * 8, 256, 0, st>>>(L, flag, ext, n);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
