@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — Mcells/s for fill + D8 (+flat resolution) + accumulation on the C2 workload.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one pass of the hot path (hc_fill_d8_accum: PitRemove -> D8FlowDir -> AreaD8 semantics,
+run_aws.py:580-617) over one synthetic 10801 x 10801 float32 DEM with random pits (BASELINE.json
+configs[1]) that is already resident in HBM.  `e2e` times the same call through the HOST-buffer C
+ABI (hc_fill_d8_accum_host) with pinned host arrays, H2D/D2H inside the timed region.  N > 1 runs
+one such unit per GPU (weak scaling, no data-path collective), timed as max over ranks.
+
+--impl reference times the CPU path on the host cores: the oracle port of the WhiteboxTools /
+TauDEM algorithms (the binaries pydrodem shells out to are not installable here), farmed over
+min(cores, 14) independent 3601^2 units the way the reference farms units over a process pool
+(models/depression_handling.py:1625-1635).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mcells/s fill+D8+accum"
+UNIT = "Mcells/s"
+BYTES_PER_CELL = {"fill": 8, "d8": 5, "flats": 0, "accum": 5}  # 18 B/cell in total
+KERNEL_PASS = {
+    "k_ptr": "fill", "k_perim": "fill", "k_flatten": "fill", "k_minedge": "fill", "k_tab_init": "fill",
+    "k_hook": "fill", "k_mutual": "fill", "k_jump": "fill", "k_merge": "fill", "k_repflat": "fill",
+    "k_levels": "fill", "k_apply": "fill", "k_nodata_mask": "fill", "k_lab_init": "fill", "k_lab_merge": "fill",
+    "k_lab_compress": "fill", "k_ext_flag_border": "fill", "k_ext_out": "fill",
+    "k_d8": "d8", "k_flat_init": "flats", "k_flat_relax": "flats", "k_flat_dirs": "flats",
+    "k_acc_init": "accum", "k_acc_walk": "accum", "k_acc_out": "accum",
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            s = sorted(sm)
+            out.update(sm_mhz=s[len(s) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_chain_rate(z, threads=1):
+    """Oracle fill+D8+flats+accum on numpy DEM(s); returns (Mcells/s, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import hydro_oracle as O
+    O.build()
+    zs = z if isinstance(z, list) else [z]
+    t0 = time.perf_counter()
+    if threads == 1:
+        for a in zs:
+            O.fill_d8_accum(a, dx=30.0, dy=30.0, seed_mode=O.SEED_TAUDEM, table=O.TABLE_TAUDEM)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda a: O.fill_d8_accum(a, dx=30.0, dy=30.0, seed_mode=O.SEED_TAUDEM,
+                                                  table=O.TABLE_TAUDEM), zs))
+    dt = time.perf_counter() - t0
+    cells = sum(a.size for a in zs)
+    return cells / dt / 1e6, dt
+
+
+def run_reference(args):
+    """CPU arm: unit farm over the host cores, 3601^2 units (BASELINE.json configs[0] size)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from pydrodem_b200 import synth
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 14))
+    side = args.ref_size
+    units = [synth.make_dem_numpy(side, side, 1002 + i) for i in range(threads)]
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_chain_rate(units, threads)
+    tot_cells, tot_t = 0, 0.0
+    steps = args.steps
+    for _ in range(steps):
+        r, dt = cpu_chain_rate(units, threads)
+        tot_cells += sum(u.size for u in units)
+        tot_t += dt
+    value = tot_cells / tot_t / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": tot_t / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2 recipe (fBm + random pits + bowls, 1 cm), {threads} units of {side}x{side} per step, "
+                               "fill+D8+flats+accum (TauDEM semantics)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{threads} x {side}^2 units per step over a {threads}-thread pool "
+                                   f"({cores} logical cores on the box); oracle port of WBT/TauDEM algorithms"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=10801, help="DEM edge (default: configs[1] = 10801)")
+    ap.add_argument("--ref-size", type=int, default=3601)
+    ap.add_argument("--cpu-sample", type=int, default=5400, help="edge of the crop timed on the CPU (0 = skip)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--flats", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import pydrodem_b200 as hc
+    from pydrodem_b200 import _lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ny = nx = args.size
+    cells = ny * nx
+    # one unit per GPU (weak scaling): same recipe, per-rank seed
+    z = torch.empty((ny, nx), dtype=torch.float32, device=dev)
+    band = 1024
+    for r0 in range(0, ny, band):
+        nr = min(band, ny - r0)
+        z[r0:r0 + nr] = synth.make_dem(ny, nx, 1002 + rank, row0=r0, nrows=nr, device=dev)
+    torch.cuda.synchronize()
+
+    kw = dict(dx=30.0, dy=30.0, seed_mode=hc.SEED_TAUDEM, table=hc.TABLE_TAUDEM, flats=bool(args.flats),
+              want_slope=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for _ in range(args.warmup):
+        out = hc.fill_d8_accum(z, **kw)
+    barrier()
+    _lib.profile_enable(True, local)
+    launches0 = _lib.launch_count(local)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = hc.fill_d8_accum(z, **kw)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count(local) - launches0
+    prof = _lib.profile_read(local)
+    _lib.profile_enable(False, local)
+    basins, rounds = hc.core.fill_stats(local)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * cells * args.steps / (ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C ABI ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        import ctypes
+        lib = _lib.load()
+        ctx = _lib.context(local)
+        hz = torch.empty((ny, nx), dtype=torch.float32, pin_memory=True)
+        hz.copy_(z)
+        hf = torch.empty((ny, nx), dtype=torch.float32, pin_memory=True)
+        hd = torch.empty((ny, nx), dtype=torch.uint8, pin_memory=True)
+        ha = torch.empty((ny, nx), dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def host_call():
+            _lib.check(lib.hc_fill_d8_accum_host(ctx, hz.data_ptr(), hf.data_ptr(), hd.data_ptr(), None, ha.data_ptr(),
+                                                 ny, nx, -9999.0, 30.0, 30.0, hc.SEED_TAUDEM, hc.TABLE_TAUDEM,
+                                                 int(bool(args.flats))), "hc_fill_d8_accum_host")
+        host_call()
+        ksteps = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            host_call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * cells * ksteps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": cells * 4,
+               "d2h_bytes_per_step": cells * 9, "steps": ksteps,
+               "api": "hc_fill_d8_accum_host (pinned host buffers in, filled+dir+acc out)"}
+        # the host path must give the same answer as the resident path
+        assert torch.equal(hf, out[0].cpu()) and torch.equal(hd, out[1].cpu()) and torch.equal(ha, out[3].cpu())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel + per-pass table ---------------------------------------
+    peak, peak_src = peaks()
+    pass_ms = {}
+    for k, (cnt, tot, mx) in prof.items():
+        pass_ms[KERNEL_PASS.get(k, "other")] = pass_ms.get(KERNEL_PASS.get(k, "other"), 0.0) + tot / args.steps
+    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
+    roof = None
+    if dom:
+        name, (cnt, tot, mx) = dom
+        pname = KERNEL_PASS.get(name, "other")
+        avg_ms = tot / cnt
+        alg_bytes = BYTES_PER_CELL.get(pname, 0) * cells
+        if pname == "flats":
+            alg_bytes = BYTES_PER_CELL["d8"] * cells  # flat resolution is part of producing the D8 raster
+        ach = alg_bytes / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "pass": pname, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "launches_per_step": cnt / args.steps,
+                "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "step_share": tot / args.steps / (ms_max / args.steps)}
+    kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t_ / args.steps} for k, (c, t_, m) in
+               sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    passes = {p: {"ms_per_step": v,
+                  "hbm_frac_algorithmic": (BYTES_PER_CELL.get(p, 0) * cells / (v * 1e-3) / 1e9 / peak) if v > 0 else None}
+              for p, v in pass_ms.items()}
+
+    cpu = None
+    if world == 1 and args.cpu_sample > 0:
+        s = min(args.cpu_sample, ny)
+        crop = np.ascontiguousarray(z[:s, :s].cpu().numpy())
+        rate, secs = cpu_chain_rate(crop, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "seconds": secs,
+               "sample": f"top-left {s}x{s} crop of the same DEM, same chain, single-thread oracle port "
+                         f"(WBT/TauDEM binaries unavailable); host has {os.cpu_count()} logical cores"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: synthetic {ny}x{nx} float32 DEM with random pits (0.5% cells + 200 bowls, 1 cm "
+                               "quantised), fill + D8 + flat resolution + accumulation, TauDEM semantics "
+                               "(PitRemove/D8FlowDir/AreaD8), one unit per GPU",
+                   "cells_per_gpu": cells, "l2": "inputs (467 MB z + outputs) exceed the 126 MB L2; no explicit flush",
+                   "flats": bool(args.flats), "basins": basins, "boruvka_rounds": rounds,
+                   "algorithmic_bytes_per_cell": 18},
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "hbm_frac_algorithmic_whole_step": 18 * cells / (ms_max / args.steps * 1e-3) / 1e9 / peak,
+        "passes": passes, "kernels": kernels,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -101,6 +101,12 @@ int hc_fill_d8_accum_host(hc_ctx *ctx, const float *z, float *filled, uint8_t *d
 int hc_label_host(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn,
                   int32_t *nlab);
 
+/* Per-kernel timing with CUDA events on the launching stream (what bench.py's roofline line is
+ * computed from).  enable(on=1) starts logging every launch; read() synchronises, writes one line
+ * "kernel_name launches total_ms max_ms" per kernel into buf and clears the log. */
+int hc_profile_enable(hc_ctx *ctx, int on, int max_records);
+int hc_profile_read(hc_ctx *ctx, char *buf, int64_t buflen);
+
 /* Diagnostics of the last fill on this context: basins found, Boruvka rounds run. */
 int hc_fill_stats(const hc_ctx *ctx, int64_t *n_basins, int32_t *n_rounds);
 

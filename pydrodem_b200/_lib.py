@@ -36,6 +36,8 @@ SIGNATURES = {
     "hc_fill_d8_accum_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64,
                                              c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "hc_label_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32)]),
+    "hc_profile_enable": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
+    "hc_profile_read": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "hc_fill_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i32)]),
 }
 
@@ -92,3 +94,18 @@ def context(device=0):
 
 def launch_count(device=0):
     return int(load().hc_launch_count(context(device)))
+
+
+def profile_enable(on=True, device=0, max_records=16384):
+    check(load().hc_profile_enable(context(device), int(bool(on)), int(max_records)), "hc_profile_enable")
+
+
+def profile_read(device=0):
+    """{kernel_name: (launches, total_ms, max_ms)} since the last read; synchronises the device."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(load().hc_profile_read(context(device), buf, len(buf)), "hc_profile_read")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, tot, mx = line.split()
+        out[name] = (int(cnt), float(tot), float(mx))
+    return out

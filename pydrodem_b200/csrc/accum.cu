@@ -103,16 +103,21 @@ int accum_run(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_
   dim3 tg((unsigned)((nx + 63) / 64), (unsigned)((ny + 31) / 32));
   unsigned wb = (unsigned)((n + 255) / 256);
   if (table == HC_TABLE_WBT) {
+    HC_PROF(ctx, st, "k_acc_init");
     k_acc_init<HC_TABLE_WBT><<<tg, 256, 0, st>>>(dir, state, (int)ny, (int)nx);
     HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_acc_walk");
     k_acc_walk<HC_TABLE_WBT><<<wb, 256, 0, st>>>(state, (int)ny, (int)nx);
     HC_LAUNCH_CHECK(ctx);
   } else {
+    HC_PROF(ctx, st, "k_acc_init");
     k_acc_init<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(dir, state, (int)ny, (int)nx);
     HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_acc_walk");
     k_acc_walk<HC_TABLE_TAUDEM><<<wb, 256, 0, st>>>(state, (int)ny, (int)nx);
     HC_LAUNCH_CHECK(ctx);
   }
+  HC_PROF(ctx, st, "k_acc_out");
   k_acc_out<<<ctx->sm_count * 8, 256, 0, st>>>(state, acc, n);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;

@@ -63,6 +63,65 @@ void *arena_take(hc_ctx *ctx, size_t bytes) {
   return p;
 }
 
+// ---- per-kernel event timing --------------------------------------------------------------------
+void prof_begin(hc_ctx *ctx, cudaStream_t st, const char *name) {
+  if (ctx->prof_n >= ctx->prof_cap) return;  // pool exhausted: stop recording, keep running
+  int i = ctx->prof_n;
+  ctx->prof_name[i] = name;
+  ctx->prof_stream = st;
+  cudaEventRecord(ctx->prof_ev[2 * i], st);
+  ctx->prof_open = 1;
+}
+void prof_end(hc_ctx *ctx) {
+  cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], ctx->prof_stream);
+  ctx->prof_n++;
+  ctx->prof_open = 0;
+}
+
+extern "C" int hc_profile_enable(hc_ctx *ctx, int on, int max_records) {
+  if (!ctx) return HC_ERR_ARG;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (on && !ctx->prof_ev) {
+    int cap = max_records > 0 ? max_records : 8192;
+    ctx->prof_ev = (cudaEvent_t *)calloc((size_t)cap * 2, sizeof(cudaEvent_t));
+    ctx->prof_name = (const char **)calloc((size_t)cap, sizeof(char *));
+    if (!ctx->prof_ev || !ctx->prof_name) return HC_ERR_NOMEM;
+    for (int i = 0; i < cap * 2; i++) HC_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+    ctx->prof_cap = cap;
+  }
+  ctx->prof_on = on ? 1 : 0;
+  ctx->prof_n = 0;
+  ctx->prof_open = 0;
+  return HC_OK;
+}
+
+// Writes "name count total_ms max_ms\n" per kernel name into buf (NUL terminated); resets the log.
+extern "C" int hc_profile_read(hc_ctx *ctx, char *buf, int64_t buflen) {
+  if (!ctx || !buf || buflen < 2) return HC_ERR_ARG;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HC_CUDA(cudaDeviceSynchronize());
+  struct agg { const char *name; int64_t cnt; double tot, mx; };
+  agg a[128];
+  int na = 0;
+  for (int i = 0; i < ctx->prof_n; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+    int j = 0;
+    for (; j < na; j++) if (a[j].name == ctx->prof_name[i] || !strcmp(a[j].name, ctx->prof_name[i])) break;
+    if (j == na) { if (na == 128) continue; a[na].name = ctx->prof_name[i]; a[na].cnt = 0; a[na].tot = 0; a[na].mx = 0; na++; }
+    a[j].cnt++; a[j].tot += ms; if (ms > a[j].mx) a[j].mx = ms;
+  }
+  int64_t off = 0;
+  buf[0] = 0;
+  for (int j = 0; j < na; j++) {
+    int w = snprintf(buf + off, (size_t)(buflen - off), "%s %lld %.6f %.6f\n", a[j].name, (long long)a[j].cnt, a[j].tot, a[j].mx);
+    if (w < 0 || off + w >= buflen) break;
+    off += w;
+  }
+  ctx->prof_n = 0;
+  return HC_OK;
+}
+
 // ---- context ----------------------------------------------------------------------------------
 extern "C" int hc_create(hc_ctx **out, int device) {
   if (!out) { hc_set_error("hc_create: null out"); return HC_ERR_ARG; }
@@ -92,6 +151,7 @@ extern "C" int hc_destroy(hc_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < ctx->n_blocks; i++) cudaFree(ctx->blocks[i].p);
+  for (int i = 0; i < 5; i++) if (ctx->io[i]) cudaFree(ctx->io[i]);
   if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
   free(ctx);
   return HC_OK;
@@ -182,14 +242,21 @@ extern "C" int hc_label_dev(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int6
 }
 
 // ---- host entry points --------------------------------------------------------------------------
+static int io_get(hc_ctx *ctx, int slot, size_t bytes, void **out) {
+  if (ctx->io_cap[slot] < bytes) {
+    if (ctx->io[slot]) { HC_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->io[slot]); ctx->io[slot] = nullptr; ctx->io_cap[slot] = 0; }
+    cudaError_t e = cudaMalloc(&ctx->io[slot], bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); hc_set_error("cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e)); return HC_ERR_NOMEM; }
+    ctx->io_cap[slot] = bytes;
+  }
+  *out = ctx->io[slot];
+  return HC_OK;
+}
 struct dev_buf {
   void *p = nullptr;
-  ~dev_buf() { if (p) cudaFree(p); }
-  int alloc(size_t b) {
-    cudaError_t e = cudaMalloc(&p, b ? b : 1);
-    if (e != cudaSuccess) { cudaGetLastError(); hc_set_error("cudaMalloc(%zu) -> %s", b, cudaGetErrorString(e)); p = nullptr; return HC_ERR_NOMEM; }
-    return HC_OK;
-  }
+  hc_ctx *ctx; int slot;
+  dev_buf(hc_ctx *c, int s) : ctx(c), slot(s) {}
+  int alloc(size_t b) { return io_get(ctx, slot, b ? b : 1, &p); }
 };
 
 extern "C" int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
@@ -199,7 +266,7 @@ extern "C" int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny,
   size_t n = (size_t)ny * nx;
   if (!n) return HC_OK;
   if (!z || !out) { hc_set_error("hc_fill_host: null pointer"); return HC_ERR_ARG; }
-  dev_buf dz, dout;
+  dev_buf dz(ctx, 0), dout(ctx, 1);
   HC_TRY(dz.alloc(n * 4));
   HC_TRY(dout.alloc(n * 4));
   HC_CUDA(cudaMemcpyAsync(dz.p, z, n * 4, cudaMemcpyHostToDevice, 0));
@@ -217,7 +284,7 @@ extern "C" int hc_fill_d8_accum_host(hc_ctx *ctx, const float *z, float *filled,
   size_t n = (size_t)ny * nx;
   if (!n) return HC_OK;
   if (!z || !filled || !dir || !acc) { hc_set_error("hc_fill_d8_accum_host: null pointer"); return HC_ERR_ARG; }
-  dev_buf dz, df, dd, ds, da;
+  dev_buf dz(ctx, 0), df(ctx, 1), dd(ctx, 2), ds(ctx, 3), da(ctx, 4);
   HC_TRY(dz.alloc(n * 4));
   HC_TRY(df.alloc(n * 4));
   HC_TRY(dd.alloc(n));
@@ -242,7 +309,7 @@ extern "C" int hc_label_host(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int
   if (nlab) *nlab = 0;
   if (!n) return HC_OK;
   if (!mask || !lab) { hc_set_error("hc_label_host: null pointer"); return HC_ERR_ARG; }
-  dev_buf dm, dl;
+  dev_buf dm(ctx, 2), dl(ctx, 4);
   HC_TRY(dm.alloc(n));
   HC_TRY(dl.alloc(n * 4));
   HC_CUDA(cudaMemcpyAsync(dm.p, mask, n, cudaMemcpyHostToDevice, 0));

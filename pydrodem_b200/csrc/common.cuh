@@ -33,9 +33,17 @@ void hc_set_error(const char *fmt, ...);
     if (r__ != HC_OK) return r__; \
   } while (0)
 
+// optional per-kernel timing: HC_PROF(ctx, st, "name") before a launch, the matching
+// HC_LAUNCH_CHECK records the closing event (see prof_begin / prof_end in api.cu)
+#define HC_PROF(ctx, st, name)                              \
+  do {                                                      \
+    if ((ctx)->prof_on) prof_begin((ctx), (st), (name));    \
+  } while (0)
+
 #define HC_LAUNCH_CHECK(ctx)                                                            \
   do {                                                                                  \
     (ctx)->launches++;                                                                  \
+    if ((ctx)->prof_open) prof_end(ctx);                                                \
     cudaError_t e__ = cudaGetLastError();                                               \
     if (e__ != cudaSuccess) {                                                           \
       hc_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__));  \
@@ -60,7 +68,19 @@ struct hc_ctx {
   // stats of the last fill
   int64_t fill_basins;
   int32_t fill_rounds;
+  // grow-only device staging buffers of the *_host entry points (z, filled, dir, slope, acc)
+  void *io[5];
+  size_t io_cap[5];
+  // per-kernel event timing (off by default)
+  int prof_on, prof_open;
+  int prof_n, prof_cap;
+  cudaEvent_t *prof_ev;      // 2 per record
+  const char **prof_name;
+  cudaStream_t prof_stream;
 };
+
+void prof_begin(hc_ctx *ctx, cudaStream_t st, const char *name);
+void prof_end(hc_ctx *ctx);
 
 int arena_reset(hc_ctx *ctx);
 void *arena_take(hc_ctx *ctx, size_t bytes);  // 256-B aligned; nullptr (+error set) on failure

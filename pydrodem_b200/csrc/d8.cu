@@ -90,11 +90,11 @@ int d8_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, 
   }
   dim3 grid((unsigned)((nx + D8_TC - 1) / D8_TC), (unsigned)((ny + D8_TR - 1) / D8_TR));
   if (table == HC_TABLE_WBT) {
-    if (slope) k_d8<HC_TABLE_WBT, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm);
-    else k_d8<HC_TABLE_WBT, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm);
+    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }
+    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }
   } else {
-    if (slope) k_d8<HC_TABLE_TAUDEM, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm);
-    else k_d8<HC_TABLE_TAUDEM, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm);
+    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }
+    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }
   }
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;

@@ -366,11 +366,14 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
 
   HC_CUDA(cudaMemsetAsync(cnt, 0, 256, st));
   dim3 tg(tx, ty);
+  HC_PROF(ctx, st, "k_ptr");
   k_ptr<<<tg, NTHREADS, 0, st>>>(z, ext, P, (int)ny, (int)nx, nodata, cnt);
   HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_perim");
   k_perim<<<tg, 256, 0, st>>>(P, (int)ny, (int)nx);
   HC_LAUNCH_CHECK(ctx);
   int gblocks = ctx->sm_count * 8;
+  HC_PROF(ctx, st, "k_flatten");
   k_flatten<<<gblocks, 256, 0, st>>>(P, n);
   HC_LAUNCH_CHECK(ctx);
 
@@ -392,6 +395,7 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
 
   const int tb = 256;
   const int tgK = (int)((K1 + tb - 1) / tb);
+  HC_PROF(ctx, st, "k_tab_init");
   k_tab_init<<<tgK, tb, 0, st>>>(rep, lvl, hp, K1);
   HC_LAUNCH_CHECK(ctx);
 
@@ -401,19 +405,24 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
   while (active > 0) {
     if (round > 64) { hc_set_error("fill: Boruvka did not converge"); return HC_ERR_INTERNAL; }
     HC_CUDA(cudaMemsetAsync(best, 0xFF, (size_t)K1 * 8, st));
+    HC_PROF(ctx, st, "k_minedge");
     k_minedge<<<tg, NTHREADS, 0, st>>>(z, P, rep, best, act_in, act_out, (int)ny, (int)nx, nodata);
     HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_hook");
     k_hook<<<tgK, tb, 0, st>>>(rep, best, ptr2, lvl, K1);
     HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_mutual");
     k_mutual<<<tgK, tb, 0, st>>>(rep, ptr2, ptr, K1);
     HC_LAUNCH_CHECK(ctx);
     // pointer doubling to the roots: 4 doublings per read-back
     for (int it = 0; it < 16; it++) {
       for (int j = 0; j < 3; j++) {
+        HC_PROF(ctx, st, "k_jump");
         k_jump<<<tgK, tb, 0, st>>>(ptr, K1, cnt + 3);
         HC_LAUNCH_CHECK(ctx);
       }
       HC_CUDA(cudaMemsetAsync(cnt + 1, 0, 4, st));
+      HC_PROF(ctx, st, "k_jump");
       k_jump<<<tgK, tb, 0, st>>>(ptr, K1, cnt + 1);
       HC_LAUNCH_CHECK(ctx);
       HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 1, 4, cudaMemcpyDeviceToHost, st));
@@ -421,8 +430,10 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
       if (!ctx->h_mail[0]) break;
     }
     HC_CUDA(cudaMemsetAsync(cnt + 2, 0, 4, st));
+    HC_PROF(ctx, st, "k_merge");
     k_merge<<<tgK, tb, 0, st>>>(rep, hp, ptr, K1, cnt + 2);
     HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_repflat");
     k_repflat<<<tgK, tb, 0, st>>>(rep, K1);
     HC_LAUNCH_CHECK(ctx);
     HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 2, 4, cudaMemcpyDeviceToHost, st));
@@ -434,8 +445,10 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
   }
   ctx->fill_rounds = round;
 
+  HC_PROF(ctx, st, "k_levels");
   k_levels<<<tgK, tb, 0, st>>>(hp, lvl, level0, K1);
   HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_apply");
   k_apply<<<gblocks, 256, 0, st>>>(z, P, level0, out, n);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;

@@ -236,6 +236,7 @@ int flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx,
     attr_set = true;
   }
   dim3 tg(tx, ty);
+  HC_PROF(ctx, st, "k_flat_init");
   k_flat_init<<<tg, NTHREADS, 0, st>>>(z, dir, nf, dlo, dhi, tile_has, (int)ny, (int)nx, nodata);
   HC_LAUNCH_CHECK(ctx);
   HC_CUDA(cudaMemsetAsync(dA, 1, tiles, st));
@@ -244,6 +245,7 @@ int flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx,
     if (it > 100000) { hc_set_error("flats: relaxation did not converge"); return HC_ERR_INTERNAL; }
     HC_CUDA(cudaMemsetAsync(dout, 0, tiles, st));
     HC_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+    HC_PROF(ctx, st, "k_flat_relax");
     k_flat_relax<<<tg, NTHREADS, FLAT_SMEM, st>>>(z, nf, dlo, dhi, tile_has, din, dout, flag, (int)ny, (int)nx, nodata);
     HC_LAUNCH_CHECK(ctx);
     HC_CUDA(cudaMemcpyAsync(ctx->h_mail, flag, 4, cudaMemcpyDeviceToHost, st));
@@ -251,6 +253,7 @@ int flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx,
     if (!ctx->h_mail[0]) break;
     uint8_t *t = din; din = dout; dout = t;
   }
+  HC_PROF(ctx, st, "k_flat_dirs");
   if (table == HC_TABLE_WBT)
     k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(z, nf, dlo, dhi, dir, tile_has, (int)ny, (int)nx, nodata);
   else

@@ -148,10 +148,13 @@ size_t label_workspace(int64_t ny, int64_t nx) {
 static int label_roots(hc_ctx *ctx, const uint8_t *mask, u32 *L, int64_t ny, int64_t nx, int conn, cudaStream_t st) {
   size_t n = (size_t)ny * nx;
   unsigned nb = (unsigned)((n + 255) / 256);
+  HC_PROF(ctx, st, "k_lab_init");
   k_lab_init<<<ctx->sm_count * 8, 256, 0, st>>>(mask, L, n);
   HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_lab_merge");
   k_lab_merge<<<nb, 256, 0, st>>>(mask, L, (int)ny, (int)nx, conn == 8);
   HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_lab_compress");
   k_lab_compress<<<nb, 256, 0, st>>>(L, n);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
@@ -172,12 +175,16 @@ int label_run(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_
   u32 *total = (u32 *)arena_take(ctx, 256);
   if (!L || !R || !bsum || !total) return HC_ERR_NOMEM;
   HC_TRY(label_roots(ctx, mask, L, ny, nx, conn, st));
+  HC_PROF(ctx, st, "k_root_count");
   k_root_count<<<nchunks, 256, 0, st>>>(L, bsum, n);
   HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_scan_blocks");
   k_scan_blocks<<<1, 1024, 0, st>>>(bsum, nchunks, total);
   HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_root_rank");
   k_root_rank<<<nchunks, 256, 0, st>>>(L, bsum, R, n);
   HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_lab_out");
   k_lab_out<<<ctx->sm_count * 8, 256, 0, st>>>(L, R, lab, n);
   HC_LAUNCH_CHECK(ctx);
   HC_CUDA(cudaMemcpyAsync(ctx->h_mail, total, 4, cudaMemcpyDeviceToHost, st));
@@ -237,6 +244,7 @@ int ext_nodata_mask(hc_ctx *ctx, const float *z, uint8_t *ext, int64_t ny, int64
   u32 *flagw = (u32 *)arena_take(ctx, 256);
   if (!flagw) return HC_ERR_NOMEM;
   HC_CUDA(cudaMemsetAsync(flagw, 0, 4, st));
+  HC_PROF(ctx, st, "k_nodata_mask");
   k_nodata_mask<<<ctx->sm_count * 8, 256, 0, st>>>(z, ext, (int)ny, (int)nx, nodata, flagw);
   HC_LAUNCH_CHECK(ctx);
   HC_CUDA(cudaMemcpyAsync(ctx->h_mail, flagw, 4, cudaMemcpyDeviceToHost, st));
@@ -249,8 +257,10 @@ int ext_nodata_mask(hc_ctx *ctx, const float *z, uint8_t *ext, int64_t ny, int64
   HC_TRY(label_roots(ctx, ext, L, ny, nx, 8, st));
   HC_CUDA(cudaMemsetAsync(flag, 0, n, st));
   int nbord = (int)(2 * nx + 2 * ny);
+  HC_PROF(ctx, st, "k_ext_flag_border");
   k_ext_flag_border<<<(nbord + 255) / 256, 256, 0, st>>>(L, flag, (int)ny, (int)nx);
   HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_ext_out");
   k_ext_out<<<ctx->sm_count * 8, 256, 0, st>>>(L, flag, ext, n);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
