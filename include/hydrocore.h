@@ -106,6 +106,8 @@ int hc_label_host(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, in
  * "kernel_name launches total_ms max_ms" per kernel into buf and clears the log. */
 int hc_profile_enable(hc_ctx *ctx, int on, int max_records);
 int hc_profile_read(hc_ctx *ctx, char *buf, int64_t buflen);
+/* 16 internal work counters (sweeps, tile visits ...) since the last read; diagnostics only. */
+int hc_debug_read(hc_ctx *ctx, unsigned long long *out16);
 
 /* Diagnostics of the last fill on this context: basins found, Boruvka rounds run. */
 int hc_fill_stats(const hc_ctx *ctx, int64_t *n_basins, int32_t *n_rounds);

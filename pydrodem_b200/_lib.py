@@ -38,6 +38,7 @@ SIGNATURES = {
     "hc_label_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32)]),
     "hc_profile_enable": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "hc_profile_read": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
+    "hc_debug_read": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "hc_fill_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i32)]),
 }
 
@@ -109,3 +110,9 @@ def profile_read(device=0):
         name, cnt, tot, mx = line.split()
         out[name] = (int(cnt), float(tot), float(mx))
     return out
+
+
+def debug_read(device=0):
+    out = (ctypes.c_uint64 * 16)()
+    check(load().hc_debug_read(context(device), out), "hc_debug_read")
+    return list(out)

@@ -15,6 +15,15 @@ void hc_set_error(const char *fmt, ...) {
 extern "C" const char *hc_last_error(void) { return g_err; }
 extern "C" int hc_version(void) { return 100; }
 
+extern "C" int hc_debug_read(hc_ctx *ctx, unsigned long long *out16) {
+  if (!ctx || !out16) return HC_ERR_ARG;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HC_CUDA(cudaDeviceSynchronize());
+  HC_CUDA(cudaMemcpy(out16, ctx->d_dbg, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
+  HC_CUDA(cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 16));
+  return HC_OK;
+}
+
 // ---- arena ------------------------------------------------------------------------------------
 int arena_reset(hc_ctx *ctx) {
   if (ctx->n_blocks > 1) {
@@ -142,6 +151,8 @@ extern "C" int hc_create(hc_ctx **out, int device) {
   HC_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
   HC_CUDA(cudaMallocHost(&ctx->h_mail, 256));
+  HC_CUDA(cudaMalloc(&ctx->d_dbg, 16 * sizeof(unsigned long long)));
+  HC_CUDA(cudaMemset(ctx->d_dbg, 0, 16 * sizeof(unsigned long long)));
   *out = ctx;
   return HC_OK;
 }
@@ -227,8 +238,8 @@ extern "C" int hc_fill_d8_accum_dev(hc_ctx *ctx, const float *z, float *filled, 
   if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("bad seed_mode"); return HC_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   HC_TRY(fill_run(ctx, z, filled, ny, nx, nodata, seed_mode, st));
-  HC_TRY(d8_run(ctx, filled, dir, slope, ny, nx, nodata, dx, dy, table, st));
-  if (resolve_flats) HC_TRY(flats_run(ctx, filled, dir, ny, nx, nodata, table, st));
+  if (resolve_flats) HC_TRY(d8_flats_run(ctx, filled, dir, slope, ny, nx, nodata, dx, dy, table, st));
+  else HC_TRY(d8_run(ctx, filled, dir, slope, ny, nx, nodata, dx, dy, table, st));
   HC_TRY(accum_run(ctx, dir, acc, ny, nx, table, st));
   return HC_OK;
 }

@@ -71,6 +71,7 @@ struct hc_ctx {
   // grow-only device staging buffers of the *_host entry points (z, filled, dir, slope, acc)
   void *io[5];
   size_t io_cap[5];
+  unsigned long long *d_dbg;  // 16 device work counters
   // per-kernel event timing (off by default)
   int prof_on, prof_open;
   int prof_n, prof_cap;
@@ -98,6 +99,9 @@ __device__ __forceinline__ float d_funord(u32 u) {
   return __uint_as_float(b);
 }
 
+// debug counters (cheap; read and reset with hc_debug_read)
+#define HC_DBG(i, v) atomicAdd(&dbg[(i)], (unsigned long long)(v))
+
 // neighbour tables, in each tool's own search order (see oracle/hydro_oracle.c)
 __constant__ const int c_dr[2][8] = {{-1, 0, 1, 1, 1, 0, -1, -1}, {0, -1, -1, -1, 0, 1, 1, 1}};
 __constant__ const int c_dc[2][8] = {{1, 1, 1, 0, -1, -1, -1, 0}, {1, 1, 0, -1, -1, -1, 0, 1}};
@@ -121,6 +125,8 @@ int d8_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, 
 int flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx, float nodata, int table,
               cudaStream_t st);
 size_t flats_workspace(int64_t ny, int64_t nx);
+int d8_flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx, float nodata,
+                 double dx, double dy, int table, cudaStream_t st);
 int accum_run(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_t nx, int table,
               cudaStream_t st);
 size_t accum_workspace(int64_t ny, int64_t nx);

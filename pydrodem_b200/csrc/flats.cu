@@ -8,27 +8,218 @@
 // Parallel form used here.  Both BFS fields are geodesic (8-connected, unit-step) distances
 // through the NOFLOW cells of one elevation, i.e. the unique fixed point of
 //      d(c) = 1 + min over same-flat neighbours d(n),  sources fixed at 1,
-// so they are computed by chaotic relaxation: each 64x64 tile iterates to its local fixed point in
-// shared memory, tiles whose halo changed are re-queued, until nothing changes.  No flat labels
-// are needed: two 8-adjacent cells of equal elevation are always in the same flat, FlatHeight is
-// a per-flat constant that cancels in every comparison the masked D8 makes, and a flat without a
-// low edge is exactly one whose cells the "towards lower" field never reaches.
+// so they can be computed by chaotic relaxation.  No flat labels are needed: two 8-adjacent cells
+// of equal elevation are always in the same flat, FlatHeight is a per-flat constant that cancels
+// in every comparison the masked D8 makes, and a flat without a low edge is exactly one whose
+// cells the "towards lower" field never reaches.
+//
+// Two tiers:
+//   fast  k_flat_fast: one CTA per 64x64 tile loads the tile plus an 8-cell apron (80x80) into
+//         shared memory, classifies, relaxes to the fixed point over a compact list of the NOFLOW
+//         cells and writes final directions for every flat that lies completely inside the apron
+//         (on a filled DEM that is nearly all of them: each filled pit is a flat a few cells
+//         wide).  One read of z and dir, one write of dir.
+//   slow  flats that reach the apron's rim are marked pending (code 254) and solved by tile
+//         relaxation against global distance arrays with re-queueing of tiles whose halo changed
+//         (k_flat_init / k_flat_relax / k_flat_dirs), run only on the tiles that hold pending
+//         cells and their neighbours.
 #include "common.cuh"
 
 #define T HC_TILE
 #define TH (T + 2)
 #define NTHREADS 256
+#define HC_DIR_PENDING 254
 
-// ---- classify ---------------------------------------------------------------------------------
+// ================================================================================================
+// fast tier
+// ================================================================================================
+#define FH 8                 // apron
+#define FR (T + 2 * FH)      // region edge (80)
+#define F_NF 0x4000u         // flags live in the top bits of the 16-bit "lo" word
+#define F_OPEN 0x8000u
+#define F_LO 0x3FFFu
+#define FLCAP 1536           // NOFLOW cells a tile may hold before it is left to the slow tier
+#define FSWEEPS 40           // sweep cap: a flat that fits the apron converges well inside it
+#define FAST_SMEM (FR * FR * (4 + 2 + 2) + FLCAP * 2 + 16)
+
+template <int TABLE>
+__global__ void __launch_bounds__(NTHREADS)
+k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB,
+            uint8_t *__restrict__ tile_pending, int ny, int nx, float nodata, unsigned long long *dbg) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float *sz = (float *)smem;
+  unsigned short *slo = (unsigned short *)(smem + FR * FR * 4);  // [OPEN | NF | lo:14]
+  unsigned short *shi = (unsigned short *)(smem + FR * FR * 6);
+  unsigned short *list = (unsigned short *)(smem + FR * FR * 8);
+  u32 *s_n = (u32 *)(smem + FR * FR * 8 + FLCAP * 2);
+
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.y * T - FH, c0 = blockIdx.x * T - FH;
+  const float qnan = __int_as_float(0x7fc00000);
+  if (tid == 0) s_n[0] = 0;
+  __syncthreads();
+  // 1. load: elevation (NaN = not a cell), NOFLOW flag; non-rim NOFLOW cells go on the work list
+#pragma unroll 5
+  for (int i = tid; i < FR * FR; i += NTHREADS) {
+    int lr = i / FR, lc = i - lr * FR;
+    int r = r0 + lr, c = c0 + lc;
+    float v = qnan;
+    u32 w = 0;
+    if (r >= 0 && r < ny && c >= 0 && c < nx) {
+      size_t g = (size_t)r * nx + c;
+      v = __ldg(&z[g]);
+      if (v == nodata) v = qnan;
+      if (v == v && __ldg(&dirA[g]) == HC_DIR_NOFLOW) {
+        // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
+        // (conservatively also when the rim coincides with the raster border)
+        if (lr == 0 || lc == 0 || lr == FR - 1 || lc == FR - 1) w = F_NF | F_OPEN;
+        else {
+          w = F_NF;
+          u32 k = atomicAdd(&s_n[0], 1u);
+          if (k < FLCAP) list[k] = (unsigned short)i;
+        }
+      }
+    }
+    sz[i] = v;
+    slo[i] = (unsigned short)w;
+    shi[i] = 0;
+  }
+  __syncthreads();
+  const u32 nlist = s_n[0];
+  bool giveup = nlist > FLCAP;
+  if (!giveup && nlist) {
+    // 2. edges: a NOFLOW cell next to higher ground is a high edge (hi = 1); a cell WITH a
+    //    direction next to an equal NOFLOW cell is a low edge (lo = 1).  All writers store 1.
+    for (u32 k = tid; k < nlist; k += NTHREADS) {
+      int ci = list[k];
+      float v = sz[ci];
+      u32 hi = 0;
+#pragma unroll
+      for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+        for (int dc = -1; dc <= 1; dc++) {
+          if (!dr && !dc) continue;
+          int ni = ci + dr * FR + dc;
+          float zn = sz[ni];
+          if (zn > v) hi = 1;
+          else if (zn == v && !(slo[ni] & F_NF)) slo[ni] = 1;
+        }
+      shi[ci] = (unsigned short)hi;
+    }
+    __syncthreads();
+    // 3. relax the two distance fields and the "open" flag to their fixed point
+    int sweeps = 0;
+    for (;;) {
+      int changed = 0;
+      for (u32 k = tid; k < nlist; k += NTHREADS) {
+        int ci = list[k];
+        u32 w = slo[ci];
+        float v = sz[ci];
+        u32 lo = w & F_LO, hi = shi[ci];
+        u32 blo = lo ? lo : 0xFFFFu, bhi = hi ? hi : 0xFFFFu;
+        u32 open = w & F_OPEN;
+#pragma unroll
+        for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+          for (int dc = -1; dc <= 1; dc++) {
+            if (!dr && !dc) continue;
+            int ni = ci + dr * FR + dc;
+            if (sz[ni] != v) continue;
+            u32 nw = slo[ni];
+            u32 nlo = nw & F_LO;
+            if (nlo && nlo + 1 < blo) blo = nlo + 1;
+            if (nw & F_NF) {
+              u32 nhi = shi[ni];
+              if (nhi && nhi + 1 < bhi) bhi = nhi + 1;
+              open |= nw & F_OPEN;
+            }
+          }
+        if (blo == 0xFFFFu) blo = 0;
+        if (bhi == 0xFFFFu) bhi = 0;
+        u32 nw2 = F_NF | open | blo;
+        if (nw2 != w) { slo[ci] = (unsigned short)nw2; changed = 1; }
+        if (bhi != hi) { shi[ci] = (unsigned short)bhi; changed = 1; }
+      }
+      sweeps++;
+      if (!__syncthreads_or(changed)) break;
+      if (sweeps >= FSWEEPS) { giveup = true; break; }
+    }
+    if (tid == 0) { HC_DBG(0, sweeps); HC_DBG(1, 1); }
+  }
+  // 4. write the tile: copy dirA, resolve closed flats, mark open ones pending
+  int pend = 0;
+  for (int i = tid; i < T * T; i += NTHREADS) {
+    int lr = i / T, lc = i - lr * T;
+    int r = r0 + FH + lr, c = c0 + FH + lc;
+    if (r >= ny || c >= nx) continue;
+    int ci = (lr + FH) * FR + lc + FH;
+    size_t g = (size_t)r * nx + c;
+    u32 w = slo[ci];
+    uint8_t d;
+    if (w & F_NF) {
+      d = HC_DIR_NOFLOW;
+      if (giveup || (w & F_OPEN)) { d = HC_DIR_PENDING; pend = 1; }
+      else if (w & F_LO) {
+        float v = sz[ci];
+        int own = 2 * (int)(w & F_LO) - (int)shi[ci];
+        int mn = own, best = -1;
+        bool bdiag = false;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          int ni = ci + c_dr[TABLE][k] * FR + c_dc[TABLE][k];
+          if (sz[ni] != v) continue;
+          u32 nw = slo[ni];
+          int key;
+          if (nw & F_NF) {
+            if (!(nw & F_LO)) continue;
+            key = 2 * (int)(nw & F_LO) - (int)shi[ni];
+          } else {
+            key = -0x40000000;
+          }
+          bool kdiag = (c_dr[TABLE][k] != 0) && (c_dc[TABLE][k] != 0);
+          if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = k; bdiag = kdiag; }
+        }
+        if (best >= 0) d = (uint8_t)c_code[TABLE][best];
+      }
+    } else {
+      d = __ldg(&dirA[g]);
+    }
+    dirB[g] = d;
+  }
+  pend = __syncthreads_or(pend);
+  if (tid == 0 && pend) HC_DBG(2, 1);  // pending tiles
+  if (tid == 0) tile_pending[blockIdx.y * gridDim.x + blockIdx.x] = (uint8_t)(pend ? 1 : 0);
+}
+
+// active = pending tiles and their 8 neighbours; also counts pending tiles
+__global__ void k_flat_dilate(const uint8_t *__restrict__ pending, uint8_t *__restrict__ active, int tx, int ty,
+                              u32 *__restrict__ n_pending) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= tx * ty) return;
+  int y = t / tx, x = t - y * tx;
+  int a = 0;
+  for (int dy = -1; dy <= 1; dy++)
+    for (int dx = -1; dx <= 1; dx++) {
+      int yy = y + dy, xx = x + dx;
+      if (yy >= 0 && yy < ty && xx >= 0 && xx < tx) a |= pending[yy * tx + xx];
+    }
+  active[t] = (uint8_t)a;
+  if (pending[t]) atomicAdd(n_pending, 1u);
+}
+
+// ================================================================================================
+// slow tier (general: any flat size), restricted to `active` tiles
+// ================================================================================================
 // nf[c]  = 1 if c is valid and has no direction (NOFLOW)
 // dlo[c] = 1 for low edges (valid, has a direction, touches an equal-elevation NOFLOW cell)
 // dhi[c] = 1 for high edges (NOFLOW, touches a higher valid cell); 0 = not reached yet
 __global__ void __launch_bounds__(NTHREADS)
-k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, uint8_t *__restrict__ nf,
-            u32 *__restrict__ dlo, u32 *__restrict__ dhi, uint8_t *__restrict__ tile_has, int ny, int nx,
-            float nodata) {
+k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const uint8_t *__restrict__ dirB,
+            uint8_t *__restrict__ nf, u32 *__restrict__ dlo, u32 *__restrict__ dhi,
+            const uint8_t *__restrict__ active, int ny, int nx, float nodata) {
   __shared__ float sz[TH * TH];
   __shared__ uint8_t sd[TH * TH];
+  if (!active[blockIdx.y * gridDim.x + blockIdx.x]) return;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
@@ -47,7 +238,6 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, uint8_
     sd[i] = d;
   }
   __syncthreads();
-  int any = 0;
   for (int i = tid; i < T * T; i += NTHREADS) {
     int lr = i / T, lc = i - lr * T;
     int r = r0 + lr, c = c0 + lc;
@@ -71,182 +261,260 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, uint8_
         }
     }
     size_t g = (size_t)r * nx + c;
+    // every NOFLOW cell of an active tile takes part: a flat can be resolved in one tile (it fits
+    // that tile's apron) and pending in the next, and its distances must still flow through both
     nf[g] = isnf;
     dlo[g] = lo;
     dhi[g] = hi;
-    any |= isnf;
   }
-  any = __syncthreads_or(any);
-  if (tid == 0) tile_has[blockIdx.y * gridDim.x + blockIdx.x] = (uint8_t)(any ? 1 : 0);
 }
 
-// ---- tile relaxation ---------------------------------------------------------------------------
-// dynamic smem: z[TH*TH] f32 | lo[TH*TH] u32 | hi[TH*TH] u32 | nf[TH*TH] u8
-#define FLAT_SMEM (TH * TH * (4 + 4 + 4 + 1))
+// smem: z f32 | lo u32 (bit 31 = NOFLOW flag) | hi u32, pitch TP (odd)
+#define TP (TH + 1)
+#define R_NF 0x80000000u
+#define FLAT_SMEM (TH * TP * 12 + T * T * 2 + 16)
+
+__device__ __forceinline__ int slow_relax(const float *sz, u32 *slo, u32 *shi, int ci) {
+  u32 w = slo[ci];
+  if (!(w & R_NF)) return 0;
+  float v = sz[ci];
+  u32 lo = w & ~R_NF, hi = shi[ci];
+  u32 blo = lo ? lo : 0x7FFFFFFFu, bhi = hi ? hi : 0x7FFFFFFFu;
+#pragma unroll
+  for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+    for (int dc = -1; dc <= 1; dc++) {
+      if (!dr && !dc) continue;
+      int ni = ci + dr * TP + dc;
+      if (sz[ni] != v) continue;
+      u32 nw = slo[ni];
+      u32 nlo = nw & ~R_NF;
+      if (nlo && nlo + 1 < blo) blo = nlo + 1;
+      if (nw & R_NF) {
+        u32 nhi = shi[ni];
+        if (nhi && nhi + 1 < bhi) bhi = nhi + 1;
+      }
+    }
+  int changed = 0;
+  if (blo != 0x7FFFFFFFu && blo != lo) { slo[ci] = R_NF | blo; changed = 1; }
+  if (bhi != 0x7FFFFFFFu && bhi != hi) { shi[ci] = bhi; changed = 1; }
+  return changed;
+}
 
 __global__ void __launch_bounds__(NTHREADS)
 k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
-             const uint8_t *__restrict__ tile_has, const uint8_t *__restrict__ dirty_in,
-             uint8_t *__restrict__ dirty_out, u32 *__restrict__ changed_flag, int ny, int nx, float nodata) {
+             const uint8_t *__restrict__ active, const uint8_t *__restrict__ dirty_in,
+             uint8_t *__restrict__ dirty_out, u32 *__restrict__ changed_flag, int ny, int nx, float nodata,
+             unsigned long long *dbg) {
   extern __shared__ __align__(16) unsigned char smem[];
   float *sz = (float *)smem;
-  u32 *slo = (u32 *)(smem + TH * TH * 4);
-  u32 *shi = (u32 *)(smem + TH * TH * 8);
-  uint8_t *snf = (uint8_t *)(smem + TH * TH * 12);
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (!tile_has[tile] || !dirty_in[tile]) return;
+  u32 *slo = (u32 *)(smem + TH * TP * 4);
+  u32 *shi = (u32 *)(smem + TH * TP * 8);
+  unsigned short *list = (unsigned short *)(smem + TH * TP * 12);
+  __shared__ int s_side;
+  __shared__ u32 s_n;
+  const int tx = gridDim.x, ty = gridDim.y;
+  const int tile = blockIdx.y * tx + blockIdx.x;
+  if (!active[tile] || !dirty_in[tile]) return;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
+  if (tid == 0) { s_side = 0; s_n = 0; }
+  __syncthreads();
   for (int i = tid; i < TH * TH; i += NTHREADS) {
     int lr = i / TH, lc = i - lr * TH;
     int r = r0 + lr - 1, c = c0 + lc - 1;
     float v = qnan;
     u32 lo = 0, hi = 0;
-    uint8_t f = 0;
     if (r >= 0 && r < ny && c >= 0 && c < nx) {
-      size_t g = (size_t)r * nx + c;
-      v = __ldg(&z[g]);
-      if (v == nodata) v = qnan;
-      lo = __ldcg(&dlo[g]);
-      hi = __ldcg(&dhi[g]);
-      f = __ldg(&nf[g]);
+      // halo cells of tiles outside the active set hold no state: treat as not in any flat
+      int ht = (r / T) * tx + (c / T);
+      if (active[ht]) {
+        size_t g = (size_t)r * nx + c;
+        v = __ldg(&z[g]);
+        if (v == nodata) v = qnan;
+        lo = __ldcg(&dlo[g]);
+        hi = __ldcg(&dhi[g]);
+        if (__ldg(&nf[g])) {
+          lo |= R_NF;
+          if (lr >= 1 && lr <= T && lc >= 1 && lc <= T) list[atomicAdd(&s_n, 1u)] = (unsigned short)(lr * TP + lc);
+        }
+      }
     }
-    sz[i] = v; slo[i] = lo; shi[i] = hi; snf[i] = f;
+    sz[lr * TP + lc] = v; slo[lr * TP + lc] = lo; shi[lr * TP + lc] = hi;
   }
   __syncthreads();
-  int ever = 0;
-  for (;;) {
-    int changed = 0;
-    for (int i = tid; i < T * T; i += NTHREADS) {
-      int lr = i / T, lc = i - lr * T;
-      int ci = (lr + 1) * TH + lc + 1;
-      if (!snf[ci]) continue;
-      float v = sz[ci];
-      u32 lo = slo[ci], hi = shi[ci];
-      u32 blo = lo ? lo : 0xFFFFFFFFu, bhi = hi ? hi : 0xFFFFFFFFu;
-#pragma unroll
-      for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-        for (int dc = -1; dc <= 1; dc++) {
-          if (!dr && !dc) continue;
-          int ni = ci + dr * TH + dc;
-          if (sz[ni] != v) continue;
-          u32 nlo = slo[ni];
-          if (nlo && nlo + 1 < blo) blo = nlo + 1;
-          u32 nhi = shi[ni];
-          if (nhi && snf[ni] && nhi + 1 < bhi) bhi = nhi + 1;
-        }
-      if (blo != 0xFFFFFFFFu && blo != lo) { slo[ci] = blo; changed = 1; }
-      if (bhi != 0xFFFFFFFFu && bhi != hi) { shi[ci] = bhi; changed = 1; }
+  const u32 nlist = s_n;
+  if (!nlist) return;
+  int ever = 0, nsweeps = 0;
+  if (nlist * 4 > T * T) {
+    // dense flat (lake): directional Gauss-Seidel sweeps (rows ->, columns v, rows <-, columns ^);
+    // inside a line the distance front crosses the tile in one sweep.  Thread t: line (t % T),
+    // quarter (t / T).
+    const int line = 1 + tid % T, a0 = 1 + (tid / T) * 16, a1 = a0 + 15;
+    int quiet = 0;
+    for (int sweep = 0; quiet < 4; sweep++) {
+      int changed = 0;
+      switch (sweep & 3) {
+        case 0: for (int c = a0; c <= a1; c++) changed |= slow_relax(sz, slo, shi, line * TP + c); break;
+        case 1: for (int r = a0; r <= a1; r++) changed |= slow_relax(sz, slo, shi, r * TP + line); break;
+        case 2: for (int c = a1; c >= a0; c--) changed |= slow_relax(sz, slo, shi, line * TP + c); break;
+        default: for (int r = a1; r >= a0; r--) changed |= slow_relax(sz, slo, shi, r * TP + line); break;
+      }
+      if (__syncthreads_or(changed)) { quiet = 0; ever = 1; } else quiet++;
+      nsweeps++;
     }
-    if (!__syncthreads_or(changed)) break;
-    ever = 1;
+  } else {
+    // sparse: Jacobi over the compact list of pending cells
+    for (;;) {
+      int changed = 0;
+      for (u32 k = tid; k < nlist; k += NTHREADS) changed |= slow_relax(sz, slo, shi, list[k]);
+      nsweeps++;
+      if (!__syncthreads_or(changed)) break;
+      ever = 1;
+    }
   }
+  if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); if (nlist * 4 > T * T) HC_DBG(5, 1); }
   if (!ever) return;
+  // write back and find out which sides of the tile changed on the rim
+  int side = 0;  // bit0 N, bit1 S, bit2 W, bit3 E
   for (int i = tid; i < T * T; i += NTHREADS) {
     int lr = i / T, lc = i - lr * T;
     int r = r0 + lr, c = c0 + lc;
     if (r >= ny || c >= nx) continue;
-    int ci = (lr + 1) * TH + lc + 1;
-    if (!snf[ci]) continue;
+    int ci = (lr + 1) * TP + lc + 1;
+    u32 w = slo[ci];
+    if (!(w & R_NF)) continue;
     size_t g = (size_t)r * nx + c;
-    dlo[g] = slo[ci];
-    dhi[g] = shi[ci];
+    u32 lo = w & ~R_NF, hi = shi[ci];
+    if (lo != dlo[g] || hi != dhi[g]) {
+      dlo[g] = lo;
+      dhi[g] = hi;
+      if (lr == 0) side |= 1;
+      if (lr == T - 1 || r == ny - 1) side |= 2;
+      if (lc == 0) side |= 4;
+      if (lc == T - 1 || c == nx - 1) side |= 8;
+    }
   }
-  if (tid < 9) {
-    int ty = (int)blockIdx.y + tid / 3 - 1, tx = (int)blockIdx.x + tid % 3 - 1;
-    if (ty >= 0 && ty < (int)gridDim.y && tx >= 0 && tx < (int)gridDim.x) dirty_out[ty * gridDim.x + tx] = 1;
+  if (side) atomicOr(&s_side, side);
+  __syncthreads();
+  side = s_side;
+  if (tid < 9 && tid != 4) {
+    int dy = tid / 3 - 1, dx = tid % 3 - 1;
+    bool need = true;
+    if (dy == -1 && !(side & 1)) need = false;
+    if (dy == 1 && !(side & 2)) need = false;
+    if (dx == -1 && !(side & 4)) need = false;
+    if (dx == 1 && !(side & 8)) need = false;
+    int yy = (int)blockIdx.y + dy, xx = (int)blockIdx.x + dx;
+    if (need && yy >= 0 && yy < ty && xx >= 0 && xx < tx && active[yy * tx + xx]) dirty_out[yy * tx + xx] = 1;
   }
-  if (tid == 0) *changed_flag = 1u;
+  if (tid == 0 && side) *changed_flag = 1u;
 }
 
-// ---- masked D8 ---------------------------------------------------------------------------------
+// masked D8 for the pending cells
 template <int TABLE>
 __global__ void __launch_bounds__(256)
 k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ nf, const u32 *__restrict__ dlo,
-            const u32 *__restrict__ dhi, uint8_t *__restrict__ dir, const uint8_t *__restrict__ tile_has,
+            const u32 *__restrict__ dhi, uint8_t *__restrict__ dirB, const uint8_t *__restrict__ pending,
             int ny, int nx, float nodata) {
-  // one block per 64x64 tile, 16 cells per thread; direct (cached) neighbour reads: only the
-  // sparse NOFLOW cells do any work
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (!tile_has[tile]) return;
+  if (!pending[tile]) return;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   for (int i = threadIdx.x; i < T * T; i += 256) {
     int lr = i / T, lc = i - lr * T;
     int r = r0 + lr, c = c0 + lc;
     if (r >= ny || c >= nx) continue;
     size_t g = (size_t)r * nx + c;
-    if (!nf[g]) continue;
+    if (dirB[g] != HC_DIR_PENDING) continue;
+    uint8_t out = HC_DIR_NOFLOW;
     u32 lo = dlo[g];
-    if (!lo) continue;  // flat without an outlet: stays NOFLOW
-    float v = z[g];
-    long long own = 2ll * (long long)lo - (long long)dhi[g];
-    long long mn = own;
-    int best = -1;
-    bool bdiag = false;
+    if (lo) {
+      float v = z[g];
+      long long own = 2ll * (long long)lo - (long long)dhi[g];
+      long long mn = own;
+      int best = -1;
+      bool bdiag = false;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      int rr = r + c_dr[TABLE][k], cc = c + c_dc[TABLE][k];
-      if (rr < 0 || rr >= ny || cc < 0 || cc >= nx) continue;
-      size_t gn = (size_t)rr * nx + cc;
-      float zn = z[gn];
-      if (zn != v) continue;  // also drops nodata / NaN
-      u32 nlo = dlo[gn];
-      long long key;
-      if (nf[gn]) {
-        if (!nlo) continue;   // cannot happen inside a reached flat; keep it safe
-        key = 2ll * (long long)nlo - (long long)dhi[gn];
-      } else {
-        key = -0x4000000000000000ll;  // low edge: below every mask value
+      for (int k = 0; k < 8; k++) {
+        int rr = r + c_dr[TABLE][k], cc = c + c_dc[TABLE][k];
+        if (rr < 0 || rr >= ny || cc < 0 || cc >= nx) continue;
+        size_t gn = (size_t)rr * nx + cc;
+        float zn = z[gn];
+        if (zn != v) continue;  // also drops nodata / NaN
+        long long key;
+        if (nf[gn]) {
+          u32 nlo = dlo[gn];
+          if (!nlo) continue;
+          key = 2ll * (long long)nlo - (long long)dhi[gn];
+        } else {
+          key = -0x4000000000000000ll;  // low edge: below every mask value
+        }
+        bool kdiag = (c_dr[TABLE][k] != 0) && (c_dc[TABLE][k] != 0);
+        if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = k; bdiag = kdiag; }
       }
-      bool kdiag = (c_dr[TABLE][k] != 0) && (c_dc[TABLE][k] != 0);
-      if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = k; bdiag = kdiag; }
+      if (best >= 0) out = (uint8_t)c_code[TABLE][best];
     }
-    if (best >= 0) dir[g] = (uint8_t)c_code[TABLE][best];
+    dirB[g] = out;
   }
 }
 
 size_t flats_workspace(int64_t ny, int64_t nx) {
   size_t n = (size_t)ny * nx;
   size_t tiles = (size_t)((ny + T - 1) / T) * ((nx + T - 1) / T);
-  return hc_align(n) + 2 * hc_align(n * 4) + 3 * hc_align(tiles) + hc_align(256);
+  return 2 * hc_align(n) + 2 * hc_align(n * 4) + 4 * hc_align(tiles) + hc_align(256);
 }
 
-int flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx, float nodata, int table,
-              cudaStream_t st) {
-  if (ny <= 0 || nx <= 0) return HC_OK;
-  if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("flats: bad table %d", table); return HC_ERR_ARG; }
+// dirA: D8 codes with NOFLOW on flats (read only); dirB: output (may not alias dirA).
+int flats_core(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx,
+               float nodata, int table, cudaStream_t st) {
   size_t n = (size_t)ny * nx;
   const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t tiles = (size_t)tx * ty;
-  HC_TRY(arena_reset(ctx));
-  uint8_t *nf = (uint8_t *)arena_take(ctx, n);
-  u32 *dlo = (u32 *)arena_take(ctx, n * 4);
-  u32 *dhi = (u32 *)arena_take(ctx, n * 4);
-  uint8_t *tile_has = (uint8_t *)arena_take(ctx, tiles);
+  uint8_t *pending = (uint8_t *)arena_take(ctx, tiles);
+  uint8_t *active = (uint8_t *)arena_take(ctx, tiles);
   uint8_t *dA = (uint8_t *)arena_take(ctx, tiles);
   uint8_t *dB = (uint8_t *)arena_take(ctx, tiles);
   u32 *flag = (u32 *)arena_take(ctx, 256);
-  if (!nf || !dlo || !dhi || !tile_has || !dA || !dB || !flag) return HC_ERR_NOMEM;
+  if (!pending || !active || !dA || !dB || !flag) return HC_ERR_NOMEM;
 
   static bool attr_set = false;
   if (!attr_set) {
     HC_CUDA(cudaFuncSetAttribute(k_flat_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, FLAT_SMEM));
+    HC_CUDA(cudaFuncSetAttribute(k_flat_fast<HC_TABLE_WBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
+    HC_CUDA(cudaFuncSetAttribute(k_flat_fast<HC_TABLE_TAUDEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
     attr_set = true;
   }
   dim3 tg(tx, ty);
+  HC_PROF(ctx, st, "k_flat_fast");
+  if (table == HC_TABLE_WBT)
+    k_flat_fast<HC_TABLE_WBT><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, pending, (int)ny, (int)nx, nodata, ctx->d_dbg);
+  else
+    k_flat_fast<HC_TABLE_TAUDEM><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, pending, (int)ny, (int)nx, nodata, ctx->d_dbg);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemsetAsync(flag, 0, 8, st));
+  HC_PROF(ctx, st, "k_flat_dilate");
+  k_flat_dilate<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(pending, active, tx, ty, flag + 1);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, flag + 1, 4, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  if (!ctx->h_mail[0]) return HC_OK;  // every flat was resolved inside its apron
+
+  uint8_t *nf = (uint8_t *)arena_take(ctx, n);
+  u32 *dlo = (u32 *)arena_take(ctx, n * 4);
+  u32 *dhi = (u32 *)arena_take(ctx, n * 4);
+  if (!nf || !dlo || !dhi) return HC_ERR_NOMEM;
   HC_PROF(ctx, st, "k_flat_init");
-  k_flat_init<<<tg, NTHREADS, 0, st>>>(z, dir, nf, dlo, dhi, tile_has, (int)ny, (int)nx, nodata);
+  k_flat_init<<<tg, NTHREADS, 0, st>>>(z, dirA, dirB, nf, dlo, dhi, active, (int)ny, (int)nx, nodata);
   HC_LAUNCH_CHECK(ctx);
   HC_CUDA(cudaMemsetAsync(dA, 1, tiles, st));
   uint8_t *din = dA, *dout = dB;
   for (int it = 0;; it++) {
-    if (it > 100000) { hc_set_error("flats: relaxation did not converge"); return HC_ERR_INTERNAL; }
+    if (it > 1000000) { hc_set_error("flats: relaxation did not converge"); return HC_ERR_INTERNAL; }
     HC_CUDA(cudaMemsetAsync(dout, 0, tiles, st));
     HC_CUDA(cudaMemsetAsync(flag, 0, 4, st));
     HC_PROF(ctx, st, "k_flat_relax");
-    k_flat_relax<<<tg, NTHREADS, FLAT_SMEM, st>>>(z, nf, dlo, dhi, tile_has, din, dout, flag, (int)ny, (int)nx, nodata);
+    k_flat_relax<<<tg, NTHREADS, FLAT_SMEM, st>>>(z, nf, dlo, dhi, active, din, dout, flag, (int)ny, (int)nx, nodata, ctx->d_dbg);
     HC_LAUNCH_CHECK(ctx);
     HC_CUDA(cudaMemcpyAsync(ctx->h_mail, flag, 4, cudaMemcpyDeviceToHost, st));
     HC_CUDA(cudaStreamSynchronize(st));
@@ -255,9 +523,34 @@ int flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx,
   }
   HC_PROF(ctx, st, "k_flat_dirs");
   if (table == HC_TABLE_WBT)
-    k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(z, nf, dlo, dhi, dir, tile_has, (int)ny, (int)nx, nodata);
+    k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(z, nf, dlo, dhi, dirB, pending, (int)ny, (int)nx, nodata);
   else
-    k_flat_dirs<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(z, nf, dlo, dhi, dir, tile_has, (int)ny, (int)nx, nodata);
+    k_flat_dirs<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(z, nf, dlo, dhi, dirB, pending, (int)ny, (int)nx, nodata);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
+}
+
+// in-place public form: dir is copied aside first
+int flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx, float nodata, int table,
+              cudaStream_t st) {
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("flats: bad table %d", table); return HC_ERR_ARG; }
+  size_t n = (size_t)ny * nx;
+  HC_TRY(arena_reset(ctx));
+  uint8_t *dirA = (uint8_t *)arena_take(ctx, n);
+  if (!dirA) return HC_ERR_NOMEM;
+  HC_CUDA(cudaMemcpyAsync(dirA, dir, n, cudaMemcpyDeviceToDevice, st));
+  return flats_core(ctx, z, dirA, dir, ny, nx, nodata, table, st);
+}
+
+// D8 into an arena temporary, then flats straight into the caller's raster (no copy)
+int d8_flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx, float nodata,
+                 double dx, double dy, int table, cudaStream_t st) {
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  size_t n = (size_t)ny * nx;
+  HC_TRY(arena_reset(ctx));
+  uint8_t *dirA = (uint8_t *)arena_take(ctx, n);
+  if (!dirA) return HC_ERR_NOMEM;
+  HC_TRY(d8_run(ctx, z, dirA, slope, ny, nx, nodata, dx, dy, table, st));
+  return flats_core(ctx, z, dirA, dir, ny, nx, nodata, table, st);
 }
