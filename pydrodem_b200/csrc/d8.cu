@@ -8,70 +8,80 @@
 // with a nodata neighbour as contaminated (code 255).
 #include "common.cuh"
 
-#define D8_TR 16
-#define D8_TC 128
-#define D8_THREADS 256
+#define D8_RS 32        // rows per thread (column strip)
+#define D8_THREADS 256  // columns per block
 
 struct d8_params {
   double len[8];
   float fact[8];
 };
 
+// Column-strip stencil: lane = column, each thread walks D8_RS rows keeping the 3x3 window in
+// registers, so a cell costs 3 coalesced loads (two of them L1 hits), no shared memory, no barrier.
 template <int TABLE, bool SLOPE>
 __global__ void __launch_bounds__(D8_THREADS)
 k_d8(const float *__restrict__ z, uint8_t *__restrict__ dir, float *__restrict__ slope, int ny, int nx,
      float nodata, d8_params prm) {
-  __shared__ float sz[(D8_TR + 2) * (D8_TC + 2)];
-  const int r0 = blockIdx.y * D8_TR, c0 = blockIdx.x * D8_TC;
-  const int W = D8_TC + 2;
+  const int c = blockIdx.x * D8_THREADS + threadIdx.x;
+  if (c >= nx) return;
+  const int rbeg = blockIdx.y * D8_RS, rend = min(rbeg + D8_RS, ny);
   const float qnan = __int_as_float(0x7fc00000);
-  for (int i = threadIdx.x; i < (D8_TR + 2) * W; i += D8_THREADS) {
-    int lr = i / W, lc = i - lr * W;
-    int r = r0 + lr - 1, c = c0 + lc - 1;
-    float v = qnan;
-    if (r >= 0 && r < ny && c >= 0 && c < nx) {
-      v = __ldg(&z[(size_t)r * nx + c]);
-      if (v == nodata) v = qnan;
-    }
-    sz[i] = v;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < D8_TR * D8_TC; i += D8_THREADS) {
-    int lr = i / D8_TC, lc = i - lr * D8_TC;
-    int r = r0 + lr, c = c0 + lc;
-    if (r >= ny || c >= nx) continue;
-    size_t g = (size_t)r * nx + c;
-    float v = sz[(lr + 1) * W + lc + 1];
+  const bool hasl = c > 0, hasr = c < nx - 1;
+  auto ld3 = [&](int r, float &l, float &m, float &rr) {
+    l = m = rr = qnan;
+    if (r < 0 || r >= ny) return;
+    const float *row = z + (size_t)r * nx + c;
+    float vm = __ldg(row);
+    float vl = hasl ? __ldg(row - 1) : qnan;
+    float vr = hasr ? __ldg(row + 1) : qnan;
+    m = vm == nodata ? qnan : vm;
+    l = vl == nodata ? qnan : vl;
+    rr = vr == nodata ? qnan : vr;
+  };
+  float w[3][3];
+  ld3(rbeg - 1, w[0][0], w[0][1], w[0][2]);
+  ld3(rbeg, w[1][0], w[1][1], w[1][2]);
+#pragma unroll 4
+  for (int r = rbeg; r < rend; r++) {
+    ld3(r + 1, w[2][0], w[2][1], w[2][2]);
+    const size_t g = (size_t)r * nx + c;
+    const float v = w[1][1];
+    uint8_t code;
+    float sl;
     if (v != v) {
-      dir[g] = HC_DIR_NODATA;
-      if (SLOPE) slope[g] = -1.0f;
-      continue;
-    }
-    int best = -1;
-    bool contaminated = false;
-    double smax = 0.0;
-    float smaxf = 0.0f;
+      code = HC_DIR_NODATA;
+      sl = -1.0f;
+    } else {
+      int best = -1;
+      bool contaminated = false;
+      double smax = 0.0;
+      float smaxf = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      float zn = sz[(lr + 1 + c_dr[TABLE][k]) * W + lc + 1 + c_dc[TABLE][k]];
-      if (zn != zn) { contaminated = true; continue; }
-      if (TABLE == HC_TABLE_WBT) {
-        if (zn < v) {
-          double s = ((double)v - (double)zn) / prm.len[k];
-          if (s > smax) { smax = s; best = k; }
+      for (int k = 0; k < 8; k++) {
+        const float zn = w[1 + c_dr[TABLE][k]][1 + c_dc[TABLE][k]];
+        if (zn != zn) { contaminated = true; continue; }
+        if (TABLE == HC_TABLE_WBT) {
+          if (zn < v) {
+            double s = ((double)v - (double)zn) / prm.len[k];
+            if (s > smax) { smax = s; best = k; }
+          }
+        } else {
+          float s = __fmul_rn(prm.fact[k], __fsub_rn(v, zn));
+          if (s > smaxf) { smaxf = s; best = k; }
         }
+      }
+      if (TABLE == HC_TABLE_TAUDEM && contaminated) {
+        code = HC_DIR_NODATA;
+        sl = -1.0f;
       } else {
-        float s = __fmul_rn(prm.fact[k], __fsub_rn(v, zn));
-        if (s > smaxf) { smaxf = s; best = k; }
+        code = best < 0 ? (uint8_t)HC_DIR_NOFLOW : (uint8_t)c_code[TABLE][best];
+        sl = TABLE == HC_TABLE_WBT ? (float)smax : smaxf;
       }
     }
-    if (TABLE == HC_TABLE_TAUDEM && contaminated) {
-      dir[g] = HC_DIR_NODATA;
-      if (SLOPE) slope[g] = -1.0f;
-      continue;
-    }
-    dir[g] = best < 0 ? (uint8_t)HC_DIR_NOFLOW : (uint8_t)c_code[TABLE][best];
-    if (SLOPE) slope[g] = TABLE == HC_TABLE_WBT ? (float)smax : smaxf;
+    dir[g] = code;
+    if (SLOPE) slope[g] = sl;
+#pragma unroll
+    for (int j = 0; j < 3; j++) { w[0][j] = w[1][j]; w[1][j] = w[2][j]; }
   }
 }
 
@@ -88,7 +98,7 @@ int d8_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, 
     prm.len[k] = l;
     prm.fact[k] = (float)(1.0 / l);
   }
-  dim3 grid((unsigned)((nx + D8_TC - 1) / D8_TC), (unsigned)((ny + D8_TR - 1) / D8_TR));
+  dim3 grid((unsigned)((nx + D8_THREADS - 1) / D8_THREADS), (unsigned)((ny + D8_RS - 1) / D8_RS));
   if (table == HC_TABLE_WBT) {
     if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }
     else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }

@@ -28,6 +28,8 @@
 //
 // Only float comparisons/min/max touch elevations, so the result is bit-identical to the serial
 // priority-flood (the eps=0 surface is unique).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define T HC_TILE
@@ -189,44 +191,39 @@ k_flatten(u32 *P, size_t n) {
 // ---------------------------------------------------------------------------------------------
 // 4. Boruvka rounds
 // ---------------------------------------------------------------------------------------------
+// EMIT: besides picking the cheapest edge, append every (closed cell, foreign neighbour) pair to a
+// compact edge list; later rounds then run on that list instead of the grid.
+template <bool EMIT>
 __global__ void __launch_bounds__(NTHREADS)
 k_minedge(const float *__restrict__ z, const u32 *__restrict__ P, const u32 *__restrict__ rep,
-          u64 *__restrict__ best, const uint8_t *__restrict__ act_in, uint8_t *__restrict__ act_out, int ny,
-          int nx, float nodata) {
+          u64 *__restrict__ best, int ny, int nx, u32 *__restrict__ eA, u32 *__restrict__ eB,
+          float *__restrict__ eW, u32 *__restrict__ ecount, u32 ecap) {
   __shared__ float sz[TH * TH];
   __shared__ u32 sa[TH * TH];
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (act_in && !act_in[tile]) {
-    if (threadIdx.x == 0) act_out[tile] = 0;
-    return;
-  }
+  __shared__ u32 s_tot, s_base;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
+  if (tid == 0) s_tot = 0;
+#pragma unroll 4
   for (int i = tid; i < TH * TH; i += NTHREADS) {
     int lr = i / TH, lc = i - lr * TH;
     int r = r0 + lr - 1, c = c0 + lc - 1;
-    float v = 0.f;
+    bool inb = r >= 0 && r < ny && c >= 0 && c < nx;
+    size_t g = inb ? (size_t)r * nx + c : 0;
+    u32 id = __ldg(&P[g]) & 0x7FFFFFFFu;
+    float v = __ldg(&z[g]);
     u32 a = HC_NONE;
-    if (r >= 0 && r < ny && c >= 0 && c < nx) {
-      size_t g = (size_t)r * nx + c;
-      u32 id = __ldg(&P[g]) & 0x7FFFFFFFu;
-      if (id != HC_LAB_NODATA) {
-        a = id ? __ldg(&rep[id]) : 0u;
-        v = __ldg(&z[g]);
-      }
-    }
+    if (inb && id != HC_LAB_NODATA) a = id ? __ldg(&rep[id]) : 0u;
     sz[i] = v;
     sa[i] = a;
   }
   __syncthreads();
-  int any = 0;
+  u32 cnt = 0;
   for (int i = tid; i < T * T; i += NTHREADS) {
-    int lr = i / T, lc = i - lr * T;
+    int lr = i >> 6, lc = i & (T - 1);
     int ci = (lr + 1) * TH + lc + 1;
     u32 a = sa[ci];
     if (a == 0u || a == HC_NONE) continue;
-    if (r0 + lr >= ny || c0 + lc >= nx) continue;
-    any = 1;
     float v = sz[ci];
     u64 key = ~0ull;
 #pragma unroll
@@ -240,13 +237,53 @@ k_minedge(const float *__restrict__ z, const u32 *__restrict__ P, const u32 *__r
         float w = fmaxf(v, sz[ni]);
         u64 k = ((u64)d_ford(w) << 32) | (u64)b;
         key = k < key ? k : key;
+        cnt++;
       }
     if (key != ~0ull) {
       if (key < __ldcg(&best[a])) atomicMin(&best[a], key);
     }
   }
-  any = __syncthreads_or(any);
-  if (tid == 0) act_out[tile] = (uint8_t)(any ? 1 : 0);
+  if (!EMIT) return;
+  u32 off = cnt ? atomicAdd(&s_tot, cnt) : 0u;
+  __syncthreads();
+  if (tid == 0) s_base = s_tot ? atomicAdd(ecount, s_tot) : 0u;
+  __syncthreads();
+  if (!cnt || (u64)s_base + s_tot > (u64)ecap) return;  // overflow: host falls back to grid rounds
+  u32 o = s_base + off;
+  for (int i = tid; i < T * T; i += NTHREADS) {
+    int lr = i >> 6, lc = i & (T - 1);
+    int ci = (lr + 1) * TH + lc + 1;
+    u32 a = sa[ci];
+    if (a == 0u || a == HC_NONE) continue;
+    float v = sz[ci];
+#pragma unroll
+    for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+      for (int dc = -1; dc <= 1; dc++) {
+        if (dr == 0 && dc == 0) continue;
+        int ni = ci + dr * TH + dc;
+        u32 b = sa[ni];
+        if (b == a || b == HC_NONE) continue;
+        eA[o] = a;
+        eB[o] = b;
+        eW[o] = fmaxf(v, sz[ni]);
+        o++;
+      }
+  }
+}
+
+// a Boruvka pick round on the compact edge list
+__global__ void __launch_bounds__(256)
+k_minedge_list(const u32 *__restrict__ eA, const u32 *__restrict__ eB, const float *__restrict__ eW, u32 ne,
+               const u32 *__restrict__ rep, u64 *__restrict__ best) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  u32 a = __ldg(&rep[eA[i]]);
+  if (a == 0u) return;
+  u32 b = __ldg(&rep[eB[i]]);
+  if (a == b) return;
+  u64 key = ((u64)d_ford(eW[i]) << 32) | (u64)b;
+  if (key < __ldcg(&best[a])) atomicMin(&best[a], key);
 }
 
 __global__ void k_tab_init(u32 *rep, float *lvl, u32 *hp, u32 K1) {
@@ -392,6 +429,16 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
   float *lvl = (float *)arena_take(ctx, (size_t)K1 * 4);
   if (!best || !rep || !hp || !ptr || !ptr2 || !lvl) return HC_ERR_NOMEM;
   float *level0 = (float *)ptr2;  // reused after the rounds
+  // compact edge list for the rounds after the second grid pass
+  size_t ecap_sz = n / 4 > (size_t)(1u << 20) ? n / 4 : (size_t)(1u << 20);
+  if (ecap_sz > (size_t)(1u << 28)) ecap_sz = (size_t)(1u << 28);
+  const u32 ecap = (u32)ecap_sz;
+  u32 *eA = (u32 *)arena_take(ctx, (size_t)ecap * 4);
+  u32 *eB = (u32 *)arena_take(ctx, (size_t)ecap * 4);
+  float *eW = (float *)arena_take(ctx, (size_t)ecap * 4);
+  if (!eA || !eB || !eW) return HC_ERR_NOMEM;
+  u32 ne = 0;
+  bool have_list = false;
 
   const int tb = 256;
   const int tgK = (int)((K1 + tb - 1) / tb);
@@ -399,15 +446,26 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
   k_tab_init<<<tgK, tb, 0, st>>>(rep, lvl, hp, K1);
   HC_LAUNCH_CHECK(ctx);
 
-  uint8_t *act_in = nullptr, *act_out = actA;
   u32 active = K;
   int round = 0;
   while (active > 0) {
     if (round > 64) { hc_set_error("fill: Boruvka did not converge"); return HC_ERR_INTERNAL; }
     HC_CUDA(cudaMemsetAsync(best, 0xFF, (size_t)K1 * 8, st));
-    HC_PROF(ctx, st, "k_minedge");
-    k_minedge<<<tg, NTHREADS, 0, st>>>(z, P, rep, best, act_in, act_out, (int)ny, (int)nx, nodata);
-    HC_LAUNCH_CHECK(ctx);
+    if (have_list) {
+      HC_PROF(ctx, st, "k_minedge_list");
+      k_minedge_list<<<(ne + 255) / 256, 256, 0, st>>>(eA, eB, eW, ne, rep, best);
+      HC_LAUNCH_CHECK(ctx);
+    } else if (round == 1) {
+      HC_CUDA(cudaMemsetAsync(cnt + 4, 0, 4, st));
+      HC_PROF(ctx, st, "k_minedge_emit");
+      k_minedge<true><<<tg, NTHREADS, 0, st>>>(z, P, rep, best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap);
+      HC_LAUNCH_CHECK(ctx);
+      HC_CUDA(cudaMemcpyAsync(ctx->h_mail + 4, cnt + 4, 4, cudaMemcpyDeviceToHost, st));
+    } else {
+      HC_PROF(ctx, st, "k_minedge");
+      k_minedge<false><<<tg, NTHREADS, 0, st>>>(z, P, rep, best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap);
+      HC_LAUNCH_CHECK(ctx);
+    }
     HC_PROF(ctx, st, "k_hook");
     k_hook<<<tgK, tb, 0, st>>>(rep, best, ptr2, lvl, K1);
     HC_LAUNCH_CHECK(ctx);
@@ -439,8 +497,11 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
     HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 2, 4, cudaMemcpyDeviceToHost, st));
     HC_CUDA(cudaStreamSynchronize(st));
     active = ctx->h_mail[0];
-    act_in = act_out;
-    act_out = (act_out == actA) ? actB : actA;
+    if (round == 1 && !have_list) {  // the emit round's count arrived with the syncs above
+      ne = ctx->h_mail[4];
+      have_list = ne <= ecap;
+    }
+    if (getenv("HC_TRACE")) fprintf(stderr, "[fill] round %d: %u closed supernodes left of %u basins (edge list %u%s)\n", round, active, K, ne, have_list ? "" : " unused");
     round++;
   }
   ctx->fill_rounds = round;

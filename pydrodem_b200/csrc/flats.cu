@@ -58,29 +58,34 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
   const float qnan = __int_as_float(0x7fc00000);
   if (tid == 0) s_n[0] = 0;
   __syncthreads();
-  // 1. load: elevation (NaN = not a cell), NOFLOW flag; non-rim NOFLOW cells go on the work list
+  // 1a. pure copy global -> shared with many loads in flight (dir parked in the `hi` array)
 #pragma unroll 5
   for (int i = tid; i < FR * FR; i += NTHREADS) {
     int lr = i / FR, lc = i - lr * FR;
     int r = r0 + lr, c = c0 + lc;
-    float v = qnan;
+    bool inb = r >= 0 && r < ny && c >= 0 && c < nx;
+    size_t g = inb ? (size_t)r * nx + c : 0;
+    float v = __ldg(&z[g]);
+    uint8_t d = __ldg(&dirA[g]);
+    sz[i] = (inb && v != nodata) ? v : qnan;
+    shi[i] = d;
+  }
+  __syncthreads();
+  // 1b. NOFLOW flag; non-rim NOFLOW cells go on the work list
+  for (int i = tid; i < FR * FR; i += NTHREADS) {
     u32 w = 0;
-    if (r >= 0 && r < ny && c >= 0 && c < nx) {
-      size_t g = (size_t)r * nx + c;
-      v = __ldg(&z[g]);
-      if (v == nodata) v = qnan;
-      if (v == v && __ldg(&dirA[g]) == HC_DIR_NOFLOW) {
-        // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
-        // (conservatively also when the rim coincides with the raster border)
-        if (lr == 0 || lc == 0 || lr == FR - 1 || lc == FR - 1) w = F_NF | F_OPEN;
-        else {
-          w = F_NF;
-          u32 k = atomicAdd(&s_n[0], 1u);
-          if (k < FLCAP) list[k] = (unsigned short)i;
-        }
+    float v = sz[i];
+    if (v == v && shi[i] == HC_DIR_NOFLOW) {
+      int lr = i / FR, lc = i - lr * FR;
+      // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
+      // (conservatively also when the rim coincides with the raster border)
+      if (lr == 0 || lc == 0 || lr == FR - 1 || lc == FR - 1) w = F_NF | F_OPEN;
+      else {
+        w = F_NF;
+        u32 k = atomicAdd(&s_n[0], 1u);
+        if (k < FLCAP) list[k] = (unsigned short)i;
       }
     }
-    sz[i] = v;
     slo[i] = (unsigned short)w;
     shi[i] = 0;
   }
@@ -319,29 +324,33 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
+  __shared__ uint8_t s_act[9];
   if (tid == 0) { s_side = 0; s_n = 0; }
+  if (tid < 9) {
+    int yy = (int)blockIdx.y + tid / 3 - 1, xx = (int)blockIdx.x + tid % 3 - 1;
+    s_act[tid] = (yy >= 0 && yy < ty && xx >= 0 && xx < tx) ? active[yy * tx + xx] : 0;
+  }
   __syncthreads();
+#pragma unroll 4
   for (int i = tid; i < TH * TH; i += NTHREADS) {
     int lr = i / TH, lc = i - lr * TH;
     int r = r0 + lr - 1, c = c0 + lc - 1;
-    float v = qnan;
-    u32 lo = 0, hi = 0;
-    if (r >= 0 && r < ny && c >= 0 && c < nx) {
-      // halo cells of tiles outside the active set hold no state: treat as not in any flat
-      int ht = (r / T) * tx + (c / T);
-      if (active[ht]) {
-        size_t g = (size_t)r * nx + c;
-        v = __ldg(&z[g]);
-        if (v == nodata) v = qnan;
-        lo = __ldcg(&dlo[g]);
-        hi = __ldcg(&dhi[g]);
-        if (__ldg(&nf[g])) {
-          lo |= R_NF;
-          if (lr >= 1 && lr <= T && lc >= 1 && lc <= T) list[atomicAdd(&s_n, 1u)] = (unsigned short)(lr * TP + lc);
-        }
-      }
+    // halo cells of tiles outside the active set hold no state: treat as not in any flat
+    int ay = lr == 0 ? 0 : (lr == TH - 1 ? 2 : 1), ax = lc == 0 ? 0 : (lc == TH - 1 ? 2 : 1);
+    bool inb = r >= 0 && r < ny && c >= 0 && c < nx && s_act[ay * 3 + ax];
+    size_t g = inb ? (size_t)r * nx + c : 0;
+    float v = __ldg(&z[g]);
+    u32 lo = __ldcg(&dlo[g]);
+    u32 hi = __ldcg(&dhi[g]);
+    uint8_t f = __ldg(&nf[g]);
+    if (!inb) { lo = 0; hi = 0; f = 0; }
+    if (f) {
+      lo |= R_NF;
+      if (lr >= 1 && lr <= T && lc >= 1 && lc <= T) list[atomicAdd(&s_n, 1u)] = (unsigned short)(lr * TP + lc);
     }
-    sz[lr * TP + lc] = v; slo[lr * TP + lc] = lo; shi[lr * TP + lc] = hi;
+    sz[lr * TP + lc] = (inb && v != nodata) ? v : qnan;
+    slo[lr * TP + lc] = lo;
+    shi[lr * TP + lc] = hi;
   }
   __syncthreads();
   const u32 nlist = s_n;
@@ -353,7 +362,8 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
     // quarter (t / T).
     const int line = 1 + tid % T, a0 = 1 + (tid / T) * 16, a1 = a0 + 15;
     int quiet = 0;
-    for (int sweep = 0; quiet < 4; sweep++) {
+    // one sweep that changes nothing proves the fixed point (every cell was just re-evaluated)
+    for (int sweep = 0; quiet < 1; sweep++) {
       int changed = 0;
       switch (sweep & 3) {
         case 0: for (int c = a0; c <= a1; c++) changed |= slow_relax(sz, slo, shi, line * TP + c); break;
