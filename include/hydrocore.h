@@ -92,6 +92,43 @@ int hc_fill_d8_accum_dev(hc_ctx *ctx, const float *z, float *filled, uint8_t *di
 int hc_label_dev(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn,
                  int32_t *nlab, void *stream);
 
+/* WhiteboxTools' single-cell-pit tools (models/depression_handling.py:259-261,
+ * models/find_sinks.py:118).  fill: an interior cell whose 8 neighbours are all valid and strictly
+ * higher is raised to the lowest of them.  breach: for such a pit (two cells from the edge at
+ * least), every lower 2-ring cell cuts the bridging 1-ring cell to the mean of pit and target
+ * (serial last-write-wins order reproduced).  z and out may not alias. */
+int hc_fill_single_cell_pits_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx,
+                                 float nodata, void *stream);
+int hc_breach_single_cell_pits_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx,
+                                   float nodata, void *stream);
+
+/* TaudemCheck (models/taudem_check.py:143-147): mask = D8 is nodata (255) on a valid cell whose
+ * flatten mask is in 2..5 and whose EDM value is < 4; *n_problem (host pointer) gets the count.
+ * hc_taudem_fix (fix_basin, :183-194): cells with flat > 0 are raised by `bump` (0.10 m). */
+int hc_taudem_check_dev(hc_ctx *ctx, const uint8_t *p, const float *fel, const uint8_t *flat,
+                        const uint8_t *edm, uint8_t *mask, int64_t *n_problem, int64_t ny, int64_t nx,
+                        float nodata, void *stream);
+int hc_taudem_fix_dev(hc_ctx *ctx, const float *dem, const uint8_t *flat, float *out, int64_t ny,
+                      int64_t nx, float nodata, float bump, void *stream);
+
+/* Smoothing stencils of CreateDTM (models/dem_noise_removal.py:397-487) and dep.create_clump_array.
+ * conv2d_symm = scipy.signal.convolve2d(boundary='symm', mode='same') as pdt.apply_convolve_filter
+ * calls it (tools/derive.py:94); kernel is a HOST pointer to kh*kw float32 (odd sizes <= 31).
+ * slope: pdt.slope_D2 (d4=0) / slope_D4 (d4=1) -> int8 degrees (deg) and/or float32 magnitude (mag).
+ * curvature_d2: pdt.curvature_D2.  mean_std: np.mean/np.std in float64.  dtm_select: the filter
+ * selection block (:414-471); masks may be NULL; cbreak0/1 = float32(curvebreak * sigma). */
+int hc_conv2d_symm_dev(hc_ctx *ctx, const float *in, const float *kernel_host, int kh, int kw, float *out,
+                       int64_t ny, int64_t nx, void *stream);
+int hc_slope_dev(hc_ctx *ctx, const float *z, int8_t *deg, float *mag, int64_t ny, int64_t nx, double dx,
+                 double dy, int d4, void *stream);
+int hc_curvature_d2_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, double dx, double dy,
+                        int geometric, void *stream);
+int hc_mean_std_dev(hc_ctx *ctx, const float *x, int64_t n, double *mean, double *std, void *stream);
+int hc_dtm_select_dev(hc_ctx *ctx, const float *dem, const float *z9, const float *z7, const float *z5,
+                      const float *z3, const int8_t *slope0, const float *curv, const uint8_t *swo,
+                      const uint8_t *edm, const uint8_t *tx, const uint8_t *artifact, float *zf, int8_t *filt,
+                      int64_t n, float cbreak0, float cbreak1, const int *slopebreaks5, void *stream);
+
 /* HOST-buffer variants (H2D + kernels + D2H inside the call; synchronous). */
 int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
                  int seed_mode);

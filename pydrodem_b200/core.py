@@ -168,3 +168,68 @@ def fill_stats(device=0):
     nb, nr = ctypes.c_int64(0), ctypes.c_int32(0)
     _lib.check(_lib.load().hc_fill_stats(_lib.context(device), ctypes.byref(nb), ctypes.byref(nr)), "hc_fill_stats")
     return int(nb.value), int(nr.value)
+
+
+def _unary_f32(z, fn_name, nodata):
+    import torch
+    lib = _lib.load()
+    host = not _is_torch(z)
+    if host:
+        z = torch.from_numpy(_np2d(z, np.float32)).cuda()
+    z = _tdev(z, torch.float32, fn_name)
+    out = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        _lib.check(getattr(lib, fn_name)(_lib.context(z.device.index or 0), _tp(z), _tp(out), z.shape[0], z.shape[1],
+                                         nodata, _stream(z)), fn_name)
+    return out.cpu().numpy() if host else out
+
+
+def fill_single_cell_pits(z, nodata=-9999.0):
+    """wbt.fill_single_cell_pits (models/depression_handling.py:261, models/find_sinks.py:118)."""
+    return _unary_f32(z, "hc_fill_single_cell_pits_dev", nodata)
+
+
+def breach_single_cell_pits(z, nodata=-9999.0):
+    """wbt.breach_single_cell_pits (models/depression_handling.py:259)."""
+    return _unary_f32(z, "hc_breach_single_cell_pits_dev", nodata)
+
+
+def taudem_check(p, fel, flat_mask, edm, nodata=-9999.0):
+    """TaudemCheck.check_basin's problem mask (models/taudem_check.py:143-147): returns (mask uint8, count).
+    `p` is the uint8 D8 raster with 255 = nodata."""
+    import torch
+    lib = _lib.load()
+    host = not _is_torch(p)
+    if host:
+        p = torch.from_numpy(_np2d(p, np.uint8)).cuda()
+        fel = torch.from_numpy(_np2d(fel, np.float32)).cuda()
+        flat_mask = torch.from_numpy(_np2d(flat_mask, np.uint8)).cuda()
+        edm = torch.from_numpy(_np2d(edm, np.uint8)).cuda()
+    p = _tdev(p, torch.uint8, "taudem_check")
+    fel = _tdev(fel, torch.float32, "taudem_check")
+    flat_mask = _tdev(flat_mask, torch.uint8, "taudem_check")
+    edm = _tdev(edm, torch.uint8, "taudem_check")
+    mask = torch.empty_like(p)
+    n = ctypes.c_int64(0)
+    with torch.cuda.device(p.device):
+        _lib.check(lib.hc_taudem_check_dev(_lib.context(p.device.index or 0), _tp(p), _tp(fel), _tp(flat_mask), _tp(edm),
+                                           _tp(mask), ctypes.byref(n), p.shape[0], p.shape[1], nodata, _stream(p)),
+                   "hc_taudem_check_dev")
+    return (mask.cpu().numpy() if host else mask), int(n.value)
+
+
+def taudem_fix(dem, flat_mask, nodata=-9999.0, bump=0.10):
+    """TaudemCheck.fix_basin (models/taudem_check.py:183-194): water cells (+flat mask > 0) += bump."""
+    import torch
+    lib = _lib.load()
+    host = not _is_torch(dem)
+    if host:
+        dem = torch.from_numpy(_np2d(dem, np.float32)).cuda()
+        flat_mask = torch.from_numpy(_np2d(flat_mask, np.uint8)).cuda()
+    dem = _tdev(dem, torch.float32, "taudem_fix")
+    flat_mask = _tdev(flat_mask, torch.uint8, "taudem_fix")
+    out = torch.empty_like(dem)
+    with torch.cuda.device(dem.device):
+        _lib.check(lib.hc_taudem_fix_dev(_lib.context(dem.device.index or 0), _tp(dem), _tp(flat_mask), _tp(out),
+                                         dem.shape[0], dem.shape[1], nodata, bump, _stream(dem)), "hc_taudem_fix_dev")
+    return out.cpu().numpy() if host else out

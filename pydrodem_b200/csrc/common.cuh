@@ -133,3 +133,4 @@ size_t accum_workspace(int64_t ny, int64_t nx);
 int label_run(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn, int32_t *nlab,
               cudaStream_t st);
 size_t label_workspace(int64_t ny, int64_t nx);
+int scp_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata, int breach, cudaStream_t st);

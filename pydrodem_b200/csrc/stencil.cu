@@ -1,0 +1,296 @@
+// stencil.cu — the dem_noise_removal / veg-bias smoothing stencils.
+//
+//   hc_conv2d_symm      pdt.apply_convolve_filter = scipy.signal.convolve2d(boundary='symm', mode='same')
+//                       tools/derive.py:66-99 (DW kernels from bop.build_kernel, tools/build_operators.py:327-351;
+//                       also the box dilation of dep.create_clump_array, tools/depressions.py:1640-1644)
+//   hc_slope            pdt.slope_D2 / slope_D4 -> int8 degrees            tools/derive.py:102-130, 176-246
+//   hc_curvature_d2     pdt.curvature_D2 (geometric or Laplacian)          tools/derive.py:133-173
+//   hc_mean_std         np.std(curvature), the global sigma of CreateDTM    models/dem_noise_removal.py:413
+//   hc_dtm_select       the filter-selection block of CreateDTM.run_tile    models/dem_noise_removal.py:414-471
+//
+// Arithmetic: np.gradient on float32 is (a - b) / float32(2h) inside, (a - b) / float32(h) one-sided
+// at the array edges, every step rounded to float32 - reproduced with _rn intrinsics so gradients and
+// curvature are bit-identical; atan/rad2deg go through CUDA's atanf, so int8 degrees can differ by one
+// at a truncation boundary; the convolution accumulates in float32 (FMA), scipy's summation order is
+// not reproducible, so it is a tolerance-class result (tests state the tolerance).
+#include "common.cuh"
+
+#define CONV_MAXK 31
+__constant__ float c_kern[CONV_MAXK * CONV_MAXK];
+
+__device__ __forceinline__ int symm(int i, int n) {
+  // half-sample symmetric reflection (d c b a | a b c d | d c b a)
+  while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - i - 1;
+  return i;
+}
+
+#define CV_TR 32
+#define CV_TC 64
+__global__ void __launch_bounds__(256)
+k_conv2d_symm(const float *__restrict__ in, float *__restrict__ out, int ny, int nx, int kh, int kw) {
+  extern __shared__ float sm[];
+  const int ph = kh / 2, pw = kw / 2;
+  const int W = CV_TC + kw - 1, H = CV_TR + kh - 1;
+  const int r0 = blockIdx.y * CV_TR, c0 = blockIdx.x * CV_TC;
+  for (int i = threadIdx.x; i < W * H; i += 256) {
+    int lr = i / W, lc = i - lr * W;
+    int r = symm(r0 + lr - ph, ny), c = symm(c0 + lc - pw, nx);
+    sm[i] = __ldg(&in[(size_t)r * nx + c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV_TR * CV_TC; i += 256) {
+    int lr = i / CV_TC, lc = i - lr * CV_TC;
+    int r = r0 + lr, c = c0 + lc;
+    if (r >= ny || c >= nx) continue;
+    float s = 0.f;
+    // true convolution: out[i,j] = sum_ab ker[a,b] * in[i + ph - a, j + pw - b]
+    for (int a = 0; a < kh; a++) {
+      const float *row = &sm[(lr + kh - 1 - a) * W + lc + kw - 1];
+      const float *kr = &c_kern[a * kw];
+      for (int b = 0; b < kw; b++) s = fmaf(kr[b], row[-b], s);
+    }
+    out[(size_t)r * nx + c] = s;
+  }
+}
+
+// ---- np.gradient pieces ------------------------------------------------------------------------
+struct grad_prm { float h2x, h2y, hx, hy; double dxy; };  // float32(2dx), float32(2dy), float32(dx), float32(dy); float64 diagonal factor
+
+__device__ __forceinline__ float gy(const float *z, int r, int c, int ny, int nx, const grad_prm &p) {
+  if (ny == 1) return 0.f;
+  if (r == 0) return __fdiv_rn(__fsub_rn(z[(size_t)nx + c], z[c]), p.hy);
+  if (r == ny - 1) return __fdiv_rn(__fsub_rn(z[(size_t)r * nx + c], z[(size_t)(r - 1) * nx + c]), p.hy);
+  return __fdiv_rn(__fsub_rn(z[(size_t)(r + 1) * nx + c], z[(size_t)(r - 1) * nx + c]), p.h2y);
+}
+__device__ __forceinline__ float gx(const float *z, int r, int c, int ny, int nx, const grad_prm &p) {
+  if (nx == 1) return 0.f;
+  const float *row = z + (size_t)r * nx;
+  if (c == 0) return __fdiv_rn(__fsub_rn(row[1], row[0]), p.hx);
+  if (c == nx - 1) return __fdiv_rn(__fsub_rn(row[c], row[c - 1]), p.hx);
+  return __fdiv_rn(__fsub_rn(row[c + 1], row[c - 1]), p.h2x);
+}
+
+__device__ __forceinline__ int8_t to_deg_i8(float slope) {
+  float deg = atanf(slope) * 57.29577951308232f;  // np.rad2deg(np.arctan(.)) in float32
+  return (int8_t)(int)deg;                       // astype(int8): truncation toward zero
+}
+
+// mode 0: slope_D2, mode 1: slope_D4 (max |central difference| over x, y and the two diagonals)
+__global__ void __launch_bounds__(256)
+k_slope(const float *__restrict__ z, int8_t *__restrict__ out, float *__restrict__ mag, int ny, int nx, grad_prm p,
+        int mode) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= nx) return;
+  float dy = gy(z, r, c, ny, nx, p), dx = gx(z, r, c, ny, nx, p);
+  float s;
+  if (mode == 0) {
+    s = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+  } else {
+    // diagonal kernels are convolved in float64 and narrowed to float32 (tools/derive.py:226-241)
+    int ru = symm(r - 1, ny), rd = symm(r + 1, ny), cl = symm(c - 1, nx), cr = symm(c + 1, nx);
+    const double dxy = p.dxy;
+    float dnw = (float)__dadd_rn(__dmul_rn(dxy, (double)z[(size_t)rd * nx + cr]), __dmul_rn(-dxy, (double)z[(size_t)ru * nx + cl]));
+    float dne = (float)__dadd_rn(__dmul_rn(dxy, (double)z[(size_t)rd * nx + cl]), __dmul_rn(-dxy, (double)z[(size_t)ru * nx + cr]));
+    s = fmaxf(fmaxf(fabsf(dx), fabsf(dne)), fmaxf(fabsf(dy), fabsf(dnw)));
+  }
+  if (out) out[(size_t)r * nx + c] = to_deg_i8(s);
+  if (mag) mag[(size_t)r * nx + c] = s;
+}
+
+__device__ __forceinline__ void norm_grad(const float *z, int r, int c, int ny, int nx, const grad_prm &p, float *ny_,
+                                          float *nx_) {
+  float dy = gy(z, r, c, ny, nx, p), dx = gx(z, r, c, ny, nx, p);
+  float m = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx))), 0.1f);
+  *ny_ = __fdiv_rn(dy, m);
+  *nx_ = __fdiv_rn(dx, m);
+}
+
+__global__ void __launch_bounds__(256)
+k_curv_d2(const float *__restrict__ z, float *__restrict__ out, int ny, int nx, grad_prm p, int geometric) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= nx) return;
+  // first-stage field F_y (for d/dy) and F_x (for d/dx) at a point
+  auto Fy = [&](int rr, int cc) { float a, b; if (geometric) { norm_grad(z, rr, cc, ny, nx, p, &a, &b); return a; } return gy(z, rr, cc, ny, nx, p); };
+  auto Fx = [&](int rr, int cc) { float a, b; if (geometric) { norm_grad(z, rr, cc, ny, nx, p, &a, &b); return b; } return gx(z, rr, cc, ny, nx, p); };
+  float d2y, d2x;
+  if (ny == 1) d2y = 0.f;
+  else if (r == 0) d2y = __fdiv_rn(__fsub_rn(Fy(1, c), Fy(0, c)), p.hy);
+  else if (r == ny - 1) d2y = __fdiv_rn(__fsub_rn(Fy(r, c), Fy(r - 1, c)), p.hy);
+  else d2y = __fdiv_rn(__fsub_rn(Fy(r + 1, c), Fy(r - 1, c)), p.h2y);
+  if (nx == 1) d2x = 0.f;
+  else if (c == 0) d2x = __fdiv_rn(__fsub_rn(Fx(r, 1), Fx(r, 0)), p.hx);
+  else if (c == nx - 1) d2x = __fdiv_rn(__fsub_rn(Fx(r, c), Fx(r, c - 1)), p.hx);
+  else d2x = __fdiv_rn(__fsub_rn(Fx(r, c + 1), Fx(r, c - 1)), p.h2x);
+  out[(size_t)r * nx + c] = __fadd_rn(d2y, d2x);
+}
+
+// ---- global mean / population std (float64 accumulation) ----------------------------------------
+__global__ void __launch_bounds__(256)
+k_sum2(const float *__restrict__ x, size_t n, double *__restrict__ acc /* [sum, sumsq] */, double shift) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  double s = 0.0, q = 0.0;
+  for (; i < n; i += stride) { double v = (double)x[i] - shift; s += v; q += v * v; }
+  for (int o = 16; o; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); q += __shfl_down_sync(0xffffffffu, q, o); }
+  __shared__ double ss[8], sq[8];
+  int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { ss[w] = s; sq[w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) { s += ss[k]; q += sq[k]; }
+    atomicAdd(&acc[0], s);
+    atomicAdd(&acc[1], q);
+  }
+}
+
+// ---- CreateDTM filter selection (models/dem_noise_removal.py:414-471) -------------------------------
+struct dtm_prm { float cb0, cb1; int sb1, sb2, sb3, sb4; };  // sigma-scaled curvature breaks, slope breaks
+
+__global__ void __launch_bounds__(256)
+k_dtm_select(const float *__restrict__ dem, const float *__restrict__ z9, const float *__restrict__ z7,
+             const float *__restrict__ z5, const float *__restrict__ z3, const int8_t *__restrict__ slope0,
+             const float *__restrict__ curv, const uint8_t *__restrict__ swo, const uint8_t *__restrict__ edm,
+             const uint8_t *__restrict__ tx, const uint8_t *__restrict__ artifact, float *__restrict__ zf,
+             int8_t *__restrict__ filt, size_t n, dtm_prm p) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float d = dem[i], cv = curv[i];
+    const int s = slope0[i];
+    const bool peak = cv < -p.cb1, peakfill = cv >= -p.cb1 && cv < -p.cb0;
+    const bool valley = cv > p.cb1, valleyfill = cv <= p.cb1 && cv > p.cb0;
+    const bool steep = s >= p.sb4;
+    float z = z9[i];
+    int f = 9;
+    if (s >= p.sb1 && s <= p.sb2) { f = 7; z = z7[i]; }
+    if (s >= p.sb2 && s <= p.sb3) { f = 5; z = z5[i]; }
+    if ((s >= p.sb3 && s <= p.sb4) || valleyfill || peakfill) { f = 3; z = z3[i]; }
+    if (steep) f = 1;
+    if (peak) f = 2;
+    if (valley) f = 0;
+    if (steep || peak || valley) z = d;
+    if (swo && swo[i]) { f = 3; z = z3[i]; }
+    if (edm && edm[i] == 5 && f < 3) { f = 3; z = z3[i]; }
+    if (tx && tx[i]) { f = 1; z = d; }
+    if (artifact && artifact[i] == 1) z = d;
+    zf[i] = z;
+    filt[i] = (int8_t)f;
+  }
+}
+
+// ---- C ABI --------------------------------------------------------------------------------------------
+#define ST_CTX(ctx)                                                  \
+  do {                                                               \
+    if (!(ctx)) { hc_set_error("null context"); return HC_ERR_ARG; } \
+    HC_CUDA(cudaSetDevice((ctx)->device));                           \
+  } while (0)
+
+static grad_prm make_grad(double dx, double dy) {
+  grad_prm p;
+  p.h2x = (float)(2.0 * dx); p.h2y = (float)(2.0 * dy); p.hx = (float)dx; p.hy = (float)dy;
+  p.dxy = 1.0 / (2.0 * sqrt(dx * dx + dy * dy));  // float64 Python scalar in the reference
+  return p;
+}
+
+extern "C" int hc_conv2d_symm_dev(hc_ctx *ctx, const float *in, const float *kernel_host, int kh, int kw, float *out,
+                                  int64_t ny, int64_t nx, void *stream) {
+  ST_CTX(ctx);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!in || !out || !kernel_host || in == out) { hc_set_error("hc_conv2d_symm: bad pointer"); return HC_ERR_ARG; }
+  if (kh < 1 || kw < 1 || kh > CONV_MAXK || kw > CONV_MAXK || !(kh & 1) || !(kw & 1)) {
+    hc_set_error("hc_conv2d_symm: kernel must be odd x odd, at most %d", CONV_MAXK);
+    return HC_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_CUDA(cudaMemcpyToSymbolAsync(c_kern, kernel_host, sizeof(float) * kh * kw, 0, cudaMemcpyHostToDevice, st));
+  dim3 grid((unsigned)((nx + CV_TC - 1) / CV_TC), (unsigned)((ny + CV_TR - 1) / CV_TR));
+  size_t smem = sizeof(float) * (CV_TC + kw - 1) * (CV_TR + kh - 1);
+  HC_PROF(ctx, st, "k_conv2d_symm");
+  k_conv2d_symm<<<grid, 256, smem, st>>>(in, out, (int)ny, (int)nx, kh, kw);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+extern "C" int hc_slope_dev(hc_ctx *ctx, const float *z, int8_t *deg, float *mag, int64_t ny, int64_t nx, double dx,
+                            double dy, int d4, void *stream) {
+  ST_CTX(ctx);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!z || (!deg && !mag) || ny > 65535) { hc_set_error("hc_slope: bad argument"); return HC_ERR_ARG; }
+  grad_prm p = make_grad(dx, dy);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((nx + 255) / 256), (unsigned)ny);
+  HC_PROF(ctx, st, "k_slope");
+  k_slope<<<grid, 256, 0, st>>>(z, deg, mag, (int)ny, (int)nx, p, d4 ? 1 : 0);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+extern "C" int hc_curvature_d2_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, double dx, double dy,
+                                   int geometric, void *stream) {
+  ST_CTX(ctx);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!z || !out || ny > 65535) { hc_set_error("hc_curvature_d2: bad argument"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((nx + 255) / 256), (unsigned)ny);
+  HC_PROF(ctx, st, "k_curv_d2");
+  k_curv_d2<<<grid, 256, 0, st>>>(z, out, (int)ny, (int)nx, make_grad(dx, dy), geometric ? 1 : 0);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+extern "C" int hc_mean_std_dev(hc_ctx *ctx, const float *x, int64_t n, double *mean, double *std, void *stream) {
+  ST_CTX(ctx);
+  if (mean) *mean = 0;
+  if (std) *std = 0;
+  if (n <= 0) return HC_OK;
+  if (!x) { hc_set_error("hc_mean_std: null pointer"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_TRY(arena_reset(ctx));
+  double *acc = (double *)arena_take(ctx, 256);
+  if (!acc) return HC_ERR_NOMEM;
+  double host[2];
+  // two passes: mean first, then centred second moment (stable)
+  HC_CUDA(cudaMemsetAsync(acc, 0, 16, st));
+  HC_PROF(ctx, st, "k_sum2");
+  k_sum2<<<ctx->sm_count * 8, 256, 0, st>>>(x, (size_t)n, acc, 0.0);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(host, acc, 16, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  double m = host[0] / (double)n;
+  HC_CUDA(cudaMemsetAsync(acc, 0, 16, st));
+  HC_PROF(ctx, st, "k_sum2");
+  k_sum2<<<ctx->sm_count * 8, 256, 0, st>>>(x, (size_t)n, acc, m);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(host, acc, 16, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  if (mean) *mean = m + host[0] / (double)n;
+  if (std) {
+    double d = host[0] / (double)n;
+    *std = sqrt(fmax(host[1] / (double)n - d * d, 0.0));
+  }
+  return HC_OK;
+}
+
+extern "C" int hc_dtm_select_dev(hc_ctx *ctx, const float *dem, const float *z9, const float *z7, const float *z5,
+                                 const float *z3, const int8_t *slope0, const float *curv, const uint8_t *swo,
+                                 const uint8_t *edm, const uint8_t *tx, const uint8_t *artifact, float *zf, int8_t *filt,
+                                 int64_t n, float cbreak0, float cbreak1, const int *slopebreaks5, void *stream) {
+  ST_CTX(ctx);
+  if (n <= 0) return HC_OK;
+  if (!dem || !z9 || !z7 || !z5 || !z3 || !slope0 || !curv || !zf || !filt || !slopebreaks5) {
+    hc_set_error("hc_dtm_select: null pointer");
+    return HC_ERR_ARG;
+  }
+  dtm_prm p;
+  // cbreak = [c * np.std(curv) for c in curvebreaks] are np.float32 scalars in the reference (NEP 50):
+  // the caller passes them already narrowed
+  p.cb0 = cbreak0;
+  p.cb1 = cbreak1;
+  p.sb1 = slopebreaks5[1]; p.sb2 = slopebreaks5[2]; p.sb3 = slopebreaks5[3]; p.sb4 = slopebreaks5[4];
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_PROF(ctx, st, "k_dtm_select");
+  k_dtm_select<<<ctx->sm_count * 8, 256, 0, st>>>(dem, z9, z7, z5, z3, slope0, curv, swo, edm, tx, artifact, zf, filt,
+                                                  (size_t)n, p);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}

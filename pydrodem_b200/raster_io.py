@@ -1,0 +1,202 @@
+"""Minimal single-band GeoTIFF / .npy raster I/O for the file-path boundary.
+
+pydrodem hands rasters to WhiteboxTools / TauDEM as GeoTIFF paths written by `pyct.npy2tif`
+(tools/convert.py:128-169: one band, `SetNoDataValue`, geotransform + projection copied from a
+stencil).  GDAL is not available in this environment, so this module reads and writes the subset
+that protocol needs: classic or BigTIFF, little endian, one sample per pixel, uncompressed strips
+(or tiles on read), float32/float64/int16/uint8/int32/uint32, the GDAL_NODATA tag (42113) and the
+GeoTIFF georeferencing tags (33550 ModelPixelScale, 33922 ModelTiepoint, 34735-34737 GeoKeys), which
+are carried through verbatim.  Anything else raises.  `.npy` paths are accepted everywhere with a
+`<path>.json` side-car for nodata / georeferencing.
+"""
+import json
+import os
+import struct
+
+import numpy as np
+
+_TYPES = {1: ("B", 1), 2: ("c", 1), 3: ("H", 2), 4: ("I", 4), 5: ("II", 8), 6: ("b", 1), 8: ("h", 2), 9: ("i", 4),
+          11: ("f", 4), 12: ("d", 8), 16: ("Q", 8), 17: ("q", 8), 18: ("Q", 8)}
+_GEO_TAGS = (33550, 33922, 34735, 34736, 34737)
+_SF = {1: {8: np.uint8, 16: np.uint16, 32: np.uint32}, 2: {8: np.int8, 16: np.int16, 32: np.int32},
+       3: {32: np.float32, 64: np.float64}}
+
+
+class RasterMeta(dict):
+    """nodata (float or None), geo (dict tag -> (type, values)), dx, dy convenience."""
+
+    @property
+    def nodata(self):
+        return self.get("nodata")
+
+    @property
+    def pixel_size(self):
+        g = self.get("geo", {}).get(33550)
+        if g:
+            return float(g[1][0]), float(g[1][1])
+        return 1.0, 1.0
+
+
+def _read_ifd(f, big, off):
+    f.seek(off)
+    n = struct.unpack("<Q" if big else "<H", f.read(8 if big else 2))[0]
+    tags = {}
+    for _ in range(n):
+        if big:
+            tag, typ, cnt = struct.unpack("<HHQ", f.read(12))
+            raw = f.read(8)
+        else:
+            tag, typ, cnt = struct.unpack("<HHI", f.read(8))
+            raw = f.read(4)
+        tags[tag] = (typ, cnt, raw)
+    return tags
+
+
+def _tag_values(f, big, entry):
+    typ, cnt, raw = entry
+    fmt, size = _TYPES[typ]
+    total = size * cnt
+    if total <= (8 if big else 4):
+        data = raw[:total]
+    else:
+        off = struct.unpack("<Q" if big else "<I", raw)[0]
+        pos = f.tell()
+        f.seek(off)
+        data = f.read(total)
+        f.seek(pos)
+    if typ == 2:
+        return data.rstrip(b"\x00").decode("ascii", "replace")
+    if typ == 5:
+        v = struct.unpack("<" + "II" * cnt, data)
+        return [v[2 * i] / max(v[2 * i + 1], 1) for i in range(cnt)]
+    return list(struct.unpack("<" + fmt * cnt, data))
+
+
+def read_raster(path):
+    """-> (2-D numpy array, RasterMeta)."""
+    if path.endswith(".npy"):
+        arr = np.load(path)
+        meta = RasterMeta()
+        if os.path.exists(path + ".json"):
+            with open(path + ".json") as fh:
+                meta.update(json.load(fh))
+            meta["geo"] = {int(k): tuple(v) for k, v in meta.get("geo", {}).items()}
+        return arr, meta
+    with open(path, "rb") as f:
+        head = f.read(16)
+        if head[:2] != b"II":
+            raise ValueError(f"{path}: only little-endian TIFF is supported")
+        magic = struct.unpack("<H", head[2:4])[0]
+        big = magic == 43
+        if magic not in (42, 43):
+            raise ValueError(f"{path}: not a TIFF")
+        off = struct.unpack("<Q", head[8:16])[0] if big else struct.unpack("<I", head[4:8])[0]
+        tags = _read_ifd(f, big, off)
+        val = lambda t, d=None: _tag_values(f, big, tags[t]) if t in tags else d  # noqa: E731
+        nx, ny = val(256)[0], val(257)[0]
+        bits, spp = val(258, [1])[0], val(277, [1])[0]
+        comp, fmtc = val(259, [1])[0], val(339, [1])[0]
+        if spp != 1 or comp != 1:
+            raise ValueError(f"{path}: need 1 band, uncompressed (got bands={spp}, compression={comp})")
+        dtype = np.dtype(_SF[fmtc][bits])
+        arr = np.empty((ny, nx), dtype)
+        if 322 in tags:  # tiled
+            tw, th = val(322)[0], val(323)[0]
+            offs = val(324)
+            tx = (nx + tw - 1) // tw
+            for i, o in enumerate(offs):
+                f.seek(o)
+                t = np.frombuffer(f.read(tw * th * dtype.itemsize), dtype).reshape(th, tw)
+                r0, c0 = (i // tx) * th, (i % tx) * tw
+                arr[r0:r0 + th, c0:c0 + tw] = t[:ny - r0, :nx - c0]
+        else:
+            rps = val(278, [ny])[0]
+            offs = val(273)
+            for i, o in enumerate(offs):
+                r0 = i * rps
+                nr = min(rps, ny - r0)
+                f.seek(o)
+                arr[r0:r0 + nr] = np.frombuffer(f.read(nr * nx * dtype.itemsize), dtype).reshape(nr, nx)
+        meta = RasterMeta()
+        nd = val(42113)
+        if nd is not None:
+            try:
+                meta["nodata"] = float(nd)
+            except ValueError:
+                meta["nodata"] = None
+        meta["geo"] = {t: (tags[t][0], val(t)) for t in _GEO_TAGS if t in tags}
+        return arr, meta
+
+
+def write_raster(path, arr, meta=None, nodata=None):
+    """Write a 2-D array as an uncompressed single-strip-per-row-block GeoTIFF (BigTIFF above 3.9 GB)."""
+    arr = np.ascontiguousarray(arr)
+    if arr.ndim != 2:
+        raise ValueError("write_raster needs a 2-D array")
+    meta = RasterMeta(meta or {})
+    if nodata is not None:
+        meta["nodata"] = float(nodata)
+    if path.endswith(".npy"):
+        np.save(path, arr)
+        side = {"nodata": meta.get("nodata"), "geo": {str(k): list(v) for k, v in meta.get("geo", {}).items()}}
+        with open(path + ".json", "w") as fh:
+            json.dump(side, fh)
+        return
+    kind = arr.dtype.kind
+    fmtc = {"u": 1, "i": 2, "f": 3}.get(kind)
+    if fmtc is None or arr.dtype.itemsize * 8 not in _SF[fmtc]:
+        raise ValueError(f"unsupported dtype {arr.dtype}")
+    if arr.dtype.byteorder == ">":
+        arr = arr.astype(arr.dtype.newbyteorder("<"))
+    ny, nx = arr.shape
+    row_bytes = nx * arr.dtype.itemsize
+    rps = max(1, min(ny, (8 << 20) // max(row_bytes, 1)))
+    nstrips = (ny + rps - 1) // rps
+    big = arr.nbytes > 3_900_000_000
+    head = 16 if big else 8
+    offs = [head + i * rps * row_bytes for i in range(nstrips)]
+    cnts = [min(rps, ny - i * rps) * row_bytes for i in range(nstrips)]
+    LONG = 16 if big else 4
+    entries = [(256, 4, [nx]), (257, 4, [ny]), (258, 3, [arr.dtype.itemsize * 8]), (259, 3, [1]), (262, 3, [1]),
+               (273, LONG, offs), (277, 3, [1]), (278, 4, [rps]), (279, LONG, cnts), (284, 3, [1]), (339, 3, [fmtc])]
+    for t, (typ, vals) in sorted(meta.get("geo", {}).items()):
+        entries.append((int(t), int(typ), vals))
+    if meta.get("nodata") is not None:
+        nd = meta["nodata"]
+        entries.append((42113, 2, (repr(int(nd)) if float(nd).is_integer() else repr(float(nd)))))
+    entries.sort(key=lambda e: e[0])
+    ifd_off = head + arr.nbytes
+    ifd_off += ifd_off & 1
+    esize = 20 if big else 12
+    ifd_len = (8 if big else 2) + esize * len(entries) + (8 if big else 4)
+    extra_off = ifd_off + ifd_len
+    ifd, extra = bytearray(), bytearray()
+    ifd += struct.pack("<Q" if big else "<H", len(entries))
+    inline = 8 if big else 4
+    for tag, typ, vals in entries:
+        if typ == 2:
+            data = vals.encode("ascii") + b"\x00"
+            cnt = len(data)
+        else:
+            fmt, _ = _TYPES[typ]
+            data = struct.pack("<" + fmt * len(vals), *vals)
+            cnt = len(vals)
+        ifd += struct.pack("<HHQ" if big else "<HHI", tag, typ, cnt)
+        if len(data) <= inline:
+            ifd += data.ljust(inline, b"\x00")
+        else:
+            if len(extra) & 1:
+                extra += b"\x00"
+            ifd += struct.pack("<Q" if big else "<I", extra_off + len(extra))
+            extra += data
+    ifd += struct.pack("<Q" if big else "<I", 0)
+    with open(path, "wb") as f:
+        if big:
+            f.write(b"II" + struct.pack("<HHHQ", 43, 8, 0, ifd_off))
+        else:
+            f.write(b"II" + struct.pack("<HI", 42, ifd_off))
+        f.write(arr.tobytes() if arr.nbytes < (1 << 30) else memoryview(arr).cast("B"))
+        if (head + arr.nbytes) & 1:
+            f.write(b"\x00")
+        f.write(ifd)
+        f.write(extra)

@@ -1,0 +1,155 @@
+"""Python front of the smoothing stencils (csrc/stencil.cu) with the reference's signatures.
+
+Mirrors `tools/derive.py` (apply_convolve_filter :66, slope_D2 :102, curvature_D2 :133, slope_D4 :176)
+and `tools/build_operators.py` build_kernel :327, plus the smoothing core of
+`CreateDTM.run_tile` (models/dem_noise_removal.py:397-487).  numpy in -> numpy out, torch CUDA
+tensor in -> tensor out; kernels only, no CPU arithmetic on rasters.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .core import _is_torch, _np2d, _stream, _tdev, _tp
+
+
+def build_kernel(weights, dtype=np.int8, normalize=False):
+    """Square ring kernel: weights[0] at the centre, weights[-1] on the outer ring
+    (same construction as tools/build_operators.py:327-351; host-side, a few dozen floats)."""
+    f = len(weights)
+    n = 2 * f - 1
+    w = np.zeros((n, n), dtype=dtype)
+    c = f - 1
+    for ring in range(f - 1, -1, -1):  # paint from the outside in
+        w[c - ring:c + ring + 1, c - ring:c + ring + 1] = weights[ring]
+    if normalize:
+        w = (1. / np.sum(w)) * w
+    return w
+
+
+def _to_dev(a, dtype):
+    import torch
+    if _is_torch(a):
+        return a, False
+    return torch.from_numpy(_np2d(a, dtype)).cuda(), True
+
+
+def apply_convolve_filter(array, kernel, normalize_kernel=False, boundary='symm', mode='same', dtype=np.float32):
+    """scipy.signal.convolve2d(array, kernel, boundary='symm', mode='same') in float32."""
+    import torch
+    if boundary != 'symm' or mode != 'same':
+        raise NotImplementedError("only boundary='symm', mode='same' is on the reference path")
+    kernel = np.asarray(kernel, dtype=np.float64)
+    if normalize_kernel:
+        kernel = (1. / np.sum(kernel)) * kernel
+    k32 = np.ascontiguousarray(kernel, dtype=np.float32)
+    if not _is_torch(array):
+        array = np.asarray(array).astype(np.float32)
+    a, host = _to_dev(array, np.float32)
+    a = _tdev(a, torch.float32, "apply_convolve_filter")
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().hc_conv2d_symm_dev(_lib.context(a.device.index or 0), _tp(a),
+                                                  ctypes.c_void_p(k32.ctypes.data), k32.shape[0], k32.shape[1], _tp(out),
+                                                  a.shape[0], a.shape[1], _stream(a)), "hc_conv2d_symm_dev")
+        torch.cuda.current_stream(a.device).synchronize()  # k32 is host memory read by the async copy
+    if host:
+        return out.cpu().numpy().astype(dtype)
+    return out
+
+
+def _slope(array, dx, dy, d4, unit):
+    import torch
+    a, host = _to_dev(array, np.float32)
+    a = _tdev(a, torch.float32, "slope")
+    deg = torch.empty(a.shape, dtype=torch.int8, device=a.device) if unit == 'degree' else None
+    mag = torch.empty_like(a) if unit != 'degree' else None
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().hc_slope_dev(_lib.context(a.device.index or 0), _tp(a), _tp(deg), _tp(mag), a.shape[0],
+                                            a.shape[1], float(dx), float(dy), int(d4), _stream(a)), "hc_slope_dev")
+    out = deg if unit == 'degree' else mag
+    return out.cpu().numpy() if host else out
+
+
+def slope_D2(array, dx, dy, unit='degree'):
+    return _slope(array, dx, dy, 0, unit)
+
+
+def slope_D4(array, dx, dy, unit='degree'):
+    return _slope(array, dx, dy, 1, unit)
+
+
+def curvature_D2(array, dx, dy, geometric=True):
+    import torch
+    a, host = _to_dev(array, np.float32)
+    a = _tdev(a, torch.float32, "curvature_D2")
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().hc_curvature_d2_dev(_lib.context(a.device.index or 0), _tp(a), _tp(out), a.shape[0],
+                                                   a.shape[1], float(dx), float(dy), int(bool(geometric)), _stream(a)),
+                   "hc_curvature_d2_dev")
+    return out.cpu().numpy() if host else out
+
+
+def mean_std(array):
+    """(mean, population std) in float64 — np.std(curvature) of models/dem_noise_removal.py:413."""
+    import torch
+    a, _ = _to_dev(array, np.float32)
+    a = _tdev(a, torch.float32, "mean_std")
+    m, s = ctypes.c_double(0), ctypes.c_double(0)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().hc_mean_std_dev(_lib.context(a.device.index or 0), _tp(a), a.numel(), ctypes.byref(m),
+                                               ctypes.byref(s), _stream(a)), "hc_mean_std_dev")
+    return float(m.value), float(s.value)
+
+
+DW_WEIGHTS = {  # CreateDTM.setfweights, filtertype 'DW' (models/dem_noise_removal.py:1265-1280)
+    9: [1., 0.8, 0.6, 0.4, 0.2], 7: [1., 0.75, 0.5, 0.25], 5: [1., 0.7, 0.35], 3: [1., 0.5]}
+
+
+def dtm_select(dem, z9, z7, z5, z3, slope0, curv, sigma, curvebreaks=(1.0, 2.5), slopebreaks=(0, 2, 6, 15, 30),
+               swo=None, edm=None, tx=None, artifact=None):
+    """Filter-selection block of CreateDTM.run_tile (:414-471) -> (Zf float32, filter_array int8)."""
+    import torch
+    host = not _is_torch(dem)
+    f32 = [(_to_dev(x, np.float32)[0]) for x in (dem, z9, z7, z5, z3, curv)]
+    s0 = _to_dev(slope0, np.int8)[0]
+    masks = [None if m is None else _to_dev(np.asarray(m, np.uint8) if not _is_torch(m) else m, np.uint8)[0]
+             for m in (swo, edm, tx, artifact)]
+    d = f32[0]
+    zf = torch.empty_like(d)
+    filt = torch.empty(d.shape, dtype=torch.int8, device=d.device)
+    cb = [np.float32(c) * np.float32(sigma) for c in curvebreaks]  # np.float32 scalars, as in the reference
+    sb = (ctypes.c_int * 5)(*[int(v) for v in slopebreaks])
+    with torch.cuda.device(d.device):
+        _lib.check(_lib.load().hc_dtm_select_dev(_lib.context(d.device.index or 0), _tp(f32[0]), _tp(f32[1]), _tp(f32[2]),
+                                                 _tp(f32[3]), _tp(f32[4]), _tp(s0), _tp(f32[5]), _tp(masks[0]),
+                                                 _tp(masks[1]), _tp(masks[2]), _tp(masks[3]), _tp(zf), _tp(filt),
+                                                 d.numel(), float(cb[0]), float(cb[1]), ctypes.cast(sb, ctypes.c_void_p),
+                                                 _stream(d)), "hc_dtm_select_dev")
+    if host:
+        return zf.cpu().numpy(), filt.cpu().numpy()
+    return zf, filt
+
+
+def smooth_core(dem, dx, dy, gdir=4, fweights=None, slopebreaks=(0, 2, 6, 15, 30), curvebreaks=(1.0, 2.5), swo=None,
+                edm=None, tx=None, artifact=None):
+    """Smoothing core of CreateDTM.run_tile (models/dem_noise_removal.py:397-476), device resident:
+    four DW smoothings, slope/curvature of the 5x5 result, global sigma, filter selection, final slope.
+    Returns (Zf float32, filter_array int8, slope_array int8)."""
+    import torch
+    host = not _is_torch(dem)
+    d = _to_dev(dem, np.float32)[0]
+    fweights = fweights or [DW_WEIGHTS[9], DW_WEIGHTS[7], DW_WEIGHTS[5], DW_WEIGHTS[3]]
+    zs = [apply_convolve_filter(d, build_kernel(w, dtype=np.float32, normalize=True)) for w in fweights]
+    s0ind = 2  # 0=9x9, 1=7x7, 2=5x5, 3=3x3: the 5x5 result drives slope/curvature (:147, :405-410)
+    slope0 = (slope_D4 if gdir == 4 else slope_D2)(zs[s0ind], dx, dy)
+    curv = curvature_D2(zs[s0ind], dx, dy)
+    _, sigma = mean_std(curv)
+    sigma32 = np.float32(sigma)
+    zf, filt = dtm_select(d, zs[0], zs[1], zs[2], zs[3], slope0, curv, sigma32, curvebreaks, slopebreaks, swo, edm, tx,
+                          artifact)
+    slope = (slope_D4 if gdir == 4 else slope_D2)(zf, dx, dy)
+    if host:
+        return zf.cpu().numpy(), filt.cpu().numpy(), slope.cpu().numpy()
+    return zf, filt, slope

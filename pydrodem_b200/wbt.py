@@ -1,0 +1,118 @@
+"""`WhiteboxToolsGPU` — a duck type of the `wbt` object pydrodem passes around.
+
+pydrodem builds one `whitebox_tools.WhiteboxTools()` per process (models/depression_handling.py:237-242,
+models/find_sinks.py:47-52) and hands it positionally to `dep.fill_pits(inDEM, wbt, ...)`,
+`dep.create_clump_array(..., wbt, ...)` etc.; every method takes GeoTIFF *paths*.  This class exposes
+the method subset on the depression/D8 path with the exact keyword names the reference uses
+ and runs them on libhydrocore through the C ABI.  Like the real tool it returns 0 on
+success; unlike it, it raises on failure (the reference ignores return codes and only notices a
+missing output file).
+
+Deliberate differences, all stated where they apply:
+  * `fix_flats=True` / `flat_increment>0` (Priority-Flood+epsilon) is order dependent inside
+    WhiteboxTools itself and is not offered on the GPU path: NotImplementedError.
+  * outputs are float32 GeoTIFFs (WhiteboxTools writes float64 and pydrodem narrows them right
+    away with `pyct.tifdowncast`, tools/depressions.py:1306); D8 pointers are int16 with -32768 on
+    nodata cells as WhiteboxTools writes them.
+  * breach_depressions / breach_depressions_least_cost are not built yet.
+"""
+import numpy as np
+
+from . import core, raster_io
+from ._lib import SEED_WBT, TABLE_WBT
+
+
+class WhiteboxToolsGPU:
+    def __init__(self):
+        self.verbose = False
+        self.exe_path = None
+
+    # -- plumbing the reference calls at construction ------------------------------------------------
+    def set_verbose_mode(self, val=True):
+        self.verbose = bool(val)
+        return 0
+
+    def set_whitebox_dir(self, path):
+        self.exe_path = path
+        return 0
+
+    def _say(self, *a):
+        if self.verbose:
+            print(*a)
+
+    @staticmethod
+    def _load(path):
+        arr, meta = raster_io.read_raster(path)
+        nodata = meta.nodata if meta.nodata is not None else -9999.0
+        return arr, meta, float(nodata)
+
+    @staticmethod
+    def _no_eps(fix_flats, flat_increment):
+        if fix_flats or (flat_increment is not None and flat_increment > 0):
+            raise NotImplementedError(
+                "fix_flats / flat_increment > 0 (Priority-Flood+epsilon) is order dependent in WhiteboxTools and is "
+                "not reproduced on the GPU path; pydrodem's default is flat_increment = 0.0 "
+                "(config_files/config_local.ini:161)")
+
+    # -- fills (tools/depressions.py:1277-1286, :1006, :1385) ---------------------------------------
+    def fill_depressions_wang_and_liu(self, dem, output, fix_flats=True, flat_increment=None, callback=None):
+        self._no_eps(fix_flats, flat_increment)
+        z, meta, nodata = self._load(dem)
+        out = core.fill(np.asarray(z, np.float32), nodata=nodata, seed_mode=SEED_WBT)
+        raster_io.write_raster(output, out, meta, nodata=nodata)
+        self._say("fill_depressions_wang_and_liu ->", output)
+        return 0
+
+    def fill_depressions(self, dem, output, fix_flats=True, flat_increment=None, max_depth=None, callback=None):
+        if max_depth is not None:
+            raise NotImplementedError("fill_depressions(max_depth=...) is not built; pydrodem passes None "
+                                      "(tools/depressions.py:1278)")
+        # with fix_flats=False and no depth cap this is the same unique surface as the Wang & Liu tool
+        return self.fill_depressions_wang_and_liu(dem, output, fix_flats=fix_flats, flat_increment=flat_increment)
+
+    # -- single-cell pits (models/depression_handling.py:259-261, models/find_sinks.py:118) ----------
+    def fill_single_cell_pits(self, dem, output, callback=None):
+        z, meta, nodata = self._load(dem)
+        raster_io.write_raster(output, core.fill_single_cell_pits(np.asarray(z, np.float32), nodata), meta, nodata=nodata)
+        return 0
+
+    def breach_single_cell_pits(self, dem, output, callback=None):
+        z, meta, nodata = self._load(dem)
+        raster_io.write_raster(output, core.breach_single_cell_pits(np.asarray(z, np.float32), nodata), meta,
+                               nodata=nodata)
+        return 0
+
+    # -- D8 (run_aws.py:539, :544) ------------------------------------------------------------------
+    def d8_pointer(self, dem, output, esri_pntr=False, callback=None):
+        if esri_pntr:
+            raise NotImplementedError("esri_pntr=True is not used by pydrodem")
+        z, meta, nodata = self._load(dem)
+        dx, dy = meta.pixel_size
+        d = core.d8(np.asarray(z, np.float32), nodata=nodata, dx=dx, dy=dy, table=TABLE_WBT, want_slope=False)
+        p = d.astype(np.int16)
+        p[d == 255] = -32768
+        raster_io.write_raster(output, p, meta, nodata=-32768)
+        return 0
+
+    def d8_flow_accumulation(self, i, output, out_type="cells", log=False, clip=False, pntr=False, esri_pntr=False,
+                             callback=None):
+        if not pntr:
+            raise NotImplementedError("pydrodem calls d8_flow_accumulation with pntr=True (run_aws.py:544)")
+        if out_type != "cells" or log or clip or esri_pntr:
+            raise NotImplementedError("only out_type='cells' without log/clip is on the reference path")
+        p, meta, nodata = self._load(i)
+        d = np.where(p == nodata, 255, p).astype(np.uint8)
+        a = core.accum(d, table=TABLE_WBT).astype(np.float32)
+        a[d == 255] = -32768.0
+        raster_io.write_raster(output, a, meta, nodata=-32768.0)
+        return 0
+
+    # -- not on the GPU path yet --------------------------------------------------------------------
+    def breach_depressions(self, dem, output, max_depth=None, max_length=None, flat_increment=None, fill_pits=False,
+                           callback=None):
+        raise NotImplementedError("breach_depressions (Lindsay 2016) is scheduled after the bandwidth-bound passes "
+                                  "(SURVEY.md §8f-3); it is not built yet")
+
+    def breach_depressions_least_cost(self, dem, output, dist, max_cost=None, min_dist=True, flat_increment=None,
+                                      fill=True, callback=None):
+        raise NotImplementedError("breach_depressions_least_cost is not built yet (SURVEY.md §8f-3)")
