@@ -129,6 +129,47 @@ int hc_dtm_select_dev(hc_ctx *ctx, const float *dem, const float *z9, const floa
                       const uint8_t *edm, const uint8_t *tx, const uint8_t *artifact, float *zf, int8_t *filt,
                       int64_t n, float cbreak0, float cbreak1, const int *slopebreaks5, void *stream);
 
+/* ---- Row-band sharding (BASELINE.json configs[2]: one 40000^2 DEM over 2/4/8 GPUs) ----
+ * A band owns rows [0, nb) of its slice; its rasters carry ONE halo row above (row -1) when
+ * flags & 1 (there is a band above) and below (row nb) when flags & 2.  Pointers passed here
+ * point at own row 0.  Every pass is split into a band-local phase, an exchange the HOST performs
+ * (torch.distributed all_gather over NCCL in pydrodem_b200/bands.py — the library never talks to
+ * another rank) and a finish phase every rank runs on the gathered seam records.  Results are
+ * bit-identical to the whole-raster entry points above.  The equivalent in the reference is the
+ * MPI decomposition inside TauDEM (`mpiexec -n N PitRemove/D8FlowDir/AreaD8`, run_aws.py:584-612).
+ *
+ * fill   local : watershed labels with every seam cell a terminal of its own; publishes <= cap
+ *                (a, b, float-bits w) edges in global node ids (0 = outside,
+ *                1 + (band*2 + side)*nx + col = seam cell): the minimum spanning forest of the
+ *                band's terminal graph + the cross-seam edges of its bottom seam; unused entries 0.
+ *        finish: all_edges = nbands * cap triples (band order); solves the seam graph, writes out.
+ *        Only HC_SEED_TAUDEM (the WBT exterior-nodata rule would need a global labelling). */
+int64_t hc_band_fill_edge_cap(int64_t nx);
+int hc_band_fill_local_dev(hc_ctx *ctx, const float *z, int64_t nb, int64_t nx, float nodata, int seed_mode,
+                           int flags, int64_t band_index, uint32_t *edges_out, void *stream);
+int hc_band_fill_finish_dev(hc_ctx *ctx, const uint32_t *all_edges, int64_t nbands, float *out, void *stream);
+/* D8 on a band (z with halo rows; seam rows are not raster border). */
+int hc_band_d8_dev(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t nb, int64_t nx,
+                   float nodata, double dx, double dy, int table, int flags, void *stream);
+/* flats: begin (fast tier + slow-tier init; z and dirA carry halo rows), then repeat
+ * { relax; get_seams -> exchange -> put_halos } until no band reports `changed`, then finish.
+ * seam record: uint32 [2 sides][3 fields nf,dlo,dhi][nx]; put_halos takes the upper neighbour's
+ * side-1 record as `top` and the lower neighbour's side-0 record as `bot` (NULL where none). */
+int hc_band_flats_begin_dev(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t nb,
+                            int64_t nx, float nodata, int table, int flags, void *stream);
+int hc_band_flats_get_seams_dev(hc_ctx *ctx, uint32_t *out, void *stream);
+int hc_band_flats_put_halos_dev(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int *changed, void *stream);
+int hc_band_flats_relax_dev(hc_ctx *ctx, void *stream);
+int hc_band_flats_finish_dev(hc_ctx *ctx, void *stream);
+/* accumulation: local publishes uint32 [2 sides][2 fields exit_of,bout][nx]; finish takes all bands'
+ * records (band order), solves the seam forest and writes the band's counts. dir carries halo rows. */
+int hc_band_accum_local_dev(hc_ctx *ctx, const uint8_t *dir, int64_t nb, int64_t nx, int table, int flags,
+                            uint32_t *seam_out, void *stream);
+int hc_band_accum_finish_dev(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index,
+                             uint32_t *acc, void *stream);
+/* diagnostics of the last banded fill: terminal-graph edges emitted, MSF rounds, seam-graph rounds */
+int hc_band_stats(const hc_ctx *ctx, int64_t *term_edges, int32_t *msf_rounds, int32_t *global_rounds);
+
 /* HOST-buffer variants (H2D + kernels + D2H inside the call; synchronous). */
 int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
                  int seed_mode);

@@ -46,6 +46,21 @@ SIGNATURES = {
     "hc_fill_d8_accum_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64,
                                              c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "hc_label_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32)]),
+    "hc_band_fill_edge_cap": (c_i64, [c_i64]),
+    "hc_band_fill_local_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, ctypes.c_int, c_i64, c_vp,
+                                              c_vp]),
+    "hc_band_fill_finish_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "hc_band_d8_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64, c_f64, ctypes.c_int,
+                                      ctypes.c_int, c_vp]),
+    "hc_band_flats_begin_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, ctypes.c_int,
+                                               c_vp]),
+    "hc_band_flats_get_seams_dev": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "hc_band_flats_put_halos_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(ctypes.c_int), c_vp]),
+    "hc_band_flats_relax_dev": (ctypes.c_int, [c_vp, c_vp]),
+    "hc_band_flats_finish_dev": (ctypes.c_int, [c_vp, c_vp]),
+    "hc_band_accum_local_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "hc_band_accum_finish_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "hc_band_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "hc_profile_enable": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "hc_profile_read": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "hc_debug_read": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_uint64)]),
@@ -101,6 +116,22 @@ def context(device=0):
                                      f"{lib.hc_last_error().decode('utf-8', 'replace')}")
             h = _ctxs[device] = p
     return h
+
+
+def new_context(device=0):
+    """A private hc_ctx (row bands keep per-band state in their context; several bands can share a
+    device).  The caller owns it: free with destroy_context."""
+    lib = load()
+    p = c_vp()
+    rc = lib.hc_create(ctypes.byref(p), int(device))
+    if rc != 0:
+        raise HydrocoreError(f"hc_create(device={device}) failed (rc={rc}): "
+                             f"{lib.hc_last_error().decode('utf-8', 'replace')}")
+    return p
+
+
+def destroy_context(ctx):
+    load().hc_destroy(ctx)
 
 
 def launch_count(device=0):

@@ -1,0 +1,250 @@
+"""Row-band sharding of the fill -> D8 -> flats -> accumulation chain (BASELINE.json
+configs[2]: one large DEM over the GPUs of a box).
+
+The reference gets its multi-process runs from TauDEM's own MPI decomposition (`mpiexec -n N
+PitRemove / D8FlowDir / AreaD8`, run_aws.py:584-612): the DEM is cut into row bands, one per rank.
+Here a band lives on one GPU; every pass is "band-local phase -> seam exchange -> finish phase":
+
+  fill    local watershed labels with the seam cells as terminals, the terminal graph reduced to its
+          minimum spanning forest (Barnes 2016 with a band as the tile) -> ONE all_gather of <= 5 nx
+          edges per band -> every rank solves the seam graph redundantly and applies the levels;
+  D8      needs the filled halo rows (one all_gather of seam rows);
+  flats   the two geodesic distance fields are relaxed band-locally, seam rows exchanged, repeated
+          until no halo row changes anywhere (all_gather + all_reduce per round);
+  accum   local counts, flow leaving the band parked per seam cell, where inflow entering a seam cell
+          leaves again (Barnes 2017) -> ONE all_gather -> seam forest solved redundantly -> final pass.
+
+All exchanges are all_gathers of seam-sized records (a few nx words), issued through
+torch.distributed (NCCL over NVLink on GPUs); the kernels are the library's hc_band_* entry points.
+A process may hold several consecutive bands (world_size 1 with N bands emulates N ranks on one
+GPU: that is what the single-GPU parity tests do).  Results are bit-identical to the whole-raster
+chain.
+"""
+import ctypes
+
+from . import _lib
+from ._lib import SEED_TAUDEM, TABLE_TAUDEM
+
+
+def split_rows(ny, nbands):
+    """Row counts of `nbands` contiguous bands covering ny rows (first bands one row taller)."""
+    base, extra = divmod(ny, nbands)
+    return [base + (1 if i < extra else 0) for i in range(nbands)]
+
+
+class SeamComm:
+    """all_gather / any-reduce of per-band seam records over the ranks (identity for world 1)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def gather(self, local):
+        """local: [nlocal, ...] -> [world * nlocal, ...] in band order (ranks hold consecutive bands)."""
+        if self.world == 1:
+            return local
+        import torch
+        out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                          device=local.device)
+        self.dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out
+
+    def any(self, flag, device):
+        if self.world == 1:
+            return bool(flag)
+        import torch
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return bool(t.item())
+
+
+class BandedChain:
+    """The chain on this process's bands.  `band_rows`: rows of each LOCAL band (consecutive global
+    bands first_band, first_band+1, ...); `nbands`: bands in the whole DEM."""
+
+    def __init__(self, band_rows, nx, nbands, first_band, device, comm=None, nodata=-9999.0, dx=1.0, dy=1.0,
+                 seed_mode=SEED_TAUDEM, table=TABLE_TAUDEM, flats=True, want_slope=False):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.dev_index = self.device.index or 0
+        self.rows = list(band_rows)
+        self.nx, self.nbands, self.first = int(nx), int(nbands), int(first_band)
+        self.nodata, self.dx, self.dy = float(nodata), float(dx), float(dy)
+        self.seed_mode, self.table, self.flats, self.want_slope = seed_mode, table, bool(flats), bool(want_slope)
+        self.comm = comm if comm is not None else SeamComm()
+        nl = len(self.rows)
+        if self.comm.world * nl != self.nbands:
+            raise ValueError("every rank must hold nbands / world consecutive bands")
+        self.cap = int(self.lib.hc_band_fill_edge_cap(self.nx))
+        self.ctx = [_lib.new_context(self.dev_index) for _ in range(nl)]
+        f32, u8, i32 = torch.float32, torch.uint8, torch.int32
+        mk = lambda nb, dt: torch.empty((nb + 2, self.nx), dtype=dt, device=self.device)  # noqa: E731
+        self.zh = [mk(nb, f32) for nb in self.rows]
+        self.fh = [mk(nb, f32) for nb in self.rows]
+        self.da = [mk(nb, u8) for nb in self.rows]
+        self.db = [mk(nb, u8) for nb in self.rows] if self.flats else self.da
+        self.acc = [torch.empty((nb, self.nx), dtype=i32, device=self.device) for nb in self.rows]
+        self.slope = [torch.empty((nb, self.nx), dtype=f32, device=self.device) for nb in self.rows] \
+            if self.want_slope else [None] * nl
+        self.edges = torch.zeros((nl, self.cap, 3), dtype=i32, device=self.device)
+        self.fseam = torch.zeros((nl, 2, 3, self.nx), dtype=i32, device=self.device)
+        self.aseam = torch.zeros((nl, 2, 2, self.nx), dtype=i32, device=self.device)
+        self.flat_rounds = 0
+
+    def close(self):
+        for c in self.ctx:
+            _lib.destroy_context(c)
+        self.ctx = []
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def flags(self, i):
+        g = self.first + i
+        return (1 if g > 0 else 0) | (2 if g < self.nbands - 1 else 0)
+
+    def z_view(self, i):
+        """Own rows of local band i's input buffer (write the band's DEM here, then run())."""
+        return self.zh[i][1:-1]
+
+    def _p(self, t, row=1):
+        """device pointer to own row 0 of a halo'd buffer (row=1) or to a plain tensor (row=0)."""
+        return ctypes.c_void_p(t.data_ptr() + row * self.nx * t.element_size())
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _halo_exchange(self, bufs):
+        """Fill the halo rows of every local band from its neighbours' seam rows."""
+        torch = self.torch
+        seams = torch.stack([torch.stack((b[1], b[-2])) for b in bufs])  # [nl, 2, nx]
+        allseams = self.comm.gather(seams)
+        for i, b in enumerate(bufs):
+            g = self.first + i
+            if g > 0:
+                b[0].copy_(allseams[g - 1, 1])
+            if g < self.nbands - 1:
+                b[-1].copy_(allseams[g + 1, 0])
+
+    def _chk(self, rc, what):
+        _lib.check(rc, what)
+
+    # ---- the chain -------------------------------------------------------------------------------
+    def run(self, z_list=None):
+        torch, lib, nx = self.torch, self.lib, self.nx
+        nl = len(self.rows)
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            if z_list is not None:
+                for i, z in enumerate(z_list):
+                    self.z_view(i).copy_(z)
+            self._halo_exchange(self.zh)
+            # fill
+            for i, nb in enumerate(self.rows):
+                self._chk(lib.hc_band_fill_local_dev(self.ctx[i], self._p(self.zh[i]), nb, nx, self.nodata, self.seed_mode,
+                                                     self.flags(i), self.first + i, ctypes.c_void_p(self.edges[i].data_ptr()),
+                                                     st), "hc_band_fill_local_dev")
+            all_edges = self.comm.gather(self.edges)
+            for i, nb in enumerate(self.rows):
+                self._chk(lib.hc_band_fill_finish_dev(self.ctx[i], ctypes.c_void_p(all_edges.data_ptr()), self.nbands,
+                                                      self._p(self.fh[i]), st), "hc_band_fill_finish_dev")
+            self._halo_exchange(self.fh)
+            # D8 (+ slope)
+            for i, nb in enumerate(self.rows):
+                sp = ctypes.c_void_p(self.slope[i].data_ptr()) if self.want_slope else None
+                self._chk(lib.hc_band_d8_dev(self.ctx[i], self._p(self.fh[i]), self._p(self.da[i]), sp, nb, nx, self.nodata,
+                                             self.dx, self.dy, self.table, self.flags(i), st), "hc_band_d8_dev")
+            self._halo_exchange(self.da)
+            # flats
+            if self.flats:
+                for i, nb in enumerate(self.rows):
+                    self._chk(lib.hc_band_flats_begin_dev(self.ctx[i], self._p(self.fh[i]), self._p(self.da[i]),
+                                                          self._p(self.db[i]), nb, nx, self.nodata, self.table,
+                                                          self.flags(i), st), "hc_band_flats_begin_dev")
+                self.flat_rounds = 0
+                first = True
+                while True:
+                    if not first:
+                        for i in range(nl):
+                            self._chk(lib.hc_band_flats_relax_dev(self.ctx[i], st), "hc_band_flats_relax_dev")
+                        self.flat_rounds += 1
+                    for i in range(nl):
+                        self._chk(lib.hc_band_flats_get_seams_dev(self.ctx[i], ctypes.c_void_p(self.fseam[i].data_ptr()), st),
+                                  "hc_band_flats_get_seams_dev")
+                    allf = self.comm.gather(self.fseam)
+                    changed = False
+                    for i in range(nl):
+                        g = self.first + i
+                        top = ctypes.c_void_p(allf[g - 1, 1].data_ptr()) if g > 0 else None
+                        bot = ctypes.c_void_p(allf[g + 1, 0].data_ptr()) if g < self.nbands - 1 else None
+                        ch = ctypes.c_int(0)
+                        self._chk(lib.hc_band_flats_put_halos_dev(self.ctx[i], top, bot, ctypes.byref(ch), st),
+                                  "hc_band_flats_put_halos_dev")
+                        changed = changed or bool(ch.value)
+                    changed = self.comm.any(changed, self.device)
+                    if not first and not changed:
+                        break
+                    first = False
+                    if self.flat_rounds > 100000:
+                        raise _lib.HydrocoreError("banded flats did not converge")
+                for i in range(nl):
+                    self._chk(lib.hc_band_flats_finish_dev(self.ctx[i], st), "hc_band_flats_finish_dev")
+                self._halo_exchange(self.db)
+            # accumulation
+            for i, nb in enumerate(self.rows):
+                self._chk(lib.hc_band_accum_local_dev(self.ctx[i], self._p(self.db[i]), nb, nx, self.table, self.flags(i),
+                                                      ctypes.c_void_p(self.aseam[i].data_ptr()), st),
+                          "hc_band_accum_local_dev")
+            alls = self.comm.gather(self.aseam)
+            for i, nb in enumerate(self.rows):
+                self._chk(lib.hc_band_accum_finish_dev(self.ctx[i], ctypes.c_void_p(alls.data_ptr()), self.nbands,
+                                                       self.first + i, ctypes.c_void_p(self.acc[i].data_ptr()), st),
+                          "hc_band_accum_finish_dev")
+        return [(self.fh[i][1:-1], self.db[i][1:-1], self.slope[i], self.acc[i]) for i in range(nl)]
+
+    def launches(self):
+        return sum(int(self.lib.hc_launch_count(c)) for c in self.ctx)
+
+    def stats(self):
+        out = []
+        for c in self.ctx:
+            te, mr, gr = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0)
+            self.lib.hc_band_stats(c, ctypes.byref(te), ctypes.byref(mr), ctypes.byref(gr))
+            out.append({"term_edges": int(te.value), "msf_rounds": int(mr.value), "seam_rounds": int(gr.value)})
+        return out
+
+
+def fill_d8_accum_banded(z, nbands, nodata=-9999.0, dx=1.0, dy=1.0, table=TABLE_TAUDEM, flats=True, want_slope=True):
+    """Whole-raster convenience: cut `z` (2-D torch CUDA tensor or numpy array) into `nbands` row bands on one
+    device, run the banded chain, and stitch the results.  Same return as core.fill_d8_accum."""
+    import numpy as np
+    import torch
+    host = not type(z).__module__.startswith("torch")
+    zt = torch.from_numpy(np.ascontiguousarray(z, dtype=np.float32)).cuda() if host else z
+    ny, nx = zt.shape
+    rows = split_rows(ny, nbands)
+    ch = BandedChain(rows, nx, nbands, 0, zt.device, nodata=nodata, dx=dx, dy=dy, table=table, flats=flats,
+                     want_slope=want_slope)
+    try:
+        r0 = 0
+        zs = []
+        for nb in rows:
+            zs.append(zt[r0:r0 + nb])
+            r0 += nb
+        res = ch.run(zs)
+        f = torch.cat([r[0] for r in res])
+        d = torch.cat([r[1] for r in res])
+        s = torch.cat([r[2] for r in res]) if want_slope else None
+        a = torch.cat([r[3] for r in res])
+        torch.cuda.synchronize()
+        ch.last_stats = ch.stats()
+        fill_d8_accum_banded.last_stats = ch.last_stats
+        fill_d8_accum_banded.last_flat_rounds = ch.flat_rounds
+    finally:
+        ch.close()
+    if host:
+        return (f.cpu().numpy(), d.cpu().numpy(), s.cpu().numpy() if s is not None else None,
+                a.cpu().numpy().view(np.uint32))
+    return f, d, s, a

@@ -32,6 +32,8 @@
 #define NOSLOT 0xFFFFu
 #define DN_NONE 0xFFFFu  // no downstream inside or outside the tile (terminal)
 #define DN_EXIT 0xFFFEu  // downstream is a valid cell of another tile
+// pdown of a slot whose downstream cell lies in a neighbouring BAND: top bit | side << 30 | column
+#define BAND_EXIT 0x80000000u
 
 __device__ __forceinline__ int perim_slot(int lr, int lc, int hr, int hc) {
   if (lr == 0) return lc;
@@ -45,7 +47,7 @@ template <int TABLE, bool FINAL>
 __global__ void __launch_bounds__(NTHREADS)
 k_acc_tile(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsigned short *__restrict__ pexit,
            u32 *__restrict__ pdown, u32 *__restrict__ pinflow, uint32_t *__restrict__ acc, int ny, int nx,
-           unsigned long long *dbg) {
+           unsigned long long *dbg, hc_rows rw) {
   // 32-bit shared-memory atomics only (64-bit ones are CAS spin loops):
   //   local pass : st = [count:24 | pending:8]  (an in-tile count is at most 4096)
   //   final pass : counts reach 2^31, so count (sacc) and pending counter (st) are separate words
@@ -66,8 +68,8 @@ k_acc_tile(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsigned s
   for (int i = tid; i < TH * TH; i += NTHREADS) {
     int lr = i / TH, lc = i - lr * TH;
     int r = r0 + lr - 1, c = c0 + lc - 1;
-    bool inb = r >= 0 && r < ny && c >= 0 && c < nx;
-    uint8_t d = __ldg(&dir[inb ? (size_t)r * nx + c : 0]);
+    bool inb = r >= rw.rlo && r < rw.rhi && c >= 0 && c < nx;
+    uint8_t d = __ldg(dir + (inb ? (long long)r * nx + c : 0));  // r = -1 / ny: a band's halo rows
     sd[i] = inb ? d : (uint8_t)HC_DIR_NODATA;
   }
   __syncthreads();
@@ -167,10 +169,14 @@ k_acc_tile(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsigned s
       if (dn[my_cell] == DN_EXIT) {
         int k = d_code_to_k(TABLE, sd[(lr + 1) * TH + lc + 1]);
         int gr = r0 + lr + c_dr[TABLE][k], gc = c0 + lc + c_dc[TABLE][k];
-        int tyy = gr / T, txx = gc / T;
-        int hr2 = min(T, ny - tyy * T), hc2 = min(T, nx - txx * T);
-        int s2 = perim_slot(gr - tyy * T, gc - txx * T, hr2, hc2);
-        my_down = (u32)((tyy * gridDim.x + txx) * PSLOTS + s2);
+        if (gr < 0) my_down = BAND_EXIT | (u32)gc;
+        else if (gr >= ny) my_down = BAND_EXIT | 0x40000000u | (u32)gc;
+        else {
+          int tyy = gr / T, txx = gc / T;
+          int hr2 = min(T, ny - tyy * T), hc2 = min(T, nx - txx * T);
+          int s2 = perim_slot(gr - tyy * T, gc - txx * T, hr2, hc2);
+          my_down = (u32)((tyy * gridDim.x + txx) * PSLOTS + s2);
+        }
         my_state = (u64)(st[my_cell] >> 8) << 16;  // [local count : 48 | feeders : 16]
       }
     }
@@ -209,7 +215,7 @@ k_acc_link_count(u64 *pstate, const unsigned short *__restrict__ pexit, const u3
   size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nslots) return;
   u32 e = pdown[s];
-  if (e == HC_NONE) return;
+  if (e == HC_NONE || (e & BAND_EXIT)) return;
   unsigned short x2 = pexit[e];
   if (x2 == NOSLOT) return;
   atomicAdd(&pstate[(size_t)(e / PSLOTS) * PSLOTS + x2], 1ull);
@@ -228,7 +234,7 @@ k_acc_link_mark(u64 *pstate, const u32 *__restrict__ pdown, size_t nslots) {
 // B2: dependency walk over tile crossings
 __global__ void __launch_bounds__(256)
 k_acc_link_walk(u64 *pstate, const unsigned short *__restrict__ pexit, const u32 *__restrict__ pdown,
-                u32 *pinflow, size_t nslots) {
+                u32 *pinflow, size_t nslots, u32 *bout, int nx) {
   size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nslots) return;
   if (pdown[s] == HC_NONE) return;
@@ -238,6 +244,10 @@ k_acc_link_walk(u64 *pstate, const unsigned short *__restrict__ pexit, const u32
   size_t x = s;
   for (;;) {
     u32 e = pdown[x];
+    if (e & BAND_EXIT) {  // leaves the band: credit the neighbouring band's seam cell
+      atomicAdd(&bout[(size_t)((e >> 30) & 1u) * nx + (e & 0x3FFFFFFFu)], (u32)total);
+      return;
+    }
     atomicAdd(&pinflow[e], (u32)total);
     unsigned short x2 = pexit[e];
     if (x2 == NOSLOT) return;
@@ -254,19 +264,25 @@ size_t accum_workspace(int64_t ny, int64_t nx) {
   return hc_align(tiles * PSLOTS * 8) + hc_align(tiles * PSLOTS * 2) + 2 * hc_align(tiles * PSLOTS * 4);
 }
 
+// phases A + B (tile-local counts, then the walk over tile crossings); state left in ctx->band
 template <int TABLE>
-static int accum_impl(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_t nx, cudaStream_t st) {
+static int accum_local_impl(hc_ctx *ctx, const uint8_t *dir, int64_t ny, int64_t nx, hc_rows rw, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
   const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t nslots = (size_t)tx * ty * PSLOTS;
   u64 *pstate = (u64 *)arena_take(ctx, nslots * 8);
   unsigned short *pexit = (unsigned short *)arena_take(ctx, nslots * 2);
   u32 *pdown = (u32 *)arena_take(ctx, nslots * 4);
   u32 *pinflow = (u32 *)arena_take(ctx, nslots * 4);
-  if (!pstate || !pexit || !pdown || !pinflow) return HC_ERR_NOMEM;
+  u32 *bout = (u32 *)arena_take(ctx, (size_t)2 * nx * 4);
+  if (!pstate || !pexit || !pdown || !pinflow || !bout) return HC_ERR_NOMEM;
+  bs->pstate = pstate; bs->pexit = pexit; bs->pdown = pdown; bs->pinflow = pinflow; bs->bout = bout;
+  bs->dir = dir; bs->nb = ny; bs->nx = nx;
+  if (rw.top || rw.bot) HC_CUDA(cudaMemsetAsync(bout, 0, (size_t)2 * nx * 4, st));
   dim3 tg(tx, ty);
   unsigned sb = (unsigned)((nslots + 255) / 256);
   HC_PROF(ctx, st, "k_acc_tile_local");
-  k_acc_tile<TABLE, false><<<tg, NTHREADS, 0, st>>>(dir, pstate, pexit, pdown, pinflow, acc, (int)ny, (int)nx, ctx->d_dbg);
+  k_acc_tile<TABLE, false><<<tg, NTHREADS, 0, st>>>(dir, pstate, pexit, pdown, pinflow, nullptr, (int)ny, (int)nx, ctx->d_dbg, rw);
   HC_LAUNCH_CHECK(ctx);
   HC_PROF(ctx, st, "k_acc_link_count");
   k_acc_link_count<<<sb, 256, 0, st>>>(pstate, pexit, pdown, nslots);
@@ -275,10 +291,18 @@ static int accum_impl(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny
   k_acc_link_mark<<<sb, 256, 0, st>>>(pstate, pdown, nslots);
   HC_LAUNCH_CHECK(ctx);
   HC_PROF(ctx, st, "k_acc_link_walk");
-  k_acc_link_walk<<<sb, 256, 0, st>>>(pstate, pexit, pdown, pinflow, nslots);
+  k_acc_link_walk<<<sb, 256, 0, st>>>(pstate, pexit, pdown, pinflow, nslots, bout, (int)nx);
   HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+template <int TABLE>
+static int accum_final_impl(hc_ctx *ctx, uint32_t *acc, hc_rows rw, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  const int64_t ny = bs->nb, nx = bs->nx;
+  dim3 tg((unsigned)((nx + T - 1) / T), (unsigned)((ny + T - 1) / T));
   HC_PROF(ctx, st, "k_acc_tile_final");
-  k_acc_tile<TABLE, true><<<tg, NTHREADS, 0, st>>>(dir, pstate, pexit, pdown, pinflow, acc, (int)ny, (int)nx, ctx->d_dbg);
+  k_acc_tile<TABLE, true><<<tg, NTHREADS, 0, st>>>(bs->dir, bs->pstate, bs->pexit, bs->pdown, bs->pinflow, acc, (int)ny, (int)nx, ctx->d_dbg, rw);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
@@ -288,6 +312,201 @@ int accum_run(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_
   if (ny <= 0 || nx <= 0) return HC_OK;
   if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("accum: bad table %d", table); return HC_ERR_ARG; }
   HC_TRY(arena_reset(ctx));
-  if (table == HC_TABLE_WBT) return accum_impl<HC_TABLE_WBT>(ctx, dir, acc, ny, nx, st);
-  return accum_impl<HC_TABLE_TAUDEM>(ctx, dir, acc, ny, nx, st);
+  hc_rows rw = hc_make_rows(ny, 0);
+  if (table == HC_TABLE_WBT) {
+    HC_TRY(accum_local_impl<HC_TABLE_WBT>(ctx, dir, ny, nx, rw, st));
+    return accum_final_impl<HC_TABLE_WBT>(ctx, acc, rw, st);
+  }
+  HC_TRY(accum_local_impl<HC_TABLE_TAUDEM>(ctx, dir, ny, nx, rw, st));
+  return accum_final_impl<HC_TABLE_TAUDEM>(ctx, acc, rw, st);
+}
+
+// ================================================================================================
+// row bands (the one-exchange scheme of Barnes 2017 with a band as the unit).
+//   local   phases A + B with flow that leaves the band parked in bout[side][col] (credited to the
+//           neighbouring band's seam cell); then, for every own seam cell, the walk over tile
+//           crossings tells where a unit of inflow arriving there leaves the band again (exit_of).
+//           The band publishes seam_out[side][{exit_of, bout}][nx].
+//   finish  every rank solves the forest over all seam cells (X = inflow a seam cell receives from
+//           the other side = neighbour's bout + sum of X of the seam cells that exit into it), adds
+//           X along each own seam cell's path through the tile-entry slots, and runs phase C.
+// Integer adds only => identical to the whole-raster result.
+// ================================================================================================
+#define SEAM_NONE 0xFFFFFFFFu
+
+__global__ void __launch_bounds__(256)
+k_acc_seam_exit(const unsigned short *__restrict__ pexit, const u32 *__restrict__ pdown, const uint8_t *__restrict__ dir,
+                int ny, int nx, int tx, hc_rows rw, u32 *__restrict__ seam_out, const u32 *__restrict__ bout, u32 *err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * nx) return;
+  const int side = i / nx, c = i - side * nx;
+  u32 *o = seam_out + (size_t)side * 2 * nx;
+  o[nx + c] = bout[i];
+  u32 ex = SEAM_NONE;
+  if ((side == 0 && rw.top) || (side == 1 && rw.bot)) {
+    const int r = side ? ny - 1 : 0;
+    if (dir[(size_t)r * nx + c] != HC_DIR_NODATA) {
+      int tyy = r / T, txx = c / T;
+      int hr = min(T, ny - tyy * T), hc = min(T, nx - txx * T);
+      u32 t = (u32)(tyy * tx + txx);
+      int s = perim_slot(r - tyy * T, c - txx * T, hr, hc);
+      for (int hop = 0;; hop++) {
+        if (hop > (1 << 26)) { *err = 1u; break; }  // a cycle: not a D8 forest
+        unsigned short x = pexit[(size_t)t * PSLOTS + s];
+        if (x == NOSLOT) break;
+        u32 d = pdown[(size_t)t * PSLOTS + x];
+        if (d & BAND_EXIT) { ex = d & 0x7FFFFFFFu; break; }  // side << 30 | column of the receiving cell
+        t = d / PSLOTS;
+        s = (int)(d % PSLOTS);
+      }
+    }
+  }
+  o[c] = ex;
+}
+
+// global seam forest.  Node g = (band*2 + side)*nx + c.  all[band][side][{exit_of,bout}][nx].
+__device__ __forceinline__ long long seam_recv(u32 ex, long long band, int nx) {
+  // exit through the top (side bit 0) lands on the bottom seam of band-1, through the bottom on the top of band+1
+  int via_bottom = (ex >> 30) & 1;
+  long long col = ex & 0x3FFFFFFFu;
+  return via_bottom ? ((band + 1) * 2 + 0) * (long long)nx + col : ((band - 1) * 2 + 1) * (long long)nx + col;
+}
+
+__global__ void k_seam_init(const u32 *__restrict__ all, int nbands, int nx, u64 *__restrict__ state) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = (long long)nbands * 2 * nx;
+  if (g >= M) return;
+  long long band = g / (2ll * nx);
+  int side = (int)((g / nx) & 1), c = (int)(g % nx);
+  // inflow from the neighbouring band's local sources: its bout record aimed at me
+  long long nb_band = side ? band + 1 : band - 1;
+  u64 x0 = 0;
+  if (nb_band >= 0 && nb_band < nbands) x0 = all[((size_t)nb_band * 2 + (side ? 0 : 1)) * 2 * nx + nx + c];
+  state[g] = x0 << 24;
+}
+__global__ void k_seam_count(const u32 *__restrict__ all, int nbands, int nx, u64 *__restrict__ state) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = (long long)nbands * 2 * nx;
+  if (g >= M) return;
+  long long band = g / (2ll * nx);
+  int side = (int)((g / nx) & 1), c = (int)(g % nx);
+  u32 ex = all[((size_t)band * 2 + side) * 2 * nx + c];
+  if (ex == SEAM_NONE) return;
+  long long t = seam_recv(ex, band, nx);
+  if (t < 0 || t >= M) return;
+  atomicAdd(&state[t], 1ull);
+}
+__global__ void k_seam_mark(const u32 *__restrict__ all, int nbands, int nx, u64 *__restrict__ state) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = (long long)nbands * 2 * nx;
+  if (g >= M) return;
+  u64 w = state[g];
+  if ((w & 0xFFFFFFull) == 0) state[g] = w | 0xFFFFFFull;  // a source of the seam walk
+}
+__global__ void k_seam_walk(const u32 *__restrict__ all, int nbands, int nx, u64 *__restrict__ state) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = (long long)nbands * 2 * nx;
+  if (g >= M) return;
+  u64 w = state[g];
+  if ((w & 0xFFFFFFull) != 0xFFFFFFull) return;
+  u64 total = w >> 24;
+  long long x = g;
+  for (;;) {
+    long long band = x / (2ll * nx);
+    int side = (int)((x / nx) & 1), c = (int)(x % nx);
+    u32 ex = all[((size_t)band * 2 + side) * 2 * nx + c];
+    if (ex == SEAM_NONE) return;
+    long long t = seam_recv(ex, band, nx);
+    if (t < 0 || t >= M) return;
+    u64 old = atomicAdd(&state[t], (total << 24) - 1ull);
+    if ((old & 0xFFFFFFull) != 1ull) return;
+    total += old >> 24;
+    x = t;
+  }
+}
+
+// add X (inflow from the other band) along an own seam cell's path through the tile-entry slots
+__global__ void __launch_bounds__(256)
+k_acc_seam_apply(const unsigned short *__restrict__ pexit, const u32 *__restrict__ pdown, u32 *pinflow,
+                 const uint8_t *__restrict__ dir, int ny, int nx, int tx, hc_rows rw, const u64 *__restrict__ state,
+                 long long gbase) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * nx) return;
+  const int side = i / nx, c = i - side * nx;
+  if (!((side == 0 && rw.top) || (side == 1 && rw.bot))) return;
+  u32 X = (u32)(state[gbase + i] >> 24);
+  if (!X) return;
+  const int r = side ? ny - 1 : 0;
+  if (dir[(size_t)r * nx + c] == HC_DIR_NODATA) return;
+  int tyy = r / T, txx = c / T;
+  int hr = min(T, ny - tyy * T), hc = min(T, nx - txx * T);
+  u32 t = (u32)(tyy * tx + txx);
+  int s = perim_slot(r - tyy * T, c - txx * T, hr, hc);
+  for (;;) {
+    atomicAdd(&pinflow[(size_t)t * PSLOTS + s], X);
+    unsigned short x = pexit[(size_t)t * PSLOTS + s];
+    if (x == NOSLOT) return;
+    u32 d = pdown[(size_t)t * PSLOTS + x];
+    if (d & BAND_EXIT) return;
+    t = d / PSLOTS;
+    s = (int)(d % PSLOTS);
+  }
+}
+
+int band_accum_local(hc_ctx *ctx, const uint8_t *dir, int64_t nb, int64_t nx, int table, int flags,
+                     uint32_t *seam_out, cudaStream_t st) {
+  if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("accum: bad table %d", table); return HC_ERR_ARG; }
+  if (nx >= (1 << 30)) { hc_set_error("band too wide"); return HC_ERR_TOO_LARGE; }
+  HC_TRY(arena_reset(ctx));
+  hc_band_state *bs = &ctx->band;
+  hc_rows rw = hc_make_rows(nb, flags);
+  bs->flags = flags; bs->table = table;
+  if (table == HC_TABLE_WBT) HC_TRY(accum_local_impl<HC_TABLE_WBT>(ctx, dir, nb, nx, rw, st));
+  else HC_TRY(accum_local_impl<HC_TABLE_TAUDEM>(ctx, dir, nb, nx, rw, st));
+  if (!(flags & 3)) HC_CUDA(cudaMemsetAsync(bs->bout, 0, (size_t)2 * nx * 4, st));
+  u32 *err = (u32 *)arena_take(ctx, 256);
+  if (!err) return HC_ERR_NOMEM;
+  HC_CUDA(cudaMemsetAsync(err, 0, 4, st));
+  const int tx = (int)((nx + T - 1) / T);
+  HC_PROF(ctx, st, "k_acc_seam_exit");
+  k_acc_seam_exit<<<(unsigned)((2 * nx + 255) / 256), 256, 0, st>>>(bs->pexit, bs->pdown, dir, (int)nb, (int)nx, tx, rw, seam_out, bs->bout, err);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, err, 4, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  if (ctx->h_mail[0]) { hc_set_error("band accumulation: the direction raster contains a cycle"); return HC_ERR_ARG; }
+  bs->acc_ready = 1;
+  return HC_OK;
+}
+
+int band_accum_finish(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index, uint32_t *acc,
+                      cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  if (!bs->acc_ready) { hc_set_error("hc_band_accum_finish without hc_band_accum_local"); return HC_ERR_ARG; }
+  bs->acc_ready = 0;
+  const int64_t nb = bs->nb, nx = bs->nx;
+  hc_rows rw = hc_make_rows(nb, bs->flags);
+  if (bs->flags & 3) {
+    const long long M = (long long)nbands * 2 * nx;
+    u64 *state = (u64 *)arena_take(ctx, (size_t)M * 8);
+    if (!state) return HC_ERR_NOMEM;
+    unsigned gb = (unsigned)((M + 255) / 256);
+    HC_PROF(ctx, st, "k_seam_init");
+    k_seam_init<<<gb, 256, 0, st>>>(all_seams, (int)nbands, (int)nx, state);
+    HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_seam_count");
+    k_seam_count<<<gb, 256, 0, st>>>(all_seams, (int)nbands, (int)nx, state);
+    HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_seam_mark");
+    k_seam_mark<<<gb, 256, 0, st>>>(all_seams, (int)nbands, (int)nx, state);
+    HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_seam_walk");
+    k_seam_walk<<<gb, 256, 0, st>>>(all_seams, (int)nbands, (int)nx, state);
+    HC_LAUNCH_CHECK(ctx);
+    const int tx = (int)((nx + T - 1) / T);
+    HC_PROF(ctx, st, "k_acc_seam_apply");
+    k_acc_seam_apply<<<(unsigned)((2 * nx + 255) / 256), 256, 0, st>>>(bs->pexit, bs->pdown, bs->pinflow, bs->dir, (int)nb, (int)nx, tx, rw, state, (long long)band_index * 2 * nx);
+    HC_LAUNCH_CHECK(ctx);
+  }
+  if (bs->table == HC_TABLE_WBT) return accum_final_impl<HC_TABLE_WBT>(ctx, acc, rw, st);
+  return accum_final_impl<HC_TABLE_TAUDEM>(ctx, acc, rw, st);
 }

@@ -51,6 +51,26 @@ void hc_set_error(const char *fmt, ...);
     }                                                                                   \
   } while (0)
 
+// Row-band sharding: a band's rasters carry one halo row above (row -1) and below (row nb) when the
+// band has a neighbour there.  Kernels may READ rows [rlo, rhi); they own rows [0, nb).
+struct hc_rows { int rlo, rhi, top, bot; };
+static inline hc_rows hc_make_rows(int64_t nb, int flags) {
+  hc_rows rw = {(flags & 1) ? -1 : 0, (int)nb + ((flags & 2) ? 1 : 0), flags & 1, (flags >> 1) & 1};
+  return rw;
+}
+
+// state a band keeps between the phases of one pass (pointers into the arena)
+struct hc_band_state {
+  int flags; int64_t nb, nx, band_index;
+  // fill
+  int fill_ready; const float *z; u32 *P; float *level0; u32 *troot; u32 K1, nopen; u32 *cnt;
+  // flats
+  int flats_ready, table; float nodata; const float *fz; const uint8_t *dirA; uint8_t *dirB;
+  uint8_t *pending, *active, *dA, *dB, *nf; u32 *dlo, *dhi, *flag; int n_pending;
+  // accumulation
+  int acc_ready; const uint8_t *dir; unsigned long long *pstate; unsigned short *pexit; u32 *pdown, *pinflow, *bout;
+};
+
 #define HC_MAX_BLOCKS 64
 struct hc_block { char *p; size_t cap, off; };
 
@@ -68,6 +88,10 @@ struct hc_ctx {
   // stats of the last fill
   int64_t fill_basins;
   int32_t fill_rounds;
+  // band diagnostics: terminal-graph edges emitted, MSF rounds, global seam-graph rounds
+  int64_t band_term_edges;
+  int32_t band_msf_rounds, band_global_rounds;
+  hc_band_state band;
   // grow-only device staging buffers of the *_host entry points (z, filled, dir, slope, acc)
   void *io[5];
   size_t io_cap[5];
@@ -133,4 +157,21 @@ size_t accum_workspace(int64_t ny, int64_t nx);
 int label_run(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn, int32_t *nlab,
               cudaStream_t st);
 size_t label_workspace(int64_t ny, int64_t nx);
+// row-band phases (band.cu holds the extern "C" wrappers)
+int64_t band_fill_edge_cap(int64_t nx);
+int band_fill_local(hc_ctx *ctx, const float *z, int64_t nb, int64_t nx, float nodata, int seed_mode, int flags,
+                    int64_t band_index, uint32_t *edges_out, cudaStream_t st);
+int band_fill_finish(hc_ctx *ctx, const uint32_t *all_edges, int64_t nbands, float *out, cudaStream_t st);
+int d8_run_rows(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx, float nodata,
+                double dx, double dy, int table, hc_rows rw, cudaStream_t st);
+int band_flats_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t nb, int64_t nx,
+                     float nodata, int table, int flags, cudaStream_t st);
+int band_flats_get_seams(hc_ctx *ctx, uint32_t *out, cudaStream_t st);
+int band_flats_put_halos(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int *changed, cudaStream_t st);
+int band_flats_relax(hc_ctx *ctx, cudaStream_t st);
+int band_flats_finish(hc_ctx *ctx, cudaStream_t st);
+int band_accum_local(hc_ctx *ctx, const uint8_t *dir, int64_t nb, int64_t nx, int table, int flags,
+                     uint32_t *seam_out, cudaStream_t st);
+int band_accum_finish(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index, uint32_t *acc,
+                      cudaStream_t st);
 int scp_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata, int breach, cudaStream_t st);

@@ -21,7 +21,7 @@ struct d8_params {
 template <int TABLE, bool SLOPE>
 __global__ void __launch_bounds__(D8_THREADS)
 k_d8(const float *__restrict__ z, uint8_t *__restrict__ dir, float *__restrict__ slope, int ny, int nx,
-     float nodata, d8_params prm) {
+     float nodata, d8_params prm, hc_rows rw) {
   const int c = blockIdx.x * D8_THREADS + threadIdx.x;
   if (c >= nx) return;
   const int rbeg = blockIdx.y * D8_RS, rend = min(rbeg + D8_RS, ny);
@@ -29,8 +29,8 @@ k_d8(const float *__restrict__ z, uint8_t *__restrict__ dir, float *__restrict__
   const bool hasl = c > 0, hasr = c < nx - 1;
   auto ld3 = [&](int r, float &l, float &m, float &rr) {
     l = m = rr = qnan;
-    if (r < 0 || r >= ny) return;
-    const float *row = z + (size_t)r * nx + c;
+    if (r < rw.rlo || r >= rw.rhi) return;
+    const float *row = z + ((long long)r * nx + c);  // r = -1 / ny: a band's halo rows
     float vm = __ldg(row);
     float vl = hasl ? __ldg(row - 1) : qnan;
     float vr = hasr ? __ldg(row + 1) : qnan;
@@ -87,6 +87,11 @@ k_d8(const float *__restrict__ z, uint8_t *__restrict__ dir, float *__restrict__
 
 int d8_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx, float nodata,
            double dx, double dy, int table, cudaStream_t st) {
+  return d8_run_rows(ctx, z, dir, slope, ny, nx, nodata, dx, dy, table, hc_make_rows(ny, 0), st);
+}
+
+int d8_run_rows(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx, float nodata,
+                double dx, double dy, int table, hc_rows rw, cudaStream_t st) {
   if (ny <= 0 || nx <= 0) return HC_OK;
   if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("d8: bad table %d", table); return HC_ERR_ARG; }
   if (!(dx > 0) || !(dy > 0)) { hc_set_error("d8: dx, dy must be > 0"); return HC_ERR_ARG; }
@@ -100,11 +105,11 @@ int d8_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, 
   }
   dim3 grid((unsigned)((nx + D8_THREADS - 1) / D8_THREADS), (unsigned)((ny + D8_RS - 1) / D8_RS));
   if (table == HC_TABLE_WBT) {
-    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }
-    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }
+    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm, rw); }
+    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm, rw); }
   } else {
-    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }
-    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm); }
+    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm, rw); }
+    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm, rw); }
   }
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;

@@ -41,7 +41,7 @@
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS)
 k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restrict__ P, int ny, int nx,
-      float nodata, u32 *__restrict__ pit_counter) {
+      float nodata, u32 *__restrict__ pit_counter, hc_rows rw, u32 idbase, uint8_t *__restrict__ seam_seed) {
   __shared__ float sz[TH * TH];
   __shared__ unsigned short snxt[T * T];
   __shared__ u32 stv[T * T];
@@ -55,8 +55,8 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
     int lr = i / TH, lc = i - lr * TH;
     int r = r0 + lr - 1, c = c0 + lc - 1;
     float v = __int_as_float(0x7fc00000);
-    if (r >= 0 && r < ny && c >= 0 && c < nx) {
-      v = __ldg(&z[(size_t)r * nx + c]);
+    if (r >= rw.rlo && r < rw.rhi && c >= 0 && c < nx) {
+      v = __ldg(z + ((long long)r * nx + c));  // r may be -1 / ny: the band's halo rows
       if (v == nodata) v = __int_as_float(0x7fc00000);
     }
     sz[i] = v;
@@ -72,7 +72,9 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
     if (r < ny && c < nx) {
       float v = sz[(lr + 1) * TH + lc + 1];
       if (v == v) {
-        bool seed = (r == 0 || c == 0 || r == ny - 1 || c == nx - 1);
+        // a band's seam rows (first / last own row next to another band) are not raster border
+        const bool seam_t = rw.top && r == 0, seam_b = rw.bot && r == ny - 1;
+        bool seed = ((r == 0 && !rw.top) || c == 0 || (r == ny - 1 && !rw.bot) || c == nx - 1);
         float bz = v;
         int bdr = 0, bdc = 0;
 #pragma unroll
@@ -84,7 +86,7 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
             if (zn != zn) {
               // nodata neighbour: seed if that nodata is exterior (ext == NULL: all nodata is)
               int rr = r + dr, cc = c + dc;
-              if (rr >= 0 && rr < ny && cc >= 0 && cc < nx) {
+              if (rr >= rw.rlo && rr < rw.rhi && cc >= 0 && cc < nx) {
                 if (ext == nullptr || ext[(size_t)rr * nx + cc]) seed = true;
               }
               continue;
@@ -93,7 +95,13 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
             bool lower = zn < bz || (zn == bz && (dr < bdr || (dr == bdr && dc < bdc)));
             if (lower) { bz = zn; bdr = dr; bdc = dc; }
           }
-        if (seed) {
+        if (seam_t || seam_b) {
+          // every seam cell is the root of its own "terminal" basin with a fixed id (Barnes 2016:
+          // the tile perimeter); whether it is also a seed is remembered for the seam graph
+          u32 sidx = (seam_t ? 0u : (u32)nx) + (u32)c;
+          tv = HC_TAG | (1u + sidx);
+          seam_seed[sidx] = seed ? 1 : 0;
+        } else if (seed) {
           tv = HC_TAG;  // basin 0
         } else if (bdr == 0 && bdc == 0) {
           tv = HC_TAG | 0x7FFFFFFEu;  // pit, id patched below
@@ -121,7 +129,7 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
   for (int i = tid; i < T * T; i += NTHREADS) {
     if (stv[i] == (HC_TAG | 0x7FFFFFFEu)) {
       u32 k = atomicAdd(&s_npit, 1u);
-      stv[i] = HC_TAG | (s_base + k + 1u);
+      stv[i] = HC_TAG | (idbase + s_base + k + 1u);
     }
   }
   __syncthreads();
@@ -197,7 +205,7 @@ template <bool EMIT>
 __global__ void __launch_bounds__(NTHREADS)
 k_minedge(const float *__restrict__ z, const u32 *__restrict__ P, const u32 *__restrict__ rep,
           u64 *__restrict__ best, int ny, int nx, u32 *__restrict__ eA, u32 *__restrict__ eB,
-          float *__restrict__ eW, u32 *__restrict__ ecount, u32 ecap) {
+          float *__restrict__ eW, u32 *__restrict__ ecount, u32 ecap, u32 nopen) {
   __shared__ float sz[TH * TH];
   __shared__ u32 sa[TH * TH];
   __shared__ u32 s_tot, s_base;
@@ -223,7 +231,7 @@ k_minedge(const float *__restrict__ z, const u32 *__restrict__ P, const u32 *__r
     int lr = i >> 6, lc = i & (T - 1);
     int ci = (lr + 1) * TH + lc + 1;
     u32 a = sa[ci];
-    if (a == 0u || a == HC_NONE) continue;
+    if (a < nopen || a == HC_NONE) continue;
     float v = sz[ci];
     u64 key = ~0ull;
 #pragma unroll
@@ -254,7 +262,7 @@ k_minedge(const float *__restrict__ z, const u32 *__restrict__ P, const u32 *__r
     int lr = i >> 6, lc = i & (T - 1);
     int ci = (lr + 1) * TH + lc + 1;
     u32 a = sa[ci];
-    if (a == 0u || a == HC_NONE) continue;
+    if (a < nopen || a == HC_NONE) continue;
     float v = sz[ci];
 #pragma unroll
     for (int dr = -1; dr <= 1; dr++)
@@ -275,11 +283,11 @@ k_minedge(const float *__restrict__ z, const u32 *__restrict__ P, const u32 *__r
 // a Boruvka pick round on the compact edge list
 __global__ void __launch_bounds__(256)
 k_minedge_list(const u32 *__restrict__ eA, const u32 *__restrict__ eB, const float *__restrict__ eW, u32 ne,
-               const u32 *__restrict__ rep, u64 *__restrict__ best) {
+               const u32 *__restrict__ rep, u64 *__restrict__ best, u32 nopen) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ne) return;
   u32 a = __ldg(&rep[eA[i]]);
-  if (a == 0u) return;
+  if (a < nopen) return;
   u32 b = __ldg(&rep[eB[i]]);
   if (a == b) return;
   u64 key = ((u64)d_ford(eW[i]) << 32) | (u64)b;
@@ -295,10 +303,10 @@ __global__ void k_tab_init(u32 *rep, float *lvl, u32 *hp, u32 K1) {
 }
 
 // each active basin adopts its cheapest edge: ptr = target, lvl = max(lvl, weight)
-__global__ void k_hook(const u32 *rep, const u64 *best, u32 *ptr, float *lvl, u32 K1) {
+__global__ void k_hook(const u32 *rep, const u64 *best, u32 *ptr, float *lvl, u32 K1, u32 nopen) {
   u32 b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= K1) return;
-  if (b == 0 || rep[b] != b) { ptr[b] = b == 0 ? 0u : rep[b]; return; }
+  if (b < nopen || rep[b] != b) { ptr[b] = b < nopen ? b : rep[b]; return; }
   u64 k = best[b];
   if (k == ~0ull) { ptr[b] = 0u; return; }  // no neighbour at all (walled in): never raised
   float w = d_funord((u32)(k >> 32));
@@ -307,11 +315,11 @@ __global__ void k_hook(const u32 *rep, const u64 *best, u32 *ptr, float *lvl, u3
 }
 
 // break mutual pairs: the smaller id becomes the root of the pair's tree
-__global__ void k_mutual(const u32 *rep, const u32 *ptr, u32 *ptr2, u32 K1) {
+__global__ void k_mutual(const u32 *rep, const u32 *ptr, u32 *ptr2, u32 K1, u32 nopen) {
   u32 b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= K1) return;
   u32 p = ptr[b];
-  if (b != 0 && rep[b] == b && p != 0 && ptr[p] == b && b < p) p = b;
+  if (b >= nopen && rep[b] == b && p >= nopen && ptr[p] == b && b < p) p = b;
   ptr2[b] = p;
 }
 
@@ -324,12 +332,13 @@ __global__ void k_jump(u32 *ptr, u32 K1, u32 *changed) {
 }
 
 // merge trees into their roots, count what is still closed
-__global__ void k_merge(u32 *rep, u32 *hp, const u32 *ptr, u32 K1, u32 *n_active) {
+// n_active[0] = closed roots left, n_active[1] = roots merged this round
+__global__ void k_merge(u32 *rep, u32 *hp, const u32 *ptr, u32 K1, u32 *n_active, u32 nopen) {
   u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= K1 || b == 0) return;
+  if (b >= K1 || b < nopen) return;
   if (rep[b] != b) return;
   u32 r = ptr[b];
-  if (r != b) { hp[b] = r; rep[b] = r; }
+  if (r != b) { hp[b] = r; rep[b] = r; atomicAdd(n_active + 1, 1u); }
   else atomicAdd(n_active, 1u);
 }
 
@@ -342,13 +351,15 @@ __global__ void k_repflat(u32 *rep, u32 K1) {
 }
 
 // final level of an original basin = max of pick weights up its contraction chain
-__global__ void k_levels(const u32 *hp, const float *lvl, float *level0, u32 K1) {
+// (troot = the open node the chain ends in: 0 = outside, or a band's seam terminal)
+__global__ void k_levels(const u32 *hp, const float *lvl, float *level0, u32 *troot, u32 K1, u32 nopen) {
   u32 b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= K1) return;
   float m = -INFINITY;
   u32 x = b;
-  while (x != 0) { m = fmaxf(m, lvl[x]); x = hp[x]; }
+  while (x >= nopen) { m = fmaxf(m, lvl[x]); x = hp[x]; }
   level0[b] = m;
+  if (troot) troot[b] = x;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -378,11 +389,137 @@ size_t fill_workspace(int64_t ny, int64_t nx) {
 int ext_nodata_mask(hc_ctx *ctx, const float *z, uint8_t *ext, int64_t ny, int64_t nx, float nodata,
                     int *has_interior, cudaStream_t st);
 
-int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata, int seed_mode,
-             cudaStream_t st) {
-  if (ny <= 0 || nx <= 0) return HC_OK;
+// ---------------------------------------------------------------------------------------------
+// generic Boruvka rounds on an explicit undirected edge list (both endpoints see every entry; ties
+// broken by (weight, entry index), which is the same key from both ends => only 2-cycles).
+// Nodes < nopen are "open" (never hook).  msf = 1: a closed component without outgoing edges
+// stays a root (minimum spanning FOREST); msf = 0: it is attached to node 0 unraised.
+// mark (optional) receives 1 for every entry picked: the MST/MSF edges.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pick_both(const u32 *__restrict__ eA, const u32 *__restrict__ eB, const float *__restrict__ eW, u32 ne,
+            const u32 *__restrict__ rep, u64 *__restrict__ best, u32 nopen) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  u32 a = __ldg(&rep[eA[i]]), b = __ldg(&rep[eB[i]]);
+  if (a == b) return;
+  u64 key = ((u64)d_ford(eW[i]) << 32) | (u64)i;
+  if (a >= nopen && key < __ldcg(&best[a])) atomicMin(&best[a], key);
+  if (b >= nopen && key < __ldcg(&best[b])) atomicMin(&best[b], key);
+}
+
+__global__ void k_hook_idx(const u32 *rep, const u64 *best, u32 *ptr, float *lvl, u32 K1, u32 nopen,
+                           const u32 *__restrict__ eA, const u32 *__restrict__ eB, const float *__restrict__ eW,
+                           uint8_t *mark, int msf) {
+  u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= K1) return;
+  if (b < nopen || rep[b] != b) { ptr[b] = b < nopen ? b : rep[b]; return; }
+  u64 k = best[b];
+  if (k == ~0ull) { ptr[b] = msf ? b : 0u; return; }
+  u32 idx = (u32)(k & 0xFFFFFFFFu);
+  u32 ra = rep[eA[idx]], rb = rep[eB[idx]];
+  ptr[b] = ra == b ? rb : ra;
+  lvl[b] = fmaxf(lvl[b], eW[idx]);
+  if (mark) mark[idx] = 1;
+}
+
+struct bor_tabs { u64 *best; u32 *rep, *hp, *ptr, *ptr2; float *lvl; };
+
+static int bor_tabs_alloc(hc_ctx *ctx, bor_tabs *t, u32 K1) {
+  t->best = (u64 *)arena_take(ctx, (size_t)K1 * 8);
+  t->rep = (u32 *)arena_take(ctx, (size_t)K1 * 4);
+  t->hp = (u32 *)arena_take(ctx, (size_t)K1 * 4);
+  t->ptr = (u32 *)arena_take(ctx, (size_t)K1 * 4);
+  t->ptr2 = (u32 *)arena_take(ctx, (size_t)K1 * 4);
+  t->lvl = (float *)arena_take(ctx, (size_t)K1 * 4);
+  if (!t->best || !t->rep || !t->hp || !t->ptr || !t->ptr2 || !t->lvl) return HC_ERR_NOMEM;
+  return HC_OK;
+}
+
+// hook -> break mutual pairs -> pointer-double to the roots -> merge; cnt: [1]=changed [2]=active [3]=merged
+static int bor_contract(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, u32 *cnt, u32 *active, u32 *merged,
+                        cudaStream_t st) {
+  const int tb = 256;
+  const int tgK = (int)((K1 + tb - 1) / tb);
+  HC_PROF(ctx, st, "k_mutual");
+  k_mutual<<<tgK, tb, 0, st>>>(t.rep, t.ptr2, t.ptr, K1, nopen);
+  HC_LAUNCH_CHECK(ctx);
+  // pointer doubling to the roots: 4 doublings per read-back
+  for (int it = 0; it < 16; it++) {
+    for (int j = 0; j < 3; j++) {
+      HC_PROF(ctx, st, "k_jump");
+      k_jump<<<tgK, tb, 0, st>>>(t.ptr, K1, cnt + 5);
+      HC_LAUNCH_CHECK(ctx);
+    }
+    HC_CUDA(cudaMemsetAsync(cnt + 1, 0, 4, st));
+    HC_PROF(ctx, st, "k_jump");
+    k_jump<<<tgK, tb, 0, st>>>(t.ptr, K1, cnt + 1);
+    HC_LAUNCH_CHECK(ctx);
+    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 1, 4, cudaMemcpyDeviceToHost, st));
+    HC_CUDA(cudaStreamSynchronize(st));
+    if (!ctx->h_mail[0]) break;
+  }
+  HC_CUDA(cudaMemsetAsync(cnt + 2, 0, 8, st));
+  HC_PROF(ctx, st, "k_merge");
+  k_merge<<<tgK, tb, 0, st>>>(t.rep, t.hp, t.ptr, K1, cnt + 2, nopen);
+  HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_repflat");
+  k_repflat<<<tgK, tb, 0, st>>>(t.rep, K1);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 2, 8, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  *active = ctx->h_mail[0];
+  *merged = ctx->h_mail[1];
+  return HC_OK;
+}
+
+static int bor_list_solve(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, const u32 *eA, const u32 *eB,
+                          const float *eW, u32 ne, int msf, uint8_t *mark, u32 *cnt, int *rounds, cudaStream_t st) {
+  const int tb = 256;
+  const int tgK = (int)((K1 + tb - 1) / tb);
+  HC_PROF(ctx, st, "k_tab_init");
+  k_tab_init<<<tgK, tb, 0, st>>>(t.rep, t.lvl, t.hp, K1);
+  HC_LAUNCH_CHECK(ctx);
+  if (mark && ne) HC_CUDA(cudaMemsetAsync(mark, 0, ne, st));
+  u32 active = K1 > nopen ? K1 - nopen : 0, merged = 1;
+  int round = 0;
+  while (active > 0 && merged > 0) {
+    if (round > 64) { hc_set_error("fill: list Boruvka did not converge"); return HC_ERR_INTERNAL; }
+    HC_CUDA(cudaMemsetAsync(t.best, 0xFF, (size_t)K1 * 8, st));
+    if (ne) {
+      HC_PROF(ctx, st, "k_pick_both");
+      k_pick_both<<<(ne + 255) / 256, 256, 0, st>>>(eA, eB, eW, ne, t.rep, t.best, nopen);
+      HC_LAUNCH_CHECK(ctx);
+    }
+    HC_PROF(ctx, st, "k_hook_idx");
+    k_hook_idx<<<tgK, tb, 0, st>>>(t.rep, t.best, t.ptr2, t.lvl, K1, nopen, eA, eB, eW, mark, msf);
+    HC_LAUNCH_CHECK(ctx);
+    HC_TRY(bor_contract(ctx, t, K1, nopen, cnt, &active, &merged, st));
+    round++;
+  }
+  if (rounds) *rounds = round;
+  return HC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 1 (shared by the whole-raster fill and the band-local fill): watershed labels P, local
+// levels level0 (relative to the open nodes), troot (which open node each basin hangs under)
+// ---------------------------------------------------------------------------------------------
+struct fill_state {
+  u32 *P; float *level0; u32 *troot; u32 K1, nopen; u32 *cnt; uint8_t *seam_seed;
+  u32 *eA, *eB; float *eW; u32 ecap;
+};
+
+static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float nodata, int seed_mode, hc_rows rw,
+                      fill_state *fs, cudaStream_t st) {
   size_t n = (size_t)ny * nx;
   if (n >= 0x7FFFFFF0ull) { hc_set_error("raster too large for 31-bit cell indices"); return HC_ERR_TOO_LARGE; }
+  const bool banded = rw.top || rw.bot;
+  if (banded && ny < 2) { hc_set_error("a band needs at least 2 rows"); return HC_ERR_ARG; }
+  if (banded && seed_mode != HC_SEED_TAUDEM) {
+    hc_set_error("banded fill: only HC_SEED_TAUDEM (the WBT exterior-nodata rule needs a global labelling)");
+    return HC_ERR_ARG;
+  }
   const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t tiles = (size_t)tx * ty;
   HC_TRY(arena_reset(ctx));
@@ -396,15 +533,17 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
     if (!has_interior) ext = nullptr;  // every nodata cell sits on the raster border: all exterior
   }
   u32 *P = (u32 *)arena_take(ctx, n * 4);
-  uint8_t *actA = (uint8_t *)arena_take(ctx, tiles);
-  uint8_t *actB = (uint8_t *)arena_take(ctx, tiles);
-  u32 *cnt = (u32 *)arena_take(ctx, 256);  // [0]=pit counter [1]=changed [2]=n_active
-  if (!P || !actA || !actB || !cnt) return HC_ERR_NOMEM;
+  u32 *cnt = (u32 *)arena_take(ctx, 256);  // [0]=pit counter [1]=changed [2]=n_active [3]=n_merged [4]=edges
+  uint8_t *seam_seed = (uint8_t *)arena_take(ctx, banded ? (size_t)2 * nx : 1);
+  if (!P || !cnt || !seam_seed) return HC_ERR_NOMEM;
+  (void)tiles;
+  const u32 nopen = banded ? (u32)(2 * nx + 1) : 1u;
 
   HC_CUDA(cudaMemsetAsync(cnt, 0, 256, st));
+  if (banded) HC_CUDA(cudaMemsetAsync(seam_seed, 0, (size_t)2 * nx, st));
   dim3 tg(tx, ty);
   HC_PROF(ctx, st, "k_ptr");
-  k_ptr<<<tg, NTHREADS, 0, st>>>(z, ext, P, (int)ny, (int)nx, nodata, cnt);
+  k_ptr<<<tg, NTHREADS, 0, st>>>(z, ext, P, (int)ny, (int)nx, nodata, cnt, rw, nopen - 1, seam_seed);
   HC_LAUNCH_CHECK(ctx);
   HC_PROF(ctx, st, "k_perim");
   k_perim<<<tg, 256, 0, st>>>(P, (int)ny, (int)nx);
@@ -416,19 +555,15 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
 
   HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt, 4, cudaMemcpyDeviceToHost, st));
   HC_CUDA(cudaStreamSynchronize(st));
-  const u32 K = ctx->h_mail[0];
-  const u32 K1 = K + 1;
+  const u32 K = ctx->h_mail[0];        // pits
+  const u32 K1 = nopen + K;            // open nodes + pits
   ctx->fill_basins = K;
   ctx->fill_rounds = 0;
 
-  u64 *best = (u64 *)arena_take(ctx, (size_t)K1 * 8);
-  u32 *rep = (u32 *)arena_take(ctx, (size_t)K1 * 4);
-  u32 *hp = (u32 *)arena_take(ctx, (size_t)K1 * 4);
-  u32 *ptr = (u32 *)arena_take(ctx, (size_t)K1 * 4);
-  u32 *ptr2 = (u32 *)arena_take(ctx, (size_t)K1 * 4);
-  float *lvl = (float *)arena_take(ctx, (size_t)K1 * 4);
-  if (!best || !rep || !hp || !ptr || !ptr2 || !lvl) return HC_ERR_NOMEM;
-  float *level0 = (float *)ptr2;  // reused after the rounds
+  bor_tabs t;
+  HC_TRY(bor_tabs_alloc(ctx, &t, K1));
+  float *level0 = (float *)t.ptr2;  // reused after the rounds
+  u32 *troot = t.ptr;
   // compact edge list for the rounds after the second grid pass
   size_t ecap_sz = n / 4 > (size_t)(1u << 20) ? n / 4 : (size_t)(1u << 20);
   if (ecap_sz > (size_t)(1u << 28)) ecap_sz = (size_t)(1u << 28);
@@ -443,60 +578,33 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
   const int tb = 256;
   const int tgK = (int)((K1 + tb - 1) / tb);
   HC_PROF(ctx, st, "k_tab_init");
-  k_tab_init<<<tgK, tb, 0, st>>>(rep, lvl, hp, K1);
+  k_tab_init<<<tgK, tb, 0, st>>>(t.rep, t.lvl, t.hp, K1);
   HC_LAUNCH_CHECK(ctx);
 
-  u32 active = K;
+  u32 active = K, merged = 0;
   int round = 0;
   while (active > 0) {
     if (round > 64) { hc_set_error("fill: Boruvka did not converge"); return HC_ERR_INTERNAL; }
-    HC_CUDA(cudaMemsetAsync(best, 0xFF, (size_t)K1 * 8, st));
+    HC_CUDA(cudaMemsetAsync(t.best, 0xFF, (size_t)K1 * 8, st));
     if (have_list) {
       HC_PROF(ctx, st, "k_minedge_list");
-      k_minedge_list<<<(ne + 255) / 256, 256, 0, st>>>(eA, eB, eW, ne, rep, best);
+      k_minedge_list<<<(ne + 255) / 256, 256, 0, st>>>(eA, eB, eW, ne, t.rep, t.best, nopen);
       HC_LAUNCH_CHECK(ctx);
     } else if (round == 1) {
       HC_CUDA(cudaMemsetAsync(cnt + 4, 0, 4, st));
       HC_PROF(ctx, st, "k_minedge_emit");
-      k_minedge<true><<<tg, NTHREADS, 0, st>>>(z, P, rep, best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap);
+      k_minedge<true><<<tg, NTHREADS, 0, st>>>(z, P, t.rep, t.best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen);
       HC_LAUNCH_CHECK(ctx);
       HC_CUDA(cudaMemcpyAsync(ctx->h_mail + 4, cnt + 4, 4, cudaMemcpyDeviceToHost, st));
     } else {
       HC_PROF(ctx, st, "k_minedge");
-      k_minedge<false><<<tg, NTHREADS, 0, st>>>(z, P, rep, best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap);
+      k_minedge<false><<<tg, NTHREADS, 0, st>>>(z, P, t.rep, t.best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen);
       HC_LAUNCH_CHECK(ctx);
     }
     HC_PROF(ctx, st, "k_hook");
-    k_hook<<<tgK, tb, 0, st>>>(rep, best, ptr2, lvl, K1);
+    k_hook<<<tgK, tb, 0, st>>>(t.rep, t.best, t.ptr2, t.lvl, K1, nopen);
     HC_LAUNCH_CHECK(ctx);
-    HC_PROF(ctx, st, "k_mutual");
-    k_mutual<<<tgK, tb, 0, st>>>(rep, ptr2, ptr, K1);
-    HC_LAUNCH_CHECK(ctx);
-    // pointer doubling to the roots: 4 doublings per read-back
-    for (int it = 0; it < 16; it++) {
-      for (int j = 0; j < 3; j++) {
-        HC_PROF(ctx, st, "k_jump");
-        k_jump<<<tgK, tb, 0, st>>>(ptr, K1, cnt + 3);
-        HC_LAUNCH_CHECK(ctx);
-      }
-      HC_CUDA(cudaMemsetAsync(cnt + 1, 0, 4, st));
-      HC_PROF(ctx, st, "k_jump");
-      k_jump<<<tgK, tb, 0, st>>>(ptr, K1, cnt + 1);
-      HC_LAUNCH_CHECK(ctx);
-      HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 1, 4, cudaMemcpyDeviceToHost, st));
-      HC_CUDA(cudaStreamSynchronize(st));
-      if (!ctx->h_mail[0]) break;
-    }
-    HC_CUDA(cudaMemsetAsync(cnt + 2, 0, 4, st));
-    HC_PROF(ctx, st, "k_merge");
-    k_merge<<<tgK, tb, 0, st>>>(rep, hp, ptr, K1, cnt + 2);
-    HC_LAUNCH_CHECK(ctx);
-    HC_PROF(ctx, st, "k_repflat");
-    k_repflat<<<tgK, tb, 0, st>>>(rep, K1);
-    HC_LAUNCH_CHECK(ctx);
-    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 2, 4, cudaMemcpyDeviceToHost, st));
-    HC_CUDA(cudaStreamSynchronize(st));
-    active = ctx->h_mail[0];
+    HC_TRY(bor_contract(ctx, t, K1, nopen, cnt, &active, &merged, st));
     if (round == 1 && !have_list) {  // the emit round's count arrived with the syncs above
       ne = ctx->h_mail[4];
       have_list = ne <= ecap;
@@ -507,10 +615,273 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
   ctx->fill_rounds = round;
 
   HC_PROF(ctx, st, "k_levels");
-  k_levels<<<tgK, tb, 0, st>>>(hp, lvl, level0, K1);
+  k_levels<<<tgK, tb, 0, st>>>(t.hp, t.lvl, level0, banded ? troot : nullptr, K1, nopen);
   HC_LAUNCH_CHECK(ctx);
+  fs->P = P; fs->level0 = level0; fs->troot = troot; fs->K1 = K1; fs->nopen = nopen; fs->cnt = cnt;
+  fs->seam_seed = seam_seed; fs->eA = eA; fs->eB = eB; fs->eW = eW; fs->ecap = ecap;
+  return HC_OK;
+}
+
+int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata, int seed_mode,
+             cudaStream_t st) {
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  fill_state fs;
+  hc_rows rw = {0, (int)ny, 0, 0};
+  HC_TRY(fill_local(ctx, z, ny, nx, nodata, seed_mode, rw, &fs, st));
   HC_PROF(ctx, st, "k_apply");
-  k_apply<<<gblocks, 256, 0, st>>>(z, P, level0, out, n);
+  k_apply<<<ctx->sm_count * 8, 256, 0, st>>>(z, fs.P, fs.level0, out, (size_t)ny * nx);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+// =============================================================================================
+// Row-band sharding (Barnes 2016 "Parallel priority-flood depression filling for
+// trillion cell DEMs" with a band as the tile).
+//
+//   local   every seam cell (first / last own row next to another band) is the root of its own
+//           terminal basin; phase 1 contracts the closed basins into the open nodes {outside,
+//           terminals} and yields level0 = minimax level relative to the nearest open node and
+//           troot = that node.  The graph among the open nodes (edge = lowest locally-filled pass
+//           between two terminal watersheds) is reduced to its minimum spanning forest, which
+//           preserves every pairwise minimax distance; the band publishes those <= 2nx edges plus
+//           the <= 3nx cross-seam edges of its bottom seam.
+//   finish  every rank solves the union of all bands' edges for the terminals' true levels
+//           (redundantly; the graph is tiny) and applies out = max(z, level0, level[troot]).
+// Exactness: level(B) = max(level0(B), level(troot(B))) because a closed component's outgoing
+// edges are all band-local (cross-seam edges touch terminals only) — see DESIGN.md §6.
+// =============================================================================================
+__global__ void __launch_bounds__(NTHREADS)
+k_term_edges(const float *__restrict__ z, const u32 *__restrict__ P, const u32 *__restrict__ troot,
+             const float *__restrict__ level0, int ny, int nx, u32 *__restrict__ eA, u32 *__restrict__ eB,
+             float *__restrict__ eW, u32 *__restrict__ ecount, u32 ecap) {
+  __shared__ float sz[TH * TH];
+  __shared__ u32 sa[TH * TH];
+  __shared__ u32 s_tot, s_base;
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_tot = 0;
+  for (int i = tid; i < TH * TH; i += NTHREADS) {
+    int lr = i / TH, lc = i - lr * TH;
+    int r = r0 + lr - 1, c = c0 + lc - 1;
+    bool inb = r >= 0 && r < ny && c >= 0 && c < nx;
+    size_t g = inb ? (size_t)r * nx + c : 0;
+    u32 id = __ldg(&P[g]) & 0x7FFFFFFFu;
+    float v = __ldg(&z[g]);
+    u32 a = HC_NONE;
+    if (inb && id != HC_LAB_NODATA) {
+      a = id ? __ldg(&troot[id]) : 0u;
+      if (id) v = fmaxf(v, __ldg(&level0[id]));  // locally filled elevation
+    }
+    sz[i] = v;
+    sa[i] = a;
+  }
+  __syncthreads();
+  // an adjacent pair in different terminal watersheds is emitted once, by the cell with the smaller node
+  u32 cnt = 0;
+  for (int i = tid; i < T * T; i += NTHREADS) {
+    int lr = i >> 6, lc = i & (T - 1);
+    int ci = (lr + 1) * TH + lc + 1;
+    u32 a = sa[ci];
+    if (a == HC_NONE) continue;
+#pragma unroll
+    for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+      for (int dc = -1; dc <= 1; dc++) {
+        if (dr == 0 && dc == 0) continue;
+        u32 b = sa[ci + dr * TH + dc];
+        if (b != HC_NONE && a < b) cnt++;
+      }
+  }
+  u32 off = cnt ? atomicAdd(&s_tot, cnt) : 0u;
+  __syncthreads();
+  if (tid == 0) s_base = s_tot ? atomicAdd(ecount, s_tot) : 0u;
+  __syncthreads();
+  if (!cnt || (u64)s_base + s_tot > (u64)ecap) return;  // overflow: host reports it
+  u32 o = s_base + off;
+  for (int i = tid; i < T * T; i += NTHREADS) {
+    int lr = i >> 6, lc = i & (T - 1);
+    int ci = (lr + 1) * TH + lc + 1;
+    u32 a = sa[ci];
+    if (a == HC_NONE) continue;
+    float v = sz[ci];
+#pragma unroll
+    for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+      for (int dc = -1; dc <= 1; dc++) {
+        if (dr == 0 && dc == 0) continue;
+        int ni = ci + dr * TH + dc;
+        u32 b = sa[ni];
+        if (b == HC_NONE || !(a < b)) continue;
+        eA[o] = a;
+        eB[o] = b;
+        eW[o] = fmaxf(v, sz[ni]);
+        o++;
+      }
+  }
+}
+
+// seam cells that are seeds themselves: edge (outside, terminal, z)
+__global__ void k_seam_seed_edges(const float *__restrict__ z, const uint8_t *__restrict__ seam_seed, int ny, int nx,
+                                  u32 *eA, u32 *eB, float *eW, u32 *ecount, u32 ecap) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * nx || !seam_seed[i]) return;
+  int side = i / nx, c = i - side * nx;
+  float v = z[(size_t)(side ? ny - 1 : 0) * nx + c];
+  u32 o = atomicAdd(ecount, 1u);
+  if (o >= ecap) return;
+  eA[o] = 0u;
+  eB[o] = 1u + (u32)i;
+  eW[o] = v;
+}
+
+// out triples (a, b, w bits) in GLOBAL node ids: 0 = outside, 1 + (band*2 + side)*nx + c = seam cell
+__global__ void k_compact_marked(const u32 *__restrict__ eA, const u32 *__restrict__ eB, const float *__restrict__ eW,
+                                 const uint8_t *__restrict__ mark, u32 ne, u32 gbase, u32 *out, u32 *ocount, u32 ocap) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ne || !mark[i]) return;
+  u32 o = atomicAdd(ocount, 1u);
+  if (o >= ocap) return;
+  u32 a = eA[i], b = eB[i];
+  out[3 * (size_t)o] = a ? gbase + a : 0u;
+  out[3 * (size_t)o + 1] = b ? gbase + b : 0u;
+  out[3 * (size_t)o + 2] = __float_as_uint(eW[i]);
+}
+
+// cross-seam edges of the bottom seam: own cell (ny-1, c) -- halo cell (ny, c+d), weight max(z, z)
+__global__ void k_cross_edges(const float *__restrict__ z, int ny, int nx, float nodata, u32 g_own, u32 g_next,
+                              u32 *out, u32 *ocount, u32 ocap) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nx) return;
+  float v = z[(size_t)(ny - 1) * nx + c];
+  if (d_is_nodata(v, nodata)) return;
+  for (int d = -1; d <= 1; d++) {
+    int cc = c + d;
+    if (cc < 0 || cc >= nx) continue;
+    float w = z[(size_t)ny * nx + cc];
+    if (d_is_nodata(w, nodata)) continue;
+    u32 o = atomicAdd(ocount, 1u);
+    if (o >= ocap) return;
+    out[3 * (size_t)o] = g_own + (u32)c;
+    out[3 * (size_t)o + 1] = g_next + (u32)cc;
+    out[3 * (size_t)o + 2] = __float_as_uint(fmaxf(v, w));
+  }
+}
+
+__global__ void k_unpack_edges(const u32 *__restrict__ in, u32 ne, u32 *eA, u32 *eB, float *eW) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  eA[i] = in[3 * (size_t)i];
+  eB[i] = in[3 * (size_t)i + 1];
+  eW[i] = __uint_as_float(in[3 * (size_t)i + 2]);
+}
+
+// final level of a local basin = max(local level, true level of the terminal it hangs under)
+__global__ void k_level_final(const float *__restrict__ level0, const u32 *__restrict__ troot,
+                              const float *__restrict__ tlevel, u32 gbase, float *__restrict__ lf, u32 K1) {
+  u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= K1) return;
+  float m = level0[b];
+  u32 t = troot[b];
+  if (t) m = fmaxf(m, tlevel[gbase + t]);
+  lf[b] = m;
+}
+
+int64_t band_fill_edge_cap(int64_t nx) { return 5 * nx + 16; }
+
+int band_fill_local(hc_ctx *ctx, const float *z, int64_t nb, int64_t nx, float nodata, int seed_mode, int flags,
+                    int64_t band_index, uint32_t *edges_out, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  hc_rows rw = {(flags & 1) ? -1 : 0, (int)nb + ((flags & 2) ? 1 : 0), flags & 1, (flags >> 1) & 1};
+  const int64_t cap = band_fill_edge_cap(nx);
+  fill_state fs;
+  if ((double)(band_index + 2) * 2.0 * (double)nx >= 4294967000.0) { hc_set_error("too many seam cells"); return HC_ERR_TOO_LARGE; }
+  if (!(flags & 3)) {
+    // a single band: no terminals at all, nothing to publish
+    HC_TRY(fill_local(ctx, z, nb, nx, nodata, seed_mode, rw, &fs, st));
+    HC_CUDA(cudaMemsetAsync(edges_out, 0, (size_t)cap * 12, st));
+  } else {
+    HC_TRY(fill_local(ctx, z, nb, nx, nodata, seed_mode, rw, &fs, st));
+    HC_CUDA(cudaMemsetAsync(edges_out, 0, (size_t)cap * 12, st));
+    const int tx = (int)((nx + T - 1) / T), ty = (int)((nb + T - 1) / T);
+    dim3 tg(tx, ty);
+    u32 *cnt = fs.cnt;
+    HC_CUDA(cudaMemsetAsync(cnt + 4, 0, 4, st));
+    HC_PROF(ctx, st, "k_term_edges");
+    k_term_edges<<<tg, NTHREADS, 0, st>>>(z, fs.P, fs.troot, fs.level0, (int)nb, (int)nx, fs.eA, fs.eB, fs.eW, cnt + 4, fs.ecap);
+    HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_seam_seed_edges");
+    k_seam_seed_edges<<<(unsigned)((2 * nx + 255) / 256), 256, 0, st>>>(z, fs.seam_seed, (int)nb, (int)nx, fs.eA, fs.eB, fs.eW, cnt + 4, fs.ecap);
+    HC_LAUNCH_CHECK(ctx);
+    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 4, 4, cudaMemcpyDeviceToHost, st));
+    HC_CUDA(cudaStreamSynchronize(st));
+    const u32 ne = ctx->h_mail[0];
+    ctx->band_term_edges = ne;
+    if (ne > fs.ecap) { hc_set_error("banded fill: %u terminal edges exceed the list capacity %u", ne, fs.ecap); return HC_ERR_TOO_LARGE; }
+    // minimum spanning forest of the open-node graph
+    bor_tabs t2;
+    HC_TRY(bor_tabs_alloc(ctx, &t2, fs.nopen));
+    uint8_t *mark = (uint8_t *)arena_take(ctx, ne ? ne : 1);
+    if (!mark) return HC_ERR_NOMEM;
+    int rounds = 0;
+    HC_TRY(bor_list_solve(ctx, t2, fs.nopen, 0u, fs.eA, fs.eB, fs.eW, ne, 1, mark, cnt, &rounds, st));
+    ctx->band_msf_rounds = rounds;
+    HC_CUDA(cudaMemsetAsync(cnt + 6, 0, 4, st));
+    const u32 gbase = (u32)(band_index * 2 * nx);  // global id of local node t >= 1 is gbase + t
+    if (ne) {
+      HC_PROF(ctx, st, "k_compact_marked");
+      k_compact_marked<<<(ne + 255) / 256, 256, 0, st>>>(fs.eA, fs.eB, fs.eW, mark, ne, gbase, edges_out, cnt + 6, (u32)cap);
+      HC_LAUNCH_CHECK(ctx);
+    }
+    if (flags & 2) {
+      HC_PROF(ctx, st, "k_cross_edges");
+      k_cross_edges<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(z, (int)nb, (int)nx, nodata, gbase + 1u + (u32)nx,
+                                                                   (u32)((band_index + 1) * 2 * nx) + 1u, edges_out, cnt + 6, (u32)cap);
+      HC_LAUNCH_CHECK(ctx);
+    }
+  }
+  bs->flags = flags; bs->nb = nb; bs->nx = nx; bs->band_index = band_index;
+  bs->z = z; bs->P = fs.P; bs->level0 = fs.level0; bs->troot = fs.troot; bs->K1 = fs.K1; bs->nopen = fs.nopen;
+  bs->cnt = fs.cnt;
+  bs->fill_ready = 1;
+  return HC_OK;
+}
+
+int band_fill_finish(hc_ctx *ctx, const uint32_t *all_edges, int64_t nbands, float *out, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  if (!bs->fill_ready) { hc_set_error("hc_band_fill_finish without hc_band_fill_local"); return HC_ERR_ARG; }
+  bs->fill_ready = 0;
+  const int64_t nx = bs->nx, nb = bs->nb;
+  const size_t n = (size_t)nb * nx;
+  const float *level = bs->level0;
+  if (bs->flags & 3) {
+    const int64_t cap = band_fill_edge_cap(nx);
+    const u32 ne = (u32)(nbands * cap);
+    const u32 K1g = (u32)(1 + nbands * 2 * nx);
+    u32 *eA = (u32 *)arena_take(ctx, (size_t)ne * 4);
+    u32 *eB = (u32 *)arena_take(ctx, (size_t)ne * 4);
+    float *eW = (float *)arena_take(ctx, (size_t)ne * 4);
+    float *lf = (float *)arena_take(ctx, (size_t)bs->K1 * 4);
+    if (!eA || !eB || !eW || !lf) return HC_ERR_NOMEM;
+    HC_PROF(ctx, st, "k_unpack_edges");
+    k_unpack_edges<<<(ne + 255) / 256, 256, 0, st>>>(all_edges, ne, eA, eB, eW);
+    HC_LAUNCH_CHECK(ctx);
+    bor_tabs tg;
+    HC_TRY(bor_tabs_alloc(ctx, &tg, K1g));
+    int rounds = 0;
+    HC_TRY(bor_list_solve(ctx, tg, K1g, 1u, eA, eB, eW, ne, 0, nullptr, bs->cnt, &rounds, st));
+    ctx->band_global_rounds = rounds;
+    float *tlevel = (float *)tg.ptr2;
+    const int tb = 256;
+    HC_PROF(ctx, st, "k_levels");
+    k_levels<<<(K1g + tb - 1) / tb, tb, 0, st>>>(tg.hp, tg.lvl, tlevel, nullptr, K1g, 1u);
+    HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_level_final");
+    k_level_final<<<(bs->K1 + tb - 1) / tb, tb, 0, st>>>(bs->level0, bs->troot, tlevel, (u32)(bs->band_index * 2 * nx), lf, bs->K1);
+    HC_LAUNCH_CHECK(ctx);
+    level = lf;
+  }
+  HC_PROF(ctx, st, "k_apply");
+  k_apply<<<ctx->sm_count * 8, 256, 0, st>>>(bs->z, bs->P, level, out, n);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }

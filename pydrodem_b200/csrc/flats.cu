@@ -45,7 +45,7 @@
 template <int TABLE>
 __global__ void __launch_bounds__(NTHREADS)
 k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB,
-            uint8_t *__restrict__ tile_pending, int ny, int nx, float nodata, unsigned long long *dbg) {
+            uint8_t *__restrict__ tile_pending, int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw) {
   extern __shared__ __align__(16) unsigned char smem[];
   float *sz = (float *)smem;
   unsigned short *slo = (unsigned short *)(smem + FR * FR * 4);  // [OPEN | NF | lo:14]
@@ -63,10 +63,10 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
   for (int i = tid; i < FR * FR; i += NTHREADS) {
     int lr = i / FR, lc = i - lr * FR;
     int r = r0 + lr, c = c0 + lc;
-    bool inb = r >= 0 && r < ny && c >= 0 && c < nx;
-    size_t g = inb ? (size_t)r * nx + c : 0;
-    float v = __ldg(&z[g]);
-    uint8_t d = __ldg(&dirA[g]);
+    bool inb = r >= rw.rlo && r < rw.rhi && c >= 0 && c < nx;
+    long long g = inb ? (long long)r * nx + c : 0;  // r = -1 / ny: a band's halo rows
+    float v = __ldg(z + g);
+    uint8_t d = __ldg(dirA + g);
     sz[i] = (inb && v != nodata) ? v : qnan;
     shi[i] = d;
   }
@@ -79,7 +79,9 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
       int lr = i / FR, lc = i - lr * FR;
       // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
       // (conservatively also when the rim coincides with the raster border)
-      if (lr == 0 || lc == 0 || lr == FR - 1 || lc == FR - 1) w = F_NF | F_OPEN;
+      // ... and a NOFLOW cell of a band's halo row belongs to the neighbouring band: open too
+      int r = r0 + lr;
+      if (lr == 0 || lc == 0 || lr == FR - 1 || lc == FR - 1 || r < 0 || r >= ny) w = F_NF | F_OPEN;
       else {
         w = F_NF;
         u32 k = atomicAdd(&s_n[0], 1u);
@@ -198,7 +200,7 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
 
 // active = pending tiles and their 8 neighbours; also counts pending tiles
 __global__ void k_flat_dilate(const uint8_t *__restrict__ pending, uint8_t *__restrict__ active, int tx, int ty,
-                              u32 *__restrict__ n_pending) {
+                              u32 *__restrict__ n_pending, hc_rows rw) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= tx * ty) return;
   int y = t / tx, x = t - y * tx;
@@ -208,6 +210,8 @@ __global__ void k_flat_dilate(const uint8_t *__restrict__ pending, uint8_t *__re
       int yy = y + dy, xx = x + dx;
       if (yy >= 0 && yy < ty && xx >= 0 && xx < tx) a |= pending[yy * tx + xx];
     }
+  // a band's seam tile rows always take part: the neighbouring band's flats may end on them
+  if ((rw.top && y == 0) || (rw.bot && y == ty - 1)) a = 1;
   active[t] = (uint8_t)a;
   if (pending[t]) atomicAdd(n_pending, 1u);
 }
@@ -221,7 +225,7 @@ __global__ void k_flat_dilate(const uint8_t *__restrict__ pending, uint8_t *__re
 __global__ void __launch_bounds__(NTHREADS)
 k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const uint8_t *__restrict__ dirB,
             uint8_t *__restrict__ nf, u32 *__restrict__ dlo, u32 *__restrict__ dhi,
-            const uint8_t *__restrict__ active, int ny, int nx, float nodata) {
+            const uint8_t *__restrict__ active, int ny, int nx, float nodata, hc_rows rw) {
   __shared__ float sz[TH * TH];
   __shared__ uint8_t sd[TH * TH];
   if (!active[blockIdx.y * gridDim.x + blockIdx.x]) return;
@@ -233,11 +237,11 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
     int r = r0 + lr - 1, c = c0 + lc - 1;
     float v = qnan;
     uint8_t d = HC_DIR_NODATA;
-    if (r >= 0 && r < ny && c >= 0 && c < nx) {
-      size_t g = (size_t)r * nx + c;
-      v = __ldg(&z[g]);
+    if (r >= rw.rlo && r < rw.rhi && c >= 0 && c < nx) {
+      long long g = (long long)r * nx + c;
+      v = __ldg(z + g);
       if (v == nodata) v = qnan;
-      d = __ldg(&dir[g]);
+      d = __ldg(dir + g);
     }
     sz[i] = v;
     sd[i] = d;
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(NTHREADS)
 k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
              const uint8_t *__restrict__ active, const uint8_t *__restrict__ dirty_in,
              uint8_t *__restrict__ dirty_out, u32 *__restrict__ changed_flag, int ny, int nx, float nodata,
-             unsigned long long *dbg) {
+             unsigned long long *dbg, hc_rows rw) {
   extern __shared__ __align__(16) unsigned char smem[];
   float *sz = (float *)smem;
   u32 *slo = (u32 *)(smem + TH * TP * 4);
@@ -337,16 +341,18 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
     int r = r0 + lr - 1, c = c0 + lc - 1;
     // halo cells of tiles outside the active set hold no state: treat as not in any flat
     int ay = lr == 0 ? 0 : (lr == TH - 1 ? 2 : 1), ax = lc == 0 ? 0 : (lc == TH - 1 ? 2 : 1);
-    bool inb = r >= 0 && r < ny && c >= 0 && c < nx && s_act[ay * 3 + ax];
-    size_t g = inb ? (size_t)r * nx + c : 0;
-    float v = __ldg(&z[g]);
-    u32 lo = __ldcg(&dlo[g]);
-    u32 hi = __ldcg(&dhi[g]);
-    uint8_t f = __ldg(&nf[g]);
+    // (a band's halo rows hold the neighbouring band's state, refreshed between relaxations)
+    bool halo_row = (r == -1 && rw.top) || (r == ny && rw.bot);
+    bool inb = c >= 0 && c < nx && ((r >= 0 && r < ny && s_act[ay * 3 + ax]) || halo_row);
+    long long g = inb ? (long long)r * nx + c : 0;
+    float v = __ldg(z + g);
+    u32 lo = __ldcg(dlo + g);
+    u32 hi = __ldcg(dhi + g);
+    uint8_t f = __ldcg(nf + g);
     if (!inb) { lo = 0; hi = 0; f = 0; }
     if (f) {
       lo |= R_NF;
-      if (lr >= 1 && lr <= T && lc >= 1 && lc <= T) list[atomicAdd(&s_n, 1u)] = (unsigned short)(lr * TP + lc);
+      if (lr >= 1 && lr <= T && lc >= 1 && lc <= T && r < ny) list[atomicAdd(&s_n, 1u)] = (unsigned short)(lr * TP + lc);
     }
     sz[lr * TP + lc] = (inb && v != nodata) ? v : qnan;
     slo[lr * TP + lc] = lo;
@@ -427,7 +433,7 @@ template <int TABLE>
 __global__ void __launch_bounds__(256)
 k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ nf, const u32 *__restrict__ dlo,
             const u32 *__restrict__ dhi, uint8_t *__restrict__ dirB, const uint8_t *__restrict__ pending,
-            int ny, int nx, float nodata) {
+            int ny, int nx, float nodata, hc_rows rw) {
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
   if (!pending[tile]) return;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
@@ -448,8 +454,8 @@ k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ nf, const u
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         int rr = r + c_dr[TABLE][k], cc = c + c_dc[TABLE][k];
-        if (rr < 0 || rr >= ny || cc < 0 || cc >= nx) continue;
-        size_t gn = (size_t)rr * nx + cc;
+        if (rr < rw.rlo || rr >= rw.rhi || cc < 0 || cc >= nx) continue;
+        long long gn = (long long)rr * nx + cc;
         float zn = z[gn];
         if (zn != v) continue;  // also drops nodata / NaN
         long long key;
@@ -475,18 +481,21 @@ size_t flats_workspace(int64_t ny, int64_t nx) {
   return 2 * hc_align(n) + 2 * hc_align(n * 4) + 4 * hc_align(tiles) + hc_align(256);
 }
 
-// dirA: D8 codes with NOFLOW on flats (read only); dirB: output (may not alias dirA).
-int flats_core(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx,
-               float nodata, int table, cudaStream_t st) {
-  size_t n = (size_t)ny * nx;
+// ---- the pass in pieces (the whole-raster call runs them back to back; a band interleaves the
+// ---- relaxation with seam exchanges).  State lives in ctx->band.
+static int flats_fast_tier(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx,
+                           float nodata, int table, hc_rows rw, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
   const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t tiles = (size_t)tx * ty;
-  uint8_t *pending = (uint8_t *)arena_take(ctx, tiles);
-  uint8_t *active = (uint8_t *)arena_take(ctx, tiles);
-  uint8_t *dA = (uint8_t *)arena_take(ctx, tiles);
-  uint8_t *dB = (uint8_t *)arena_take(ctx, tiles);
-  u32 *flag = (u32 *)arena_take(ctx, 256);
-  if (!pending || !active || !dA || !dB || !flag) return HC_ERR_NOMEM;
+  bs->pending = (uint8_t *)arena_take(ctx, tiles);
+  bs->active = (uint8_t *)arena_take(ctx, tiles);
+  bs->dA = (uint8_t *)arena_take(ctx, tiles);
+  bs->dB = (uint8_t *)arena_take(ctx, tiles);
+  bs->flag = (u32 *)arena_take(ctx, 256);
+  if (!bs->pending || !bs->active || !bs->dA || !bs->dB || !bs->flag) return HC_ERR_NOMEM;
+  bs->fz = z; bs->dirA = dirA; bs->dirB = dirB; bs->nb = ny; bs->nx = nx; bs->nodata = nodata; bs->table = table;
+  bs->nf = nullptr;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -498,46 +507,92 @@ int flats_core(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, 
   dim3 tg(tx, ty);
   HC_PROF(ctx, st, "k_flat_fast");
   if (table == HC_TABLE_WBT)
-    k_flat_fast<HC_TABLE_WBT><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, pending, (int)ny, (int)nx, nodata, ctx->d_dbg);
+    k_flat_fast<HC_TABLE_WBT><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
   else
-    k_flat_fast<HC_TABLE_TAUDEM><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, pending, (int)ny, (int)nx, nodata, ctx->d_dbg);
+    k_flat_fast<HC_TABLE_TAUDEM><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
   HC_LAUNCH_CHECK(ctx);
-  HC_CUDA(cudaMemsetAsync(flag, 0, 8, st));
+  HC_CUDA(cudaMemsetAsync(bs->flag, 0, 16, st));
   HC_PROF(ctx, st, "k_flat_dilate");
-  k_flat_dilate<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(pending, active, tx, ty, flag + 1);
+  k_flat_dilate<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(bs->pending, bs->active, tx, ty, bs->flag + 1, rw);
   HC_LAUNCH_CHECK(ctx);
-  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, flag + 1, 4, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag + 1, 4, cudaMemcpyDeviceToHost, st));
   HC_CUDA(cudaStreamSynchronize(st));
-  if (!ctx->h_mail[0]) return HC_OK;  // every flat was resolved inside its apron
+  bs->n_pending = (int)ctx->h_mail[0];
+  return HC_OK;
+}
 
-  uint8_t *nf = (uint8_t *)arena_take(ctx, n);
-  u32 *dlo = (u32 *)arena_take(ctx, n * 4);
-  u32 *dhi = (u32 *)arena_take(ctx, n * 4);
+static int flats_slow_init(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  const int64_t ny = bs->nb, nx = bs->nx;
+  const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
+  const size_t tiles = (size_t)tx * ty;
+  // state rasters carry the band's halo rows (row -1 and row ny) like z and dir do
+  const size_t nh = (size_t)(ny + 2) * nx;
+  uint8_t *nf = (uint8_t *)arena_take(ctx, nh);
+  u32 *dlo = (u32 *)arena_take(ctx, nh * 4);
+  u32 *dhi = (u32 *)arena_take(ctx, nh * 4);
   if (!nf || !dlo || !dhi) return HC_ERR_NOMEM;
+  HC_CUDA(cudaMemsetAsync(nf, 0, (size_t)nx, st));
+  HC_CUDA(cudaMemsetAsync(nf + (size_t)(ny + 1) * nx, 0, (size_t)nx, st));
+  HC_CUDA(cudaMemsetAsync(dlo, 0, (size_t)nx * 4, st));
+  HC_CUDA(cudaMemsetAsync(dlo + (size_t)(ny + 1) * nx, 0, (size_t)nx * 4, st));
+  HC_CUDA(cudaMemsetAsync(dhi, 0, (size_t)nx * 4, st));
+  HC_CUDA(cudaMemsetAsync(dhi + (size_t)(ny + 1) * nx, 0, (size_t)nx * 4, st));
+  bs->nf = nf + nx; bs->dlo = dlo + nx; bs->dhi = dhi + nx;
+  dim3 tg(tx, ty);
   HC_PROF(ctx, st, "k_flat_init");
-  k_flat_init<<<tg, NTHREADS, 0, st>>>(z, dirA, dirB, nf, dlo, dhi, active, (int)ny, (int)nx, nodata);
+  k_flat_init<<<tg, NTHREADS, 0, st>>>(bs->fz, bs->dirA, bs->dirB, bs->nf, bs->dlo, bs->dhi, bs->active, (int)ny, (int)nx, bs->nodata, rw);
   HC_LAUNCH_CHECK(ctx);
-  HC_CUDA(cudaMemsetAsync(dA, 1, tiles, st));
-  uint8_t *din = dA, *dout = dB;
+  HC_CUDA(cudaMemsetAsync(bs->dA, 1, tiles, st));  // first relaxation visits every active tile
+  return HC_OK;
+}
+
+// relax until no tile changes; on return bs->dA is all zero (the dirty map of the next call)
+static int flats_relax_loop(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  const int64_t ny = bs->nb, nx = bs->nx;
+  const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
+  const size_t tiles = (size_t)tx * ty;
+  dim3 tg(tx, ty);
+  uint8_t *din = bs->dA, *dout = bs->dB;
   for (int it = 0;; it++) {
     if (it > 1000000) { hc_set_error("flats: relaxation did not converge"); return HC_ERR_INTERNAL; }
     HC_CUDA(cudaMemsetAsync(dout, 0, tiles, st));
-    HC_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+    HC_CUDA(cudaMemsetAsync(bs->flag, 0, 4, st));
     HC_PROF(ctx, st, "k_flat_relax");
-    k_flat_relax<<<tg, NTHREADS, FLAT_SMEM, st>>>(z, nf, dlo, dhi, active, din, dout, flag, (int)ny, (int)nx, nodata, ctx->d_dbg);
+    k_flat_relax<<<tg, NTHREADS, FLAT_SMEM, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->active, din, dout, bs->flag, (int)ny, (int)nx, bs->nodata, ctx->d_dbg, rw);
     HC_LAUNCH_CHECK(ctx);
-    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, flag, 4, cudaMemcpyDeviceToHost, st));
+    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag, 4, cudaMemcpyDeviceToHost, st));
     HC_CUDA(cudaStreamSynchronize(st));
-    if (!ctx->h_mail[0]) break;
     uint8_t *t = din; din = dout; dout = t;
+    if (!ctx->h_mail[0]) break;
   }
+  bs->dA = din; bs->dB = dout;  // din = the last (all-zero) dirty_out
+  return HC_OK;
+}
+
+static int flats_dirs(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  const int64_t ny = bs->nb, nx = bs->nx;
+  dim3 tg((unsigned)((nx + T - 1) / T), (unsigned)((ny + T - 1) / T));
   HC_PROF(ctx, st, "k_flat_dirs");
-  if (table == HC_TABLE_WBT)
-    k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(z, nf, dlo, dhi, dirB, pending, (int)ny, (int)nx, nodata);
+  if (bs->table == HC_TABLE_WBT)
+    k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->dirB, bs->pending, (int)ny, (int)nx, bs->nodata, rw);
   else
-    k_flat_dirs<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(z, nf, dlo, dhi, dirB, pending, (int)ny, (int)nx, nodata);
+    k_flat_dirs<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->dirB, bs->pending, (int)ny, (int)nx, bs->nodata, rw);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
+}
+
+// dirA: D8 codes with NOFLOW on flats (read only); dirB: output (may not alias dirA).
+int flats_core(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx,
+               float nodata, int table, cudaStream_t st) {
+  hc_rows rw = hc_make_rows(ny, 0);
+  HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, ny, nx, nodata, table, rw, st));
+  if (!ctx->band.n_pending) return HC_OK;  // every flat was resolved inside its apron
+  HC_TRY(flats_slow_init(ctx, rw, st));
+  HC_TRY(flats_relax_loop(ctx, rw, st));
+  return flats_dirs(ctx, rw, st);
 }
 
 // in-place public form: dir is copied aside first
@@ -563,4 +618,96 @@ int d8_flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_
   if (!dirA) return HC_ERR_NOMEM;
   HC_TRY(d8_run(ctx, z, dirA, slope, ny, nx, nodata, dx, dy, table, st));
   return flats_core(ctx, z, dirA, dir, ny, nx, nodata, table, st);
+}
+
+// ================================================================================================
+// row bands: the fast tier leaves every flat that touches a seam pending; the slow
+// tier's distance fields are relaxed band-locally, seam rows are exchanged, and the relaxation is
+// repeated until no halo row changes anywhere (chaotic relaxation converges to the same geodesic
+// distances in any order, so the result equals the whole-raster one bit for bit).
+// ================================================================================================
+int band_flats_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t nb, int64_t nx,
+                     float nodata, int table, int flags, cudaStream_t st) {
+  if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("flats: bad table %d", table); return HC_ERR_ARG; }
+  hc_rows rw = hc_make_rows(nb, flags);
+  HC_TRY(arena_reset(ctx));
+  ctx->band.flags = flags;
+  HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, nb, nx, nodata, table, rw, st));
+  HC_TRY(flats_slow_init(ctx, rw, st));
+  ctx->band.flats_ready = 1;
+  return HC_OK;
+}
+
+// out[side][field][nx] (u32): side 0 = first own row, 1 = last own row; fields nf, dlo, dhi
+__global__ void k_flat_get_seams(const uint8_t *__restrict__ nf, const u32 *__restrict__ dlo, const u32 *__restrict__ dhi,
+                                 int ny, int nx, u32 *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * nx) return;
+  int side = i / nx, c = i - side * nx;
+  size_t g = (size_t)(side ? ny - 1 : 0) * nx + c;
+  u32 *o = out + (size_t)side * 3 * nx;
+  o[c] = nf[g];
+  o[nx + c] = dlo[g];
+  o[2 * (size_t)nx + c] = dhi[g];
+}
+
+// write a halo row from the neighbour's seam record; flag[2] != 0 if anything differed
+__global__ void k_flat_put_halo(uint8_t *nf, u32 *dlo, u32 *dhi, long long row, int nx, const u32 *__restrict__ in,
+                                u32 *flag) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nx) return;
+  long long g = row * nx + c;
+  u32 f = in[c], lo = in[nx + c], hi = in[2 * (size_t)nx + c];
+  if (nf[g] != (uint8_t)f || dlo[g] != lo || dhi[g] != hi) {
+    nf[g] = (uint8_t)f; dlo[g] = lo; dhi[g] = hi;
+    *flag = 1u;
+  }
+}
+
+int band_flats_get_seams(hc_ctx *ctx, uint32_t *out, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  if (!bs->flats_ready) { hc_set_error("band flats: begin first"); return HC_ERR_ARG; }
+  HC_PROF(ctx, st, "k_flat_get_seams");
+  k_flat_get_seams<<<(unsigned)((2 * bs->nx + 255) / 256), 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, (int)bs->nb, (int)bs->nx, out);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+int band_flats_put_halos(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int *changed, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  if (!bs->flats_ready) { hc_set_error("band flats: begin first"); return HC_ERR_ARG; }
+  const int64_t ny = bs->nb, nx = bs->nx;
+  const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
+  HC_CUDA(cudaMemsetAsync(bs->flag + 2, 0, 8, st));
+  unsigned gb = (unsigned)((nx + 255) / 256);
+  if (top && (bs->flags & 1)) {
+    HC_PROF(ctx, st, "k_flat_put_halo");
+    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, -1ll, (int)nx, top, bs->flag + 2);
+    HC_LAUNCH_CHECK(ctx);
+  }
+  if (bot && (bs->flags & 2)) {
+    HC_PROF(ctx, st, "k_flat_put_halo");
+    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, (long long)ny, (int)nx, bot, bs->flag + 3);
+    HC_LAUNCH_CHECK(ctx);
+  }
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag + 2, 8, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  // tiles next to a halo row that changed are relaxed again (bs->dA is the next dirty map)
+  if (ctx->h_mail[0]) HC_CUDA(cudaMemsetAsync(bs->dA, 1, (size_t)tx, st));
+  if (ctx->h_mail[1]) HC_CUDA(cudaMemsetAsync(bs->dA + (size_t)(ty - 1) * tx, 1, (size_t)tx, st));
+  if (changed) *changed = (ctx->h_mail[0] || ctx->h_mail[1]) ? 1 : 0;
+  return HC_OK;
+}
+
+int band_flats_relax(hc_ctx *ctx, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  if (!bs->flats_ready) { hc_set_error("band flats: begin first"); return HC_ERR_ARG; }
+  return flats_relax_loop(ctx, hc_make_rows(bs->nb, bs->flags), st);
+}
+
+int band_flats_finish(hc_ctx *ctx, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  if (!bs->flats_ready) { hc_set_error("band flats: begin first"); return HC_ERR_ARG; }
+  bs->flats_ready = 0;
+  return flats_dirs(ctx, hc_make_rows(bs->nb, bs->flags), st);
 }
