@@ -36,6 +36,13 @@ KERNEL_PASS = {
     "k_lab_compress": "fill", "k_ext_flag_border": "fill", "k_ext_out": "fill",
     "k_d8": "d8", "k_flat_init": "flats", "k_flat_relax": "flats", "k_flat_dirs": "flats",
     "k_acc_init": "accum", "k_acc_walk": "accum", "k_acc_out": "accum",
+    "k_minedge_emit": "fill", "k_minedge_list": "fill", "k_term_edges": "fill", "k_seam_seed_edges": "fill",
+    "k_pick_both": "fill", "k_hook_idx": "fill", "k_compact_marked": "fill", "k_cross_edges": "fill",
+    "k_unpack_edges": "fill", "k_level_final": "fill",
+    "k_flat_fast": "flats", "k_flat_dilate": "flats", "k_flat_get_seams": "flats", "k_flat_put_halo": "flats",
+    "k_acc_tile_local": "accum", "k_acc_tile_final": "accum", "k_acc_link_count": "accum", "k_acc_link_mark": "accum",
+    "k_acc_link_walk": "accum", "k_acc_seam_exit": "accum", "k_seam_init": "accum", "k_seam_count": "accum",
+    "k_seam_mark": "accum", "k_seam_walk": "accum", "k_acc_seam_apply": "accum",
 }
 
 
@@ -152,6 +159,184 @@ def run_reference(args):
     return 0
 
 
+def run_banded(args, world, rank, local, dev):
+    """One DEM cut into row bands, a band per GPU (BASELINE.json configs[2]); seam exchange over NCCL."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pydrodem_b200 import _lib, bands, synth
+    import pydrodem_b200 as hc
+
+    nl = args.local_bands
+    nbands = world * nl
+    if args.workload == "c3":
+        nx, ny_total = 40000, 40000
+        rows_all = bands.split_rows(ny_total, nbands)
+        scaling = "strong"
+        wl = f"C3: one synthetic {ny_total}x{nx} float32 DEM row-band-sharded over {nbands} band(s)"
+    else:
+        nx = args.size
+        rows_all = [args.size] * nbands
+        ny_total = args.size * nbands
+        scaling = "weak"
+        wl = (f"C2 recipe as ONE {ny_total}x{nx} float32 DEM row-band-sharded, a {args.size}x{nx} band per GPU "
+              f"({nbands} band(s))")
+    first = rank * nl
+    my_rows = rows_all[first:first + nl]
+    row0s = [sum(rows_all[:first + i]) for i in range(nl)]
+    seams = [sum(rows_all[:i]) for i in range(1, nbands)]
+    comm = bands.SeamComm()
+    chain = bands.BandedChain(my_rows, nx, nbands, first, dev, comm=comm, dx=30.0, dy=30.0, flats=bool(args.flats),
+                              want_slope=False)
+    n_bowls = max(200, int(200 * ny_total * nx / (10801.0 * 10801.0)))
+    for i, nb in enumerate(my_rows):
+        zv = chain.z_view(i)
+        for r0 in range(0, nb, 512):
+            nr = min(512, nb - r0)
+            zv[r0:r0 + nr] = synth.make_dem(ny_total, nx, 1003, row0=row0s[i] + r0, nrows=nr, device=dev,
+                                            n_bowls=n_bowls, seam_rows=seams, plateau_rows=seams[:1])
+    torch.cuda.synchronize()
+    cells_local = sum(my_rows) * nx
+    cells_total = ny_total * nx
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for _ in range(args.warmup):
+        out = chain.run()
+    barrier()
+    for c in chain.ctx:
+        _lib.profile_enable(True, ctx=c)
+    launches0 = chain.launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = chain.run()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = chain.launches() - launches0
+    prof = {}
+    for c in chain.ctx:
+        for k, (cnt, tot, mx) in _lib.profile_read(ctx=c).items():
+            a = prof.get(k, (0, 0.0, 0.0))
+            prof[k] = (a[0] + cnt, a[1] + tot, max(a[2], mx))
+        _lib.profile_enable(False, ctx=c)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = cells_total * args.steps / (ms_max * 1e-3) / 1e6
+    stats = chain.stats()
+    flat_rounds = chain.flat_rounds
+
+    # size-independent checks on the full-size result (tests/run_bands_nccl.py checks the flow identity too)
+    tot_in = torch.zeros(3, dtype=torch.float64, device=dev)
+    for i, (f, d, s_, a) in enumerate(out):
+        z = chain.z_view(i)
+        tot_in[0] += (f < z).sum()                    # fill never lowers a cell
+        tot_in[1] += (d == 0).sum()                   # cells left without a direction (undrainable flats)
+        tot_in[2] += ((d != 255) & (a < 1)).sum()     # every cell with a direction counts itself
+    if world > 1:
+        dist.all_reduce(tot_in)
+    chk = {"cells_below_input": int(tot_in[0].item()), "noflow_cells": int(tot_in[1].item()),
+           "valid_cells_with_zero_count": int(tot_in[2].item())}
+
+    # ---- end to end: pinned host band in, filled + dir + acc out, through the same public call ----
+    e2e = None
+    if not args.no_e2e:
+        hz = [torch.empty((nb, nx), dtype=torch.float32, pin_memory=True) for nb in my_rows]
+        hf = [torch.empty((nb, nx), dtype=torch.float32, pin_memory=True) for nb in my_rows]
+        hd = [torch.empty((nb, nx), dtype=torch.uint8, pin_memory=True) for nb in my_rows]
+        ha = [torch.empty((nb, nx), dtype=torch.int32, pin_memory=True) for nb in my_rows]
+        for i in range(nl):
+            hz[i].copy_(chain.z_view(i))
+        torch.cuda.synchronize()
+
+        def host_step():
+            for i in range(nl):
+                chain.z_view(i).copy_(hz[i], non_blocking=True)
+            res = chain.run()
+            for i, (f, d, s_, a) in enumerate(res):
+                hf[i].copy_(f, non_blocking=True)
+                hd[i].copy_(d, non_blocking=True)
+                ha[i].copy_(a, non_blocking=True)
+            torch.cuda.synchronize()
+        host_step()
+        ksteps = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            host_step()
+        if world > 1:
+            dist.barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": cells_total * ksteps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": cells_total * 4,
+               "d2h_bytes_per_step": cells_total * 9, "steps": ksteps,
+               "api": "bands.BandedChain.run (pinned host band in, filled+dir+acc out per rank)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    cells = cells_local  # rank 0's share, for the per-kernel roofline
+    pass_ms = {}
+    for k, (cnt, tot, mx) in prof.items():
+        pass_ms[KERNEL_PASS.get(k, "other")] = pass_ms.get(KERNEL_PASS.get(k, "other"), 0.0) + tot / args.steps
+    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
+    roof = None
+    if dom:
+        name, (cnt, tot, mx) = dom
+        pname = KERNEL_PASS.get(name, "other")
+        avg_ms = tot / cnt
+        alg_bytes = BYTES_PER_CELL.get(pname, 0) * (cells // nl)
+        if pname == "flats":
+            alg_bytes = BYTES_PER_CELL["d8"] * (cells // nl)
+        ach = alg_bytes / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "pass": pname, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "launches_per_step": cnt / args.steps,
+                "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "step_share": tot / args.steps / (ms_max / args.steps)}
+    kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t_ / args.steps} for k, (c, t_, m) in
+               sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    passes = {p_: {"ms_per_step": v,
+                   "hbm_frac_algorithmic": (BYTES_PER_CELL.get(p_, 0) * cells / (v * 1e-3) / 1e9 / peak) if v > 0 else None}
+              for p_, v in pass_ms.items()}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl + "; fill + D8 + flat resolution + accumulation, TauDEM semantics; bowls centred on "
+                                    "every seam and one plateau across the first seam; halo + seam-graph exchange by "
+                                    "all_gather over NCCL",
+                   "cells_total": cells_total, "cells_per_gpu": cells_local, "bands": nbands,
+                   "l2": "every band's rasters exceed the 126 MB L2; no explicit flush", "flats": bool(args.flats),
+                   "flat_exchange_rounds": flat_rounds, "band_stats_rank0": stats,
+                   "algorithmic_bytes_per_cell": 18, "checks": chk},
+        "roofline": roof, "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "hbm_frac_algorithmic_whole_step": 18 * cells_local / (ms_max / args.steps * 1e-3) / 1e9 / peak,
+        "passes": passes, "kernels": kernels,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,6 +348,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=5400, help="edge of the crop timed on the CPU (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flats", type=int, default=1)
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "bands", "c3"],
+                    help="auto: c2 (one 10801^2 DEM) at N=1, bands (one 10801 x 10801*N DEM, a band per GPU, seam "
+                         "exchange over NCCL) at N>1; c3: the 40000^2 DEM row-band-sharded over the N GPUs")
+    ap.add_argument("--local-bands", type=int, default=1, help="bands per rank (N=1 with >1 emulates the exchange)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -182,7 +371,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION would print a banner there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.workload == "auto":
+        args.workload = "c2" if world == 1 and args.local_bands == 1 else "bands"
+    if args.workload in ("bands", "c3"):
+        return run_banded(args, world, rank, local, dev)
 
     ny = nx = args.size
     cells = ny * nx

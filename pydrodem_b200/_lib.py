@@ -134,18 +134,19 @@ def destroy_context(ctx):
     load().hc_destroy(ctx)
 
 
-def launch_count(device=0):
-    return int(load().hc_launch_count(context(device)))
+def launch_count(device=0, ctx=None):
+    return int(load().hc_launch_count(ctx if ctx is not None else context(device)))
 
 
-def profile_enable(on=True, device=0, max_records=16384):
-    check(load().hc_profile_enable(context(device), int(bool(on)), int(max_records)), "hc_profile_enable")
+def profile_enable(on=True, device=0, max_records=16384, ctx=None):
+    check(load().hc_profile_enable(ctx if ctx is not None else context(device), int(bool(on)), int(max_records)),
+          "hc_profile_enable")
 
 
-def profile_read(device=0):
+def profile_read(device=0, ctx=None):
     """{kernel_name: (launches, total_ms, max_ms)} since the last read; synchronises the device."""
     buf = ctypes.create_string_buffer(1 << 16)
-    check(load().hc_profile_read(context(device), buf, len(buf)), "hc_profile_read")
+    check(load().hc_profile_read(ctx if ctx is not None else context(device), buf, len(buf)), "hc_profile_read")
     out = {}
     for line in buf.value.decode().splitlines():
         name, cnt, tot, mx = line.split()

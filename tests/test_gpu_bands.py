@@ -70,3 +70,19 @@ def test_banded_rejects_wbt_seed(cuda):
     with pytest.raises(_lib.HydrocoreError):
         ch.run([z[:10], z[10:]])
     ch.close()
+
+
+def test_bands_over_nccl_two_ranks(cuda):
+    """One band per GPU with the real NCCL exchange (needs >= 2 GPUs; the single-GPU box skips)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests/test_gpu_bands.py -k nccl)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "run_bands_nccl.py"), "--ny", "2500",
+           "--nx", "1800", "--full"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "BANDS_NCCL_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
