@@ -60,6 +60,21 @@ class SeamComm:
         return bool(t.item())
 
 
+def exchange_halos(bufs, first, nbands, comm):
+    """bufs: this process's halo'd band rasters [(nb+2), nx] (consecutive global bands first, first+1, ...).
+    Row 0 / row -1 of each are overwritten with the neighbouring band's last / first own row: ONE all_gather of
+    the [nlocal, 2, nx] seam rows.  Works on CPU tensors over gloo as well (tests)."""
+    import torch
+    seams = torch.stack([torch.stack((b[1], b[-2])) for b in bufs])  # [nl, 2, nx]
+    allseams = comm.gather(seams)
+    for i, b in enumerate(bufs):
+        g = first + i
+        if g > 0:
+            b[0].copy_(allseams[g - 1, 1])
+        if g < nbands - 1:
+            b[-1].copy_(allseams[g + 1, 0])
+
+
 class BandedChain:
     """The chain on this process's bands.  `band_rows`: rows of each LOCAL band (consecutive global
     bands first_band, first_band+1, ...); `nbands`: bands in the whole DEM."""
@@ -118,15 +133,7 @@ class BandedChain:
 
     def _halo_exchange(self, bufs):
         """Fill the halo rows of every local band from its neighbours' seam rows."""
-        torch = self.torch
-        seams = torch.stack([torch.stack((b[1], b[-2])) for b in bufs])  # [nl, 2, nx]
-        allseams = self.comm.gather(seams)
-        for i, b in enumerate(bufs):
-            g = self.first + i
-            if g > 0:
-                b[0].copy_(allseams[g - 1, 1])
-            if g < self.nbands - 1:
-                b[-1].copy_(allseams[g + 1, 0])
+        exchange_halos(bufs, self.first, self.nbands, self.comm)
 
     def _chk(self, rc, what):
         _lib.check(rc, what)
