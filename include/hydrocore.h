@@ -161,10 +161,11 @@ int hc_band_flats_get_seams_dev(hc_ctx *ctx, uint32_t *out, void *stream);
 int hc_band_flats_put_halos_dev(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int *changed, void *stream);
 int hc_band_flats_relax_dev(hc_ctx *ctx, void *stream);
 int hc_band_flats_finish_dev(hc_ctx *ctx, void *stream);
-/* accumulation: local publishes uint32 [2 sides][2 fields exit_of,bout][nx]; finish takes all bands'
- * records (band order), solves the seam forest and writes the band's counts. dir carries halo rows. */
-int hc_band_accum_local_dev(hc_ctx *ctx, const uint8_t *dir, int64_t nb, int64_t nx, int table, int flags,
-                            uint32_t *seam_out, void *stream);
+/* accumulation: local writes the band-local counts into acc and publishes uint32
+ * [2 sides][2 fields exit_of,bout][nx]; finish takes all bands' records (band order), solves the seam
+ * forest and completes the SAME acc raster. dir carries halo rows. */
+int hc_band_accum_local_dev(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t nb, int64_t nx, int table,
+                            int flags, uint32_t *seam_out, void *stream);
 int hc_band_accum_finish_dev(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index,
                              uint32_t *acc, void *stream);
 /* diagnostics of the last banded fill: terminal-graph edges emitted, MSF rounds, seam-graph rounds */

@@ -58,7 +58,7 @@ SIGNATURES = {
     "hc_band_flats_put_halos_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(ctypes.c_int), c_vp]),
     "hc_band_flats_relax_dev": (ctypes.c_int, [c_vp, c_vp]),
     "hc_band_flats_finish_dev": (ctypes.c_int, [c_vp, c_vp]),
-    "hc_band_accum_local_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "hc_band_accum_local_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "hc_band_accum_finish_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "hc_band_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "hc_profile_enable": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),

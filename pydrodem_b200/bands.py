@@ -201,7 +201,8 @@ class BandedChain:
                 self._halo_exchange(self.db)
             # accumulation
             for i, nb in enumerate(self.rows):
-                self._chk(lib.hc_band_accum_local_dev(self.ctx[i], self._p(self.db[i]), nb, nx, self.table, self.flags(i),
+                self._chk(lib.hc_band_accum_local_dev(self.ctx[i], self._p(self.db[i]), ctypes.c_void_p(self.acc[i].data_ptr()), nb, nx,
+                                                      self.table, self.flags(i),
                                                       ctypes.c_void_p(self.aseam[i].data_ptr()), st),
                           "hc_band_accum_local_dev")
             alls = self.comm.gather(self.aseam)

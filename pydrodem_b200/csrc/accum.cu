@@ -8,16 +8,17 @@
 // of Barnes 2017, "Parallel non-divergent flow accumulation for trillion cell DEMs", with a GPU
 // tile as the unit):
 //
-//   A  k_acc_tile<false>  per 64x64 tile, in shared memory: in-tile in-degrees, dependency walk
+//   A  k_acc_tile_local   per 64x64 tile, in shared memory: in-tile in-degrees, dependency walk
 //                         with one shared-memory atomicAdd per hop, giving every cell's LOCAL
-//                         count; pointer jumping gives, for each perimeter cell, the perimeter
-//                         cell through which its in-tile path leaves the tile.  Only perimeter
-//                         records leave the SM (256 slots per tile).
+//                         count (written to the raster); each perimeter cell walks its in-tile
+//                         path to the perimeter cell through which it leaves the tile.  Perimeter
+//                         records go to 256 slots per tile.
 //   B  k_acc_link*        the same dependency walk on the graph of tile-exit cells (one global
 //                         atomic per TILE crossing instead of per cell), which also deposits the
 //                         inflow every tile-entry cell receives from outside its tile.
-//   C  k_acc_tile<true>   phase A again with the entry cells' weights raised by their inflow;
-//                         writes the final uint32 raster.
+//   C  k_acc_tile_final   counts are linear in the entry inflows: every entry cell with inflow
+//                         adds it along its in-tile path (fire-and-forget shared reductions, no
+//                         dependency waits) on top of the local counts.
 //
 // A cell's state word packs [count : high bits | pending-upstream counter : low bits]; a delivery
 // is ONE atomicAdd of ((count << S) - 1): it credits the count and retires a dependency at once,
@@ -43,21 +44,39 @@ __device__ __forceinline__ int perim_slot(int lr, int lc, int hr, int hc) {
   return -1;
 }
 
-template <int TABLE, bool FINAL>
+// neighbour offsets from packed immediates (a dynamic index into __constant__ tables serialises
+// when the lanes of a warp disagree): 2-bit fields holding offset + 1, slot k = 0..7
+__host__ __device__ constexpr u32 pack_offsets(int a0, int a1, int a2, int a3, int a4, int a5, int a6, int a7) {
+  return (u32)(a0 + 1) | (u32)(a1 + 1) << 2 | (u32)(a2 + 1) << 4 | (u32)(a3 + 1) << 6 | (u32)(a4 + 1) << 8 |
+         (u32)(a5 + 1) << 10 | (u32)(a6 + 1) << 12 | (u32)(a7 + 1) << 14;
+}
+template <int TABLE>
+__device__ __forceinline__ void k_to_drdc(int k, int &dr, int &dc) {
+  constexpr u32 DRW = TABLE == HC_TABLE_WBT ? pack_offsets(-1, 0, 1, 1, 1, 0, -1, -1) : pack_offsets(0, -1, -1, -1, 0, 1, 1, 1);
+  constexpr u32 DCW = TABLE == HC_TABLE_WBT ? pack_offsets(1, 1, 1, 0, -1, -1, -1, 0) : pack_offsets(1, 1, 0, -1, -1, -1, 0, 1);
+  dr = (int)((DRW >> (2 * k)) & 3u) - 1;
+  dc = (int)((DCW >> (2 * k)) & 3u) - 1;
+}
+
+// packed per-cell word of the local pass: [count:14 @17 | pending-upstream:4 @13 | downstream:13 @0]
+#define W_DN 0x1FFFu
+#define W_NONE 0x1FFFu   // no downstream (terminal)
+#define W_EXIT 0x1FFEu   // downstream is a valid cell outside the tile
+#define W_PEND_ONE (1u << 13)
+#define W_PEND(w) (((w) >> 13) & 15u)
+#define W_CNT(w) ((w) >> 17)
+
+// Phase A: per tile, local counts by a dependency walk in shared memory.  One 32-bit shared atomic
+// per hop: it credits the count, retires a dependency, and its return value carries the target's
+// own downstream pointer, so the walk needs no other load.  Writes the local counts to `acc` and the
+// perimeter records (exit slot, downstream slot, exit count) phase B works on.
+template <int TABLE>
 __global__ void __launch_bounds__(NTHREADS)
-k_acc_tile(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsigned short *__restrict__ pexit,
-           u32 *__restrict__ pdown, u32 *__restrict__ pinflow, uint32_t *__restrict__ acc, int ny, int nx,
-           unsigned long long *dbg, hc_rows rw) {
-  // 32-bit shared-memory atomics only (64-bit ones are CAS spin loops):
-  //   local pass : st = [count:24 | pending:8]  (an in-tile count is at most 4096)
-  //   final pass : counts reach 2^31, so count (sacc) and pending counter (st) are separate words
-  // (measured alternatives that were NOT faster: in-degree by 8-neighbour gather, plain updates for
-  //  single-contributor cells, one-hop-per-iteration walk with immediate source refill)
+k_acc_tile_local(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsigned short *__restrict__ pexit,
+                 u32 *__restrict__ pdown, u32 *__restrict__ pinflow, uint32_t *__restrict__ acc, int ny, int nx,
+                 hc_rows rw) {
   __shared__ uint8_t sd[TH * TH];
-  __shared__ unsigned short dn[T * T];
   __shared__ u32 st[T * T];
-  __shared__ u32 sacc[FINAL ? T * T : 1];
-  __shared__ unsigned short jmp[FINAL ? 1 : T * T];
 
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
@@ -74,101 +93,75 @@ k_acc_tile(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsigned s
   }
   __syncthreads();
 
-  // downstream slot and initial state of every cell (pending counters start at 0)
   for (int i = tid; i < T * T; i += NTHREADS) {
     int lr = i >> 6, lc = i & (T - 1);
-    unsigned short down = DN_NONE;
-    u32 weight = 0;
-    int ci = (lr + 1) * TH + lc + 1;
-    int d = sd[ci];
+    u32 down = W_NONE, weight = 0;
+    int d = sd[(lr + 1) * TH + lc + 1];
     if (d != HC_DIR_NODATA && lr < hr && lc < hc) {
       int k = d_code_to_k(TABLE, d);
       if (k >= 0) {
-        int nr = lr + c_dr[TABLE][k], nc = lc + c_dc[TABLE][k];
+        int dr, dc;
+        k_to_drdc<TABLE>(k, dr, dc);
+        int nr = lr + dr, nc = lc + dc;
         if (sd[(nr + 1) * TH + nc + 1] != HC_DIR_NODATA)
-          down = (nr >= 0 && nr < hr && nc >= 0 && nc < hc) ? (unsigned short)(nr * T + nc) : (unsigned short)DN_EXIT;
+          down = (nr >= 0 && nr < hr && nc >= 0 && nc < hc) ? (u32)(nr * T + nc) : W_EXIT;
       }
       weight = 1;
-      if (FINAL) {
-        int s = perim_slot(lr, lc, hr, hc);
-        if (s >= 0) weight += __ldcg(&pinflow[(size_t)tile * PSLOTS + s]);
-      }
     }
-    dn[i] = down;
-    if (FINAL) { st[i] = 0; sacc[i] = weight; }
-    else st[i] = weight << 8;
+    st[i] = down | (weight << 17);
   }
   __syncthreads();
   // in-tile in-degree by scatter: one shared atomic per cell
   for (int i = tid; i < T * T; i += NTHREADS) {
-    unsigned short d = dn[i];
-    if (d < DN_EXIT) atomicAdd(&st[d], 1u);
+    u32 d = st[i] & W_DN;   // the low 13 bits never change
+    if (d < W_EXIT) atomicAdd(&st[d], W_PEND_ONE);
   }
   __syncthreads();
-  // sources = cells nobody in the tile drains into; remembered before any counter can reach 0 again
+  // sources = valid cells nobody in the tile drains into; remembered before any counter can reach 0 again
   u32 srcmask = 0;
 #pragma unroll
   for (int j = 0; j < T * T / NTHREADS; j++) {
-    int i = tid + j * NTHREADS;
-    if ((st[i] & 0xFFu) == 0u && sd[((i >> 6) + 1) * TH + (i & (T - 1)) + 1] != HC_DIR_NODATA) srcmask |= 1u << j;
+    u32 w = st[tid + j * NTHREADS];
+    if (W_PEND(w) == 0u && W_CNT(w) != 0u) srcmask |= 1u << j;
   }
   __syncthreads();
-
-  // dependency walk from the in-tile sources
   for (int j = 0; j < T * T / NTHREADS; j++) {
     if (!(srcmask & (1u << j))) continue;
-    int i = tid + j * NTHREADS;
-    int cur = i;
-    if (FINAL) {
-      u32 a = sacc[i];
-      for (;;) {
-        unsigned short d = dn[cur];
-        if (d >= DN_EXIT) break;
-        atomicAdd(&sacc[d], a);
-        __threadfence_block();
-        u32 old = atomicSub(&st[d], 1u);
-        if (old != 1u) break;
-        a = *((volatile u32 *)&sacc[d]);
-        cur = d;
-      }
-    } else {
-      u32 a = st[i] >> 8;
-      for (;;) {
-        unsigned short d = dn[cur];
-        if (d >= DN_EXIT) break;
-        u32 old = atomicAdd(&st[d], (a << 8) - 1u);
-        if ((old & 0xFFu) != 1u) break;
-        a += old >> 8;
-        cur = d;
-      }
+    u32 w = st[tid + j * NTHREADS];
+    u32 a = W_CNT(w), d = w & W_DN;
+    while (d < W_EXIT) {
+      u32 old = atomicAdd(&st[d], (a << 17) - W_PEND_ONE);
+      if (W_PEND(old) != 1u) break;
+      a += W_CNT(old);
+      d = old & W_DN;
     }
   }
   __syncthreads();
 
-  if (FINAL) {
-    for (int i = tid; i < T * T; i += NTHREADS) {
-      int lr = i >> 6, lc = i & (T - 1);
-      if (lr < hr && lc < hc) acc[(size_t)(r0 + lr) * nx + (c0 + lc)] = sacc[i];
-    }
-    return;
+  // local counts -> raster (phase C adds the inflow from other tiles along the in-tile paths)
+  for (int i = tid; i < T * T; i += NTHREADS) {
+    int lr = i >> 6, lc = i & (T - 1);
+    if (lr < hr && lc < hc) acc[(size_t)(r0 + lr) * nx + (c0 + lc)] = W_CNT(st[i]);
   }
 
-  // phase A epilogue: perimeter records
+  // perimeter records: thread t owns perimeter slot t
   u64 my_state = 0;
   u32 my_down = HC_NONE;
-  int my_cell = -1;
+  unsigned short ex = NOSLOT;
   {
-    // thread t owns perimeter slot t
     int s = tid, lr = -1, lc = -1;
     if (s < T) { lr = 0; lc = s; }
     else if (s < 2 * T) { lr = hr - 1; lc = s - T; if (hr == 1) lr = -1; }
     else if (s < 3 * T) { lr = s - 2 * T; lc = 0; if (lr == 0 || lr >= hr - 1) lr = -1; }
     else { lr = s - 3 * T; lc = hc - 1; if (lr == 0 || lr >= hr - 1 || hc == 1) lr = -1; }
     if (lr >= 0 && lr < hr && lc >= 0 && lc < hc) {
-      my_cell = lr * T + lc;
-      if (dn[my_cell] == DN_EXIT) {
+      const int my_cell = lr * T + lc;
+      u32 w = st[my_cell];
+      if ((w & W_DN) == W_EXIT) {
         int k = d_code_to_k(TABLE, sd[(lr + 1) * TH + lc + 1]);
-        int gr = r0 + lr + c_dr[TABLE][k], gc = c0 + lc + c_dc[TABLE][k];
+        int dr, dc;
+        k_to_drdc<TABLE>(k, dr, dc);
+        int gr = r0 + lr + dr, gc = c0 + lc + dc;
         if (gr < 0) my_down = BAND_EXIT | (u32)gc;
         else if (gr >= ny) my_down = BAND_EXIT | 0x40000000u | (u32)gc;
         else {
@@ -177,35 +170,87 @@ k_acc_tile(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsigned s
           int s2 = perim_slot(gr - tyy * T, gc - txx * T, hr2, hc2);
           my_down = (u32)((tyy * gridDim.x + txx) * PSLOTS + s2);
         }
-        my_state = (u64)(st[my_cell] >> 8) << 16;  // [local count : 48 | feeders : 16]
+        my_state = (u64)W_CNT(w) << 16;  // [local count : 48 | feeders : 16]
+      }
+      // the perimeter cell through which this cell's in-tile path leaves the tile (a D8 forest has no
+      // cycles; the hop cap only guards against a malformed direction raster)
+      int cur = my_cell;
+      u32 d = w & W_DN;
+      for (int hop = 0; d < W_EXIT && hop < T * T; hop++) { cur = (int)d; d = st[cur] & W_DN; }
+      if (d == W_EXIT) ex = (unsigned short)perim_slot(cur >> 6, cur & (T - 1), hr, hc);
+    }
+  }
+  size_t g = (size_t)tile * PSLOTS + tid;
+  pexit[g] = ex;
+  pdown[g] = my_down;
+  pstate[g] = my_state;
+  pinflow[g] = 0;
+}
+
+// Phase C: add the inflow every tile-entry cell receives from outside its tile along that cell's
+// in-tile path (plain shared-memory reductions, no dependency waits), on top of the local counts.
+template <int TABLE>
+__global__ void __launch_bounds__(NTHREADS)
+k_acc_tile_final(const uint8_t *__restrict__ dir, const u32 *__restrict__ pinflow, uint32_t *__restrict__ acc,
+                 int ny, int nx) {
+  __shared__ uint8_t sd[T * T];
+  __shared__ unsigned short dn[T * T];
+  __shared__ u32 sacc[T * T];
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  const int hr = min(T, ny - r0), hc = min(T, nx - c0);
+  const int tid = threadIdx.x;
+
+  const u32 X = __ldg(&pinflow[(size_t)tile * PSLOTS + tid]);
+  if (!__syncthreads_or(X != 0u)) return;  // nothing flows into this tile: the local counts are final
+
+#pragma unroll 4
+  for (int i = tid; i < T * T; i += NTHREADS) {
+    int lr = i >> 6, lc = i & (T - 1);
+    bool inb = lr < hr && lc < hc;
+    size_t g = inb ? (size_t)(r0 + lr) * nx + (c0 + lc) : 0;
+    uint8_t d = __ldg(&dir[g]);
+    u32 a = __ldcg(&acc[g]);
+    sd[i] = inb ? d : (uint8_t)HC_DIR_NODATA;
+    sacc[i] = inb ? a : 0u;
+  }
+  __syncthreads();
+  for (int i = tid; i < T * T; i += NTHREADS) {
+    int lr = i >> 6, lc = i & (T - 1);
+    unsigned short down = DN_NONE;
+    int d = sd[i];
+    if (d != HC_DIR_NODATA) {
+      int k = d_code_to_k(TABLE, d);
+      if (k >= 0) {
+        int dr, dc;
+        k_to_drdc<TABLE>(k, dr, dc);
+        int nr = lr + dr, nc = lc + dc;
+        if (nr >= 0 && nr < hr && nc >= 0 && nc < hc && sd[nr * T + nc] != HC_DIR_NODATA) down = (unsigned short)(nr * T + nc);
+      }
+    }
+    dn[i] = down;
+  }
+  __syncthreads();
+  if (X) {
+    int s = tid, lr = -1, lc = -1;
+    if (s < T) { lr = 0; lc = s; }
+    else if (s < 2 * T) { lr = hr - 1; lc = s - T; if (hr == 1) lr = -1; }
+    else if (s < 3 * T) { lr = s - 2 * T; lc = 0; if (lr == 0 || lr >= hr - 1) lr = -1; }
+    else { lr = s - 3 * T; lc = hc - 1; if (lr == 0 || lr >= hr - 1 || hc == 1) lr = -1; }
+    if (lr >= 0 && lr < hr && lc >= 0 && lc < hc && sd[lr * T + lc] != HC_DIR_NODATA) {
+      int cur = lr * T + lc;
+      for (int hop = 0; hop < T * T; hop++) {
+        atomicAdd(&sacc[cur], X);
+        unsigned short d = dn[cur];
+        if (d >= DN_EXIT) break;
+        cur = d;
       }
     }
   }
-  for (int i = tid; i < T * T; i += NTHREADS) {
-    unsigned short d = dn[i];
-    jmp[i] = d >= DN_EXIT ? (unsigned short)i : d;
-  }
   __syncthreads();
-  for (;;) {
-    int changed = 0;
-    for (int i = tid; i < T * T; i += NTHREADS) {
-      unsigned short p = jmp[i];
-      unsigned short pp = jmp[p];
-      if (pp != p) { jmp[i] = pp; changed = 1; }
-    }
-    if (!__syncthreads_or(changed)) break;
-  }
-  {
-    size_t g = (size_t)tile * PSLOTS + tid;
-    unsigned short ex = NOSLOT;
-    if (my_cell >= 0) {
-      int root = jmp[my_cell];
-      if (dn[root] == DN_EXIT) ex = (unsigned short)perim_slot(root / T, root % T, hr, hc);
-    }
-    pexit[g] = ex;
-    pdown[g] = my_down;
-    pstate[g] = my_state;
-    pinflow[g] = 0;
+  for (int i = tid; i < T * T; i += NTHREADS) {
+    int lr = i >> 6, lc = i & (T - 1);
+    if (lr < hr && lc < hc) acc[(size_t)(r0 + lr) * nx + (c0 + lc)] = sacc[i];
   }
 }
 
@@ -266,7 +311,8 @@ size_t accum_workspace(int64_t ny, int64_t nx) {
 
 // phases A + B (tile-local counts, then the walk over tile crossings); state left in ctx->band
 template <int TABLE>
-static int accum_local_impl(hc_ctx *ctx, const uint8_t *dir, int64_t ny, int64_t nx, hc_rows rw, cudaStream_t st) {
+static int accum_local_impl(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_t nx, hc_rows rw,
+                            cudaStream_t st) {
   hc_band_state *bs = &ctx->band;
   const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t nslots = (size_t)tx * ty * PSLOTS;
@@ -282,7 +328,7 @@ static int accum_local_impl(hc_ctx *ctx, const uint8_t *dir, int64_t ny, int64_t
   dim3 tg(tx, ty);
   unsigned sb = (unsigned)((nslots + 255) / 256);
   HC_PROF(ctx, st, "k_acc_tile_local");
-  k_acc_tile<TABLE, false><<<tg, NTHREADS, 0, st>>>(dir, pstate, pexit, pdown, pinflow, nullptr, (int)ny, (int)nx, ctx->d_dbg, rw);
+  k_acc_tile_local<TABLE><<<tg, NTHREADS, 0, st>>>(dir, pstate, pexit, pdown, pinflow, acc, (int)ny, (int)nx, rw);
   HC_LAUNCH_CHECK(ctx);
   HC_PROF(ctx, st, "k_acc_link_count");
   k_acc_link_count<<<sb, 256, 0, st>>>(pstate, pexit, pdown, nslots);
@@ -302,7 +348,8 @@ static int accum_final_impl(hc_ctx *ctx, uint32_t *acc, hc_rows rw, cudaStream_t
   const int64_t ny = bs->nb, nx = bs->nx;
   dim3 tg((unsigned)((nx + T - 1) / T), (unsigned)((ny + T - 1) / T));
   HC_PROF(ctx, st, "k_acc_tile_final");
-  k_acc_tile<TABLE, true><<<tg, NTHREADS, 0, st>>>(bs->dir, bs->pstate, bs->pexit, bs->pdown, bs->pinflow, acc, (int)ny, (int)nx, ctx->d_dbg, rw);
+  (void)rw;
+  k_acc_tile_final<TABLE><<<tg, NTHREADS, 0, st>>>(bs->dir, bs->pinflow, acc, (int)ny, (int)nx);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
@@ -314,10 +361,10 @@ int accum_run(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_
   HC_TRY(arena_reset(ctx));
   hc_rows rw = hc_make_rows(ny, 0);
   if (table == HC_TABLE_WBT) {
-    HC_TRY(accum_local_impl<HC_TABLE_WBT>(ctx, dir, ny, nx, rw, st));
+    HC_TRY(accum_local_impl<HC_TABLE_WBT>(ctx, dir, acc, ny, nx, rw, st));
     return accum_final_impl<HC_TABLE_WBT>(ctx, acc, rw, st);
   }
-  HC_TRY(accum_local_impl<HC_TABLE_TAUDEM>(ctx, dir, ny, nx, rw, st));
+  HC_TRY(accum_local_impl<HC_TABLE_TAUDEM>(ctx, dir, acc, ny, nx, rw, st));
   return accum_final_impl<HC_TABLE_TAUDEM>(ctx, acc, rw, st);
 }
 
@@ -453,7 +500,7 @@ k_acc_seam_apply(const unsigned short *__restrict__ pexit, const u32 *__restrict
   }
 }
 
-int band_accum_local(hc_ctx *ctx, const uint8_t *dir, int64_t nb, int64_t nx, int table, int flags,
+int band_accum_local(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t nb, int64_t nx, int table, int flags,
                      uint32_t *seam_out, cudaStream_t st) {
   if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("accum: bad table %d", table); return HC_ERR_ARG; }
   if (nx >= (1 << 30)) { hc_set_error("band too wide"); return HC_ERR_TOO_LARGE; }
@@ -461,8 +508,8 @@ int band_accum_local(hc_ctx *ctx, const uint8_t *dir, int64_t nb, int64_t nx, in
   hc_band_state *bs = &ctx->band;
   hc_rows rw = hc_make_rows(nb, flags);
   bs->flags = flags; bs->table = table;
-  if (table == HC_TABLE_WBT) HC_TRY(accum_local_impl<HC_TABLE_WBT>(ctx, dir, nb, nx, rw, st));
-  else HC_TRY(accum_local_impl<HC_TABLE_TAUDEM>(ctx, dir, nb, nx, rw, st));
+  if (table == HC_TABLE_WBT) HC_TRY(accum_local_impl<HC_TABLE_WBT>(ctx, dir, acc, nb, nx, rw, st));
+  else HC_TRY(accum_local_impl<HC_TABLE_TAUDEM>(ctx, dir, acc, nb, nx, rw, st));
   if (!(flags & 3)) HC_CUDA(cudaMemsetAsync(bs->bout, 0, (size_t)2 * nx * 4, st));
   u32 *err = (u32 *)arena_take(ctx, 256);
   if (!err) return HC_ERR_NOMEM;

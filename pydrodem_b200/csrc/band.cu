@@ -67,12 +67,12 @@ extern "C" int hc_band_flats_finish_dev(hc_ctx *ctx, void *stream) {
   return band_flats_finish(ctx, (cudaStream_t)stream);
 }
 
-extern "C" int hc_band_accum_local_dev(hc_ctx *ctx, const uint8_t *dir, int64_t nb, int64_t nx, int table, int flags,
-                                       uint32_t *seam_out, void *stream) {
+extern "C" int hc_band_accum_local_dev(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t nb, int64_t nx, int table,
+                                       int flags, uint32_t *seam_out, void *stream) {
   CHECK_CTX(ctx);
   HC_TRY(check_band(nb, nx, flags));
-  if (!dir || !seam_out) { hc_set_error("hc_band_accum_local: null pointer"); return HC_ERR_ARG; }
-  return band_accum_local(ctx, dir, nb, nx, table, flags, seam_out, (cudaStream_t)stream);
+  if (!dir || !acc || !seam_out) { hc_set_error("hc_band_accum_local: null pointer"); return HC_ERR_ARG; }
+  return band_accum_local(ctx, dir, acc, nb, nx, table, flags, seam_out, (cudaStream_t)stream);
 }
 extern "C" int hc_band_accum_finish_dev(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index,
                                         uint32_t *acc, void *stream) {

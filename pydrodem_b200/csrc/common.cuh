@@ -170,7 +170,7 @@ int band_flats_get_seams(hc_ctx *ctx, uint32_t *out, cudaStream_t st);
 int band_flats_put_halos(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int *changed, cudaStream_t st);
 int band_flats_relax(hc_ctx *ctx, cudaStream_t st);
 int band_flats_finish(hc_ctx *ctx, cudaStream_t st);
-int band_accum_local(hc_ctx *ctx, const uint8_t *dir, int64_t nb, int64_t nx, int table, int flags,
+int band_accum_local(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t nb, int64_t nx, int table, int flags,
                      uint32_t *seam_out, cudaStream_t st);
 int band_accum_finish(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index, uint32_t *acc,
                       cudaStream_t st);

@@ -72,9 +72,11 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
   }
   __syncthreads();
   // 1b. NOFLOW flag; non-rim NOFLOW cells go on the work list
-  for (int i = tid; i < FR * FR; i += NTHREADS) {
+  for (int i0 = 0; i0 < FR * FR; i0 += NTHREADS) {  // FR*FR is a multiple of NTHREADS: warps stay whole
+    const int i = i0 + tid;
     u32 w = 0;
     float v = sz[i];
+    bool want = false;
     if (v == v && shi[i] == HC_DIR_NOFLOW) {
       int lr = i / FR, lc = i - lr * FR;
       // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
@@ -82,9 +84,17 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
       // ... and a NOFLOW cell of a band's halo row belongs to the neighbouring band: open too
       int r = r0 + lr;
       if (lr == 0 || lc == 0 || lr == FR - 1 || lc == FR - 1 || r < 0 || r >= ny) w = F_NF | F_OPEN;
-      else {
-        w = F_NF;
-        u32 k = atomicAdd(&s_n[0], 1u);
+      else { w = F_NF; want = true; }
+    }
+    // warp-aggregated append: one shared atomic per warp instead of one per NOFLOW cell
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, want);
+    if (bal) {
+      const int lane = tid & 31;
+      u32 base = 0;
+      if (lane == 0) base = atomicAdd(&s_n[0], (u32)__popc(bal));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (want) {
+        u32 k = base + (u32)__popc(bal & ((1u << lane) - 1u));
         if (k < FLCAP) list[k] = (unsigned short)i;
       }
     }
@@ -336,27 +346,38 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
   }
   __syncthreads();
 #pragma unroll 4
-  for (int i = tid; i < TH * TH; i += NTHREADS) {
-    int lr = i / TH, lc = i - lr * TH;
+  for (int i0 = 0; i0 < TH * TH; i0 += NTHREADS) {
+    const int i = i0 + tid;
+    const bool ivalid = i < TH * TH;
+    int lr = ivalid ? i / TH : 0, lc = ivalid ? i - lr * TH : 0;
     int r = r0 + lr - 1, c = c0 + lc - 1;
     // halo cells of tiles outside the active set hold no state: treat as not in any flat
     int ay = lr == 0 ? 0 : (lr == TH - 1 ? 2 : 1), ax = lc == 0 ? 0 : (lc == TH - 1 ? 2 : 1);
     // (a band's halo rows hold the neighbouring band's state, refreshed between relaxations)
     bool halo_row = (r == -1 && rw.top) || (r == ny && rw.bot);
-    bool inb = c >= 0 && c < nx && ((r >= 0 && r < ny && s_act[ay * 3 + ax]) || halo_row);
+    bool inb = ivalid && c >= 0 && c < nx && ((r >= 0 && r < ny && s_act[ay * 3 + ax]) || halo_row);
     long long g = inb ? (long long)r * nx + c : 0;
     float v = __ldg(z + g);
     u32 lo = __ldcg(dlo + g);
     u32 hi = __ldcg(dhi + g);
     uint8_t f = __ldcg(nf + g);
-    if (!inb) { lo = 0; hi = 0; f = 0; }
-    if (f) {
-      lo |= R_NF;
-      if (lr >= 1 && lr <= T && lc >= 1 && lc <= T && r < ny) list[atomicAdd(&s_n, 1u)] = (unsigned short)(lr * TP + lc);
+    if (!inb || !ivalid) { lo = 0; hi = 0; f = 0; }
+    if (f) lo |= R_NF;
+    // warp-aggregated append to the work list (one shared atomic per warp)
+    const bool want = f && lr >= 1 && lr <= T && lc >= 1 && lc <= T && r < ny;
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, want);
+    if (bal) {
+      const int lane = tid & 31;
+      u32 base = 0;
+      if (lane == 0) base = atomicAdd(&s_n, (u32)__popc(bal));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (want) list[base + (u32)__popc(bal & ((1u << lane) - 1u))] = (unsigned short)(lr * TP + lc);
     }
-    sz[lr * TP + lc] = (inb && v != nodata) ? v : qnan;
-    slo[lr * TP + lc] = lo;
-    shi[lr * TP + lc] = hi;
+    if (ivalid) {
+      sz[lr * TP + lc] = (inb && v != nodata) ? v : qnan;
+      slo[lr * TP + lc] = lo;
+      shi[lr * TP + lc] = hi;
+    }
   }
   __syncthreads();
   const u32 nlist = s_n;
