@@ -125,15 +125,25 @@ k_acc_tile_local(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsi
     if (W_PEND(w) == 0u && W_CNT(w) != 0u) srcmask |= 1u << j;
   }
   __syncthreads();
-  for (int j = 0; j < T * T / NTHREADS; j++) {
-    if (!(srcmask & (1u << j))) continue;
-    u32 w = st[tid + j * NTHREADS];
-    u32 a = W_CNT(w), d = w & W_DN;
-    while (d < W_EXIT) {
-      u32 old = atomicAdd(&st[d], (a << 17) - W_PEND_ONE);
-      if (W_PEND(old) != 1u) break;
-      a += W_CNT(old);
-      d = old & W_DN;
+  // one merged loop: a lane whose chain ended fetches its next source in the same iteration the other
+  // lanes hop, so a warp iterates max over lanes of (sum of its chains), not sum over sources of the
+  // longest chain among the lanes
+  {
+    u32 a = 0, d = W_NONE;
+    for (;;) {
+      if (d >= W_EXIT) {
+        if (!srcmask) break;
+        int j = __ffs(srcmask) - 1;
+        srcmask &= srcmask - 1;
+        u32 w = st[tid + j * NTHREADS];
+        a = W_CNT(w);
+        d = w & W_DN;
+      }
+      if (d < W_EXIT) {
+        u32 old = atomicAdd(&st[d], (a << 17) - W_PEND_ONE);
+        if (W_PEND(old) != 1u) d = W_NONE;
+        else { a += W_CNT(old); d = old & W_DN; }
+      }
     }
   }
   __syncthreads();

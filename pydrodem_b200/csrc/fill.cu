@@ -49,52 +49,73 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
 
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const float qnan = __int_as_float(0x7fc00000);
   if (tid == 0) s_npit = 0;
 
-  for (int i = tid; i < TH * TH; i += NTHREADS) {
-    int lr = i / TH, lc = i - lr * TH;
-    int r = r0 + lr - 1, c = c0 + lc - 1;
-    float v = __int_as_float(0x7fc00000);
-    if (r >= rw.rlo && r < rw.rhi && c >= 0 && c < nx) {
-      v = __ldg(z + ((long long)r * nx + c));  // r may be -1 / ny: the band's halo rows
-      if (v == nodata) v = __int_as_float(0x7fc00000);
+  // tile + 1-cell halo -> shared; warp w takes rows w, w+8, ..., a lane columns lane, lane+32, lane+64
+  for (int lr = warp; lr < TH; lr += NTHREADS / 32) {
+    const int r = r0 + lr - 1;
+    const bool rok = r >= rw.rlo && r < rw.rhi;
+    const float *row = z + ((long long)r * nx + (c0 - 1));  // r may be -1 / ny: the band's halo rows
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const int lc = lane + 32 * m;
+      if (lc < TH) {
+        const int c = c0 + lc - 1;
+        float v = qnan;
+        if (rok && c >= 0 && c < nx) {
+          v = __ldg(row + lc);
+          if (v == nodata) v = qnan;
+        }
+        sz[lr * TH + lc] = v;
+      }
     }
-    sz[i] = v;
   }
   __syncthreads();
 
-  // pass A: classify, pick lowest neighbour, count pits
+  // pass A: classify, pick lowest neighbour, count pits.  Total order (z, row-major index): scanning
+  // the 3x3 window in row-major order with a strict "<" keeps the first minimum, i.e. the smallest
+  // index among equal elevations (the centre sits at position 4 of that scan).
+  const int rb0 = rw.top ? -1 : 0, rb1 = rw.bot ? -1 : ny - 1;  // raster-border rows of this band (-1: none)
   for (int i = tid; i < T * T; i += NTHREADS) {
-    int lr = i / T, lc = i - lr * T;
+    int lr = i >> 6, lc = i & (T - 1);
     int r = r0 + lr, c = c0 + lc;
     unsigned short nxt = (unsigned short)i;
     u32 tv = HC_NONE;  // nodata / outside raster
     if (r < ny && c < nx) {
-      float v = sz[(lr + 1) * TH + lc + 1];
+      const float *w = &sz[lr * TH + lc];  // top-left corner of the 3x3 window
+      const float v = w[TH + 1];
       if (v == v) {
+        // positions 3,2,1,0 (before the centre in index order) win ties against the centre and against
+        // later ones: scan them backwards with "<="; positions 5..8 need a strictly lower elevation
+        float bz = v;
+        int bk = 4;
+        bool anynan = false;
+#define HC_SCAN(K, OFF, CMP)                   \
+        {                                      \
+          float zn = w[OFF];                   \
+          anynan |= zn != zn;                  \
+          if (zn CMP bz) { bz = zn; bk = K; }  \
+        }
+        HC_SCAN(3, TH, <=) HC_SCAN(2, 2, <=) HC_SCAN(1, 1, <=) HC_SCAN(0, 0, <=)
+        HC_SCAN(5, TH + 2, <) HC_SCAN(6, 2 * TH, <) HC_SCAN(7, 2 * TH + 1, <) HC_SCAN(8, 2 * TH + 2, <)
+#undef HC_SCAN
+        // seeds: raster border, or next to nodata (to EXTERIOR nodata only under the WBT rule).  A NaN
+        // in the window that lies outside the raster can only belong to a border cell.
+        bool seed = r == rb0 || r == rb1 || c == 0 || c == nx - 1;
+        if (anynan && !seed) {
+          if (ext == nullptr) seed = true;
+          else {
+            for (int dr = -1; dr <= 1; dr++)
+              for (int dc = -1; dc <= 1; dc++) {
+                float zn = w[(dr + 1) * TH + dc + 1];
+                if (zn != zn && ext[(size_t)(r + dr) * nx + (c + dc)]) seed = true;
+              }
+          }
+        }
         // a band's seam rows (first / last own row next to another band) are not raster border
         const bool seam_t = rw.top && r == 0, seam_b = rw.bot && r == ny - 1;
-        bool seed = ((r == 0 && !rw.top) || c == 0 || (r == ny - 1 && !rw.bot) || c == nx - 1);
-        float bz = v;
-        int bdr = 0, bdc = 0;
-#pragma unroll
-        for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-          for (int dc = -1; dc <= 1; dc++) {
-            if (dr == 0 && dc == 0) continue;
-            float zn = sz[(lr + 1 + dr) * TH + lc + 1 + dc];
-            if (zn != zn) {
-              // nodata neighbour: seed if that nodata is exterior (ext == NULL: all nodata is)
-              int rr = r + dr, cc = c + dc;
-              if (rr >= rw.rlo && rr < rw.rhi && cc >= 0 && cc < nx) {
-                if (ext == nullptr || ext[(size_t)rr * nx + cc]) seed = true;
-              }
-              continue;
-            }
-            // total order (z, index): row-major index grows with (dr, dc) lexicographically
-            bool lower = zn < bz || (zn == bz && (dr < bdr || (dr == bdr && dc < bdc)));
-            if (lower) { bz = zn; bdr = dr; bdc = dc; }
-          }
         if (seam_t || seam_b) {
           // every seam cell is the root of its own "terminal" basin with a fixed id (Barnes 2016:
           // the tile perimeter); whether it is also a seed is remembered for the seam graph
@@ -103,10 +124,11 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
           seam_seed[sidx] = seed ? 1 : 0;
         } else if (seed) {
           tv = HC_TAG;  // basin 0
-        } else if (bdr == 0 && bdc == 0) {
+        } else if (bk == 4) {
           tv = HC_TAG | 0x7FFFFFFEu;  // pit, id patched below
           atomicAdd(&s_npit, 1u);
         } else {
+          const int bdr = bk / 3 - 1, bdc = bk - (bk / 3) * 3 - 1;
           int nlr = lr + bdr, nlc = lc + bdc;
           if (nlr >= 0 && nlr < T && nlc >= 0 && nlc < T) {
             nxt = (unsigned short)(nlr * T + nlc);
@@ -134,19 +156,26 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
   }
   __syncthreads();
 
-  // pass B: pointer jumping inside the tile until every cell points at a terminal
+  // pass B: pointer jumping inside the tile until every cell points at a terminal.  Terminals point
+  // at themselves and nothing else does, so "my target is its own target" means resolved: such a
+  // cell drops out of the live mask and is never touched again.
+  u32 live = 0xFFFFu;
   for (;;) {
     int changed = 0;
-    for (int i = tid; i < T * T; i += NTHREADS) {
+#pragma unroll
+    for (int j = 0; j < T * T / NTHREADS; j++) {
+      if (!(live & (1u << j))) continue;
+      const int i = tid + j * NTHREADS;
       unsigned short p = snxt[i];
       unsigned short pp = snxt[p];
       if (pp != p) { snxt[i] = pp; changed = 1; }
+      else live &= ~(1u << j);
     }
     if (!__syncthreads_or(changed)) break;
   }
 
   for (int i = tid; i < T * T; i += NTHREADS) {
-    int lr = i / T, lc = i - lr * T;
+    int lr = i >> 6, lc = i & (T - 1);
     int r = r0 + lr, c = c0 + lc;
     if (r < ny && c < nx) {
       u32 tv = stv[snxt[i]];

@@ -1,0 +1,15 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, pydrodem_b200 as hc
+from pydrodem_b200 import synth
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10801
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+dev = torch.device("cuda:0")
+z = torch.empty((n, n), dtype=torch.float32, device=dev)
+for r0 in range(0, n, 1024):
+    nr = min(1024, n - r0)
+    z[r0:r0 + nr] = synth.make_dem(n, n, 1002, row0=r0, nrows=nr, device=dev)
+kw = dict(dx=30.0, dy=30.0, seed_mode=1, table=1, flats=True, want_slope=False)
+for _ in range(reps):
+    hc.fill_d8_accum(z, **kw); torch.cuda.synchronize()
+print("done")
