@@ -171,6 +171,53 @@ int hc_band_accum_finish_dev(hc_ctx *ctx, const uint32_t *all_seams, int64_t nba
 /* diagnostics of the last banded fill: terminal-graph edges emitted, MSF rounds, seam-graph rounds */
 int hc_band_stats(const hc_ctx *ctx, int64_t *term_edges, int32_t *msf_rounds, int32_t *global_rounds);
 
+/* ---- Pit catalog / solution selection (tools/depressions.py:272-810, 1140-1228, 1471-1531) ----
+ * The reference's per-pit Python loops as segmented reductions keyed by the label rasters.  All
+ * pointers are DEVICE pointers; per-pit tables have npits+1 entries (entry 0 unused), per-carve tables
+ * ncarves+1.  Sums are accumulated in float64 and returned as float32 (the reference sums float32
+ * pairwise): tolerance 1e-5 relative on volfill / volcarve / volfillbehind, everything else exact. */
+/* generic: max / min / float64 sum / count of vals (may be NULL) per label in [lo_id, nseg], restricted
+ * to cells with sel[i] != 0 when sel is given; outputs may be NULL */
+int hc_seg_stats_dev(hc_ctx *ctx, const int32_t *ids, const float *vals, const int32_t *sel, int64_t n,
+                     int32_t nseg, int32_t lo_id, float *vmax, float *vmin, double *vsum, int64_t *count,
+                     void *stream);
+/* dep.build_pit_catalog (:272-509).  carve_bound receives carveID restricted to valid DEM cells (:330);
+ * pairs_out the distinct (pit << 32 | carve) pairs sharing a cell, pair_included the reference's test
+ * "carve's highest cell inside the pit OR lowest cell outside" (:435-439); *npairs is a host pointer.
+ * carveout_id = carveID at the first nodata cell (:335), ignored when carveout != 0. */
+int hc_pit_catalog_dev(hc_ctx *ctx, const float *dem, float nodata, const float *carve, const float *diff_carve,
+                       const float *diff_fill, const int32_t *fillID, const int32_t *carveID,
+                       const int32_t *carvefillID, int64_t n, int32_t npits, int32_t ncarves, int carveout,
+                       int32_t carveout_id, int32_t *carve_bound, float *maxfill, float *volfill, int64_t *nfill,
+                       float *maxcarve, float *volcarve, int64_t *ncarvecells, float *volfb, float *maxfb,
+                       int8_t *complete, uint8_t *pit_out, int64_t *carve_amax, int64_t *carve_amin,
+                       float *carve_min, double *carve_sum, int64_t *carve_n, int64_t *pairs_out, int64_t pair_cap,
+                       uint8_t *pair_included, int64_t *npairs, void *stream);
+/* dep.select_solution (:517-810): decision tree per pit -> 4-digit codes.  wall / sink may be NULL; water
+ * must not be (the reference raises NameError without a water mask, :606-647).  float32_scalars selects
+ * the arithmetic numpy gives the reference's scalar expressions: 1 = float32 (numpy >= 2, weak Python
+ * scalars; what the golden vectors were produced with), 0 = float64 (numpy < 2 value-based promotion). */
+int hc_pit_select_dev(hc_ctx *ctx, const int32_t *fillID, const int32_t *carve_bound, int64_t n, int32_t npits,
+                      int32_t ncarves, const float *maxfill, const float *volfill, const float *maxcarve,
+                      const float *volcarve, const float *volfb, const float *maxfb, const int8_t *complete,
+                      const int64_t *nfill, const int64_t *ncarvecells, const uint8_t *pit_out, const int64_t *pairs,
+                      const uint8_t *pair_included, int64_t npairs, const float *wall, const float *water,
+                      const float *sink, double fill_vol_thresh, double carve_vol_thresh, double max_carve_depth,
+                      double maxcarve_factor, int apply_shallow_fill, int float32_scalars, int32_t *solution,
+                      void *stream);
+/* dep.apply_solution (:1140-1228): scatter fill / carve values by pit solution (later pits win, as in the
+ * reference's loop order) and the int16 solution mask (in/out).  excluded: u8[npits+1] or NULL. */
+int hc_pit_apply_dev(hc_ctx *ctx, const float *dem, const float *fillv, const float *carvev, const int32_t *fillID,
+                     const int32_t *carve_bound, const int32_t *carvefillID, int64_t n, int32_t npits,
+                     int32_t ncarves, const int32_t *solution, const uint8_t *excluded, const uint8_t *pit_out,
+                     const int64_t *ncarvecells, const int64_t *pairs, const uint8_t *pair_included, int64_t npairs,
+                     float *out, int16_t *mask, void *stream);
+/* dep.fill_shallow_pits (:1471-1531): mod (in/out) takes the filled value wherever the cell's label
+ * (0 = background included) has no cell deeper than sfill and no water-mask cell (water may be NULL). */
+int hc_fill_shallow_pits_dev(hc_ctx *ctx, float *mod, float sfill, const int32_t *fillID, const float *diff_fill,
+                             const float *fillv, const float *water, int64_t n, int32_t npits, int64_t *n_shallow,
+                             void *stream);
+
 /* HOST-buffer variants (H2D + kernels + D2H inside the call; synchronous). */
 int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
                  int seed_mode);
