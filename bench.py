@@ -337,6 +337,99 @@ def run_banded(args, world, rank, local, dev):
     return 0
 
 
+def run_c5(args, world, rank, local, dev):
+    """BASELINE.json configs[4]: dem_noise_removal smoothing core (4 DW smoothings 9/7/5/3, slope_D4 + curvature_D2 of
+    the 5x5 result, global sigma, filter selection, final slope; models/dem_noise_removal.py:397-476) on a 20000^2 DEM,
+    all-zero masks (pure bandwidth).  One unit per GPU.  Not the driver's headline metric: an extra measured line."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pydrodem_b200 import _lib, stencils, synth
+    n = 20000 if args.size == 10801 else args.size
+    cells = n * n
+    z = torch.empty((n, n), dtype=torch.float32, device=dev)
+    for r0 in range(0, n, 1024):
+        nr = min(1024, n - r0)
+        z[r0:r0 + nr] = synth.make_dem(n, n, 1005 + rank, row0=r0, nrows=nr, device=dev, quantise=False)
+    z += torch.randn(z.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1005 + rank)) * 1.5
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        out = stencils.smooth_core(z, 30.0, 30.0)
+    barrier()
+    _lib.profile_enable(True, local)
+    launches0 = _lib.launch_count(local)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = stencils.smooth_core(z, 30.0, 30.0)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count(local) - launches0
+    prof = _lib.profile_read(local)
+    _lib.profile_enable(False, local)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * cells * args.steps / (ms_max * 1e-3) / 1e6
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = peaks()
+    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
+    roof = None
+    if dom:
+        name, (cnt, tot, mx) = dom
+        avg_ms = tot / cnt
+        alg = 8 * cells  # one k x k smoothing pass: 4 B in + 4 B out per cell (SURVEY.md 8d)
+        ach = alg / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "pass": "smoothing", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "launches_per_step": cnt / args.steps,
+                "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg,
+                "step_share": tot / args.steps / (ms_max / args.steps)}
+    cpu = None
+    if world == 1 and args.cpu_sample > 0:
+        from scipy.signal import convolve2d
+        s = min(2000, n)
+        crop = np.ascontiguousarray(z[:s, :s].cpu().numpy())
+        t0 = time.perf_counter()
+        for w in (9, 7, 5, 3):
+            k = stencils.build_kernel(stencils.DW_WEIGHTS[w], dtype=np.float32, normalize=True)
+            convolve2d(crop, k, boundary="symm", mode="same")   # the reference's own call (tools/derive.py:94)
+        gy, gx = np.gradient(crop, 30.0, 30.0)
+        dt = time.perf_counter() - t0
+        cpu = {"value": crop.size / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+               "sample": f"{s}x{s} crop: the four scipy.signal.convolve2d(boundary='symm') smoothings + one np.gradient, the "
+                         "library calls tools/derive.py makes (selection / slopes not included: an upper bound on the CPU rate)"}
+    kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t_ / args.steps} for k, (c, t_, m) in
+               sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    line = {"metric": "Mcells/s DEM-NR smoothing core (configs[4])", "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C5: {n}x{n} float32 DEM, DW 9/7/5/3 smoothing + slope_D4 + curvature_D2 + sigma + filter "
+                                   "selection + final slope (CreateDTM.run_tile smoothing core), all-zero masks, one unit per GPU",
+                       "cells_per_gpu": cells, "l2": "1.6 GB rasters exceed the 126 MB L2; no explicit flush",
+                       "algorithmic_bytes_per_cell_fused_pipeline": 12},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": None, "gpu_launches": launches, "clocks": clocks,
+            "hbm_frac_algorithmic_whole_step": 12 * cells / (ms_max / args.steps * 1e-3) / 1e9 / peak, "kernels": kernels}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -348,7 +441,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=5400, help="edge of the crop timed on the CPU (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flats", type=int, default=1)
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "bands", "c3"],
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "bands", "c3", "c5"],
                     help="auto: c2 (one 10801^2 DEM) at N=1, bands (one 10801 x 10801*N DEM, a band per GPU, seam "
                          "exchange over NCCL) at N>1; c3: the 40000^2 DEM row-band-sharded over the N GPUs")
     ap.add_argument("--local-bands", type=int, default=1, help="bands per rank (N=1 with >1 emulates the exchange)")
@@ -379,6 +472,8 @@ def main():
         args.workload = "c2" if world == 1 and args.local_bands == 1 else "bands"
     if args.workload in ("bands", "c3"):
         return run_banded(args, world, rank, local, dev)
+    if args.workload == "c5":
+        return run_c5(args, world, rank, local, dev)
 
     ny = nx = args.size
     cells = ny * nx
