@@ -413,8 +413,11 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
   }
   if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); if (nlist * 4 > T * T) HC_DBG(5, 1); }
   if (!ever) return;
-  // write back and find out which sides of the tile changed on the rim
-  int side = 0;  // bit0 N, bit1 S, bit2 W, bit3 E
+  // write back; a neighbouring tile is re-queued only if one of ITS rim cells (my halo) can actually improve
+  // from a rim cell of mine that changed (distances only ever decrease, so a stale halo value can cause a
+  // spurious visit but never a missed one).  Without this test a tile is revisited every time the front
+  // moves on in any neighbour.
+  int nb9 = 0;  // bit (dy+1)*3 + (dx+1)
   for (int i = tid; i < T * T; i += NTHREADS) {
     int lr = i / T, lc = i - lr * T;
     int r = r0 + lr, c = c0 + lc;
@@ -427,26 +430,35 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
     if (lo != dlo[g] || hi != dhi[g]) {
       dlo[g] = lo;
       dhi[g] = hi;
-      if (lr == 0) side |= 1;
-      if (lr == T - 1 || r == ny - 1) side |= 2;
-      if (lc == 0) side |= 4;
-      if (lc == T - 1 || c == nx - 1) side |= 8;
+      if (lr == 0 || lc == 0 || lr == T - 1 || lc == T - 1) {
+        const float v = sz[ci];
+#pragma unroll
+        for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+          for (int dc = -1; dc <= 1; dc++) {
+            const int hr = lr + 1 + dr, hc = lc + 1 + dc;
+            if (!(hr == 0 || hr == TH - 1 || hc == 0 || hc == TH - 1)) continue;  // not a halo cell
+            const int ni = hr * TP + hc;
+            if (sz[ni] != v) continue;
+            const u32 nw = slo[ni];
+            if (!(nw & R_NF)) continue;
+            const u32 nlo = nw & ~R_NF, nhi = shi[ni];
+            if ((lo && (nlo == 0 || lo + 1 < nlo)) || (hi && (nhi == 0 || hi + 1 < nhi)))
+              nb9 |= 1 << ((hr == 0 ? 0 : (hr == TH - 1 ? 2 : 1)) * 3 + (hc == 0 ? 0 : (hc == TH - 1 ? 2 : 1)));
+          }
+      }
     }
   }
-  if (side) atomicOr(&s_side, side);
+  if (nb9) atomicOr(&s_side, nb9);
   __syncthreads();
-  side = s_side;
-  if (tid < 9 && tid != 4) {
-    int dy = tid / 3 - 1, dx = tid % 3 - 1;
-    bool need = true;
-    if (dy == -1 && !(side & 1)) need = false;
-    if (dy == 1 && !(side & 2)) need = false;
-    if (dx == -1 && !(side & 4)) need = false;
-    if (dx == 1 && !(side & 8)) need = false;
-    int yy = (int)blockIdx.y + dy, xx = (int)blockIdx.x + dx;
-    if (need && yy >= 0 && yy < ty && xx >= 0 && xx < tx && active[yy * tx + xx]) dirty_out[yy * tx + xx] = 1;
+  nb9 = s_side;
+  if (tid < 9 && tid != 4 && (nb9 & (1 << tid))) {
+    int yy = (int)blockIdx.y + tid / 3 - 1, xx = (int)blockIdx.x + tid % 3 - 1;
+    if (yy >= 0 && yy < ty && xx >= 0 && xx < tx && active[yy * tx + xx]) {
+      dirty_out[yy * tx + xx] = 1;
+      *changed_flag = 1u;
+    }
   }
-  if (tid == 0 && side) *changed_flag = 1u;
 }
 
 // masked D8 for the pending cells
