@@ -28,9 +28,12 @@
 //
 // Only float comparisons/min/max touch elevations, so the result is bit-identical to the serial
 // priority-flood (the eps=0 surface is unique).
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 #define T HC_TILE
 #define TH (T + 2)
@@ -425,33 +428,6 @@ int ext_nodata_mask(hc_ctx *ctx, const float *z, uint8_t *ext, int64_t ny, int64
 // stays a root (minimum spanning FOREST); msf = 0: it is attached to node 0 unraised.
 // mark (optional) receives 1 for every entry picked: the MST/MSF edges.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_pick_both(const u32 *__restrict__ eA, const u32 *__restrict__ eB, const float *__restrict__ eW, u32 ne,
-            const u32 *__restrict__ rep, u64 *__restrict__ best, u32 nopen) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ne) return;
-  u32 a = __ldg(&rep[eA[i]]), b = __ldg(&rep[eB[i]]);
-  if (a == b) return;
-  u64 key = ((u64)d_ford(eW[i]) << 32) | (u64)i;
-  if (a >= nopen && key < __ldcg(&best[a])) atomicMin(&best[a], key);
-  if (b >= nopen && key < __ldcg(&best[b])) atomicMin(&best[b], key);
-}
-
-__global__ void k_hook_idx(const u32 *rep, const u64 *best, u32 *ptr, float *lvl, u32 K1, u32 nopen,
-                           const u32 *__restrict__ eA, const u32 *__restrict__ eB, const float *__restrict__ eW,
-                           uint8_t *mark, int msf) {
-  u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= K1) return;
-  if (b < nopen || rep[b] != b) { ptr[b] = b < nopen ? b : rep[b]; return; }
-  u64 k = best[b];
-  if (k == ~0ull) { ptr[b] = msf ? b : 0u; return; }
-  u32 idx = (u32)(k & 0xFFFFFFFFu);
-  u32 ra = rep[eA[idx]], rb = rep[eB[idx]];
-  ptr[b] = ra == b ? rb : ra;
-  lvl[b] = fmaxf(lvl[b], eW[idx]);
-  if (mark) mark[idx] = 1;
-}
-
 struct bor_tabs { u64 *best; u32 *rep, *hp, *ptr, *ptr2; float *lvl; };
 
 static int bor_tabs_alloc(hc_ctx *ctx, bor_tabs *t, u32 K1) {
@@ -502,32 +478,144 @@ static int bor_contract(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, u32 *
   return HC_OK;
 }
 
+// The remaining Boruvka rounds in ONE cooperative launch: every phase is a grid-stride loop, phases are
+// separated by grid.sync(), loop decisions are read from counters every block sees after a sync.  Replaces
+// ~10 tiny launches and 2-3 host read-backs per round (the rounds are latency, not throughput: the tables
+// have 1e4..1e6 entries).  idx_keys = 1: undirected list, key (weight, entry index), both ends pick, picked
+// entries are marked (MSF / seam graph); idx_keys = 0: the fill's directed list, key (weight, neighbour).
+// ctl: [0..2] jump-changed flags (rotating: a flag is cleared two syncs after its last reader),
+//      [3..6] active/merged counters (parity), [7] rounds done
+struct bor_pargs {
+  u64 *best; u32 *rep, *hp, *ptr, *ptr2; float *lvl;
+  const u32 *eA, *eB; const float *eW; uint8_t *mark; u32 *ctl;
+  u32 K1, nopen, ne; int msf, idx_keys, do_init, max_rounds;
+};
+__global__ void __launch_bounds__(512)
+k_bor_persistent(bor_pargs a) {
+  cg::grid_group grid = cg::this_grid();
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (a.do_init) {
+    for (u32 b = tid; b < a.K1; b += nth) { a.rep[b] = b; a.lvl[b] = -INFINITY; a.hp[b] = 0; }
+    if (a.mark) for (u32 i = tid; i < a.ne; i += nth) a.mark[i] = 0;
+  }
+  if (tid < 8) a.ctl[tid] = 0;
+  grid.sync();
+  int round = 0;
+  for (; round < a.max_rounds; round++) {
+    for (u32 b = tid; b < a.K1; b += nth) a.best[b] = ~0ull;
+    grid.sync();
+    // pick
+    for (u32 i = tid; i < a.ne; i += nth) {
+      u32 ra = __ldcg(&a.rep[a.eA[i]]);
+      u32 rb = __ldcg(&a.rep[a.eB[i]]);
+      if (ra == rb) continue;
+      if (a.idx_keys) {
+        u64 key = ((u64)d_ford(a.eW[i]) << 32) | (u64)i;
+        if (ra >= a.nopen && key < __ldcg(&a.best[ra])) atomicMin(&a.best[ra], key);
+        if (rb >= a.nopen && key < __ldcg(&a.best[rb])) atomicMin(&a.best[rb], key);
+      } else if (ra >= a.nopen) {
+        u64 key = ((u64)d_ford(a.eW[i]) << 32) | (u64)rb;
+        if (key < __ldcg(&a.best[ra])) atomicMin(&a.best[ra], key);
+      }
+    }
+    grid.sync();
+    // hook -> ptr2
+    for (u32 b = tid; b < a.K1; b += nth) {
+      u32 r = __ldcg(&a.rep[b]);
+      if (b < a.nopen || r != b) { a.ptr2[b] = b < a.nopen ? b : r; continue; }
+      u64 k = __ldcg(&a.best[b]);
+      if (k == ~0ull) { a.ptr2[b] = a.msf ? b : 0u; continue; }
+      if (a.idx_keys) {
+        u32 idx = (u32)(k & 0xFFFFFFFFu);
+        u32 ra = __ldcg(&a.rep[a.eA[idx]]), rb = __ldcg(&a.rep[a.eB[idx]]);
+        a.ptr2[b] = ra == b ? rb : ra;
+        a.lvl[b] = fmaxf(a.lvl[b], a.eW[idx]);
+        if (a.mark) a.mark[idx] = 1;
+      } else {
+        a.ptr2[b] = (u32)(k & 0xFFFFFFFFu);
+        a.lvl[b] = fmaxf(a.lvl[b], d_funord((u32)(k >> 32)));
+      }
+    }
+    grid.sync();
+    // break mutual pairs -> ptr
+    for (u32 b = tid; b < a.K1; b += nth) {
+      u32 p = __ldcg(&a.ptr2[b]);
+      if (b >= a.nopen && __ldcg(&a.rep[b]) == b && p >= a.nopen && __ldcg(&a.ptr2[p]) == b && b < p) p = b;
+      a.ptr[b] = p;
+    }
+    grid.sync();
+    // pointer doubling to the roots
+    for (int it = 0;; it++) {
+      u32 *flag = &a.ctl[it % 3];
+      if (tid == 0) a.ctl[(it + 1) % 3] = 0;   // last read in iteration it-2: every thread has passed a sync since
+      int ch = 0;
+      for (u32 b = tid; b < a.K1; b += nth) {
+        u32 p = __ldcg(&a.ptr[b]);
+        u32 pp = __ldcg(&a.ptr[p]);
+        if (pp != p) { a.ptr[b] = pp; ch = 1; }
+      }
+      if (ch) *flag = 1u;
+      grid.sync();
+      if (!__ldcg(flag)) break;
+    }
+    // merge trees into their roots
+    u32 *ctr = &a.ctl[3 + 2 * (round & 1)];
+    if (tid == 0) { a.ctl[3 + 2 * ((round + 1) & 1)] = 0; a.ctl[4 + 2 * ((round + 1) & 1)] = 0; }
+    u32 nact = 0, nmer = 0;
+    for (u32 b = tid; b < a.K1; b += nth) {
+      if (b < a.nopen || __ldcg(&a.rep[b]) != b) continue;
+      u32 r = __ldcg(&a.ptr[b]);
+      if (r != b) { a.hp[b] = r; a.rep[b] = r; nmer++; }
+      else nact++;
+    }
+    if (nact) atomicAdd(ctr, nact);
+    if (nmer) atomicAdd(ctr + 1, nmer);
+    grid.sync();
+    for (u32 b = tid; b < a.K1; b += nth) {
+      u32 s0 = __ldcg(&a.rep[b]);
+      u32 r = __ldcg(&a.rep[s0]);
+      if (r != s0) a.rep[b] = r;
+    }
+    grid.sync();
+    const u32 active = __ldcg(ctr), merged = __ldcg(ctr + 1);
+    if (active == 0 || merged == 0) { round++; break; }
+  }
+  if (tid == 0) a.ctl[7] = (u32)round;
+}
+
+// launch helper: as many co-resident 512-thread blocks as the work needs (at most the device holds)
+static int bor_persistent_launch(hc_ctx *ctx, bor_pargs &a, int *rounds, cudaStream_t st) {
+  static int max_blocks = 0;
+  if (!max_blocks) {
+    int per_sm = 0;
+    HC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bor_persistent, 512, 0));
+    max_blocks = per_sm * ctx->sm_count;
+    if (max_blocks < 1) { hc_set_error("cooperative launch: no resident block"); return HC_ERR_CUDA; }
+  }
+  size_t work = a.ne > a.K1 ? a.ne : a.K1;
+  int blocks = (int)((work + 2047) / 2048);
+  if (blocks < 1) blocks = 1;
+  if (blocks > max_blocks) blocks = max_blocks;
+  void *args[] = {&a};
+  HC_PROF(ctx, st, "k_bor_persistent");
+  HC_CUDA(cudaLaunchCooperativeKernel((void *)k_bor_persistent, dim3(blocks), dim3(512), args, 0, st));
+  HC_LAUNCH_CHECK(ctx);
+  if (rounds) {
+    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, a.ctl + 7, 4, cudaMemcpyDeviceToHost, st));
+    HC_CUDA(cudaStreamSynchronize(st));
+    *rounds = (int)ctx->h_mail[0];
+  }
+  return HC_OK;
+}
+
 static int bor_list_solve(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, const u32 *eA, const u32 *eB,
                           const float *eW, u32 ne, int msf, uint8_t *mark, u32 *cnt, int *rounds, cudaStream_t st) {
-  const int tb = 256;
-  const int tgK = (int)((K1 + tb - 1) / tb);
-  HC_PROF(ctx, st, "k_tab_init");
-  k_tab_init<<<tgK, tb, 0, st>>>(t.rep, t.lvl, t.hp, K1);
-  HC_LAUNCH_CHECK(ctx);
-  if (mark && ne) HC_CUDA(cudaMemsetAsync(mark, 0, ne, st));
-  u32 active = K1 > nopen ? K1 - nopen : 0, merged = 1;
-  int round = 0;
-  while (active > 0 && merged > 0) {
-    if (round > 64) { hc_set_error("fill: list Boruvka did not converge"); return HC_ERR_INTERNAL; }
-    HC_CUDA(cudaMemsetAsync(t.best, 0xFF, (size_t)K1 * 8, st));
-    if (ne) {
-      HC_PROF(ctx, st, "k_pick_both");
-      k_pick_both<<<(ne + 255) / 256, 256, 0, st>>>(eA, eB, eW, ne, t.rep, t.best, nopen);
-      HC_LAUNCH_CHECK(ctx);
-    }
-    HC_PROF(ctx, st, "k_hook_idx");
-    k_hook_idx<<<tgK, tb, 0, st>>>(t.rep, t.best, t.ptr2, t.lvl, K1, nopen, eA, eB, eW, mark, msf);
-    HC_LAUNCH_CHECK(ctx);
-    HC_TRY(bor_contract(ctx, t, K1, nopen, cnt, &active, &merged, st));
-    round++;
-  }
-  if (rounds) *rounds = round;
-  return HC_OK;
+  bor_pargs a;
+  a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
+  a.eA = eA; a.eB = eB; a.eW = eW; a.mark = mark; a.ctl = cnt + 16;
+  a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = msf; a.idx_keys = 1; a.do_init = 1; a.max_rounds = 64;
+  if (getenv("HC_BOR_NO_ROUNDS")) rounds = nullptr;   // (diagnostic read-back costs a host sync)
+  return bor_persistent_launch(ctx, a, rounds, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -640,6 +728,18 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
     }
     if (getenv("HC_TRACE")) fprintf(stderr, "[fill] round %d: %u closed supernodes left of %u basins (edge list %u%s)\n", round, active, K, ne, have_list ? "" : " unused");
     round++;
+    if (have_list && active > 0 && (size_t)K1 + ne < (size_t)(2u << 20)) {
+      // small tables are latency bound: all remaining rounds in one cooperative launch (big ones keep the
+      // per-round launches, whose kernels fill the machine)
+      bor_pargs a;
+      a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
+      a.eA = eA; a.eB = eB; a.eW = eW; a.mark = nullptr; a.ctl = cnt + 16;
+      a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = 0; a.idx_keys = 0; a.do_init = 0; a.max_rounds = 64;
+      int more = 0;
+      HC_TRY(bor_persistent_launch(ctx, a, &more, st));
+      round += more;
+      active = 0;
+    }
   }
   ctx->fill_rounds = round;
 
