@@ -230,6 +230,12 @@ def run_banded(args, world, rank, local, dev):
             a = prof.get(k, (0, 0.0, 0.0))
             prof[k] = (a[0] + cnt, a[1] + tot, max(a[2], mx))
         _lib.profile_enable(False, ctx=c)
+    # per-phase device time (includes the host read-backs each phase waits on), 2 extra untimed steps
+    chain.timing = True
+    for _ in range(2):
+        chain.run()
+    chain.timing = False
+    phases = {k: v / 2 for k, v in chain.phase_ms.items()}
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -325,7 +331,7 @@ def run_banded(args, world, rank, local, dev):
                                     "all_gather over NCCL",
                    "cells_total": cells_total, "cells_per_gpu": cells_local, "bands": nbands,
                    "l2": "every band's rasters exceed the 126 MB L2; no explicit flush", "flats": bool(args.flats),
-                   "flat_exchange_rounds": flat_rounds, "band_stats_rank0": stats,
+                   "flat_exchange_rounds": flat_rounds, "band_stats_rank0": stats, "phase_ms_rank0": phases,
                    "algorithmic_bytes_per_cell": 18, "checks": chk},
         "roofline": roof, "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "hbm_frac_algorithmic_whole_step": 18 * cells_local / (ms_max / args.steps * 1e-3) / 1e9 / peak,

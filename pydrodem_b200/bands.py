@@ -109,6 +109,23 @@ class BandedChain:
         self.fseam = torch.zeros((nl, 2, 3, self.nx), dtype=i32, device=self.device)
         self.aseam = torch.zeros((nl, 2, 2, self.nx), dtype=i32, device=self.device)
         self.flat_rounds = 0
+        self.timing = False      # set True to collect per-phase device times of run() in self.phase_ms
+        self.phase_ms = {}
+        self._ev = []
+
+    def _mark(self, name):
+        if self.timing:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record(self.torch.cuda.current_stream(self.device))
+            self._ev.append((name, e))
+
+    def _collect(self):
+        if not self.timing or len(self._ev) < 2:
+            return
+        self.torch.cuda.synchronize(self.device)
+        for (n0, e0), (n1, e1) in zip(self._ev[:-1], self._ev[1:]):
+            self.phase_ms[n1] = self.phase_ms.get(n1, 0.0) + e0.elapsed_time(e1)
+        self._ev = []
 
     def close(self):
         for c in self.ctx:
@@ -147,29 +164,38 @@ class BandedChain:
             if z_list is not None:
                 for i, z in enumerate(z_list):
                     self.z_view(i).copy_(z)
+            self._mark("start")
             self._halo_exchange(self.zh)
+            self._mark("halo_z")
             # fill
             for i, nb in enumerate(self.rows):
                 self._chk(lib.hc_band_fill_local_dev(self.ctx[i], self._p(self.zh[i]), nb, nx, self.nodata, self.seed_mode,
                                                      self.flags(i), self.first + i, ctypes.c_void_p(self.edges[i].data_ptr()),
                                                      st), "hc_band_fill_local_dev")
+            self._mark("fill_local")
             all_edges = self.comm.gather(self.edges)
+            self._mark("gather_edges")
             for i, nb in enumerate(self.rows):
                 self._chk(lib.hc_band_fill_finish_dev(self.ctx[i], ctypes.c_void_p(all_edges.data_ptr()), self.nbands,
                                                       self._p(self.fh[i]), st), "hc_band_fill_finish_dev")
+            self._mark("fill_finish")
             self._halo_exchange(self.fh)
+            self._mark("halo_filled")
             # D8 (+ slope)
             for i, nb in enumerate(self.rows):
                 sp = ctypes.c_void_p(self.slope[i].data_ptr()) if self.want_slope else None
                 self._chk(lib.hc_band_d8_dev(self.ctx[i], self._p(self.fh[i]), self._p(self.da[i]), sp, nb, nx, self.nodata,
                                              self.dx, self.dy, self.table, self.flags(i), st), "hc_band_d8_dev")
+            self._mark("d8")
             self._halo_exchange(self.da)
+            self._mark("halo_dir")
             # flats
             if self.flats:
                 for i, nb in enumerate(self.rows):
                     self._chk(lib.hc_band_flats_begin_dev(self.ctx[i], self._p(self.fh[i]), self._p(self.da[i]),
                                                           self._p(self.db[i]), nb, nx, self.nodata, self.table,
                                                           self.flags(i), st), "hc_band_flats_begin_dev")
+                self._mark("flats_begin")
                 self.flat_rounds = 0
                 first = True
                 while True:
@@ -196,20 +222,26 @@ class BandedChain:
                     first = False
                     if self.flat_rounds > 100000:
                         raise _lib.HydrocoreError("banded flats did not converge")
+                self._mark("flats_relax_exchange")
                 for i in range(nl):
                     self._chk(lib.hc_band_flats_finish_dev(self.ctx[i], st), "hc_band_flats_finish_dev")
                 self._halo_exchange(self.db)
+                self._mark("flats_finish_halo")
             # accumulation
             for i, nb in enumerate(self.rows):
                 self._chk(lib.hc_band_accum_local_dev(self.ctx[i], self._p(self.db[i]), ctypes.c_void_p(self.acc[i].data_ptr()), nb, nx,
                                                       self.table, self.flags(i),
                                                       ctypes.c_void_p(self.aseam[i].data_ptr()), st),
                           "hc_band_accum_local_dev")
+            self._mark("accum_local")
             alls = self.comm.gather(self.aseam)
+            self._mark("gather_seams")
             for i, nb in enumerate(self.rows):
                 self._chk(lib.hc_band_accum_finish_dev(self.ctx[i], ctypes.c_void_p(alls.data_ptr()), self.nbands,
                                                        self.first + i, ctypes.c_void_p(self.acc[i].data_ptr()), st),
                           "hc_band_accum_finish_dev")
+            self._mark("accum_finish")
+            self._collect()
         return [(self.fh[i][1:-1], self.db[i][1:-1], self.slope[i], self.acc[i]) for i in range(nl)]
 
     def launches(self):

@@ -320,28 +320,26 @@ __device__ __forceinline__ int slow_relax(const float *sz, u32 *slo, u32 *shi, i
   return changed;
 }
 
-__global__ void __launch_bounds__(NTHREADS)
-k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
-             const uint8_t *__restrict__ active, const uint8_t *__restrict__ dirty_in,
-             uint8_t *__restrict__ dirty_out, u32 *__restrict__ changed_flag, int ny, int nx, float nodata,
-             unsigned long long *dbg, hc_rows rw) {
-  extern __shared__ __align__(16) unsigned char smem[];
+// one visit of tile (by, bx): load, relax to the local fixed point, write back, queue the neighbours that can improve
+__device__ __forceinline__ void relax_tile(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
+                                           const uint8_t *__restrict__ active, u32 *__restrict__ list_out,
+                                           u32 *__restrict__ n_out, u32 *__restrict__ queued, int ny, int nx,
+                                           float nodata, unsigned long long *dbg, hc_rows rw, int by, int bx, int tx, int ty,
+                                           unsigned char *smem) {
   float *sz = (float *)smem;
   u32 *slo = (u32 *)(smem + TH * TP * 4);
   u32 *shi = (u32 *)(smem + TH * TP * 8);
   unsigned short *list = (unsigned short *)(smem + TH * TP * 12);
   __shared__ int s_side;
   __shared__ u32 s_n;
-  const int tx = gridDim.x, ty = gridDim.y;
-  const int tile = blockIdx.y * tx + blockIdx.x;
-  if (!active[tile] || !dirty_in[tile]) return;
-  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  const int r0 = by * T, c0 = bx * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
   __shared__ uint8_t s_act[9];
+  __syncthreads();  // the previous tile of this CTA is completely done with the shared arrays
   if (tid == 0) { s_side = 0; s_n = 0; }
   if (tid < 9) {
-    int yy = (int)blockIdx.y + tid / 3 - 1, xx = (int)blockIdx.x + tid % 3 - 1;
+    int yy = by + tid / 3 - 1, xx = bx + tid % 3 - 1;
     s_act[tid] = (yy >= 0 && yy < ty && xx >= 0 && xx < tx) ? active[yy * tx + xx] : 0;
   }
   __syncthreads();
@@ -453,12 +451,43 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
   __syncthreads();
   nb9 = s_side;
   if (tid < 9 && tid != 4 && (nb9 & (1 << tid))) {
-    int yy = (int)blockIdx.y + tid / 3 - 1, xx = (int)blockIdx.x + tid % 3 - 1;
+    int yy = by + tid / 3 - 1, xx = bx + tid % 3 - 1;
     if (yy >= 0 && yy < ty && xx >= 0 && xx < tx && active[yy * tx + xx]) {
-      dirty_out[yy * tx + xx] = 1;
-      *changed_flag = 1u;
+      // the first one to flag a tile appends it to the next round's queue
+      const u32 t = (u32)(yy * tx + xx);
+      if (atomicExch(&queued[t], 1u) == 0u) list_out[atomicAdd(n_out, 1u)] = t;
     }
   }
+}
+
+// persistent form: the CTAs walk the queue of dirty tiles (a full-grid launch spends most of its time on
+// CTAs that find their tile clean)
+__global__ void __launch_bounds__(NTHREADS)
+k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
+             const uint8_t *__restrict__ active, const u32 *__restrict__ list_in, const u32 *__restrict__ n_in,
+             u32 *__restrict__ list_out, u32 *__restrict__ n_out, u32 *__restrict__ queued, u32 *__restrict__ next,
+             int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw, int tx, int ty) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ u32 s_q;
+  const u32 n = *n_in;
+  for (;;) {
+    // dynamic fetch: tile costs differ by orders of magnitude (a lake tile vs one with a few pits)
+    __syncthreads();
+    if (threadIdx.x == 0) s_q = atomicAdd(next, 1u);
+    __syncthreads();
+    const u32 q = s_q;
+    if (q >= n) break;
+    const u32 t = list_in[q];
+    relax_tile(z, nf, dlo, dhi, active, list_out, n_out, queued, ny, nx, nodata, dbg, rw, (int)(t / tx), (int)(t % tx), tx, ty, smem);
+  }
+}
+
+// queue builders: every active tile (first round) / the active tiles of one tile row (after a halo row changed)
+__global__ void k_flat_queue_tiles(const uint8_t *__restrict__ active, u32 first, u32 count, u32 *queued, u32 *list, u32 *n) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u32 t = first + i;
+  if (active[t] && atomicExch(&queued[t], 1u) == 0u) list[atomicAdd(n, 1u)] = t;
 }
 
 // masked D8 for the pending cells
@@ -523,10 +552,11 @@ static int flats_fast_tier(hc_ctx *ctx, const float *z, const uint8_t *dirA, uin
   const size_t tiles = (size_t)tx * ty;
   bs->pending = (uint8_t *)arena_take(ctx, tiles);
   bs->active = (uint8_t *)arena_take(ctx, tiles);
-  bs->dA = (uint8_t *)arena_take(ctx, tiles);
-  bs->dB = (uint8_t *)arena_take(ctx, tiles);
-  bs->flag = (u32 *)arena_take(ctx, 256);
-  if (!bs->pending || !bs->active || !bs->dA || !bs->dB || !bs->flag) return HC_ERR_NOMEM;
+  bs->qA = (u32 *)arena_take(ctx, tiles * 4);
+  bs->qB = (u32 *)arena_take(ctx, tiles * 4);
+  bs->queued = (u32 *)arena_take(ctx, tiles * 4);
+  bs->flag = (u32 *)arena_take(ctx, 256);   // [1] pending tiles, [2..3] halo changed, [8] n(qA), [9] n(qB)
+  if (!bs->pending || !bs->active || !bs->qA || !bs->qB || !bs->queued || !bs->flag) return HC_ERR_NOMEM;
   bs->fz = z; bs->dirA = dirA; bs->dirB = dirB; bs->nb = ny; bs->nx = nx; bs->nodata = nodata; bs->table = table;
   bs->nf = nullptr;
 
@@ -544,7 +574,7 @@ static int flats_fast_tier(hc_ctx *ctx, const float *z, const uint8_t *dirA, uin
   else
     k_flat_fast<HC_TABLE_TAUDEM><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
   HC_LAUNCH_CHECK(ctx);
-  HC_CUDA(cudaMemsetAsync(bs->flag, 0, 16, st));
+  HC_CUDA(cudaMemsetAsync(bs->flag, 0, 64, st));
   HC_PROF(ctx, st, "k_flat_dilate");
   k_flat_dilate<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(bs->pending, bs->active, tx, ty, bs->flag + 1, rw);
   HC_LAUNCH_CHECK(ctx);
@@ -576,31 +606,39 @@ static int flats_slow_init(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   HC_PROF(ctx, st, "k_flat_init");
   k_flat_init<<<tg, NTHREADS, 0, st>>>(bs->fz, bs->dirA, bs->dirB, bs->nf, bs->dlo, bs->dhi, bs->active, (int)ny, (int)nx, bs->nodata, rw);
   HC_LAUNCH_CHECK(ctx);
-  HC_CUDA(cudaMemsetAsync(bs->dA, 1, tiles, st));  // first relaxation visits every active tile
+  // first relaxation visits every active tile: queue A
+  HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
+  HC_PROF(ctx, st, "k_flat_queue_tiles");
+  k_flat_queue_tiles<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(bs->active, 0u, (u32)tiles, bs->queued, bs->qA, bs->flag + 8);
+  HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
 
-// relax until no tile changes; on return bs->dA is all zero (the dirty map of the next call)
+// relax until the queue runs dry; on return queue A (the next call's input) is empty and clean
 static int flats_relax_loop(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   hc_band_state *bs = &ctx->band;
   const int64_t ny = bs->nb, nx = bs->nx;
   const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t tiles = (size_t)tx * ty;
-  dim3 tg(tx, ty);
-  uint8_t *din = bs->dA, *dout = bs->dB;
+  const unsigned grid = (unsigned)(tiles < (size_t)ctx->sm_count * 3 ? tiles : (size_t)ctx->sm_count * 3);
   for (int it = 0;; it++) {
     if (it > 1000000) { hc_set_error("flats: relaxation did not converge"); return HC_ERR_INTERNAL; }
-    HC_CUDA(cudaMemsetAsync(dout, 0, tiles, st));
-    HC_CUDA(cudaMemsetAsync(bs->flag, 0, 4, st));
+    // queue A holds this round's tiles, queue B collects the next round's
+    HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
+    HC_CUDA(cudaMemsetAsync(bs->flag + 9, 0, 8, st));   // n(qB) and the fetch counter [10]
     HC_PROF(ctx, st, "k_flat_relax");
-    k_flat_relax<<<tg, NTHREADS, FLAT_SMEM, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->active, din, dout, bs->flag, (int)ny, (int)nx, bs->nodata, ctx->d_dbg, rw);
+    k_flat_relax<<<grid, NTHREADS, FLAT_SMEM, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->active, bs->qA, bs->flag + 8, bs->qB,
+                                                    bs->flag + 9, bs->queued, bs->flag + 10, (int)ny, (int)nx, bs->nodata,
+                                                    ctx->d_dbg, rw, tx, ty);
     HC_LAUNCH_CHECK(ctx);
-    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag, 4, cudaMemcpyDeviceToHost, st));
+    // next round: B becomes A
+    HC_CUDA(cudaMemcpyAsync(bs->flag + 8, bs->flag + 9, 4, cudaMemcpyDeviceToDevice, st));
+    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag + 9, 4, cudaMemcpyDeviceToHost, st));
+    u32 *t = bs->qA; bs->qA = bs->qB; bs->qB = t;
     HC_CUDA(cudaStreamSynchronize(st));
-    uint8_t *t = din; din = dout; dout = t;
     if (!ctx->h_mail[0]) break;
   }
-  bs->dA = din; bs->dB = dout;  // din = the last (all-zero) dirty_out
+  HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));  // put_halos may queue seam tiles for the next call
   return HC_OK;
 }
 
@@ -725,9 +763,15 @@ int band_flats_put_halos(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, 
   }
   HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag + 2, 8, cudaMemcpyDeviceToHost, st));
   HC_CUDA(cudaStreamSynchronize(st));
-  // tiles next to a halo row that changed are relaxed again (bs->dA is the next dirty map)
-  if (ctx->h_mail[0]) HC_CUDA(cudaMemsetAsync(bs->dA, 1, (size_t)tx, st));
-  if (ctx->h_mail[1]) HC_CUDA(cudaMemsetAsync(bs->dA + (size_t)(ty - 1) * tx, 1, (size_t)tx, st));
+  // tiles next to a halo row that changed are relaxed again: into queue A (the next relax call's input)
+  if (ctx->h_mail[0]) {
+    k_flat_queue_tiles<<<(unsigned)((tx + 255) / 256), 256, 0, st>>>(bs->active, 0u, (u32)tx, bs->queued, bs->qA, bs->flag + 8);
+    HC_LAUNCH_CHECK(ctx);
+  }
+  if (ctx->h_mail[1]) {
+    k_flat_queue_tiles<<<(unsigned)((tx + 255) / 256), 256, 0, st>>>(bs->active, (u32)((ty - 1) * tx), (u32)tx, bs->queued, bs->qA, bs->flag + 8);
+    HC_LAUNCH_CHECK(ctx);
+  }
   if (changed) *changed = (ctx->h_mail[0] || ctx->h_mail[1]) ? 1 : 0;
   return HC_OK;
 }
