@@ -46,6 +46,17 @@ KERNEL_PASS = {
 }
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/ncu_traffic.json),
+    or None.  Only meaningful for the C2 single-GPU workload the capture was taken on."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["kernels"][kernel]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -583,9 +594,10 @@ def main():
             alg_bytes = BYTES_PER_CELL["d8"] * cells  # flat resolution is part of producing the D8 raster
         ach = alg_bytes / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": name, "pass": pname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "launches_per_step": cnt / args.steps,
-                "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "step_share": tot / args.steps / (ms_max / args.steps)}
+                "frac": ach / peak, "traffic": ncu_traffic(name) if ny == 10801 else None, "peak_source": peak_src,
+                "launches_per_step": cnt / args.steps, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "step_share": tot / args.steps / (ms_max / args.steps),
+                "traffic_source": "profiles/ncu_traffic.json (ncu dram__bytes_read+write per launch)"}
     kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t_ / args.steps} for k, (c, t_, m) in
                sorted(prof.items(), key=lambda kv: -kv[1][1])}
     passes = {p: {"ms_per_step": v,
