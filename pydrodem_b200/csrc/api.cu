@@ -153,6 +153,10 @@ extern "C" int hc_create(hc_ctx **out, int device) {
   HC_CUDA(cudaMallocHost(&ctx->h_mail, 256));
   HC_CUDA(cudaMalloc(&ctx->d_dbg, 16 * sizeof(unsigned long long)));
   HC_CUDA(cudaMemset(ctx->d_dbg, 0, 16 * sizeof(unsigned long long)));
+  HC_CUDA(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+  HC_CUDA(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+  HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fill, cudaEventDisableTiming));
+  HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_dir, cudaEventDisableTiming));
   *out = ctx;
   return HC_OK;
 }
@@ -164,6 +168,10 @@ extern "C" int hc_destroy(hc_ctx *ctx) {
   for (int i = 0; i < ctx->n_blocks; i++) cudaFree(ctx->blocks[i].p);
   for (int i = 0; i < 5; i++) if (ctx->io[i]) cudaFree(ctx->io[i]);
   if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+  if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+  if (ctx->ev_fill) cudaEventDestroy(ctx->ev_fill);
+  if (ctx->ev_dir) cudaEventDestroy(ctx->ev_dir);
   free(ctx);
   return HC_OK;
 }
@@ -295,20 +303,32 @@ extern "C" int hc_fill_d8_accum_host(hc_ctx *ctx, const float *z, float *filled,
   size_t n = (size_t)ny * nx;
   if (!n) return HC_OK;
   if (!z || !filled || !dir || !acc) { hc_set_error("hc_fill_d8_accum_host: null pointer"); return HC_ERR_ARG; }
+  if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("bad seed_mode"); return HC_ERR_ARG; }
+  if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("bad table"); return HC_ERR_ARG; }
   dev_buf dz(ctx, 0), df(ctx, 1), dd(ctx, 2), ds(ctx, 3), da(ctx, 4);
   HC_TRY(dz.alloc(n * 4));
   HC_TRY(df.alloc(n * 4));
   HC_TRY(dd.alloc(n));
   if (slope) HC_TRY(ds.alloc(n * 4));
   HC_TRY(da.alloc(n * 4));
-  HC_CUDA(cudaMemcpyAsync(dz.p, z, n * 4, cudaMemcpyHostToDevice, 0));
-  HC_TRY(hc_fill_d8_accum_dev(ctx, (const float *)dz.p, (float *)df.p, (uint8_t *)dd.p, (float *)ds.p,
-                              (uint32_t *)da.p, ny, nx, nodata, dx, dy, seed_mode, table, resolve_flats, nullptr));
-  HC_CUDA(cudaMemcpyAsync(filled, df.p, n * 4, cudaMemcpyDeviceToHost, 0));
-  HC_CUDA(cudaMemcpyAsync(dir, dd.p, n, cudaMemcpyDeviceToHost, 0));
-  if (slope) HC_CUDA(cudaMemcpyAsync(slope, ds.p, n * 4, cudaMemcpyDeviceToHost, 0));
-  HC_CUDA(cudaMemcpyAsync(acc, da.p, n * 4, cudaMemcpyDeviceToHost, 0));
-  HC_CUDA(cudaStreamSynchronize(0));
+  // compute on one stream, device->host copies on another: the filled raster travels while D8 / flats run,
+  // the direction raster while the accumulation runs (the PCIe link, not the kernels, bounds this entry point)
+  cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
+  HC_CUDA(cudaMemcpyAsync(dz.p, z, n * 4, cudaMemcpyHostToDevice, sc));
+  HC_TRY(fill_run(ctx, (const float *)dz.p, (float *)df.p, ny, nx, nodata, seed_mode, sc));
+  HC_CUDA(cudaEventRecord(ctx->ev_fill, sc));
+  HC_CUDA(cudaStreamWaitEvent(sx, ctx->ev_fill, 0));
+  HC_CUDA(cudaMemcpyAsync(filled, df.p, n * 4, cudaMemcpyDeviceToHost, sx));
+  if (resolve_flats) HC_TRY(d8_flats_run(ctx, (const float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, nx, nodata, dx, dy, table, sc));
+  else HC_TRY(d8_run(ctx, (const float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, nx, nodata, dx, dy, table, sc));
+  HC_CUDA(cudaEventRecord(ctx->ev_dir, sc));
+  HC_CUDA(cudaStreamWaitEvent(sx, ctx->ev_dir, 0));
+  HC_CUDA(cudaMemcpyAsync(dir, dd.p, n, cudaMemcpyDeviceToHost, sx));
+  if (slope) HC_CUDA(cudaMemcpyAsync(slope, ds.p, n * 4, cudaMemcpyDeviceToHost, sx));
+  HC_TRY(accum_run(ctx, (const uint8_t *)dd.p, (uint32_t *)da.p, ny, nx, table, sc));
+  HC_CUDA(cudaMemcpyAsync(acc, da.p, n * 4, cudaMemcpyDeviceToHost, sc));
+  HC_CUDA(cudaStreamSynchronize(sx));
+  HC_CUDA(cudaStreamSynchronize(sc));
   return HC_OK;
 }
 

@@ -96,6 +96,9 @@ struct hc_ctx {
   // grow-only device staging buffers of the *_host entry points (z, filled, dir, slope, acc)
   void *io[5];
   size_t io_cap[5];
+  // streams / events of the *_host chain: compute and device->host copies overlap
+  cudaStream_t s_compute, s_copy;
+  cudaEvent_t ev_fill, ev_dir;
   unsigned long long *d_dbg;  // 16 device work counters
   // per-kernel event timing (off by default)
   int prof_on, prof_open;
