@@ -682,8 +682,10 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
   float *level0 = (float *)t.ptr2;  // reused after the rounds
   u32 *troot = t.ptr;
   // compact edge list for the rounds after the second grid pass
-  size_t ecap_sz = n / 4 > (size_t)(1u << 20) ? n / 4 : (size_t)(1u << 20);
-  if (ecap_sz > (size_t)(1u << 28)) ecap_sz = (size_t)(1u << 28);
+  // (the emit round lists ~0.2 entries per cell on the C2 recipe; if it overflows, the rounds fall back to grid
+  // passes, which is correct but costs a full sweep per round: 6 B/cell of headroom is cheap on a 180 GB part)
+  size_t ecap_sz = n / 2 > (size_t)(1u << 20) ? n / 2 : (size_t)(1u << 20);
+  if (ecap_sz > (size_t)(1u << 30)) ecap_sz = (size_t)(1u << 30);
   const u32 ecap = (u32)ecap_sz;
   u32 *eA = (u32 *)arena_take(ctx, (size_t)ecap * 4);
   u32 *eB = (u32 *)arena_take(ctx, (size_t)ecap * 4);

@@ -291,13 +291,15 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
 // smem: z f32 | lo u32 (bit 31 = NOFLOW flag) | hi u32, pitch TP (odd)
 #define TP (TH + 1)
 #define R_NF 0x80000000u
+#define R_CHG 0x40000000u   // set when this visit changed the cell (write-back then needs no global re-read)
+#define R_VAL 0x3FFFFFFFu
 #define FLAT_SMEM (TH * TP * 12 + T * T * 2 + 16)
 
 __device__ __forceinline__ int slow_relax(const float *sz, u32 *slo, u32 *shi, int ci) {
   u32 w = slo[ci];
   if (!(w & R_NF)) return 0;
   float v = sz[ci];
-  u32 lo = w & ~R_NF, hi = shi[ci];
+  u32 lo = w & R_VAL, hi = shi[ci];
   u32 blo = lo ? lo : 0x7FFFFFFFu, bhi = hi ? hi : 0x7FFFFFFFu;
 #pragma unroll
   for (int dr = -1; dr <= 1; dr++)
@@ -307,7 +309,7 @@ __device__ __forceinline__ int slow_relax(const float *sz, u32 *slo, u32 *shi, i
       int ni = ci + dr * TP + dc;
       if (sz[ni] != v) continue;
       u32 nw = slo[ni];
-      u32 nlo = nw & ~R_NF;
+      u32 nlo = nw & R_VAL;
       if (nlo && nlo + 1 < blo) blo = nlo + 1;
       if (nw & R_NF) {
         u32 nhi = shi[ni];
@@ -315,8 +317,10 @@ __device__ __forceinline__ int slow_relax(const float *sz, u32 *slo, u32 *shi, i
       }
     }
   int changed = 0;
-  if (blo != 0x7FFFFFFFu && blo != lo) { slo[ci] = R_NF | blo; changed = 1; }
+  if (blo == 0x7FFFFFFFu) blo = lo;
   if (bhi != 0x7FFFFFFFu && bhi != hi) { shi[ci] = bhi; changed = 1; }
+  if (blo != lo) changed = 1;
+  if (changed) slo[ci] = R_NF | R_CHG | blo;
   return changed;
 }
 
@@ -382,22 +386,22 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
   if (!nlist) return;
   int ever = 0, nsweeps = 0;
   if (nlist * 4 > T * T) {
-    // dense flat (lake): directional Gauss-Seidel sweeps (rows ->, columns v, rows <-, columns ^);
-    // inside a line the distance front crosses the tile in one sweep.  Thread t: line (t % T),
-    // quarter (t / T).
-    const int line = 1 + tid % T, a0 = 1 + (tid / T) * 16, a1 = a0 + 15;
-    int quiet = 0;
-    // one sweep that changes nothing proves the fixed point (every cell was just re-evaluated)
-    for (int sweep = 0; quiet < 1; sweep++) {
+    // dense flat (lake): Gauss-Seidel along whole lines, all four directions at once (thread t walks line
+    // t % T in direction t / T: rows ->, columns v, rows <-, columns ^), so one pass carries the distance
+    // front across the full tile in every axis direction; concurrent writers only ever lower a value.
+    const int line = 1 + tid % T, dirn = tid / T;
+    // a pass that changes nothing proves the fixed point (every cell was just re-evaluated)
+    for (;;) {
       int changed = 0;
-      switch (sweep & 3) {
-        case 0: for (int c = a0; c <= a1; c++) changed |= slow_relax(sz, slo, shi, line * TP + c); break;
-        case 1: for (int r = a0; r <= a1; r++) changed |= slow_relax(sz, slo, shi, r * TP + line); break;
-        case 2: for (int c = a1; c >= a0; c--) changed |= slow_relax(sz, slo, shi, line * TP + c); break;
-        default: for (int r = a1; r >= a0; r--) changed |= slow_relax(sz, slo, shi, r * TP + line); break;
+      switch (dirn) {
+        case 0: for (int c = 1; c <= T; c++) changed |= slow_relax(sz, slo, shi, line * TP + c); break;
+        case 1: for (int r = 1; r <= T; r++) changed |= slow_relax(sz, slo, shi, r * TP + line); break;
+        case 2: for (int c = T; c >= 1; c--) changed |= slow_relax(sz, slo, shi, line * TP + c); break;
+        default: for (int r = T; r >= 1; r--) changed |= slow_relax(sz, slo, shi, r * TP + line); break;
       }
-      if (__syncthreads_or(changed)) { quiet = 0; ever = 1; } else quiet++;
-      nsweeps++;
+      nsweeps += 4;
+      if (!__syncthreads_or(changed)) break;
+      ever = 1;
     }
   } else {
     // sparse: Jacobi over the compact list of pending cells
@@ -422,10 +426,10 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
     if (r >= ny || c >= nx) continue;
     int ci = (lr + 1) * TP + lc + 1;
     u32 w = slo[ci];
-    if (!(w & R_NF)) continue;
+    if (!(w & R_CHG)) continue;
     size_t g = (size_t)r * nx + c;
-    u32 lo = w & ~R_NF, hi = shi[ci];
-    if (lo != dlo[g] || hi != dhi[g]) {
+    u32 lo = w & R_VAL, hi = shi[ci];
+    {
       dlo[g] = lo;
       dhi[g] = hi;
       if (lr == 0 || lc == 0 || lr == T - 1 || lc == T - 1) {
@@ -440,7 +444,7 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
             if (sz[ni] != v) continue;
             const u32 nw = slo[ni];
             if (!(nw & R_NF)) continue;
-            const u32 nlo = nw & ~R_NF, nhi = shi[ni];
+            const u32 nlo = nw & R_VAL, nhi = shi[ni];
             if ((lo && (nlo == 0 || lo + 1 < nlo)) || (hi && (nhi == 0 || hi + 1 < nhi)))
               nb9 |= 1 << ((hr == 0 ? 0 : (hr == TH - 1 ? 2 : 1)) * 3 + (hc == 0 ? 0 : (hc == TH - 1 ? 2 : 1)));
           }
