@@ -218,6 +218,10 @@ int hc_fill_shallow_pits_dev(hc_ctx *ctx, float *mod, float sfill, const int32_t
                              const float *fillv, const float *water, int64_t n, int32_t npits, int64_t *n_shallow,
                              void *stream);
 
+/* k-th smallest element (0-based) of x[0..n), exact (radix select; no NaN in x).  The order statistics behind
+ * np.percentile(raster_array, 1) in endo.find_sink (tools/endo.py:286).  value is a host pointer. */
+int hc_kth_value_dev(hc_ctx *ctx, const float *x, int64_t n, int64_t k, float *value, void *stream);
+
 /* HOST-buffer variants (H2D + kernels + D2H inside the call; synchronous). */
 int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
                  int seed_mode);

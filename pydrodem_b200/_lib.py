@@ -69,6 +69,7 @@ SIGNATURES = {
     "hc_pit_apply_dev": (ctypes.c_int, [c_vp] + [c_vp] * 6 + [c_i64, c_i32, c_i32] + [c_vp] * 6 + [c_i64, c_vp, c_vp, c_vp]),
     "hc_fill_shallow_pits_dev": (ctypes.c_int, [c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32,
                                                 ctypes.POINTER(c_i64), c_vp]),
+    "hc_kth_value_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.POINTER(c_f32), c_vp]),
     "hc_profile_enable": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "hc_profile_read": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "hc_debug_read": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_uint64)]),

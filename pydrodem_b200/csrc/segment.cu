@@ -511,3 +511,53 @@ extern "C" int hc_fill_shallow_pits_dev(hc_ctx *ctx, float *mod, float sfill, co
   }
   return HC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// exact order statistics (np.percentile of endo.find_sink, tools/endo.py:286): radix select over the
+// monotone uint image of the floats, 8 bits per pass (4 passes, one 256-bin histogram each)
+__global__ void __launch_bounds__(256)
+k_radix_hist(const float *__restrict__ x, size_t n, u32 prefix, u32 prefix_mask, int shift, unsigned long long *hist) {
+  __shared__ u32 sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    u32 u = d_ford(x[i]);
+    if ((u & prefix_mask) == prefix) atomicAdd(&sh[(u >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+// value of the k-th smallest element (0-based) of x[0..n); x must not contain NaN.  Host pointer out.
+extern "C" int hc_kth_value_dev(hc_ctx *ctx, const float *x, int64_t n, int64_t k, float *value, void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (!x || !value || n <= 0 || k < 0 || k >= n) { hc_set_error("hc_kth_value: bad argument"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_TRY(arena_reset(ctx));
+  unsigned long long *hist = (unsigned long long *)arena_take(ctx, 256 * 8);
+  if (!hist) return HC_ERR_NOMEM;
+  unsigned long long hh[256];
+  u32 prefix = 0, mask = 0;
+  unsigned long long rank = (unsigned long long)k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    HC_CUDA(cudaMemsetAsync(hist, 0, 256 * 8, st));
+    HC_PROF(ctx, st, "k_radix_hist");
+    k_radix_hist<<<ctx->sm_count * 8, 256, 0, st>>>(x, (size_t)n, prefix, mask, shift, hist);
+    HC_LAUNCH_CHECK(ctx);
+    HC_CUDA(cudaMemcpyAsync(hh, hist, 256 * 8, cudaMemcpyDeviceToHost, st));
+    HC_CUDA(cudaStreamSynchronize(st));
+    int d = 0;
+    for (; d < 256; d++) {
+      if (rank < hh[d]) break;
+      rank -= hh[d];
+    }
+    if (d == 256) { hc_set_error("hc_kth_value: internal (NaN in input?)"); return HC_ERR_INTERNAL; }
+    prefix |= (u32)d << shift;
+    mask |= 255u << shift;
+  }
+  u32 b = (prefix & 0x80000000u) ? (prefix & 0x7FFFFFFFu) : ~prefix;
+  memcpy(value, &b, 4);
+  return HC_OK;
+}
