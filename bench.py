@@ -458,7 +458,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=5400, help="edge of the crop timed on the CPU (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flats", type=int, default=1)
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "bands", "c3", "c5"],
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "bands", "c3", "c4", "c5"],
                     help="auto: c2 (one 10801^2 DEM) at N=1, bands (one 10801 x 10801*N DEM, a band per GPU, seam "
                          "exchange over NCCL) at N>1; c3: the 40000^2 DEM row-band-sharded over the N GPUs")
     ap.add_argument("--local-bands", type=int, default=1, help="bands per rank (N=1 with >1 emulates the exchange)")
@@ -497,9 +497,13 @@ def main():
     # one unit per GPU (weak scaling): same recipe, per-rank seed
     z = torch.empty((ny, nx), dtype=torch.float32, device=dev)
     band = 1024
-    for r0 in range(0, ny, band):
-        nr = min(band, ny - r0)
-        z[r0:r0 + nr] = synth.make_dem(ny, nx, 1002 + rank, row0=r0, nrows=nr, device=dev)
+    if args.workload == "c4":
+        # configs[3]: flattened lakes + burned rivers (large exact flats: flat resolution heavy)
+        z, _water = synth.make_c4(ny, nx, 1004 + rank, device=dev)
+    else:
+        for r0 in range(0, ny, band):
+            nr = min(band, ny - r0)
+            z[r0:r0 + nr] = synth.make_dem(ny, nx, 1002 + rank, row0=r0, nrows=nr, device=dev)
     torch.cuda.synchronize()
 
     kw = dict(dx=30.0, dy=30.0, seed_mode=hc.SEED_TAUDEM, table=hc.TABLE_TAUDEM, flats=bool(args.flats),
@@ -617,8 +621,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2: synthetic {ny}x{nx} float32 DEM with random pits (0.5% cells + 200 bowls, 1 cm "
-                               "quantised), fill + D8 + flat resolution + accumulation, TauDEM semantics "
+        "config": {"workload": (f"C4: synthetic {ny}x{nx} float32 DEM with flattened lakes and burned rivers (large exact "
+                                "flats) on the C2 terrain" if args.workload == "c4" else
+                                f"C2: synthetic {ny}x{nx} float32 DEM with random pits (0.5% cells + 200 bowls, 1 cm "
+                                "quantised)") + ", fill + D8 + flat resolution + accumulation, TauDEM semantics "
                                "(PitRemove/D8FlowDir/AreaD8), one unit per GPU",
                    "cells_per_gpu": cells, "l2": "inputs (467 MB z + outputs) exceed the 126 MB L2; no explicit flush",
                    "flats": bool(args.flats), "basins": basins, "boruvka_rounds": rounds,

@@ -152,3 +152,52 @@ def random_dem(ny, nx, seed, kind="noise", nodata_holes=0, levels=None):
         r, c = rng.integers(0, ny - h + 1), rng.integers(0, nx - w + 1)
         z[r:r + h, c:c + w] = NODATA
     return z
+
+
+def make_c4(ny, nx, seed, device="cpu", n_lakes=None, n_rivers=4):
+    """BASELINE.json configs[3]: the C2 terrain with the large EXACT flats pydrodem's water burning creates —
+    lakes set to one constant (tools/water.py:594), meandering rivers 5-40 px wide set to a per-reach constant
+    (tools/water.py:1383,1722), everything under water clamped to >= -1.0 (models/burn_rivers.py:754-762).
+    Returns (float32 DEM, uint8 water mask with the codes of models/burn_rivers.py:309-324: 1 river, 3 lake)."""
+    z = make_dem(ny, nx, seed, device=device, n_bowls=max(20, int(40 * ny * nx / (10801.0 * 10801.0))))
+    mask = torch.zeros((ny, nx), dtype=torch.uint8, device=device)
+    rng = np.random.default_rng(seed + 11)
+    n_lakes = n_lakes if n_lakes is not None else max(3, int(60 * ny * nx / (10801.0 * 10801.0)))
+    rows = torch.arange(ny, device=device, dtype=torch.float32)[:, None]
+    cols = torch.arange(nx, device=device, dtype=torch.float32)[None, :]
+    for _ in range(n_lakes):
+        r, c = rng.uniform(0.05, 0.95) * ny, rng.uniform(0.05, 0.95) * nx
+        rad = rng.uniform(0.004, 0.03) * min(ny, nx)
+        r0, r1 = int(max(0, r - rad)), int(min(ny, r + rad + 1))
+        c0, c1 = int(max(0, c - rad)), int(min(nx, c + rad + 1))
+        if r0 >= r1 or c0 >= c1:
+            continue
+        disc = ((rows[r0:r1] - r) ** 2 + (cols[:, c0:c1] - c) ** 2) <= rad * rad
+        sub = z[r0:r1, c0:c1]
+        lvl = torch.round(sub[disc].min() * 100.0) / 100.0 if bool(disc.any()) else None
+        if lvl is None:
+            continue
+        z[r0:r1, c0:c1] = torch.where(disc, lvl, sub)
+        mask[r0:r1, c0:c1] = torch.where(disc, torch.tensor(3, dtype=torch.uint8, device=device), mask[r0:r1, c0:c1])
+    for k in range(n_rivers):
+        # a meandering polyline from the high (north-west) side to the low (south-east) side, cut into reaches
+        t = np.linspace(0, 1, max(50, (ny + nx) // 16))
+        rr = (0.05 + 0.9 * t) * ny + 0.06 * ny * np.sin(2 * np.pi * (3 + k) * t + k)
+        cc = (0.1 + 0.2 * k + 0.6 * t) * nx % nx + 0.05 * nx * np.cos(2 * np.pi * (2 + k) * t)
+        width = rng.uniform(5, 40) * min(1.0, min(ny, nx) / 3000.0) + 2
+        for i in range(len(t) - 1):
+            r, c = rr[i], cc[i]
+            r0, r1 = int(max(0, r - width)), int(min(ny, r + width + 1))
+            c0, c1 = int(max(0, c - width)), int(min(nx, c + width + 1))
+            if r0 >= r1 or c0 >= c1:
+                continue
+            disc = ((rows[r0:r1] - r) ** 2 + (cols[:, c0:c1] - c) ** 2) <= (width / 2) ** 2
+            if not bool(disc.any()):
+                continue
+            sub = z[r0:r1, c0:c1]
+            lvl = torch.round(sub[disc].min() * 100.0) / 100.0
+            z[r0:r1, c0:c1] = torch.where(disc, lvl, sub)
+            mask[r0:r1, c0:c1] = torch.where(disc & (mask[r0:r1, c0:c1] == 0), torch.tensor(1, dtype=torch.uint8, device=device),
+                                             mask[r0:r1, c0:c1])
+    z = torch.where((mask > 0) & (z < -1.0), torch.tensor(-1.0, device=device), z)
+    return z.contiguous(), mask

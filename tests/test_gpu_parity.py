@@ -111,3 +111,18 @@ def test_medium_synthetic_tile(oracle, cuda):
         assert np.array_equal(gd, d)
         assert np.array_equal(gs, s)
         assert np.array_equal(ga, a)
+
+
+def test_c4_flattened_lakes_and_rivers(oracle, cuda):
+    """configs[3] recipe at 900 x 1100: lakes and river reaches set to exact constants (flat resolution heavy:
+    flats hundreds of cells across go through the slow tier), whole raster and 3 bands, vs the oracle."""
+    import pydrodem_b200 as hc
+    from pydrodem_b200 import bands, synth
+    z, mask = synth.make_c4(900, 1100, 1004)
+    z = z.numpy()
+    assert (mask.numpy() == 3).sum() > 500 and (mask.numpy() == 1).sum() > 2000
+    f, d, s, a = oracle.fill_d8_accum(z, dx=30.0, dy=30.0, seed_mode=1, table=1)
+    gf, gd, gs, ga = hc.fill_d8_accum(z, dx=30.0, dy=30.0, seed_mode=1, table=1)
+    assert np.array_equal(gf, f) and np.array_equal(gd, d) and np.array_equal(gs, s) and np.array_equal(ga, a)
+    bf, bd, bs, ba = bands.fill_d8_accum_banded(z, 3, dx=30.0, dy=30.0, table=1)
+    assert np.array_equal(bf, f) and np.array_equal(bd, d) and np.array_equal(ba, a)
