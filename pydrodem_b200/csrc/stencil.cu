@@ -330,6 +330,27 @@ extern "C" int hc_mean_std_dev(hc_ctx *ctx, const float *x, int64_t n, double *m
   return HC_OK;
 }
 
+// sums[0] = sum(x - shift), sums[1] = sum((x - shift)^2) in float64 (host pointer): the partial sums a row band
+// contributes to the global sigma of CreateDTM (models/dem_noise_removal.py:413) before an all_reduce
+extern "C" int hc_sum_shifted_dev(hc_ctx *ctx, const float *x, int64_t n, double shift, double *sums, void *stream) {
+  ST_CTX(ctx);
+  if (!sums) { hc_set_error("hc_sum_shifted: null pointer"); return HC_ERR_ARG; }
+  sums[0] = sums[1] = 0.0;
+  if (n <= 0) return HC_OK;
+  if (!x) { hc_set_error("hc_sum_shifted: null pointer"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_TRY(arena_reset(ctx));
+  double *acc = (double *)arena_take(ctx, 256);
+  if (!acc) return HC_ERR_NOMEM;
+  HC_CUDA(cudaMemsetAsync(acc, 0, 16, st));
+  HC_PROF(ctx, st, "k_sum2");
+  k_sum2<<<ctx->sm_count * 8, 256, 0, st>>>(x, (size_t)n, acc, shift);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(sums, acc, 16, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  return HC_OK;
+}
+
 extern "C" int hc_dtm_select_dev(hc_ctx *ctx, const float *dem, const float *z9, const float *z7, const float *z5,
                                  const float *z3, const int8_t *slope0, const float *curv, const uint8_t *swo,
                                  const uint8_t *edm, const uint8_t *tx, const uint8_t *artifact, float *zf, int8_t *filt,

@@ -153,3 +153,101 @@ def smooth_core(dem, dx, dy, gdir=4, fweights=None, slopebreaks=(0, 2, 6, 15, 30
     if host:
         return zf.cpu().numpy(), filt.cpu().numpy(), slope.cpu().numpy()
     return zf, filt, slope
+
+
+# ---- row bands (SURVEY.md §8e "smoothing stencils": bands + halo rows; sigma by all_reduce) -----------------------
+SMOOTH_HALO = 8   # rows: 4 (9x9 window) + 2 (curvature of the 5x5 result) + 1 (slope of Zf) and a margin
+
+
+def _sum_shifted(t, shift):
+    import torch
+    out = (ctypes.c_double * 2)()
+    x = t.reshape(-1)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().hc_sum_shifted_dev(_lib.context(x.device.index or 0), _tp(x), x.numel(), float(shift), out,
+                                                  _stream(x)), "hc_sum_shifted_dev")
+    return float(out[0]), float(out[1])
+
+
+class BandSmoother:
+    """Smoothing core of CreateDTM.run_tile on ONE row band that carries SMOOTH_HALO halo rows where it has a
+    neighbour (`top` / `bot`).  Three phases so that the caller can all_reduce the sigma sums in between:
+    a = stage1() -> (n, sum x); stage2(mean) -> (sum(x-m), sum((x-m)^2)); finish(sigma) -> (Zf, filter, slope) of the
+    own rows.  Everything away from the outer rows of the haloed array is identical to the whole-raster result
+    (the 'symm' padding and one-sided gradients only touch rows that are cropped)."""
+
+    def __init__(self, dem_h, top, bot, dx, dy, gdir=4, slopebreaks=(0, 2, 6, 15, 30), curvebreaks=(1.0, 2.5)):
+        self.d, self.top, self.bot = dem_h, bool(top), bool(bot)
+        self.dx, self.dy, self.gdir = dx, dy, gdir
+        self.sb, self.cb = slopebreaks, curvebreaks
+        self.lo = SMOOTH_HALO if self.top else 0
+        self.hi = dem_h.shape[0] - (SMOOTH_HALO if self.bot else 0)
+
+    def stage1(self):
+        d = self.d
+        ws = [DW_WEIGHTS[9], DW_WEIGHTS[7], DW_WEIGHTS[5], DW_WEIGHTS[3]]
+        self.zs = [apply_convolve_filter(d, build_kernel(w, dtype=np.float32, normalize=True)) for w in ws]
+        sl = slope_D4 if self.gdir == 4 else slope_D2
+        self.slope0 = sl(self.zs[2], self.dx, self.dy)
+        self.curv = curvature_D2(self.zs[2], self.dx, self.dy)
+        own = self.curv[self.lo:self.hi]
+        s1, _ = _sum_shifted(own, 0.0)
+        return own.numel(), s1
+
+    def stage2(self, mean):
+        return _sum_shifted(self.curv[self.lo:self.hi], mean)
+
+    def finish(self, sigma):
+        zf, filt = dtm_select(self.d, self.zs[0], self.zs[1], self.zs[2], self.zs[3], self.slope0, self.curv,
+                              np.float32(sigma), self.cb, self.sb)
+        sl = slope_D4 if self.gdir == 4 else slope_D2
+        slope = sl(zf, self.dx, self.dy)
+        return zf[self.lo:self.hi], filt[self.lo:self.hi], slope[self.lo:self.hi]
+
+
+def _sigma_from_sums(n, d1, d2):
+    d = d1 / n
+    return float(np.sqrt(max(d2 / n - d * d, 0.0)))
+
+
+def smooth_core_banded(dem, nbands, dx, dy, **kw):
+    """Single-process emulation: cut `dem` (torch CUDA tensor or numpy) into row bands with halos, run the
+    three phases band by band, combine the sigma sums as the all_reduce would, stitch.  Same return as smooth_core."""
+    import torch
+    host = not _is_torch(dem)
+    d = _to_dev(dem, np.float32)[0]
+    ny = d.shape[0]
+    base, extra = divmod(ny, nbands)
+    rows = [base + (1 if i < extra else 0) for i in range(nbands)]
+    r0s = np.concatenate([[0], np.cumsum(rows)])
+    sm = []
+    for i in range(nbands):
+        a, b = int(r0s[i]), int(r0s[i + 1])
+        top, bot = i > 0, i < nbands - 1
+        sm.append(BandSmoother(d[max(0, a - SMOOTH_HALO) if top else a: min(ny, b + SMOOTH_HALO) if bot else b].contiguous(),
+                               top, bot, dx, dy, **kw))
+    s = [x.stage1() for x in sm]
+    n = sum(v[0] for v in s)
+    mean = sum(v[1] for v in s) / n
+    s2 = [x.stage2(mean) for x in sm]
+    sigma = _sigma_from_sums(n, sum(v[0] for v in s2), sum(v[1] for v in s2))
+    outs = [x.finish(sigma) for x in sm]
+    zf, filt, slope = (torch.cat([o[k] for o in outs]) for k in range(3))
+    if host:
+        return zf.cpu().numpy(), filt.cpu().numpy(), slope.cpu().numpy()
+    return zf, filt, slope
+
+
+def smooth_core_rank(dem_h, top, bot, dx, dy, group=None, **kw):
+    """One band per rank over torch.distributed: `dem_h` = this rank's rows plus SMOOTH_HALO halo rows where a
+    neighbour exists (the caller exchanges them, e.g. with bands.exchange_halos on 8-row seams); sigma by two
+    all_reduces of (n, sum) and (sum, sum of squares).  Returns this band's (Zf, filter, slope)."""
+    import torch
+    import torch.distributed as dist
+    x = BandSmoother(dem_h, top, bot, dx, dy, **kw)
+    t = torch.tensor(list(x.stage1()), dtype=torch.float64, device=dem_h.device)
+    dist.all_reduce(t, group=group)
+    n, mean = float(t[0]), float(t[1] / t[0])
+    t2 = torch.tensor(list(x.stage2(mean)), dtype=torch.float64, device=dem_h.device)
+    dist.all_reduce(t2, group=group)
+    return x.finish(_sigma_from_sums(n, float(t2[0]), float(t2[1])))

@@ -96,3 +96,18 @@ def test_smooth_core_end_to_end(gold, cuda):
     tol = 2e-6 * float(np.abs(gold["zf_masked"]).max())
     assert float(np.abs(zf - gold["zf_masked"])[same].max()) <= tol
     assert (np.abs(slope.astype(int) - gold["slope_final_masked"].astype(int))[same] <= 1).all()
+
+
+@pytest.mark.parametrize("nbands", [2, 3, 5])
+def test_smoothing_core_row_bands_match_whole_raster(gold, cuda, nbands):
+    """the smoothing core shards into row bands with an 8-row halo; sigma is combined from per-band
+    float64 sums.  Zf / filter / slope must equal the whole-raster result cell for cell."""
+    from pydrodem_b200 import stencils
+    from pydrodem_b200 import synth
+    dem = synth.make_dem_numpy(230, 190, 1005, quantise=False)
+    dem = (dem + np.random.default_rng(3).normal(0, 1.5, dem.shape)).astype(np.float32)
+    zf, filt, slope = stencils.smooth_core(dem, 30.0, 30.0)
+    bzf, bfilt, bslope = stencils.smooth_core_banded(dem, nbands, 30.0, 30.0)
+    assert np.array_equal(bfilt, filt)
+    assert np.array_equal(bzf, zf)
+    assert np.array_equal(bslope, slope)
