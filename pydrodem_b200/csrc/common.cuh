@@ -167,7 +167,7 @@ int band_fill_local(hc_ctx *ctx, const float *z, int64_t nb, int64_t nx, float n
                     int64_t band_index, uint32_t *edges_out, cudaStream_t st);
 int band_fill_finish(hc_ctx *ctx, const uint32_t *all_edges, int64_t nbands, float *out, cudaStream_t st);
 int d8_run_rows(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx, float nodata,
-                double dx, double dy, int table, hc_rows rw, cudaStream_t st);
+                double dx, double dy, int table, hc_rows rw, cudaStream_t st, uint8_t *dir2 = nullptr);
 int band_flats_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t nb, int64_t nx,
                      float nodata, int table, int flags, cudaStream_t st);
 int band_flats_get_seams(hc_ctx *ctx, uint32_t *out, cudaStream_t st);

@@ -20,8 +20,8 @@ struct d8_params {
 // registers, so a cell costs 3 coalesced loads (two of them L1 hits), no shared memory, no barrier.
 template <int TABLE, bool SLOPE>
 __global__ void __launch_bounds__(D8_THREADS)
-k_d8(const float *__restrict__ z, uint8_t *__restrict__ dir, float *__restrict__ slope, int ny, int nx,
-     float nodata, d8_params prm, hc_rows rw) {
+k_d8(const float *__restrict__ z, uint8_t *__restrict__ dir, uint8_t *__restrict__ dir2, float *__restrict__ slope,
+     int ny, int nx, float nodata, d8_params prm, hc_rows rw) {
   const int c = blockIdx.x * D8_THREADS + threadIdx.x;
   if (c >= nx) return;
   const int rbeg = blockIdx.y * D8_RS, rend = min(rbeg + D8_RS, ny);
@@ -79,6 +79,7 @@ k_d8(const float *__restrict__ z, uint8_t *__restrict__ dir, float *__restrict__
       }
     }
     dir[g] = code;
+    if (dir2) dir2[g] = code;  // second copy: the flat pass then only rewrites NOFLOW cells
     if (SLOPE) slope[g] = sl;
 #pragma unroll
     for (int j = 0; j < 3; j++) { w[0][j] = w[1][j]; w[1][j] = w[2][j]; }
@@ -87,11 +88,11 @@ k_d8(const float *__restrict__ z, uint8_t *__restrict__ dir, float *__restrict__
 
 int d8_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx, float nodata,
            double dx, double dy, int table, cudaStream_t st) {
-  return d8_run_rows(ctx, z, dir, slope, ny, nx, nodata, dx, dy, table, hc_make_rows(ny, 0), st);
+  return d8_run_rows(ctx, z, dir, slope, ny, nx, nodata, dx, dy, table, hc_make_rows(ny, 0), st, nullptr);
 }
 
 int d8_run_rows(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx, float nodata,
-                double dx, double dy, int table, hc_rows rw, cudaStream_t st) {
+                double dx, double dy, int table, hc_rows rw, cudaStream_t st, uint8_t *dir2) {
   if (ny <= 0 || nx <= 0) return HC_OK;
   if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("d8: bad table %d", table); return HC_ERR_ARG; }
   if (!(dx > 0) || !(dy > 0)) { hc_set_error("d8: dx, dy must be > 0"); return HC_ERR_ARG; }
@@ -105,11 +106,11 @@ int d8_run_rows(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t
   }
   dim3 grid((unsigned)((nx + D8_THREADS - 1) / D8_THREADS), (unsigned)((ny + D8_RS - 1) / D8_RS));
   if (table == HC_TABLE_WBT) {
-    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm, rw); }
-    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm, rw); }
+    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, true><<<grid, D8_THREADS, 0, st>>>(z, dir, dir2, slope, (int)ny, (int)nx, nodata, prm, rw); }
+    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_WBT, false><<<grid, D8_THREADS, 0, st>>>(z, dir, dir2, slope, (int)ny, (int)nx, nodata, prm, rw); }
   } else {
-    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, true><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm, rw); }
-    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, false><<<grid, D8_THREADS, 0, st>>>(z, dir, slope, (int)ny, (int)nx, nodata, prm, rw); }
+    if (slope) { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, true><<<grid, D8_THREADS, 0, st>>>(z, dir, dir2, slope, (int)ny, (int)nx, nodata, prm, rw); }
+    else { HC_PROF(ctx, st, "k_d8"); k_d8<HC_TABLE_TAUDEM, false><<<grid, D8_THREADS, 0, st>>>(z, dir, dir2, slope, (int)ny, (int)nx, nodata, prm, rw); }
   }
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;

@@ -58,31 +58,24 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
   const float qnan = __int_as_float(0x7fc00000);
   if (tid == 0) s_n[0] = 0;
   __syncthreads();
-  // 1a. pure copy global -> shared with many loads in flight (dir parked in the `hi` array)
+  // 1. load + classify in one pass: NOFLOW flag, "open" on the region's rim, work list of the rest
+  //    (FR*FR is a multiple of NTHREADS: warps stay whole for the ballot)
 #pragma unroll 5
-  for (int i = tid; i < FR * FR; i += NTHREADS) {
+  for (int i0 = 0; i0 < FR * FR; i0 += NTHREADS) {
+    const int i = i0 + tid;
     int lr = i / FR, lc = i - lr * FR;
     int r = r0 + lr, c = c0 + lc;
     bool inb = r >= rw.rlo && r < rw.rhi && c >= 0 && c < nx;
     long long g = inb ? (long long)r * nx + c : 0;  // r = -1 / ny: a band's halo rows
     float v = __ldg(z + g);
     uint8_t d = __ldg(dirA + g);
-    sz[i] = (inb && v != nodata) ? v : qnan;
-    shi[i] = d;
-  }
-  __syncthreads();
-  // 1b. NOFLOW flag; non-rim NOFLOW cells go on the work list
-  for (int i0 = 0; i0 < FR * FR; i0 += NTHREADS) {  // FR*FR is a multiple of NTHREADS: warps stay whole
-    const int i = i0 + tid;
+    const bool valid = inb && v != nodata && v == v;
     u32 w = 0;
-    float v = sz[i];
     bool want = false;
-    if (v == v && shi[i] == HC_DIR_NOFLOW) {
-      int lr = i / FR, lc = i - lr * FR;
+    if (valid && d == HC_DIR_NOFLOW) {
       // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
       // (conservatively also when the rim coincides with the raster border)
       // ... and a NOFLOW cell of a band's halo row belongs to the neighbouring band: open too
-      int r = r0 + lr;
       if (lr == 0 || lc == 0 || lr == FR - 1 || lc == FR - 1 || r < 0 || r >= ny) w = F_NF | F_OPEN;
       else { w = F_NF; want = true; }
     }
@@ -98,6 +91,7 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
         if (k < FLCAP) list[k] = (unsigned short)i;
       }
     }
+    sz[i] = valid ? v : qnan;
     slo[i] = (unsigned short)w;
     shi[i] = 0;
   }
@@ -163,45 +157,52 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
     }
     if (tid == 0) { HC_DBG(0, sweeps); HC_DBG(1, 1); }
   }
-  // 4. write the tile: copy dirA, resolve closed flats, mark open ones pending
+  // 4. write: dirB already holds dirA's codes, so only the NOFLOW cells of the own tile are touched —
+  //    closed flats get their direction, open ones are marked pending
   int pend = 0;
-  for (int i = tid; i < T * T; i += NTHREADS) {
-    int lr = i / T, lc = i - lr * T;
-    int r = r0 + FH + lr, c = c0 + FH + lc;
-    if (r >= ny || c >= nx) continue;
-    int ci = (lr + FH) * FR + lc + FH;
-    size_t g = (size_t)r * nx + c;
+  auto resolve = [&](int ci, int lr, int lc) {
+    int r = r0 + lr, c = c0 + lc;
+    if (lr < FH || lr >= FH + T || lc < FH || lc >= FH + T || r >= ny || c >= nx) return;  // not an own cell
     u32 w = slo[ci];
-    uint8_t d;
-    if (w & F_NF) {
-      d = HC_DIR_NOFLOW;
-      if (giveup || (w & F_OPEN)) { d = HC_DIR_PENDING; pend = 1; }
-      else if (w & F_LO) {
-        float v = sz[ci];
-        int own = 2 * (int)(w & F_LO) - (int)shi[ci];
-        int mn = own, best = -1;
-        bool bdiag = false;
+    uint8_t d = HC_DIR_NOFLOW;
+    if (giveup || (w & F_OPEN)) { d = HC_DIR_PENDING; pend = 1; }
+    else if (w & F_LO) {
+      float v = sz[ci];
+      int own = 2 * (int)(w & F_LO) - (int)shi[ci];
+      int mn = own, best = -1;
+      bool bdiag = false;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          int ni = ci + c_dr[TABLE][k] * FR + c_dc[TABLE][k];
-          if (sz[ni] != v) continue;
-          u32 nw = slo[ni];
-          int key;
-          if (nw & F_NF) {
-            if (!(nw & F_LO)) continue;
-            key = 2 * (int)(nw & F_LO) - (int)shi[ni];
-          } else {
-            key = -0x40000000;
-          }
-          bool kdiag = (c_dr[TABLE][k] != 0) && (c_dc[TABLE][k] != 0);
-          if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = k; bdiag = kdiag; }
+      for (int k = 0; k < 8; k++) {
+        int ni = ci + c_dr[TABLE][k] * FR + c_dc[TABLE][k];
+        if (sz[ni] != v) continue;
+        u32 nw = slo[ni];
+        int key;
+        if (nw & F_NF) {
+          if (!(nw & F_LO)) continue;
+          key = 2 * (int)(nw & F_LO) - (int)shi[ni];
+        } else {
+          key = -0x40000000;
         }
-        if (best >= 0) d = (uint8_t)c_code[TABLE][best];
+        bool kdiag = (c_dr[TABLE][k] != 0) && (c_dc[TABLE][k] != 0);
+        if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = k; bdiag = kdiag; }
       }
-    } else {
-      d = __ldg(&dirA[g]);
+      if (best >= 0) d = (uint8_t)c_code[TABLE][best];
     }
-    dirB[g] = d;
+    if (d != HC_DIR_NOFLOW) dirB[(size_t)r * nx + c] = d;
+  };
+  if (!giveup) {
+    for (u32 k = tid; k < nlist; k += NTHREADS) {
+      int ci = list[k];
+      int lr = ci / FR;
+      resolve(ci, lr, ci - lr * FR);
+    }
+  } else {
+    // the work list overflowed: every NOFLOW cell of the tile goes to the slow tier
+    for (int i = tid; i < T * T; i += NTHREADS) {
+      int lr = i / T + FH, lc = i % T + FH;
+      int ci = lr * FR + lc;
+      if (slo[ci] & F_NF) resolve(ci, lr, lc);
+    }
   }
   pend = __syncthreads_or(pend);
   if (tid == 0 && pend) HC_DBG(2, 1);  // pending tiles
@@ -691,7 +692,8 @@ int d8_flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_
   HC_TRY(arena_reset(ctx));
   uint8_t *dirA = (uint8_t *)arena_take(ctx, n);
   if (!dirA) return HC_ERR_NOMEM;
-  HC_TRY(d8_run(ctx, z, dirA, slope, ny, nx, nodata, dx, dy, table, st));
+  // D8 writes both rasters; the flat pass then only rewrites the NOFLOW cells of `dir`
+  HC_TRY(d8_run_rows(ctx, z, dirA, slope, ny, nx, nodata, dx, dy, table, hc_make_rows(ny, 0), st, dir));
   return flats_core(ctx, z, dirA, dir, ny, nx, nodata, table, st);
 }
 
@@ -707,6 +709,7 @@ int band_flats_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *
   hc_rows rw = hc_make_rows(nb, flags);
   HC_TRY(arena_reset(ctx));
   ctx->band.flags = flags;
+  HC_CUDA(cudaMemcpyAsync(dirB, dirA, (size_t)nb * nx, cudaMemcpyDeviceToDevice, st));  // the fast tier only rewrites NOFLOW cells
   HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, nb, nx, nodata, table, rw, st));
   HC_TRY(flats_slow_init(ctx, rw, st));
   ctx->band.flats_ready = 1;
