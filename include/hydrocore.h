@@ -170,6 +170,18 @@ int hc_band_accum_local_dev(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int6
                             int flags, uint32_t *seam_out, void *stream);
 int hc_band_accum_finish_dev(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index,
                              uint32_t *acc, void *stream);
+/* labels of ONE mask over row bands (scipy numbering over the whole raster): local union-find, then rounds of
+ * { all_gather the uint32 [2][nx] seam records; relax } until no band reports `changed`, rank (returns the number of
+ * components whose first cell lies in this band), all_gather the counts (offset = sum over earlier bands), publish the
+ * (root, id) pairs of owned seam components [2][nx][2], all_gather + sort them by root (host side), finish. */
+int hc_band_label_local_dev(hc_ctx *ctx, const uint8_t *mask, int64_t nb, int64_t nx, int conn, int64_t row0,
+                            uint32_t *seam_out, void *stream);
+int hc_band_label_relax_dev(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index,
+                            uint32_t *seam_out, int *changed, void *stream);
+int hc_band_label_rank_dev(hc_ctx *ctx, int64_t *n_owned, void *stream);
+int hc_band_label_pairs_dev(hc_ctx *ctx, int64_t offset, uint32_t *pairs_out, void *stream);
+int hc_band_label_finish_dev(hc_ctx *ctx, int64_t offset, const uint32_t *keys, const uint32_t *vals, int64_t nkeys,
+                             int32_t *lab, void *stream);
 /* diagnostics of the last banded fill: terminal-graph edges emitted, MSF rounds, seam-graph rounds */
 int hc_band_stats(const hc_ctx *ctx, int64_t *term_edges, int32_t *msf_rounds, int32_t *global_rounds);
 

@@ -61,6 +61,11 @@ SIGNATURES = {
     "hc_band_flats_finish_dev": (ctypes.c_int, [c_vp, c_vp]),
     "hc_band_accum_local_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "hc_band_accum_finish_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "hc_band_label_local_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_i64, c_vp, c_vp]),
+    "hc_band_label_relax_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, ctypes.POINTER(ctypes.c_int), c_vp]),
+    "hc_band_label_rank_dev": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), c_vp]),
+    "hc_band_label_pairs_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "hc_band_label_finish_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "hc_band_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "hc_seg_stats_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hc_pit_catalog_dev": (ctypes.c_int, [c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32,

@@ -288,3 +288,96 @@ def fill_d8_accum_banded(z, nbands, nodata=-9999.0, dx=1.0, dy=1.0, table=TABLE_
         return (f.cpu().numpy(), d.cpu().numpy(), s.cpu().numpy() if s is not None else None,
                 a.cpu().numpy().view(np.uint32))
     return f, d, s, a
+
+
+class BandedLabel:
+    """scipy.ndimage.label numbering of ONE mask cut into row bands (SURVEY.md §8e "Labelling").  Local union-find
+    per band, min-root propagation across the seams (all_gather + relax rounds), ids = owner band's offset + local rank;
+    see csrc/label.cu.  `band_rows`: rows of this process's consecutive bands; returns int32 label tensors + total."""
+
+    def __init__(self, band_rows, nx, nbands, first_band, row0s, device, comm=None):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.rows, self.nx, self.nbands, self.first = list(band_rows), int(nx), int(nbands), int(first_band)
+        self.row0s = list(row0s)          # global first row of each LOCAL band
+        self.comm = comm if comm is not None else SeamComm()
+        self.ctx = [_lib.new_context(self.device.index or 0) for _ in self.rows]
+        self.rounds = 0
+
+    def close(self):
+        for c in self.ctx:
+            _lib.destroy_context(c)
+        self.ctx = []
+
+    def run(self, masks, conn=8):
+        torch, lib, nx = self.torch, self.lib, self.nx
+        nl = len(self.rows)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+        with torch.cuda.device(self.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            masks = [m.to(torch.uint8).contiguous() for m in masks]
+            seams = torch.empty((nl, 2, nx), dtype=torch.int32, device=self.device)
+            for i, nb in enumerate(self.rows):
+                _lib.check(lib.hc_band_label_local_dev(self.ctx[i], p(masks[i]), nb, nx, conn, self.row0s[i], p(seams[i]), st),
+                           "hc_band_label_local_dev")
+            self.rounds = 0
+            while True:
+                alls = self.comm.gather(seams)
+                changed = False
+                for i in range(nl):
+                    ch = ctypes.c_int(0)
+                    _lib.check(lib.hc_band_label_relax_dev(self.ctx[i], p(alls), self.nbands, self.first + i, p(seams[i]),
+                                                           ctypes.byref(ch), st), "hc_band_label_relax_dev")
+                    changed = changed or bool(ch.value)
+                self.rounds += 1
+                if not self.comm.any(changed, self.device):
+                    break
+                if self.rounds > 100000:
+                    raise _lib.HydrocoreError("banded labelling did not converge")
+            owned = torch.zeros((nl,), dtype=torch.int64, device=self.device)
+            for i in range(nl):
+                n = ctypes.c_int64(0)
+                _lib.check(lib.hc_band_label_rank_dev(self.ctx[i], ctypes.byref(n), st), "hc_band_label_rank_dev")
+                owned[i] = n.value
+            counts = self.comm.gather(owned.reshape(nl, 1)).reshape(-1)
+            offs = torch.cumsum(counts, 0) - counts
+            total = int(counts.sum())
+            pairs = torch.empty((nl, 2, nx, 2), dtype=torch.int32, device=self.device)
+            for i in range(nl):
+                _lib.check(lib.hc_band_label_pairs_dev(self.ctx[i], int(offs[self.first + i]), p(pairs[i]), st),
+                           "hc_band_label_pairs_dev")
+            allp = self.comm.gather(pairs).reshape(-1, 2)
+            allp = allp[allp[:, 1] > 0]
+            keys64 = allp[:, 0].to(torch.int64) & 0xFFFFFFFF
+            order = torch.argsort(keys64)
+            keys = allp[order, 0].contiguous()
+            vals = allp[order, 1].contiguous()
+            labs = []
+            for i, nb in enumerate(self.rows):
+                lab = torch.empty((nb, nx), dtype=torch.int32, device=self.device)
+                _lib.check(lib.hc_band_label_finish_dev(self.ctx[i], int(offs[self.first + i]), p(keys), p(vals), keys.numel(),
+                                                        p(lab), st), "hc_band_label_finish_dev")
+                labs.append(lab)
+        return labs, total
+
+
+def label_banded(mask, nbands, conn=8):
+    """Whole-raster convenience (single process, `nbands` local bands): returns (int32 labels, n) like core.label."""
+    import numpy as np
+    import torch
+    host = not type(mask).__module__.startswith("torch")
+    m = torch.from_numpy(np.ascontiguousarray(np.asarray(mask) != 0).astype(np.uint8)).cuda() if host else mask
+    ny, nx = m.shape
+    rows = split_rows(ny, nbands)
+    row0s = [sum(rows[:i]) for i in range(nbands)]
+    bl = BandedLabel(rows, nx, nbands, 0, row0s, m.device)
+    try:
+        labs, n = bl.run([m[r0:r0 + nb] for r0, nb in zip(row0s, rows)], conn)
+        out = torch.cat(labs)
+        torch.cuda.synchronize()
+        label_banded.last_rounds = bl.rounds
+    finally:
+        bl.close()
+    return (out.cpu().numpy(), n) if host else (out, n)

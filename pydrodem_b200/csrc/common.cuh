@@ -72,6 +72,9 @@ struct hc_band_state {
   int acc_ready; const uint8_t *dir; unsigned long long *pstate; unsigned short *pexit; u32 *pdown, *pinflow, *bout;
 };
 
+// banded labelling: state between the phases (pointers into the arena)
+struct band_label_state { u32 *L, *G, *R, *flag; int64_t nb, nx; int conn, ready; u32 base, owned; };
+
 #define HC_MAX_BLOCKS 64
 struct hc_block { char *p; size_t cap, off; };
 
@@ -93,6 +96,7 @@ struct hc_ctx {
   int64_t band_term_edges;
   int32_t band_msf_rounds, band_global_rounds;
   hc_band_state band;
+  band_label_state band_label;
   // grow-only device staging buffers of the *_host entry points (z, filled, dir, slope, acc)
   void *io[5];
   size_t io_cap[5];

@@ -265,3 +265,182 @@ int ext_nodata_mask(hc_ctx *ctx, const float *z, uint8_t *ext, int64_t ny, int64
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
+
+// =================================================================================================
+// Row bands (SURVEY.md §8e "Labelling"): local union-find per band; a component's GLOBAL root is the
+// smallest global cell index over all its parts.  Parts are joined by min-label propagation across the
+// seams: every round each band publishes, for its seam cells, the current global root of their component
+// and lowers its own components to the smallest root seen across the seam (one all_gather + one small
+// kernel per round, until nothing changes anywhere: as many rounds as a component's path has seam
+// crossings).  Ids then follow scipy's rule: rank of the global root among all roots in raster order =
+// owner band's offset (all_gather of the bands' owned-root counts) + local rank; components rooted in
+// another band look their id up in the (root, id) pairs the owners publish for their seam cells.
+// =================================================================================================
+__global__ void k_band_lab_groot_init(const u32 *__restrict__ L, u32 *__restrict__ G, u32 base, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) G[i] = (L[i] == (u32)i) ? base + (u32)i : HC_NONE;   // defined at local roots only
+}
+// out[side][c] = global root of the seam cell's component, or NONE
+__global__ void k_band_lab_seams(const u32 *__restrict__ L, const u32 *__restrict__ G, int ny, int nx, u32 *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * nx) return;
+  int side = i / nx, c = i - side * nx;
+  u32 p = L[(size_t)(side ? ny - 1 : 0) * nx + c];
+  out[i] = p == HC_NONE ? HC_NONE : G[p];
+}
+// lower own components to the smallest root seen across the seams; *changed != 0 if anything moved
+__global__ void k_band_lab_relax(const u32 *__restrict__ L, u32 *G, int ny, int nx, const u32 *__restrict__ all, int band,
+                                 int nbands, int conn8, u32 *changed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * nx) return;
+  int side = i / nx, c = i - side * nx;
+  int ob = side ? band + 1 : band - 1;   // the band across this seam
+  if (ob < 0 || ob >= nbands) return;
+  u32 p = L[(size_t)(side ? ny - 1 : 0) * nx + c];
+  if (p == HC_NONE) return;
+  const u32 *row = all + ((size_t)ob * 2 + (side ? 0 : 1)) * nx;   // its facing seam row
+  u32 m = HC_NONE;
+  for (int d = conn8 ? -1 : 0; d <= (conn8 ? 1 : 0); d++) {
+    int cc = c + d;
+    if (cc < 0 || cc >= nx) continue;
+    u32 g = row[cc];
+    if (g < m) m = g;
+  }
+  if (m != HC_NONE && m < G[p]) {
+    if (atomicMin(&G[p], m) > m) *changed = 1u;
+  }
+}
+// Lo[i] = i for local roots whose component's first cell lies in this band (owned), else NONE
+__global__ void k_band_lab_owned(const u32 *__restrict__ L, const u32 *__restrict__ G, u32 base, u32 *__restrict__ Lo, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) Lo[i] = (L[i] == (u32)i && G[i] == base + (u32)i) ? (u32)i : HC_NONE;
+}
+// pairs[side][c] = (global root, id) for seam cells of OWNED components, (NONE, 0) otherwise
+__global__ void k_band_lab_pairs(const u32 *__restrict__ L, const u32 *__restrict__ G, const u32 *__restrict__ R, u32 base,
+                                 u32 offset, int ny, int nx, u32 *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * nx) return;
+  int side = i / nx, c = i - side * nx;
+  u32 p = L[(size_t)(side ? ny - 1 : 0) * nx + c];
+  u32 g = HC_NONE, id = 0;
+  if (p != HC_NONE && G[p] == base + p) { g = G[p]; id = offset + R[p]; }
+  out[2 * (size_t)i] = g;
+  out[2 * (size_t)i + 1] = id;
+}
+__global__ void __launch_bounds__(256)
+k_band_lab_out(const u32 *__restrict__ L, const u32 *__restrict__ G, const u32 *__restrict__ R, u32 base, u32 offset,
+               const u32 *__restrict__ keys, const u32 *__restrict__ vals, int nkeys, int32_t *__restrict__ lab, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    u32 p = L[i];
+    int32_t id = 0;
+    if (p != HC_NONE) {
+      u32 g = G[p];
+      if (g == base + p) id = (int32_t)(offset + __ldg(&R[p]));
+      else {
+        int lo = 0, hi = nkeys - 1;   // sorted (root, id) pairs published by the owners
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < g) lo = mid + 1; else hi = mid; }
+        id = (nkeys > 0 && keys[lo] == g) ? (int32_t)vals[lo] : -1;
+      }
+    }
+    lab[i] = id;
+  }
+}
+
+
+// local: union-find of the band's own rows; seam_out[2][nx] = global roots of the seam cells; *n_owned_guess unused
+extern "C" int hc_band_label_local_dev(hc_ctx *ctx, const uint8_t *mask, int64_t nb, int64_t nx, int conn, int64_t row0,
+                                       uint32_t *seam_out, void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (!mask || !seam_out || nb <= 0 || nx <= 0 || (conn != 4 && conn != 8)) { hc_set_error("hc_band_label_local: bad argument"); return HC_ERR_ARG; }
+  if ((double)(row0 + nb) * (double)nx >= 2147483632.0) { hc_set_error("labelled raster exceeds the 31-bit cell index"); return HC_ERR_TOO_LARGE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)nb * nx;
+  HC_TRY(arena_reset(ctx));
+  band_label_state *s = &ctx->band_label;
+  s->L = (u32 *)arena_take(ctx, n * 4);
+  s->G = (u32 *)arena_take(ctx, n * 4);
+  s->R = (u32 *)arena_take(ctx, n * 4);
+  s->flag = (u32 *)arena_take(ctx, 256);
+  if (!s->L || !s->G || !s->R || !s->flag) return HC_ERR_NOMEM;
+  s->nb = nb; s->nx = nx; s->conn = conn; s->base = (u32)(row0 * nx); s->ready = 1;
+  HC_TRY(label_roots(ctx, mask, s->L, nb, nx, conn, st));
+  unsigned gb = (unsigned)((n + 255) / 256);
+  k_band_lab_groot_init<<<gb, 256, 0, st>>>(s->L, s->G, s->base, n);
+  HC_LAUNCH_CHECK(ctx);
+  k_band_lab_seams<<<(unsigned)((2 * nx + 255) / 256), 256, 0, st>>>(s->L, s->G, (int)nb, (int)nx, seam_out);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+// one propagation round: takes every band's seam record, lowers own components, republishes; *changed (host)
+extern "C" int hc_band_label_relax_dev(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index,
+                                       uint32_t *seam_out, int *changed, void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  band_label_state *s = &ctx->band_label;
+  if (!s->ready || !all_seams || !seam_out) { hc_set_error("hc_band_label_relax: local phase first"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_CUDA(cudaMemsetAsync(s->flag, 0, 4, st));
+  unsigned gs = (unsigned)((2 * s->nx + 255) / 256);
+  k_band_lab_relax<<<gs, 256, 0, st>>>(s->L, s->G, (int)s->nb, (int)s->nx, all_seams, (int)band_index, (int)nbands, s->conn == 8, s->flag);
+  HC_LAUNCH_CHECK(ctx);
+  k_band_lab_seams<<<gs, 256, 0, st>>>(s->L, s->G, (int)s->nb, (int)s->nx, seam_out);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, s->flag, 4, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  if (changed) *changed = ctx->h_mail[0] ? 1 : 0;
+  return HC_OK;
+}
+// rank the owned roots locally; *n_owned (host) = components whose first cell lies in this band
+extern "C" int hc_band_label_rank_dev(hc_ctx *ctx, int64_t *n_owned, void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  band_label_state *s = &ctx->band_label;
+  if (!s->ready) { hc_set_error("hc_band_label_rank: local phase first"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)s->nb * s->nx;
+  u32 nchunks = (u32)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  u32 *Lo = (u32 *)arena_take(ctx, n * 4);
+  u32 *bsum = (u32 *)arena_take(ctx, (size_t)nchunks * 4);
+  if (!Lo || !bsum) return HC_ERR_NOMEM;
+  k_band_lab_owned<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->L, s->G, s->base, Lo, n);
+  HC_LAUNCH_CHECK(ctx);
+  k_root_count<<<nchunks, 256, 0, st>>>(Lo, bsum, n);
+  HC_LAUNCH_CHECK(ctx);
+  k_scan_blocks<<<1, 1024, 0, st>>>(bsum, nchunks, s->flag + 1);
+  HC_LAUNCH_CHECK(ctx);
+  k_root_rank<<<nchunks, 256, 0, st>>>(Lo, bsum, s->R, n);
+  HC_LAUNCH_CHECK(ctx);
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, s->flag + 1, 4, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  s->owned = ctx->h_mail[0];
+  if (n_owned) *n_owned = s->owned;
+  return HC_OK;
+}
+// pairs_out[2][nx][2]: (global root, id) of the seam cells of owned components (id = offset + local rank)
+extern "C" int hc_band_label_pairs_dev(hc_ctx *ctx, int64_t offset, uint32_t *pairs_out, void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  band_label_state *s = &ctx->band_label;
+  if (!s->ready || !pairs_out) { hc_set_error("hc_band_label_pairs: rank phase first"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  k_band_lab_pairs<<<(unsigned)((2 * s->nx + 255) / 256), 256, 0, st>>>(s->L, s->G, s->R, s->base, (u32)offset, (int)s->nb, (int)s->nx, pairs_out);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+// final ids: keys/vals = every band's published (root, id) pairs with id > 0, sorted by root (device pointers)
+extern "C" int hc_band_label_finish_dev(hc_ctx *ctx, int64_t offset, const uint32_t *keys, const uint32_t *vals,
+                                        int64_t nkeys, int32_t *lab, void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  band_label_state *s = &ctx->band_label;
+  if (!s->ready || !lab) { hc_set_error("hc_band_label_finish: rank phase first"); return HC_ERR_ARG; }
+  s->ready = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)s->nb * s->nx;
+  k_band_lab_out<<<ctx->sm_count * 8, 256, 0, st>>>(s->L, s->G, s->R, s->base, (u32)offset, keys, vals, (int)nkeys, lab, n);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}

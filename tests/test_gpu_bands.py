@@ -86,3 +86,19 @@ def test_bands_over_nccl_two_ranks(cuda):
            "--nx", "1800", "--full"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "BANDS_NCCL_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("conn", [4, 8])
+@pytest.mark.parametrize("shape,p,seed,nbands", [((40, 30), 0.5, 1, 2), ((64, 64), 0.6, 3, 4), ((130, 257), 0.45, 4, 5),
+                                                 ((500, 333), 0.55, 5, 7), ((300, 300), 1.0, 7, 3), ((300, 300), 0.0, 8, 3),
+                                                 ((90, 120), 0.62, 9, 45)])
+def test_banded_labels_match_scipy(shape, p, seed, nbands, conn, oracle, cuda):
+    """Row-band labelling: ids identical to scipy.ndimage.label over the WHOLE mask (components snake across many seams at
+    p ~ 0.6: the min-root propagation needs several rounds)."""
+    from pydrodem_b200 import bands
+    rng = np.random.default_rng(seed)
+    m = (rng.random(shape) < p).astype(np.uint8)
+    want, n_want = oracle.label(m, conn)
+    got, n_got = bands.label_banded(m, nbands, conn)
+    assert n_got == n_want
+    assert np.array_equal(got, want), f"{(got != want).sum()} cells differ (rounds {bands.label_banded.last_rounds})"
