@@ -145,10 +145,12 @@ int hc_dtm_select_dev(hc_ctx *ctx, const float *dem, const float *z9, const floa
  *                1 + (band*2 + side)*nx + col = seam cell): the minimum spanning forest of the
  *                band's terminal graph + the cross-seam edges of its bottom seam; unused entries 0.
  *        finish: all_edges = nbands * cap triples (band order); solves the seam graph, writes out.
- *        Only HC_SEED_TAUDEM (the WBT exterior-nodata rule would need a global labelling). */
+ *        HC_SEED_WBT: `ext` = uint8 raster (halo rows like z) that is 1 on nodata cells connected to the raster
+ *        frame through nodata — a band cannot know that by itself; bands.py derives it from the banded labelling
+ *        of the nodata mask.  ext == NULL means every nodata cell is exterior.  Ignored for HC_SEED_TAUDEM. */
 int64_t hc_band_fill_edge_cap(int64_t nx);
 int hc_band_fill_local_dev(hc_ctx *ctx, const float *z, int64_t nb, int64_t nx, float nodata, int seed_mode,
-                           int flags, int64_t band_index, uint32_t *edges_out, void *stream);
+                           int flags, int64_t band_index, const uint8_t *ext, uint32_t *edges_out, void *stream);
 int hc_band_fill_finish_dev(hc_ctx *ctx, const uint32_t *all_edges, int64_t nbands, float *out, void *stream);
 /* D8 on a band (z with halo rows; seam rows are not raster border). */
 int hc_band_d8_dev(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t nb, int64_t nx,
@@ -182,6 +184,8 @@ int hc_band_label_rank_dev(hc_ctx *ctx, int64_t *n_owned, void *stream);
 int hc_band_label_pairs_dev(hc_ctx *ctx, int64_t offset, uint32_t *pairs_out, void *stream);
 int hc_band_label_finish_dev(hc_ctx *ctx, int64_t offset, const uint32_t *keys, const uint32_t *vals, int64_t nkeys,
                              int32_t *lab, void *stream);
+/* out[i] = flag[lab[i]] (flag[0] = 0): turns per-component flags into a raster (exterior nodata of the WBT seed rule) */
+int hc_gather_flag_dev(hc_ctx *ctx, const int32_t *lab, const uint8_t *flag, uint8_t *out, int64_t n, void *stream);
 /* diagnostics of the last banded fill: terminal-graph edges emitted, MSF rounds, seam-graph rounds */
 int hc_band_stats(const hc_ctx *ctx, int64_t *term_edges, int32_t *msf_rounds, int32_t *global_rounds);
 

@@ -49,7 +49,7 @@ SIGNATURES = {
     "hc_label_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32)]),
     "hc_band_fill_edge_cap": (c_i64, [c_i64]),
     "hc_band_fill_local_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, ctypes.c_int, c_i64, c_vp,
-                                              c_vp]),
+                                              c_vp, c_vp]),
     "hc_band_fill_finish_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "hc_band_d8_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64, c_f64, ctypes.c_int,
                                       ctypes.c_int, c_vp]),
@@ -66,6 +66,7 @@ SIGNATURES = {
     "hc_band_label_rank_dev": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), c_vp]),
     "hc_band_label_pairs_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
     "hc_band_label_finish_dev": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "hc_gather_flag_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "hc_band_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "hc_seg_stats_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hc_pit_catalog_dev": (ctypes.c_int, [c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32,

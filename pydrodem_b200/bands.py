@@ -23,7 +23,7 @@ chain.
 import ctypes
 
 from . import _lib
-from ._lib import SEED_TAUDEM, TABLE_TAUDEM
+from ._lib import SEED_TAUDEM, SEED_WBT, TABLE_TAUDEM  # noqa: F401
 
 
 def split_rows(ny, nbands):
@@ -155,6 +155,56 @@ class BandedChain:
     def _chk(self, rc, what):
         _lib.check(rc, what)
 
+    def _exterior_nodata(self):
+        """WBT seed rule on bands: nodata cells connected to the raster frame through nodata (8-connectivity).  Banded
+        labels of the nodata mask, a per-component "touches the frame" flag (max-reduced over the ranks), and the flag
+        gathered back into halo'd uint8 rasters."""
+        torch, lib, nx = self.torch, self.lib, self.nx
+        nl = len(self.rows)
+        st = self._stream()
+        masks = []
+        for i in range(nl):
+            z = self.z_view(i)
+            masks.append(((z == self.nodata) | torch.isnan(z)).to(torch.uint8))
+        any_nd = self.comm.any(any(bool(m.any()) for m in masks), self.device)
+        if not any_nd:
+            return [None] * nl
+        rows_all = self.comm.gather(torch.tensor(self.rows, dtype=torch.int64, device=self.device).reshape(nl, 1)).reshape(-1)
+        row0_all = (torch.cumsum(rows_all, 0) - rows_all).tolist()
+        bl = BandedLabel(self.rows, nx, self.nbands, self.first, [row0_all[self.first + i] for i in range(nl)], self.device,
+                         comm=self.comm)
+        try:
+            labs, total = bl.run(masks, 8)
+        finally:
+            bl.close()
+        touch = torch.zeros(total + 1, dtype=torch.float32, device=self.device)
+        for i, nb in enumerate(self.rows):
+            g = self.first + i
+            border = torch.zeros((nb, nx), dtype=torch.float32, device=self.device)
+            border[:, 0] = 1
+            border[:, -1] = 1
+            if g == 0:
+                border[0] = 1
+            if g == self.nbands - 1:
+                border[-1] = 1
+            t = torch.empty(total + 1, dtype=torch.float32, device=self.device)
+            self._chk(lib.hc_seg_stats_dev(self.ctx[i], ctypes.c_void_p(labs[i].data_ptr()), ctypes.c_void_p(border.data_ptr()),
+                                           None, nb * nx, total, 1, ctypes.c_void_p(t.data_ptr()), None, None, None, st),
+                      "hc_seg_stats_dev")
+            touch = torch.maximum(touch, torch.clamp(t, min=0.0))
+        if self.comm.world > 1:
+            self.comm.dist.all_reduce(touch, op=self.comm.dist.ReduceOp.MAX, group=self.comm.group)
+        flag = (touch > 0).to(torch.uint8)
+        flag[0] = 0
+        exts = []
+        for i, nb in enumerate(self.rows):
+            e = torch.zeros((nb + 2, nx), dtype=torch.uint8, device=self.device)
+            self._chk(lib.hc_gather_flag_dev(self.ctx[i], ctypes.c_void_p(labs[i].data_ptr()), ctypes.c_void_p(flag.data_ptr()),
+                                             self._p(e), nb * nx, st), "hc_gather_flag_dev")
+            exts.append(e)
+        self._halo_exchange(exts)
+        return exts
+
     # ---- the chain -------------------------------------------------------------------------------
     def run(self, z_list=None):
         torch, lib, nx = self.torch, self.lib, self.nx
@@ -167,11 +217,13 @@ class BandedChain:
             self._mark("start")
             self._halo_exchange(self.zh)
             self._mark("halo_z")
+            exts = self._exterior_nodata() if self.seed_mode != SEED_TAUDEM else [None] * nl
             # fill
             for i, nb in enumerate(self.rows):
                 self._chk(lib.hc_band_fill_local_dev(self.ctx[i], self._p(self.zh[i]), nb, nx, self.nodata, self.seed_mode,
-                                                     self.flags(i), self.first + i, ctypes.c_void_p(self.edges[i].data_ptr()),
-                                                     st), "hc_band_fill_local_dev")
+                                                     self.flags(i), self.first + i,
+                                                     self._p(exts[i]) if exts[i] is not None else None,
+                                                     ctypes.c_void_p(self.edges[i].data_ptr()), st), "hc_band_fill_local_dev")
             self._mark("fill_local")
             all_edges = self.comm.gather(self.edges)
             self._mark("gather_edges")
@@ -256,7 +308,8 @@ class BandedChain:
         return out
 
 
-def fill_d8_accum_banded(z, nbands, nodata=-9999.0, dx=1.0, dy=1.0, table=TABLE_TAUDEM, flats=True, want_slope=True):
+def fill_d8_accum_banded(z, nbands, nodata=-9999.0, dx=1.0, dy=1.0, table=TABLE_TAUDEM, flats=True, want_slope=True,
+                         seed_mode=SEED_TAUDEM):
     """Whole-raster convenience: cut `z` (2-D torch CUDA tensor or numpy array) into `nbands` row bands on one
     device, run the banded chain, and stitch the results.  Same return as core.fill_d8_accum."""
     import numpy as np
@@ -266,7 +319,7 @@ def fill_d8_accum_banded(z, nbands, nodata=-9999.0, dx=1.0, dy=1.0, table=TABLE_
     ny, nx = zt.shape
     rows = split_rows(ny, nbands)
     ch = BandedChain(rows, nx, nbands, 0, zt.device, nodata=nodata, dx=dx, dy=dy, table=table, flats=flats,
-                     want_slope=want_slope)
+                     want_slope=want_slope, seed_mode=seed_mode)
     try:
         r0 = 0
         zs = []

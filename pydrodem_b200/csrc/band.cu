@@ -21,11 +21,12 @@ static int check_band(int64_t nb, int64_t nx, int flags) {
 extern "C" int64_t hc_band_fill_edge_cap(int64_t nx) { return band_fill_edge_cap(nx); }
 
 extern "C" int hc_band_fill_local_dev(hc_ctx *ctx, const float *z, int64_t nb, int64_t nx, float nodata, int seed_mode,
-                                      int flags, int64_t band_index, uint32_t *edges_out, void *stream) {
+                                      int flags, int64_t band_index, const uint8_t *ext, uint32_t *edges_out, void *stream) {
   CHECK_CTX(ctx);
   HC_TRY(check_band(nb, nx, flags));
   if (!z || !edges_out || band_index < 0) { hc_set_error("hc_band_fill_local: bad argument"); return HC_ERR_ARG; }
-  return band_fill_local(ctx, z, nb, nx, nodata, seed_mode, flags, band_index, edges_out, (cudaStream_t)stream);
+  if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("hc_band_fill_local: bad seed_mode"); return HC_ERR_ARG; }
+  return band_fill_local(ctx, z, nb, nx, nodata, seed_mode, flags, band_index, edges_out, (cudaStream_t)stream, ext);
 }
 
 extern "C" int hc_band_fill_finish_dev(hc_ctx *ctx, const uint32_t *all_edges, int64_t nbands, float *out, void *stream) {

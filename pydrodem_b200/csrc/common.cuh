@@ -168,7 +168,7 @@ size_t label_workspace(int64_t ny, int64_t nx);
 // row-band phases (band.cu holds the extern "C" wrappers)
 int64_t band_fill_edge_cap(int64_t nx);
 int band_fill_local(hc_ctx *ctx, const float *z, int64_t nb, int64_t nx, float nodata, int seed_mode, int flags,
-                    int64_t band_index, uint32_t *edges_out, cudaStream_t st);
+                    int64_t band_index, uint32_t *edges_out, cudaStream_t st, const uint8_t *ext = nullptr);
 int band_fill_finish(hc_ctx *ctx, const uint32_t *all_edges, int64_t nbands, float *out, cudaStream_t st);
 int d8_run_rows(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_t ny, int64_t nx, float nodata,
                 double dx, double dy, int table, hc_rows rw, cudaStream_t st, uint8_t *dir2 = nullptr);

@@ -113,7 +113,7 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
             for (int dr = -1; dr <= 1; dr++)
               for (int dc = -1; dc <= 1; dc++) {
                 float zn = w[(dr + 1) * TH + dc + 1];
-                if (zn != zn && ext[(size_t)(r + dr) * nx + (c + dc)]) seed = true;
+                if (zn != zn && ext[(long long)(r + dr) * nx + (c + dc)]) seed = true;  // (halo rows of a band: r + dr = -1 / ny)
               }
           }
         }
@@ -628,26 +628,26 @@ struct fill_state {
 };
 
 static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float nodata, int seed_mode, hc_rows rw,
-                      fill_state *fs, cudaStream_t st) {
+                      fill_state *fs, cudaStream_t st, const uint8_t *ext_in = nullptr) {
   size_t n = (size_t)ny * nx;
   if (n >= 0x7FFFFFF0ull) { hc_set_error("raster too large for 31-bit cell indices"); return HC_ERR_TOO_LARGE; }
   const bool banded = rw.top || rw.bot;
   if (banded && ny < 2) { hc_set_error("a band needs at least 2 rows"); return HC_ERR_ARG; }
-  if (banded && seed_mode != HC_SEED_TAUDEM) {
-    hc_set_error("banded fill: only HC_SEED_TAUDEM (the WBT exterior-nodata rule needs a global labelling)");
-    return HC_ERR_ARG;
-  }
+  // (a band cannot tell exterior from interior nodata by itself: under the WBT rule the caller passes the
+  //  exterior-nodata raster it got from the banded labelling, halo rows included; NULL = all nodata is exterior)
   const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t tiles = (size_t)tx * ty;
   HC_TRY(arena_reset(ctx));
 
-  uint8_t *ext = nullptr;
-  if (seed_mode == HC_SEED_WBT) {
-    ext = (uint8_t *)arena_take(ctx, n);
-    if (!ext) return HC_ERR_NOMEM;
+  const uint8_t *ext = nullptr;
+  if (seed_mode == HC_SEED_WBT && banded) {
+    ext = ext_in;
+  } else if (seed_mode == HC_SEED_WBT) {
+    uint8_t *e = (uint8_t *)arena_take(ctx, n);
+    if (!e) return HC_ERR_NOMEM;
     int has_interior = 0;
-    HC_TRY(ext_nodata_mask(ctx, z, ext, ny, nx, nodata, &has_interior, st));
-    if (!has_interior) ext = nullptr;  // every nodata cell sits on the raster border: all exterior
+    HC_TRY(ext_nodata_mask(ctx, z, e, ny, nx, nodata, &has_interior, st));
+    ext = has_interior ? e : nullptr;  // every nodata cell sits on the raster border: all exterior
   }
   u32 *P = (u32 *)arena_take(ctx, n * 4);
   u32 *cnt = (u32 *)arena_take(ctx, 256);  // [0]=pit counter [1]=changed [2]=n_active [3]=n_merged [4]=edges
@@ -920,7 +920,7 @@ __global__ void k_level_final(const float *__restrict__ level0, const u32 *__res
 int64_t band_fill_edge_cap(int64_t nx) { return 5 * nx + 16; }
 
 int band_fill_local(hc_ctx *ctx, const float *z, int64_t nb, int64_t nx, float nodata, int seed_mode, int flags,
-                    int64_t band_index, uint32_t *edges_out, cudaStream_t st) {
+                    int64_t band_index, uint32_t *edges_out, cudaStream_t st, const uint8_t *ext) {
   hc_band_state *bs = &ctx->band;
   hc_rows rw = {(flags & 1) ? -1 : 0, (int)nb + ((flags & 2) ? 1 : 0), flags & 1, (flags >> 1) & 1};
   const int64_t cap = band_fill_edge_cap(nx);
@@ -928,10 +928,10 @@ int band_fill_local(hc_ctx *ctx, const float *z, int64_t nb, int64_t nx, float n
   if ((double)(band_index + 2) * 2.0 * (double)nx >= 4294967000.0) { hc_set_error("too many seam cells"); return HC_ERR_TOO_LARGE; }
   if (!(flags & 3)) {
     // a single band: no terminals at all, nothing to publish
-    HC_TRY(fill_local(ctx, z, nb, nx, nodata, seed_mode, rw, &fs, st));
+    HC_TRY(fill_local(ctx, z, nb, nx, nodata, seed_mode, rw, &fs, st, ext));
     HC_CUDA(cudaMemsetAsync(edges_out, 0, (size_t)cap * 12, st));
   } else {
-    HC_TRY(fill_local(ctx, z, nb, nx, nodata, seed_mode, rw, &fs, st));
+    HC_TRY(fill_local(ctx, z, nb, nx, nodata, seed_mode, rw, &fs, st, ext));
     HC_CUDA(cudaMemsetAsync(edges_out, 0, (size_t)cap * 12, st));
     const int tx = (int)((nx + T - 1) / T), ty = (int)((nb + T - 1) / T);
     dim3 tg(tx, ty);

@@ -444,3 +444,19 @@ extern "C" int hc_band_label_finish_dev(hc_ctx *ctx, int64_t offset, const uint3
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
+
+// out[i] = flag[lab[i]] (flag[0] must be 0: background): the exterior-nodata raster from banded labels
+__global__ void k_gather_flag(const int32_t *__restrict__ lab, const uint8_t *__restrict__ flag, uint8_t *__restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = flag[lab[i]];
+}
+extern "C" int hc_gather_flag_dev(hc_ctx *ctx, const int32_t *lab, const uint8_t *flag, uint8_t *out, int64_t n, void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (n <= 0) return HC_OK;
+  if (!lab || !flag || !out) { hc_set_error("hc_gather_flag: null pointer"); return HC_ERR_ARG; }
+  k_gather_flag<<<ctx->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(lab, flag, out, (size_t)n);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}

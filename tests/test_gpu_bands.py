@@ -62,14 +62,17 @@ def test_banded_c2_recipe(oracle, cuda):
     assert np.array_equal(ga, a)
 
 
-def test_banded_rejects_wbt_seed(cuda):
-    import torch
-    from pydrodem_b200 import bands, _lib
-    z = torch.zeros((20, 20), device=cuda)
-    ch = bands.BandedChain([10, 10], 20, 2, 0, cuda, seed_mode=0)
-    with pytest.raises(_lib.HydrocoreError):
-        ch.run([z[:10], z[10:]])
-    ch.close()
+@pytest.mark.parametrize("case", [CASES[3], CASES[5], CASES[7], CASES[9]], ids=lambda c: f"{c[0]}x{c[1]}-{c[2]}-b{c[6]}")
+def test_banded_wbt_seed_rule(case, oracle, cuda):
+    """WhiteboxTools' seed rule on bands: interior nodata holes are walls, only nodata connected to the raster frame
+    seeds; the exterior-nodata raster comes from the banded labelling of the nodata mask."""
+    from pydrodem_b200 import bands
+    z = _dem(case)
+    z[0, :5] = -9999.0          # exterior nodata touching the frame, next to an interior hole in some cases
+    f, d, s, a = oracle.fill_d8_accum(z, dx=30.0, dy=20.0, seed_mode=0, table=0)
+    gf, gd, gs, ga = bands.fill_d8_accum_banded(z, case[6], dx=30.0, dy=20.0, table=0, seed_mode=0)
+    assert np.array_equal(gf, f), f"fill: {(gf != f).sum()} cells differ"
+    assert np.array_equal(gd, d) and np.array_equal(gs, s) and np.array_equal(ga, a)
 
 
 def test_bands_over_nccl_two_ranks(cuda):
