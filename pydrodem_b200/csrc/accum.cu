@@ -65,6 +65,7 @@ __device__ __forceinline__ void k_to_drdc(int k, int &dr, int &dc) {
 #define W_PEND_ONE (1u << 13)
 #define W_PEND(w) (((w) >> 13) & 15u)
 #define W_CNT(w) ((w) >> 17)
+#define ACC_HOPS 8
 
 // Phase A: per tile, local counts by a dependency walk in shared memory.  One 32-bit shared atomic
 // per hop: it credits the count, retires a dependency, and its return value carries the target's
@@ -127,9 +128,16 @@ k_acc_tile_local(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsi
   __syncthreads();
   // one merged loop: a lane whose chain ended fetches its next source in the same iteration the other
   // lanes hop, so a warp iterates max over lanes of (sum of its chains), not sum over sources of the
-  // longest chain among the lanes
+  // longest chain among the lanes.  A chain that runs longer than ACC_HOPS hops (a stream: one lane would
+  // keep its whole warp issuing for it) is parked as a continuation (count, next cell) and finished in a
+  // second phase where the parked chains of the whole tile share one or two warps.
+  __shared__ u32 s_nq;
+  __shared__ u32 sq[T * T / ACC_HOPS];
+  if (tid == 0) s_nq = 0;
+  __syncthreads();
   {
     u32 a = 0, d = W_NONE;
+    int hops = 0;
     for (;;) {
       if (d >= W_EXIT) {
         if (!srcmask) break;
@@ -138,12 +146,29 @@ k_acc_tile_local(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsi
         u32 w = st[tid + j * NTHREADS];
         a = W_CNT(w);
         d = w & W_DN;
+        hops = 0;
       }
       if (d < W_EXIT) {
-        u32 old = atomicAdd(&st[d], (a << 17) - W_PEND_ONE);
-        if (W_PEND(old) != 1u) d = W_NONE;
-        else { a += W_CNT(old); d = old & W_DN; }
+        if (hops == ACC_HOPS) {
+          sq[atomicAdd(&s_nq, 1u)] = (a << 13) | d;   // count < 2^14, cell < 2^13
+          d = W_NONE;
+        } else {
+          u32 old = atomicAdd(&st[d], (a << 17) - W_PEND_ONE);
+          if (W_PEND(old) != 1u) d = W_NONE;
+          else { a += W_CNT(old); d = old & W_DN; hops++; }
+        }
       }
+    }
+  }
+  __syncthreads();
+  for (u32 k = tid; k < s_nq; k += NTHREADS) {
+    u32 e = sq[k];
+    u32 a = e >> 13, d = e & W_DN;
+    while (d < W_EXIT) {
+      u32 old = atomicAdd(&st[d], (a << 17) - W_PEND_ONE);
+      if (W_PEND(old) != 1u) break;
+      a += W_CNT(old);
+      d = old & W_DN;
     }
   }
   __syncthreads();
