@@ -65,7 +65,7 @@ __device__ __forceinline__ void k_to_drdc(int k, int &dr, int &dc) {
 #define W_PEND_ONE (1u << 13)
 #define W_PEND(w) (((w) >> 13) & 15u)
 #define W_CNT(w) ((w) >> 17)
-#define ACC_HOPS 8
+#define ACC_HOPS 4
 
 // Phase A: per tile, local counts by a dependency walk in shared memory.  One 32-bit shared atomic
 // per hop: it credits the count, retires a dependency, and its return value carries the target's

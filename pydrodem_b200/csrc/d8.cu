@@ -59,7 +59,7 @@ k_d8(const float *__restrict__ z, uint8_t *__restrict__ dir, uint8_t *__restrict
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const float zn = w[1 + c_dr[TABLE][k]][1 + c_dc[TABLE][k]];
-        if (zn != zn) { contaminated = true; continue; }
+        contaminated |= zn != zn;   // (a NaN neighbour never wins below: every comparison with NaN is false)
         if (TABLE == HC_TABLE_WBT) {
           if (zn < v) {
             double s = ((double)v - (double)zn) / prm.len[k];
