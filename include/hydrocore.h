@@ -119,6 +119,10 @@ int hc_taudem_fix_dev(hc_ctx *ctx, const float *dem, const uint8_t *flat, float 
  * selection block (:414-471); masks may be NULL; cbreak0/1 = float32(curvebreak * sigma). */
 int hc_conv2d_symm_dev(hc_ctx *ctx, const float *in, const float *kernel_host, int kh, int kw, float *out,
                        int64_t ny, int64_t nx, void *stream);
+/* the four DW smoothers of CreateDTM (models/dem_noise_removal.py:399-402) in one pass over the raster:
+ * kernels_host = the 9x9, 7x7, 5x5, 3x3 float32 kernels back to back (164 floats, host pointer) */
+int hc_conv2d_symm_dw4_dev(hc_ctx *ctx, const float *in, const float *kernels_host, float *out9, float *out7,
+                           float *out5, float *out3, int64_t ny, int64_t nx, void *stream);
 int hc_slope_dev(hc_ctx *ctx, const float *z, int8_t *deg, float *mag, int64_t ny, int64_t nx, double dx,
                  double dy, int d4, void *stream);
 int hc_curvature_d2_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, double dx, double dy,

@@ -101,6 +101,56 @@ k_conv2d_symm_rt(const float *__restrict__ in, float *__restrict__ out, int ny, 
   }
 }
 
+// The four DW smoothers of CreateDTM (9x9, 7x7, 5x5, 3x3 on the SAME raster, models/dem_noise_removal.py:399-402)
+// in one pass: the shared tile (halo 4) is loaded once and each kernel is applied from it with the register-tiled
+// column walk above.  c_kern holds the four kernels back to back (81 + 49 + 25 + 9 floats).
+template <int KH>
+__device__ __forceinline__ void conv_apply_rt(const float *sm, int W, int off, const float *kern, int x, int y0,
+                                              float *__restrict__ out, int r0, int c0, int ny, int nx) {
+  // sm row 0 / col 0 = raster (r0 - 4, c0 - 4); this kernel's window starts `off` = 4 - KH/2 cells in
+  float acc[CT_RPT];
+#pragma unroll
+  for (int j = 0; j < CT_RPT; j++) acc[j] = 0.f;
+  for (int b = 0; b < KH; b++) {
+    float kc[KH], w[CT_RPT + KH - 1];
+#pragma unroll
+    for (int a = 0; a < KH; a++) kc[a] = kern[a * KH + b];
+    const float *col = &sm[(y0 + off) * W + off + x + KH - 1 - b];
+#pragma unroll
+    for (int m = 0; m < CT_RPT + KH - 1; m++) w[m] = col[m * W];
+#pragma unroll
+    for (int a = 0; a < KH; a++)
+#pragma unroll
+      for (int j = 0; j < CT_RPT; j++) acc[j] = fmaf(kc[a], w[j + KH - 1 - a], acc[j]);
+  }
+  const int c = c0 + x;
+  if (c >= nx) return;
+#pragma unroll
+  for (int j = 0; j < CT_RPT; j++) {
+    int r = r0 + y0 + j;
+    if (r < ny) out[(size_t)r * nx + c] = acc[j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_conv2d_symm_dw4(const float *__restrict__ in, float *__restrict__ o9, float *__restrict__ o7, float *__restrict__ o5,
+                  float *__restrict__ o3, int ny, int nx) {
+  extern __shared__ float sm[];
+  const int W = CT_TC + 8, H = CT_TR + 8;
+  const int r0 = blockIdx.y * CT_TR, c0 = blockIdx.x * CT_TC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int lr = warp; lr < H; lr += 8) {
+    const float *row = in + (size_t)symm(r0 + lr - 4, ny) * nx;
+    for (int lc = lane; lc < W; lc += 32) sm[lr * W + lc] = __ldg(row + symm(c0 + lc - 4, nx));
+  }
+  __syncthreads();
+  const int x = threadIdx.x & (CT_TC - 1), y0 = (threadIdx.x / CT_TC) * CT_RPT;
+  conv_apply_rt<9>(sm, W, 0, c_kern, x, y0, o9, r0, c0, ny, nx);
+  conv_apply_rt<7>(sm, W, 1, c_kern + 81, x, y0, o7, r0, c0, ny, nx);
+  conv_apply_rt<5>(sm, W, 2, c_kern + 81 + 49, x, y0, o5, r0, c0, ny, nx);
+  conv_apply_rt<3>(sm, W, 3, c_kern + 81 + 49 + 25, x, y0, o3, r0, c0, ny, nx);
+}
+
 // ---- np.gradient pieces ------------------------------------------------------------------------
 struct grad_prm { float h2x, h2y, hx, hy; double dxy; };  // float32(2dx), float32(2dy), float32(dx), float32(dy); float64 diagonal factor
 
@@ -153,23 +203,46 @@ __device__ __forceinline__ void norm_grad(const float *z, int r, int c, int ny, 
   *nx_ = __fdiv_rn(dx, m);
 }
 
+// Tiled: the first-stage field (normalised gradient, or the plain gradient for the Laplacian form) costs five
+// IEEE divisions / square roots per point; it is evaluated ONCE per point of the tile + 1-cell ring into shared
+// memory and the second differences read it from there (the untiled form re-evaluated it at four neighbours of
+// every cell: 22 such operations per output instead of ~7.5).  Same operations in the same order per value, so
+// the result is bit-identical.
+#define CU_TR 16
+#define CU_TC 64
 __global__ void __launch_bounds__(256)
 k_curv_d2(const float *__restrict__ z, float *__restrict__ out, int ny, int nx, grad_prm p, int geometric) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-  if (c >= nx) return;
-  // first-stage field F_y (for d/dy) and F_x (for d/dx) at a point
-  auto Fy = [&](int rr, int cc) { float a, b; if (geometric) { norm_grad(z, rr, cc, ny, nx, p, &a, &b); return a; } return gy(z, rr, cc, ny, nx, p); };
-  auto Fx = [&](int rr, int cc) { float a, b; if (geometric) { norm_grad(z, rr, cc, ny, nx, p, &a, &b); return b; } return gx(z, rr, cc, ny, nx, p); };
-  float d2y, d2x;
-  if (ny == 1) d2y = 0.f;
-  else if (r == 0) d2y = __fdiv_rn(__fsub_rn(Fy(1, c), Fy(0, c)), p.hy);
-  else if (r == ny - 1) d2y = __fdiv_rn(__fsub_rn(Fy(r, c), Fy(r - 1, c)), p.hy);
-  else d2y = __fdiv_rn(__fsub_rn(Fy(r + 1, c), Fy(r - 1, c)), p.h2y);
-  if (nx == 1) d2x = 0.f;
-  else if (c == 0) d2x = __fdiv_rn(__fsub_rn(Fx(r, 1), Fx(r, 0)), p.hx);
-  else if (c == nx - 1) d2x = __fdiv_rn(__fsub_rn(Fx(r, c), Fx(r, c - 1)), p.hx);
-  else d2x = __fdiv_rn(__fsub_rn(Fx(r, c + 1), Fx(r, c - 1)), p.h2x);
-  out[(size_t)r * nx + c] = __fadd_rn(d2y, d2x);
+  __shared__ float fy[(CU_TR + 2) * (CU_TC + 2)], fx[(CU_TR + 2) * (CU_TC + 2)];
+  const int r0 = blockIdx.y * CU_TR, c0 = blockIdx.x * CU_TC;
+  const int W = CU_TC + 2;
+  for (int i = threadIdx.x; i < (CU_TR + 2) * W; i += 256) {
+    int lr = i / W, lc = i - lr * W;
+    int rr = r0 + lr - 1, cc = c0 + lc - 1;
+    float a = 0.f, b = 0.f;
+    if (rr >= 0 && rr < ny && cc >= 0 && cc < nx) {
+      if (geometric) norm_grad(z, rr, cc, ny, nx, p, &a, &b);
+      else { a = gy(z, rr, cc, ny, nx, p); b = gx(z, rr, cc, ny, nx, p); }
+    }
+    fy[i] = a;
+    fx[i] = b;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CU_TR * CU_TC; i += 256) {
+    int lr = i / CU_TC, lc = i - lr * CU_TC;
+    int r = r0 + lr, c = c0 + lc;
+    if (r >= ny || c >= nx) continue;
+    const int ci = (lr + 1) * W + lc + 1;
+    float d2y, d2x;
+    if (ny == 1) d2y = 0.f;
+    else if (r == 0) d2y = __fdiv_rn(__fsub_rn(fy[ci + W], fy[ci]), p.hy);
+    else if (r == ny - 1) d2y = __fdiv_rn(__fsub_rn(fy[ci], fy[ci - W]), p.hy);
+    else d2y = __fdiv_rn(__fsub_rn(fy[ci + W], fy[ci - W]), p.h2y);
+    if (nx == 1) d2x = 0.f;
+    else if (c == 0) d2x = __fdiv_rn(__fsub_rn(fx[ci + 1], fx[ci]), p.hx);
+    else if (c == nx - 1) d2x = __fdiv_rn(__fsub_rn(fx[ci], fx[ci - 1]), p.hx);
+    else d2x = __fdiv_rn(__fsub_rn(fx[ci + 1], fx[ci - 1]), p.h2x);
+    out[(size_t)r * nx + c] = __fadd_rn(d2y, d2x);
+  }
 }
 
 // ---- global mean / population std (float64 accumulation) ----------------------------------------
@@ -270,6 +343,22 @@ extern "C" int hc_conv2d_symm_dev(hc_ctx *ctx, const float *in, const float *ker
   return HC_OK;
 }
 
+// kernels_host: 81 + 49 + 25 + 9 float32 (the 9x9, 7x7, 5x5 and 3x3 kernels back to back, HOST pointer)
+extern "C" int hc_conv2d_symm_dw4_dev(hc_ctx *ctx, const float *in, const float *kernels_host, float *out9, float *out7,
+                                      float *out5, float *out3, int64_t ny, int64_t nx, void *stream) {
+  ST_CTX(ctx);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!in || !kernels_host || !out9 || !out7 || !out5 || !out3) { hc_set_error("hc_conv2d_symm_dw4: null pointer"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_CUDA(cudaMemcpyToSymbolAsync(c_kern, kernels_host, sizeof(float) * (81 + 49 + 25 + 9), 0, cudaMemcpyHostToDevice, st));
+  dim3 grid((unsigned)((nx + CT_TC - 1) / CT_TC), (unsigned)((ny + CT_TR - 1) / CT_TR));
+  size_t smem = sizeof(float) * (CT_TC + 8) * (CT_TR + 8);
+  HC_PROF(ctx, st, "k_conv2d_symm_dw4");
+  k_conv2d_symm_dw4<<<grid, 256, smem, st>>>(in, out9, out7, out5, out3, (int)ny, (int)nx);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
 extern "C" int hc_slope_dev(hc_ctx *ctx, const float *z, int8_t *deg, float *mag, int64_t ny, int64_t nx, double dx,
                             double dy, int d4, void *stream) {
   ST_CTX(ctx);
@@ -288,9 +377,9 @@ extern "C" int hc_curvature_d2_dev(hc_ctx *ctx, const float *z, float *out, int6
                                    int geometric, void *stream) {
   ST_CTX(ctx);
   if (ny <= 0 || nx <= 0) return HC_OK;
-  if (!z || !out || ny > 65535) { hc_set_error("hc_curvature_d2: bad argument"); return HC_ERR_ARG; }
+  if (!z || !out || ny > 65535 * CU_TR) { hc_set_error("hc_curvature_d2: bad argument"); return HC_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((nx + 255) / 256), (unsigned)ny);
+  dim3 grid((unsigned)((nx + CU_TC - 1) / CU_TC), (unsigned)((ny + CU_TR - 1) / CU_TR));
   HC_PROF(ctx, st, "k_curv_d2");
   k_curv_d2<<<grid, 256, 0, st>>>(z, out, (int)ny, (int)nx, make_grad(dx, dy), geometric ? 1 : 0);
   HC_LAUNCH_CHECK(ctx);

@@ -58,6 +58,24 @@ def apply_convolve_filter(array, kernel, normalize_kernel=False, boundary='symm'
     return out
 
 
+def dw_smooth4(array, kernels):
+    """The four smoothings of CreateDTM.run_tile (:399-402) in one pass: `kernels` = the 9x9, 7x7, 5x5 and 3x3 kernels
+    (as build_kernel returns them).  Returns [z9, z7, z5, z3]; same arithmetic as four apply_convolve_filter calls."""
+    import torch
+    if [k.shape for k in kernels] != [(9, 9), (7, 7), (5, 5), (3, 3)]:
+        return [apply_convolve_filter(array, k) for k in kernels]
+    a, host = _to_dev(array if _is_torch(array) else np.asarray(array).astype(np.float32), np.float32)
+    a = _tdev(a, torch.float32, "dw_smooth4")
+    k32 = np.ascontiguousarray(np.concatenate([np.asarray(k, dtype=np.float64).astype(np.float32).ravel() for k in kernels]))
+    outs = [torch.empty_like(a) for _ in range(4)]
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().hc_conv2d_symm_dw4_dev(_lib.context(a.device.index or 0), _tp(a),
+                                                      ctypes.c_void_p(k32.ctypes.data), *[_tp(o) for o in outs], a.shape[0],
+                                                      a.shape[1], _stream(a)), "hc_conv2d_symm_dw4_dev")
+        torch.cuda.current_stream(a.device).synchronize()  # k32 is host memory read by the async copy
+    return [o.cpu().numpy() for o in outs] if host else outs
+
+
 def _slope(array, dx, dy, d4, unit):
     import torch
     a, host = _to_dev(array, np.float32)
@@ -141,7 +159,7 @@ def smooth_core(dem, dx, dy, gdir=4, fweights=None, slopebreaks=(0, 2, 6, 15, 30
     host = not _is_torch(dem)
     d = _to_dev(dem, np.float32)[0]
     fweights = fweights or [DW_WEIGHTS[9], DW_WEIGHTS[7], DW_WEIGHTS[5], DW_WEIGHTS[3]]
-    zs = [apply_convolve_filter(d, build_kernel(w, dtype=np.float32, normalize=True)) for w in fweights]
+    zs = dw_smooth4(d, [build_kernel(w, dtype=np.float32, normalize=True) for w in fweights])
     s0ind = 2  # 0=9x9, 1=7x7, 2=5x5, 3=3x3: the 5x5 result drives slope/curvature (:147, :405-410)
     slope0 = (slope_D4 if gdir == 4 else slope_D2)(zs[s0ind], dx, dy)
     curv = curvature_D2(zs[s0ind], dx, dy)
@@ -186,7 +204,7 @@ class BandSmoother:
     def stage1(self):
         d = self.d
         ws = [DW_WEIGHTS[9], DW_WEIGHTS[7], DW_WEIGHTS[5], DW_WEIGHTS[3]]
-        self.zs = [apply_convolve_filter(d, build_kernel(w, dtype=np.float32, normalize=True)) for w in ws]
+        self.zs = dw_smooth4(d, [build_kernel(w, dtype=np.float32, normalize=True) for w in ws])
         sl = slope_D4 if self.gdir == 4 else slope_D2
         self.slope0 = sl(self.zs[2], self.dx, self.dy)
         self.curv = curvature_D2(self.zs[2], self.dx, self.dy)
