@@ -23,6 +23,8 @@
 //         relaxation against global distance arrays with re-queueing of tiles whose halo changed
 //         (k_flat_init / k_flat_relax / k_flat_dirs), run only on the tiles that hold pending
 //         cells and their neighbours.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define T HC_TILE
@@ -236,10 +238,13 @@ __global__ void k_flat_dilate(const uint8_t *__restrict__ pending, uint8_t *__re
 __global__ void __launch_bounds__(NTHREADS)
 k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const uint8_t *__restrict__ dirB,
             uint8_t *__restrict__ nf, u32 *__restrict__ dlo, u32 *__restrict__ dhi,
-            const uint8_t *__restrict__ active, int ny, int nx, float nodata, hc_rows rw) {
+            const uint8_t *__restrict__ active, const uint8_t *__restrict__ pending, uint8_t *__restrict__ startq,
+            int ny, int nx, float nodata, hc_rows rw, int start_all, unsigned long long *dbgp) {
   __shared__ float sz[TH * TH];
   __shared__ uint8_t sd[TH * TH];
-  if (!active[blockIdx.y * gridDim.x + blockIdx.x]) return;
+  __shared__ uint8_t sp[TH * TH];   // dirB: the fast tier's PENDING marks, looked at on the halo ring only
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  if (!active[tile]) { if (threadIdx.x == 0) startq[tile] = 0; return; }
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
@@ -247,17 +252,24 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
     int lr = i / TH, lc = i - lr * TH;
     int r = r0 + lr - 1, c = c0 + lc - 1;
     float v = qnan;
-    uint8_t d = HC_DIR_NODATA;
+    uint8_t d = HC_DIR_NODATA, pb = 0;
     if (r >= rw.rlo && r < rw.rhi && c >= 0 && c < nx) {
       long long g = (long long)r * nx + c;
       v = __ldg(z + g);
       if (v == nodata) v = qnan;
       d = __ldg(dir + g);
+      pb = __ldcg(dirB + g);
     }
     sz[i] = v;
     sd[i] = d;
+    sp[i] = pb;
   }
   __syncthreads();
+  // Does this tile have to be relaxed before anyone asks for it?  Yes if it holds pending cells itself, or if one
+  // of its NOFLOW cells touches a PENDING cell of the same elevation in a neighbouring tile (it then holds part of
+  // a flat that is open over there, possibly with that flat's only sources).  Every other active tile just keeps
+  // its initial values until a neighbour's rim shows it something better.
+  int touch = 0;
   for (int i = tid; i < T * T; i += NTHREADS) {
     int lr = i / T, lc = i - lr * T;
     int r = r0 + lr, c = c0 + lc;
@@ -268,6 +280,17 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
     u32 lo = 0, hi = 0;
     if (v == v) {
       isnf = sd[ci] == HC_DIR_NOFLOW;
+      if (isnf && (lr == 0 || lc == 0 || lr == T - 1 || lc == T - 1 || r == ny - 1 || c == nx - 1)) {
+#pragma unroll
+        for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+          for (int dc = -1; dc <= 1; dc++) {
+            const int hr = lr + 1 + dr, hc = lc + 1 + dc;
+            if (hr >= 1 && hr <= T && hc >= 1 && hc <= T) continue;   // own cell
+            const int ni = hr * TH + hc;
+            if (sz[ni] == v && sp[ni] == HC_DIR_PENDING) touch = 1;
+          }
+      }
 #pragma unroll
       for (int dr = -1; dr <= 1; dr++)
 #pragma unroll
@@ -286,6 +309,12 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
     nf[g] = isnf;
     dlo[g] = lo;
     dhi[g] = hi;
+  }
+  touch = __syncthreads_or(touch);
+  if (tid == 0) {
+    // a band cannot see the neighbouring band's pending marks: its seam tile rows always start
+    const bool seam = (rw.top && blockIdx.y == 0) || (rw.bot && blockIdx.y == gridDim.y - 1);
+    startq[tile] = (uint8_t)((pending[tile] || touch || seam || start_all) ? 1 : 0);
   }
 }
 
@@ -328,9 +357,9 @@ __device__ __forceinline__ int slow_relax(const float *sz, u32 *slo, u32 *shi, i
 // one visit of tile (by, bx): load, relax to the local fixed point, write back, queue the neighbours that can improve
 __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
                                            const uint8_t *__restrict__ active, u32 *__restrict__ list_out,
-                                           u32 *__restrict__ n_out, u32 *__restrict__ queued, int ny, int nx,
-                                           float nodata, unsigned long long *dbg, hc_rows rw, int by, int bx, int tx, int ty,
-                                           unsigned char *smem) {
+                                           u32 *__restrict__ n_out, u32 *__restrict__ queued, uint8_t *__restrict__ visited,
+                                           int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw, int by, int bx,
+                                           int tx, int ty, unsigned char *smem) {
   float *sz = (float *)smem;
   u32 *slo = (u32 *)(smem + TH * TP * 4);
   u32 *shi = (u32 *)(smem + TH * TP * 8);
@@ -340,14 +369,20 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
   const int r0 = by * T, c0 = bx * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
-  __shared__ uint8_t s_act[9];
+  __shared__ uint8_t s_act[9], s_vis[9];
   __syncthreads();  // the previous tile of this CTA is completely done with the shared arrays
   if (tid == 0) { s_side = 0; s_n = 0; }
   if (tid < 9) {
     int yy = by + tid / 3 - 1, xx = bx + tid % 3 - 1;
-    s_act[tid] = (yy >= 0 && yy < ty && xx >= 0 && xx < tx) ? active[yy * tx + xx] : 0;
+    bool in = yy >= 0 && yy < ty && xx >= 0 && xx < tx;
+    s_act[tid] = in ? active[yy * tx + xx] : 0;
+    s_vis[tid] = in ? visited[yy * tx + xx] : 1;
   }
   __syncthreads();
+  // first visit of this tile: it must wake the not-yet-visited neighbours that hold more of its flats (they may
+  // own the flat's only sources, and nothing else would ever ask for them)
+  const bool first = s_vis[4] == 0;
+  if (tid == 0) visited[by * tx + bx] = 1;
 #pragma unroll 4
   for (int i0 = 0; i0 < TH * TH; i0 += NTHREADS) {
     const int i = i0 + tid;
@@ -415,7 +450,7 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
     }
   }
   if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); if (nlist * 4 > T * T) HC_DBG(5, 1); }
-  if (!ever) return;
+  if (!ever && !first) return;
   // write back; a neighbouring tile is re-queued only if one of ITS rim cells (my halo) can actually improve
   // from a rim cell of mine that changed (distances only ever decrease, so a stale halo value can cause a
   // spurious visit but never a missed one).  Without this test a tile is revisited every time the front
@@ -427,12 +462,16 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
     if (r >= ny || c >= nx) continue;
     int ci = (lr + 1) * TP + lc + 1;
     u32 w = slo[ci];
-    if (!(w & R_CHG)) continue;
+    if (!(w & R_NF)) continue;
+    const bool chg = (w & R_CHG) != 0;
+    if (!chg && !first) continue;
     size_t g = (size_t)r * nx + c;
     u32 lo = w & R_VAL, hi = shi[ci];
     {
-      dlo[g] = lo;
-      dhi[g] = hi;
+      if (chg) {
+        dlo[g] = lo;
+        dhi[g] = hi;
+      }
       if (lr == 0 || lc == 0 || lr == T - 1 || lc == T - 1) {
         const float v = sz[ci];
 #pragma unroll
@@ -446,8 +485,9 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
             const u32 nw = slo[ni];
             if (!(nw & R_NF)) continue;
             const u32 nlo = nw & R_VAL, nhi = shi[ni];
-            if ((lo && (nlo == 0 || lo + 1 < nlo)) || (hi && (nhi == 0 || hi + 1 < nhi)))
-              nb9 |= 1 << ((hr == 0 ? 0 : (hr == TH - 1 ? 2 : 1)) * 3 + (hc == 0 ? 0 : (hc == TH - 1 ? 2 : 1)));
+            const int nb = (hr == 0 ? 0 : (hr == TH - 1 ? 2 : 1)) * 3 + (hc == 0 ? 0 : (hc == TH - 1 ? 2 : 1));
+            if ((chg && ((lo && (nlo == 0 || lo + 1 < nlo)) || (hi && (nhi == 0 || hi + 1 < nhi)))) || (first && !s_vis[nb]))
+              nb9 |= 1 << nb;
           }
       }
     }
@@ -471,7 +511,7 @@ __global__ void __launch_bounds__(NTHREADS)
 k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
              const uint8_t *__restrict__ active, const u32 *__restrict__ list_in, const u32 *__restrict__ n_in,
              u32 *__restrict__ list_out, u32 *__restrict__ n_out, u32 *__restrict__ queued, u32 *__restrict__ next,
-             int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw, int tx, int ty) {
+             uint8_t *__restrict__ visited, int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw, int tx, int ty) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ u32 s_q;
   const u32 n = *n_in;
@@ -483,7 +523,7 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
     const u32 q = s_q;
     if (q >= n) break;
     const u32 t = list_in[q];
-    relax_tile(z, nf, dlo, dhi, active, list_out, n_out, queued, ny, nx, nodata, dbg, rw, (int)(t / tx), (int)(t % tx), tx, ty, smem);
+    relax_tile(z, nf, dlo, dhi, active, list_out, n_out, queued, visited, ny, nx, nodata, dbg, rw, (int)(t / tx), (int)(t % tx), tx, ty, smem);
   }
 }
 
@@ -609,12 +649,17 @@ static int flats_slow_init(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   bs->nf = nf + nx; bs->dlo = dlo + nx; bs->dhi = dhi + nx;
   dim3 tg(tx, ty);
   HC_PROF(ctx, st, "k_flat_init");
-  k_flat_init<<<tg, NTHREADS, 0, st>>>(bs->fz, bs->dirA, bs->dirB, bs->nf, bs->dlo, bs->dhi, bs->active, (int)ny, (int)nx, bs->nodata, rw);
+  uint8_t *startq = (uint8_t *)arena_take(ctx, tiles);
+  bs->visited = (uint8_t *)arena_take(ctx, tiles);   // per-tile "visited" map of the slow tier
+  if (!startq || !bs->visited) return HC_ERR_NOMEM;
+  HC_CUDA(cudaMemsetAsync(bs->visited, 0, tiles, st));
+  k_flat_init<<<tg, NTHREADS, 0, st>>>(bs->fz, bs->dirA, bs->dirB, bs->nf, bs->dlo, bs->dhi, bs->active, bs->pending, startq,
+                                       (int)ny, (int)nx, bs->nodata, rw, getenv("HC_FLAT_START_ALL") ? 1 : 0, ctx->d_dbg);
   HC_LAUNCH_CHECK(ctx);
   // first relaxation visits every active tile: queue A
   HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
   HC_PROF(ctx, st, "k_flat_queue_tiles");
-  k_flat_queue_tiles<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(bs->active, 0u, (u32)tiles, bs->queued, bs->qA, bs->flag + 8);
+  k_flat_queue_tiles<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(startq, 0u, (u32)tiles, bs->queued, bs->qA, bs->flag + 8);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
@@ -633,7 +678,7 @@ static int flats_relax_loop(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
     HC_CUDA(cudaMemsetAsync(bs->flag + 9, 0, 8, st));   // n(qB) and the fetch counter [10]
     HC_PROF(ctx, st, "k_flat_relax");
     k_flat_relax<<<grid, NTHREADS, FLAT_SMEM, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->active, bs->qA, bs->flag + 8, bs->qB,
-                                                    bs->flag + 9, bs->queued, bs->flag + 10, (int)ny, (int)nx, bs->nodata,
+                                                    bs->flag + 9, bs->queued, bs->flag + 10, bs->visited, (int)ny, (int)nx, bs->nodata,
                                                     ctx->d_dbg, rw, tx, ty);
     HC_LAUNCH_CHECK(ctx);
     // next round: B becomes A

@@ -13,5 +13,5 @@ hc.fill_d8_accum(z, **kw); torch.cuda.synchronize()
 _lib.debug_read(0)
 f, d, s, a = hc.fill_d8_accum(z, **kw); torch.cuda.synchronize()
 c = _lib.debug_read(0)
-print("fast sweeps", c[0], "fast tiles with work", c[1], "pending tiles", c[2], "slow sweeps", c[3], "slow visits", c[4], "dense visits", c[5], "other", c[6:12])
+print("fast sweeps", c[0], "fast tiles with work", c[1], "pending tiles", c[2], "slow sweeps", c[3], "slow visits", c[4], "dense visits", c[5], "other", c[6:16])
 print("noflow cells after fill d8:", int((d == 0).sum()))

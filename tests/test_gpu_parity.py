@@ -126,3 +126,19 @@ def test_c4_flattened_lakes_and_rivers(oracle, cuda):
     assert np.array_equal(gf, f) and np.array_equal(gd, d) and np.array_equal(gs, s) and np.array_equal(ga, a)
     bf, bd, bs, ba = bands.fill_d8_accum_banded(z, 3, dx=30.0, dy=30.0, table=1)
     assert np.array_equal(bf, f) and np.array_equal(bd, d) and np.array_equal(ba, a)
+
+
+@pytest.mark.parametrize("seed,levels", [(41, 30), (42, 80), (43, 12)])
+def test_flats_spanning_many_tiles(seed, levels, oracle, cuda):
+    """Terraced terrain (elevation quantised to a few dozen levels) gives flats that wind across many 64x64 tiles,
+    with their outlets in tiles that hold no pending cell themselves: the slow tier's lazy start (only tiles that
+    hold part of an open flat, woken transitively) must still reach every one of them."""
+    import pydrodem_b200 as hc
+    from pydrodem_b200 import synth
+    z = synth.random_dem(1100, 1300, seed, "smooth", nodata_holes=2, levels=levels)
+    f = oracle.fill(z, seed_mode=1)
+    d0, _ = oracle.d8(f, dx=30.0, dy=30.0, table=1)
+    want = oracle.resolve_flats(f, d0, table=1)
+    got = hc.resolve_flats(f, d0, table=1)
+    assert np.array_equal(got, want), f"{(got != want).sum()} cells differ"
+    assert np.array_equal(hc.accum(got, table=1), oracle.accum(want, table=1))
