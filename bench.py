@@ -248,7 +248,11 @@ def run_banded(args, world, rank, local, dev):
     chain.timing = False
     phases = {k: v / 2 for k, v in chain.phase_ms.items()}
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank = [ms / args.steps]
     if world > 1:
+        allms = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allms, t)
+        per_rank = [float(x.item()) / args.steps for x in allms]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = cells_total * args.steps / (ms_max * 1e-3) / 1e6
@@ -342,7 +346,7 @@ def run_banded(args, world, rank, local, dev):
                                     "all_gather over NCCL",
                    "cells_total": cells_total, "cells_per_gpu": cells_local, "bands": nbands,
                    "l2": "every band's rasters exceed the 126 MB L2; no explicit flush", "flats": bool(args.flats),
-                   "flat_exchange_rounds": flat_rounds, "band_stats_rank0": stats, "phase_ms_rank0": phases,
+                   "flat_exchange_rounds": flat_rounds, "band_stats_rank0": stats, "phase_ms_rank0": phases, "ms_per_step_per_rank": per_rank,
                    "algorithmic_bytes_per_cell": 18, "checks": chk},
         "roofline": roof, "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "hbm_frac_algorithmic_whole_step": 18 * cells_local / (ms_max / args.steps * 1e-3) / 1e9 / peak,
@@ -480,6 +484,15 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        # one rank per GPU, each with its own pair of host cores: every seam exchange waits for the slowest rank, so a
+        # rank that gets descheduled at one of its host read-backs stalls all of them
+        try:
+            ncpu = os.cpu_count() or 1
+            per = max(1, ncpu // world)
+            os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
+        except (AttributeError, OSError):
+            pass
     if world > 1:
         # keep stdout to the one JSON line: NCCL's version banner / debug output goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")

@@ -539,6 +539,11 @@ int band_accum_local(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t nb,
                      uint32_t *seam_out, cudaStream_t st) {
   if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("accum: bad table %d", table); return HC_ERR_ARG; }
   if (nx >= (1 << 30)) { hc_set_error("band too wide"); return HC_ERR_TOO_LARGE; }
+  if (ctx->h_mail[8]) {
+    ctx->h_mail[8] = 0;
+    hc_set_error("band accumulation: the previous direction raster contained a cycle (not a D8 forest)");
+    return HC_ERR_ARG;
+  }
   HC_TRY(arena_reset(ctx));
   hc_band_state *bs = &ctx->band;
   hc_rows rw = hc_make_rows(nb, flags);
@@ -553,9 +558,7 @@ int band_accum_local(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t nb,
   HC_PROF(ctx, st, "k_acc_seam_exit");
   k_acc_seam_exit<<<(unsigned)((2 * nx + 255) / 256), 256, 0, st>>>(bs->pexit, bs->pdown, dir, (int)nb, (int)nx, tx, rw, seam_out, bs->bout, err);
   HC_LAUNCH_CHECK(ctx);
-  HC_CUDA(cudaMemcpyAsync(ctx->h_mail, err, 4, cudaMemcpyDeviceToHost, st));
-  HC_CUDA(cudaStreamSynchronize(st));
-  if (ctx->h_mail[0]) { hc_set_error("band accumulation: the direction raster contains a cycle"); return HC_ERR_ARG; }
+  bs->acc_err = err;   // checked in the finish phase (one read-back there instead of a sync here)
   bs->acc_ready = 1;
   return HC_OK;
 }
@@ -589,6 +592,10 @@ int band_accum_finish(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, in
     k_acc_seam_apply<<<(unsigned)((2 * nx + 255) / 256), 256, 0, st>>>(bs->pexit, bs->pdown, bs->pinflow, bs->dir, (int)nb, (int)nx, tx, rw, state, (long long)band_index * 2 * nx);
     HC_LAUNCH_CHECK(ctx);
   }
-  if (bs->table == HC_TABLE_WBT) return accum_final_impl<HC_TABLE_WBT>(ctx, acc, rw, st);
-  return accum_final_impl<HC_TABLE_TAUDEM>(ctx, acc, rw, st);
+  if (bs->table == HC_TABLE_WBT) HC_TRY(accum_final_impl<HC_TABLE_WBT>(ctx, acc, rw, st));
+  else HC_TRY(accum_final_impl<HC_TABLE_TAUDEM>(ctx, acc, rw, st));
+  // deferred check of the seam walk's cycle guard: the copy is queued behind the kernels, the flag is looked at
+  // at the start of the NEXT banded accumulation on this context (no host synchronisation on the hot path)
+  HC_CUDA(cudaMemcpyAsync(ctx->h_mail + 8, bs->acc_err, 4, cudaMemcpyDeviceToHost, st));
+  return HC_OK;
 }

@@ -151,6 +151,7 @@ extern "C" int hc_create(hc_ctx **out, int device) {
   HC_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
   HC_CUDA(cudaMallocHost(&ctx->h_mail, 256));
+  memset(ctx->h_mail, 0, 256);
   HC_CUDA(cudaMalloc(&ctx->d_dbg, 16 * sizeof(unsigned long long)));
   HC_CUDA(cudaMemset(ctx->d_dbg, 0, 16 * sizeof(unsigned long long)));
   HC_CUDA(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));

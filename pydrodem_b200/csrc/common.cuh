@@ -69,7 +69,7 @@ struct hc_band_state {
   uint8_t *pending, *active, *nf, *visited; u32 *dlo, *dhi, *flag; int n_pending;
   u32 *qA, *qB, *queued;   // dirty-tile queues of the slow tier (current / next) and the per-tile "already queued" marks
   // accumulation
-  int acc_ready; const uint8_t *dir; unsigned long long *pstate; unsigned short *pexit; u32 *pdown, *pinflow, *bout;
+  int acc_ready; const uint8_t *dir; unsigned long long *pstate; unsigned short *pexit; u32 *pdown, *pinflow, *bout, *acc_err;
 };
 
 // banded labelling: state between the phases (pointers into the arena)

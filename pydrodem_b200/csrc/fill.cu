@@ -449,9 +449,9 @@ static int bor_contract(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, u32 *
   HC_PROF(ctx, st, "k_mutual");
   k_mutual<<<tgK, tb, 0, st>>>(t.rep, t.ptr2, t.ptr, K1, nopen);
   HC_LAUNCH_CHECK(ctx);
-  // pointer doubling to the roots: 4 doublings per read-back
+  // pointer doubling to the roots: 8 doublings (paths up to 256 hops) per read-back
   for (int it = 0; it < 16; it++) {
-    for (int j = 0; j < 3; j++) {
+    for (int j = 0; j < 7; j++) {
       HC_PROF(ctx, st, "k_jump");
       k_jump<<<tgK, tb, 0, st>>>(t.ptr, K1, cnt + 5);
       HC_LAUNCH_CHECK(ctx);
@@ -614,7 +614,7 @@ static int bor_list_solve(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, con
   a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
   a.eA = eA; a.eB = eB; a.eW = eW; a.mark = mark; a.ctl = cnt + 16;
   a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = msf; a.idx_keys = 1; a.do_init = 1; a.max_rounds = 64;
-  if (getenv("HC_BOR_NO_ROUNDS")) rounds = nullptr;   // (diagnostic read-back costs a host sync)
+  if (!getenv("HC_BAND_STATS")) rounds = nullptr;   // (the diagnostic read-back costs a host sync per solve)
   return bor_persistent_launch(ctx, a, rounds, st);
 }
 
