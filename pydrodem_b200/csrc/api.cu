@@ -158,6 +158,9 @@ extern "C" int hc_create(hc_ctx **out, int device) {
   HC_CUDA(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fill, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_dir, cudaEventDisableTiming));
+  HC_CUDA(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+  HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   *out = ctx;
   return HC_OK;
 }
@@ -173,6 +176,9 @@ extern "C" int hc_destroy(hc_ctx *ctx) {
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   if (ctx->ev_fill) cudaEventDestroy(ctx->ev_fill);
   if (ctx->ev_dir) cudaEventDestroy(ctx->ev_dir);
+  if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   free(ctx);
   return HC_OK;
 }

@@ -66,7 +66,7 @@ struct hc_band_state {
   int fill_ready; const float *z; u32 *P; float *level0; u32 *troot; u32 K1, nopen; u32 *cnt;
   // flats
   int flats_ready, table; float nodata; const float *fz; const uint8_t *dirA; uint8_t *dirB;
-  uint8_t *pending, *active, *nf, *visited; u32 *dlo, *dhi, *flag; int n_pending;
+  uint8_t *pending, *active, *nf, *visited, *tmask; u32 *dlo, *dhi, *flag, *tcount; unsigned short *tlist; int n_pending;
   u32 *qA, *qB, *queued;   // dirty-tile queues of the slow tier (current / next) and the per-tile "already queued" marks
   // accumulation
   int acc_ready; const uint8_t *dir; unsigned long long *pstate; unsigned short *pexit; u32 *pdown, *pinflow, *bout, *acc_err;
@@ -103,6 +103,9 @@ struct hc_ctx {
   // streams / events of the *_host chain: compute and device->host copies overlap
   cudaStream_t s_compute, s_copy;
   cudaEvent_t ev_fill, ev_dir;
+  // auxiliary stream of the flat pass (light and window relaxation kernels run side by side)
+  cudaStream_t s_aux;
+  cudaEvent_t ev_fork, ev_join;
   unsigned long long *d_dbg;  // 16 device work counters
   // per-kernel event timing (off by default)
   int prof_on, prof_open;

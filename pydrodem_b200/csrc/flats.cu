@@ -31,6 +31,8 @@
 #define TH (T + 2)
 #define NTHREADS 256
 #define HC_DIR_PENDING 254
+#define FL_LCAP 256   // NOFLOW cells a tile may hold to take the light relaxation path
+#define FL_LT 64      // threads of a light-path CTA
 
 // ================================================================================================
 // fast tier
@@ -239,12 +241,15 @@ __global__ void __launch_bounds__(NTHREADS)
 k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const uint8_t *__restrict__ dirB,
             uint8_t *__restrict__ nf, u32 *__restrict__ dlo, u32 *__restrict__ dhi,
             const uint8_t *__restrict__ active, const uint8_t *__restrict__ pending, uint8_t *__restrict__ startq,
+            unsigned short *__restrict__ tlist, uint8_t *__restrict__ tmask, u32 *__restrict__ tcount,
             int ny, int nx, float nodata, hc_rows rw, int start_all, unsigned long long *dbgp) {
+  __shared__ u32 s_cnt;
   __shared__ float sz[TH * TH];
   __shared__ uint8_t sd[TH * TH];
   __shared__ uint8_t sp[TH * TH];   // dirB: the fast tier's PENDING marks, looked at on the halo ring only
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (!active[tile]) { if (threadIdx.x == 0) startq[tile] = 0; return; }
+  if (!active[tile]) { if (threadIdx.x == 0) { startq[tile] = 0; tcount[tile] = 0; } return; }
+  if (threadIdx.x == 0) s_cnt = 0;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
@@ -309,12 +314,32 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
     nf[g] = isnf;
     dlo[g] = lo;
     dhi[g] = hi;
+    if (isnf) {
+      // compact list for the light relaxation path: local index + mask of the equal-elevation neighbours
+      // (bit k = k-th neighbour of the 3x3 window in row-major order, centre skipped)
+      u32 m = 0;
+      int k = 0;
+#pragma unroll
+      for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+        for (int dc = -1; dc <= 1; dc++) {
+          if (!dr && !dc) continue;
+          if (sz[ci + dr * TH + dc] == v) m |= 1u << k;
+          k++;
+        }
+      u32 pos = atomicAdd(&s_cnt, 1u);
+      if (pos < FL_LCAP) {
+        tlist[(size_t)tile * FL_LCAP + pos] = (unsigned short)(lr * T + lc);
+        tmask[(size_t)tile * FL_LCAP + pos] = (uint8_t)m;
+      }
+    }
   }
   touch = __syncthreads_or(touch);
   if (tid == 0) {
     // a band cannot see the neighbouring band's pending marks: its seam tile rows always start
     const bool seam = (rw.top && blockIdx.y == 0) || (rw.bot && blockIdx.y == gridDim.y - 1);
     startq[tile] = (uint8_t)((pending[tile] || touch || seam || start_all) ? 1 : 0);
+    tcount[tile] = s_cnt;
   }
 }
 
@@ -505,13 +530,118 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
   }
 }
 
+// Light path for tiles with at most FL_LCAP NOFLOW cells (most visits): no shared-memory window at all.  The
+// tile's compact cell list and neighbour masks were built at init; a 64-thread CTA relaxes those cells straight on
+// the L2-resident distance rasters (Jacobi sweeps with block votes), so a visit touches a few KB instead of staging
+// 57 KB, and 16+ CTAs per SM hide the L2 latency.  Same re-queue / wake rules as the window path.
+__global__ void __launch_bounds__(FL_LT)
+k_flat_relax_light(const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi, const uint8_t *__restrict__ active,
+                   const unsigned short *__restrict__ tlist, const uint8_t *__restrict__ tmask, const u32 *__restrict__ tcount,
+                   const u32 *__restrict__ list_in, const u32 *__restrict__ n_in, u32 *__restrict__ list_out,
+                   u32 *__restrict__ n_out, u32 *__restrict__ queued, u32 *__restrict__ next, uint8_t *visited, int ny, int nx,
+                   int tx, int ty, unsigned long long *dbg) {
+  __shared__ u32 s_q;
+  const int tid = threadIdx.x;
+  const u32 n = *n_in;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_q = atomicAdd(next, 1u);
+    __syncthreads();
+    const u32 q = s_q;
+    if (q >= n) break;
+    const u32 t = list_in[q];
+    const u32 cnt = tcount[t];
+    if (cnt > FL_LCAP || cnt == 0) continue;   // the window kernel takes the big ones
+    const int by = (int)(t / tx), bx = (int)(t % tx);
+    const int r0 = by * T, c0 = bx * T;
+    const bool first = visited[t] == 0;
+    long long g[FL_LCAP / FL_LT];
+    u32 lo[FL_LCAP / FL_LT], hi[FL_LCAP / FL_LT], msk[FL_LCAP / FL_LT], li[FL_LCAP / FL_LT];
+    u32 chg = 0;
+#pragma unroll
+    for (int j = 0; j < FL_LCAP / FL_LT; j++) {
+      const u32 k = tid + j * FL_LT;
+      msk[j] = 0; li[j] = 0; g[j] = 0; lo[j] = hi[j] = 0;
+      if (k < cnt) {
+        li[j] = tlist[(size_t)t * FL_LCAP + k];
+        msk[j] = tmask[(size_t)t * FL_LCAP + k] | 0x100u;   // bit 8 = "this slot holds a cell"
+        g[j] = (long long)(r0 + (int)(li[j] >> 6)) * nx + (c0 + (int)(li[j] & 63u));
+        lo[j] = __ldcg(dlo + g[j]);
+        hi[j] = __ldcg(dhi + g[j]);
+      }
+    }
+    int nsweeps = 0;
+    for (;;) {
+      int changed = 0;
+#pragma unroll
+      for (int j = 0; j < FL_LCAP / FL_LT; j++) {
+        if (!(msk[j] & 0x100u)) continue;
+        u32 blo = lo[j] ? lo[j] : 0x7FFFFFFFu, bhi = hi[j] ? hi[j] : 0x7FFFFFFFu;
+        // all neighbour loads are issued before any is used: a visit is a chain of L2 round trips otherwise
+        u32 nlo[8], nhi[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int kk = k + (k >= 4);                               // position in the 3x3 window
+          const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
+          const bool on = (msk[j] >> k) & 1u;
+          nlo[k] = on ? __ldcg(dlo + gn) : 0u;
+          nhi[k] = on ? __ldcg(dhi + gn) : 0u;                       // (dhi of a cell with a direction is 0)
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (nlo[k] && nlo[k] + 1 < blo) blo = nlo[k] + 1;
+          if (nhi[k] && nhi[k] + 1 < bhi) bhi = nhi[k] + 1;
+        }
+        if (blo != 0x7FFFFFFFu && blo != lo[j]) { lo[j] = blo; __stcg(dlo + g[j], blo); chg |= 1u << j; changed = 1; }
+        if (bhi != 0x7FFFFFFFu && bhi != hi[j]) { hi[j] = bhi; __stcg(dhi + g[j], bhi); chg |= 1u << j; changed = 1; }
+      }
+      nsweeps++;
+      if (!__syncthreads_or(changed)) break;
+    }
+    if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); HC_DBG(6, 1); }
+    // re-queue neighbours that can improve from a changed rim cell; on the first visit also wake the unvisited
+    // neighbours that hold more of this tile's flats
+    __threadfence();
+#pragma unroll
+    for (int j = 0; j < FL_LCAP / FL_LT; j++) {
+      if (!(msk[j] & 0x100u)) continue;
+      const bool c = (chg >> j) & 1u;
+      if (!c && !first) continue;
+      const int lr = (int)(li[j] >> 6), lc = (int)(li[j] & 63u);
+      if (lr != 0 && lc != 0 && lr != T - 1 && lc != T - 1) continue;
+      u32 m = msk[j] & 0xFFu;
+      while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        const int kk = k + (k >= 4);
+        const int nr = lr + kk / 3 - 1, nc = lc + kk % 3 - 1;
+        if (nr >= 0 && nr < T && nc >= 0 && nc < T) continue;   // inside this tile
+        const int yy = by + (nr < 0 ? -1 : (nr >= T ? 1 : 0)), xx = bx + (nc < 0 ? -1 : (nc >= T ? 1 : 0));
+        if (yy < 0 || yy >= ty || xx < 0 || xx >= tx) continue;  // a band's halo row: the exchange handles it
+        const u32 tt = (u32)(yy * tx + xx);
+        if (!active[tt]) continue;
+        const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
+        if (!__ldcg(nf + gn)) continue;
+        const u32 nlo = __ldcg(dlo + gn), nhi = __ldcg(dhi + gn);
+        const bool benefit = c && ((lo[j] && (nlo == 0 || lo[j] + 1 < nlo)) || (hi[j] && (nhi == 0 || hi[j] + 1 < nhi)));
+        if (benefit || (first && !visited[tt])) {
+          if (atomicExch(&queued[tt], 1u) == 0u) list_out[atomicAdd(n_out, 1u)] = tt;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) visited[t] = 1;
+  }
+}
+
 // persistent form: the CTAs walk the queue of dirty tiles (a full-grid launch spends most of its time on
 // CTAs that find their tile clean)
 __global__ void __launch_bounds__(NTHREADS)
 k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
              const uint8_t *__restrict__ active, const u32 *__restrict__ list_in, const u32 *__restrict__ n_in,
              u32 *__restrict__ list_out, u32 *__restrict__ n_out, u32 *__restrict__ queued, u32 *__restrict__ next,
-             uint8_t *__restrict__ visited, int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw, int tx, int ty) {
+             uint8_t *__restrict__ visited, const u32 *__restrict__ tcount, int ny, int nx, float nodata,
+             unsigned long long *dbg, hc_rows rw, int tx, int ty) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ u32 s_q;
   const u32 n = *n_in;
@@ -523,6 +653,7 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
     const u32 q = s_q;
     if (q >= n) break;
     const u32 t = list_in[q];
+    if (tcount[t] <= FL_LCAP) continue;   // the light kernel takes the small ones
     relax_tile(z, nf, dlo, dhi, active, list_out, n_out, queued, visited, ny, nx, nodata, dbg, rw, (int)(t / tx), (int)(t % tx), tx, ty, smem);
   }
 }
@@ -651,10 +782,13 @@ static int flats_slow_init(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   HC_PROF(ctx, st, "k_flat_init");
   uint8_t *startq = (uint8_t *)arena_take(ctx, tiles);
   bs->visited = (uint8_t *)arena_take(ctx, tiles);   // per-tile "visited" map of the slow tier
-  if (!startq || !bs->visited) return HC_ERR_NOMEM;
+  bs->tlist = (unsigned short *)arena_take(ctx, tiles * FL_LCAP * 2);
+  bs->tmask = (uint8_t *)arena_take(ctx, tiles * FL_LCAP);
+  bs->tcount = (u32 *)arena_take(ctx, tiles * 4);
+  if (!startq || !bs->visited || !bs->tlist || !bs->tmask || !bs->tcount) return HC_ERR_NOMEM;
   HC_CUDA(cudaMemsetAsync(bs->visited, 0, tiles, st));
   k_flat_init<<<tg, NTHREADS, 0, st>>>(bs->fz, bs->dirA, bs->dirB, bs->nf, bs->dlo, bs->dhi, bs->active, bs->pending, startq,
-                                       (int)ny, (int)nx, bs->nodata, rw, getenv("HC_FLAT_START_ALL") ? 1 : 0, ctx->d_dbg);
+                                       bs->tlist, bs->tmask, bs->tcount, (int)ny, (int)nx, bs->nodata, rw, getenv("HC_FLAT_START_ALL") ? 1 : 0, ctx->d_dbg);
   HC_LAUNCH_CHECK(ctx);
   // first relaxation visits every active tile: queue A
   HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
@@ -671,16 +805,27 @@ static int flats_relax_loop(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t tiles = (size_t)tx * ty;
   const unsigned grid = (unsigned)(tiles < (size_t)ctx->sm_count * 3 ? tiles : (size_t)ctx->sm_count * 3);
+  const unsigned lgrid = (unsigned)(tiles < (size_t)ctx->sm_count * 24 ? tiles : (size_t)ctx->sm_count * 24);
   for (int it = 0;; it++) {
     if (it > 1000000) { hc_set_error("flats: relaxation did not converge"); return HC_ERR_INTERNAL; }
     // queue A holds this round's tiles, queue B collects the next round's
     HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
-    HC_CUDA(cudaMemsetAsync(bs->flag + 9, 0, 8, st));   // n(qB) and the fetch counter [10]
+    HC_CUDA(cudaMemsetAsync(bs->flag + 9, 0, 12, st));   // n(qB) and the two fetch counters [10], [11]
+    // small tiles (<= FL_LCAP NOFLOW cells) on the light path, the rest through the shared-memory window; the two
+    // kernels share the queue and run side by side (the light one on the context's auxiliary stream)
+    HC_CUDA(cudaEventRecord(ctx->ev_fork, st));
+    HC_CUDA(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
+    k_flat_relax_light<<<lgrid, FL_LT, 0, ctx->s_aux>>>(bs->nf, bs->dlo, bs->dhi, bs->active, bs->tlist, bs->tmask, bs->tcount,
+                                                         bs->qA, bs->flag + 8, bs->qB, bs->flag + 9, bs->queued, bs->flag + 11,
+                                                         bs->visited, (int)ny, (int)nx, tx, ty, ctx->d_dbg);
+    ctx->launches++;
+    HC_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_aux));
     HC_PROF(ctx, st, "k_flat_relax");
     k_flat_relax<<<grid, NTHREADS, FLAT_SMEM, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->active, bs->qA, bs->flag + 8, bs->qB,
-                                                    bs->flag + 9, bs->queued, bs->flag + 10, bs->visited, (int)ny, (int)nx, bs->nodata,
-                                                    ctx->d_dbg, rw, tx, ty);
+                                                    bs->flag + 9, bs->queued, bs->flag + 10, bs->visited, bs->tcount, (int)ny,
+                                                    (int)nx, bs->nodata, ctx->d_dbg, rw, tx, ty);
     HC_LAUNCH_CHECK(ctx);
+    HC_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     // next round: B becomes A
     HC_CUDA(cudaMemcpyAsync(bs->flag + 8, bs->flag + 9, 4, cudaMemcpyDeviceToDevice, st));
     HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag + 9, 4, cudaMemcpyDeviceToHost, st));
