@@ -31,8 +31,8 @@
 #define TH (T + 2)
 #define NTHREADS 256
 #define HC_DIR_PENDING 254
-#define FL_LCAP 256   // NOFLOW cells a tile may hold to take the light relaxation path
-#define FL_LT 64      // threads of a light-path CTA
+#define FL_LCAP 1024  // NOFLOW cells a tile may hold to take the light relaxation path
+#define FL_LT 256     // threads of a light-path CTA
 
 // ================================================================================================
 // fast tier
