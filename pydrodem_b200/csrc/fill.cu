@@ -233,9 +233,12 @@ k_flatten(u32 *P, size_t n) {
 // ---------------------------------------------------------------------------------------------
 // EMIT: besides picking the cheapest edge, append every (closed cell, foreign neighbour) pair to a
 // compact edge list; later rounds then run on that list instead of the grid.
-template <bool EMIT>
+// FIRST (round 0): the cross-tile flatten is folded into the load — a pointer that is not yet a tagged basin id
+// aims at a perimeter cell k_perim has resolved, so one more hop gives the id, which is written back for the own
+// cells (later kernels see a flat P) — and rep[] is the identity, so its look-up is skipped.
+template <bool EMIT, bool FIRST>
 __global__ void __launch_bounds__(NTHREADS)
-k_minedge(const float *__restrict__ z, const u32 *__restrict__ P, const u32 *__restrict__ rep,
+k_minedge(const float *__restrict__ z, u32 *P, const u32 *__restrict__ rep,
           u64 *__restrict__ best, int ny, int nx, u32 *__restrict__ eA, u32 *__restrict__ eB,
           float *__restrict__ eW, u32 *__restrict__ ecount, u32 ecap, u32 nopen) {
   __shared__ float sz[TH * TH];
@@ -250,10 +253,15 @@ k_minedge(const float *__restrict__ z, const u32 *__restrict__ P, const u32 *__r
     int r = r0 + lr - 1, c = c0 + lc - 1;
     bool inb = r >= 0 && r < ny && c >= 0 && c < nx;
     size_t g = inb ? (size_t)r * nx + c : 0;
-    u32 id = __ldg(&P[g]) & 0x7FFFFFFFu;
+    u32 p = __ldcg(&P[g]);
     float v = __ldg(&z[g]);
+    if (FIRST && inb && !(p & HC_TAG)) {
+      p = __ldcg(&P[p]);   // tagged: a perimeter cell (a stale read of a cell being flattened right now is still a valid pointer)
+      if (lr >= 1 && lr <= T && lc >= 1 && lc <= T) P[g] = p;
+    }
+    u32 id = p & 0x7FFFFFFFu;
     u32 a = HC_NONE;
-    if (inb && id != HC_LAB_NODATA) a = id ? __ldg(&rep[id]) : 0u;
+    if (inb && id != HC_LAB_NODATA) a = FIRST ? id : (id ? __ldg(&rep[id]) : 0u);
     sz[i] = v;
     sa[i] = a;
   }
@@ -666,9 +674,6 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
   k_perim<<<tg, 256, 0, st>>>(P, (int)ny, (int)nx);
   HC_LAUNCH_CHECK(ctx);
   int gblocks = ctx->sm_count * 8;
-  HC_PROF(ctx, st, "k_flatten");
-  k_flatten<<<gblocks, 256, 0, st>>>(P, n);
-  HC_LAUNCH_CHECK(ctx);
 
   HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt, 4, cudaMemcpyDeviceToHost, st));
   HC_CUDA(cudaStreamSynchronize(st));
@@ -702,6 +707,11 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
 
   u32 active = K, merged = 0;
   int round = 0;
+  if (K == 0) {   // no pit at all: no round will fold the flatten into its load
+    HC_PROF(ctx, st, "k_flatten");
+    k_flatten<<<gblocks, 256, 0, st>>>(P, n);
+    HC_LAUNCH_CHECK(ctx);
+  }
   while (active > 0) {
     if (round > 64) { hc_set_error("fill: Boruvka did not converge"); return HC_ERR_INTERNAL; }
     HC_CUDA(cudaMemsetAsync(t.best, 0xFF, (size_t)K1 * 8, st));
@@ -712,12 +722,13 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
     } else if (round == 1) {
       HC_CUDA(cudaMemsetAsync(cnt + 4, 0, 4, st));
       HC_PROF(ctx, st, "k_minedge_emit");
-      k_minedge<true><<<tg, NTHREADS, 0, st>>>(z, P, t.rep, t.best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen);
+      k_minedge<true, false><<<tg, NTHREADS, 0, st>>>(z, P, t.rep, t.best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen);
       HC_LAUNCH_CHECK(ctx);
       HC_CUDA(cudaMemcpyAsync(ctx->h_mail + 4, cnt + 4, 4, cudaMemcpyDeviceToHost, st));
     } else {
       HC_PROF(ctx, st, "k_minedge");
-      k_minedge<false><<<tg, NTHREADS, 0, st>>>(z, P, t.rep, t.best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen);
+      if (round == 0) k_minedge<false, true><<<tg, NTHREADS, 0, st>>>(z, P, t.rep, t.best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen);
+      else k_minedge<false, false><<<tg, NTHREADS, 0, st>>>(z, P, t.rep, t.best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen);
       HC_LAUNCH_CHECK(ctx);
     }
     HC_PROF(ctx, st, "k_hook");
