@@ -32,6 +32,7 @@
 #define NTHREADS 256
 #define HC_DIR_PENDING 254
 #define FL_LCAP 1024  // NOFLOW cells a tile may hold to take the light relaxation path
+#define FLAT_BATCH 3  // relaxation rounds enqueued per host read-back
 #define FL_LT 256     // threads of a light-path CTA
 
 // ================================================================================================
@@ -808,28 +809,33 @@ static int flats_relax_loop(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   const unsigned lgrid = (unsigned)(tiles < (size_t)ctx->sm_count * 24 ? tiles : (size_t)ctx->sm_count * 24);
   for (int it = 0;; it++) {
     if (it > 1000000) { hc_set_error("flats: relaxation did not converge"); return HC_ERR_INTERNAL; }
-    // queue A holds this round's tiles, queue B collects the next round's
-    HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
-    HC_CUDA(cudaMemsetAsync(bs->flag + 9, 0, 12, st));   // n(qB) and the two fetch counters [10], [11]
-    // small tiles (<= FL_LCAP NOFLOW cells) on the light path, the rest through the shared-memory window; the two
-    // kernels share the queue and run side by side (the light one on the context's auxiliary stream)
-    HC_CUDA(cudaEventRecord(ctx->ev_fork, st));
-    HC_CUDA(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
-    k_flat_relax_light<<<lgrid, FL_LT, 0, ctx->s_aux>>>(bs->nf, bs->dlo, bs->dhi, bs->active, bs->tlist, bs->tmask, bs->tcount,
-                                                         bs->qA, bs->flag + 8, bs->qB, bs->flag + 9, bs->queued, bs->flag + 11,
-                                                         bs->visited, (int)ny, (int)nx, tx, ty, ctx->d_dbg);
-    ctx->launches++;
-    HC_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_aux));
-    HC_PROF(ctx, st, "k_flat_relax");
-    k_flat_relax<<<grid, NTHREADS, FLAT_SMEM, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->active, bs->qA, bs->flag + 8, bs->qB,
-                                                    bs->flag + 9, bs->queued, bs->flag + 10, bs->visited, bs->tcount, (int)ny,
-                                                    (int)nx, bs->nodata, ctx->d_dbg, rw, tx, ty);
-    HC_LAUNCH_CHECK(ctx);
-    HC_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    // next round: B becomes A
-    HC_CUDA(cudaMemcpyAsync(bs->flag + 8, bs->flag + 9, 4, cudaMemcpyDeviceToDevice, st));
-    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag + 9, 4, cudaMemcpyDeviceToHost, st));
-    u32 *t = bs->qA; bs->qA = bs->qB; bs->qB = t;
+    // FLAT_BATCH rounds are enqueued back to back before the host looks at the queue length again (a round on an
+    // empty queue costs a few microseconds; a read-back costs a synchronisation — and, on a multi-GPU run, a point
+    // where one delayed rank stalls all the others)
+    for (int sub = 0; sub < FLAT_BATCH; sub++) {
+      // queue A holds this round's tiles, queue B collects the next round's
+      HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
+      HC_CUDA(cudaMemsetAsync(bs->flag + 9, 0, 12, st));   // n(qB) and the two fetch counters [10], [11]
+      // small tiles (<= FL_LCAP NOFLOW cells) on the light path, the rest through the shared-memory window; the two
+      // kernels share the queue and run side by side (the light one on the context's auxiliary stream)
+      HC_CUDA(cudaEventRecord(ctx->ev_fork, st));
+      HC_CUDA(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
+      k_flat_relax_light<<<lgrid, FL_LT, 0, ctx->s_aux>>>(bs->nf, bs->dlo, bs->dhi, bs->active, bs->tlist, bs->tmask, bs->tcount,
+                                                          bs->qA, bs->flag + 8, bs->qB, bs->flag + 9, bs->queued, bs->flag + 11,
+                                                          bs->visited, (int)ny, (int)nx, tx, ty, ctx->d_dbg);
+      ctx->launches++;
+      HC_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_aux));
+      HC_PROF(ctx, st, "k_flat_relax");
+      k_flat_relax<<<grid, NTHREADS, FLAT_SMEM, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->active, bs->qA, bs->flag + 8, bs->qB,
+                                                      bs->flag + 9, bs->queued, bs->flag + 10, bs->visited, bs->tcount, (int)ny,
+                                                      (int)nx, bs->nodata, ctx->d_dbg, rw, tx, ty);
+      HC_LAUNCH_CHECK(ctx);
+      HC_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+      // next round: B becomes A
+      HC_CUDA(cudaMemcpyAsync(bs->flag + 8, bs->flag + 9, 4, cudaMemcpyDeviceToDevice, st));
+      u32 *t = bs->qA; bs->qA = bs->qB; bs->qB = t;
+    }
+    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag + 8, 4, cudaMemcpyDeviceToHost, st));
     HC_CUDA(cudaStreamSynchronize(st));
     if (!ctx->h_mail[0]) break;
   }
