@@ -496,7 +496,7 @@ static int bor_contract(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, u32 *
 struct bor_pargs {
   u64 *best; u32 *rep, *hp, *ptr, *ptr2; float *lvl;
   const u32 *eA, *eB; const float *eW; uint8_t *mark; u32 *ctl;
-  u32 K1, nopen, ne; int msf, idx_keys, do_init, max_rounds;
+  u32 K1, nopen, ne; int msf, idx_keys, do_init, max_rounds, skip_pick;
 };
 __global__ void __launch_bounds__(512)
 k_bor_persistent(bor_pargs a) {
@@ -506,10 +506,12 @@ k_bor_persistent(bor_pargs a) {
     for (u32 b = tid; b < a.K1; b += nth) { a.rep[b] = b; a.lvl[b] = -INFINITY; a.hp[b] = 0; }
     if (a.mark) for (u32 i = tid; i < a.ne; i += nth) a.mark[i] = 0;
   }
-  if (tid < 8) a.ctl[tid] = 0;
+  if (tid < 9) a.ctl[tid] = 0;
   grid.sync();
   int round = 0;
   for (; round < a.max_rounds; round++) {
+    // (skip_pick: best[] was filled by a grid pass over the raster; this launch only contracts)
+    if (!a.skip_pick) {
     for (u32 b = tid; b < a.K1; b += nth) a.best[b] = ~0ull;
     grid.sync();
     // pick
@@ -527,6 +529,7 @@ k_bor_persistent(bor_pargs a) {
       }
     }
     grid.sync();
+    }
     // hook -> ptr2
     for (u32 b = tid; b < a.K1; b += nth) {
       u32 r = __ldcg(&a.rep[b]);
@@ -588,7 +591,7 @@ k_bor_persistent(bor_pargs a) {
     const u32 active = __ldcg(ctr), merged = __ldcg(ctr + 1);
     if (active == 0 || merged == 0) { round++; break; }
   }
-  if (tid == 0) a.ctl[7] = (u32)round;
+  if (tid == 0) { a.ctl[7] = (u32)round; a.ctl[8] = a.ctl[3 + 2 * ((round - 1) & 1)]; }   // rounds done, closed roots left
 }
 
 // launch helper: as many co-resident 512-thread blocks as the work needs (at most the device holds)
@@ -621,7 +624,7 @@ static int bor_list_solve(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, con
   bor_pargs a;
   a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
   a.eA = eA; a.eB = eB; a.eW = eW; a.mark = mark; a.ctl = cnt + 16;
-  a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = msf; a.idx_keys = 1; a.do_init = 1; a.max_rounds = 64;
+  a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = msf; a.idx_keys = 1; a.do_init = 1; a.max_rounds = 64; a.skip_pick = 0;
   if (!getenv("HC_BAND_STATS")) rounds = nullptr;   // (the diagnostic read-back costs a host sync per solve)
   return bor_persistent_launch(ctx, a, rounds, st);
 }
@@ -731,10 +734,24 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
       else k_minedge<false, false><<<tg, NTHREADS, 0, st>>>(z, P, t.rep, t.best, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen);
       HC_LAUNCH_CHECK(ctx);
     }
-    HC_PROF(ctx, st, "k_hook");
-    k_hook<<<tgK, tb, 0, st>>>(t.rep, t.best, t.ptr2, t.lvl, K1, nopen);
-    HC_LAUNCH_CHECK(ctx);
-    HC_TRY(bor_contract(ctx, t, K1, nopen, cnt, &active, &merged, st));
+    if (!have_list) {
+      // contraction of a grid round in one cooperative launch (hook, mutual pairs, pointer doubling to convergence,
+      // merge): one host read-back per round instead of one per four doublings plus one for the counters
+      bor_pargs a;
+      a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
+      a.eA = nullptr; a.eB = nullptr; a.eW = nullptr; a.mark = nullptr; a.ctl = cnt + 16;
+      a.K1 = K1; a.nopen = nopen; a.ne = 0; a.msf = 0; a.idx_keys = 0; a.do_init = 0; a.max_rounds = 1; a.skip_pick = 1;
+      HC_TRY(bor_persistent_launch(ctx, a, nullptr, st));
+      HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 16 + 8, 4, cudaMemcpyDeviceToHost, st));
+      HC_CUDA(cudaStreamSynchronize(st));
+      active = ctx->h_mail[0];
+      merged = 1;
+    } else {
+      HC_PROF(ctx, st, "k_hook");
+      k_hook<<<tgK, tb, 0, st>>>(t.rep, t.best, t.ptr2, t.lvl, K1, nopen);
+      HC_LAUNCH_CHECK(ctx);
+      HC_TRY(bor_contract(ctx, t, K1, nopen, cnt, &active, &merged, st));
+    }
     if (round == 1 && !have_list) {  // the emit round's count arrived with the syncs above
       ne = ctx->h_mail[4];
       have_list = ne <= ecap;
@@ -747,7 +764,7 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
       bor_pargs a;
       a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
       a.eA = eA; a.eB = eB; a.eW = eW; a.mark = nullptr; a.ctl = cnt + 16;
-      a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = 0; a.idx_keys = 0; a.do_init = 0; a.max_rounds = 64;
+      a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = 0; a.idx_keys = 0; a.do_init = 0; a.max_rounds = 64; a.skip_pick = 0;
       int more = 0;
       HC_TRY(bor_persistent_launch(ctx, a, &more, st));
       round += more;
