@@ -42,7 +42,7 @@ KERNEL_PASS = {
     "k_flat_fast": "flats", "k_flat_dilate": "flats", "k_flat_get_seams": "flats", "k_flat_put_halo": "flats",
     "k_acc_tile_local": "accum", "k_acc_tile_final": "accum", "k_acc_link_count": "accum", "k_acc_link_mark": "accum",
     "k_acc_link_walk": "accum", "k_acc_seam_exit": "accum", "k_seam_init": "accum", "k_seam_count": "accum",
-    "k_seam_mark": "accum", "k_seam_walk": "accum", "k_acc_seam_apply": "accum",
+    "k_seam_mark": "accum", "k_seam_walk": "accum", "k_acc_seam_apply": "accum", "k_acc_seam_inject": "accum",
 }
 
 

@@ -507,11 +507,14 @@ __global__ void k_seam_walk(const u32 *__restrict__ all, int nbands, int nx, u64
   }
 }
 
-// add X (inflow from the other band) along an own seam cell's path through the tile-entry slots
+// inject X (inflow from the other band) at an own seam cell: the cell's own entry slot takes it directly, and the
+// exit slot its in-tile path leads to receives it as the "local count" of a second walk over the tile crossings
+// (k_acc_link_count / mark / walk on pstate2), which then spreads it to every entry slot further down — each slot
+// visited once.  (Walking every seam cell's path separately costs seam cells x path length atomics, thousands of them
+// on the same river slots: that was 14 ms on the downstream bands of an 8-band run.)
 __global__ void __launch_bounds__(256)
-k_acc_seam_apply(const unsigned short *__restrict__ pexit, const u32 *__restrict__ pdown, u32 *pinflow,
-                 const uint8_t *__restrict__ dir, int ny, int nx, int tx, hc_rows rw, const u64 *__restrict__ state,
-                 long long gbase) {
+k_acc_seam_inject(const unsigned short *__restrict__ pexit, u32 *pinflow, u64 *pstate2, const uint8_t *__restrict__ dir, int ny,
+                  int nx, int tx, hc_rows rw, const u64 *__restrict__ state, long long gbase) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * nx) return;
   const int side = i / nx, c = i - side * nx;
@@ -522,17 +525,11 @@ k_acc_seam_apply(const unsigned short *__restrict__ pexit, const u32 *__restrict
   if (dir[(size_t)r * nx + c] == HC_DIR_NODATA) return;
   int tyy = r / T, txx = c / T;
   int hr = min(T, ny - tyy * T), hc = min(T, nx - txx * T);
-  u32 t = (u32)(tyy * tx + txx);
+  size_t t = (size_t)(tyy * tx + txx);
   int s = perim_slot(r - tyy * T, c - txx * T, hr, hc);
-  for (;;) {
-    atomicAdd(&pinflow[(size_t)t * PSLOTS + s], X);
-    unsigned short x = pexit[(size_t)t * PSLOTS + s];
-    if (x == NOSLOT) return;
-    u32 d = pdown[(size_t)t * PSLOTS + x];
-    if (d & BAND_EXIT) return;
-    t = d / PSLOTS;
-    s = (int)(d % PSLOTS);
-  }
+  atomicAdd(&pinflow[t * PSLOTS + s], X);
+  unsigned short x = pexit[t * PSLOTS + s];
+  if (x != NOSLOT) atomicAdd(&pstate2[t * PSLOTS + x], (u64)X << 16);
 }
 
 int band_accum_local(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t nb, int64_t nx, int table, int flags,
@@ -587,9 +584,24 @@ int band_accum_finish(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, in
     HC_PROF(ctx, st, "k_seam_walk");
     k_seam_walk<<<gb, 256, 0, st>>>(all_seams, (int)nbands, (int)nx, state);
     HC_LAUNCH_CHECK(ctx);
-    const int tx = (int)((nx + T - 1) / T);
-    HC_PROF(ctx, st, "k_acc_seam_apply");
-    k_acc_seam_apply<<<(unsigned)((2 * nx + 255) / 256), 256, 0, st>>>(bs->pexit, bs->pdown, bs->pinflow, bs->dir, (int)nb, (int)nx, tx, rw, state, (long long)band_index * 2 * nx);
+    const int tx = (int)((nx + T - 1) / T), ty = (int)((nb + T - 1) / T);
+    const size_t nslots = (size_t)tx * ty * PSLOTS;
+    u64 *pstate2 = (u64 *)arena_take(ctx, nslots * 8);
+    u32 *bout2 = (u32 *)arena_take(ctx, (size_t)2 * nx * 4);   // the second walk's band exits are already in X
+    if (!pstate2 || !bout2) return HC_ERR_NOMEM;
+    HC_CUDA(cudaMemsetAsync(pstate2, 0, nslots * 8, st));
+    HC_PROF(ctx, st, "k_acc_seam_inject");
+    k_acc_seam_inject<<<(unsigned)((2 * nx + 255) / 256), 256, 0, st>>>(bs->pexit, bs->pinflow, pstate2, bs->dir, (int)nb, (int)nx, tx, rw, state, (long long)band_index * 2 * nx);
+    HC_LAUNCH_CHECK(ctx);
+    unsigned sb = (unsigned)((nslots + 255) / 256);
+    HC_PROF(ctx, st, "k_acc_link_count");
+    k_acc_link_count<<<sb, 256, 0, st>>>(pstate2, bs->pexit, bs->pdown, nslots);
+    HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_acc_link_mark");
+    k_acc_link_mark<<<sb, 256, 0, st>>>(pstate2, bs->pdown, nslots);
+    HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_acc_link_walk");
+    k_acc_link_walk<<<sb, 256, 0, st>>>(pstate2, bs->pexit, bs->pdown, bs->pinflow, nslots, bout2, (int)nx);
     HC_LAUNCH_CHECK(ctx);
   }
   if (bs->table == HC_TABLE_WBT) HC_TRY(accum_final_impl<HC_TABLE_WBT>(ctx, acc, rw, st));
