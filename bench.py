@@ -76,10 +76,18 @@ class ClockSampler:
         self.p = None
 
     def start(self):
+        if int(os.environ.get("RANK", "0")) != 0:
+            return   # one sampler per job: eight nvidia-smi pollers contend with the ranks for the driver and the cores
         try:
+            # the sampler must not share the rank's pinned cores (a child inherits the affinity mask)
+            def _unpin():
+                try:
+                    os.sched_setaffinity(0, set(range(os.cpu_count() or 1)))
+                except (AttributeError, OSError):
+                    pass
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+                                      stdout=self.f, stderr=subprocess.DEVNULL, preexec_fn=_unpin)
         except OSError:
             self.p = None
 
