@@ -244,9 +244,9 @@ def select_solution(DFpits, fillcells_dct, carvecells_dct, carvecells_only_dct, 
         numpy_scalars = "weak" if int(np.__version__.split(".")[0]) >= 2 else "legacy"
     if numpy_scalars not in ("weak", "legacy"):
         raise ValueError("numpy_scalars must be 'weak' or 'legacy'")
-    torch = _torch()
     if water_mask_array is None:
         raise NameError("name 'water_mask_vec' is not defined")  # the reference's latent bug, kept
+    torch = _torch()
     s = _state_of(fillcells_dct, carvecells_dct, carvecells_only_dct)
     lib = _L.load()
     f32 = torch.float32

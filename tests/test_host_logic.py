@@ -36,3 +36,62 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "Mcells/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_percentile_from_order_stats_is_numpys():
+    """endo.find_sink's threshold: the GPU supplies two exact order statistics, the interpolation reuses numpy's own
+    index / gamma / lerp helpers — so it must equal np.percentile for float32 input, ties and tiny arrays included."""
+    from pydrodem_b200.tools import endo
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 10, 101, 4097, 250_000):
+        x = rng.normal(0, 50, n).astype(np.float32)
+        x[rng.integers(0, n, max(1, n // 7))] = np.float32(1.25)
+        s = np.sort(x)
+        for q in (0, 1, 2.5, 50, 99, 100):
+            got = endo._percentile_from_order_stats(n, q, lambda i: s[i])
+            want = np.percentile(x, q)
+            assert got == want and np.asarray(got).dtype == np.asarray(want).dtype, (n, q)
+
+
+def test_band_helpers_without_a_gpu():
+    from pydrodem_b200 import bands, stencils
+    assert bands.split_rows(40000, 8) == [5000] * 8 and bands.split_rows(7, 3) == [3, 2, 2]
+    # sigma from all-reduced partial sums == the two-pass population std
+    rng = np.random.default_rng(2)
+    x = rng.normal(3.0, 2.0, 100_000)
+    parts = np.array_split(x, 5)
+    n = sum(p.size for p in parts)
+    mean = sum(p.sum() for p in parts) / n
+    d1 = sum((p - mean).sum() for p in parts)
+    d2 = sum(((p - mean) ** 2).sum() for p in parts)
+    assert abs(stencils._sigma_from_sums(n, d1, d2) - np.std(x)) < 1e-12
+
+
+def test_catalog_api_fails_loudly_without_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("only meaningful on a box without a GPU")
+    from pydrodem_b200 import HydrocoreError
+    from pydrodem_b200.tools import depressions as dep
+    z = np.zeros(16, np.float32)
+    ids = np.zeros(16, np.int32)
+    with pytest.raises(HydrocoreError):
+        dep.build_pit_catalog(z, -9999.0, z, z, z, ids, ids, ids, verbose_print=False)
+    with pytest.raises(NameError):        # the reference's own behaviour without a water mask
+        dep.select_solution(None, {}, {}, {}, z, z, ids, ids, 1.0, 1.0, 1.0)
+    with pytest.raises(ValueError):
+        dep.select_solution(None, {}, {}, {}, z, z, ids, ids, 1.0, 1.0, 1.0, water_mask_array=z, numpy_scalars="float16")
+
+
+def test_golden_files_are_present_and_described():
+    g = os.path.join(ROOT, "tests", "golden")
+    for f, gen in (("stencils_reference.npz", "make_stencil_golden.py"), ("catalog_reference.npz", "make_catalog_golden.py"),
+                   ("oracle_hashes.json", "make_golden.py")):
+        assert os.path.exists(os.path.join(g, f)) and os.path.exists(os.path.join(g, gen)), f
+    d = np.load(os.path.join(g, "catalog_reference.npz"))
+    codes = set()
+    for k in d.files:
+        if k.endswith("_solution"):
+            codes |= set(int(v) for v in np.unique(d[k]))
+    assert {1, 7, 1002, 1006, 1200, 2000, 2004, 2006, 2009, 2100, 4000} <= codes
