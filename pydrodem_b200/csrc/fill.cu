@@ -15,13 +15,16 @@
 //                 written, so a pointer leaves the kernel either resolved (tagged basin id) or
 //                 aimed at a cell on another tile's perimeter.
 //   2. k_perim    perimeter cells chase their chain across tiles to a tagged id.
-//   3. k_flatten  every other cell takes its (now resolved) perimeter target's id.
+//   3. (flatten)  every other cell takes its (now resolved) perimeter target's id: folded into the load of
+//                 the first edge pass below (k_flatten only runs when there is no pit at all).
 //   4. Boruvka rounds on the basin graph.  Edge weight between adjacent basins = the lowest pass
 //                 min over adjacent cell pairs of max(z_a, z_b).  Each still-closed basin picks
 //                 its cheapest outgoing edge straight from the grid (k_minedge, one 64-bit
 //                 atomicMin per basin-boundary cell at most), the pointer forest of those picks
 //                 is rooted and compressed on the K-entry tables, trees that reach basin 0 are
-//                 resolved, the others contract into their root.  A basin's final level is the
+//                 resolved, the others contract into their root.  The second round also emits the compact
+//                 list of (closed cell, foreign neighbour) pairs; later rounds run on that list.  Table
+//                 work of a round is one cooperative launch (k_bor_persistent, grid.sync between phases).  A basin's final level is the
 //                 max of the pick weights up its contraction chain (see DESIGN.md for the proof
 //                 that this equals the minimax level).
 //   5. k_apply    out = max(z, level[basin]).

@@ -20,9 +20,13 @@
 //         (on a filled DEM that is nearly all of them: each filled pit is a flat a few cells
 //         wide).  One read of z and dir, one write of dir.
 //   slow  flats that reach the apron's rim are marked pending (code 254) and solved by tile
-//         relaxation against global distance arrays with re-queueing of tiles whose halo changed
-//         (k_flat_init / k_flat_relax / k_flat_dirs), run only on the tiles that hold pending
-//         cells and their neighbours.
+//         relaxation against global distance arrays (k_flat_init / k_flat_relax[_light] / k_flat_dirs)
+//         on the tiles that hold pending cells and their neighbours.  A device queue holds the dirty
+//         tiles of a round; tiles with <= 1024 NOFLOW cells relax straight on the L2-resident rasters
+//         from compact per-tile lists (k_flat_relax_light), lake tiles through a shared-memory window
+//         with whole-line Gauss-Seidel sweeps (k_flat_relax), side by side on two streams.  A tile is
+//         started only if it holds part of an open flat (first visits wake unvisited neighbours that
+//         share flat cells) and re-queued only if one of its rim cells can improve.
 #include <stdlib.h>
 
 #include "common.cuh"

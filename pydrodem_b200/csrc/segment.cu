@@ -31,10 +31,6 @@ __global__ void k_fill_f32(float *p, float v, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
-__global__ void k_fill_i64(long long *p, long long v, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
 
 // per-segment max, min, sum (f64), count of vals over cells whose id is in [lo_id, nseg] and whose
 // optional selector sel[i] != 0
