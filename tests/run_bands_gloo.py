@@ -8,7 +8,8 @@ Each rank holds one band of a small DEM and runs the SAME protocol as pydrodem_b
 hc_band_* kernels — seam terminals, local minimax to the nearest open node, terminal graph reduced to a
 minimum spanning forest, one all_gather of fixed-size edge records through bands.SeamComm, redundant seam
 solve; and for accumulation: parked outflow + exit_of per seam cell, one all_gather, seam forest solve,
-inflow added along each seam cell's path — in plain Python/numpy.  Rank 0 compares with the whole-raster
+inflow added along each seam cell's path — and for labelling: local components,
+min-root propagation across the seam, owner offsets, (root, id) pairs — in plain Python/numpy.  Rank 0 compares with the whole-raster
 CPU oracle.  This pins the algorithm of DESIGN.md §6 and the host plumbing (SeamComm.gather/any,
 exchange_halos) independently of the CUDA code.  Prints BANDS_GLOO_OK.
 """
@@ -292,6 +293,71 @@ def main():
         if not np.array_equal(acc, want_a[r0:r0 + nb]):
             ok = False
             print(f"rank {rank} seed {seed}: banded accumulation model differs at {(acc != want_a[r0:r0+nb]).sum()} cells", flush=True)
+    # ---- labelling: local components, min-root propagation across the seam, owner-offset ranking ----
+    from scipy import ndimage
+    for seed, (ny, nx), p, conn in ((5, (26, 19), 0.55, 8), (6, (31, 24), 0.6, 4), (7, (12, 33), 0.62, 8)):
+        rng = np.random.default_rng(seed)
+        m = (rng.random((ny, nx)) < p)
+        rows = bands.split_rows(ny, world)
+        r0 = sum(rows[:rank])
+        nb = rows[rank]
+        st = np.ones((3, 3), int) if conn == 8 else np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+        loc, nloc = ndimage.label(m[r0:r0 + nb], structure=st)
+        # global root of a local component = global index of its first cell (raster order)
+        first = {}
+        flat = loc.ravel()
+        for i in np.flatnonzero(flat):
+            first.setdefault(int(flat[i]), r0 * nx + int(i))
+        G = dict(first)
+        NONE = 2 ** 31 - 1
+
+        def seams():
+            t = torch.full((1, 2, nx), NONE, dtype=torch.int64)
+            for side, r in ((0, 0), (1, nb - 1)):
+                for c in range(nx):
+                    if loc[r, c]:
+                        t[0, side, c] = G[int(loc[r, c])]
+            return t
+        rounds = 0
+        while True:
+            alls = comm.gather(seams()).numpy()
+            changed = False
+            for side, r, ob in ((0, 0, rank - 1), (1, nb - 1, rank + 1)):
+                if ob < 0 or ob >= world:
+                    continue
+                row = alls[ob, 0 if side else 1]
+                for c in range(nx):
+                    if not loc[r, c]:
+                        continue
+                    cand = [row[cc] for cc in ((c - 1, c, c + 1) if conn == 8 else (c,)) if 0 <= cc < nx]
+                    mn = min(cand)
+                    if mn < G[int(loc[r, c])]:
+                        G[int(loc[r, c])] = int(mn)
+                        changed = True
+            rounds += 1
+            if not comm.any(changed, torch.device("cpu")):
+                break
+        owned = sorted(first[k] for k in first if G[k] == first[k])
+        counts = comm.gather(torch.tensor([[len(owned)]], dtype=torch.int64)).numpy().ravel()
+        offset = int(counts[:rank].sum())
+        myid = {g: offset + i + 1 for i, g in enumerate(owned)}
+        pairs = torch.zeros((1, 2 * nx, 2), dtype=torch.int64)
+        k = 0
+        for side, r in ((0, 0), (1, nb - 1)):
+            for c in range(nx):
+                if loc[r, c] and G[int(loc[r, c])] in myid:
+                    pairs[0, k, 0], pairs[0, k, 1] = G[int(loc[r, c])], myid[G[int(loc[r, c])]]
+                    k += 1
+        allp = comm.gather(pairs).numpy().reshape(-1, 2)
+        lut = {int(a): int(b) for a, b in allp if b > 0}
+        lut.update(myid)
+        out = np.zeros((nb, nx), np.int64)
+        for k_, g in G.items():
+            out[loc == k_] = lut[g]
+        want, nwant = ndimage.label(m, structure=st)
+        if not np.array_equal(out, want[r0:r0 + nb]) or int(counts.sum()) != nwant:
+            ok = False
+            print(f"rank {rank} seed {seed}: banded label model differs (rounds {rounds})", flush=True)
     anybad = comm.any(not ok, torch.device("cpu"))
     assert comm.any(rank == 1, torch.device("cpu")) is True and comm.any(False, torch.device("cpu")) is False
     if rank == 0:
