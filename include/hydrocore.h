@@ -130,6 +130,20 @@ int hc_curvature_d2_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int
 int hc_mean_std_dev(hc_ctx *ctx, const float *x, int64_t n, double *mean, double *std, void *stream);
 /* partial sums of a row band for the global sigma: sums[0] = sum(x - shift), sums[1] = sum((x - shift)^2) (host) */
 int hc_sum_shifted_dev(hc_ctx *ctx, const float *x, int64_t n, double shift, double *sums, void *stream);
+/* Vegetation-bias lookup of CreateDTM.compute_veg_bias_3D (models/dem_noise_removal.py:764-805; the 2-D table of
+ * compute_veg_bias_2D :620-629 is n1 == 1 with i1 NULL).
+ * box3_index: inputs first capped at in_max (:777) and zeroed where in_zero != 0 (nullable; the ocean mask, :687);
+ *   3x3 symmetric-border mean in float64, narrowed to float32, values > zero_above set to 0, astype(int)
+ *   (:766-772, :778-781); `smooth` (nullable) receives the float32 array (self.TC_array).  Pass INFINITY to
+ *   disable in_max / zero_above.
+ * lut3d_gather: bias = cube[i0, i1, min(i2, cap2)] (float64, C order n0 x n1 x n2); i2 is capped in place (:792);
+ *   bias is 0 where zero_mask != 0 (nullable; :361); dem_out = dem - bias in float64 when dem/dem_out are given
+ *   (:364); bias or dem_out may be NULL.  An index outside the table is an error (*oob_host = 1, HC_ERR_ARG). */
+int hc_box3_index_dev(hc_ctx *ctx, const float *in, const uint8_t *in_zero, float in_max, int64_t ny, int64_t nx,
+                      float zero_above, int32_t *idx, float *smooth, void *stream);
+int hc_lut3d_gather_dev(hc_ctx *ctx, const int32_t *i0, const int32_t *i1, int8_t *i2, int cap2, const double *cube,
+                        int n0, int n1, int n2, const uint8_t *zero_mask, double *bias, const float *dem,
+                        double *dem_out, int64_t n, int *oob_host, void *stream);
 int hc_dtm_select_dev(hc_ctx *ctx, const float *dem, const float *z9, const float *z7, const float *z5,
                       const float *z3, const int8_t *slope0, const float *curv, const uint8_t *swo,
                       const uint8_t *edm, const uint8_t *tx, const uint8_t *artifact, float *zf, int8_t *filt,

@@ -440,6 +440,101 @@ extern "C" int hc_sum_shifted_dev(hc_ctx *ctx, const float *x, int64_t n, double
   return HC_OK;
 }
 
+// ---- vegetation-bias lookup (models/dem_noise_removal.py:764-805) ------------------------------------------------
+// 3x3 box mean with symmetric borders, the way apply_convolve_filter(x, np.ones((3,3)), normalize_kernel=True) makes
+// it for a non-float32 raster: nine float64 products with w = 1/9 summed in float64, narrowed to float32, values
+// above `zero_above` set to 0 (:771, tree cover only), then astype(int).  For integer-valued inputs (the Byte
+// tree-cover / tree-height rasters) the float32 narrowing makes the result independent of the summation order, so
+// the index is exact; `smooth` (optional) receives the float32 array the reference keeps as self.TC_array.
+__global__ void __launch_bounds__(256)
+k_box3_index(const float *__restrict__ in, const uint8_t *__restrict__ in_zero, float in_max, int ny, int nx,
+             double w, float zero_above, int32_t *__restrict__ idx, float *__restrict__ smooth) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= nx) return;
+  int cl = symm(c - 1, nx), cr = symm(c + 1, nx);
+  double acc = 0.0;
+#pragma unroll
+  for (int dr = -1; dr <= 1; dr++) {
+    size_t o = (size_t)symm(r + dr, ny) * nx;
+    int cc[3] = {cl, c, cr};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float x = in[o + cc[k]];
+      if (x > in_max) x = in_max;                  // Theight_array[Theight_array > max] = max (:777)
+      if (in_zero && in_zero[o + cc[k]]) x = 0.f;  // TC_array[ocean_mask == 1] = 0 (:687)
+      acc = __dadd_rn(acc, __dmul_rn((double)x, w));
+    }
+  }
+  float f = (float)acc;
+  if (f > zero_above) f = 0.f;
+  size_t i = (size_t)r * nx + c;
+  if (smooth) smooth[i] = f;
+  idx[i] = (int32_t)f;
+}
+
+// bias = cube[i0, i1, min(i2, cap2)] per cell (:802-805; the 2-D table of :620-629 is the n1 == 1 case with i1 null),
+// the capped third index written back (:792), bias zeroed under `zero_mask` (:361) and, when `dem` is given,
+// dem_out = dem - bias in float64 (:364) -- one pass over the rasters; the table (a few hundred KB) stays in L1/L2.
+__global__ void __launch_bounds__(256)
+k_lut3d_gather(const int32_t *__restrict__ i0, const int32_t *__restrict__ i1, int8_t *__restrict__ i2, int cap2,
+               const double *__restrict__ cube, int n0, int n1, int n2, const uint8_t *__restrict__ zero_mask,
+               double *__restrict__ bias, const float *__restrict__ dem, double *__restrict__ dem_out, size_t n,
+               int *__restrict__ oob) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int a = i0[i], b = i1 ? i1[i] : 0, s = i2[i];
+    if (s > cap2) { s = cap2; i2[i] = (int8_t)s; }
+    double v = 0.0;
+    if ((unsigned)a < (unsigned)n0 && (unsigned)b < (unsigned)n1 && (unsigned)s < (unsigned)n2)
+      v = __ldg(cube + ((size_t)a * n1 + b) * n2 + s);
+    else
+      *oob = 1;
+    if (zero_mask && zero_mask[i]) v = 0.0;
+    if (bias) bias[i] = v;
+    if (dem_out) dem_out[i] = (double)dem[i] - v;
+  }
+}
+
+extern "C" int hc_box3_index_dev(hc_ctx *ctx, const float *in, const uint8_t *in_zero, float in_max, int64_t ny,
+                                 int64_t nx, float zero_above, int32_t *idx, float *smooth, void *stream) {
+  ST_CTX(ctx);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!in || !idx || ny > 65535) { hc_set_error("hc_box3_index: bad argument"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((nx + 255) / 256), (unsigned)ny);
+  HC_PROF(ctx, st, "k_box3_index");
+  k_box3_index<<<grid, 256, 0, st>>>(in, in_zero, in_max, (int)ny, (int)nx, 1.0 / 9.0, zero_above, idx, smooth);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+extern "C" int hc_lut3d_gather_dev(hc_ctx *ctx, const int32_t *i0, const int32_t *i1, int8_t *i2, int cap2,
+                                   const double *cube, int n0, int n1, int n2, const uint8_t *zero_mask, double *bias,
+                                   const float *dem, double *dem_out, int64_t n, int *oob_host, void *stream) {
+  ST_CTX(ctx);
+  if (oob_host) *oob_host = 0;
+  if (n <= 0) return HC_OK;
+  if (!i0 || !i2 || !cube || n0 <= 0 || n1 <= 0 || n2 <= 0 || (!bias && !dem_out) || (dem_out && !dem) ||
+      (n1 > 1 && !i1)) {
+    hc_set_error("hc_lut3d_gather: bad argument");
+    return HC_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_TRY(arena_reset(ctx));
+  int *oob = (int *)arena_take(ctx, 256);
+  if (!oob) return HC_ERR_NOMEM;
+  HC_CUDA(cudaMemsetAsync(oob, 0, sizeof(int), st));
+  HC_PROF(ctx, st, "k_lut3d_gather");
+  k_lut3d_gather<<<ctx->sm_count * 8, 256, 0, st>>>(i0, i1, i2, cap2, cube, n0, n1, n2, zero_mask, bias, dem, dem_out,
+                                                    (size_t)n, oob);
+  HC_LAUNCH_CHECK(ctx);
+  int h = 0;
+  HC_CUDA(cudaMemcpyAsync(&h, oob, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  if (oob_host) *oob_host = h;
+  if (h) { hc_set_error("hc_lut3d_gather: index outside the lookup table"); return HC_ERR_ARG; }
+  return HC_OK;
+}
+
 extern "C" int hc_dtm_select_dev(hc_ctx *ctx, const float *dem, const float *z9, const float *z7, const float *z5,
                                  const float *z3, const int8_t *slope0, const float *curv, const uint8_t *swo,
                                  const uint8_t *edm, const uint8_t *tx, const uint8_t *artifact, float *zf, int8_t *filt,
