@@ -130,6 +130,29 @@ int hc_curvature_d2_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int
 int hc_mean_std_dev(hc_ctx *ctx, const float *x, int64_t n, double *mean, double *std, void *stream);
 /* partial sums of a row band for the global sigma: sums[0] = sum(x - shift), sums[1] = sum((x - shift)^2) (host) */
 int hc_sum_shifted_dev(hc_ctx *ctx, const float *x, int64_t n, double shift, double *sums, void *stream);
+/* Water stencils of tools/water.py (called from models/depression_handling.py:647,889,898 and
+ * models/burn_rivers.py:841,856).  wm = water_mask_array as uint8, swo = SWO_array as int16, dem/burn float32;
+ * `burn` (DEM_burn_arr) is updated in place and may alias `dem`, as in the reference's own calls.
+ * minmax_filter: scipy.ndimage.minimum_filter / maximum_filter(in, size=size) (mode 'reflect'), elem_bytes 1 (uint8)
+ *   or 4 (float32).  conv2d_symm_f64: apply_convolve_filter with a float64 kernel (host pointer, odd sizes <= 15):
+ *   float64 accumulation, float32 result.
+ * river_minimize :786-847 (out may not alias dem); raise_small_rivers :1010-1045; raise_small_streams :960-1007;
+ * smooth_rivers :928-957.  The scalar parameters are the reference's keyword arguments, narrowed to float32 the
+ * way numpy narrows a Python float against a float32 array. */
+int hc_minmax_filter_dev(hc_ctx *ctx, const void *in, void *out, int64_t ny, int64_t nx, int size, int is_max,
+                         int elem_bytes, void *stream);
+int hc_conv2d_symm_f64_dev(hc_ctx *ctx, const float *in, const double *kernel_host, int kh, int kw, float *out,
+                           int64_t ny, int64_t nx, void *stream);
+int hc_river_minimize_dev(hc_ctx *ctx, const float *dem, const uint8_t *wm, const int16_t *swo, float nodata,
+                          float max_burn, int filter_size, float *out, int64_t ny, int64_t nx, void *stream);
+int hc_raise_small_rivers_dev(hc_ctx *ctx, const float *dem, float *burn, const uint8_t *wm, const int16_t *swo,
+                              float nodata, int swo_high, int swo_low, float extra_raise, float max_raise,
+                              int filter_size, int64_t ny, int64_t nx, void *stream);
+int hc_raise_small_streams_dev(hc_ctx *ctx, const float *dem, float *burn, const uint8_t *wm, float nodata,
+                               float extra_raise, float max_raise, int fsize, int64_t ny, int64_t nx, void *stream);
+int hc_smooth_rivers_dev(hc_ctx *ctx, const float *dem, float *burn, const uint8_t *wm, const int16_t *swo,
+                         float nodata, int swo_cut, float max_lower, int filter_size, int64_t ny, int64_t nx,
+                         void *stream);
 /* Vegetation-bias lookup of CreateDTM.compute_veg_bias_3D (models/dem_noise_removal.py:764-805; the 2-D table of
  * compute_veg_bias_2D :620-629 is n1 == 1 with i1 NULL).
  * box3_index: inputs first capped at in_max (:777) and zeroed where in_zero != 0 (nullable; the ocean mask, :687);

@@ -43,6 +43,17 @@ SIGNATURES = {
     "hc_curvature_d2_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_f64, ctypes.c_int, c_vp]),
     "hc_mean_std_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_vp]),
     "hc_sum_shifted_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_f64, ctypes.POINTER(c_f64), c_vp]),
+    "hc_minmax_filter_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            c_vp]),
+    "hc_conv2d_symm_f64_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_i64, c_vp]),
+    "hc_river_minimize_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, ctypes.c_int, c_vp, c_i64, c_i64,
+                                             c_vp]),
+    "hc_raise_small_rivers_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, ctypes.c_int, ctypes.c_int, c_f32,
+                                                 c_f32, ctypes.c_int, c_i64, c_i64, c_vp]),
+    "hc_raise_small_streams_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, ctypes.c_int, c_i64,
+                                                  c_i64, c_vp]),
+    "hc_smooth_rivers_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, ctypes.c_int, c_f32, ctypes.c_int,
+                                            c_i64, c_i64, c_vp]),
     "hc_box3_index_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_f32, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "hc_lut3d_gather_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(ctypes.c_int),
