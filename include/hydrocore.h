@@ -130,6 +130,15 @@ int hc_curvature_d2_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int
 int hc_mean_std_dev(hc_ctx *ctx, const float *x, int64_t n, double *mean, double *std, void *stream);
 /* partial sums of a row band for the global sigma: sums[0] = sum(x - shift), sums[1] = sum((x - shift)^2) (host) */
 int hc_sum_shifted_dev(hc_ctx *ctx, const float *x, int64_t n, double shift, double *sums, void *stream);
+/* Depression breaching, Lindsay (2016): wbt.breach_depressions(dem, out, max_length=radius, max_depth=None,
+ * fill_pits=True, flat_increment=0.0) as dep.breach_pits calls it (tools/depressions.py:1376-1380, :1012-1014).
+ * HOST arithmetic (one global priority order, not a bandwidth-bound pass; no context needed):
+ * z/out are host rasters (out != z).  max_length <= 0 and max_depth <= 0 / inf mean unconstrained.  do_fill = 1 also
+ * fills what could not be breached (host priority flood); with do_fill = 0 the caller runs hc_fill_* (seed mode WBT)
+ * on the result.  flat_increment is 0 (level channels).  stats (5 x int64, nullable): pits met, breached, left to the
+ * fill, cells lowered, cells raised.  Specification and its PARITY-UNPINNED status: csrc/breach.cu. */
+int hc_breach_depressions_host(const float *z, float *out, int64_t ny, int64_t nx, float nodata, int64_t max_length,
+                               double max_depth, int fill_pits, int do_fill, int64_t *stats);
 /* Water stencils of tools/water.py (called from models/depression_handling.py:647,889,898 and
  * models/burn_rivers.py:841,856).  wm = water_mask_array as uint8, swo = SWO_array as int16, dem/burn float32;
  * `burn` (DEM_burn_arr) is updated in place and may alias `dem`, as in the reference's own calls.

@@ -194,6 +194,35 @@ def breach_single_cell_pits(z, nodata=-9999.0):
     return _unary_f32(z, "hc_breach_single_cell_pits_dev", nodata)
 
 
+def breach_depressions(z, nodata=-9999.0, max_length=None, max_depth=None, fill_pits=False, flat_increment=None,
+                       return_stats=False):
+    """wbt.breach_depressions (Lindsay 2016) as dep.breach_pits calls it (tools/depressions.py:1376-1380):
+    constrained breaching on the host (`hc_breach_depressions_host`, one global priority order -- SURVEY.md 8 row
+    a2), then the depressions that could not be breached are filled by the GPU fill with WhiteboxTools' seed rule.
+    float32 in, float32 out (numpy in -> numpy out, CUDA tensor in -> CUDA tensor out)."""
+    import ctypes
+    import numpy as np
+    if flat_increment is not None and flat_increment > 0:
+        raise NotImplementedError("flat_increment > 0 (graded breach channels / Priority-Flood+epsilon) is order "
+                                  "dependent in WhiteboxTools and is not offered; pydrodem's default is 0.0")
+    host = not _is_torch(z)
+    zh = _np2d(z if host else z.detach().cpu().numpy(), np.float32)
+    cut = np.empty_like(zh)
+    st = (ctypes.c_int64 * 5)()
+    _lib.check(_lib.load().hc_breach_depressions_host(_vp(zh), _vp(cut), zh.shape[0], zh.shape[1], float(nodata),
+                                                     int(max_length) if max_length else 0,
+                                                     float(max_depth) if max_depth else 0.0, int(bool(fill_pits)), 0,
+                                                     st), "hc_breach_depressions_host")
+    if host:
+        out = fill(cut, nodata=nodata, seed_mode=SEED_WBT)
+    else:
+        import torch
+        out = fill(torch.from_numpy(cut).to(z.device), nodata=nodata, seed_mode=SEED_WBT)
+    if return_stats:
+        return out, dict(pits=st[0], breached=st[1], left_to_fill=st[2], cells_lowered=st[3])
+    return out
+
+
 def taudem_check(p, fel, flat_mask, edm, nodata=-9999.0):
     """TaudemCheck.check_basin's problem mask (models/taudem_check.py:143-147): returns (mask uint8, count).
     `p` is the uint8 D8 raster with 255 = nodata."""

@@ -1,0 +1,203 @@
+// breach.cu -- host-side depression breaching (Lindsay 2016), the arithmetic behind
+//   wbt.breach_depressions(dem, out, max_length=radius, max_depth=None, fill_pits=True, flat_increment=0.0)
+// as dep.breach_pits calls it (tools/depressions.py:1376-1380; also :1012-1014 inside combined_solution).
+//
+// breaching follows ONE global priority order, it does not shard and it is not one of the
+// bandwidth-bound passes; "host C++ first is acceptable".  This file is that host implementation -- product code of
+// the library (single thread, O(N log N)), not a fallback for anything: there is no GPU breach yet.  The final
+// "fill what could not be breached" step is the library's ordinary fill (GPU, hc_fill_dev) when the caller asks for
+// do_fill = 0 and runs it afterwards, or a host priority flood (do_fill = 1) so that the whole tool can be checked
+// without a GPU.
+//
+// WhiteboxTools is not in /root/reference (un-vendored, version unpinned), so this restates the published algorithm
+// (Lindsay 2016, "Efficient hybrid breaching-filling sink removal methods for flow path enforcement in digital
+// elevation models", Hydrol. Process. 30) -- PARITY UNPINNED:
+//   0. fill_pits: single-cell pits are raised to their lowest neighbour first (same rule as hc_fill_single_cell_pits).
+//   1. Priority flood from the seed cells (valid cells on the raster frame or 8-adjacent to exterior-connected nodata --
+//      the seed rule of the WBT fill, oracle/hydro_oracle.c orc_seed_mask), min-heap on (elevation, push order);
+//      neighbours are scanned NE, E, SE, S, SW, W, NW, N.  A cell discovered from cell c gets the back-link c.
+//   2. When a popped cell p is a pit (no valid neighbour is lower on the current surface), the breach path is the chain
+//      of back-links from p toward the seeds: it is followed until a cell lower than z(p) -- or a seed, which drains off
+//      the raster -- is reached.  If the walk is no longer than max_length cells and never has to cut deeper than
+//      max_depth, every cell of it that is higher than z(p) is lowered to z(p) (flat_increment = 0: a level channel);
+//      otherwise the pit is left for step 3.  Path cells were all popped earlier, so cutting never disturbs the heap.
+//   3. Depressions that remain are filled (epsilon 0).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <queue>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+const int B_DR[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
+const int B_DC[8] = {1, 1, 1, 0, -1, -1, -1, 0};
+
+struct item {
+  float z;
+  uint64_t seq;
+  int64_t i;
+};
+struct item_after {
+  bool operator()(const item &a, const item &b) const { return a.z > b.z || (a.z == b.z && a.seq > b.seq); }
+};
+typedef std::priority_queue<item, std::vector<item>, item_after> heap_t;
+
+inline bool b_nodata(float v, float nodata) { return v == nodata || v != v; }
+
+// seeds of the WBT rule: frame cells and cells 8-adjacent to nodata connected to the frame
+void seed_mask(const float *z, std::vector<uint8_t> &seed, int64_t ny, int64_t nx, float nodata) {
+  const int64_t n = ny * nx;
+  seed.assign((size_t)n, 0);
+  std::vector<uint8_t> ext((size_t)n, 0);
+  std::vector<int64_t> stack;
+  for (int64_t r = 0; r < ny; r++)
+    for (int64_t c = 0; c < nx; c++) {
+      if (!(r == 0 || c == 0 || r == ny - 1 || c == nx - 1)) continue;
+      int64_t i = r * nx + c;
+      if (b_nodata(z[i], nodata)) {
+        if (!ext[i]) { ext[i] = 1; stack.push_back(i); }
+      } else {
+        seed[i] = 1;
+      }
+    }
+  while (!stack.empty()) {
+    int64_t i = stack.back();
+    stack.pop_back();
+    int64_t r = i / nx, c = i % nx;
+    for (int k = 0; k < 8; k++) {
+      int64_t rr = r + B_DR[k], cc = c + B_DC[k];
+      if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
+      int64_t j = rr * nx + cc;
+      if (b_nodata(z[j], nodata)) {
+        if (!ext[j]) { ext[j] = 1; stack.push_back(j); }
+      } else {
+        seed[j] = 1;
+      }
+    }
+  }
+}
+
+void fill_single_cell_pits(const float *z, float *out, int64_t ny, int64_t nx, float nodata) {
+  memcpy(out, z, sizeof(float) * (size_t)(ny * nx));
+  for (int64_t r = 1; r < ny - 1; r++)
+    for (int64_t c = 1; c < nx - 1; c++) {
+      float v = z[r * nx + c];
+      if (b_nodata(v, nodata)) continue;
+      float mn = INFINITY;
+      bool pit = true;
+      for (int k = 0; k < 8 && pit; k++) {
+        float zn = z[(r + B_DR[k]) * nx + c + B_DC[k]];
+        if (b_nodata(zn, nodata) || !(zn > v)) pit = false;
+        else if (zn < mn) mn = zn;
+      }
+      if (pit) out[r * nx + c] = mn;
+    }
+}
+
+}  // namespace
+
+// stats[0] pits met, [1] pits breached, [2] pits left to the fill, [3] cells lowered, [4] cells raised by the final fill
+extern "C" int hc_breach_depressions_host(const float *z, float *out, int64_t ny, int64_t nx, float nodata,
+                                          int64_t max_length, double max_depth, int fill_pits, int do_fill,
+                                          int64_t *stats) {
+  if (stats) memset(stats, 0, sizeof(int64_t) * 5);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!z || !out || z == out) { hc_set_error("hc_breach_depressions: bad argument"); return HC_ERR_ARG; }
+  const int64_t n = ny * nx;
+  const bool lim_len = max_length > 0;
+  const bool lim_depth = max_depth > 0 && std::isfinite(max_depth);
+  try {
+    float *w = out;
+    if (fill_pits) fill_single_cell_pits(z, w, ny, nx, nodata);
+    else memcpy(w, z, sizeof(float) * (size_t)n);
+    std::vector<uint8_t> seed;
+    seed_mask(w, seed, ny, nx, nodata);
+    std::vector<uint8_t> visited((size_t)n, 0);
+    std::vector<int8_t> back((size_t)n, -1);   // direction slot toward the cell this one was discovered from
+    heap_t heap;
+    uint64_t seq = 0;
+    for (int64_t i = 0; i < n; i++)
+      if (seed[i]) { visited[i] = 1; heap.push(item{w[i], seq++, i}); }
+    std::vector<int64_t> path;
+    int64_t s_pits = 0, s_done = 0, s_left = 0, s_cut = 0;
+    while (!heap.empty()) {
+      item t = heap.top();
+      heap.pop();
+      const int64_t p = t.i, r = p / nx, c = p % nx;
+      if (!seed[p]) {
+        const float zt = w[p];
+        bool pit = true;
+        for (int k = 0; k < 8 && pit; k++) {
+          int64_t rr = r + B_DR[k], cc = c + B_DC[k];
+          if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
+          float zn = w[rr * nx + cc];
+          if (!b_nodata(zn, nodata) && zn < zt) pit = false;
+        }
+        if (pit) {
+          s_pits++;
+          path.clear();
+          int64_t q = p, len = 0;
+          double depth = 0.0;
+          bool ok = true;
+          while (back[q] >= 0) {
+            int k = back[q];
+            q = (q / nx + B_DR[k]) * nx + (q % nx + B_DC[k]);
+            len++;
+            if (lim_len && len > max_length) { ok = false; break; }
+            if (w[q] < zt) break;                       // lower ground reached: the pit drains
+            double d = (double)w[q] - (double)zt;
+            if (d > depth) depth = d;
+            if (lim_depth && depth > max_depth) { ok = false; break; }
+            if (w[q] > zt) path.push_back(q);
+          }
+          if (ok) {
+            s_done++;
+            for (int64_t qq : path) w[qq] = zt;
+            s_cut += (int64_t)path.size();
+          } else {
+            s_left++;
+          }
+        }
+      }
+      for (int k = 0; k < 8; k++) {
+        int64_t rr = r + B_DR[k], cc = c + B_DC[k];
+        if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
+        int64_t j = rr * nx + cc;
+        if (visited[j] || b_nodata(w[j], nodata)) continue;
+        visited[j] = 1;
+        back[j] = (int8_t)((k + 4) & 7);
+        heap.push(item{w[j], seq++, j});
+      }
+    }
+    int64_t s_raised = 0;
+    if (do_fill) {
+      // priority-flood fill (epsilon 0) of what is left, same seeds
+      std::fill(visited.begin(), visited.end(), 0);
+      seq = 0;
+      for (int64_t i = 0; i < n; i++)
+        if (seed[i]) { visited[i] = 1; heap.push(item{w[i], seq++, i}); }
+      while (!heap.empty()) {
+        item t = heap.top();
+        heap.pop();
+        const int64_t r = t.i / nx, c = t.i % nx;
+        for (int k = 0; k < 8; k++) {
+          int64_t rr = r + B_DR[k], cc = c + B_DC[k];
+          if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
+          int64_t j = rr * nx + cc;
+          if (visited[j] || b_nodata(w[j], nodata)) continue;
+          visited[j] = 1;
+          if (w[j] < t.z) { w[j] = t.z; s_raised++; }
+          heap.push(item{w[j], seq++, j});
+        }
+      }
+    }
+    if (stats) { stats[0] = s_pits; stats[1] = s_done; stats[2] = s_left; stats[3] = s_cut; stats[4] = s_raised; }
+  } catch (const std::bad_alloc &) {
+    hc_set_error("hc_breach_depressions: out of host memory");
+    return HC_ERR_NOMEM;
+  }
+  return HC_OK;
+}

@@ -4,7 +4,7 @@ Same signatures and file protocol (`<in>_WL.tif`, `<in>_WL_DIFF.tif`, clump-ID r
 replaced by pydrodem_b200.raster_io, WhiteboxTools by the `wbt` duck type (pydrodem_b200.wbt) and
 scipy.ndimage.label / convolve2d by the CUDA kernels.  build_pit_catalog / select_solution /
 apply_solution / fill_shallow_pits run as segmented reductions on the GPU (csrc/segment.cu);
-breach_pits and combined_solution (both need WhiteboxTools' breach) are not built.
+breach_pits runs through `wbt.breach_depressions` (host breach + GPU fill, csrc/breach.cu).
 """
 import os
 
@@ -33,6 +33,34 @@ def fill_pits(inDEM, wbt, fill_method='WL', nodataval=-9999, fixflats=False, fla
         diff_tif_fill = fill_tif.replace('.tif', '_DIFF.tif')
         raster_io.write_raster(diff_tif_fill, diff_fill_array.astype(np.float32), meta, nodata=nodataval)
     return fill_array, diff_fill_array
+
+
+def breach_pits(inDEM_tif, radius, maxcost, wbt, min_dist=False, flat_increment=0.0, breach_increment=0.0001,
+                nodataval=-9999, method='SC', fixflats=False, save_tif=True):
+    """tools/depressions.py:1319-1403.  Returns (carve_array, diff_carve_array); writes `<in>_<method>_<radius>.tif`
+    (re-used when it exists, :1369) and (save_tif) its `_DIFF.tif`."""
+    carve_path = inDEM_tif.replace('.tif', '_{1}_{0}.tif'.format(radius, method))
+    carvefill_path = inDEM_tif.replace('.tif', '_{1}_{0}_filled.tif'.format(radius, method))
+    if flat_increment > 0.0:
+        fixflats = True
+    if not os.path.exists(carve_path):
+        if method == 'LC':
+            wbt.breach_depressions_least_cost(inDEM_tif, carve_path, radius, max_cost=maxcost, min_dist=min_dist,
+                                              flat_increment=breach_increment, fill=False)
+        else:
+            wbt.breach_depressions(inDEM_tif, carve_path, max_length=radius, max_depth=None, fill_pits=True,
+                                   callback=None, flat_increment=flat_increment)
+    if method == 'LC':
+        wbt.fill_depressions_wang_and_liu(carve_path, carvefill_path, fix_flats=fixflats, flat_increment=flat_increment)
+    else:
+        carvefill_path = carve_path
+    inDEM_array, meta = raster_io.read_raster(inDEM_tif)
+    carve_array, _ = raster_io.read_raster(carvefill_path)
+    diff_carve_array = np.round((carve_array - inDEM_array), 3)  # :1395
+    if save_tif:
+        diff_tif_carve = carvefill_path.replace('.tif', '_DIFF.tif')
+        raster_io.write_raster(diff_tif_carve, diff_carve_array.astype(np.float32), meta, nodata=nodataval)
+    return carve_array, diff_carve_array
 
 
 def create_clump_array(input_array, clump_ID_tif, stencil_tif, wbt, nodataval=-9999, noflow_array=None,
@@ -74,10 +102,29 @@ def create_clump_array(input_array, clump_ID_tif, stencil_tif, wbt, nodataval=-9
     return clump_ID_array
 
 
-def fix_shifted_data(in_array, shift_array, nodataval=-9999, failtest=False, vprint=False):
-    """tools/depressions.py:1406-1468 repairs a one-pixel shift artefact of WhiteboxTools' GeoTIFF
-    writer; the GPU path never shifts, so the arrays are returned unchanged."""
-    return shift_array
+def fix_shifted_data(in_array, shift_array, nodataval, failtest='negative_diff', vprint=False):
+    """tools/depressions.py:1406-1468: undo a whole-raster pixel shift of a WhiteboxTools output (detected from the
+    bounding boxes of the valid cells) and recompute the rounded difference map.  Returns (shift_array, diff_array).
+    The GPU tools never shift a raster, so on this path the shift is (0, 0) and only the difference map is rebuilt;
+    the index arithmetic is kept so that a raster produced elsewhere is repaired the same way (host numpy: a rare
+    repair path over index lists, not a kernel)."""
+    data_ind = np.nonzero(in_array != nodataval)
+    nodata_ind = np.nonzero(in_array == nodataval)
+    fill_data_ind = np.nonzero(shift_array != nodataval)
+    shift_1 = fill_data_ind[1].max() - data_ind[1].max()
+    shift_0 = fill_data_ind[0].max() - data_ind[0].max()
+    ind_diff = np.abs(len(data_ind[0]) - len(fill_data_ind[0]))
+    fill_data_ind_shift = (fill_data_ind[0] - shift_0, fill_data_ind[1] - shift_1)
+    shift_array[fill_data_ind_shift] = shift_array[fill_data_ind]
+    shift_array[nodata_ind] = nodataval
+    diff_array = np.round((shift_array - in_array), 3)
+    if failtest == 'negative_diff':
+        fail_diff = np.nonzero(diff_array < 0.0)
+    elif failtest == 'positive_diff':
+        fail_diff = np.nonzero(diff_array > 0.0)
+    num_fail = len(fail_diff[0])
+    assert num_fail <= ind_diff + 3, 'Re-mapped fill diff has too many negative values'
+    return shift_array, diff_array
 
 
 # ==================================================================================================
@@ -321,3 +368,237 @@ def fill_shallow_pits(modDEM_vec, sfill, fillID_vec, diff_fill_array, fill_array
         modDEM_vec[:] = out            # the reference modifies its argument in place and returns it
         return modDEM_vec
     return out
+
+
+# ==================================================================================================
+# initial_fill_carve (tools/depressions.py:41-264): the orchestration that turns one DEM GeoTIFF into the eight
+# vectors the pit catalog consumes -- two fills, four clump rasters, one breach.
+# ==================================================================================================
+def initial_fill_carve(inDEM_tif, basename, outpath, fill_method, maxcost, radius, min_dist, nodataval, starttime, wbt,
+                       sfill=None, flat_increment=0.0, watermask=None, water_mask_array=None, carveout=False,
+                       carve_method='SC', verbose_print=True, del_temp_files=False):
+    """Same signature, file names and return tuple as the reference:
+    (modDEM_vec, fill_vec, carve_vec, diff_vec_fill, diff_vec_carve, fillID_vec, carveID_vec, carvefillID_vec, nx, ny).
+    `watermask` (the lake raise of :163-176) is refused: `raise_lake_connected_pits` is broken upstream."""
+    import glob
+    if watermask is not None:
+        raise NotImplementedError("initial_fill_carve(watermask=...) calls raise_lake_connected_pits, which cannot run "
+                                  "in the reference either (tools/depressions.py:1536-1590; DESIGN.md 7)")
+    inDEM_array, meta = raster_io.read_raster(inDEM_tif)
+    ny, nx = inDEM_array.shape
+    water_mask_vec = np.ravel(water_mask_array) if water_mask_array is not None else None
+
+    # initial fill: finds lake-draining and shallow pits (:103-117)
+    fill_array, diff_fill_array = fill_pits(inDEM_tif, wbt, fill_method=fill_method, nodataval=nodataval,
+                                            flat_increment=0.0)
+    if np.amin(diff_fill_array) < 0.0:
+        fill_array, diff_fill_array = fix_shifted_data(inDEM_array, fill_array, nodataval)
+    fillID_path = os.path.join(outpath, '{0}_pitID_initial.tif'.format(basename))
+    fillID_array = create_clump_array(diff_fill_array, fillID_path, inDEM_tif, wbt, nodataval=nodataval,
+                                      condition='greaterthan')
+    fillID_vec = fillID_array.reshape(ny * nx,)
+    inDEM_vec = inDEM_array.reshape(ny * nx,)
+    modDEM_vec = np.copy(inDEM_vec)
+    modDEM_vec[np.where(np.isnan(modDEM_vec))] = nodataval
+
+    if sfill is not None:                                                                     # :133-138
+        modDEM_vec = fill_shallow_pits(modDEM_vec, sfill, fillID_vec, diff_fill_array, fill_array,
+                                       water_vec=water_mask_vec, verbose_print=verbose_print)
+
+    if sfill is None:                                                                         # :160-162
+        modDEM_tif = inDEM_tif
+    else:                                                                                     # :163-185
+        modDEM_array = np.asarray(modDEM_vec).reshape(ny, nx)
+        modDEM_tif = os.path.join(outpath, f"{basename}_shallowfill.tif")
+        raster_io.write_raster(modDEM_tif, modDEM_array.astype(np.float32), meta, nodata=nodataval)
+        fill_array, diff_fill_array = fill_pits(modDEM_tif, wbt, fill_method=fill_method, nodataval=nodataval,
+                                                flat_increment=flat_increment)
+        if np.amin(diff_fill_array) < 0.0:
+            fill_array, diff_fill_array = fix_shifted_data(modDEM_array, fill_array, nodataval)
+
+    fillID_path = os.path.join(outpath, '{0}_pitID.tif'.format(basename))                     # :187-192
+    fillID_array = create_clump_array(diff_fill_array, fillID_path, inDEM_tif, wbt, nodataval=nodataval,
+                                      condition='greaterthan', clumpbuffer=1)
+    fillID_vec = fillID_array.reshape(ny * nx,)
+    fill_vec = fill_array.reshape(ny * nx,)
+    diff_vec_fill = diff_fill_array.reshape(ny * nx,)
+
+    carve_array, diff_carve_array = breach_pits(modDEM_tif, radius, maxcost, wbt, min_dist=min_dist,   # :199-205
+                                                nodataval=nodataval, method=carve_method,
+                                                flat_increment=flat_increment)
+    carve_vec = carve_array.reshape(ny * nx,)
+    diff_vec_carve = np.copy(diff_carve_array).reshape(ny * nx,)
+
+    carveID_path = os.path.join(outpath, '{0}_carveID.tif'.format(basename))                  # :210-226
+    carve_fillID_path = os.path.join(outpath, '{0}_carve_fillID.tif'.format(basename))
+    if not carveout:   # nodata pixels join the carve clumps, so that carves leaving the raster can be told apart
+        diff_carve_array[inDEM_array == nodataval] = -1.0
+    carveID_array = create_clump_array(diff_carve_array, carveID_path, inDEM_tif, wbt, nodataval=nodataval,
+                                       condition='lessthan')
+    carvefillID_array = create_clump_array(diff_carve_array, carve_fillID_path, inDEM_tif, wbt, nodataval=nodataval,
+                                           condition='greaterthan')
+    carveID_vec = carveID_array.reshape(ny * nx,)
+    carvefillID_vec = carvefillID_array.reshape(ny * nx,)
+
+    if del_temp_files:                                                                        # :236-238 (ft.erase_files)
+        basename_mod = os.path.splitext(os.path.basename(modDEM_tif))[0]
+        for f in glob.glob(os.path.join(outpath, '{0}_*.tif'.format(basename_mod))):
+            if os.path.isfile(f):
+                os.remove(f)
+    return modDEM_vec, fill_vec, carve_vec, diff_vec_fill, diff_vec_carve, fillID_vec, carveID_vec, carvefillID_vec, \
+        nx, ny
+
+
+# ==================================================================================================
+# combined_solution (tools/depressions.py:813-1137): for one big pit, try partial fills at fractions of its depth,
+# re-breach each inside a window around the pit, and keep the cheapest complete result.
+# ==================================================================================================
+def _window_meta(meta, row_min, col_min):
+    """geo-referencing of a sub-window (what pyct.clip_to_window derives from the geotransform, tools/convert.py:590-599)"""
+    m = raster_io.RasterMeta(meta or {})
+    geo = dict(m.get("geo", {}))
+    tie, scale = geo.get(33922), geo.get(33550)
+    if tie and scale:
+        v = list(tie[1])
+        v[3] = v[3] + col_min * scale[1][0]
+        v[4] = v[4] - row_min * scale[1][1]
+        geo[33922] = (tie[0], v)
+    m["geo"] = geo
+    return m
+
+
+def combined_solution(inDEM, inDEM_array, outpath, nx, ny, DFpits, fillcells_dct, carvecells_dct, carve_fillcells_dct,
+                      pit_id, combined_fill_interval, fillID_vec, fill_vec, carve_vec, radius, maxcost, min_dist,
+                      max_carve_depth, wbt, nodataval=-9999, fixflats=False, flat_increment=0.0, carve_method='SC',
+                      water_array=None, wall_vec=None, del_temp_files=True):
+    """Same arguments and return value -- (solution_name, sol_df[vol, elevs, solution, footprint]) -- as the
+    reference.  Host orchestration over a window of (pit bounding box + radius + 2) cells; the breaches go through
+    `wbt.breach_depressions(max_length=radius, max_depth=max_carve_depth, fill_pits=False)` and the carve clumps
+    through the GPU labelling (8-connectivity, scipy numbering)."""
+    import glob
+    import pandas as pd
+    pit_df = DFpits.loc[pit_id].copy()
+    init_sol = pit_df.solution
+    footprint = np.asarray(fillcells_dct[pit_id])
+    completecarve = pit_df.completecarve
+    combined_sol = init_sol - 1000   # 3000 or 3020
+    combined_path = os.path.join(outpath, "combined_solutions")
+    os.makedirs(combined_path, exist_ok=True)
+
+    # window = bounding box of the pit + (radius + 2) cells, clipped to the raster (pyct.clip_to_window)
+    clip_buf = radius + 2
+    rows, cols = np.unravel_index(footprint, (ny, nx))
+    row_min = int(max(0, rows.min() - clip_buf))
+    row_max = int(min(ny, rows.max() + clip_buf + 1))
+    col_min = int(max(0, cols.min() - clip_buf))
+    col_max = int(min(nx, cols.max() + clip_buf + 1))
+    ny_c, nx_c = row_max - row_min, col_max - col_min
+    rr, cc = np.mgrid[row_min:row_max, col_min:col_max]
+    clipped_ind = np.ravel_multi_index((rr.ravel(), cc.ravel()), (ny, nx))
+    win = (slice(row_min, row_max), slice(col_min, col_max))
+    _, meta = raster_io.read_raster(inDEM)
+    wmeta = _window_meta(meta, row_min, col_min)
+    clippedDEM = os.path.join(combined_path, "{0}.tif".format(pit_id))
+    inDEM_array_clipped = np.ascontiguousarray(np.asarray(inDEM_array)[win], dtype=np.float32)
+    raster_io.write_raster(clippedDEM, inDEM_array_clipped, wmeta, nodata=nodataval)
+    inDEM_vec_clipped = inDEM_array_clipped.reshape(ny_c * nx_c,)
+    fill_vec_clipped = np.asarray(fill_vec).reshape(ny, nx)[win].reshape(ny_c * nx_c,)
+    carve_vec_orig_clipped = np.asarray(carve_vec).reshape(ny, nx)[win].reshape(ny_c * nx_c,)
+    fillID_clipped_vec = np.asarray(fillID_vec)[clipped_ind]
+    footprint_clipped = np.flatnonzero(fillID_clipped_vec == pit_id)
+
+    maxfill_value = pit_df.maxfill
+    vols, elevs, sol_names, dep_indices = [], [], [], []
+
+    fraction_list = np.round(np.arange(combined_fill_interval, 1, combined_fill_interval), 1)
+    for frac in fraction_list:
+        # lower the full fill by a constant (keeps any gradient of the fill), never below ground (:905-914)
+        SF_vec = np.copy(fill_vec_clipped)
+        fill_depth_remove = maxfill_value * (1 - frac)
+        SF_vec[footprint_clipped] = SF_vec[footprint_clipped] - fill_depth_remove
+        SF_diff = np.round((SF_vec - inDEM_vec_clipped), 3)
+        belowground_ind = np.where(SF_diff < 0)[0]
+        fill_frac_ind = np.where(SF_diff > 0)[0]
+        SF_vec[belowground_ind] = inDEM_vec_clipped[belowground_ind]
+        p_fill_min = (SF_vec[fill_frac_ind]).min()
+        carve_fill_min = (carve_vec_orig_clipped[fill_frac_ind]).min()
+        if (completecarve == 1) and (p_fill_min > carve_fill_min):   # partial fill above the carve's back-fill
+            continue
+        clippedDEM_SF = os.path.join(combined_path, "{0}_SF_{1}.tif".format(pit_id, frac))
+        raster_io.write_raster(clippedDEM_SF, SF_vec.reshape(ny_c, nx_c).astype(np.float32), wmeta, nodata=nodataval)
+        clippedDEM_carved = os.path.join(combined_path, "{0}_SF_{1}_{2}.tif".format(pit_id, frac, carve_method))
+        if carve_method == 'LC':
+            wbt.breach_depressions_least_cost(clippedDEM_SF, clippedDEM_carved, radius, max_cost=maxcost,
+                                              min_dist=min_dist, flat_increment=flat_increment, fill=False)
+            clippedDEM_filled = os.path.join(combined_path, "{0}_SF_{1}_{2}_filled.tif".format(pit_id, frac, carve_method))
+            wbt.fill_depressions_wang_and_liu(clippedDEM_carved, clippedDEM_filled, fix_flats=fixflats,
+                                              flat_increment=flat_increment)
+        else:
+            wbt.breach_depressions(clippedDEM_SF, clippedDEM_carved, max_length=radius, max_depth=max_carve_depth,
+                                   fill_pits=False, flat_increment=flat_increment, callback=None)
+        clippedDEM_carved_array, _ = raster_io.read_raster(clippedDEM_carved)
+
+        # carves that touch the pit, as 8-connected clumps of (lowered or nodata) cells (:958-985)
+        diff_array_clip = np.round((clippedDEM_carved_array - inDEM_array_clipped), 4)
+        diff_vec_clip = diff_array_clip.reshape(ny_c * nx_c,)
+        mask_carve = np.zeros(inDEM_array_clipped.shape, dtype=np.int8)
+        mask_carve[diff_array_clip < 0] = 1
+        mask_carve[inDEM_array_clipped == nodataval] = 1
+        carveID_clip_array, _ = core.label(mask_carve, 8)
+        carveID_clip_vec = np.asarray(carveID_clip_array).reshape(ny_c * nx_c,)
+        carve_ind_clipped = np.flatnonzero(diff_vec_clip < 0.0)
+        carve_intersect = np.intersect1d(footprint_clipped, carve_ind_clipped, assume_unique=True)
+        carveIDs_pit = np.unique(carveID_clip_vec[carve_intersect])
+        carvecells_add = list(np.flatnonzero(np.isin(carveID_clip_vec, carveIDs_pit)))
+        nodata_clipped_ind = np.flatnonzero(inDEM_vec_clipped == nodataval)
+        if len(nodata_clipped_ind > 0):        # the window holds raster edge: a carve running off it is disqualified
+            carveout_ID = carveID_clip_vec[nodata_clipped_ind][0]
+            if carveout_ID in list(carveIDs_pit):
+                continue
+        if len(carvecells_add) < 1:
+            continue
+        expanded_footprint_clipped = list(set(carvecells_add + list(footprint_clipped)))
+        expanded_footprint = clipped_ind[expanded_footprint_clipped]
+        volchange = np.sum(abs(diff_vec_clip[expanded_footprint_clipped]))
+        maxcarvedepth = abs(diff_vec_clip[expanded_footprint_clipped].min())
+        if maxcarvedepth <= max_carve_depth:
+            elevs.append(list(clippedDEM_carved_array.reshape(ny_c * nx_c,)[expanded_footprint_clipped]))
+            vols.append(volchange)
+            dep_indices.append(expanded_footprint.astype(int))
+            if int(frac * 10) == 0:
+                if combined_sol == 3020:
+                    sol_names.append(1020)
+                elif combined_sol == 3000:
+                    sol_names.append(1003)
+            else:
+                sol_names.append(int(combined_sol + (10 * frac)))
+        if del_temp_files:
+            for f in glob.glob(os.path.join(combined_path, '{0}_*.tif'.format(pit_id))):
+                if os.path.isfile(f):
+                    os.remove(f)
+
+    # the plain fill, and the plain carve when it is complete, compete too (:1098-1117)
+    sol_names.append(2003)
+    vols.append(pit_df.volfill)
+    dep_indices.append(footprint)
+    elevs.append(list(np.asarray(fill_vec)[footprint]))
+    if completecarve == 1:
+        vol_total = pit_df.volcarve + pit_df.volfillbehind
+        carve_cells_all = list(set(list(carvecells_dct[pit_id]) + list(carve_fillcells_dct[pit_id]) + list(footprint)))
+        if not np.isnan(vol_total):
+            sol_names.append(1003)
+            vols.append(vol_total)
+            dep_indices.append(carve_cells_all)
+            elevs.append(list(np.asarray(carve_vec)[carve_cells_all]))
+
+    df_combined = pd.DataFrame(columns=["vol", "elevs", "solution", "footprint"])
+    df_combined["vol"] = vols
+    df_combined["elevs"] = elevs
+    df_combined["solution"] = sol_names
+    df_combined["footprint"] = dep_indices
+    solution_name = df_combined.solution[df_combined["vol"].idxmin()]
+    sol_df = df_combined.loc[df_combined.solution == solution_name].copy()
+    for f in glob.glob(os.path.join(combined_path, '*.tif')):
+        if os.path.isfile(f):
+            os.remove(f)
+    return solution_name, sol_df

@@ -14,7 +14,8 @@ Deliberate differences, all stated where they apply:
   * outputs are float32 GeoTIFFs (WhiteboxTools writes float64 and pydrodem narrows them right
     away with `pyct.tifdowncast`, tools/depressions.py:1306); D8 pointers are int16 with -32768 on
     nodata cells as WhiteboxTools writes them.
-  * breach_depressions / breach_depressions_least_cost are not built yet.
+  * breach_depressions runs its priority-order part on the host (csrc/breach.cu) and the closing fill on the GPU;
+    breach_depressions_least_cost is not built.
 """
 import numpy as np
 
@@ -107,12 +108,19 @@ class WhiteboxToolsGPU:
         raster_io.write_raster(output, a, meta, nodata=-32768.0)
         return 0
 
-    # -- not on the GPU path yet --------------------------------------------------------------------
+    # -- breach (tools/depressions.py:1376-1380, :1012-1014) ------------------------------------------
     def breach_depressions(self, dem, output, max_depth=None, max_length=None, flat_increment=None, fill_pits=False,
                            callback=None):
-        raise NotImplementedError("breach_depressions (Lindsay 2016) is scheduled after the bandwidth-bound passes "
-                                  "(SURVEY.md §8f-3); it is not built yet")
+        """Lindsay (2016) constrained breaching + fill of the rest; see core.breach_depressions for what runs where"""
+        z, meta, nodata = self._load(dem)
+        out = core.breach_depressions(np.asarray(z, np.float32), nodata=nodata, max_length=max_length,
+                                      max_depth=max_depth, fill_pits=fill_pits, flat_increment=flat_increment)
+        raster_io.write_raster(output, out, meta, nodata=nodata)
+        self._say("breach_depressions ->", output)
+        return 0
 
+    # -- not built ----------------------------------------------------------------------------------
     def breach_depressions_least_cost(self, dem, output, dist, max_cost=None, min_dist=True, flat_increment=None,
                                       fill=True, callback=None):
-        raise NotImplementedError("breach_depressions_least_cost is not built yet (SURVEY.md §8f-3)")
+        raise NotImplementedError("breach_depressions_least_cost (Lindsay & Dhun 2015) is not built; pydrodem's "
+                                  "default carve method is 'SC' = breach_depressions (tools/depressions.py:1320)")

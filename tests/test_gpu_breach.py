@@ -1,0 +1,68 @@
+"""Breach through the product API: host priority-order part (csrc/breach.cu) + GPU fill of what is left."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from pydrodem_b200 import _lib, synth
+
+ND = -9999.0
+
+
+def host_breach(z, max_length=0, max_depth=0.0, fill_pits=True, do_fill=True):
+    z = np.ascontiguousarray(z, np.float32)
+    out = np.empty_like(z)
+    st = (ctypes.c_int64 * 5)()
+    assert _lib.load().hc_breach_depressions_host(z.ctypes.data, out.ctypes.data, z.shape[0], z.shape[1], ND, max_length,
+                                                  max_depth, int(fill_pits), int(do_fill), st) == 0
+    return out, list(st)
+
+
+def scene(ny, nx, seed):
+    rng = np.random.default_rng(seed)
+    z = (synth.make_dem_numpy(ny, nx, seed) * 0.02).astype(np.float32)
+    z += rng.integers(0, 3, z.shape).astype(np.float32)
+    z[:2, :] = ND
+    z[:, -3:] = ND
+    z[ny // 2:ny // 2 + 5, nx // 3:nx // 3 + 7] = ND      # interior hole: neither a seed nor crossed
+    return z
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ny,nx,seed,ml", [(120, 150, 1, 10), (257, 190, 2, 0), (64, 300, 3, 3)])
+def test_gpu_fill_of_the_cut_surface_equals_host_fill(ny, nx, seed, ml):
+    import torch
+    import pydrodem_b200 as hc
+    z = scene(ny, nx, seed)
+    want, st = host_breach(z, max_length=ml, fill_pits=True, do_fill=True)
+    got, stats = hc.breach_depressions(z, nodata=ND, max_length=ml or None, fill_pits=True, return_stats=True)
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    assert [stats["pits"], stats["breached"], stats["left_to_fill"], stats["cells_lowered"]] == st[:4]
+    dev = hc.breach_depressions(torch.from_numpy(z).cuda(), nodata=ND, max_length=ml or None, fill_pits=True)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), want)
+    assert np.array_equal(hc.fill(got, nodata=ND, seed_mode=hc.SEED_WBT), got)       # depression free
+    with pytest.raises(NotImplementedError):
+        hc.breach_depressions(z, flat_increment=0.001)
+
+
+@pytest.mark.gpu
+def test_wbt_and_breach_pits_file_protocol(tmp_path):
+    from pydrodem_b200 import raster_io
+    from pydrodem_b200.tools import depressions as dep
+    from pydrodem_b200.wbt import WhiteboxToolsGPU
+    z = scene(90, 110, 4)
+    dem_tif = str(tmp_path / "unit.tif")
+    raster_io.write_raster(dem_tif, z, None, nodata=ND)
+    wbt = WhiteboxToolsGPU()
+    carve, diff = dep.breach_pits(dem_tif, 12, 200, wbt, nodataval=ND)
+    want, _ = host_breach(z, max_length=12, fill_pits=True, do_fill=True)
+    assert np.array_equal(carve, want)
+    assert np.array_equal(diff, np.round(want - z, 3))
+    assert os.path.exists(str(tmp_path / "unit_SC_12.tif")) and os.path.exists(str(tmp_path / "unit_SC_12_DIFF.tif"))
+    # cached: an existing carve raster is re-used, not recomputed (tools/depressions.py:1369)
+    raster_io.write_raster(str(tmp_path / "unit_SC_12.tif"), z, None, nodata=ND)
+    carve2, diff2 = dep.breach_pits(dem_tif, 12, 200, wbt, nodataval=ND)
+    assert np.array_equal(carve2, z) and not diff2.any()
+    with pytest.raises(NotImplementedError):
+        dep.breach_pits(dem_tif, 13, 200, wbt, method='LC')
