@@ -60,10 +60,93 @@ k_mm_v(const T *__restrict__ in, T *__restrict__ out, int ny, int nx, int lo, in
   out[(size_t)r * nx + c] = v;
 }
 
+// Shared-memory form of the two passes (windows up to a few hundred cells): a block stages its span plus the k - 1 halo
+// cells once, then builds "minimum of the next 2^j cells" tables by doubling (log2 k steps of one op per cell, ping-pong
+// between two buffers); a window of k cells is the op of two overlapping 2^p spans (p = floor(log2 k)).  ~3 log2 k
+// shared-memory accesses per cell instead of k loads, and every input cell is read from global memory once per pass
+// (plus the halo).  Tail cells whose span would leave the staged range are never a dependency of a stored result.
+#define MMH_W 2048      // outputs per block, horizontal pass
+#define MMV_R 128       // output rows per block, vertical pass
+
+template <typename T, bool IS_MAX>
+__global__ void __launch_bounds__(256)
+k_mm_h_sm(const T *__restrict__ in, T *__restrict__ out, int ny, int nx, int lo, int k) {
+  extern __shared__ __align__(16) unsigned char mm_smem[];
+  const int len = MMH_W + k - 1;
+  T *cur = (T *)mm_smem, *nxt = cur + len;
+  const int c0 = blockIdx.x * MMH_W, r = blockIdx.y;
+  const T *row = in + (size_t)r * nx;
+  for (int i = threadIdx.x; i < len; i += 256) cur[i] = row[wsymm(c0 - lo + i, nx)];
+  __syncthreads();
+  int P = 1;
+  for (int s = 1; 2 * s <= k; s *= 2) {
+    for (int i = threadIdx.x; i < len; i += 256) nxt[i] = mm_op<T, IS_MAX>(cur[i], cur[min(i + s, len - 1)]);
+    __syncthreads();
+    T *t = cur; cur = nxt; nxt = t;
+    P = 2 * s;
+  }
+  for (int j = threadIdx.x; j < MMH_W && c0 + j < nx; j += 256)
+    out[(size_t)r * nx + c0 + j] = mm_op<T, IS_MAX>(cur[j], cur[j + k - P]);
+}
+
+// TC columns x MMV_R rows per block; threads (TC, 256 / TC): shared-memory rows are TC cells wide, so the doubling
+// along rows is conflict free
+template <typename T, bool IS_MAX, int TC>
+__global__ void __launch_bounds__(256)
+k_mm_v_sm(const T *__restrict__ in, T *__restrict__ out, int ny, int nx, int lo, int k) {
+  extern __shared__ __align__(16) unsigned char mm_smem[];
+  const int L = MMV_R + k - 1, TY = 256 / TC;
+  T *cur = (T *)mm_smem, *nxt = cur + (size_t)L * TC;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * TC + tx, r0 = blockIdx.y * MMV_R;
+  const bool live = c < nx;
+  for (int rr = ty; rr < L; rr += TY)
+    cur[rr * TC + tx] = live ? in[(size_t)wsymm(r0 - lo + rr, ny) * nx + c] : (T)0;
+  __syncthreads();
+  int P = 1;
+  for (int s = 1; 2 * s <= k; s *= 2) {
+    for (int rr = ty; rr < L; rr += TY)
+      nxt[rr * TC + tx] = mm_op<T, IS_MAX>(cur[rr * TC + tx], cur[min(rr + s, L - 1) * TC + tx]);
+    __syncthreads();
+    T *t = cur; cur = nxt; nxt = t;
+    P = 2 * s;
+  }
+  if (!live) return;
+  for (int j = ty; j < MMV_R && r0 + j < ny; j += TY)
+    out[(size_t)(r0 + j) * nx + c] = mm_op<T, IS_MAX>(cur[j * TC + tx], cur[(j + k - P) * TC + tx]);
+}
+
+#define MM_SMEM_MAX (96 * 1024)
+
 // square window of `size` cells, scipy's origin convention: [i - size/2, i + size - 1 - size/2]
 template <typename T>
 static int mm_filter(hc_ctx *ctx, const T *in, T *out, T *tmp, int ny, int nx, int size, int is_max, cudaStream_t st) {
   int lo = size / 2, hi = size - 1 - size / 2;
+  constexpr int TC = sizeof(T) == 1 ? 128 : 32;
+  size_t smem_h = 2 * (size_t)(MMH_W + size - 1) * sizeof(T);
+  size_t smem_v = 2 * (size_t)(MMV_R + size - 1) * TC * sizeof(T);
+  if (smem_h <= MM_SMEM_MAX && smem_v <= MM_SMEM_MAX && ny <= 65535 * MMV_R) {
+    // (per device and cheap: set on every call rather than cached, a process may drive several devices)
+    if (is_max) {
+      HC_CUDA(cudaFuncSetAttribute(k_mm_h_sm<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_MAX));
+      HC_CUDA(cudaFuncSetAttribute(k_mm_v_sm<T, true, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_MAX));
+    } else {
+      HC_CUDA(cudaFuncSetAttribute(k_mm_h_sm<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_MAX));
+      HC_CUDA(cudaFuncSetAttribute(k_mm_v_sm<T, false, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_MAX));
+    }
+    dim3 gh((unsigned)((nx + MMH_W - 1) / MMH_W), (unsigned)ny);
+    dim3 bv(TC, 256 / TC), gv((unsigned)((nx + TC - 1) / TC), (unsigned)((ny + MMV_R - 1) / MMV_R));
+    HC_PROF(ctx, st, "k_mm_h_sm");
+    if (is_max) k_mm_h_sm<T, true><<<gh, 256, smem_h, st>>>(in, tmp, ny, nx, lo, size);
+    else k_mm_h_sm<T, false><<<gh, 256, smem_h, st>>>(in, tmp, ny, nx, lo, size);
+    HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_mm_v_sm");
+    if (is_max) k_mm_v_sm<T, true, TC><<<gv, bv, smem_v, st>>>(tmp, out, ny, nx, lo, size);
+    else k_mm_v_sm<T, false, TC><<<gv, bv, smem_v, st>>>(tmp, out, ny, nx, lo, size);
+    HC_LAUNCH_CHECK(ctx);
+    return HC_OK;
+  }
+  // very large windows: direct form
   dim3 gh((unsigned)((nx + 255) / 256), (unsigned)ny);
   dim3 bv(64, 16), gv((unsigned)((nx + 63) / 64), (unsigned)((ny + 15) / 16));
   HC_PROF(ctx, st, "k_mm_h");
@@ -115,10 +198,17 @@ k_conv_f64(const float *__restrict__ in, float *__restrict__ out, int ny, int nx
   int ry = kh / 2, rx = kw / 2;
   double acc = 0.0;
   // out[r, c] = sum_{a, b} kern[a, b] * in[r + ry - a, c + rx - b]  (true convolution: the kernel is flipped)
-  for (int a = 0; a < kh; a++) {
-    const float *row = in + (size_t)wsymm(r + ry - a, ny) * nx;
-    for (int b = 0; b < kw; b++)
-      acc = __dadd_rn(acc, __dmul_rn(c_wkern[a * kw + b], (double)row[wsymm(c + rx - b, nx)]));
+  if (r >= ry && r + ry < ny && c >= rx && c + rx < nx) {   // interior: same taps in the same order, no reflection
+    for (int a = 0; a < kh; a++) {
+      const float *row = in + (size_t)(r + ry - a) * nx + c + rx;
+      for (int b = 0; b < kw; b++) acc = __dadd_rn(acc, __dmul_rn(c_wkern[a * kw + b], (double)row[-b]));
+    }
+  } else {
+    for (int a = 0; a < kh; a++) {
+      const float *row = in + (size_t)wsymm(r + ry - a, ny) * nx;
+      for (int b = 0; b < kw; b++)
+        acc = __dadd_rn(acc, __dmul_rn(c_wkern[a * kw + b], (double)row[wsymm(c + rx - b, nx)]));
+    }
   }
   out[(size_t)r * nx + c] = (float)acc;
 }
