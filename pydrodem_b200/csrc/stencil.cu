@@ -451,11 +451,13 @@ k_box3_index(const float *__restrict__ in, const uint8_t *__restrict__ in_zero, 
              double w, float zero_above, int32_t *__restrict__ idx, float *__restrict__ smooth) {
   int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
   if (c >= nx) return;
-  int cl = symm(c - 1, nx), cr = symm(c + 1, nx);
+  // (interior cells skip the reflection arithmetic; same taps, same order)
+  const bool inner = r > 0 && r + 1 < ny && c > 0 && c + 1 < nx;
+  int cl = inner ? c - 1 : symm(c - 1, nx), cr = inner ? c + 1 : symm(c + 1, nx);
   double acc = 0.0;
 #pragma unroll
   for (int dr = -1; dr <= 1; dr++) {
-    size_t o = (size_t)symm(r + dr, ny) * nx;
+    size_t o = (size_t)(inner ? r + dr : symm(r + dr, ny)) * nx;
     int cc[3] = {cl, c, cr};
 #pragma unroll
     for (int k = 0; k < 3; k++) {

@@ -87,7 +87,8 @@ def test_catalog_api_fails_loudly_without_cuda():
 def test_golden_files_are_present_and_described():
     g = os.path.join(ROOT, "tests", "golden")
     for f, gen in (("stencils_reference.npz", "make_stencil_golden.py"), ("catalog_reference.npz", "make_catalog_golden.py"),
-                   ("oracle_hashes.json", "make_golden.py")):
+                   ("oracle_hashes.json", "make_golden.py"), ("veg_reference.npz", "make_veg_golden.py"),
+                   ("water_reference.npz", "make_water_golden.py")):
         assert os.path.exists(os.path.join(g, f)) and os.path.exists(os.path.join(g, gen)), f
     d = np.load(os.path.join(g, "catalog_reference.npz"))
     codes = set()
@@ -95,3 +96,52 @@ def test_golden_files_are_present_and_described():
         if k.endswith("_solution"):
             codes |= set(int(v) for v in np.unique(d[k]))
     assert {1, 7, 1002, 1006, 1200, 2000, 2004, 2006, 2009, 2100, 4000} <= codes
+
+
+def test_fix_shifted_data_repairs_a_whole_raster_shift():
+    """tools/depressions.py:1406-1468: a WhiteboxTools output shifted by (+1, +2) cells is moved back and the
+    rounded difference map rebuilt; an unshifted raster passes through"""
+    from pydrodem_b200.tools import depressions as dep
+    rng = np.random.default_rng(0)
+    nd = -9999.0
+    z = np.full((12, 15), nd, np.float32)
+    z[2:9, 3:11] = rng.random((7, 8)).astype(np.float32) * 10
+    filled = z.copy()
+    filled[4:6, 5:8] += 1.25
+    shifted = np.full_like(z, nd)
+    shifted[3:10, 5:13] = filled[2:9, 3:11]
+    out, diff = dep.fix_shifted_data(z, shifted.copy(), nd)
+    assert np.array_equal(out, filled)
+    assert np.array_equal(diff, np.round(filled - z, 3)) and diff.max() == 1.25
+    out2, diff2 = dep.fix_shifted_data(z, filled.copy(), nd)
+    assert np.array_equal(out2, filled) and np.array_equal(diff2, diff)
+
+
+def test_water_veg_and_breach_apis_fail_loudly_without_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("only meaningful on a box without a GPU")
+    from pydrodem_b200 import veg
+    from pydrodem_b200.tools import water
+    z = np.zeros((6, 7), np.float32)
+    m = np.zeros((6, 7), np.uint8)
+    for call in (lambda: water.river_minimize(z, m, m), lambda: water.raise_small_streams(z, z.copy(), m, -9999),
+                 lambda: water.minimum_filter(z, 5), lambda: veg.box3_index(m),
+                 lambda: veg.compute_veg_bias_3D(m, m, z, np.zeros((101, 5, 20)), 30.0, 30.0)):
+        with pytest.raises((RuntimeError, AssertionError)):      # torch refuses .cuda(); nothing computes on the CPU
+            call()
+    import pydrodem_b200 as hc
+    with pytest.raises(Exception):                               # the closing fill needs the GPU: no host substitute
+        hc.breach_depressions(z)
+
+
+def test_window_meta_shifts_the_tiepoint_only():
+    from pydrodem_b200 import raster_io
+    from pydrodem_b200.tools.depressions import _window_meta
+    meta = raster_io.RasterMeta({"nodata": -9999.0, "geo": {33550: (12, [30.0, 30.0, 0.0]),
+                                                            33922: (12, [0.0, 0.0, 0.0, 500000.0, 4100000.0, 0.0])}})
+    w = _window_meta(meta, 10, 4)
+    assert list(w["geo"][33922][1]) == [0.0, 0.0, 0.0, 500000.0 + 4 * 30.0, 4100000.0 - 10 * 30.0, 0.0]
+    assert list(meta["geo"][33922][1])[3:5] == [500000.0, 4100000.0] and w["nodata"] == -9999.0
+    assert _window_meta(None, 3, 3).get("geo") == {}
