@@ -434,3 +434,64 @@ def label_banded(mask, nbands, conn=8):
     finally:
         bl.close()
     return (out.cpu().numpy(), n) if host else (out, n)
+
+
+# ---- local-window functions over row bands (SURVEY.md §8e "smoothing stencils: bands + halo rows") ----------------
+# Any function whose output at a cell depends only on cells within `halo` rows (water stencils, vegetation bias,
+# convolutions, moving min/max) shards trivially: give every band `halo` extra rows from its neighbours, run the
+# function on the halo'd rasters, keep the own rows.  At the raster's top / bottom the band edge IS the raster edge, so
+# the function's own boundary rule (scipy's reflect) applies unchanged -- the stitched result is bit-identical.
+def apply_banded(fn, rasters, nbands, halo, out_index=None):
+    """Single-process emulation (N bands on one GPU, as the parity tests of the chain do).  `rasters`: 2-D arrays /
+    tensors of equal shape, `fn(*band_rasters)` -> raster or tuple of rasters.  Returns the stitched result(s)."""
+    ny = rasters[0].shape[0]
+    rows = split_rows(ny, nbands)
+    if nbands > 1 and min(rows) < halo:
+        raise ValueError("bands must be at least `halo` rows tall")
+    outs, r0 = [], 0
+    for i, nb in enumerate(rows):
+        a, b = max(0, r0 - halo) if i > 0 else r0, min(ny, r0 + nb + halo) if i < nbands - 1 else r0 + nb
+        res = fn(*[_band_copy(x[a:b]) for x in rasters])
+        res = res if isinstance(res, tuple) else (res,)
+        outs.append(tuple(o[r0 - a:r0 - a + nb] for o in res))
+        r0 += nb
+    cat = [_cat([o[k] for o in outs]) for k in range(len(outs[0]))]
+    return cat[0] if len(cat) == 1 else tuple(cat)
+
+
+def _band_copy(x):
+    return x.clone() if hasattr(x, "clone") else x.copy()
+
+
+def _cat(parts):
+    if hasattr(parts[0], "is_cuda") or hasattr(parts[0], "clone"):
+        import torch
+        return torch.cat(parts)
+    import numpy as np
+    return np.concatenate(parts)
+
+
+def apply_rank(fn, own_rasters, halo, comm=None):
+    """One band per rank: `own_rasters` = this rank's rows of every raster (torch tensors, CPU over gloo or CUDA over
+    NCCL).  ONE all_gather per raster carries every band's first / last `halo` rows; the function runs on the halo'd
+    band and the own rows of its result(s) are returned."""
+    import torch
+    comm = comm if comm is not None else SeamComm()
+    world = comm.world
+    rank = comm.dist.get_rank(comm.group) if world > 1 else 0
+    nb = own_rasters[0].shape[0]
+    if world > 1 and nb < halo:
+        raise ValueError("bands must be at least `halo` rows tall")
+    haloed = []
+    for x in own_rasters:
+        if world == 1:
+            haloed.append(x)
+            continue
+        edge = torch.stack((x[:halo], x[nb - halo:])).unsqueeze(0).contiguous()   # [1, 2, halo, nx]
+        alle = comm.gather(edge)
+        parts = ([alle[rank - 1, 1]] if rank > 0 else []) + [x] + ([alle[rank + 1, 0]] if rank < world - 1 else [])
+        haloed.append(torch.cat(parts))
+    res = fn(*haloed)
+    top = halo if rank > 0 else 0
+    crop = lambda o: o[top:top + nb]  # noqa: E731
+    return tuple(crop(o) for o in res) if isinstance(res, tuple) else crop(res)

@@ -124,3 +124,17 @@ def smooth_rivers(inDEM_array, DEM_burn_arr, water_mask_array, SWO_array, nodata
     _call("hc_smooth_rivers_dev", burn.device, _tp(dem), _tp(burn), _tp(wm), _tp(swo), float(nodata), int(SWO_cut),
           float(np.float32(max_lower)), int(filter_size), burn.shape[0], burn.shape[1], _stream(burn))
     return _finish_inplace(DEM_burn_arr, burn)
+
+
+def halo_rows(name, **kw):
+    """Rows of halo a row band needs for `name` to give the whole-raster result on its own rows (the dependency
+    radius of the chain: mask dilations + 5x5 mean + moving window), for bands.apply_banded / apply_rank."""
+    if name == "river_minimize":
+        return 1 + int(kw.get("river_filter_size", 3)) // 2
+    if name == "raise_small_rivers":
+        return int(kw.get("filter_size", 51)) // 2
+    if name == "raise_small_streams":
+        return 2 + int(kw.get("fsize", 51)) // 2
+    if name == "smooth_rivers":
+        return 2 + int(kw.get("filter_size", 21)) // 2
+    raise KeyError(name)

@@ -22,6 +22,7 @@ from .core import _is_torch, _stream, _tdev, _tp
 
 SLOPE_CAP_3D = 19   # models/dem_noise_removal.py:792
 SLOPE_CAP_2D = 50   # :616
+HALO_ROWS = 5       # 9x9 smoothing (4) + central-difference slope (1): halo of a row band (bands.apply_banded)
 
 
 def load_bias_cube(lookup_table):

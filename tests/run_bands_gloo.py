@@ -358,6 +358,24 @@ def main():
         if not np.array_equal(out, want[r0:r0 + nb]) or int(counts.sum()) != nwant:
             ok = False
             print(f"rank {rank} seed {seed}: banded label model differs (rounds {rounds})", flush=True)
+    # ---- local-window functions over bands: apply_rank's halo exchange (CPU stand-in functions) ----
+    rng = np.random.default_rng(99)
+    ny, nx = 61, 23
+    full = rng.random((ny, nx)).astype(np.float32)
+    fullm = (rng.random((ny, nx)) < 0.08).astype(np.uint8)
+    rows = bands.split_rows(ny, world)
+    r0 = sum(rows[:rank])
+
+    def fn(a, b):
+        return (torch.from_numpy(ndimage.minimum_filter(a.numpy(), size=15)),
+                torch.from_numpy(ndimage.maximum_filter(b.numpy(), size=7)))
+    got = bands.apply_rank(fn, [torch.from_numpy(full[r0:r0 + rows[rank]].copy()),
+                                torch.from_numpy(fullm[r0:r0 + rows[rank]].copy())], 7, comm)
+    want = (ndimage.minimum_filter(full, size=15), ndimage.maximum_filter(fullm, size=7))
+    for g, w in zip(got, want):
+        if not np.array_equal(g.numpy(), w[r0:r0 + rows[rank]]):
+            ok = False
+            print(f"rank {rank}: apply_rank differs from the whole-raster filter", flush=True)
     anybad = comm.any(not ok, torch.device("cpu"))
     assert comm.any(rank == 1, torch.device("cpu")) is True and comm.any(False, torch.device("cpu")) is False
     if rank == 0:

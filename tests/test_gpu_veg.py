@@ -106,3 +106,16 @@ def test_compute_veg_bias_3D_refuses_unfilled_treecover(gold):
     tc[10:20, 10:20] = 255
     with pytest.raises(NotImplementedError):
         veg.compute_veg_bias_3D(tc, gold["Theight"], gold["Zarr"], gold["bias_cube"], 30.0, 30.0)
+
+
+@pytest.mark.gpu
+def test_veg_bias_over_row_bands(gold):
+    from pydrodem_b200 import bands, veg
+    edm = gold["edm"]
+    ocean = np.where(edm == 4, 1, 0).astype(np.uint8)
+    dx, dy = float(gold["dx"]), float(gold["dy"])
+    whole = veg.compute_veg_bias_3D(gold["TC"], gold["Theight"], gold["Zarr"], gold["bias_cube"], dx, dy, ocean_mask=ocean)
+    got = bands.apply_banded(lambda tc, th, z, oc: veg.compute_veg_bias_3D(tc, th, z, gold["bias_cube"], dx, dy,
+                                                                            ocean_mask=oc)[:2],
+                             [gold["TC"], gold["Theight"], gold["Zarr"], ocean], 3, veg.HALO_ROWS)
+    assert np.array_equal(got[0], whole[0]) and np.array_equal(got[1], whole[1])

@@ -134,3 +134,25 @@ def test_conv_f64_matches_reference_float64_path(gold):
                                                   a.shape[0], a.shape[1], None), "hc_conv2d_symm_f64_dev")
     torch.cuda.synchronize()
     assert np.allclose(out.cpu().numpy(), want, rtol=2.4e-7, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nbands", [2, 3])
+def test_water_stencils_over_row_bands(gold, nbands):
+    """bands + halo rows: each band runs the whole-raster function on its rows plus
+    water.halo_rows(...) rows of its neighbours; the stitched result is bit-identical"""
+    from pydrodem_b200 import bands
+    from pydrodem_b200.tools import water
+    dem, burn, wm, swo = _scene(gold, "a")
+    got = bands.apply_banded(lambda b, w, s: water.river_minimize(b, w, s, 2, 5), [burn, wm, swo], nbands,
+                             water.halo_rows("river_minimize", river_filter_size=5))
+    assert np.array_equal(got, gold["a_rm_call"])
+    got = bands.apply_banded(lambda d, b, w: water.raise_small_streams(d, b, w, -9999), [dem, burn, wm], nbands,
+                             water.halo_rows("raise_small_streams"))
+    assert np.array_equal(got, gold["a_rss_default"])
+    got = bands.apply_banded(lambda d, b, w, s: water.raise_small_rivers(d, b, w, s, -9999, filter_size=31),
+                             [dem, burn, wm, swo], nbands, water.halo_rows("raise_small_rivers", filter_size=31))
+    assert np.array_equal(got, water.raise_small_rivers(dem, burn.copy(), wm, swo, -9999, filter_size=31))
+    got = bands.apply_banded(lambda d, b, w, s: water.smooth_rivers(d, b, w, s, -9999), [dem, burn, wm, swo], nbands,
+                             water.halo_rows("smooth_rivers"))
+    assert np.array_equal(got, gold["a_sr_default"])
