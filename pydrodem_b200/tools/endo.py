@@ -90,3 +90,25 @@ def find_sink_pixel(raster_array, SWO_array=None, geotransform=(0.0, 1.0, 0.0, 0
     d2 = (xs - xs.sum() / len(xs)) ** 2 + (ys - ys.sum() / len(ys)) ** 2
     j = int(torch.nonzero(d2 == d2.min())[0])
     return int(ties[j, 0]), int(ties[j, 1])
+
+
+# ---- the scalar geometry around the sink pixel (tools/endo.py:158-250): host arithmetic on two numbers ----
+def get_xy(r, c, gt):
+    """centre coordinate of raster cell (r, c) for GDAL geotransform `gt` (tools/endo.py:197-215)"""
+    x0, dx, rx, y0, ry, dy = gt
+    return (x0 + c * dx + dx / 2.0, y0 + r * dy + dy / 2.0)
+
+
+def coords_to_pixel(x, y, dx, dy, xmin, ymax):
+    """(col, row) of a coordinate; dy is the geotransform's (negative) row step (tools/endo.py:218-250)"""
+    col = int((x - xmin) / dx)
+    row = int((y - ymax) / dy)
+    return col, row
+
+
+def set_nodata_points(point_xy, raster_array, dx, dy, xmin, ymax, nodata, set_buffer=False):
+    """tools/endo.py:158-194 with the point given as (x, y) instead of a one-row GeoDataFrame: the sink pixel becomes
+    nodata (in place for a numpy array or a CUDA tensor; `set_buffer` is unused upstream too)."""
+    col, row = coords_to_pixel(point_xy[0], point_xy[1], dx, dy, xmin, ymax)
+    raster_array[row][col] = nodata
+    return raster_array

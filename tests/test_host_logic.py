@@ -145,3 +145,13 @@ def test_window_meta_shifts_the_tiepoint_only():
     assert list(w["geo"][33922][1]) == [0.0, 0.0, 0.0, 500000.0 + 4 * 30.0, 4100000.0 - 10 * 30.0, 0.0]
     assert list(meta["geo"][33922][1])[3:5] == [500000.0, 4100000.0] and w["nodata"] == -9999.0
     assert _window_meta(None, 3, 3).get("geo") == {}
+
+
+def test_sink_pixel_geometry_round_trip():
+    from pydrodem_b200.tools import endo
+    gt = (12.5, 0.000277, 0.0, 45.25, 0.0, -0.000277)
+    x, y = endo.get_xy(17, 41, gt)
+    assert endo.coords_to_pixel(x, y, gt[1], gt[5], gt[0], gt[3]) == (41, 17)
+    a = np.zeros((30, 50), np.float32)
+    out = endo.set_nodata_points((x, y), a, gt[1], gt[5], gt[0], gt[3], -9999)
+    assert out is a and a[17, 41] == -9999 and np.count_nonzero(a) == 1
