@@ -298,6 +298,15 @@ int hc_fill_d8_accum_host(hc_ctx *ctx, const float *z, float *filled, uint8_t *d
                           int seed_mode, int table, int resolve_flats);
 int hc_label_host(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn,
                   int32_t *nlab);
+/* The same chain as a begin / end pair, for a stream of units (the reference processes a region as many tiles /
+ * basins, run_local.py:636-677): `begin` uploads, computes and queues the result copies of one unit into PINNED
+ * host buffers; `end` waits for them.  slot = 0 or 1 selects one of two device staging sets, so begin(1) may be
+ * called before end(0): one unit's results travel over PCIe while the next is uploaded and computed.  The host
+ * buffers of a slot must not be touched between its begin and end. */
+int hc_fill_d8_accum_host_begin(hc_ctx *ctx, int slot, const float *z, float *filled, uint8_t *dir, float *slope,
+                                uint32_t *acc, int64_t ny, int64_t nx, float nodata, double dx, double dy,
+                                int seed_mode, int table, int resolve_flats);
+int hc_fill_d8_accum_host_end(hc_ctx *ctx, int slot);
 
 /* Per-kernel timing with CUDA events on the launching stream (what bench.py's roofline line is
  * computed from).  enable(on=1) starts logging every launch; read() synchronises, writes one line

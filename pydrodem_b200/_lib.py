@@ -65,6 +65,9 @@ SIGNATURES = {
     "hc_fill_d8_accum_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64,
                                              c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "hc_label_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32)]),
+    "hc_fill_d8_accum_host_begin": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32,
+                                                   c_f64, c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "hc_fill_d8_accum_host_end": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "hc_band_fill_edge_cap": (c_i64, [c_i64]),
     "hc_band_fill_local_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, ctypes.c_int, c_i64, c_vp,
                                               c_vp, c_vp]),

@@ -158,6 +158,9 @@ extern "C" int hc_create(hc_ctx **out, int device) {
   HC_CUDA(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fill, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_dir, cudaEventDisableTiming));
+  HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_acc, cudaEventDisableTiming));
+  HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[0], cudaEventDisableTiming));
+  HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[1], cudaEventDisableTiming));
   HC_CUDA(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -170,12 +173,14 @@ extern "C" int hc_destroy(hc_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < ctx->n_blocks; i++) cudaFree(ctx->blocks[i].p);
-  for (int i = 0; i < 5; i++) if (ctx->io[i]) cudaFree(ctx->io[i]);
+  for (int i = 0; i < 10; i++) if (ctx->io[i]) cudaFree(ctx->io[i]);
   if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
   if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   if (ctx->ev_fill) cudaEventDestroy(ctx->ev_fill);
   if (ctx->ev_dir) cudaEventDestroy(ctx->ev_dir);
+  if (ctx->ev_acc) cudaEventDestroy(ctx->ev_acc);
+  for (int i = 0; i < 2; i++) if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
   if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -302,24 +307,33 @@ extern "C" int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny,
   return HC_OK;
 }
 
-extern "C" int hc_fill_d8_accum_host(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope,
-                                     uint32_t *acc, int64_t ny, int64_t nx, float nodata, double dx, double dy,
-                                     int seed_mode, int table, int resolve_flats) {
+// Begin / end form of the host chain: `begin` copies the DEM in, runs the chain and QUEUES the device->host copies of
+// the results; `end` waits until the slot's last copy has landed.  Two slots (0 / 1) own separate device staging
+// buffers, so begin(slot ^ 1) may be called before end(slot): the PCIe link carries one unit's results (9 B/cell)
+// while the next unit is uploaded (other direction) and computed.  Host buffers must be pinned for the overlap to
+// happen and must stay untouched until `end`.
+extern "C" int hc_fill_d8_accum_host_begin(hc_ctx *ctx, int slot, const float *z, float *filled, uint8_t *dir,
+                                           float *slope, uint32_t *acc, int64_t ny, int64_t nx, float nodata,
+                                           double dx, double dy, int seed_mode, int table, int resolve_flats) {
   CHECK_CTX(ctx);
   HC_TRY(check_shape(ny, nx));
+  if (slot != 0 && slot != 1) { hc_set_error("hc_fill_d8_accum_host_begin: slot must be 0 or 1"); return HC_ERR_ARG; }
   size_t n = (size_t)ny * nx;
   if (!n) return HC_OK;
   if (!z || !filled || !dir || !acc) { hc_set_error("hc_fill_d8_accum_host: null pointer"); return HC_ERR_ARG; }
   if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("bad seed_mode"); return HC_ERR_ARG; }
   if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("bad table"); return HC_ERR_ARG; }
-  dev_buf dz(ctx, 0), df(ctx, 1), dd(ctx, 2), ds(ctx, 3), da(ctx, 4);
+  // the slot's staging buffers may still be the source of the copies of the call that used it last
+  HC_CUDA(cudaEventSynchronize(ctx->ev_done[slot]));
+  const int b = 5 * slot;
+  dev_buf dz(ctx, b + 0), df(ctx, b + 1), dd(ctx, b + 2), ds(ctx, b + 3), da(ctx, b + 4);
   HC_TRY(dz.alloc(n * 4));
   HC_TRY(df.alloc(n * 4));
   HC_TRY(dd.alloc(n));
   if (slope) HC_TRY(ds.alloc(n * 4));
   HC_TRY(da.alloc(n * 4));
-  // compute on one stream, device->host copies on another: the filled raster travels while D8 / flats run,
-  // the direction raster while the accumulation runs (the PCIe link, not the kernels, bounds this entry point)
+  // compute on one stream, device->host copies on another: the filled raster travels while D8 / flats run, the
+  // direction raster while the accumulation runs (the PCIe link, not the kernels, bounds this entry point)
   cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
   HC_CUDA(cudaMemcpyAsync(dz.p, z, n * 4, cudaMemcpyHostToDevice, sc));
   HC_TRY(fill_run(ctx, (const float *)dz.p, (float *)df.p, ny, nx, nodata, seed_mode, sc));
@@ -333,10 +347,26 @@ extern "C" int hc_fill_d8_accum_host(hc_ctx *ctx, const float *z, float *filled,
   HC_CUDA(cudaMemcpyAsync(dir, dd.p, n, cudaMemcpyDeviceToHost, sx));
   if (slope) HC_CUDA(cudaMemcpyAsync(slope, ds.p, n * 4, cudaMemcpyDeviceToHost, sx));
   HC_TRY(accum_run(ctx, (const uint8_t *)dd.p, (uint32_t *)da.p, ny, nx, table, sc));
-  HC_CUDA(cudaMemcpyAsync(acc, da.p, n * 4, cudaMemcpyDeviceToHost, sc));
-  HC_CUDA(cudaStreamSynchronize(sx));
-  HC_CUDA(cudaStreamSynchronize(sc));
+  HC_CUDA(cudaEventRecord(ctx->ev_acc, sc));
+  HC_CUDA(cudaStreamWaitEvent(sx, ctx->ev_acc, 0));
+  HC_CUDA(cudaMemcpyAsync(acc, da.p, n * 4, cudaMemcpyDeviceToHost, sx));
+  HC_CUDA(cudaEventRecord(ctx->ev_done[slot], sx));
   return HC_OK;
+}
+
+extern "C" int hc_fill_d8_accum_host_end(hc_ctx *ctx, int slot) {
+  CHECK_CTX(ctx);
+  if (slot != 0 && slot != 1) { hc_set_error("hc_fill_d8_accum_host_end: slot must be 0 or 1"); return HC_ERR_ARG; }
+  HC_CUDA(cudaEventSynchronize(ctx->ev_done[slot]));
+  return HC_OK;
+}
+
+extern "C" int hc_fill_d8_accum_host(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope,
+                                     uint32_t *acc, int64_t ny, int64_t nx, float nodata, double dx, double dy,
+                                     int seed_mode, int table, int resolve_flats) {
+  HC_TRY(hc_fill_d8_accum_host_begin(ctx, 0, z, filled, dir, slope, acc, ny, nx, nodata, dx, dy, seed_mode, table,
+                                     resolve_flats));
+  return hc_fill_d8_accum_host_end(ctx, 0);
 }
 
 extern "C" int hc_label_host(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn,

@@ -98,11 +98,12 @@ struct hc_ctx {
   hc_band_state band;
   band_label_state band_label;
   // grow-only device staging buffers of the *_host entry points (z, filled, dir, slope, acc)
-  void *io[5];
-  size_t io_cap[5];
+  void *io[10];        // [5 * slot + k]: two sets, so that one call's results can travel while the next call computes
+  size_t io_cap[10];
   // streams / events of the *_host chain: compute and device->host copies overlap
   cudaStream_t s_compute, s_copy;
   cudaEvent_t ev_fill, ev_dir;
+  cudaEvent_t ev_acc, ev_done[2];   // begin/end form of the host chain: accumulation ready; slot's last copy landed
   // auxiliary stream of the flat pass (light and window relaxation kernels run side by side)
   cudaStream_t s_aux;
   cudaEvent_t ev_fork, ev_join;
