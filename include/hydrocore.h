@@ -130,6 +130,10 @@ int hc_curvature_d2_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int
 int hc_mean_std_dev(hc_ctx *ctx, const float *x, int64_t n, double *mean, double *std, void *stream);
 /* partial sums of a row band for the global sigma: sums[0] = sum(x - shift), sums[1] = sum((x - shift)^2) (host) */
 int hc_sum_shifted_dev(hc_ctx *ctx, const float *x, int64_t n, double shift, double *sums, void *stream);
+/* TIFF LZW codec (host; TIFF 6.0 flavour with libtiff's early change) for the GeoTIFF wire format the reference uses
+ * (COMPRESS=LZW, tools/convert.py:202,312).  decode: *nout <= ndst bytes written.  encode: cap >= 2 * nsrc + 16. */
+int hc_lzw_decode_host(const uint8_t *src, int64_t nsrc, uint8_t *dst, int64_t ndst, int64_t *nout);
+int hc_lzw_encode_host(const uint8_t *src, int64_t nsrc, uint8_t *dst, int64_t cap, int64_t *nout);
 /* Depression breaching, Lindsay (2016): wbt.breach_depressions(dem, out, max_length=radius, max_depth=None,
  * fill_pits=True, flat_increment=0.0) as dep.breach_pits calls it (tools/depressions.py:1376-1380, :1012-1014).
  * HOST arithmetic (one global priority order, not a bandwidth-bound pass; no context needed):

@@ -3,8 +3,9 @@
 pydrodem hands rasters to WhiteboxTools / TauDEM as GeoTIFF paths written by `pyct.npy2tif`
 (tools/convert.py:128-169: one band, `SetNoDataValue`, geotransform + projection copied from a
 stencil).  GDAL is not available in this environment, so this module reads and writes the subset
-that protocol needs: classic or BigTIFF, little endian, one sample per pixel, uncompressed strips
-(or tiles on read), float32/float64/int16/uint8/int32/uint32, the GDAL_NODATA tag (42113) and the
+that protocol needs: classic or BigTIFF, little endian, one sample per pixel, strips (or tiles on read),
+uncompressed, LZW (what `pyct.tifcompress` / `tifdowncast` write, tools/convert.py:202,312; host codec in
+csrc/tiffcodec.cu) or deflate, predictors 1-3 on read, float32/float64/int16/uint8/int32/uint32, the GDAL_NODATA tag (42113) and the
 GeoTIFF georeferencing tags (33550 ModelPixelScale, 33922 ModelTiepoint, 34735-34737 GeoKeys), which
 are carried through verbatim.  Anything else raises.  `.npy` paths are accepted everywhere with a
 `<path>.json` side-car for nodata / georeferencing.
@@ -96,27 +97,40 @@ def read_raster(path):
         nx, ny = val(256)[0], val(257)[0]
         bits, spp = val(258, [1])[0], val(277, [1])[0]
         comp, fmtc = val(259, [1])[0], val(339, [1])[0]
-        if spp != 1 or comp != 1:
-            raise ValueError(f"{path}: need 1 band, uncompressed (got bands={spp}, compression={comp})")
+        pred = val(317, [1])[0]
+        if spp != 1 or comp not in (1, 5, 8, 32946) or pred not in (1, 2, 3):
+            raise ValueError(f"{path}: need 1 band, uncompressed / LZW / deflate (got bands={spp}, compression={comp}, "
+                             f"predictor={pred})")
         dtype = np.dtype(_SF[fmtc][bits])
         arr = np.empty((ny, nx), dtype)
+
+        def block(off, nbytes, rows, cols):
+            """one strip / tile: read, decompress, undo the predictor -> [rows, cols] array"""
+            f.seek(off)
+            raw = f.read(nbytes)
+            want = rows * cols * dtype.itemsize
+            if comp != 1:
+                raw = _decompress(raw, comp, want)
+            if len(raw) < want:
+                raise ValueError(f"{path}: short strip / tile ({len(raw)} of {want} bytes)")
+            return _unpredict(np.frombuffer(raw, np.uint8, want), pred, rows, cols, dtype)
+
         if 322 in tags:  # tiled
             tw, th = val(322)[0], val(323)[0]
-            offs = val(324)
+            offs, cnts = val(324), val(325)
             tx = (nx + tw - 1) // tw
-            for i, o in enumerate(offs):
-                f.seek(o)
-                t = np.frombuffer(f.read(tw * th * dtype.itemsize), dtype).reshape(th, tw)
+            for i, (o, c) in enumerate(zip(offs, cnts)):
+                t = block(o, c if comp != 1 else tw * th * dtype.itemsize, th, tw)
                 r0, c0 = (i // tx) * th, (i % tx) * tw
                 arr[r0:r0 + th, c0:c0 + tw] = t[:ny - r0, :nx - c0]
         else:
-            rps = val(278, [ny])[0]
+            rps = min(val(278, [ny])[0], ny)
             offs = val(273)
-            for i, o in enumerate(offs):
+            cnts = val(279, [None] * len(offs))
+            for i, (o, c) in enumerate(zip(offs, cnts)):
                 r0 = i * rps
                 nr = min(rps, ny - r0)
-                f.seek(o)
-                arr[r0:r0 + nr] = np.frombuffer(f.read(nr * nx * dtype.itemsize), dtype).reshape(nr, nx)
+                arr[r0:r0 + nr] = block(o, c if (comp != 1 and c is not None) else nr * nx * dtype.itemsize, nr, nx)
         meta = RasterMeta()
         nd = val(42113)
         if nd is not None:
@@ -128,11 +142,54 @@ def read_raster(path):
         return arr, meta
 
 
-def write_raster(path, arr, meta=None, nodata=None):
-    """Write a 2-D array as an uncompressed single-strip-per-row-block GeoTIFF (BigTIFF above 3.9 GB)."""
+def _decompress(raw, comp, want):
+    """TIFF compression 5 (LZW, libhydrocore's host codec) or 8 / 32946 (deflate, zlib)"""
+    if comp in (8, 32946):
+        import zlib
+        return zlib.decompress(raw)
+    import ctypes
+    from . import _lib
+    src = np.frombuffer(raw, np.uint8)
+    dst = np.empty(max(want, 1), np.uint8)
+    n = ctypes.c_int64()
+    _lib.check(_lib.load().hc_lzw_decode_host(ctypes.c_void_p(src.ctypes.data), len(raw), ctypes.c_void_p(dst.ctypes.data),
+                                             want, ctypes.byref(n)), "hc_lzw_decode_host")
+    return dst[:n.value].tobytes()
+
+
+def _lzw(raw):
+    import ctypes
+    from . import _lib
+    src = np.frombuffer(raw, np.uint8)
+    dst = np.empty(2 * len(raw) + 16, np.uint8)
+    n = ctypes.c_int64()
+    _lib.check(_lib.load().hc_lzw_encode_host(ctypes.c_void_p(src.ctypes.data), len(raw), ctypes.c_void_p(dst.ctypes.data),
+                                             len(dst), ctypes.byref(n)), "hc_lzw_encode_host")
+    return dst[:n.value].tobytes()
+
+
+def _unpredict(b, pred, rows, cols, dtype):
+    """undo TIFF predictor 2 (horizontal differencing of the sample words) or 3 (floating point: bytes of a row
+    regrouped most-significant plane first, then byte-differenced) on the bytes of one strip / tile"""
+    bps = dtype.itemsize
+    if pred == 1:
+        return b.view(dtype).reshape(rows, cols)
+    if pred == 2:
+        u = b.view(np.dtype(f"<u{bps}")).reshape(rows, cols)
+        return np.cumsum(u, axis=1, dtype=u.dtype).view(dtype)
+    cum = np.cumsum(b.reshape(rows, cols * bps), axis=1, dtype=np.uint8)
+    planes = cum.reshape(rows, bps, cols)[:, ::-1, :]              # little-endian byte order
+    return np.ascontiguousarray(planes.transpose(0, 2, 1)).view(dtype).reshape(rows, cols)
+
+
+def write_raster(path, arr, meta=None, nodata=None, compress=None):
+    """Write a 2-D array as a single-band GeoTIFF (BigTIFF above 3.9 GB): uncompressed strips by default,
+    `compress='lzw'` (what pyct.tifcompress produces, tools/convert.py:312) or `'deflate'`."""
     arr = np.ascontiguousarray(arr)
     if arr.ndim != 2:
         raise ValueError("write_raster needs a 2-D array")
+    if compress not in (None, 'lzw', 'deflate'):
+        raise ValueError("compress must be None, 'lzw' or 'deflate'")
     meta = RasterMeta(meta or {})
     if nodata is not None:
         meta["nodata"] = float(nodata)
@@ -150,14 +207,25 @@ def write_raster(path, arr, meta=None, nodata=None):
         arr = arr.astype(arr.dtype.newbyteorder("<"))
     ny, nx = arr.shape
     row_bytes = nx * arr.dtype.itemsize
-    rps = max(1, min(ny, (8 << 20) // max(row_bytes, 1)))
+    rps = max(1, min(ny, ((8 << 20) if compress is None else (1 << 20)) // max(row_bytes, 1)))
     nstrips = (ny + rps - 1) // rps
-    big = arr.nbytes > 3_900_000_000
+    blobs = None
+    if compress is not None:
+        import zlib
+        pack = _lzw if compress == 'lzw' else (lambda b: zlib.compress(b, 6))
+        blobs = [pack(arr[i * rps:min(ny, (i + 1) * rps)].tobytes()) for i in range(nstrips)]
+        cnts = [len(b) for b in blobs]
+        data_bytes = sum(cnts)
+    else:
+        cnts = [min(rps, ny - i * rps) * row_bytes for i in range(nstrips)]
+        data_bytes = arr.nbytes
+    big = data_bytes > 3_900_000_000
     head = 16 if big else 8
-    offs = [head + i * rps * row_bytes for i in range(nstrips)]
-    cnts = [min(rps, ny - i * rps) * row_bytes for i in range(nstrips)]
+    offs = list(head + np.concatenate([[0], np.cumsum(cnts[:-1], dtype=np.int64)]).astype(np.int64)) if nstrips else []
+    offs = [int(o) for o in offs]
     LONG = 16 if big else 4
-    entries = [(256, 4, [nx]), (257, 4, [ny]), (258, 3, [arr.dtype.itemsize * 8]), (259, 3, [1]), (262, 3, [1]),
+    entries = [(256, 4, [nx]), (257, 4, [ny]), (258, 3, [arr.dtype.itemsize * 8]),
+               (259, 3, [{None: 1, 'lzw': 5, 'deflate': 8}[compress]]), (262, 3, [1]),
                (273, LONG, offs), (277, 3, [1]), (278, 4, [rps]), (279, LONG, cnts), (284, 3, [1]), (339, 3, [fmtc])]
     for t, (typ, vals) in sorted(meta.get("geo", {}).items()):
         entries.append((int(t), int(typ), vals))
@@ -165,7 +233,7 @@ def write_raster(path, arr, meta=None, nodata=None):
         nd = meta["nodata"]
         entries.append((42113, 2, (repr(int(nd)) if float(nd).is_integer() else repr(float(nd)))))
     entries.sort(key=lambda e: e[0])
-    ifd_off = head + arr.nbytes
+    ifd_off = head + data_bytes
     ifd_off += ifd_off & 1
     esize = 20 if big else 12
     ifd_len = (8 if big else 2) + esize * len(entries) + (8 if big else 4)
@@ -195,8 +263,12 @@ def write_raster(path, arr, meta=None, nodata=None):
             f.write(b"II" + struct.pack("<HHHQ", 43, 8, 0, ifd_off))
         else:
             f.write(b"II" + struct.pack("<HI", 42, ifd_off))
-        f.write(arr.tobytes() if arr.nbytes < (1 << 30) else memoryview(arr).cast("B"))
-        if (head + arr.nbytes) & 1:
+        if blobs is None:
+            f.write(arr.tobytes() if arr.nbytes < (1 << 30) else memoryview(arr).cast("B"))
+        else:
+            for b in blobs:
+                f.write(b)
+        if (head + data_bytes) & 1:
             f.write(b"\x00")
         f.write(ifd)
         f.write(extra)
