@@ -28,10 +28,16 @@ def test_large_strips_and_empty_meta(tmp_path):
     assert np.array_equal(a, b) and meta.nodata is None and meta.pixel_size == (1.0, 1.0)
 
 
-def test_rejects_compressed(tmp_path):
+def test_reads_lzw_and_rejects_what_it_does_not_know(tmp_path):
     from PIL import Image
     from pydrodem_b200 import raster_io
     p = str(tmp_path / "lzw.tif")
-    Image.fromarray(np.zeros((8, 8), np.uint8)).save(p, compression="tiff_lzw")
+    a = (np.arange(64, dtype=np.uint8).reshape(8, 8) // 3)
+    Image.fromarray(a).save(p, compression="tiff_lzw")
+    assert np.array_equal(raster_io.read_raster(p)[0], a)
+    q = str(tmp_path / "packbits.tif")
+    Image.fromarray(a).save(q, compression="packbits")
     with pytest.raises(ValueError):
-        raster_io.read_raster(p)
+        raster_io.read_raster(q)
+    with pytest.raises(ValueError):
+        raster_io.write_raster(str(tmp_path / "x.tif"), a, None, compress="jpeg")
