@@ -113,9 +113,9 @@ def breach_flowpath(z, nodata=-9999.0, max_length=0, max_depth=None, fill_pits=T
             for q in path:
                 if w[q] > zt:
                     w[q] = zt
-                    stats["cut"] += 1
         else:
             stats["left"] += 1
+    stats["cut"] = int(np.count_nonzero(w < orig))      # cells lowered (counted once: independent of the pit order)
     if do_fill:
         w = ho.fill(w, float(nodata), ho.SEED_WBT)
     return w, stats

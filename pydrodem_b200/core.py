@@ -194,19 +194,52 @@ def breach_single_cell_pits(z, nodata=-9999.0):
     return _unary_f32(z, "hc_breach_single_cell_pits_dev", nodata)
 
 
+def _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits):
+    """EXPERIMENTAL composition of the order-independent flow-path breach (specification
+    oracle/breach_flowpath.py): single-cell pits, fill, D8 and flat resolution on the GPU, the pointer walks on the
+    host (`hc_breach_flowpath_host`, to become a kernel), closing fill on the GPU.  Returns (surface, stats)."""
+    import ctypes
+    import numpy as np
+    w = fill_single_cell_pits(zh, nodata) if fill_pits else zh
+    filled = fill(w, nodata=nodata, seed_mode=SEED_WBT)
+    dirs = d8(filled, nodata=nodata, table=TABLE_WBT, want_slope=False)
+    dirs = resolve_flats(filled, dirs, nodata=nodata, table=TABLE_WBT)
+    w = _np2d(w, np.float32)
+    cut = np.empty_like(w)
+    st = (ctypes.c_int64 * 4)()
+    _lib.check(_lib.load().hc_breach_flowpath_host(_vp(w), _vp(_np2d(filled, np.float32)), _vp(_np2d(dirs, np.uint8)),
+                                                  _vp(cut), w.shape[0], w.shape[1], float(nodata),
+                                                  int(max_length) if max_length else 0,
+                                                  float(max_depth) if max_depth else 0.0, st),
+               "hc_breach_flowpath_host")
+    return cut, st
+
+
 def breach_depressions(z, nodata=-9999.0, max_length=None, max_depth=None, fill_pits=False, flat_increment=None,
-                       return_stats=False):
+                       return_stats=False, method='flood'):
     """wbt.breach_depressions (Lindsay 2016) as dep.breach_pits calls it (tools/depressions.py:1376-1380):
     constrained breaching on the host (`hc_breach_depressions_host`, one global priority order -- SURVEY.md 8 row
     a2), then the depressions that could not be breached are filled by the GPU fill with WhiteboxTools' seed rule.
-    float32 in, float32 out (numpy in -> numpy out, CUDA tensor in -> CUDA tensor out)."""
+    float32 in, float32 out (numpy in -> numpy out, CUDA tensor in -> CUDA tensor out).
+    method='flowpath' selects the experimental order-independent formulation (see _breach_flowpath)."""
     import ctypes
     import numpy as np
     if flat_increment is not None and flat_increment > 0:
         raise NotImplementedError("flat_increment > 0 (graded breach channels / Priority-Flood+epsilon) is order "
                                   "dependent in WhiteboxTools and is not offered; pydrodem's default is 0.0")
+    if method not in ('flood', 'flowpath'):
+        raise ValueError("method must be 'flood' (the shipped formulation) or 'flowpath' (experimental)")
     host = not _is_torch(z)
     zh = _np2d(z if host else z.detach().cpu().numpy(), np.float32)
+    if method == 'flowpath':
+        cut, st = _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits)
+        out = fill(cut, nodata=nodata, seed_mode=SEED_WBT)
+        if not host:
+            import torch
+            out = torch.from_numpy(out).to(z.device)
+        if return_stats:
+            return out, dict(pits=st[0], breached=st[1], left_to_fill=st[2], cells_lowered=st[3])
+        return out
     cut = np.empty_like(zh)
     st = (ctypes.c_int64 * 5)()
     _lib.check(_lib.load().hc_breach_depressions_host(_vp(zh), _vp(cut), zh.shape[0], zh.shape[1], float(nodata),

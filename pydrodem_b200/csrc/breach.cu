@@ -201,3 +201,115 @@ extern "C" int hc_breach_depressions_host(const float *z, float *out, int64_t ny
   }
   return HC_OK;
 }
+
+
+// ---- flow-path formulation (specification: oracle/breach_flowpath.py) ---------------------------
+// Order-independent breach: every pit is breached along the flow path of the FILLED surface.  The caller supplies
+//   w      the surface to breach (after the optional single-cell-pit fill),
+//   filled hc_fill(w, seed rule WBT),
+//   dir    hc_d8(filled, table WBT) + hc_resolve_flats (codes 1, 2, 4 ... 128 = NE, E, SE, S, SW, W, NW, N; 0 = none),
+// all three from the device passes; this function does the part that is pointer chasing: (1) flats whose only way out
+// is a seed on their own level get pointers by geodesic distance to the seed, (2) one walk per pit with the length /
+// depth budgets measured on the original surface, cuts combined with min().  out = the cut surface (fill it afterwards).
+// EXPERIMENTAL: host reference of the walk a device kernel (one thread per pit) will replace; not yet the default of
+// wbt.breach_depressions.  stats (4 x int64, nullable): pits, breached, left, cells lowered.
+extern "C" int hc_breach_flowpath_host(const float *w, const float *filled, const uint8_t *dir, float *out, int64_t ny,
+                                       int64_t nx, float nodata, int64_t max_length, double max_depth, int64_t *stats) {
+  if (stats) memset(stats, 0, sizeof(int64_t) * 4);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!w || !filled || !dir || !out || w == out) { hc_set_error("hc_breach_flowpath: bad argument"); return HC_ERR_ARG; }
+  const int64_t n = ny * nx;
+  const bool lim_len = max_length > 0;
+  const bool lim_depth = max_depth > 0 && std::isfinite(max_depth);
+  try {
+    std::vector<uint8_t> seed;
+    seed_mask(w, seed, ny, nx, nodata);
+    std::vector<uint8_t> d(dir, dir + n);
+    // (1) edge flats: multi-source BFS from the seeds over pointer-less cells of the same filled level
+    std::vector<int32_t> dist((size_t)n, -1);
+    std::vector<int64_t> frontier, next;
+    for (int64_t i = 0; i < n; i++)
+      if (seed[i]) { dist[i] = 0; frontier.push_back(i); }
+    while (!frontier.empty()) {
+      next.clear();
+      for (int64_t i : frontier) {
+        const int64_t r = i / nx, c = i % nx;
+        for (int k = 0; k < 8; k++) {
+          int64_t rr = r + B_DR[k], cc = c + B_DC[k];
+          if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
+          int64_t j = rr * nx + cc;
+          if (seed[j] || dist[j] >= 0 || d[j] != 0 || b_nodata(filled[j], nodata) || filled[j] != filled[i]) continue;
+          dist[j] = dist[i] + 1;
+          next.push_back(j);
+        }
+      }
+      frontier.swap(next);
+    }
+    for (int64_t i = 0; i < n; i++) {
+      if (dist[i] <= 0) continue;
+      const int64_t r = i / nx, c = i % nx;
+      for (int k = 0; k < 8; k++) {
+        int64_t rr = r + B_DR[k], cc = c + B_DC[k];
+        if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
+        int64_t j = rr * nx + cc;
+        if (dist[j] == dist[i] - 1 && filled[j] == filled[i] && (seed[j] || dist[j] > 0)) { d[i] = (uint8_t)(1u << k); break; }
+      }
+    }
+    // (2) the walks
+    memcpy(out, w, sizeof(float) * (size_t)n);
+    int64_t s_pits = 0, s_done = 0, s_left = 0;
+    std::vector<int64_t> path;
+    for (int64_t p = 0; p < n; p++) {
+      const float zt = w[p];
+      if (seed[p] || b_nodata(zt, nodata)) continue;
+      const int64_t r = p / nx, c = p % nx;
+      bool pit = true;
+      for (int k = 0; k < 8 && pit; k++) {
+        int64_t rr = r + B_DR[k], cc = c + B_DC[k];
+        if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
+        float zn = w[rr * nx + cc];
+        if (!b_nodata(zn, nodata) && zn < zt) pit = false;
+      }
+      if (!pit) continue;
+      s_pits++;
+      path.clear();
+      int64_t q = p, steps = 0;
+      double depth = 0.0;
+      bool ok = true;
+      for (;;) {
+        uint8_t code = d[q];
+        if (code == 0 || (code & (code - 1))) {      // no pointer (or the nodata code 255): must be a seed
+          if (!seed[q]) { hc_set_error("hc_breach_flowpath: cell %lld of the filled surface has no pointer", (long long)q); return HC_ERR_ARG; }
+          break;
+        }
+        int k = 0;
+        while (!((code >> k) & 1)) k++;
+        int64_t rr = q / nx + B_DR[k], cc = q % nx + B_DC[k];
+        if (rr < 0 || cc < 0 || rr >= ny || cc >= nx || ++steps > n) { hc_set_error("hc_breach_flowpath: pointer leaves the raster / cycles"); return HC_ERR_ARG; }
+        q = rr * nx + cc;
+        if (lim_len && steps > max_length) { ok = false; break; }
+        if (w[q] < zt) break;
+        double dd = (double)w[q] - (double)zt;
+        if (dd > depth) depth = dd;
+        if (lim_depth && depth > max_depth) { ok = false; break; }
+        if (w[q] > zt) path.push_back(q);
+      }
+      if (ok) {
+        s_done++;
+        for (int64_t qq : path)
+          if (out[qq] > zt) out[qq] = zt;
+      } else {
+        s_left++;
+      }
+    }
+    if (stats) {
+      int64_t cut = 0;
+      for (int64_t i = 0; i < n; i++) cut += out[i] < w[i];
+      stats[0] = s_pits; stats[1] = s_done; stats[2] = s_left; stats[3] = cut;
+    }
+  } catch (const std::bad_alloc &) {
+    hc_set_error("hc_breach_flowpath: out of host memory");
+    return HC_ERR_NOMEM;
+  }
+  return HC_OK;
+}

@@ -73,3 +73,24 @@ def test_hand_worked_dam_matches_the_flood_formulation():
     a, sa = bf.breach_flowpath(z, ND, fill_pits=False)
     b, sb = bo.breach_depressions(z, ND, fill_pits=False)
     assert np.array_equal(a, b) and sa["cut"] == sb["cut"] == 2
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_host_walk_equals_the_specification(seed):
+    """hc_breach_flowpath_host (the pointer-chasing half, product code) fed the oracle's filled surface and pointers"""
+    import ctypes
+    from pydrodem_b200 import _lib
+    z = scene(seed + 130)
+    nd = np.float32(ND)
+    w = bo.fill_single_cell_pits(z, nd)
+    filled = ho.fill(w, ND, ho.SEED_WBT)
+    d = ho.resolve_flats(filled, ho.d8(filled, ND, table=ho.TABLE_WBT, want_slope=False), ND, ho.TABLE_WBT)
+    for ml, md in ((0, 0.0), (3, 0.0), (5, 1.5)):
+        out = np.empty_like(w)
+        st = (ctypes.c_int64 * 4)()
+        rc = _lib.load().hc_breach_flowpath_host(w.ctypes.data, filled.ctypes.data, d.ctypes.data, out.ctypes.data,
+                                                 w.shape[0], w.shape[1], ND, ml, md, st)
+        assert rc == 0, _lib.load().hc_last_error()
+        want, sw = bf.breach_flowpath(z, ND, max_length=ml, max_depth=md or None, fill_pits=True, do_fill=False)
+        assert np.array_equal(out, want)
+        assert list(st) == [sw["pits"], sw["breached"], sw["left"], sw["cut"]]
