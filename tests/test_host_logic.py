@@ -155,3 +155,27 @@ def test_sink_pixel_geometry_round_trip():
     a = np.zeros((30, 50), np.float32)
     out = endo.set_nodata_points((x, y), a, gt[1], gt[5], gt[0], gt[3], -9999)
     assert out is a and a[17, 41] == -9999 and np.count_nonzero(a) == 1
+
+
+def test_reference_module_names_resolve(tmp_path):
+    """the import swaps INTEGRATION.md shows: tools.derive / tools.build_operators / tools.convert / tools.water ..."""
+    import importlib
+    from pydrodem_b200 import raster_io
+    for m, names in (("derive", ("apply_convolve_filter", "slope_D2", "slope_D4", "curvature_D2", "DEMdifference")),
+                     ("build_operators", ("build_kernel",)), ("convert", ("npy2tif", "tifdowncast", "tifcompress")),
+                     ("water", ("river_minimize", "smooth_rivers", "raise_small_streams", "raise_small_rivers")),
+                     ("depressions", ("fill_pits", "breach_pits", "initial_fill_carve", "create_clump_array",
+                                      "fill_shallow_pits", "build_pit_catalog", "select_solution", "apply_solution",
+                                      "combined_solution", "fix_shifted_data")),
+                     ("endo", ("find_sink_pixel", "get_xy", "coords_to_pixel", "set_nodata_points"))):
+        mod = importlib.import_module(f"pydrodem_b200.tools.{m}")
+        for n in names:
+            assert callable(getattr(mod, n)), (m, n)
+    pdt = importlib.import_module("pydrodem_b200.tools.derive")
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    raster_io.write_raster(str(tmp_path / "a.tif"), a, None, nodata=-9999)
+    raster_io.write_raster(str(tmp_path / "b.tif"), a * 2 + 1, None, nodata=-9999)
+    d = pdt.DEMdifference(str(tmp_path / "a.tif"), str(tmp_path / "b.tif"), "d.tif", -9999)
+    assert np.array_equal(d, a + 1) and np.array_equal(raster_io.read_raster(str(tmp_path / "d.tif"))[0], a + 1)
+    k = importlib.import_module("pydrodem_b200.tools.build_operators").build_kernel([1., 0.5], dtype=np.float32)
+    assert k.shape == (3, 3) and k[1, 1] == 1.0 and k[0, 0] == 0.5
