@@ -182,9 +182,10 @@ def _unpredict(b, pred, rows, cols, dtype):
     return np.ascontiguousarray(planes.transpose(0, 2, 1)).view(dtype).reshape(rows, cols)
 
 
-def write_raster(path, arr, meta=None, nodata=None, compress=None):
+def write_raster(path, arr, meta=None, nodata=None, compress=None, tiled=False):
     """Write a 2-D array as a single-band GeoTIFF (BigTIFF above 3.9 GB): uncompressed strips by default,
-    `compress='lzw'` (what pyct.tifcompress produces, tools/convert.py:312) or `'deflate'`."""
+    `compress='lzw'` (what pyct.tifcompress produces, tools/convert.py:312) or `'deflate'`; `tiled=True` lays the
+    raster out in 256 x 256 tiles (GDAL's TILED=YES block size; `["COMPRESS=LZW", "TILED=YES"]`, tools/convert.py:202)."""
     arr = np.ascontiguousarray(arr)
     if arr.ndim != 2:
         raise ValueError("write_raster needs a 2-D array")
@@ -207,26 +208,39 @@ def write_raster(path, arr, meta=None, nodata=None, compress=None):
         arr = arr.astype(arr.dtype.newbyteorder("<"))
     ny, nx = arr.shape
     row_bytes = nx * arr.dtype.itemsize
+    import zlib
+    pack = {None: (lambda b: b), 'lzw': _lzw, 'deflate': (lambda b: zlib.compress(b, 6))}[compress]
     rps = max(1, min(ny, ((8 << 20) if compress is None else (1 << 20)) // max(row_bytes, 1)))
-    nstrips = (ny + rps - 1) // rps
     blobs = None
-    if compress is not None:
-        import zlib
-        pack = _lzw if compress == 'lzw' else (lambda b: zlib.compress(b, 6))
+    if tiled:
+        tw = th = 256
+        blobs = []
+        for r0 in range(0, ny, th):
+            for c0 in range(0, nx, tw):
+                t = np.zeros((th, tw), arr.dtype)
+                blk = arr[r0:r0 + th, c0:c0 + tw]
+                t[:blk.shape[0], :blk.shape[1]] = blk
+                blobs.append(pack(t.tobytes()))
+        cnts = [len(b) for b in blobs]
+    elif compress is not None:
+        nstrips = (ny + rps - 1) // rps
         blobs = [pack(arr[i * rps:min(ny, (i + 1) * rps)].tobytes()) for i in range(nstrips)]
         cnts = [len(b) for b in blobs]
-        data_bytes = sum(cnts)
     else:
+        nstrips = (ny + rps - 1) // rps
         cnts = [min(rps, ny - i * rps) * row_bytes for i in range(nstrips)]
-        data_bytes = arr.nbytes
+    data_bytes = sum(cnts)
     big = data_bytes > 3_900_000_000
     head = 16 if big else 8
-    offs = list(head + np.concatenate([[0], np.cumsum(cnts[:-1], dtype=np.int64)]).astype(np.int64)) if nstrips else []
-    offs = [int(o) for o in offs]
+    offs = [int(o) for o in head + np.concatenate([[0], np.cumsum(cnts[:-1], dtype=np.int64)])] if cnts else []
     LONG = 16 if big else 4
     entries = [(256, 4, [nx]), (257, 4, [ny]), (258, 3, [arr.dtype.itemsize * 8]),
-               (259, 3, [{None: 1, 'lzw': 5, 'deflate': 8}[compress]]), (262, 3, [1]),
-               (273, LONG, offs), (277, 3, [1]), (278, 4, [rps]), (279, LONG, cnts), (284, 3, [1]), (339, 3, [fmtc])]
+               (259, 3, [{None: 1, 'lzw': 5, 'deflate': 8}[compress]]), (262, 3, [1]), (277, 3, [1]), (284, 3, [1]),
+               (339, 3, [fmtc])]
+    if tiled:
+        entries += [(322, 4, [tw]), (323, 4, [th]), (324, LONG, offs), (325, LONG, cnts)]
+    else:
+        entries += [(273, LONG, offs), (278, 4, [rps]), (279, LONG, cnts)]
     for t, (typ, vals) in sorted(meta.get("geo", {}).items()):
         entries.append((int(t), int(typ), vals))
     if meta.get("nodata") is not None:

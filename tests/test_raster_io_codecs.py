@@ -162,3 +162,17 @@ def test_convert_helpers(tmp_path):
     assert np.array_equal(np.array(PIL.open(out)), b)
     convert.npy2tif(a > 0, stencil, str(tmp_path / "mask.tif"), nodata=0, dtype=1)
     assert raster_io.read_raster(str(tmp_path / "mask.tif"))[0].dtype == np.uint8
+
+
+@pytest.mark.parametrize("comp", [None, "lzw", "deflate"])
+def test_tiled_writing_is_read_by_libtiff_and_by_us(tmp_path, comp):
+    """`["COMPRESS=LZW", "TILED=YES"]` (tools/convert.py:202): 256 x 256 tiles, edge tiles padded"""
+    rng = np.random.default_rng(2)
+    a = (rng.random((600, 515)) * 100).astype(np.float32)
+    a[100:300] = 7
+    for arr in (a, (a > 50).astype(np.uint8)):
+        p = str(tmp_path / f"tiled_{arr.dtype}.tif")
+        raster_io.write_raster(p, arr, None, nodata=-9999, compress=comp, tiled=True)
+        b, m = raster_io.read_raster(p)
+        assert np.array_equal(b, arr) and m.nodata == -9999
+        assert np.array_equal(np.array(PIL.open(p)), arr)
