@@ -269,3 +269,18 @@ def smooth_core_rank(dem_h, top, bot, dx, dy, group=None, **kw):
     t2 = torch.tensor(list(x.stage2(mean)), dtype=torch.float64, device=dem_h.device)
     dist.all_reduce(t2, group=group)
     return x.finish(_sigma_from_sums(n, float(t2[0]), float(t2[1])))
+
+
+def clipbuffer_arr(buffered_data, buffer, set_nodata=None):
+    """CreateDTM.clipbuffer_arr (models/dem_noise_removal.py:1157-1181): drop `buffer` cells from every edge, or --
+    with `set_nodata` -- keep the shape and overwrite that frame (how run_tile blanks the halo of Zf / Filtermask / Slope,
+    :479-484).  Works on numpy arrays and on CUDA tensors (a border assignment, no kernel needed)."""
+    b = buffer
+    if set_nodata is None:
+        return buffered_data[b:-b, b:-b]
+    out = buffered_data.clone() if _is_torch(buffered_data) else np.array(buffered_data, copy=True)
+    out[:b, :] = set_nodata
+    out[-b:, :] = set_nodata
+    out[:, :b] = set_nodata
+    out[:, -b:] = set_nodata
+    return out

@@ -179,3 +179,14 @@ def test_reference_module_names_resolve(tmp_path):
     assert np.array_equal(d, a + 1) and np.array_equal(raster_io.read_raster(str(tmp_path / "d.tif"))[0], a + 1)
     k = importlib.import_module("pydrodem_b200.tools.build_operators").build_kernel([1., 0.5], dtype=np.float32)
     assert k.shape == (3, 3) and k[1, 1] == 1.0 and k[0, 0] == 0.5
+
+
+def test_clipbuffer_arr_matches_the_reference_semantics():
+    from pydrodem_b200 import stencils
+    a = np.arange(56, dtype=np.float32).reshape(7, 8)
+    assert np.array_equal(stencils.clipbuffer_arr(a, 2), a[2:-2, 2:-2])
+    mask = np.zeros_like(a, dtype=np.int8)
+    mask[2:-2, 2:-2] = 1
+    assert np.array_equal(stencils.clipbuffer_arr(a, 2, set_nodata=-9999), np.where(mask == 1, a, -9999))
+    u = np.arange(56, dtype=np.uint8).reshape(7, 8)
+    assert np.array_equal(stencils.clipbuffer_arr(u, 1, set_nodata=99)[0], np.full(8, 99, np.uint8)) and u[0, 0] == 0
