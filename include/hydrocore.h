@@ -144,11 +144,13 @@ int hc_lzw_encode_host(const uint8_t *src, int64_t nsrc, uint8_t *dst, int64_t c
 int hc_breach_depressions_host(const float *z, float *out, int64_t ny, int64_t nx, float nodata, int64_t max_length,
                                double max_depth, int fill_pits, int do_fill, int64_t *stats);
 /* EXPERIMENTAL -- the pointer-chasing half of the order-independent flow-path breach (specification
- * oracle/breach_flowpath.py): w = surface to breach, filled = hc_fill(w, WBT seeds), dir = hc_d8 + hc_resolve_flats of
- * `filled` with the WBT table (all host rasters here); out = cut surface, to be filled afterwards.  stats (4 x int64,
- * nullable): pits, breached, left, cells lowered.  Not yet what wbt.breach_depressions runs. */
+ * oracle/breach_flowpath.py): w = surface to breach, filled = hc_fill(w, WBT seeds), dir = hc_d8 + hc_resolve_flats
+ * (WBT table) of `filled` with every seed (hc_wbt_seed_mask_host) lowered by one float32 ulp, so that flats at a
+ * seed's level drain through it (all host rasters here); out = cut surface, to be filled afterwards.  stats (4 x
+ * int64, nullable): pits, breached, left, cells lowered.  Not yet what wbt.breach_depressions runs. */
 int hc_breach_flowpath_host(const float *w, const float *filled, const uint8_t *dir, float *out, int64_t ny, int64_t nx,
                             float nodata, int64_t max_length, double max_depth, int64_t *stats);
+int hc_wbt_seed_mask_host(const float *w, uint8_t *seed_out, int64_t ny, int64_t nx, float nodata);
 /* Water stencils of tools/water.py (called from models/depression_handling.py:647,889,898 and
  * models/burn_rivers.py:841,856).  wm = water_mask_array as uint8, swo = SWO_array as int16, dem/burn float32;
  * `burn` (DEM_burn_arr) is updated in place and may alias `dem`, as in the reference's own calls.

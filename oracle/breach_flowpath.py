@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE -- CPU restatement of the ORDER-INDEPENDENT breach formulation planned for the device
-(DESIGN.md 8, item 5): every pit is breached along the flow path of the FILLED surface (fill -> D8 -> flat resolution,
-all three from hydro_oracle), lengths and depths measured on the original surface, cuts combined with min().
+(DESIGN.md 8, item 5): every pit is breached along the flow path of the FILLED surface (fill -> seeds lowered by one
+ulp -> D8 -> flat resolution, all from hydro_oracle), lengths and depths measured on the original surface, cuts combined with min().
 Not used by the product yet (the shipped breach is csrc/breach.cu, pinned by oracle/breach_oracle.py); it exists so
 that the next step -- a breach kernel of one thread per pit -- has a checked specification to be compared against.
 Only tests may import it."""
@@ -36,38 +36,18 @@ def pits_of(w, seed, nodata):
     return out
 
 
-def _drain_edge_flats(filled, d, seed, nodata):
-    """WhiteboxTools' pointer raster leaves 0 on a flat whose only way out is a seed on its own level (an edge cell has
-    nowhere to point).  For the breach those flats drain THROUGH the seed: geodesic distance to the nearest seed over
-    cells of the same filled level that still have no pointer (multi-source BFS), pointer = the first neighbour in
-    table order that is one step closer.  Defined by distances, so it does not depend on the BFS visiting order."""
-    ny, nx = filled.shape
-    d = d.copy()
-    open_ = (d == 0) & (filled != nodata) & (filled == filled)
-    dist = np.full((ny, nx), -1, np.int64)
-    frontier = [(r, c) for r in range(ny) for c in range(nx) if seed[r, c]]
-    for q in frontier:
-        dist[q] = 0
-    while frontier:
-        nxt = []
-        for (r, c) in frontier:
-            for k in range(8):
-                rr, cc = r + DR[k], c + DC[k]
-                if 0 <= rr < ny and 0 <= cc < nx and open_[rr, cc] and not seed[rr, cc] and dist[rr, cc] < 0 \
-                        and filled[rr, cc] == filled[r, c]:
-                    dist[rr, cc] = dist[r, c] + 1
-                    nxt.append((rr, cc))
-        frontier = nxt
-    for r in range(ny):
-        for c in range(nx):
-            if dist[r, c] > 0:
-                for k in range(8):
-                    rr, cc = r + DR[k], c + DC[k]
-                    if 0 <= rr < ny and 0 <= cc < nx and dist[rr, cc] == dist[r, c] - 1 and \
-                            filled[rr, cc] == filled[r, c] and (seed[rr, cc] or dist[rr, cc] > 0):
-                        d[r, c] = 1 << k
-                        break
-    return d
+def pointers(w, nodata):
+    """-> (seed mask, filled surface, pointer raster).  WhiteboxTools' pointer raster leaves 0 on a flat whose only way
+    out is a seed on its own level (an edge cell has nowhere to point).  For the breach those flats must drain THROUGH
+    the seed, so the pointers are taken from the filled surface with every seed lowered by one float32 ulp: the
+    ordinary flat resolution then sees the seed as the flat's outlet, and no other pass is needed."""
+    seed = ho.seed_mask(w, float(nodata), ho.SEED_WBT).astype(bool)
+    filled = ho.fill(w, float(nodata), ho.SEED_WBT)
+    lowered = filled.copy()
+    lowered[seed] = np.nextafter(filled[seed], np.float32(-np.inf))
+    d = ho.resolve_flats(lowered, ho.d8(lowered, float(nodata), table=ho.TABLE_WBT, want_slope=False), float(nodata),
+                         ho.TABLE_WBT)
+    return seed, filled, d
 
 
 def breach_flowpath(z, nodata=-9999.0, max_length=0, max_depth=None, fill_pits=True, do_fill=True, order=None):
@@ -75,11 +55,7 @@ def breach_flowpath(z, nodata=-9999.0, max_length=0, max_depth=None, fill_pits=T
     z = np.asarray(z, np.float32)
     nodata = np.float32(nodata)
     w = bo.fill_single_cell_pits(z, nodata) if fill_pits else z.copy()
-    seed = ho.seed_mask(w, float(nodata), ho.SEED_WBT).astype(bool)
-    filled = ho.fill(w, float(nodata), ho.SEED_WBT)
-    d = ho.resolve_flats(filled, ho.d8(filled, float(nodata), table=ho.TABLE_WBT, want_slope=False), float(nodata),
-                         ho.TABLE_WBT)
-    d = _drain_edge_flats(filled, d, seed, nodata)
+    seed, filled, d = pointers(w, nodata)
     orig = w.copy()
     pits = pits_of(orig, seed, nodata)
     if order is not None:
@@ -90,10 +66,10 @@ def breach_flowpath(z, nodata=-9999.0, max_length=0, max_depth=None, fill_pits=T
         zt = orig[r, c]
         q, steps, depth, ok, path = (r, c), 0, 0.0, True, []
         while True:
-            k = K_OF_CODE.get(int(d[q]))
-            if k is None:                     # no pointer: a seed, the path leaves the raster here
-                assert seed[q], "every non-seed cell of a filled surface must have a pointer"
+            if seed[q]:                       # a seed: the path leaves the raster here
                 break
+            k = K_OF_CODE.get(int(d[q]))
+            assert k is not None, "every non-seed cell of the filled surface must have a pointer"
             q = (q[0] + DR[k], q[1] + DC[k])
             steps += 1
             assert 0 <= q[0] < ny and 0 <= q[1] < nx and steps <= ny * nx, "pointer forest must lead to a seed"

@@ -200,11 +200,18 @@ def _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits):
     host (`hc_breach_flowpath_host`, to become a kernel), closing fill on the GPU.  Returns (surface, stats)."""
     import ctypes
     import numpy as np
-    w = fill_single_cell_pits(zh, nodata) if fill_pits else zh
-    filled = fill(w, nodata=nodata, seed_mode=SEED_WBT)
-    dirs = d8(filled, nodata=nodata, table=TABLE_WBT, want_slope=False)
-    dirs = resolve_flats(filled, dirs, nodata=nodata, table=TABLE_WBT)
-    w = _np2d(w, np.float32)
+    w = _np2d(fill_single_cell_pits(zh, nodata) if fill_pits else zh, np.float32)
+    filled = _np2d(fill(w, nodata=nodata, seed_mode=SEED_WBT), np.float32)
+    # flats on a seed's own level must drain through the seed: pointers come from the filled surface with every seed
+    # lowered by one ulp (a host touch-up of the seed cells only, until the device pass has the seed mask itself)
+    seed = np.empty(w.shape, np.uint8)
+    _lib.check(_lib.load().hc_wbt_seed_mask_host(_vp(w), _vp(seed), w.shape[0], w.shape[1], float(nodata)),
+               "hc_wbt_seed_mask_host")
+    lowered = filled.copy()
+    sm = seed.astype(bool)
+    lowered[sm] = np.nextafter(filled[sm], np.float32(-np.inf))
+    dirs = d8(lowered, nodata=nodata, table=TABLE_WBT, want_slope=False)
+    dirs = resolve_flats(lowered, dirs, nodata=nodata, table=TABLE_WBT)
     cut = np.empty_like(w)
     st = (ctypes.c_int64 * 4)()
     _lib.check(_lib.load().hc_breach_flowpath_host(_vp(w), _vp(_np2d(filled, np.float32)), _vp(_np2d(dirs, np.uint8)),

@@ -207,10 +207,12 @@ extern "C" int hc_breach_depressions_host(const float *z, float *out, int64_t ny
 // Order-independent breach: every pit is breached along the flow path of the FILLED surface.  The caller supplies
 //   w      the surface to breach (after the optional single-cell-pit fill),
 //   filled hc_fill(w, seed rule WBT),
-//   dir    hc_d8(filled, table WBT) + hc_resolve_flats (codes 1, 2, 4 ... 128 = NE, E, SE, S, SW, W, NW, N; 0 = none),
-// all three from the device passes; this function does the part that is pointer chasing: (1) flats whose only way out
-// is a seed on their own level get pointers by geodesic distance to the seed, (2) one walk per pit with the length /
-// depth budgets measured on the original surface, cuts combined with min().  out = the cut surface (fill it afterwards).
+//   dir    hc_d8 + hc_resolve_flats (table WBT: codes 1, 2, 4 ... 128 = NE, E, SE, S, SW, W, NW, N) of `filled` WITH
+//          EVERY SEED LOWERED BY ONE FLOAT32 ULP (hc_wbt_seed_mask_host gives the seeds): a flat whose only way out is
+//          a seed on its own level then resolves toward that seed and every non-seed cell has a pointer,
+// all three from the device passes; this function does the part that is pointer chasing: one walk per pit with the
+// length / depth budgets measured on the original surface, cuts combined with min().  out = the cut surface (fill it
+// afterwards).
 // EXPERIMENTAL: host reference of the walk a device kernel (one thread per pit) will replace; not yet the default of
 // wbt.breach_depressions.  stats (4 x int64, nullable): pits, breached, left, cells lowered.
 extern "C" int hc_breach_flowpath_host(const float *w, const float *filled, const uint8_t *dir, float *out, int64_t ny,
@@ -224,37 +226,7 @@ extern "C" int hc_breach_flowpath_host(const float *w, const float *filled, cons
   try {
     std::vector<uint8_t> seed;
     seed_mask(w, seed, ny, nx, nodata);
-    std::vector<uint8_t> d(dir, dir + n);
-    // (1) edge flats: multi-source BFS from the seeds over pointer-less cells of the same filled level
-    std::vector<int32_t> dist((size_t)n, -1);
-    std::vector<int64_t> frontier, next;
-    for (int64_t i = 0; i < n; i++)
-      if (seed[i]) { dist[i] = 0; frontier.push_back(i); }
-    while (!frontier.empty()) {
-      next.clear();
-      for (int64_t i : frontier) {
-        const int64_t r = i / nx, c = i % nx;
-        for (int k = 0; k < 8; k++) {
-          int64_t rr = r + B_DR[k], cc = c + B_DC[k];
-          if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
-          int64_t j = rr * nx + cc;
-          if (seed[j] || dist[j] >= 0 || d[j] != 0 || b_nodata(filled[j], nodata) || filled[j] != filled[i]) continue;
-          dist[j] = dist[i] + 1;
-          next.push_back(j);
-        }
-      }
-      frontier.swap(next);
-    }
-    for (int64_t i = 0; i < n; i++) {
-      if (dist[i] <= 0) continue;
-      const int64_t r = i / nx, c = i % nx;
-      for (int k = 0; k < 8; k++) {
-        int64_t rr = r + B_DR[k], cc = c + B_DC[k];
-        if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
-        int64_t j = rr * nx + cc;
-        if (dist[j] == dist[i] - 1 && filled[j] == filled[i] && (seed[j] || dist[j] > 0)) { d[i] = (uint8_t)(1u << k); break; }
-      }
-    }
+    const uint8_t *d = dir;
     // (2) the walks
     memcpy(out, w, sizeof(float) * (size_t)n);
     int64_t s_pits = 0, s_done = 0, s_left = 0;
@@ -277,10 +249,11 @@ extern "C" int hc_breach_flowpath_host(const float *w, const float *filled, cons
       double depth = 0.0;
       bool ok = true;
       for (;;) {
+        if (seed[q]) break;                          // the path leaves the raster here
         uint8_t code = d[q];
-        if (code == 0 || (code & (code - 1))) {      // no pointer (or the nodata code 255): must be a seed
-          if (!seed[q]) { hc_set_error("hc_breach_flowpath: cell %lld of the filled surface has no pointer", (long long)q); return HC_ERR_ARG; }
-          break;
+        if (code == 0 || (code & (code - 1))) {      // no pointer (or the nodata code 255) on a non-seed cell
+          hc_set_error("hc_breach_flowpath: cell %lld of the filled surface has no pointer", (long long)q);
+          return HC_ERR_ARG;
         }
         int k = 0;
         while (!((code >> k) & 1)) k++;
@@ -309,6 +282,22 @@ extern "C" int hc_breach_flowpath_host(const float *w, const float *filled, cons
     }
   } catch (const std::bad_alloc &) {
     hc_set_error("hc_breach_flowpath: out of host memory");
+    return HC_ERR_NOMEM;
+  }
+  return HC_OK;
+}
+
+
+// seeds of the WhiteboxTools rule (valid cells on the raster frame or 8-adjacent to nodata connected to the frame)
+extern "C" int hc_wbt_seed_mask_host(const float *w, uint8_t *seed_out, int64_t ny, int64_t nx, float nodata) {
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!w || !seed_out) { hc_set_error("hc_wbt_seed_mask: null pointer"); return HC_ERR_ARG; }
+  try {
+    std::vector<uint8_t> seed;
+    seed_mask(w, seed, ny, nx, nodata);
+    memcpy(seed_out, seed.data(), (size_t)(ny * nx));
+  } catch (const std::bad_alloc &) {
+    hc_set_error("hc_wbt_seed_mask: out of host memory");
     return HC_ERR_NOMEM;
   }
   return HC_OK;

@@ -83,8 +83,10 @@ def test_host_walk_equals_the_specification(seed):
     z = scene(seed + 130)
     nd = np.float32(ND)
     w = bo.fill_single_cell_pits(z, nd)
-    filled = ho.fill(w, ND, ho.SEED_WBT)
-    d = ho.resolve_flats(filled, ho.d8(filled, ND, table=ho.TABLE_WBT, want_slope=False), ND, ho.TABLE_WBT)
+    seed, filled, d = bf.pointers(w, nd)
+    got_seed = np.empty(w.shape, np.uint8)
+    assert _lib.load().hc_wbt_seed_mask_host(w.ctypes.data, got_seed.ctypes.data, w.shape[0], w.shape[1], ND) == 0
+    assert np.array_equal(got_seed.astype(bool), seed)
     for ml, md in ((0, 0.0), (3, 0.0), (5, 1.5)):
         out = np.empty_like(w)
         st = (ctypes.c_int64 * 4)()
