@@ -222,6 +222,26 @@ def _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits):
     return cut, st
 
 
+def _breach_flowpath_dev(zh, nodata, max_length, max_depth, fill_pits, dx=1.0, dy=1.0):
+    """EXPERIMENTAL, not yet run on a GPU: the same formulation entirely on the device (`hc_breach_flowpath_dev`).
+    Returns (cut surface as a CUDA tensor, stats)."""
+    import ctypes
+    import torch
+    zt = torch.from_numpy(np.ascontiguousarray(zh, dtype=np.float32)).cuda()
+    w = fill_single_cell_pits(zt, nodata) if fill_pits else zt
+    out, filled = torch.empty_like(w), torch.empty_like(w)
+    dirs = torch.empty(w.shape, dtype=torch.uint8, device=w.device)
+    seed = torch.empty(w.shape, dtype=torch.uint8, device=w.device)
+    st = (ctypes.c_int64 * 4)()
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().hc_breach_flowpath_dev(_lib.context(w.device.index or 0), _tp(w), _tp(out), _tp(filled),
+                                                     _tp(dirs), _tp(seed), w.shape[0], w.shape[1], float(nodata),
+                                                     float(dx), float(dy), int(max_length) if max_length else 0,
+                                                     float(max_depth) if max_depth else 0.0, st, _stream(w)),
+                   "hc_breach_flowpath_dev")
+    return out, st
+
+
 def breach_depressions(z, nodata=-9999.0, max_length=None, max_depth=None, fill_pits=False, flat_increment=None,
                        return_stats=False, method='flood'):
     """wbt.breach_depressions (Lindsay 2016) as dep.breach_pits calls it (tools/depressions.py:1376-1380):
@@ -234,13 +254,17 @@ def breach_depressions(z, nodata=-9999.0, max_length=None, max_depth=None, fill_
     if flat_increment is not None and flat_increment > 0:
         raise NotImplementedError("flat_increment > 0 (graded breach channels / Priority-Flood+epsilon) is order "
                                   "dependent in WhiteboxTools and is not offered; pydrodem's default is 0.0")
-    if method not in ('flood', 'flowpath'):
-        raise ValueError("method must be 'flood' (the shipped formulation) or 'flowpath' (experimental)")
+    if method not in ('flood', 'flowpath', 'flowpath_dev'):
+        raise ValueError("method must be 'flood' (the shipped formulation), 'flowpath' or 'flowpath_dev' (experimental)")
     host = not _is_torch(z)
     zh = _np2d(z if host else z.detach().cpu().numpy(), np.float32)
-    if method == 'flowpath':
-        cut, st = _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits)
-        out = fill(cut, nodata=nodata, seed_mode=SEED_WBT)
+    if method in ('flowpath', 'flowpath_dev'):
+        if method == 'flowpath':
+            cut, st = _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits)
+            out = fill(cut, nodata=nodata, seed_mode=SEED_WBT)
+        else:
+            cut, st = _breach_flowpath_dev(zh, nodata, max_length, max_depth, fill_pits)
+            out = fill(cut, nodata=nodata, seed_mode=SEED_WBT).cpu().numpy()
         if not host:
             import torch
             out = torch.from_numpy(out).to(z.device)

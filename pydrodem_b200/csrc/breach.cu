@@ -302,3 +302,147 @@ extern "C" int hc_wbt_seed_mask_host(const float *w, uint8_t *seed_out, int64_t 
   }
   return HC_OK;
 }
+
+// ---- flow-path breach on the device (EXPERIMENTAL: written against oracle/breach_flowpath.py, NOT YET RUN ON A GPU;
+//      nothing in the default paths calls it -- tests/test_zz_gpu_experimental.py is its opt-in check) -----------------
+// seed = valid cell on the raster frame or 8-adjacent to exterior nodata (`ext`, see ext_nodata_mask in label.cu)
+__global__ void __launch_bounds__(256)
+k_bf_seed(const float *__restrict__ w, const uint8_t *__restrict__ ext, uint8_t *__restrict__ seed, int ny, int nx,
+          float nodata) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= nx) return;
+  size_t i = (size_t)r * nx + c;
+  uint8_t s = 0;
+  if (!d_is_nodata(w[i], nodata)) {
+    if (r == 0 || c == 0 || r == ny - 1 || c == nx - 1) s = 1;
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) s |= ext[(size_t)(r + c_dr[0][k]) * nx + c + c_dc[0][k]];
+    }
+  }
+  seed[i] = s;
+}
+
+// every seed one float32 ulp lower: flats on a seed's level resolve toward the seed
+__global__ void k_bf_lower_seeds(float *__restrict__ filled, const uint8_t *__restrict__ seed, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    if (seed[i]) filled[i] = nextafterf(filled[i], -INFINITY);
+}
+
+__device__ __forceinline__ void bf_atomic_min(float *addr, float val) {
+  int *a = (int *)addr;
+  int old = *a;
+  while (__int_as_float(old) > val) {
+    int assumed = old;
+    old = atomicCAS(a, assumed, __float_as_int(val));
+    if (old == assumed) break;
+  }
+}
+
+// one thread per cell; pits walk the pointer forest twice (decide, then cut).  cnt: [0] pits [1] breached [2] left
+// [3] error (a non-seed cell without pointer, or a cycle)
+__global__ void __launch_bounds__(256)
+k_bf_walk(const float *__restrict__ w, const uint8_t *__restrict__ dir, const uint8_t *__restrict__ seed,
+          float *__restrict__ out, int ny, int nx, float nodata, long long max_length, double max_depth,
+          unsigned long long *__restrict__ cnt) {
+  const size_t n = (size_t)ny * nx;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+    const float zt = w[p];
+    if (seed[p] || d_is_nodata(zt, nodata)) continue;
+    const int r = (int)(p / (size_t)nx), c = (int)(p - (size_t)r * nx);
+    bool pit = true;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int rr = r + c_dr[0][k], cc = c + c_dc[0][k];
+      if (rr < 0 || cc < 0 || rr >= ny || cc >= nx) continue;
+      float zn = w[(size_t)rr * nx + cc];
+      if (!d_is_nodata(zn, nodata) && zn < zt) pit = false;
+    }
+    if (!pit) continue;
+    atomicAdd(&cnt[0], 1ull);
+    bool ok = true;
+    long long steps_ok = 0;
+    for (int pass = 0; pass < 2 && ok; pass++) {
+      size_t q = p;
+      long long steps = 0;
+      double depth = 0.0;
+      for (;;) {
+        if (seed[q]) break;
+        int k = d_code_to_k(HC_TABLE_WBT, dir[q]);
+        if (k < 0 || (size_t)steps > n) { atomicExch(&cnt[3], 1ull); ok = false; break; }
+        q = (size_t)((long long)q + (long long)c_dr[0][k] * nx + c_dc[0][k]);
+        steps++;
+        if (pass == 1 && steps > steps_ok) break;
+        if (max_length > 0 && steps > max_length) { ok = false; break; }
+        float zq = w[q];
+        if (zq < zt) break;
+        double dd = (double)zq - (double)zt;
+        if (dd > depth) depth = dd;
+        if (max_depth > 0.0 && depth > max_depth) { ok = false; break; }
+        if (pass == 1 && zq > zt) bf_atomic_min(&out[q], zt);
+      }
+      if (pass == 0) steps_ok = steps;
+    }
+    atomicAdd(&cnt[ok ? 1 : 2], 1ull);
+  }
+}
+
+__global__ void k_bf_count_cut(const float *__restrict__ w, const float *__restrict__ out, size_t n,
+                               unsigned long long *__restrict__ cnt) {
+  unsigned long long local = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    local += out[i] < w[i];
+  if (local) atomicAdd(&cnt[4], local);
+}
+
+// w -> out (cut surface, fill it afterwards with hc_fill_dev, seed mode WBT).  filled [n float], dir [n uint8] and
+// seed [n uint8] are caller-provided device rasters that receive the intermediate results.  stats: 4 x int64 (host).
+extern "C" int hc_breach_flowpath_dev(hc_ctx *ctx, const float *w, float *out, float *filled, uint8_t *dir,
+                                      uint8_t *seed, int64_t ny, int64_t nx, float nodata, double dx, double dy,
+                                      int64_t max_length, double max_depth, int64_t *stats, void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (stats) memset(stats, 0, sizeof(int64_t) * 4);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!w || !out || !filled || !dir || !seed || w == out || ny > 65535) {
+    hc_set_error("hc_breach_flowpath_dev: bad argument");
+    return HC_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)ny * nx;
+  // seeds of the WBT rule
+  HC_TRY(arena_reset(ctx));
+  uint8_t *ext = (uint8_t *)arena_take(ctx, n);
+  if (!ext) return HC_ERR_NOMEM;
+  int has_interior = 0;
+  HC_TRY(ext_nodata_mask(ctx, w, ext, ny, nx, nodata, &has_interior, st));
+  dim3 g2((unsigned)((nx + 255) / 256), (unsigned)ny);
+  HC_PROF(ctx, st, "k_bf_seed");
+  k_bf_seed<<<g2, 256, 0, st>>>(w, ext, seed, (int)ny, (int)nx, nodata);
+  HC_LAUNCH_CHECK(ctx);
+  // pointers of the filled surface with the seeds one ulp lower
+  HC_TRY(fill_run(ctx, w, filled, ny, nx, nodata, HC_SEED_WBT, st));
+  HC_PROF(ctx, st, "k_bf_lower_seeds");
+  k_bf_lower_seeds<<<ctx->sm_count * 8, 256, 0, st>>>(filled, seed, n);
+  HC_LAUNCH_CHECK(ctx);
+  HC_TRY(d8_flats_run(ctx, filled, dir, nullptr, ny, nx, nodata, dx, dy, HC_TABLE_WBT, st));
+  // the walks
+  HC_CUDA(cudaMemcpyAsync(out, w, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  HC_TRY(arena_reset(ctx));
+  unsigned long long *cnt = (unsigned long long *)arena_take(ctx, 256);
+  if (!cnt) return HC_ERR_NOMEM;
+  HC_CUDA(cudaMemsetAsync(cnt, 0, 64, st));
+  HC_PROF(ctx, st, "k_bf_walk");
+  k_bf_walk<<<ctx->sm_count * 8, 256, 0, st>>>(w, dir, seed, out, (int)ny, (int)nx, nodata, (long long)max_length,
+                                               std::isfinite(max_depth) ? max_depth : 0.0, cnt);
+  HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_bf_count_cut");
+  k_bf_count_cut<<<ctx->sm_count * 8, 256, 0, st>>>(w, out, n, cnt);
+  HC_LAUNCH_CHECK(ctx);
+  unsigned long long h[8];
+  HC_CUDA(cudaMemcpyAsync(h, cnt, 64, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  if (h[3]) { hc_set_error("hc_breach_flowpath_dev: a non-seed cell of the filled surface has no pointer"); return HC_ERR_ARG; }
+  if (stats) { stats[0] = (int64_t)h[0]; stats[1] = (int64_t)h[1]; stats[2] = (int64_t)h[2]; stats[3] = (int64_t)h[4]; }
+  return HC_OK;
+}

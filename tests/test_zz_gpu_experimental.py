@@ -21,8 +21,9 @@ def test_flowpath_breach_composition_matches_its_specification():
         z[:2, :] = -9999.0
         for ml in (0, 6):
             want, sw = bf.breach_flowpath(z, -9999.0, max_length=ml, fill_pits=True, do_fill=True)
-            got, st = hc.breach_depressions(z, nodata=-9999.0, max_length=ml or None, fill_pits=True, return_stats=True,
-                                            method='flowpath')
-            assert np.array_equal(got, want)
-            assert [st["pits"], st["breached"], st["left_to_fill"], st["cells_lowered"]] == \
-                [sw["pits"], sw["breached"], sw["left"], sw["cut"]]
+            for method in ('flowpath', 'flowpath_dev'):
+                got, st = hc.breach_depressions(z, nodata=-9999.0, max_length=ml or None, fill_pits=True,
+                                                return_stats=True, method=method)
+                assert np.array_equal(got, want), method
+                assert [st["pits"], st["breached"], st["left_to_fill"], st["cells_lowered"]] == \
+                    [sw["pits"], sw["breached"], sw["left"], sw["cut"]], method
