@@ -1,4 +1,4 @@
-"""BASELINE.json's full size (C2: 10801 x 10801), where the single-thread oracle cannot follow in test time: the chain is
+"""BASELINE.json's full size (C2: 10801 x 10801), checked two ways: bit for bit against the single-thread oracle (about a minute), and the chain is
 checked through size-independent properties (tests/_properties.py, themselves checked against the oracle at small
 size in the CPU suite) and through two independent code paths that must agree bit for bit -- the whole-raster chain
 and the row-band chain (3 bands with seam exchange).  Runs last (file name) because it is the longest GPU test."""
@@ -43,3 +43,55 @@ def test_c2_full_size_properties_and_band_agreement():
     bf, bd, bs, ba = bands.fill_d8_accum_banded(z, 3, nodata=nodata, dx=30.0, dy=30.0, table=hc.TABLE_TAUDEM, flats=True,
                                                 want_slope=False, seed_mode=hc.SEED_TAUDEM)
     assert torch.equal(bf, f) and torch.equal(bd, d) and torch.equal(ba, a)
+
+
+def _device_dem(ny, nx, seed, dev, **kw):
+    import torch
+    from pydrodem_b200 import synth
+    z = torch.empty((ny, nx), dtype=torch.float32, device=dev)
+    for r0 in range(0, ny, 1024):
+        nr = min(1024, ny - r0)
+        z[r0:r0 + nr] = synth.make_dem(ny, nx, seed, row0=r0, nrows=nr, device=dev, **kw)
+    return z
+
+
+def _assert_chain_equals_oracle(z, oracle, seed_mode, table, nodata=-9999.0):
+    """CUDA chain vs the CPU oracle, bit for bit, on the same raster (the oracle runs a few seconds per 13 Mcells)."""
+    import numpy as np
+    import torch
+    import pydrodem_b200 as hc
+    f, d, s, a = hc.fill_d8_accum(z, nodata=nodata, dx=30.0, dy=30.0, seed_mode=seed_mode, table=table, flats=True,
+                                  want_slope=False)
+    torch.cuda.synchronize()
+    zh = z.cpu().numpy()
+    of, od, os_, oa = oracle.fill_d8_accum(zh, nodata=nodata, dx=30.0, dy=30.0, seed_mode=seed_mode, table=table)
+    gf, gd, ga = f.cpu().numpy(), d.cpu().numpy(), a.cpu().numpy().view(np.uint32)
+    assert np.array_equal(gf, of), f"fill: {(gf != of).sum()} cells differ"
+    assert np.array_equal(gd, od), f"D8 + flats: {(gd != od).sum()} cells differ"
+    assert np.array_equal(ga, oa), f"accumulation: {(ga != oa).sum()} cells differ"
+    return int((gf > zh).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed_mode,table", [(1, 1), (0, 0)], ids=["taudem", "wbt"])
+def test_c1_size_bit_exact_vs_oracle(seed_mode, table, oracle, cuda):
+    """BASELINE.json configs[0] size (3601^2, seed 1001, nodata frame on two sides): both seed rules / code tables."""
+    z = _device_dem(3601, 3601, 1001, cuda, nodata_frame=True)
+    assert _assert_chain_equals_oracle(z, oracle, seed_mode, table) > 10000
+
+
+@pytest.mark.gpu
+def test_c2_full_size_bit_exact_vs_oracle(oracle, cuda):
+    """BASELINE.json configs[1] at full size with bench.py's exact recipe and seed (10801^2, seed 1002, TauDEM semantics):
+    the whole chain against the single-thread oracle, bit for bit (about a minute of oracle time)."""
+    z = _device_dem(10801, 10801, 1002, cuda)
+    assert _assert_chain_equals_oracle(z, oracle, 1, 1) > 100000
+
+
+@pytest.mark.gpu
+def test_c4_recipe_3601_bit_exact_vs_oracle(oracle, cuda):
+    """configs[3] recipe (flattened lakes, burned rivers: large exact flats) at 3601^2 against the oracle."""
+    from pydrodem_b200 import synth
+    z, water = synth.make_c4(3601, 3601, 1004, device=cuda)
+    assert int((water > 0).sum()) > 1000
+    _assert_chain_equals_oracle(z, oracle, 1, 1)
