@@ -86,6 +86,16 @@ int hc_fill_d8_accum_dev(hc_ctx *ctx, const float *z, float *filled, uint8_t *di
                          uint32_t *acc, int64_t ny, int64_t nx, float nodata, double dx, double dy,
                          int seed_mode, int table, int resolve_flats, void *stream);
 
+/* Pitched ("leading dimension") form of hc_fill_d8_accum_dev: every raster has ld >= nx elements per row.  With ld a
+ * multiple of 16 and 16-byte aligned bases every row is vector- and TMA-addressable whatever nx is; the library
+ * overwrites the padding columns [nx, ld) of z with nodata (hence non-const) and runs the chain on the ny x ld raster,
+ * which gives the dense call's result in the first nx columns (a nodata column acts like the raster edge for seeds,
+ * contamination and counts).  Output padding columns are unspecified.  Same reference call sites as
+ * hc_fill_d8_accum_dev (run_aws.py:580-617). */
+int hc_fill_d8_accum_ld_dev(hc_ctx *ctx, float *z, float *filled, uint8_t *dir, float *slope, uint32_t *acc,
+                            int64_t ny, int64_t nx, int64_t ld, float nodata, double dx, double dy, int seed_mode,
+                            int table, int resolve_flats, void *stream);
+
 /* Connected-component labels of mask != 0, conn = 4 or 8, ids 1..n in raster-scan order of each
  * component's first cell (exactly scipy.ndimage.label, tools/depressions.py:1646-1669,
  * tools/endo.py:323).  *nlab receives n (host pointer, may be NULL). */

@@ -31,6 +31,8 @@ SIGNATURES = {
     "hc_accum_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_vp]),
     "hc_fill_d8_accum_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64,
                                             c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
+    "hc_fill_d8_accum_ld_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f64,
+                                               c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "hc_label_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32), c_vp]),
     "hc_fill_single_cell_pits_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp]),
     "hc_breach_single_cell_pits_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp]),

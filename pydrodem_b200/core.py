@@ -116,13 +116,49 @@ def accum(dirs, table=TABLE_WBT):
     return a.cpu().numpy().view(np.uint32) if host else a
 
 
+RASTER_ALIGN = 64   # elements: rows of a pitched device raster start 64 elements apart at least (16-byte aligned for uint8)
+
+
+def empty_raster(ny, nx, dtype, device):
+    """Pitched device raster: a (ny, nx) view of a (ny, ld) tensor, ld = nx rounded up to RASTER_ALIGN elements, so
+    that every row is 16-byte aligned whatever nx is (what TMA tile copies and 128-bit loads need; a dense
+    10801-wide raster offers neither).  fill_d8_accum() recognises such views (attribute `_hc_ld`), runs
+    hc_fill_d8_accum_ld_dev on them and returns pitched views; the padding columns belong to the library."""
+    import torch
+    ld = (nx + RASTER_ALIGN - 1) // RASTER_ALIGN * RASTER_ALIGN
+    base = torch.empty((ny, ld), dtype=dtype, device=device)
+    v = base[:, :nx]
+    v._hc_ld = ld
+    return v
+
+
+def _pitched(t):
+    ld = getattr(t, "_hc_ld", None)
+    if ld is None or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) != ld or t.storage_offset() != 0:
+        return None
+    return ld
+
+
 def fill_d8_accum(z, nodata=-9999.0, dx=1.0, dy=1.0, seed_mode=SEED_TAUDEM, table=TABLE_TAUDEM, flats=True,
                   want_slope=True):
     """The north-star chain (PitRemove -> D8FlowDir -> AreaD8, run_aws.py:580-617; or WBT fill ->
-    d8_pointer -> d8_flow_accumulation, run_aws.py:528-544).  Returns (filled, dir, slope, acc)."""
+    d8_pointer -> d8_flow_accumulation, run_aws.py:528-544).  Returns (filled, dir, slope, acc).
+    A pitched device raster from empty_raster() takes the TMA / vector path and gets pitched views back."""
     lib = _lib.load()
     if _is_torch(z):
         import torch
+        ld = _pitched(z) if z.is_cuda and z.dtype == torch.float32 else None
+        if ld is not None:
+            ny, nx = z.shape
+            f = empty_raster(ny, nx, torch.float32, z.device)
+            d = empty_raster(ny, nx, torch.uint8, z.device)
+            s = empty_raster(ny, nx, torch.float32, z.device) if want_slope else None
+            a = empty_raster(ny, nx, torch.int32, z.device)
+            with torch.cuda.device(z.device):
+                _lib.check(lib.hc_fill_d8_accum_ld_dev(_lib.context(z.device.index or 0), _tp(z), _tp(f), _tp(d), _tp(s),
+                                                       _tp(a), ny, nx, ld, nodata, dx, dy, seed_mode, table,
+                                                       int(bool(flats)), _stream(z)), "hc_fill_d8_accum_ld_dev")
+            return f, d, s, a
         z = _tdev(z, torch.float32, "fill_d8_accum")
         f = torch.empty_like(z)
         d = torch.empty(z.shape, dtype=torch.uint8, device=z.device)

@@ -1,7 +1,9 @@
 // api.cu — the extern "C" surface declared in include/hydrocore.h, the context and its arena.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -22,6 +24,44 @@ extern "C" int hc_debug_read(hc_ctx *ctx, unsigned long long *out16) {
   HC_CUDA(cudaMemcpy(out16, ctx->d_dbg, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
   HC_CUDA(cudaMemset(ctx->d_dbg, 0, sizeof(unsigned long long) * 16));
   return HC_OK;
+}
+
+
+// ---- TMA tensor maps ----------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver-API call; it is fetched through the runtime (no link against libcuda.so,
+// which does not exist on a build box without a GPU driver).
+typedef CUresult (*hc_pfn_encode_tiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int hc_tmap_2d(hc_tmap *out, const void *base, int elem_bytes, int is_float, uint64_t width, uint64_t height,
+               uint64_t pitch_bytes, uint32_t box_w, uint32_t box_h) {
+  static hc_pfn_encode_tiled fn = nullptr;
+  static int tried = 0;
+  out->ok = 0;
+  if (getenv("HC_NO_TMA")) return 1;
+  if (!tried) {
+    tried = 1;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (hc_pfn_encode_tiled)p;
+    else
+      cudaGetLastError();
+  }
+  if (!fn || !hc_tmap_ok(base, pitch_bytes) || box_w > 256 || box_h > 256 || ((uint64_t)box_w * elem_bytes) % 16) return 1;
+  const cuuint64_t dims[2] = {width, height};
+  const cuuint64_t strides[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {box_w, box_h};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                 : (is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32);
+  CUresult r = fn(&out->map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  is_float ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 1;
+  out->ok = 1;
+  return 0;
 }
 
 // ---- arena ------------------------------------------------------------------------------------
@@ -196,7 +236,7 @@ extern "C" int64_t hc_workspace_bytes(const hc_ctx *ctx) {
 extern "C" int64_t hc_launch_count(const hc_ctx *ctx) { return ctx->launches; }
 extern "C" int hc_fill_stats(const hc_ctx *ctx, int64_t *n_basins, int32_t *n_rounds) {
   if (n_basins) *n_basins = ctx->fill_basins;
-  if (n_rounds) *n_rounds = ctx->fill_rounds;
+  if (n_rounds) *n_rounds = ctx->fill_rounds == -1 ? (int32_t)ctx->h_mail[32] : ctx->fill_rounds;   // -1: fetched asynchronously, valid once the caller has synchronised
   return HC_OK;
 }
 
@@ -264,6 +304,47 @@ extern "C" int hc_fill_d8_accum_dev(hc_ctx *ctx, const float *z, float *filled, 
   return HC_OK;
 }
 
+
+// padding columns [nx, ld) of a pitched float raster := nodata (see hc_fill_d8_accum_ld_dev)
+__global__ void k_pad_nodata(float *z, int ny, int nx, int ld, float nodata) {
+  const int np = ld - nx;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)ny * np) return;
+  const int r = (int)(i / np), c = nx + (int)(i - (long long)r * np);
+  z[(size_t)r * ld + c] = nodata;
+}
+
+// Pitched ("leading dimension") form of the chain: every raster has ld >= nx elements per row.  With ld a multiple of
+// 16 (and 16-byte aligned bases) every row is vector- and TMA-addressable whatever nx is (a 10801-wide dense raster
+// is neither).  The padding columns are turned into nodata and the chain runs on the ny x ld raster: under both tools'
+// conventions a nodata column right of the raster acts exactly like the raster edge (column nx - 1 is a seed / is
+// contaminated either way; the padding is exterior nodata; it holds no direction and no count), so the first nx
+// columns of every output equal the dense call's result.  Output padding columns hold unspecified values.
+extern "C" int hc_fill_d8_accum_ld_dev(hc_ctx *ctx, float *z, float *filled, uint8_t *dir, float *slope,
+                                       uint32_t *acc, int64_t ny, int64_t nx, int64_t ld, float nodata, double dx,
+                                       double dy, int seed_mode, int table, int resolve_flats, void *stream) {
+  CHECK_CTX(ctx);
+  if (ld < nx) { hc_set_error("hc_fill_d8_accum_ld: ld < nx"); return HC_ERR_ARG; }
+  HC_TRY(check_shape(ny, ld));
+  if (ny && nx && (!z || !filled || !dir || !acc)) { hc_set_error("hc_fill_d8_accum_ld: null pointer"); return HC_ERR_ARG; }
+  if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("bad seed_mode"); return HC_ERR_ARG; }
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ld > nx) {
+    const long long np = (long long)ny * (ld - nx);
+    k_pad_nodata<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(z, (int)ny, (int)nx, (int)ld, nodata);
+    HC_LAUNCH_CHECK(ctx);
+  }
+  ctx->pad_from = ld > nx ? (int)nx : 0;   // (the WBT seed rule's exterior-nodata search need not label the padding)
+  int rc = fill_run(ctx, z, filled, ny, ld, nodata, seed_mode, st);
+  ctx->pad_from = 0;
+  HC_TRY(rc);
+  if (resolve_flats) HC_TRY(d8_flats_run(ctx, filled, dir, slope, ny, ld, nodata, dx, dy, table, st));
+  else HC_TRY(d8_run(ctx, filled, dir, slope, ny, ld, nodata, dx, dy, table, st));
+  HC_TRY(accum_run(ctx, dir, acc, ny, ld, table, st));
+  return HC_OK;
+}
+
 extern "C" int hc_label_dev(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn,
                             int32_t *nlab, void *stream) {
   CHECK_CTX(ctx);
@@ -325,31 +406,45 @@ extern "C" int hc_fill_d8_accum_host_begin(hc_ctx *ctx, int slot, const float *z
   if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("bad table"); return HC_ERR_ARG; }
   // the slot's staging buffers may still be the source of the copies of the call that used it last
   HC_CUDA(cudaEventSynchronize(ctx->ev_done[slot]));
+  // device staging rasters are PITCHED: ld = nx rounded up to 64 elements, so that every row is 16-byte aligned for
+  // all element sizes (TMA and vector loads need that; a dense 10801-wide raster offers neither).  The padding columns
+  // of z hold nodata (hc_fill_d8_accum_ld_dev writes them); the 2-D copies move only the nx real columns.
+  const int64_t ld = (nx + 63) & ~(int64_t)63;
+  HC_TRY(check_shape(ny, ld));
+  const size_t np = (size_t)ny * ld;
   const int b = 5 * slot;
   dev_buf dz(ctx, b + 0), df(ctx, b + 1), dd(ctx, b + 2), ds(ctx, b + 3), da(ctx, b + 4);
-  HC_TRY(dz.alloc(n * 4));
-  HC_TRY(df.alloc(n * 4));
-  HC_TRY(dd.alloc(n));
-  if (slope) HC_TRY(ds.alloc(n * 4));
-  HC_TRY(da.alloc(n * 4));
+  HC_TRY(dz.alloc(np * 4));
+  HC_TRY(df.alloc(np * 4));
+  HC_TRY(dd.alloc(np));
+  if (slope) HC_TRY(ds.alloc(np * 4));
+  HC_TRY(da.alloc(np * 4));
   // compute on one stream, device->host copies on another: the filled raster travels while D8 / flats run, the
   // direction raster while the accumulation runs (the PCIe link, not the kernels, bounds this entry point)
   cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
-  HC_CUDA(cudaMemcpyAsync(dz.p, z, n * 4, cudaMemcpyHostToDevice, sc));
-  HC_TRY(fill_run(ctx, (const float *)dz.p, (float *)df.p, ny, nx, nodata, seed_mode, sc));
+  HC_CUDA(cudaMemcpy2DAsync(dz.p, (size_t)ld * 4, z, (size_t)nx * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyHostToDevice, sc));
+  if (ld > nx) {
+    const long long npad = (long long)ny * (ld - nx);
+    k_pad_nodata<<<(unsigned)((npad + 255) / 256), 256, 0, sc>>>((float *)dz.p, (int)ny, (int)nx, (int)ld, nodata);
+    HC_LAUNCH_CHECK(ctx);
+  }
+  ctx->pad_from = ld > nx ? (int)nx : 0;
+  int rc = fill_run(ctx, (const float *)dz.p, (float *)df.p, ny, ld, nodata, seed_mode, sc);
+  ctx->pad_from = 0;
+  HC_TRY(rc);
   HC_CUDA(cudaEventRecord(ctx->ev_fill, sc));
   HC_CUDA(cudaStreamWaitEvent(sx, ctx->ev_fill, 0));
-  HC_CUDA(cudaMemcpyAsync(filled, df.p, n * 4, cudaMemcpyDeviceToHost, sx));
-  if (resolve_flats) HC_TRY(d8_flats_run(ctx, (const float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, nx, nodata, dx, dy, table, sc));
-  else HC_TRY(d8_run(ctx, (const float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, nx, nodata, dx, dy, table, sc));
+  HC_CUDA(cudaMemcpy2DAsync(filled, (size_t)nx * 4, df.p, (size_t)ld * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost, sx));
+  if (resolve_flats) HC_TRY(d8_flats_run(ctx, (const float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, ld, nodata, dx, dy, table, sc));
+  else HC_TRY(d8_run(ctx, (const float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, ld, nodata, dx, dy, table, sc));
   HC_CUDA(cudaEventRecord(ctx->ev_dir, sc));
   HC_CUDA(cudaStreamWaitEvent(sx, ctx->ev_dir, 0));
-  HC_CUDA(cudaMemcpyAsync(dir, dd.p, n, cudaMemcpyDeviceToHost, sx));
-  if (slope) HC_CUDA(cudaMemcpyAsync(slope, ds.p, n * 4, cudaMemcpyDeviceToHost, sx));
-  HC_TRY(accum_run(ctx, (const uint8_t *)dd.p, (uint32_t *)da.p, ny, nx, table, sc));
+  HC_CUDA(cudaMemcpy2DAsync(dir, (size_t)nx, dd.p, (size_t)ld, (size_t)nx, (size_t)ny, cudaMemcpyDeviceToHost, sx));
+  if (slope) HC_CUDA(cudaMemcpy2DAsync(slope, (size_t)nx * 4, ds.p, (size_t)ld * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost, sx));
+  HC_TRY(accum_run(ctx, (const uint8_t *)dd.p, (uint32_t *)da.p, ny, ld, table, sc));
   HC_CUDA(cudaEventRecord(ctx->ev_acc, sc));
   HC_CUDA(cudaStreamWaitEvent(sx, ctx->ev_acc, 0));
-  HC_CUDA(cudaMemcpyAsync(acc, da.p, n * 4, cudaMemcpyDeviceToHost, sx));
+  HC_CUDA(cudaMemcpy2DAsync(acc, (size_t)nx * 4, da.p, (size_t)ld * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost, sx));
   HC_CUDA(cudaEventRecord(ctx->ev_done[slot], sx));
   return HC_OK;
 }

@@ -92,6 +92,7 @@ struct hc_ctx {
   // stats of the last fill
   int64_t fill_basins;
   int32_t fill_rounds;
+  int pad_from;   // > 0: columns >= pad_from are the nodata padding of a pitched raster (hc_fill_d8_accum_ld_dev)
   // band diagnostics: terminal-graph edges emitted, MSF rounds, global seam-graph rounds
   int64_t band_term_edges;
   int32_t band_msf_rounds, band_global_rounds;

@@ -35,6 +35,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -45,13 +46,21 @@ namespace cg = cooperative_groups;
 // ---------------------------------------------------------------------------------------------
 // 1. pointers + in-tile compression
 // ---------------------------------------------------------------------------------------------
+// TMA = true: the (tile + halo) window arrives by ONE bulk-tensor copy (tma.cuh; outside-raster elements NaN), the
+// map's origin is the first readable row (rw.rlo: a band's halo row above); otherwise a row loader.
+#define KP_WP 72   // window pitch = TMA box width.  A box must START on a 16-byte boundary of its row, so the box begins
+#define KP_XO 3    // at column c0 - 4 and the logical window (column c0 - 1 first) sits KP_XO elements into it
+template <bool TMA>
 __global__ void __launch_bounds__(NTHREADS)
-k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restrict__ P, int ny, int nx,
-      float nodata, u32 *__restrict__ pit_counter, hc_rows rw, u32 idbase, uint8_t *__restrict__ seam_seed) {
-  __shared__ float sz[TH * TH];
+k_ptr(const float *__restrict__ z, const __grid_constant__ CUtensorMap mz, const uint8_t *__restrict__ ext,
+      u32 *__restrict__ P, int ny, int nx, float nodata, u32 *__restrict__ pit_counter, hc_rows rw, u32 idbase,
+      uint8_t *__restrict__ seam_seed) {
+  __shared__ __align__(128) float sz_box[TH * KP_WP];
+  float *sz = sz_box + KP_XO;   // logical window origin (row r0 - 1, column c0 - 1)
   __shared__ unsigned short snxt[T * T];
   __shared__ u32 stv[T * T];
   __shared__ u32 s_npit, s_base;
+  __shared__ __align__(8) uint64_t mbar;
 
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
@@ -59,22 +68,37 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
   const float qnan = __int_as_float(0x7fc00000);
   if (tid == 0) s_npit = 0;
 
-  // tile + 1-cell halo -> shared; warp w takes rows w, w+8, ..., a lane columns lane, lane+32, lane+64
-  for (int lr = warp; lr < TH; lr += NTHREADS / 32) {
-    const int r = r0 + lr - 1;
-    const bool rok = r >= rw.rlo && r < rw.rhi;
-    const float *row = z + ((long long)r * nx + (c0 - 1));  // r may be -1 / ny: the band's halo rows
+  if (TMA) {
+    if (tid == 0) {
+      hc_mbar_init(&mbar, 1);
+      hc_mbar_expect_tx(&mbar, (u32)(TH * KP_WP * 4));
+      hc_tma_load_2d(sz_box, &mz, &mbar, c0 - 1 - KP_XO, r0 - 1 - rw.rlo);
+    }
+    __syncthreads();
+    hc_mbar_wait(&mbar, 0);
+    // nodata -> NaN (outside-raster elements are NaN already)
+    for (int i = tid; i < TH * KP_WP; i += NTHREADS) {
+      const float v = sz_box[i];
+      if (v == nodata) sz_box[i] = qnan;
+    }
+  } else {
+    // tile + 1-cell halo -> shared; warp w takes rows w, w+8, ..., a lane columns lane, lane+32, lane+64
+    for (int lr = warp; lr < TH; lr += NTHREADS / 32) {
+      const int r = r0 + lr - 1;
+      const bool rok = r >= rw.rlo && r < rw.rhi;
+      const float *row = z + ((long long)r * nx + (c0 - 1));  // r may be -1 / ny: the band's halo rows
 #pragma unroll
-    for (int m = 0; m < 3; m++) {
-      const int lc = lane + 32 * m;
-      if (lc < TH) {
-        const int c = c0 + lc - 1;
-        float v = qnan;
-        if (rok && c >= 0 && c < nx) {
-          v = __ldg(row + lc);
-          if (v == nodata) v = qnan;
+      for (int m = 0; m < 3; m++) {
+        const int lc = lane + 32 * m;
+        if (lc < TH) {
+          const int c = c0 + lc - 1;
+          float v = qnan;
+          if (rok && c >= 0 && c < nx) {
+            v = __ldg(row + lc);
+            if (v == nodata) v = qnan;
+          }
+          sz[lr * KP_WP + lc] = v;
         }
-        sz[lr * TH + lc] = v;
       }
     }
   }
@@ -90,8 +114,8 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
     unsigned short nxt = (unsigned short)i;
     u32 tv = HC_NONE;  // nodata / outside raster
     if (r < ny && c < nx) {
-      const float *w = &sz[lr * TH + lc];  // top-left corner of the 3x3 window
-      const float v = w[TH + 1];
+      const float *w = &sz[lr * KP_WP + lc];  // top-left corner of the 3x3 window
+      const float v = w[KP_WP + 1];
       if (v == v) {
         // positions 3,2,1,0 (before the centre in index order) win ties against the centre and against
         // later ones: scan them backwards with "<="; positions 5..8 need a strictly lower elevation
@@ -104,8 +128,8 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
           anynan |= zn != zn;                  \
           if (zn CMP bz) { bz = zn; bk = K; }  \
         }
-        HC_SCAN(3, TH, <=) HC_SCAN(2, 2, <=) HC_SCAN(1, 1, <=) HC_SCAN(0, 0, <=)
-        HC_SCAN(5, TH + 2, <) HC_SCAN(6, 2 * TH, <) HC_SCAN(7, 2 * TH + 1, <) HC_SCAN(8, 2 * TH + 2, <)
+        HC_SCAN(3, KP_WP, <=) HC_SCAN(2, 2, <=) HC_SCAN(1, 1, <=) HC_SCAN(0, 0, <=)
+        HC_SCAN(5, KP_WP + 2, <) HC_SCAN(6, 2 * KP_WP, <) HC_SCAN(7, 2 * KP_WP + 1, <) HC_SCAN(8, 2 * KP_WP + 2, <)
 #undef HC_SCAN
         // seeds: raster border, or next to nodata (to EXTERIOR nodata only under the WBT rule).  A NaN
         // in the window that lies outside the raster can only belong to a border cell.
@@ -115,7 +139,7 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
           else {
             for (int dr = -1; dr <= 1; dr++)
               for (int dc = -1; dc <= 1; dc++) {
-                float zn = w[(dr + 1) * TH + dc + 1];
+                float zn = w[(dr + 1) * KP_WP + dc + 1];
                 if (zn != zn && ext[(long long)(r + dr) * nx + (c + dc)]) seed = true;  // (halo rows of a band: r + dr = -1 / ny)
               }
           }
@@ -162,22 +186,25 @@ k_ptr(const float *__restrict__ z, const uint8_t *__restrict__ ext, u32 *__restr
   }
   __syncthreads();
 
-  // pass B: pointer jumping inside the tile until every cell points at a terminal.  Terminals point
-  // at themselves and nothing else does, so "my target is its own target" means resolved: such a
-  // cell drops out of the live mask and is never touched again.
+  // pass B: pointer jumping inside the tile until every cell points at a terminal.  Terminals point at
+  // themselves and nothing else does.  Four hops per round (paths shrink 4x between barriers); a cell whose new
+  // target is its own target is resolved, drops out of the live mask and is never touched again.  Concurrent
+  // writers only ever replace a pointer by one of its ancestors.
   u32 live = 0xFFFFu;
   for (;;) {
-    int changed = 0;
+    int more = 0;
 #pragma unroll
     for (int j = 0; j < T * T / NTHREADS; j++) {
       if (!(live & (1u << j))) continue;
       const int i = tid + j * NTHREADS;
       unsigned short p = snxt[i];
-      unsigned short pp = snxt[p];
-      if (pp != p) { snxt[i] = pp; changed = 1; }
-      else live &= ~(1u << j);
+      p = snxt[p]; p = snxt[p]; p = snxt[p];
+      const unsigned short t_ = snxt[p];
+      snxt[i] = p;
+      if (t_ == p) live &= ~(1u << j);
+      else more = 1;
     }
-    if (!__syncthreads_or(changed)) break;
+    if (!__syncthreads_or(more)) break;
   }
 
   for (int i = tid; i < T * T; i += NTHREADS) {
@@ -320,6 +347,273 @@ k_minedge(const float *__restrict__ z, u32 *P, const u32 *__restrict__ rep,
         eW[o] = fmaxf(v, sz[ni]);
         o++;
       }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// 4a. ONE grid pass that yields the whole basin graph (replaces the two k_minedge sweeps of round 0 / 1):
+// every adjacent cell pair in different basins, at least one of them closed, is an edge (a, b, max(z_a, z_b));
+// only the cheapest edge per basin pair matters for any Boruvka round, and a basin pair meets in few tiles, so
+// the pairs are deduplicated per tile in a shared-memory hash table (key = the two basin ids, value = the
+// ordered weight, atomicMin) and only the survivors are appended to the global list: ~100 entries per 64x64 tile
+// on the C2 recipe instead of ~4700 differing cell pairs.  A thread walks 16 cells down one column and keeps the
+// pair it saw last in registers (a boundary that runs along the walk produces the same pair again and again), so
+// the table sees ~1 insert per boundary crossing.  Each unordered cell pair is looked at once, by its upper-left
+// member (E, SW, S, SE neighbours; the member in the halo belongs to the neighbouring tile's sweep).  The load
+// also folds the cross-tile flatten of P (see k_minedge<.., FIRST>).  Entries are UNDIRECTED: the list rounds let
+// both ends pick.  A tile whose table overflows (noise: every cell its own basin) appends the pair unreduced.
+// ---------------------------------------------------------------------------------------------
+#define EH_CAP 2048
+#define EH_PROBES 24
+#define EDGES_SMEM (TH * TH * 8 + EH_CAP * 12 + 16)
+
+__device__ __forceinline__ void eh_insert(u64 *keys, u32 *ws, u32 a, u32 b, u32 wf, u32 *__restrict__ eA,
+                                          u32 *__restrict__ eB, float *__restrict__ eW, u32 *__restrict__ ecount, u32 ecap) {
+  const u32 lo = a < b ? a : b, hi = a < b ? b : a;
+  const u64 key = ((u64)lo << 32) | (u64)hi;
+  u32 h = (u32)((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u));
+  h = (h ^ (h >> 15)) & (EH_CAP - 1);
+  volatile u64 *vk = keys;
+#pragma unroll 1
+  for (int probe = 0; probe < EH_PROBES; probe++) {
+    u64 cur = vk[h];
+    if (cur == ~0ull) {
+      cur = atomicCAS((unsigned long long *)&keys[h], ~0ull, (unsigned long long)key);
+      if (cur == ~0ull) cur = key;
+    }
+    if (cur == key) { atomicMin(&ws[h], wf); return; }
+    h = (h + 1) & (EH_CAP - 1);
+  }
+  u32 o = atomicAdd(ecount, 1u);   // table full around this slot: unreduced
+  if (o < ecap) { eA[o] = lo; eB[o] = hi; eW[o] = d_funord(wf); }
+}
+
+// Fast path of k_edges: the distinct basin ids of the tile + halo get dense local ids (a small shared hash table
+// keyed by the id, then a rank over its used slots); with L <= EL_MAX of them the cheapest weight per unordered
+// pair lives in a triangular L x L table and a differing cell pair costs one pre-checked 32-bit shared atomicMin.
+// Elevations are kept as order-preserving uints, so max(z_a, z_b) is one integer max.
+// TMA = true: the two (tile + halo) windows of z and P arrive by two bulk-tensor copies issued by one thread
+// (outside-raster elements: NaN / 0), see tma.cuh; otherwise a scalar loader.
+#define EK_THREADS 512
+#define WP 72                 // window pitch = TMA box width; the box starts at column c0 - 4 (16-byte aligned row start),
+#define WXO 3                 // the logical window (column c0 - 1 first) sits WXO elements into it
+#define WN (TH * WP)          // window elements (66 rows)
+#define EL_SLOTS 512
+#define EL_MAX 112
+#define EL_NONE 0xFFFFu
+#define EL_TAB (EL_MAX * (EL_MAX - 1) / 2 + 1)
+// layout: sz u32[WN] | sl u16[WN] | gid u32[EL_MAX] | big: union { P staging u32[WN] (TMA), lkeys u32[EL_SLOTS] + ldense u16[EL_SLOTS], tab u32[EL_TAB], hash } | mbar, counters
+#define EO_SL (WN * 4)
+#define EO_GID (EO_SL + WN * 2)
+#define EO_BIG ((EO_GID + EL_MAX * 4 + 127) & ~127)   // (a TMA destination: 128-byte aligned)
+#define EO_LK (EO_BIG + WN * 4)          // the label hash lives behind the P staging window (both are live in step 1)
+#define EO_LD (EO_LK + EL_SLOTS * 4)
+#define EO_MAX3(a, b, c) ((a) > (b) ? ((a) > (c) ? (a) : (c)) : ((b) > (c) ? (b) : (c)))
+#define EO_END (EO_BIG + ((EO_MAX3(WN * 4 + EL_SLOTS * 6, EL_TAB * 4, EH_CAP * 12) + 127) & ~127))
+#undef EDGES_SMEM
+#define EDGES_SMEM (EO_END + 128)
+
+template <bool TMA>
+__global__ void __launch_bounds__(EK_THREADS)
+k_edges(const float *__restrict__ z, u32 *P, const __grid_constant__ CUtensorMap mz, const __grid_constant__ CUtensorMap mp,
+        int ny, int nx, u32 *__restrict__ eA, u32 *__restrict__ eB, float *__restrict__ eW, u32 *__restrict__ ecount,
+        u32 ecap, u32 nopen, unsigned long long *dbg) {
+  extern __shared__ __align__(128) unsigned char smem_e[];
+  u32 *sz_box = (u32 *)smem_e;                                 // float bits, then d_ford(z)
+  u32 *sz = sz_box + WXO;                                      // logical window origin (row r0 - 1, column c0 - 1)
+  unsigned short *sl = (unsigned short *)(smem_e + EO_SL);     // hash slot, later dense local id (EL_NONE: no cell)
+  u32 *gid = (u32 *)(smem_e + EO_GID);
+  u32 *stage_box = (u32 *)(smem_e + EO_BIG);                   // P window (TMA path only)
+  u32 *stage = stage_box + WXO;
+  u32 *tab = (u32 *)(smem_e + EO_BIG);                         // pair table: reuses the staging area after step 2
+  u32 *lkeys = (u32 *)(smem_e + EO_LK);
+  unsigned short *ldense = (unsigned short *)(smem_e + EO_LD);
+  uint64_t *mbar = (uint64_t *)(smem_e + EO_END);
+  u32 *s_cnt = (u32 *)(smem_e + EO_END + 16);   // [0] entries, [1] base in the global list, [2] label-table overflow, [3..18] warp sums
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (TMA && tid == 0) {
+    hc_mbar_init(mbar, 1);
+    hc_mbar_expect_tx(mbar, 2u * WN * 4u);
+    hc_tma_load_2d(sz_box, &mz, mbar, c0 - 1 - WXO, r0 - 1);
+    hc_tma_load_2d(stage_box, &mp, mbar, c0 - 1 - WXO, r0 - 1);
+  }
+  if (tid < 3) s_cnt[tid] = 0;
+  for (int i = tid; i < EL_SLOTS; i += EK_THREADS) lkeys[i] = HC_NONE;
+  __syncthreads();
+  if (TMA) hc_mbar_wait(mbar, 0);
+  // 1. window -> ordered elevations + dense-id hash of the basin ids (cross-tile flatten of P folded in)
+  for (int lr = warp; lr < TH; lr += EK_THREADS / 32) {
+    const int r = r0 + lr - 1;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const int lc = lane + 32 * m;
+      if (lc >= WP) break;
+      const int c = c0 + lc - 1;
+      const int i = lr * WP + lc;
+      if (lc >= TH) { sl[i] = (unsigned short)EL_NONE; continue; }   // the window's pad columns
+      const bool inb = r >= 0 && r < ny && c >= 0 && c < nx;
+      const size_t g = inb ? (size_t)r * nx + c : 0;
+      u32 p;
+      float v;
+      if (TMA) { p = stage[i]; v = __uint_as_float(sz[i]); }
+      else { p = __ldcg(&P[g]); v = __ldg(&z[g]); }
+      if (inb && !(p & HC_TAG)) {
+        p = __ldcg(&P[p]);   // tagged: a perimeter cell k_perim resolved (a stale read of a cell being flattened right now is still a valid pointer)
+        if (lr >= 1 && lr <= T && lc >= 1 && lc <= T) P[g] = p;
+      }
+      const u32 id = p & 0x7FFFFFFFu;
+      u32 slot = EL_NONE;
+      if (inb && id != HC_LAB_NODATA) {
+        u32 h = (id * 0x9E3779B1u) >> (32 - 9);
+        for (int probe = 0; probe < EL_SLOTS; probe++) {
+          u32 cur = ((volatile u32 *)lkeys)[h];
+          if (cur == HC_NONE) {
+            cur = atomicCAS(&lkeys[h], HC_NONE, id);
+            if (cur == HC_NONE) cur = id;
+          }
+          if (cur == id) { slot = h; break; }
+          h = (h + 1) & (EL_SLOTS - 1);
+        }
+        if (slot == EL_NONE) s_cnt[2] = 1;   // more than EL_SLOTS distinct ids
+      }
+      sz[i] = d_ford(v);   // (NaN of a no-cell element maps to some uint: never used, its sl is EL_NONE)
+      sl[i] = (unsigned short)slot;
+    }
+  }
+  __syncthreads();
+  // 2. rank the used slots -> dense ids; gid[dense] = basin id
+  {
+    const u32 k0 = lkeys[tid];
+    const u32 v = k0 != HC_NONE;
+    u32 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t_ = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t_; }
+    if (lane == 31) s_cnt[3 + warp] = inc;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < warp; w++) base += s_cnt[3 + w];
+    const u32 excl = base + inc - v;
+    if (v) { ldense[tid] = (unsigned short)excl; if (excl < EL_MAX) gid[excl] = k0; }
+    if (tid == EK_THREADS - 1) s_cnt[0] = base + inc;   // L
+  }
+  __syncthreads();
+  const u32 L = s_cnt[0];
+  const bool fast = L <= EL_MAX && !s_cnt[2];
+  if (fast) {
+    for (int i = tid; i < WN; i += EK_THREADS) { const u32 s_ = sl[i]; if (s_ != EL_NONE) sl[i] = ldense[s_]; }
+  }
+  __syncthreads();
+  if (tid == 0) s_cnt[0] = 0;
+  if (fast) {
+    for (int i = tid; i < EL_TAB; i += EK_THREADS) tab[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    // 3. column walk: thread -> column lc = tid % 64, rows [8 * (tid / 64), +8); E, SW, S, SE pairs
+    const int lc = tid & (T - 1), lr0 = (tid >> 6) * (T / 8);
+    int ci = (lr0 + 1) * WP + lc + 1;
+    u32 a_m = sl[ci], a_r = sl[ci + 1];
+#pragma unroll
+    for (int k = 0; k < T / 8; k++, ci += WP) {
+      const u32 b_l = sl[ci + WP - 1], b_m = sl[ci + WP], b_r = sl[ci + WP + 1];
+      if (a_m != EL_NONE) {
+        const u32 z_m = sz[ci];
+#define HC_PAIR(B, OFF)                                                     \
+        if ((B) != a_m && (B) != EL_NONE) {                                 \
+          const u32 wf = max(z_m, sz[ci + (OFF)]);                          \
+          const u32 lo = min(a_m, (B)), hi = max(a_m, (B));                 \
+          u32 *slot_ = &tab[((hi * (hi - 1)) >> 1) + lo];                   \
+          if (wf < *(volatile u32 *)slot_) atomicMin(slot_, wf);            \
+        }
+        HC_PAIR(a_r, 1) HC_PAIR(b_l, WP - 1) HC_PAIR(b_m, WP) HC_PAIR(b_r, WP + 1)
+#undef HC_PAIR
+      }
+      a_m = b_m; a_r = b_r;
+    }
+    __syncthreads();
+    // 4. emit the pairs that met in this tile (at least one end closed)
+    u32 mine = 0;
+    for (int i = tid; i < EL_TAB; i += EK_THREADS) mine += tab[i] != 0xFFFFFFFFu;
+    u32 off = mine ? atomicAdd(&s_cnt[0], mine) : 0u;
+    __syncthreads();
+    if (tid == 0) s_cnt[1] = s_cnt[0] ? atomicAdd(ecount, s_cnt[0]) : 0u;
+    __syncthreads();
+    if (!mine || (u64)s_cnt[1] + s_cnt[0] > (u64)ecap) return;   // overflow: the host falls back to grid rounds
+    u32 o = s_cnt[1] + off;
+    for (int i = tid; i < EL_TAB; i += EK_THREADS) {
+      const u32 w = tab[i];
+      if (w == 0xFFFFFFFFu) continue;
+      // i = hi * (hi - 1) / 2 + lo  ->  hi = floor((1 + sqrt(1 + 8 i)) / 2)
+      u32 hi = (u32)((1.0f + sqrtf(1.0f + 8.0f * (float)i)) * 0.5f);
+      while (hi * (hi - 1) / 2 > (u32)i) hi--;
+      while ((hi + 1) * hi / 2 <= (u32)i) hi++;
+      const u32 lo = (u32)i - hi * (hi - 1) / 2;
+      const u32 ga = gid[lo], gb = gid[hi];
+      const bool keep = ga >= nopen || gb >= nopen;
+      eA[o] = keep ? ga : 0u;   // (an open-open pair keeps its slot as a harmless 0-0 entry: the count was taken before)
+      eB[o] = keep ? gb : 0u;
+      eW[o] = d_funord(w);
+      o++;
+    }
+    return;
+  }
+  // ---- general path (too many basins meet in this tile): 64-bit-key hash, a thread keeps its last pair ----
+  if (dbg && tid == 0) HC_DBG(8, 1);
+  u64 *keys = (u64 *)(smem_e + EO_BIG);
+  u32 *ws = (u32 *)(smem_e + EO_BIG + EH_CAP * 8);
+  for (int i = tid; i < EH_CAP; i += EK_THREADS) { keys[i] = ~0ull; ws[i] = 0xFFFFFFFFu; }
+  __syncthreads();
+  {
+    // (no room for a u32 id per cell beside the hash: ids are read through P on the fly; the own cells are flat by
+    // now, a halo cell may still need the hop)
+    const int lc = tid & (T - 1), lr0 = (tid >> 6) * (T / 8);
+    u32 ka = HC_NONE, kb = HC_NONE, kw = 0xFFFFFFFFu;
+    auto lab = [&](int lr, int lc2) -> u32 {   // basin id of window cell (lr, lc2), HC_NONE if no cell
+      int r = r0 + lr - 1, c = c0 + lc2 - 1;
+      if (r < 0 || r >= ny || c < 0 || c >= nx) return HC_NONE;
+      u32 p = __ldcg(&P[(size_t)r * nx + c]);
+      if (!(p & HC_TAG)) p = __ldcg(&P[p]);
+      p &= 0x7FFFFFFFu;
+      return p == HC_LAB_NODATA ? HC_NONE : p;
+    };
+    for (int k = 0; k < T / 8; k++) {
+      const int lr = lr0 + 1 + k, lcc = lc + 1;
+      const int ci = lr * WP + lcc;
+      const u32 a_m = lab(lr, lcc);
+      if (a_m == HC_NONE) continue;
+      const u32 z_m = sz[ci];
+      const int offs[4][2] = {{0, 1}, {1, -1}, {1, 0}, {1, 1}};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const u32 b = lab(lr + offs[q][0], lcc + offs[q][1]);
+        if (b == a_m || b == HC_NONE || (a_m < nopen && b < nopen)) continue;
+        const u32 wf = max(z_m, sz[ci + offs[q][0] * WP + offs[q][1]]);
+        const u32 lo = a_m < b ? a_m : b, hi = a_m < b ? b : a_m;
+        if (lo == ka && hi == kb) kw = wf < kw ? wf : kw;
+        else {
+          if (ka != HC_NONE) eh_insert(keys, ws, ka, kb, kw, eA, eB, eW, ecount, ecap);
+          ka = lo; kb = hi; kw = wf;
+        }
+      }
+    }
+    if (ka != HC_NONE) eh_insert(keys, ws, ka, kb, kw, eA, eB, eW, ecount, ecap);
+  }
+  __syncthreads();
+  u32 mine = 0;
+  for (int i = tid; i < EH_CAP; i += EK_THREADS) mine += keys[i] != ~0ull;
+  u32 off = mine ? atomicAdd(&s_cnt[0], mine) : 0u;
+  __syncthreads();
+  if (tid == 0) s_cnt[1] = s_cnt[0] ? atomicAdd(ecount, s_cnt[0]) : 0u;
+  __syncthreads();
+  if (!mine || (u64)s_cnt[1] + s_cnt[0] > (u64)ecap) return;
+  u32 o = s_cnt[1] + off;
+  for (int i = tid; i < EH_CAP; i += EK_THREADS) {
+    const u64 k = keys[i];
+    if (k == ~0ull) continue;
+    eA[o] = (u32)(k >> 32);
+    eB[o] = (u32)(k & 0xFFFFFFFFu);
+    eW[o] = d_funord(ws[i]);
+    o++;
   }
 }
 
@@ -499,7 +793,7 @@ static int bor_contract(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, u32 *
 struct bor_pargs {
   u64 *best; u32 *rep, *hp, *ptr, *ptr2; float *lvl;
   const u32 *eA, *eB; const float *eW; uint8_t *mark; u32 *ctl;
-  u32 K1, nopen, ne; int msf, idx_keys, do_init, max_rounds, skip_pick;
+  u32 K1, nopen, ne; int msf, idx_keys, do_init, max_rounds, skip_pick, both;
 };
 __global__ void __launch_bounds__(512)
 k_bor_persistent(bor_pargs a) {
@@ -512,6 +806,10 @@ k_bor_persistent(bor_pargs a) {
   if (tid < 9) a.ctl[tid] = 0;
   grid.sync();
   int round = 0;
+  // phase time stamps of thread 0 (ns), ctl[32 + 2 i]: diagnostic, read with HC_TRACE
+  int ts_n = 0;
+#define HC_TS() do { if (tid == 0 && ts_n < 96) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ((unsigned long long *)(a.ctl + 32))[ts_n++] = t_; } } while (0)
+  HC_TS();
   for (; round < a.max_rounds; round++) {
     // (skip_pick: best[] was filled by a grid pass over the raster; this launch only contracts)
     if (!a.skip_pick) {
@@ -526,12 +824,21 @@ k_bor_persistent(bor_pargs a) {
         u64 key = ((u64)d_ford(a.eW[i]) << 32) | (u64)i;
         if (ra >= a.nopen && key < __ldcg(&a.best[ra])) atomicMin(&a.best[ra], key);
         if (rb >= a.nopen && key < __ldcg(&a.best[rb])) atomicMin(&a.best[rb], key);
-      } else if (ra >= a.nopen) {
-        u64 key = ((u64)d_ford(a.eW[i]) << 32) | (u64)rb;
-        if (key < __ldcg(&a.best[ra])) atomicMin(&a.best[ra], key);
+      } else {
+        // key (weight, neighbour): the fill's lists; both = 1: undirected entries, either end may pick
+        const u64 wk = (u64)d_ford(a.eW[i]) << 32;
+        if (ra >= a.nopen) {
+          u64 key = wk | (u64)rb;
+          if (key < __ldcg(&a.best[ra])) atomicMin(&a.best[ra], key);
+        }
+        if (a.both && rb >= a.nopen) {
+          u64 key = wk | (u64)ra;
+          if (key < __ldcg(&a.best[rb])) atomicMin(&a.best[rb], key);
+        }
       }
     }
     grid.sync();
+    HC_TS();
     }
     // hook -> ptr2
     for (u32 b = tid; b < a.K1; b += nth) {
@@ -551,6 +858,7 @@ k_bor_persistent(bor_pargs a) {
       }
     }
     grid.sync();
+    HC_TS();
     // break mutual pairs -> ptr
     for (u32 b = tid; b < a.K1; b += nth) {
       u32 p = __ldcg(&a.ptr2[b]);
@@ -558,6 +866,7 @@ k_bor_persistent(bor_pargs a) {
       a.ptr[b] = p;
     }
     grid.sync();
+    HC_TS();
     // pointer doubling to the roots
     for (int it = 0;; it++) {
       u32 *flag = &a.ctl[it % 3];
@@ -566,12 +875,20 @@ k_bor_persistent(bor_pargs a) {
       for (u32 b = tid; b < a.K1; b += nth) {
         u32 p = __ldcg(&a.ptr[b]);
         u32 pp = __ldcg(&a.ptr[p]);
-        if (pp != p) { a.ptr[b] = pp; ch = 1; }
+        if (pp != p) {
+          // two more hops per sweep (paths shrink 4x per grid barrier instead of 2x)
+          u32 p3 = __ldcg(&a.ptr[pp]);
+          p3 = __ldcg(&a.ptr[p3]);
+          a.ptr[b] = p3; ch = 1;
+        }
       }
-      if (ch) *flag = 1u;
+      // one flag store per block: hundreds of thousands of stores to one address serialise in its L2 slice
+      ch = __syncthreads_or(ch);
+      if (ch && threadIdx.x == 0) *flag = 1u;
       grid.sync();
       if (!__ldcg(flag)) break;
     }
+    HC_TS();
     // merge trees into their roots
     u32 *ctr = &a.ctl[3 + 2 * (round & 1)];
     if (tid == 0) { a.ctl[3 + 2 * ((round + 1) & 1)] = 0; a.ctl[4 + 2 * ((round + 1) & 1)] = 0; }
@@ -582,8 +899,15 @@ k_bor_persistent(bor_pargs a) {
       if (r != b) { a.hp[b] = r; a.rep[b] = r; nmer++; }
       else nact++;
     }
-    if (nact) atomicAdd(ctr, nact);
-    if (nmer) atomicAdd(ctr + 1, nmer);
+    // (block totals first: one atomic per block, not one per thread, on the two shared counters)
+    nact = __reduce_add_sync(0xFFFFFFFFu, nact);
+    nmer = __reduce_add_sync(0xFFFFFFFFu, nmer);
+    __shared__ u32 s_act, s_mer;
+    if (threadIdx.x == 0) { s_act = 0; s_mer = 0; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { if (nact) atomicAdd(&s_act, nact); if (nmer) atomicAdd(&s_mer, nmer); }
+    __syncthreads();
+    if (threadIdx.x == 0) { if (s_act) atomicAdd(ctr, s_act); if (s_mer) atomicAdd(ctr + 1, s_mer); }
     grid.sync();
     for (u32 b = tid; b < a.K1; b += nth) {
       u32 s0 = __ldcg(&a.rep[b]);
@@ -591,10 +915,11 @@ k_bor_persistent(bor_pargs a) {
       if (r != s0) a.rep[b] = r;
     }
     grid.sync();
+    HC_TS();
     const u32 active = __ldcg(ctr), merged = __ldcg(ctr + 1);
     if (active == 0 || merged == 0) { round++; break; }
   }
-  if (tid == 0) { a.ctl[7] = (u32)round; a.ctl[8] = a.ctl[3 + 2 * ((round - 1) & 1)]; }   // rounds done, closed roots left
+  if (tid == 0) { a.ctl[7] = (u32)round; a.ctl[8] = a.ctl[3 + 2 * ((round - 1) & 1)]; a.ctl[9] = (u32)ts_n; }   // rounds done, closed roots left
 }
 
 // launch helper: as many co-resident 512-thread blocks as the work needs (at most the device holds)
@@ -627,7 +952,7 @@ static int bor_list_solve(hc_ctx *ctx, const bor_tabs &t, u32 K1, u32 nopen, con
   bor_pargs a;
   a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
   a.eA = eA; a.eB = eB; a.eW = eW; a.mark = mark; a.ctl = cnt + 16;
-  a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = msf; a.idx_keys = 1; a.do_init = 1; a.max_rounds = 64; a.skip_pick = 0;
+  a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = msf; a.idx_keys = 1; a.do_init = 1; a.max_rounds = 64; a.skip_pick = 0; a.both = 0;
   if (!getenv("HC_BAND_STATS")) rounds = nullptr;   // (the diagnostic read-back costs a host sync per solve)
   return bor_persistent_launch(ctx, a, rounds, st);
 }
@@ -664,18 +989,24 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
     ext = has_interior ? e : nullptr;  // every nodata cell sits on the raster border: all exterior
   }
   u32 *P = (u32 *)arena_take(ctx, n * 4);
-  u32 *cnt = (u32 *)arena_take(ctx, 256);  // [0]=pit counter [1]=changed [2]=n_active [3]=n_merged [4]=edges
+  u32 *cnt = (u32 *)arena_take(ctx, 2048);  // [0]=pit counter [1]=changed [2]=n_active [3]=n_merged [4]=edges
   uint8_t *seam_seed = (uint8_t *)arena_take(ctx, banded ? (size_t)2 * nx : 1);
   if (!P || !cnt || !seam_seed) return HC_ERR_NOMEM;
   (void)tiles;
   const u32 nopen = banded ? (u32)(2 * nx + 1) : 1u;
 
-  HC_CUDA(cudaMemsetAsync(cnt, 0, 256, st));
+  HC_CUDA(cudaMemsetAsync(cnt, 0, 2048, st));
   if (banded) HC_CUDA(cudaMemsetAsync(seam_seed, 0, (size_t)2 * nx, st));
   dim3 tg(tx, ty);
-  HC_PROF(ctx, st, "k_ptr");
-  k_ptr<<<tg, NTHREADS, 0, st>>>(z, ext, P, (int)ny, (int)nx, nodata, cnt, rw, nopen - 1, seam_seed);
-  HC_LAUNCH_CHECK(ctx);
+  {
+    // window map over every readable row (a band's halo rows included): box 68 x 66, origin row rw.rlo
+    hc_tmap mzp;
+    hc_tmap_2d(&mzp, z + (long long)rw.rlo * nx, 4, 1, (uint64_t)nx, (uint64_t)(rw.rhi - rw.rlo), (uint64_t)nx * 4, KP_WP, TH);
+    HC_PROF(ctx, st, "k_ptr");
+    if (mzp.ok) k_ptr<true><<<tg, NTHREADS, 0, st>>>(z, mzp.map, ext, P, (int)ny, (int)nx, nodata, cnt, rw, nopen - 1, seam_seed);
+    else k_ptr<false><<<tg, NTHREADS, 0, st>>>(z, mzp.map, ext, P, (int)ny, (int)nx, nodata, cnt, rw, nopen - 1, seam_seed);
+    HC_LAUNCH_CHECK(ctx);
+  }
   HC_PROF(ctx, st, "k_perim");
   k_perim<<<tg, 256, 0, st>>>(P, (int)ny, (int)nx);
   HC_LAUNCH_CHECK(ctx);
@@ -718,6 +1049,51 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
     k_flatten<<<gblocks, 256, 0, st>>>(P, n);
     HC_LAUNCH_CHECK(ctx);
   }
+  if (K > 0 && !getenv("HC_FILL_GRID_ROUNDS")) {
+    // one grid pass lists the basin graph (per-tile deduplicated), then every Boruvka round runs on that list in
+    // one cooperative launch; only if the list overflows (every cell its own basin) the grid rounds below take over
+    static bool attr_set = false;
+    if (!attr_set) {
+      HC_CUDA(cudaFuncSetAttribute(k_edges<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGES_SMEM));
+      HC_CUDA(cudaFuncSetAttribute(k_edges<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGES_SMEM));
+      attr_set = true;
+    }
+    HC_CUDA(cudaMemsetAsync(cnt + 4, 0, 4, st));
+    hc_tmap mz, mp;
+    hc_tmap_2d(&mz, z, 4, 1, (uint64_t)nx, (uint64_t)ny, (uint64_t)nx * 4, WP, TH);
+    hc_tmap_2d(&mp, P, 4, 0, (uint64_t)nx, (uint64_t)ny, (uint64_t)nx * 4, WP, TH);
+    HC_PROF(ctx, st, "k_edges");
+    if (mz.ok && mp.ok)
+      k_edges<true><<<tg, EK_THREADS, EDGES_SMEM, st>>>(z, P, mz.map, mp.map, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen, ctx->d_dbg);
+    else
+      k_edges<false><<<tg, EK_THREADS, EDGES_SMEM, st>>>(z, P, mz.map, mp.map, (int)ny, (int)nx, eA, eB, eW, cnt + 4, ecap, nopen, ctx->d_dbg);
+    HC_LAUNCH_CHECK(ctx);
+    HC_CUDA(cudaMemcpyAsync(ctx->h_mail + 4, cnt + 4, 4, cudaMemcpyDeviceToHost, st));
+    HC_CUDA(cudaStreamSynchronize(st));
+    ne = ctx->h_mail[4];
+    if (getenv("HC_TRACE")) fprintf(stderr, "[fill] %u basins, edge list %u of %u\n", K, ne, ecap);
+    if (ne <= ecap) {
+      bor_pargs a;
+      a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
+      a.eA = eA; a.eB = eB; a.eW = eW; a.mark = nullptr; a.ctl = cnt + 16;
+      a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = 0; a.idx_keys = 0; a.do_init = 0; a.max_rounds = 64; a.skip_pick = 0; a.both = 1;
+      HC_TRY(bor_persistent_launch(ctx, a, nullptr, st));
+      // rounds: diagnostic only, fetched without a synchronisation (hc_fill_stats reads it after the caller's own)
+      HC_CUDA(cudaMemcpyAsync(ctx->h_mail + 32, cnt + 16 + 7, 4, cudaMemcpyDeviceToHost, st));
+      ctx->fill_rounds = -1;
+      if (getenv("HC_TRACE")) {
+        static unsigned long long ts[100];
+        u32 c3[3];
+        HC_CUDA(cudaStreamSynchronize(st));
+        HC_CUDA(cudaMemcpy(c3, cnt + 16 + 7, 12, cudaMemcpyDeviceToHost));
+        HC_CUDA(cudaMemcpy(ts, cnt + 16 + 32, 96 * 8, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[fill] list rounds %u, closed roots left %u; phase us:", c3[0], c3[1]);
+        for (u32 i = 1; i < c3[2] && i < 96; i++) fprintf(stderr, " %.1f", (double)(ts[i] - ts[i - 1]) * 1e-3);
+        fprintf(stderr, "\n");
+      }
+      active = 0;
+    }
+  }
   while (active > 0) {
     if (round > 64) { hc_set_error("fill: Boruvka did not converge"); return HC_ERR_INTERNAL; }
     HC_CUDA(cudaMemsetAsync(t.best, 0xFF, (size_t)K1 * 8, st));
@@ -743,7 +1119,7 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
       bor_pargs a;
       a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
       a.eA = nullptr; a.eB = nullptr; a.eW = nullptr; a.mark = nullptr; a.ctl = cnt + 16;
-      a.K1 = K1; a.nopen = nopen; a.ne = 0; a.msf = 0; a.idx_keys = 0; a.do_init = 0; a.max_rounds = 1; a.skip_pick = 1;
+      a.K1 = K1; a.nopen = nopen; a.ne = 0; a.msf = 0; a.idx_keys = 0; a.do_init = 0; a.max_rounds = 1; a.skip_pick = 1; a.both = 0;
       HC_TRY(bor_persistent_launch(ctx, a, nullptr, st));
       HC_CUDA(cudaMemcpyAsync(ctx->h_mail, cnt + 16 + 8, 4, cudaMemcpyDeviceToHost, st));
       HC_CUDA(cudaStreamSynchronize(st));
@@ -767,14 +1143,14 @@ static int fill_local(hc_ctx *ctx, const float *z, int64_t ny, int64_t nx, float
       bor_pargs a;
       a.best = t.best; a.rep = t.rep; a.hp = t.hp; a.ptr = t.ptr; a.ptr2 = t.ptr2; a.lvl = t.lvl;
       a.eA = eA; a.eB = eB; a.eW = eW; a.mark = nullptr; a.ctl = cnt + 16;
-      a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = 0; a.idx_keys = 0; a.do_init = 0; a.max_rounds = 64; a.skip_pick = 0;
+      a.K1 = K1; a.nopen = nopen; a.ne = ne; a.msf = 0; a.idx_keys = 0; a.do_init = 0; a.max_rounds = 64; a.skip_pick = 0; a.both = 0;
       int more = 0;
       HC_TRY(bor_persistent_launch(ctx, a, &more, st));
       round += more;
       active = 0;
     }
   }
-  ctx->fill_rounds = round;
+  if (ctx->fill_rounds != -1) ctx->fill_rounds = round;
 
   HC_PROF(ctx, st, "k_levels");
   k_levels<<<tgK, tb, 0, st>>>(t.hp, t.lvl, level0, banded ? troot : nullptr, K1, nopen);

@@ -218,6 +218,240 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
   if (tid == 0) tile_pending[blockIdx.y * gridDim.x + blockIdx.x] = (uint8_t)(pend ? 1 : 0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sparse form of the fast tier.  On a filled DEM only a few percent of the cells are NOFLOW (3.4 % on the C2
+// recipe), yet k_flat_fast stages and classifies all 80 x 80 cells of its region to find them.  k_flat_list
+// compacts the NOFLOW cells of every tile once (one byte read per cell, raster order inside the tile);
+// k_flat_fast_sparse then builds its region's work list from the lists of the 3 x 3 tiles around it, reads the
+// 3 x 3 elevations of just those cells, and keeps the per-cell state in the same 80 x 80 shared grid — same
+// rules, same result, a small fraction of the instructions.
+// ------------------------------------------------------------------------------------------------
+#define NFCAP 1024   // listed NOFLOW cells per tile; a tile with more is "dense": its region is left to the slow tier
+
+__global__ void __launch_bounds__(256)
+k_flat_list(const uint8_t *__restrict__ dir, int ny, int nx, unsigned short *__restrict__ lists, u32 *__restrict__ counts) {
+  __shared__ u32 s_w[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = tid >> 2, lc0 = (tid & 3) * 16;
+  const int r = blockIdx.y * T + lr, c0 = blockIdx.x * T + lc0;
+  u32 m = 0;
+  if (r < ny && c0 < nx) {
+    const uint8_t *row = dir + (size_t)r * nx + c0;
+    if (c0 + 16 <= nx && (((uintptr_t)row) & 15u) == 0) {
+      const uint4 q = __ldg((const uint4 *)row);
+      const u32 w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if (((w4[j] >> (8 * b)) & 0xFFu) == HC_DIR_NOFLOW) m |= 1u << (4 * j + b);
+    } else {
+      for (int j = 0; j < 16 && c0 + j < nx; j++)
+        if (__ldg(row + j) == HC_DIR_NOFLOW) m |= 1u << j;
+    }
+  }
+  const u32 cnt = __popc(m);
+  u32 inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { u32 t_ = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t_; }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  u32 base = 0;
+  for (int w = 0; w < warp; w++) base += s_w[w];
+  u32 off = base + inc - cnt;
+  const size_t tile = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1;
+    if (off < NFCAP) lists[tile * NFCAP + off] = (unsigned short)(lr * T + lc0 + j);
+    off++;
+  }
+  if (tid == 255) counts[tile] = base + inc;
+}
+
+#define FS_THREADS 128
+#define FS_SMEM (FR * FR * 4 + FLCAP * 4 + 16)
+
+template <int TABLE>
+__global__ void __launch_bounds__(FS_THREADS)
+k_flat_fast_sparse(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB,
+                   const unsigned short *__restrict__ lists, const u32 *__restrict__ counts,
+                   uint8_t *__restrict__ tile_pending, int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned short *slo = (unsigned short *)smem;                          // [OPEN | NF | lo:14] per region cell
+  unsigned short *shi = (unsigned short *)(smem + FR * FR * 2);
+  unsigned short *list = (unsigned short *)(smem + FR * FR * 4);         // region index of the work cells
+  unsigned short *lmask = (unsigned short *)(smem + FR * FR * 4 + FLCAP * 2);   // [low-edge neighbours : 8 | NOFLOW neighbours : 8]
+  u32 *s_n = (u32 *)(smem + FR * FR * 4 + FLCAP * 4);                    // [0] work cells, [1] give up
+  const int tid = threadIdx.x;
+  const int by = blockIdx.y, bx = blockIdx.x, ty = gridDim.y, tx = gridDim.x;
+  const int r0 = by * T - FH, c0 = bx * T - FH;
+  if (tid < 2) s_n[tid] = 0;
+  {
+    uint4 *q = (uint4 *)smem;
+    for (int i = tid; i < FR * FR * 4 / 16; i += FS_THREADS) q[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  // 1. the region's NOFLOW cells from the lists of the 3 x 3 tiles around
+  for (int t9 = 0; t9 < 9; t9++) {
+    const int dy = t9 / 3 - 1, dx = t9 % 3 - 1;
+    const int yy = by + dy, xx = bx + dx;
+    if (yy < 0 || yy >= ty || xx < 0 || xx >= tx) continue;
+    const size_t tile = (size_t)yy * tx + xx;
+    const u32 cnt = counts[tile];
+    if (cnt > NFCAP) { if (tid == 0) s_n[1] = 1; continue; }
+    for (u32 k = tid; k < cnt; k += FS_THREADS) {
+      const int li = lists[tile * NFCAP + k];
+      const int rr = (li >> 6) + T * dy + FH, cc = (li & (T - 1)) + T * dx + FH;
+      if (rr < 0 || rr >= FR || cc < 0 || cc >= FR) continue;
+      const int ri = rr * FR + cc;
+      // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
+      if (rr == 0 || cc == 0 || rr == FR - 1 || cc == FR - 1) slo[ri] = (unsigned short)(F_NF | F_OPEN);
+      else {
+        slo[ri] = (unsigned short)F_NF;
+        const u32 pos = atomicAdd(&s_n[0], 1u);
+        if (pos < FLCAP) list[pos] = (unsigned short)ri;
+      }
+    }
+  }
+  // ... and a NOFLOW cell of a band's halo row belongs to the neighbouring band: open too (no tile lists them)
+  if (rw.top && by == 0) {
+    const int rr = -1 - r0;   // region row of raster row -1
+    for (int cc = tid; cc < FR; cc += FS_THREADS) {
+      const int c = c0 + cc;
+      if (c >= 0 && c < nx && __ldg(dirA - (long long)nx + c) == HC_DIR_NOFLOW) slo[rr * FR + cc] = (unsigned short)(F_NF | F_OPEN);
+    }
+  }
+  if (rw.bot) {
+    const int rr = ny - r0;   // region row of raster row ny
+    if (rr >= 0 && rr < FR)
+      for (int cc = tid; cc < FR; cc += FS_THREADS) {
+        const int c = c0 + cc;
+        if (c >= 0 && c < nx && __ldg(dirA + (long long)ny * nx + c) == HC_DIR_NOFLOW) slo[rr * FR + cc] = (unsigned short)(F_NF | F_OPEN);
+      }
+  }
+  __syncthreads();
+  const u32 nlist = s_n[0];
+  bool giveup = nlist > FLCAP || s_n[1];
+  if (!giveup && nlist) {
+    // 2. edges: a NOFLOW cell next to higher ground is a high edge (hi = 1); next to an equal cell that HAS a
+    //    direction (a low edge) it starts at lo = 2; equal NOFLOW neighbours are remembered as a mask
+    for (u32 k = tid; k < nlist; k += FS_THREADS) {
+      const int ri = list[k];
+      const int rr = ri / FR, cc = ri - rr * FR;
+      const int r = r0 + rr, c = c0 + cc;
+      const float v = __ldg(z + (long long)r * nx + c);
+      u32 mnf = 0, mlow = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int dr = c_dr[TABLE][j], dc = c_dc[TABLE][j];
+        const int nr = r + dr, nc = c + dc;
+        if (nr < rw.rlo || nr >= rw.rhi || nc < 0 || nc >= nx) continue;
+        const float zn = __ldg(z + (long long)nr * nx + nc);
+        if (zn == nodata) continue;
+        if (zn > v) hi = 1;
+        else if (zn == v) {
+          if (slo[ri + dr * FR + dc] & F_NF) mnf |= 1u << j;
+          else mlow |= 1u << j;
+        }
+      }
+      lmask[k] = (unsigned short)((mlow << 8) | mnf);
+      shi[ri] = (unsigned short)hi;
+      if (mlow) slo[ri] = (unsigned short)(F_NF | 2u);
+    }
+    __syncthreads();
+    // 3. relax the two distance fields and the "open" flag to their fixed point
+    int sweeps = 0;
+    for (;;) {
+      int changed = 0;
+      for (u32 k = tid; k < nlist; k += FS_THREADS) {
+        const int ri = list[k];
+        u32 mnf = lmask[k] & 0xFFu;
+        if (!mnf) continue;
+        const u32 w = slo[ri];
+        const u32 lo = w & F_LO, hi = shi[ri];
+        u32 blo = lo ? lo : 0xFFFFu, bhi = hi ? hi : 0xFFFFu;
+        u32 open = w & F_OPEN;
+        while (mnf) {
+          const int j = __ffs(mnf) - 1;
+          mnf &= mnf - 1;
+          const int ni = ri + c_dr[TABLE][j] * FR + c_dc[TABLE][j];
+          const u32 nw = slo[ni];
+          const u32 nlo = nw & F_LO;
+          if (nlo && nlo + 1 < blo) blo = nlo + 1;
+          const u32 nhi = shi[ni];
+          if (nhi && nhi + 1 < bhi) bhi = nhi + 1;
+          open |= nw & F_OPEN;
+        }
+        if (blo == 0xFFFFu) blo = 0;
+        if (bhi == 0xFFFFu) bhi = 0;
+        const u32 nw2 = F_NF | open | blo;
+        if (nw2 != w) { slo[ri] = (unsigned short)nw2; changed = 1; }
+        if (bhi != hi) { shi[ri] = (unsigned short)bhi; changed = 1; }
+      }
+      sweeps++;
+      if (!__syncthreads_or(changed)) break;
+      if (sweeps >= FSWEEPS) { giveup = true; break; }
+    }
+    if (tid == 0) { HC_DBG(0, sweeps); HC_DBG(1, 1); }
+  }
+  // 4. write: dirB already holds dirA's codes, so only the NOFLOW cells of the own tile are touched — closed flats
+  //    get their direction, open ones are marked pending
+  int pend = 0;
+  if (!giveup) {
+    for (u32 k = tid; k < nlist; k += FS_THREADS) {
+      const int ri = list[k];
+      const int rr = ri / FR, cc = ri - rr * FR;
+      if (rr < FH || rr >= FH + T || cc < FH || cc >= FH + T) continue;   // not an own cell
+      const int r = r0 + rr, c = c0 + cc;
+      const u32 w = slo[ri];
+      uint8_t d = HC_DIR_NOFLOW;
+      if (w & F_OPEN) { d = HC_DIR_PENDING; pend = 1; }
+      else if (w & F_LO) {
+        const u32 mk = lmask[k];
+        const int own = 2 * (int)(w & F_LO) - (int)shi[ri];
+        int mn = own, best = -1;
+        bool bdiag = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          int key;
+          if ((mk >> j) & 1u) {
+            const int ni = ri + c_dr[TABLE][j] * FR + c_dc[TABLE][j];
+            const u32 nw = slo[ni];
+            if (!(nw & F_LO)) continue;
+            key = 2 * (int)(nw & F_LO) - (int)shi[ni];
+          } else if ((mk >> (8 + j)) & 1u) {
+            key = -0x40000000;
+          } else continue;
+          const bool kdiag = (c_dr[TABLE][j] != 0) && (c_dc[TABLE][j] != 0);
+          if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = j; bdiag = kdiag; }
+        }
+        if (best >= 0) d = (uint8_t)c_code[TABLE][best];
+      }
+      if (d != HC_DIR_NOFLOW) dirB[(size_t)r * nx + c] = d;
+    }
+  } else {
+    // dense / overflowing region: every NOFLOW cell of the own tile goes to the slow tier
+    const size_t tile = (size_t)by * tx + bx;
+    const u32 cnt = counts[tile];
+    if (cnt > NFCAP) {
+      for (int i = tid; i < T * T; i += FS_THREADS) {
+        const int r = by * T + i / T, c = bx * T + i % T;
+        if (r < ny && c < nx && dirA[(size_t)r * nx + c] == HC_DIR_NOFLOW) { dirB[(size_t)r * nx + c] = HC_DIR_PENDING; pend = 1; }
+      }
+    } else {
+      for (u32 k = tid; k < cnt; k += FS_THREADS) {
+        const int li = lists[tile * NFCAP + k];
+        dirB[(size_t)(by * T + (li >> 6)) * nx + (bx * T + (li & (T - 1)))] = HC_DIR_PENDING;
+        pend = 1;
+      }
+    }
+  }
+  pend = __syncthreads_or(pend);
+  if (tid == 0 && pend) HC_DBG(2, 1);  // pending tiles
+  if (tid == 0) tile_pending[(size_t)by * tx + bx] = (uint8_t)(pend ? 1 : 0);
+}
+
 // active = pending tiles and their 8 neighbours; also counts pending tiles
 __global__ void k_flat_dilate(const uint8_t *__restrict__ pending, uint8_t *__restrict__ active, int tx, int ty,
                               u32 *__restrict__ n_pending, hc_rows rw) {
@@ -749,12 +983,28 @@ static int flats_fast_tier(hc_ctx *ctx, const float *z, const uint8_t *dirA, uin
     attr_set = true;
   }
   dim3 tg(tx, ty);
-  HC_PROF(ctx, st, "k_flat_fast");
-  if (table == HC_TABLE_WBT)
-    k_flat_fast<HC_TABLE_WBT><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
-  else
-    k_flat_fast<HC_TABLE_TAUDEM><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
-  HC_LAUNCH_CHECK(ctx);
+  if (getenv("HC_FLAT_DENSE_FAST")) {
+    HC_PROF(ctx, st, "k_flat_fast");
+    if (table == HC_TABLE_WBT)
+      k_flat_fast<HC_TABLE_WBT><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
+    else
+      k_flat_fast<HC_TABLE_TAUDEM><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
+    HC_LAUNCH_CHECK(ctx);
+  } else {
+    // sparse fast tier: per-tile lists of the NOFLOW cells, then only those cells are looked at
+    unsigned short *lists = (unsigned short *)arena_take(ctx, tiles * NFCAP * 2);
+    u32 *counts = (u32 *)arena_take(ctx, tiles * 4);
+    if (!lists || !counts) return HC_ERR_NOMEM;
+    HC_PROF(ctx, st, "k_flat_list");
+    k_flat_list<<<tg, 256, 0, st>>>(dirA, (int)ny, (int)nx, lists, counts);
+    HC_LAUNCH_CHECK(ctx);
+    HC_PROF(ctx, st, "k_flat_fast_sparse");
+    if (table == HC_TABLE_WBT)
+      k_flat_fast_sparse<HC_TABLE_WBT><<<tg, FS_THREADS, FS_SMEM, st>>>(z, dirA, dirB, lists, counts, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
+    else
+      k_flat_fast_sparse<HC_TABLE_TAUDEM><<<tg, FS_THREADS, FS_SMEM, st>>>(z, dirA, dirB, lists, counts, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
+    HC_LAUNCH_CHECK(ctx);
+  }
   HC_CUDA(cudaMemsetAsync(bs->flag, 0, 64, st));
   HC_PROF(ctx, st, "k_flat_dilate");
   k_flat_dilate<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(bs->pending, bs->active, tx, ty, bs->flag + 1, rw);

@@ -195,7 +195,7 @@ int label_run(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_
 
 // ---- exterior nodata (WBT seed rule) ------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_nodata_mask(const float *__restrict__ z, uint8_t *__restrict__ m, int ny, int nx, float nodata, u32 *interior) {
+k_nodata_mask(const float *__restrict__ z, uint8_t *__restrict__ m, int ny, int nx, float nodata, u32 *interior, int last_col) {
   size_t n = (size_t)ny * nx;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -206,7 +206,7 @@ k_nodata_mask(const float *__restrict__ z, uint8_t *__restrict__ m, int ny, int 
     m[i] = nd;
     if (nd) {
       int r = (int)(i / (size_t)nx), c = (int)(i - (size_t)r * nx);
-      if (r > 0 && c > 0 && r < ny - 1 && c < nx - 1) any = 1;
+      if (r > 0 && c > 0 && r < ny - 1 && c < last_col) any = 1;   // (last_col: last real column; padding beyond it is exterior)
     }
   }
   if (any) *interior = 1u;
@@ -245,7 +245,7 @@ int ext_nodata_mask(hc_ctx *ctx, const float *z, uint8_t *ext, int64_t ny, int64
   if (!flagw) return HC_ERR_NOMEM;
   HC_CUDA(cudaMemsetAsync(flagw, 0, 4, st));
   HC_PROF(ctx, st, "k_nodata_mask");
-  k_nodata_mask<<<ctx->sm_count * 8, 256, 0, st>>>(z, ext, (int)ny, (int)nx, nodata, flagw);
+  k_nodata_mask<<<ctx->sm_count * 8, 256, 0, st>>>(z, ext, (int)ny, (int)nx, nodata, flagw, (ctx->pad_from > 0 ? ctx->pad_from : (int)nx) - 1);
   HC_LAUNCH_CHECK(ctx);
   HC_CUDA(cudaMemcpyAsync(ctx->h_mail, flagw, 4, cudaMemcpyDeviceToHost, st));
   HC_CUDA(cudaStreamSynchronize(st));

@@ -26,7 +26,7 @@ class DepHandleCore:
     config_files/config_local.ini [parameters-depression-handling]) that the array-level pipeline reads."""
 
     def __init__(self, basename="DEM", nodataval=-9999, fill_method='WL', carvemethod='SC', maxcost=200, radius=50,
-                 min_dist=True, sfill=None, flat_increment=0.0, fill_vol_thresh=4000, carve_vol_thresh=2000,
+                 min_dist=False, sfill=1.0, flat_increment=0.0, fill_vol_thresh=12000, carve_vol_thresh=4000,
                  max_carve_depth=100, combined_fill_interval=0.2, del_temp_files=False, verbose_print=False, wbt=None):
         self.basename = basename
         self.nodataval = nodataval

@@ -71,3 +71,21 @@ def test_filter_weights_build_the_reference_kernels():
     k5 = stencils.build_kernel(w[2], dtype=np.float32)
     assert k5[2, 2] == 1.0 and k5[1, 1] == np.float32(0.7) and k5[0, 0] == np.float32(0.35)   # the docstring's 5x5 example
     assert np.all(stencils.build_kernel(cfg.filter_weights("mean")[3], dtype=np.float32) == 1.0)
+
+
+def test_dephandle_core_defaults_are_the_reference_ini():
+    """DepHandleCore() without arguments must condition with the reference's own parameters
+    (config_files/config_local.ini [parameters-depression-handling]; fixture from tests/golden/make_config_golden.py)."""
+    import inspect
+    import json
+    import os
+    from pydrodem_b200.models.depression_handling import DepHandleCore
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "config_local_dephandle.json")) as f:
+        ref = json.load(f)
+    sig = inspect.signature(DepHandleCore.__init__).parameters
+    for key, val in ref.items():
+        if key in ("verbose_print", "del_temp_files"):
+            continue
+        assert key in sig, key
+        assert sig[key].default == val, (key, sig[key].default, val)

@@ -142,3 +142,22 @@ def test_flats_spanning_many_tiles(seed, levels, oracle, cuda):
     got = hc.resolve_flats(f, d0, table=1)
     assert np.array_equal(got, want), f"{(got != want).sum()} cells differ"
     assert np.array_equal(hc.accum(got, table=1), oracle.accum(want, table=1))
+
+
+@pytest.mark.parametrize("case", [CASES[7], CASES[9], CASES[11], CASES[14]], ids=lambda c: f"{c[0]}x{c[1]}-{c[2]}-{c[3]}")
+@pytest.mark.parametrize("seed_mode,table", [(1, 1), (0, 0)], ids=["taudem", "wbt"])
+def test_chain_pitched_rasters_equal_dense(case, seed_mode, table, oracle, cuda):
+    """hc_fill_d8_accum_ld_dev (pitched rasters: rows padded to 64 elements, padding = nodata, TMA-staged tiles) must
+    give the dense call's / the oracle's result in the real columns, for widths that are not multiples of 4."""
+    import torch
+    import pydrodem_b200 as hc
+    z = _dem(case)
+    f, d, s, a = oracle.fill_d8_accum(z, dx=30.0, dy=30.0, seed_mode=seed_mode, table=table)
+    zp = hc.empty_raster(z.shape[0], z.shape[1], torch.float32, cuda)
+    zp.copy_(torch.from_numpy(z))
+    gf, gd, gs, ga = hc.fill_d8_accum(zp, dx=30.0, dy=30.0, seed_mode=seed_mode, table=table)
+    assert gf.stride(0) % 64 == 0 and gf.shape == z.shape
+    assert np.array_equal(gf.cpu().numpy(), f)
+    assert np.array_equal(gd.cpu().numpy(), d)
+    assert np.array_equal(gs.cpu().numpy(), s)
+    assert np.array_equal(ga.cpu().numpy().view(np.uint32), a)
