@@ -297,9 +297,7 @@ extern "C" int hc_fill_d8_accum_dev(hc_ctx *ctx, const float *z, float *filled, 
   if (ny && nx && (!z || !filled || !dir || !acc)) { hc_set_error("hc_fill_d8_accum: null pointer"); return HC_ERR_ARG; }
   if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("bad seed_mode"); return HC_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  HC_TRY(fill_run(ctx, z, filled, ny, nx, nodata, seed_mode, st));
-  if (resolve_flats) HC_TRY(d8_flats_run(ctx, filled, dir, slope, ny, nx, nodata, dx, dy, table, st));
-  else HC_TRY(d8_run(ctx, filled, dir, slope, ny, nx, nodata, dx, dy, table, st));
+  HC_TRY(fill_d8_flats_run(ctx, z, filled, dir, slope, ny, nx, nodata, dx, dy, seed_mode, table, resolve_flats, st));
   HC_TRY(accum_run(ctx, dir, acc, ny, nx, table, st));
   return HC_OK;
 }
@@ -336,11 +334,9 @@ extern "C" int hc_fill_d8_accum_ld_dev(hc_ctx *ctx, float *z, float *filled, uin
     HC_LAUNCH_CHECK(ctx);
   }
   ctx->pad_from = ld > nx ? (int)nx : 0;   // (the WBT seed rule's exterior-nodata search need not label the padding)
-  int rc = fill_run(ctx, z, filled, ny, ld, nodata, seed_mode, st);
+  int rc = fill_d8_flats_run(ctx, z, filled, dir, slope, ny, ld, nodata, dx, dy, seed_mode, table, resolve_flats, st);
   ctx->pad_from = 0;
   HC_TRY(rc);
-  if (resolve_flats) HC_TRY(d8_flats_run(ctx, filled, dir, slope, ny, ld, nodata, dx, dy, table, st));
-  else HC_TRY(d8_run(ctx, filled, dir, slope, ny, ld, nodata, dx, dy, table, st));
   HC_TRY(accum_run(ctx, dir, acc, ny, ld, table, st));
   return HC_OK;
 }
@@ -429,16 +425,13 @@ extern "C" int hc_fill_d8_accum_host_begin(hc_ctx *ctx, int slot, const float *z
     HC_LAUNCH_CHECK(ctx);
   }
   ctx->pad_from = ld > nx ? (int)nx : 0;
-  int rc = fill_run(ctx, (const float *)dz.p, (float *)df.p, ny, ld, nodata, seed_mode, sc);
+  int rc = fill_d8_flats_run(ctx, (const float *)dz.p, (float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, ld, nodata, dx, dy,
+                             seed_mode, table, resolve_flats, sc);
   ctx->pad_from = 0;
   HC_TRY(rc);
-  HC_CUDA(cudaEventRecord(ctx->ev_fill, sc));
-  HC_CUDA(cudaStreamWaitEvent(sx, ctx->ev_fill, 0));
-  HC_CUDA(cudaMemcpy2DAsync(filled, (size_t)nx * 4, df.p, (size_t)ld * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost, sx));
-  if (resolve_flats) HC_TRY(d8_flats_run(ctx, (const float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, ld, nodata, dx, dy, table, sc));
-  else HC_TRY(d8_run(ctx, (const float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, ld, nodata, dx, dy, table, sc));
   HC_CUDA(cudaEventRecord(ctx->ev_dir, sc));
   HC_CUDA(cudaStreamWaitEvent(sx, ctx->ev_dir, 0));
+  HC_CUDA(cudaMemcpy2DAsync(filled, (size_t)nx * 4, df.p, (size_t)ld * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost, sx));
   HC_CUDA(cudaMemcpy2DAsync(dir, (size_t)nx, dd.p, (size_t)ld, (size_t)nx, (size_t)ny, cudaMemcpyDeviceToHost, sx));
   if (slope) HC_CUDA(cudaMemcpy2DAsync(slope, (size_t)nx * 4, ds.p, (size_t)ld * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost, sx));
   HC_TRY(accum_run(ctx, (const uint8_t *)dd.p, (uint32_t *)da.p, ny, ld, table, sc));

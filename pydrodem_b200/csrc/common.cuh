@@ -157,6 +157,8 @@ __device__ __forceinline__ int d_code_to_k(int table, int code) {
 int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata, int seed_mode,
              cudaStream_t st);
 size_t fill_workspace(int64_t ny, int64_t nx);
+int fill_d8_flats_run(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope, int64_t ny, int64_t nx,
+                      float nodata, double dx, double dy, int seed_mode, int table, int resolve_flats, cudaStream_t st);
 // exterior-nodata raster of the WBT seed rule (label.cu); ext comes from the arena, no arena_reset inside
 int ext_nodata_mask(hc_ctx *ctx, const float *z, uint8_t *ext, int64_t ny, int64_t nx, float nodata,
                     int *has_interior, cudaStream_t st);

@@ -1172,6 +1172,177 @@ int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, fl
   return HC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 5b. apply + D8 in ONE tile pass (the whole-raster chain): filled = max(z, level[basin]) is formed for the tile and
+// its halo in shared memory and the D8 stencil (same arithmetic as d8.cu / oracle orc_d8) reads it from there, so the
+// filled raster is written once and never read back for the directions: z + P in (8 B/cell), filled + 2 x dir out
+// (6 B/cell) instead of apply (12) + D8 (6).  Windows of z and P arrive by TMA on pitched rasters (tma.cuh).
+// ---------------------------------------------------------------------------------------------
+struct fd8_params { double len[8]; float fact[8]; };
+
+template <int TABLE, bool SLOPE, bool TMA>
+__global__ void __launch_bounds__(NTHREADS)
+k_apply_d8(const float *__restrict__ z, const u32 *__restrict__ P, const __grid_constant__ CUtensorMap mz,
+           const __grid_constant__ CUtensorMap mp, const float *__restrict__ level0, float *__restrict__ filled,
+           uint8_t *__restrict__ dir, uint8_t *__restrict__ dir2, float *__restrict__ slope, int ny, int nx, float nodata,
+           fd8_params prm) {
+  __shared__ __align__(128) float sf_box[TH * WP];
+  __shared__ __align__(128) u32 sp_box[TH * WP];
+  __shared__ __align__(8) uint64_t mbar;
+  float *sf = sf_box + WXO;
+  u32 *sp = sp_box + WXO;
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float qnan = __int_as_float(0x7fc00000);
+  if (TMA) {
+    if (tid == 0) {
+      hc_mbar_init(&mbar, 1);
+      hc_mbar_expect_tx(&mbar, 2u * TH * WP * 4u);
+      hc_tma_load_2d(sf_box, &mz, &mbar, c0 - 1 - WXO, r0 - 1);
+      hc_tma_load_2d(sp_box, &mp, &mbar, c0 - 1 - WXO, r0 - 1);
+    }
+    __syncthreads();
+    hc_mbar_wait(&mbar, 0);
+  }
+  // window of FILLED elevations (NaN: no cell)
+  for (int lr = warp; lr < TH; lr += NTHREADS / 32) {
+    const int r = r0 + lr - 1;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const int lc = lane + 32 * m;
+      if (lc >= TH) break;
+      const int c = c0 + lc - 1;
+      const int i = lr * WP + lc;
+      const bool inb = r >= 0 && r < ny && c >= 0 && c < nx;
+      float v;
+      u32 p;
+      if (TMA) { v = sf[i]; p = sp[i]; }
+      else {
+        const size_t g = inb ? (size_t)r * nx + c : 0;
+        v = __ldg(&z[g]);
+        p = __ldg(&P[g]);
+      }
+      const u32 id = p & 0x7FFFFFFFu;
+      if (!inb || v == nodata || v != v) v = qnan;
+      else if (id != 0u && id != HC_LAB_NODATA) v = fmaxf(v, __ldg(&level0[id]));
+      sf[i] = v;
+    }
+  }
+  __syncthreads();
+  // column walk: thread -> column lc = tid % 64, rows [16 * (tid / 64), +16), 3x3 window in registers
+  const int lc = tid & (T - 1), lr0 = (tid >> 6) * (T / 4);
+  const int c = c0 + lc;
+  if (c >= nx) return;
+  float w[3][3];
+  {
+    const float *row = &sf[lr0 * WP + lc];
+    w[0][0] = row[0]; w[0][1] = row[1]; w[0][2] = row[2];
+    w[1][0] = row[WP]; w[1][1] = row[WP + 1]; w[1][2] = row[WP + 2];
+  }
+#pragma unroll 4
+  for (int k = 0; k < T / 4; k++) {
+    const int lr = lr0 + k, r = r0 + lr;
+    if (r >= ny) break;
+    const float *row = &sf[(lr + 2) * WP + lc];
+    w[2][0] = row[0]; w[2][1] = row[1]; w[2][2] = row[2];
+    const size_t g = (size_t)r * nx + c;
+    const float v = w[1][1];
+    uint8_t code;
+    float sl;
+    if (v != v) {
+      code = HC_DIR_NODATA;
+      sl = -1.0f;
+      filled[g] = __ldg(&z[g]);   // a nodata cell keeps its own value
+    } else {
+      filled[g] = v;
+      int best = -1;
+      bool contaminated = false;
+      double smax = 0.0;
+      float smaxf = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float zn = w[1 + c_dr[TABLE][j]][1 + c_dc[TABLE][j]];
+        contaminated |= zn != zn;   // (a NaN neighbour never wins below: every comparison with NaN is false)
+        if (TABLE == HC_TABLE_WBT) {
+          if (zn < v) {
+            double s_ = ((double)v - (double)zn) / prm.len[j];
+            if (s_ > smax) { smax = s_; best = j; }
+          }
+        } else {
+          float s_ = __fmul_rn(prm.fact[j], __fsub_rn(v, zn));
+          if (s_ > smaxf) { smaxf = s_; best = j; }
+        }
+      }
+      if (TABLE == HC_TABLE_TAUDEM && contaminated) {
+        code = HC_DIR_NODATA;
+        sl = -1.0f;
+      } else {
+        code = best < 0 ? (uint8_t)HC_DIR_NOFLOW : (uint8_t)c_code[TABLE][best];
+        sl = TABLE == HC_TABLE_WBT ? (float)smax : smaxf;
+      }
+    }
+    dir[g] = code;
+    if (dir2) dir2[g] = code;
+    if (SLOPE) slope[g] = sl;
+#pragma unroll
+    for (int j = 0; j < 3; j++) { w[0][j] = w[1][j]; w[1][j] = w[2][j]; }
+  }
+}
+
+template <int TABLE, bool SLOPE>
+static int apply_d8_launch(hc_ctx *ctx, const float *z, const fill_state &fs, float *filled, uint8_t *dir, uint8_t *dir2,
+                           float *slope, int64_t ny, int64_t nx, float nodata, const fd8_params &prm, cudaStream_t st) {
+  dim3 tg((unsigned)((nx + T - 1) / T), (unsigned)((ny + T - 1) / T));
+  hc_tmap mz, mp;
+  hc_tmap_2d(&mz, z, 4, 1, (uint64_t)nx, (uint64_t)ny, (uint64_t)nx * 4, WP, TH);
+  hc_tmap_2d(&mp, fs.P, 4, 0, (uint64_t)nx, (uint64_t)ny, (uint64_t)nx * 4, WP, TH);
+  HC_PROF(ctx, st, "k_apply_d8");
+  if (mz.ok && mp.ok)
+    k_apply_d8<TABLE, SLOPE, true><<<tg, NTHREADS, 0, st>>>(z, fs.P, mz.map, mp.map, fs.level0, filled, dir, dir2, slope, (int)ny, (int)nx, nodata, prm);
+  else
+    k_apply_d8<TABLE, SLOPE, false><<<tg, NTHREADS, 0, st>>>(z, fs.P, mz.map, mp.map, fs.level0, filled, dir, dir2, slope, (int)ny, (int)nx, nodata, prm);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+int flats_core(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx, float nodata,
+               int table, cudaStream_t st);
+
+// fill -> (apply + D8 fused) -> flat resolution, one arena generation: the head of hc_fill_d8_accum_*
+int fill_d8_flats_run(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope, int64_t ny, int64_t nx,
+                      float nodata, double dx, double dy, int seed_mode, int table, int resolve_flats, cudaStream_t st) {
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (table != HC_TABLE_WBT && table != HC_TABLE_TAUDEM) { hc_set_error("d8: bad table %d", table); return HC_ERR_ARG; }
+  if (!(dx > 0) || !(dy > 0)) { hc_set_error("d8: dx, dy must be > 0"); return HC_ERR_ARG; }
+  fill_state fs;
+  hc_rows rw = {0, (int)ny, 0, 0};
+  HC_TRY(fill_local(ctx, z, ny, nx, nodata, seed_mode, rw, &fs, st));
+  uint8_t *dirA = nullptr;
+  if (resolve_flats) {
+    dirA = (uint8_t *)arena_take(ctx, (size_t)ny * nx);
+    if (!dirA) return HC_ERR_NOMEM;
+  }
+  static const int DR[2][8] = {{-1, 0, 1, 1, 1, 0, -1, -1}, {0, -1, -1, -1, 0, 1, 1, 1}};
+  static const int DC[2][8] = {{1, 1, 1, 0, -1, -1, -1, 0}, {1, 1, 0, -1, -1, -1, 0, 1}};
+  fd8_params prm;
+  for (int k = 0; k < 8; k++) {
+    double l = sqrt((double)(DC[table][k] * DC[table][k]) * dx * dx + (double)(DR[table][k] * DR[table][k]) * dy * dy);
+    prm.len[k] = l;
+    prm.fact[k] = (float)(1.0 / l);
+  }
+  // with flats: D8 writes dirA (kept as the flat pass's read-only input) and dir; the flat pass rewrites NOFLOW cells of dir
+  uint8_t *d1 = resolve_flats ? dirA : dir, *d2 = resolve_flats ? dir : nullptr;
+  if (table == HC_TABLE_WBT) {
+    if (slope) HC_TRY((apply_d8_launch<HC_TABLE_WBT, true>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st)));
+    else HC_TRY((apply_d8_launch<HC_TABLE_WBT, false>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st)));
+  } else {
+    if (slope) HC_TRY((apply_d8_launch<HC_TABLE_TAUDEM, true>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st)));
+    else HC_TRY((apply_d8_launch<HC_TABLE_TAUDEM, false>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st)));
+  }
+  if (!resolve_flats) return HC_OK;
+  return flats_core(ctx, filled, dirA, dir, ny, nx, nodata, table, st);
+}
+
 // =============================================================================================
 // Row-band sharding (Barnes 2016 "Parallel priority-flood depression filling for
 // trillion cell DEMs" with a band as the tile).
