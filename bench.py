@@ -1,18 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — Mcells/s for fill + D8 (+flat resolution) + accumulation on the C2 workload.
+"""bench.py — Mcells/s for fill + D8 (+flat resolution) + accumulation (BASELINE.json's metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload ...]
 
-One "step" = one pass of the hot path (hc_fill_d8_accum: PitRemove -> D8FlowDir -> AreaD8 semantics,
-run_aws.py:580-617) over one synthetic 10801 x 10801 float32 DEM with random pits (BASELINE.json
-configs[1]) that is already resident in HBM.  `e2e` times the same call through the HOST-buffer C
-ABI (hc_fill_d8_accum_host) with pinned host arrays, H2D/D2H inside the timed region.  N > 1 runs
-one such unit per GPU (weak scaling, no data-path collective), timed as max over ranks.
+One "step" = one pass of the hot path (PitRemove -> D8FlowDir -> AreaD8 semantics, run_aws.py:580-617) over one batch of
+synthetic input that is already resident in HBM.
 
---impl reference times the CPU path on the host cores: the oracle port of the WhiteboxTools /
-TauDEM algorithms (the binaries pydrodem shells out to are not installable here), farmed over
-min(cores, 14) independent 3601^2 units the way the reference farms units over a process pool
-(models/depression_handling.py:1625-1635).
+  N = 1 (default)  workload C2 = BASELINE.json configs[1]: one synthetic 10801 x 10801 float32 DEM with random pits, through
+                   hc_fill_d8_accum_ld_dev on a pitched device raster (core.empty_raster: the TMA / vector path).
+  N > 1 (torchrun) workload C3 = configs[2]: ONE synthetic 40000 x 40000 DEM row-band-sharded over the N GPUs, halo and
+                   seam-graph exchange over NCCL (strong scaling; the headline line).  The same line carries, under
+                   config.weak_bands, the weak-scaling number (one 10801 x 10801 band per GPU of one 10801 x 10801 N DEM)
+                   and, under config.checks, whether the gathered bands equal the whole-raster chain bit for bit.
+  --workload c1    configs[0]: the per-unit depression pipeline (DepHandleCore.run_depression_core) on a 3601^2 DEM.
+  --workload c4 / c5 / bands / c3 / c2: the other configurations as extra measured lines.
+
+`e2e` times the same work through the host-buffer entry points (pinned host arrays in, results out, copies inside the timed
+region).  `roofline` describes the dominant FULL-GRID kernel (one launch sweeps the raster once); kernels that run many
+sparse launches per step are reported with their total time per step in `kernels`, never as a per-launch fraction.
+
+--impl reference times the CPU path on the host cores: the oracle port of the WhiteboxTools / TauDEM algorithms (the
+binaries pydrodem shells out to are not installable here), farmed over min(cores, 14) independent 3601^2 units the way
+the reference farms units over a process pool (models/depression_handling.py:1625-1635).
 """
 import argparse
 import json
@@ -43,7 +52,44 @@ KERNEL_PASS = {
     "k_acc_tile_local": "accum", "k_acc_tile_final": "accum", "k_acc_link_count": "accum", "k_acc_link_mark": "accum",
     "k_acc_link_walk": "accum", "k_acc_seam_exit": "accum", "k_seam_init": "accum", "k_seam_count": "accum",
     "k_seam_mark": "accum", "k_seam_walk": "accum", "k_acc_seam_apply": "accum", "k_acc_seam_inject": "accum",
+    "k_edges": "fill", "k_bor_persistent": "fill", "k_apply_d8": "fill+d8", "k_flat_list": "flats",
+    "k_flat_fast_sparse": "flats", "k_flat_queue_tiles": "flats", "k_pad_nodata": "fill",
 }
+# kernels whose ONE launch sweeps the whole raster once: the only candidates for the per-kernel roofline line, with the
+# algorithmic bytes per cell of what that launch reads and writes (z 4, filled 4, dir 1, acc 4; the
+# watershed-label raster P is internal and counted at its 4 B)
+FULL_GRID = {
+    "k_ptr": 8,             # z in, P out
+    "k_edges": 8,           # z + P in
+    "k_minedge": 8, "k_minedge_emit": 8,
+    "k_apply": 12,          # z + P in, filled out
+    "k_apply_d8": 14,       # z + P in, filled + 2 x dir out
+    "k_d8": 5,              # filled in, dir out
+    "k_flat_fast": 5, "k_flat_list": 1,
+    "k_acc_tile_local": 5,  # dir in, acc out
+    "k_acc_tile_final": 9,  # dir + acc in, acc out
+    "k_term_edges": 8,
+}
+BYTES_PER_CELL["fill+d8"] = 13
+
+
+def dominant_roofline(prof, steps, cells, step_ms, peak, peak_src, traffic_of=None):
+    """roofline line for the dominant full-grid kernel: achieved = its algorithmic bytes per launch / its average launch
+    time (launches per step is 1 for these kernels).  prof: name -> (launch count, total ms, max ms)."""
+    cand = {k: v for k, v in prof.items() if k in FULL_GRID and v[0] > 0}
+    if not cand:
+        return None
+    name, (cnt, tot, mx) = max(cand.items(), key=lambda kv: kv[1][1])
+    avg_ms = tot / cnt
+    alg = FULL_GRID[name] * cells
+    ach = alg / (avg_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": name, "pass": KERNEL_PASS.get(name, "other"), "achieved": ach, "peak": peak,
+            "unit": "GB/s", "frac": ach / peak, "traffic": traffic_of(name) if traffic_of else None,
+            "peak_source": peak_src, "launches_per_step": cnt / steps, "avg_launch_ms": avg_ms,
+            "algorithmic_bytes_per_launch": alg, "algorithmic_bytes_per_cell": FULL_GRID[name],
+            "step_share": tot / steps / step_ms,
+            "note": "dominant FULL-GRID kernel; multi-launch sparse kernels (k_flat_relax, k_bor_persistent) are listed "
+                    "with their total time per step under `kernels` and have no per-launch fraction"}
 
 
 def ncu_traffic(kernel):
@@ -178,8 +224,25 @@ def run_reference(args):
     return 0
 
 
-def run_banded(args, world, rank, local, dev):
-    """One DEM cut into row bands, a band per GPU (BASELINE.json configs[2]); seam exchange over NCCL."""
+def raster_hash(t, chunk_rows=512):
+    """order-sensitive 64-bit hash of a 2-D device raster (int64 wrap-around arithmetic), computed in row chunks"""
+    import torch
+    h = torch.zeros((), dtype=torch.int64, device=t.device)
+    ny, nx = t.shape
+    base = 0
+    for r0 in range(0, ny, chunk_rows):
+        x = t[r0:r0 + chunk_rows].contiguous()
+        v = x.view(torch.int32) if x.element_size() == 4 else x.to(torch.int32)
+        v = v.reshape(-1).to(torch.int64)
+        w = (torch.arange(base, base + v.numel(), device=t.device, dtype=torch.int64) % 1000003) + 1
+        h = h + (v * w).sum()
+        base += v.numel()
+    return h
+
+
+def measure_banded(args, world, rank, local, dev, workload, steps, warmup, want_e2e, want_check):
+    """One DEM cut into row bands, a band per GPU (BASELINE.json configs[2]); seam exchange over NCCL.  Returns the bench
+    line (a dict) on every rank; only rank 0's is printed."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -188,7 +251,7 @@ def run_banded(args, world, rank, local, dev):
 
     nl = args.local_bands
     nbands = world * nl
-    if args.workload == "c3":
+    if workload == "c3":
         nx, ny_total = 40000, 40000
         rows_all = bands.split_rows(ny_total, nbands)
         scaling = "strong"
@@ -208,12 +271,12 @@ def run_banded(args, world, rank, local, dev):
     chain = bands.BandedChain(my_rows, nx, nbands, first, dev, comm=comm, dx=30.0, dy=30.0, flats=bool(args.flats),
                               want_slope=False)
     n_bowls = max(200, int(200 * ny_total * nx / (10801.0 * 10801.0)))
+    dem_kw = dict(n_bowls=n_bowls, seam_rows=seams, plateau_rows=seams[:1])
     for i, nb in enumerate(my_rows):
         zv = chain.z_view(i)
         for r0 in range(0, nb, 512):
             nr = min(512, nb - r0)
-            zv[r0:r0 + nr] = synth.make_dem(ny_total, nx, 1003, row0=row0s[i] + r0, nrows=nr, device=dev,
-                                            n_bowls=n_bowls, seam_rows=seams, plateau_rows=seams[:1])
+            zv[r0:r0 + nr] = synth.make_dem(ny_total, nx, 1003, row0=row0s[i] + r0, nrows=nr, device=dev, **dem_kw)
     torch.cuda.synchronize()
     cells_local = sum(my_rows) * nx
     cells_total = ny_total * nx
@@ -225,7 +288,7 @@ def run_banded(args, world, rank, local, dev):
         torch.cuda.synchronize()
 
     out = None
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         out = chain.run()
     barrier()
     for c in chain.ctx:
@@ -236,7 +299,7 @@ def run_banded(args, world, rank, local, dev):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = chain.run()
     e1.record()
     barrier()
@@ -256,14 +319,14 @@ def run_banded(args, world, rank, local, dev):
     chain.timing = False
     phases = {k: v / 2 for k, v in chain.phase_ms.items()}
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    per_rank = [ms / args.steps]
+    per_rank = [ms / steps]
     if world > 1:
         allms = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allms, t)
-        per_rank = [float(x.item()) / args.steps for x in allms]
+        per_rank = [float(x.item()) / steps for x in allms]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = cells_total * args.steps / (ms_max * 1e-3) / 1e6
+    value = cells_total * steps / (ms_max * 1e-3) / 1e6
     stats = chain.stats()
     flat_rounds = chain.flat_rounds
 
@@ -279,32 +342,107 @@ def run_banded(args, world, rank, local, dev):
     chk = {"cells_below_input": int(tot_in[0].item()), "noflow_cells": int(tot_in[1].item()),
            "valid_cells_with_zero_count": int(tot_in[2].item())}
 
-    # ---- end to end: pinned host band in, filled + dir + acc out, through the same public call ----
+    # bit-equality with the WHOLE-RASTER chain: every rank hashes its bands' results; rank 0 runs the whole DEM through
+    # hc_fill_d8_accum on its own GPU and hashes the same row ranges
+    if want_check:
+        hb = torch.stack([torch.stack([raster_hash(f), raster_hash(d), raster_hash(a)]) for (f, d, s_, a) in out])  # [nl, 3]
+        if world > 1:
+            allh = [torch.zeros_like(hb) for _ in range(world)]
+            dist.all_gather(allh, hb)
+            hb_all = torch.cat(allh)
+        else:
+            hb_all = hb
+        equal = None
+        if rank == 0:
+            try:
+                zf = hc.empty_raster(ny_total, nx, torch.float32, dev)
+                for r0 in range(0, ny_total, 512):
+                    nr = min(512, ny_total - r0)
+                    zf[r0:r0 + nr] = synth.make_dem(ny_total, nx, 1003, row0=r0, nrows=nr, device=dev, **dem_kw)
+                wf, wd, ws_, wa = hc.fill_d8_accum(zf, dx=30.0, dy=30.0, seed_mode=hc.SEED_TAUDEM, table=hc.TABLE_TAUDEM,
+                                                   flats=bool(args.flats), want_slope=False)
+                torch.cuda.synchronize()
+                equal = True
+                r0 = 0
+                for g, nb in enumerate(rows_all):
+                    want = torch.stack([raster_hash(wf[r0:r0 + nb]), raster_hash(wd[r0:r0 + nb]), raster_hash(wa[r0:r0 + nb])])
+                    if not torch.equal(want, hb_all[g].to(want.device)):
+                        equal = False
+                    r0 += nb
+                del zf, wf, wd, wa
+                torch.cuda.empty_cache()
+            except torch.cuda.OutOfMemoryError:
+                equal = "skipped: the whole raster did not fit beside the band on rank 0"
+        chk["bands_equal_whole_raster_chain"] = equal
+        if world > 1:
+            dist.barrier()
+
+    # ---- end to end: pinned host band in, filled + dir + acc out, copies overlapped with the next unit's compute ----
     e2e = None
-    if not args.no_e2e:
+    if want_e2e:
         hz = [torch.empty((nb, nx), dtype=torch.float32, pin_memory=True) for nb in my_rows]
-        hf = [torch.empty((nb, nx), dtype=torch.float32, pin_memory=True) for nb in my_rows]
-        hd = [torch.empty((nb, nx), dtype=torch.uint8, pin_memory=True) for nb in my_rows]
-        ha = [torch.empty((nb, nx), dtype=torch.int32, pin_memory=True) for nb in my_rows]
+        # two result sets (host pinned + device staging): unit k's results cross PCIe while unit k + 1 is computed
+        hf = [[torch.empty((nb, nx), dtype=torch.float32, pin_memory=True) for nb in my_rows] for _ in range(2)]
+        hd = [[torch.empty((nb, nx), dtype=torch.uint8, pin_memory=True) for nb in my_rows] for _ in range(2)]
+        ha = [[torch.empty((nb, nx), dtype=torch.int32, pin_memory=True) for nb in my_rows] for _ in range(2)]
+        sf = [[torch.empty((nb, nx), dtype=torch.float32, device=dev) for nb in my_rows] for _ in range(2)]
+        sd = [[torch.empty((nb, nx), dtype=torch.uint8, device=dev) for nb in my_rows] for _ in range(2)]
+        sa = [[torch.empty((nb, nx), dtype=torch.int32, device=dev) for nb in my_rows] for _ in range(2)]
+        sz = [[torch.empty((nb, nx), dtype=torch.float32, device=dev) for nb in my_rows] for _ in range(2)]
         for i in range(nl):
             hz[i].copy_(chain.z_view(i))
         torch.cuda.synchronize()
+        main = torch.cuda.current_stream(dev)
+        s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ev_up = [torch.cuda.Event() for _ in range(2)]
+        ev_stage = [torch.cuda.Event() for _ in range(2)]
+        ev_down = [torch.cuda.Event() for _ in range(2)]
+        ev_zfree = [torch.cuda.Event() for _ in range(2)]
 
-        def host_step():
+        def upload(k):
+            with torch.cuda.stream(s_up):
+                s_up.wait_event(ev_zfree[k & 1])
+                for i in range(nl):
+                    sz[k & 1][i].copy_(hz[i], non_blocking=True)
+                ev_up[k & 1].record(s_up)
+
+        def compute(k):
+            main.wait_event(ev_up[k & 1])
             for i in range(nl):
-                chain.z_view(i).copy_(hz[i], non_blocking=True)
+                chain.z_view(i).copy_(sz[k & 1][i], non_blocking=True)
+            ev_zfree[k & 1].record(main)
             res = chain.run()
+            main.wait_event(ev_down[k & 1])       # the staging set's previous download has finished
             for i, (f, d, s_, a) in enumerate(res):
-                hf[i].copy_(f, non_blocking=True)
-                hd[i].copy_(d, non_blocking=True)
-                ha[i].copy_(a, non_blocking=True)
+                sf[k & 1][i].copy_(f, non_blocking=True)
+                sd[k & 1][i].copy_(d, non_blocking=True)
+                sa[k & 1][i].copy_(a, non_blocking=True)
+            ev_stage[k & 1].record(main)
+
+        def download(k):
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev_stage[k & 1])
+                for i in range(nl):
+                    hf[k & 1][i].copy_(sf[k & 1][i], non_blocking=True)
+                    hd[k & 1][i].copy_(sd[k & 1][i], non_blocking=True)
+                    ha[k & 1][i].copy_(sa[k & 1][i], non_blocking=True)
+                ev_down[k & 1].record(s_down)
+
+        def stream_units(n):
+            for e in ev_zfree + ev_down:
+                e.record(main)
+            upload(0)
+            for k in range(n):
+                if k + 1 < n:
+                    upload(k + 1)
+                compute(k)
+                download(k)
             torch.cuda.synchronize()
-        host_step()
-        ksteps = max(2, min(args.steps, 5))
+        stream_units(2)
+        ksteps = max(3, min(steps, 6))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(ksteps):
-            host_step()
+        stream_units(ksteps)
         if world > 1:
             dist.barrier()
         dt = time.perf_counter() - t0
@@ -312,42 +450,28 @@ def run_banded(args, world, rank, local, dev):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
+        same = all(torch.equal(hf[(ksteps - 1) & 1][i], out[i][0].cpu()) and torch.equal(ha[(ksteps - 1) & 1][i], out[i][3].cpu())
+                   for i in range(nl))
         e2e = {"value": cells_total * ksteps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": cells_total * 4,
-               "d2h_bytes_per_step": cells_total * 9, "steps": ksteps,
-               "api": "bands.BandedChain.run (pinned host band in, filled+dir+acc out per rank)"}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+               "d2h_bytes_per_step": cells_total * 9, "steps": ksteps, "host_results_equal_device_results": bool(same),
+               "api": "bands.BandedChain.run on a stream of units: pinned host band in, filled+dir+acc out per rank, uploads "
+                      "and downloads of neighbouring units overlap the chain (two staging sets)"}
+        del hz, hf, hd, ha, sf, sd, sa, sz
 
     peak, peak_src = peaks()
     cells = cells_local  # rank 0's share, for the per-kernel roofline
     pass_ms = {}
     for k, (cnt, tot, mx) in prof.items():
-        pass_ms[KERNEL_PASS.get(k, "other")] = pass_ms.get(KERNEL_PASS.get(k, "other"), 0.0) + tot / args.steps
-    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
-    roof = None
-    if dom:
-        name, (cnt, tot, mx) = dom
-        pname = KERNEL_PASS.get(name, "other")
-        avg_ms = tot / cnt
-        alg_bytes = BYTES_PER_CELL.get(pname, 0) * (cells // nl)
-        if pname == "flats":
-            alg_bytes = BYTES_PER_CELL["d8"] * (cells // nl)
-        ach = alg_bytes / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": name, "pass": pname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "launches_per_step": cnt / args.steps,
-                "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "step_share": tot / args.steps / (ms_max / args.steps)}
-    kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t_ / args.steps} for k, (c, t_, m) in
+        pass_ms[KERNEL_PASS.get(k, "other")] = pass_ms.get(KERNEL_PASS.get(k, "other"), 0.0) + tot / steps
+    roof = dominant_roofline(prof, steps * nl, cells // nl, ms_max / steps, peak, peak_src)
+    kernels = {k: {"launches_per_step": c / steps, "ms_per_step": t_ / steps} for k, (c, t_, m) in
                sorted(prof.items(), key=lambda kv: -kv[1][1])}
     passes = {p_: {"ms_per_step": v,
                    "hbm_frac_algorithmic": (BYTES_PER_CELL.get(p_, 0) * cells / (v * 1e-3) / 1e9 / peak) if v > 0 else None}
               for p_, v in pass_ms.items()}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl + "; fill + D8 + flat resolution + accumulation, TauDEM semantics; bowls centred on "
                                     "every seam and one plateau across the first seam; halo + seam-graph exchange by "
@@ -357,9 +481,113 @@ def run_banded(args, world, rank, local, dev):
                    "flat_exchange_rounds": flat_rounds, "band_stats_rank0": stats, "phase_ms_rank0": phases, "ms_per_step_per_rank": per_rank,
                    "algorithmic_bytes_per_cell": 18, "checks": chk},
         "roofline": roof, "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "hbm_frac_algorithmic_whole_step": 18 * cells_local / (ms_max / args.steps * 1e-3) / 1e9 / peak,
+        "hbm_frac_algorithmic_whole_step": 18 * cells_local / (ms_max / steps * 1e-3) / 1e9 / peak,
         "passes": passes, "kernels": kernels,
     }
+    chain.close()
+    del chain, out
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_banded(args, world, rank, local, dev):
+    """N > 1 (or --workload bands / c3): the headline line is C3 (40000^2, strong); workload 'auto' adds the weak-bands
+    measurement of the same chain under config.weak_bands."""
+    import torch.distributed as dist
+    auto = args.workload == "auto_n"
+    wl = "c3" if auto else args.workload
+    line = measure_banded(args, world, rank, local, dev, wl, args.steps, args.warmup, not args.no_e2e, True)
+    if auto:
+        weak = measure_banded(args, world, rank, local, dev, "bands", max(3, min(args.steps, 10)), 3, False, False)
+        line["config"]["weak_bands"] = {k: weak[k] for k in ("value", "unit", "ms_per_step", "scaling", "steps")}
+        line["config"]["weak_bands"].update(workload=weak["config"]["workload"], cells_total=weak["config"]["cells_total"],
+                                            ms_per_step_per_rank=weak["config"]["ms_per_step_per_rank"],
+                                            phase_ms_rank0=weak["config"]["phase_ms_rank0"], clocks=weak["clocks"],
+                                            checks=weak["config"]["checks"])
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_c1(args, world, rank, local, dev):
+    """BASELINE.json configs[0]: the per-unit depression pipeline (DepHandle.depression_handling's core + the final fill,
+    models/depression_handling.py:717-830, 470-484) on a synthetic 3601^2 tile, GeoTIFF in, conditioned DEM out, the
+    reference's file protocol between the stages (all-zero water mask: the only configuration the reference completes).
+    One unit per GPU.  Extra measured line; value = cells / unit time."""
+    import shutil
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pydrodem_b200 import _lib, raster_io, synth
+    from pydrodem_b200.models.depression_handling import DepHandleCore
+    import pydrodem_b200.tools.depressions as dep
+    n = 3601 if args.size == 10801 else args.size
+    z = synth.make_dem_numpy(n, n, 1001 + rank, nodata_frame=True) if n <= 1200 else \
+        synth.make_dem(n, n, 1001 + rank, nodata_frame=True, device=dev).cpu().numpy()
+    stage = {}
+    for name in ("fill_pits", "create_clump_array", "fill_shallow_pits", "breach_pits", "build_pit_catalog",
+                 "select_solution", "apply_solution", "combined_solution"):
+        fn = getattr(dep, name)
+
+        def wrap(*a, __fn=fn, __name=name, **k):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            try:
+                return __fn(*a, **k)
+            finally:
+                torch.cuda.synchronize()
+                stage[__name] = stage.get(__name, 0.0) + time.perf_counter() - t0
+        setattr(dep, name, wrap)
+    times, codes, pits = [], {}, 0
+    launches0 = _lib.launch_count(local)
+    reps = max(1, min(args.steps, 3))
+    sampler = ClockSampler(local)
+    for it in range(1 + reps):
+        tmp = tempfile.mkdtemp(prefix="hc_c1_")
+        try:
+            tif = os.path.join(tmp, "DEM.tif")
+            raster_io.write_raster(tif, z, None, nodata=-9999.0)
+            core = DepHandleCore(basename="DEM", del_temp_files=False)
+            if it == 1:
+                stage.clear()
+                sampler.start()
+                launches0 = _lib.launch_count(local)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ffill, mod, DFpits, solmask = core.run_depression_core(tif, tmp, water_mask_array=np.zeros((n, n), np.uint8))
+            torch.cuda.synchronize()
+            if it >= 1:
+                times.append(time.perf_counter() - t0)
+            pits = int(len(DFpits))
+            vals, cnts = np.unique(DFpits.solution.values, return_counts=True)
+            codes = {str(int(v)): int(c) for v, c in zip(vals, cnts)}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    clocks = sampler.stop()
+    launches = _lib.launch_count(local) - launches0
+    dt = sum(times) / len(times)
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    line = {"metric": "Mcells/s depression_handling unit (configs[0])", "value": world * n * n / dt / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": reps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C1: {n}x{n} float32 1-arcsec tile through DepHandleCore.run_depression_core (initial_fill_carve -> "
+                                   "catalog -> select -> apply -> combined solutions -> final fill), GeoTIFF files between the "
+                                   "stages as in the reference, reference ini parameters, all-zero water mask; one unit per GPU",
+                       "pits": pits, "solution_codes": codes,
+                       "stage_seconds": {k: round(v / reps, 4) for k, v in sorted(stage.items(), key=lambda kv: -kv[1])}},
+            "roofline": None, "cpu_baseline": None, "e2e": {"value": world * n * n / dt / 1e6, "unit": UNIT,
+                                                             "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                                                             "api": "the line itself is end to end: files in, files out"},
+            "gpu_launches": launches // reps, "clocks": clocks}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -470,9 +698,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=5400, help="edge of the crop timed on the CPU (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flats", type=int, default=1)
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "bands", "c3", "c4", "c5"],
-                    help="auto: c2 (one 10801^2 DEM) at N=1, bands (one 10801 x 10801*N DEM, a band per GPU, seam "
-                         "exchange over NCCL) at N>1; c3: the 40000^2 DEM row-band-sharded over the N GPUs")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "bands", "c3", "c4", "c5"],
+                    help="auto: c2 (one 10801^2 DEM) at N=1; at N>1 c3 (the 40000^2 DEM row-band-sharded over the N GPUs, "
+                         "strong scaling) as the headline with the weak-scaling bands run (one 10801 x 10801*N DEM, a band "
+                         "per GPU) reported inside the same line; c1: the per-unit depression pipeline on 3601^2")
+    ap.add_argument("--dense", action="store_true", help="C2 / C4 on a dense (unpitched) device raster: the scalar-loader path")
     ap.add_argument("--local-bands", type=int, default=1, help="bands per rank (N=1 with >1 emulates the exchange)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -507,20 +737,26 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     if args.workload == "auto":
-        args.workload = "c2" if world == 1 and args.local_bands == 1 else "bands"
-    if args.workload in ("bands", "c3"):
+        args.workload = "c2" if world == 1 and args.local_bands == 1 else ("auto_n" if world > 1 else "bands")
+    if args.workload in ("bands", "c3", "auto_n"):
         return run_banded(args, world, rank, local, dev)
+    if args.workload == "c1":
+        return run_c1(args, world, rank, local, dev)
     if args.workload == "c5":
         return run_c5(args, world, rank, local, dev)
 
     ny = nx = args.size
     cells = ny * nx
     # one unit per GPU (weak scaling): same recipe, per-rank seed
-    z = torch.empty((ny, nx), dtype=torch.float32, device=dev)
+    # pitched device raster (rows padded to 64 elements): TMA-staged tile windows and aligned vector loads; --dense
+    # keeps the caller-style dense raster, which takes the kernels' scalar loaders
+    z = torch.empty((ny, nx), dtype=torch.float32, device=dev) if args.dense else hc.empty_raster(ny, nx, torch.float32, dev)
     band = 1024
     if args.workload == "c4":
         # configs[3]: flattened lakes + burned rivers (large exact flats: flat resolution heavy)
-        z, _water = synth.make_c4(ny, nx, 1004 + rank, device=dev)
+        z0, _water = synth.make_c4(ny, nx, 1004 + rank, device=dev)
+        z.copy_(z0)
+        del z0, _water
     else:
         for r0 in range(0, ny, band):
             nr = min(band, ny - r0)
@@ -638,21 +874,10 @@ def main():
     pass_ms = {}
     for k, (cnt, tot, mx) in prof.items():
         pass_ms[KERNEL_PASS.get(k, "other")] = pass_ms.get(KERNEL_PASS.get(k, "other"), 0.0) + tot / args.steps
-    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
-    roof = None
-    if dom:
-        name, (cnt, tot, mx) = dom
-        pname = KERNEL_PASS.get(name, "other")
-        avg_ms = tot / cnt
-        alg_bytes = BYTES_PER_CELL.get(pname, 0) * cells
-        if pname == "flats":
-            alg_bytes = BYTES_PER_CELL["d8"] * cells  # flat resolution is part of producing the D8 raster
-        ach = alg_bytes / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": name, "pass": pname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": ncu_traffic(name) if ny == 10801 else None, "peak_source": peak_src,
-                "launches_per_step": cnt / args.steps, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "step_share": tot / args.steps / (ms_max / args.steps),
-                "traffic_source": "profiles/ncu_traffic.json (ncu dram__bytes_read+write per launch)"}
+    roof = dominant_roofline(prof, args.steps, cells, ms_max / args.steps, peak, peak_src,
+                             traffic_of=ncu_traffic if ny == 10801 else None)
+    if roof is not None:
+        roof["traffic_source"] = "profiles/ncu_traffic.json (ncu dram__bytes_read+write per launch)"
     kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t_ / args.steps} for k, (c, t_, m) in
                sorted(prof.items(), key=lambda kv: -kv[1][1])}
     passes = {p: {"ms_per_step": v,
@@ -678,6 +903,7 @@ def main():
                                 "quantised)") + ", fill + D8 + flat resolution + accumulation, TauDEM semantics "
                                "(PitRemove/D8FlowDir/AreaD8), one unit per GPU",
                    "cells_per_gpu": cells, "l2": "inputs (467 MB z + outputs) exceed the 126 MB L2; no explicit flush",
+                   "device_raster": "dense" if args.dense else "pitched (core.empty_raster, hc_fill_d8_accum_ld_dev): TMA path",
                    "flats": bool(args.flats), "basins": basins, "boruvka_rounds": rounds,
                    "algorithmic_bytes_per_cell": 18},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
