@@ -231,9 +231,10 @@ def breach_single_cell_pits(z, nodata=-9999.0):
 
 
 def _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits):
-    """EXPERIMENTAL composition of the order-independent flow-path breach (specification
-    oracle/breach_flowpath.py): single-cell pits, fill, D8 and flat resolution on the GPU, the pointer walks on the
-    host (`hc_breach_flowpath_host`, to become a kernel), closing fill on the GPU.  Returns (surface, stats)."""
+    """Host-walk composition of the order-independent flow-path breach (specification oracle/breach_flowpath.py):
+    single-cell pits, fill, D8 and flat resolution on the GPU, the pointer walks on the host
+    (`hc_breach_flowpath_host`), closing fill on the GPU.  Kept as a second implementation the device form is
+    checked against.  Returns (surface, stats)."""
     import ctypes
     import numpy as np
     w = _np2d(fill_single_cell_pits(zh, nodata) if fill_pits else zh, np.float32)
@@ -259,11 +260,13 @@ def _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits):
 
 
 def _breach_flowpath_dev(zh, nodata, max_length, max_depth, fill_pits, dx=1.0, dy=1.0):
-    """EXPERIMENTAL, not yet run on a GPU: the same formulation entirely on the device (`hc_breach_flowpath_dev`).
-    Returns (cut surface as a CUDA tensor, stats)."""
+    """The flow-path breach entirely on the device (`hc_breach_flowpath_dev`: seeds, fill, D8 + flats of the
+    seed-lowered filled surface, one thread per pit walking its flow path with a CAS-min on the cut surface).
+    `zh`: numpy array or CUDA tensor.  Returns (cut surface as a CUDA tensor, stats)."""
     import ctypes
     import torch
-    zt = torch.from_numpy(np.ascontiguousarray(zh, dtype=np.float32)).cuda()
+    zt = zh if _is_torch(zh) else torch.from_numpy(np.ascontiguousarray(zh, dtype=np.float32)).cuda()
+    zt = _tdev(zt, torch.float32, "breach_depressions")
     w = fill_single_cell_pits(zt, nodata) if fill_pits else zt
     out, filled = torch.empty_like(w), torch.empty_like(w)
     dirs = torch.empty(w.shape, dtype=torch.uint8, device=w.device)
@@ -279,28 +282,35 @@ def _breach_flowpath_dev(zh, nodata, max_length, max_depth, fill_pits, dx=1.0, d
 
 
 def breach_depressions(z, nodata=-9999.0, max_length=None, max_depth=None, fill_pits=False, flat_increment=None,
-                       return_stats=False, method='flood'):
-    """wbt.breach_depressions (Lindsay 2016) as dep.breach_pits calls it (tools/depressions.py:1376-1380):
-    constrained breaching on the host (`hc_breach_depressions_host`, one global priority order -- SURVEY.md 8 row
-    a2), then the depressions that could not be breached are filled by the GPU fill with WhiteboxTools' seed rule.
+                       return_stats=False, method='flowpath_dev'):
+    """wbt.breach_depressions (Lindsay 2016) as dep.breach_pits calls it (tools/depressions.py:1376-1380): constrained
+    breaching, then the depressions that could not be breached are filled with WhiteboxTools' seed rule.
     float32 in, float32 out (numpy in -> numpy out, CUDA tensor in -> CUDA tensor out).
-    method='flowpath' selects the experimental order-independent formulation (see _breach_flowpath)."""
+
+    method='flowpath_dev' (default): the order-independent flow-path formulation, every pass on the GPU
+    (specification: oracle/breach_flowpath.py).  'flowpath': the same formulation with the pointer walks
+    on the host.  'flood': the priority-order formulation on the host (`hc_breach_depressions_host`, csrc/breach.cu).
+    WhiteboxTools itself is unavailable, so all three are restatements of Lindsay (2016): parity unpinned."""
     import ctypes
     import numpy as np
     if flat_increment is not None and flat_increment > 0:
         raise NotImplementedError("flat_increment > 0 (graded breach channels / Priority-Flood+epsilon) is order "
                                   "dependent in WhiteboxTools and is not offered; pydrodem's default is 0.0")
     if method not in ('flood', 'flowpath', 'flowpath_dev'):
-        raise ValueError("method must be 'flood' (the shipped formulation), 'flowpath' or 'flowpath_dev' (experimental)")
+        raise ValueError("method must be 'flowpath_dev' (default), 'flowpath' or 'flood'")
     host = not _is_torch(z)
+    if method == 'flowpath_dev':
+        cut, st = _breach_flowpath_dev(z if not host else _np2d(z, np.float32), nodata, max_length, max_depth, fill_pits)
+        out = fill(cut, nodata=nodata, seed_mode=SEED_WBT)
+        if host:
+            out = out.cpu().numpy()
+        if return_stats:
+            return out, dict(pits=st[0], breached=st[1], left_to_fill=st[2], cells_lowered=st[3])
+        return out
     zh = _np2d(z if host else z.detach().cpu().numpy(), np.float32)
-    if method in ('flowpath', 'flowpath_dev'):
-        if method == 'flowpath':
-            cut, st = _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits)
-            out = fill(cut, nodata=nodata, seed_mode=SEED_WBT)
-        else:
-            cut, st = _breach_flowpath_dev(zh, nodata, max_length, max_depth, fill_pits)
-            out = fill(cut, nodata=nodata, seed_mode=SEED_WBT).cpu().numpy()
+    if method == 'flowpath':
+        cut, st = _breach_flowpath(zh, nodata, max_length, max_depth, fill_pits)
+        out = fill(cut, nodata=nodata, seed_mode=SEED_WBT)
         if not host:
             import torch
             out = torch.from_numpy(out).to(z.device)

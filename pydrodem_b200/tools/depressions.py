@@ -4,7 +4,7 @@ Same signatures and file protocol (`<in>_WL.tif`, `<in>_WL_DIFF.tif`, clump-ID r
 replaced by pydrodem_b200.raster_io, WhiteboxTools by the `wbt` duck type (pydrodem_b200.wbt) and
 scipy.ndimage.label / convolve2d by the CUDA kernels.  build_pit_catalog / select_solution /
 apply_solution / fill_shallow_pits run as segmented reductions on the GPU (csrc/segment.cu);
-breach_pits runs through `wbt.breach_depressions` (host breach + GPU fill, csrc/breach.cu).
+breach_pits runs through `wbt.breach_depressions` (flow-path breach on the GPU, hc_breach_flowpath_dev).
 """
 import os
 

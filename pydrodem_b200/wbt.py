@@ -14,7 +14,8 @@ Deliberate differences, all stated where they apply:
   * outputs are float32 GeoTIFFs (WhiteboxTools writes float64 and pydrodem narrows them right
     away with `pyct.tifdowncast`, tools/depressions.py:1306); D8 pointers are int16 with -32768 on
     nodata cells as WhiteboxTools writes them.
-  * breach_depressions runs its priority-order part on the host (csrc/breach.cu) and the closing fill on the GPU;
+  * breach_depressions runs the order-independent flow-path breach on the GPU (hc_breach_flowpath_dev; the host
+    priority-order formulation of csrc/breach.cu remains as core.breach_depressions(method="flood"));
     breach_depressions_least_cost is not built.
 """
 import numpy as np

@@ -1,4 +1,6 @@
-"""Breach through the product API: host priority-order part (csrc/breach.cu) + GPU fill of what is left."""
+"""Breach through the product API.  Default: the order-independent flow-path formulation, all passes on the GPU
+(`hc_breach_flowpath_dev`), checked against its CPU specification oracle/breach_flowpath.py; the host priority-order
+formulation (csrc/breach.cu, method='flood') stays available and is checked against its own host entry point."""
 import ctypes
 import os
 
@@ -31,19 +33,55 @@ def scene(ny, nx, seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("ny,nx,seed,ml", [(120, 150, 1, 10), (257, 190, 2, 0), (64, 300, 3, 3)])
-def test_gpu_fill_of_the_cut_surface_equals_host_fill(ny, nx, seed, ml):
+def test_flood_method_gpu_fill_of_the_cut_surface_equals_host_fill(ny, nx, seed, ml):
     import torch
     import pydrodem_b200 as hc
     z = scene(ny, nx, seed)
     want, st = host_breach(z, max_length=ml, fill_pits=True, do_fill=True)
-    got, stats = hc.breach_depressions(z, nodata=ND, max_length=ml or None, fill_pits=True, return_stats=True)
+    got, stats = hc.breach_depressions(z, nodata=ND, max_length=ml or None, fill_pits=True, return_stats=True, method='flood')
     assert got.dtype == np.float32 and np.array_equal(got, want)
     assert [stats["pits"], stats["breached"], stats["left_to_fill"], stats["cells_lowered"]] == st[:4]
-    dev = hc.breach_depressions(torch.from_numpy(z).cuda(), nodata=ND, max_length=ml or None, fill_pits=True)
+    dev = hc.breach_depressions(torch.from_numpy(z).cuda(), nodata=ND, max_length=ml or None, fill_pits=True, method='flood')
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), want)
     assert np.array_equal(hc.fill(got, nodata=ND, seed_mode=hc.SEED_WBT), got)       # depression free
     with pytest.raises(NotImplementedError):
         hc.breach_depressions(z, flat_increment=0.001)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ny,nx,seed,ml", [(120, 150, 1, 10), (257, 190, 2, 0), (64, 300, 3, 3), (97, 120, 5, 6)])
+def test_default_flowpath_breach_matches_its_specification(ny, nx, seed, ml):
+    """the shipped default (every pass on the device), the host-walk composition and the CPU specification agree bit
+    for bit, statistics included; numpy in -> numpy out, CUDA tensor in -> CUDA tensor out"""
+    import torch
+    import pydrodem_b200 as hc
+    from oracle import breach_flowpath as bf
+    z = scene(ny, nx, seed)
+    want, sw = bf.breach_flowpath(z, ND, max_length=ml, fill_pits=True, do_fill=True)
+    for method in (None, 'flowpath'):
+        kw = {} if method is None else {"method": method}
+        got, st = hc.breach_depressions(z, nodata=ND, max_length=ml or None, fill_pits=True, return_stats=True, **kw)
+        assert got.dtype == np.float32 and np.array_equal(got, want), method
+        assert [st["pits"], st["breached"], st["left_to_fill"], st["cells_lowered"]] == \
+            [sw["pits"], sw["breached"], sw["left"], sw["cut"]], method
+    dev = hc.breach_depressions(torch.from_numpy(z).cuda(), nodata=ND, max_length=ml or None, fill_pits=True)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), want)
+    assert np.array_equal(hc.fill(want, nodata=ND, seed_mode=hc.SEED_WBT), want)     # depression free
+    assert np.all(want[z != ND] <= hc.fill(z, nodata=ND, seed_mode=hc.SEED_WBT)[z != ND])   # never above the plain fill
+
+
+@pytest.mark.gpu
+def test_default_flowpath_breach_depth_constraint_and_no_pit_fill():
+    """combined_solution's call: max_depth set, fill_pits=False (tools/depressions.py:1012-1014)"""
+    import pydrodem_b200 as hc
+    from oracle import breach_flowpath as bf
+    z = scene(110, 140, 8)
+    for md in (0.5, 2.0):
+        want, sw = bf.breach_flowpath(z, ND, max_length=9, max_depth=md, fill_pits=False, do_fill=True)
+        got, st = hc.breach_depressions(z, nodata=ND, max_length=9, max_depth=md, fill_pits=False, return_stats=True)
+        assert np.array_equal(got, want), md
+        assert [st["pits"], st["breached"], st["left_to_fill"], st["cells_lowered"]] == \
+            [sw["pits"], sw["breached"], sw["left"], sw["cut"]], md
 
 
 @pytest.mark.gpu
@@ -55,8 +93,9 @@ def test_wbt_and_breach_pits_file_protocol(tmp_path):
     dem_tif = str(tmp_path / "unit.tif")
     raster_io.write_raster(dem_tif, z, None, nodata=ND)
     wbt = WhiteboxToolsGPU()
+    from oracle import breach_flowpath as bf
     carve, diff = dep.breach_pits(dem_tif, 12, 200, wbt, nodataval=ND)
-    want, _ = host_breach(z, max_length=12, fill_pits=True, do_fill=True)
+    want, _ = bf.breach_flowpath(z, ND, max_length=12, fill_pits=True, do_fill=True)
     assert np.array_equal(carve, want)
     assert np.array_equal(diff, np.round(want - z, 3))
     assert os.path.exists(str(tmp_path / "unit_SC_12.tif")) and os.path.exists(str(tmp_path / "unit_SC_12_DIFF.tif"))
