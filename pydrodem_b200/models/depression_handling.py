@@ -80,14 +80,16 @@ class DepHandleCore:
         DFpits_3 = DFpits[(DFpits.solution >= 4000) & (DFpits.solution < 5000)].copy()
         if len(DFpits_3.index.values) > 0:
             modDEM_array, _ = raster_io.read_raster(modDEM_tif)
-            wall_vec = None if wall_array is None else np.asarray(wall_array).reshape(ny * nx,)
+            # every pit's partial-fill candidates are evaluated from the same pre-combination surface (the reference's
+            # loop reads modDEM_array once, :768), so all of them go through one batched device pass
+            if self.carvemethod == 'LC':
+                raise NotImplementedError("carve_method='LC' (breach_depressions_least_cost) is not built")
+            results = dep.combined_solutions(list(DFpits_3.index.values), modDEM_array, nx, ny, DFpits, fillcells_dct,
+                                             carvecells_dct, carve_fillcells_dct, self.combined_fill_interval, fillID_vec,
+                                             fill_vec, carve_vec, self.radius, self.max_carve_depth,
+                                             nodataval=self.nodataval)
             for pit_id in DFpits_3.index.values:
-                solution_name, sol_df = dep.combined_solution(
-                    modDEM_tif, modDEM_array, outpath, nx, ny, DFpits, fillcells_dct, carvecells_dct,
-                    carve_fillcells_dct, pit_id, self.combined_fill_interval, fillID_vec, fill_vec, carve_vec,
-                    self.radius, self.maxcost, self.min_dist, self.max_carve_depth, self.wbt, nodataval=self.nodataval,
-                    flat_increment=self.flat_increment, carve_method=self.carvemethod, water_array=None,
-                    wall_vec=wall_vec, del_temp_files=self.del_temp_files)
+                solution_name, sol_df = results[pit_id]
                 DFpits.at[pit_id, 'solution'] = solution_name
                 combined_footprint_ind = sol_df.footprint.values[0]
                 combined_footprint_elevs = sol_df.elevs.values[0]

@@ -63,67 +63,90 @@ def breach_pits(inDEM_tif, radius, maxcost, wbt, min_dist=False, flat_increment=
     return carve_array, diff_carve_array
 
 
+def _sign_mask(values, condition, extra=None):
+    """uint8 device mask of a difference map's sign: 'greaterthan' (> 0), 'lessthan' (< 0, or `extra` == 1), 'nonzero'"""
+    import torch
+    v = values if core._is_torch(values) else torch.from_numpy(np.ascontiguousarray(values)).cuda()
+    if condition == 'greaterthan':
+        m = v > 0
+    elif condition == 'lessthan':
+        m = v < 0
+        if extra is not None:
+            e = extra if core._is_torch(extra) else torch.from_numpy(np.ascontiguousarray(extra)).cuda()
+            m = m | (e == 1)
+    elif condition == 'nonzero':
+        m = v != 0
+    else:
+        m = torch.zeros_like(v, dtype=torch.bool)
+    return m
+
+
 def create_clump_array(input_array, clump_ID_tif, stencil_tif, wbt, nodataval=-9999, noflow_array=None,
                        condition='greaterthan', clumpbuffer=None, split_mask=None, save_tif=True):
-    """tools/depressions.py:1593-1675: sign mask of a difference map -> optional (2b+1)^2 box dilation ->
-    labels (8-connectivity, or 4-connectivity when buffered), ids in scipy's raster-scan order."""
-    input_array = np.asarray(input_array)
-    clump_array = np.zeros(input_array.shape, dtype=np.int8)
-    if condition == 'greaterthan':
-        clump_array[input_array > 0] = 1
-    if condition == 'lessthan':
-        if noflow_array is not None:
-            clump_array[noflow_array == 1] = 1
-        clump_array[input_array < 0] = 1
-    if condition == 'nonzero':
-        clump_array[input_array != 0] = 1
+    """tools/depressions.py:1593-1675: clumps of a difference map's sign, ids in scipy's raster-scan order.
+    One device pipeline: sign predicate -> (clumpbuffer) square dilation as a (2b+1)-wide moving maximum
+    (`hc_minmax_filter_dev`; equal to the reference's box convolution + "> 0") -> labels (`hc_label_dev`: 4-connected
+    when dilated, 8-connected otherwise).  A `split_mask` is labelled on its own and numbered after the rest.  Only the
+    finished id raster crosses to the host."""
+    import torch
+    from . import water as _water   # (the moving-maximum binding lives with the water stencils)
+    mask = _sign_mask(np.asarray(input_array) if not core._is_torch(input_array) else input_array, condition, noflow_array)
+    mask = mask.to(torch.uint8).contiguous()
+    conn = 8
     if clumpbuffer is not None:
-        sz = (2 * clumpbuffer) + 1
-        clump_array = stencils.apply_convolve_filter(clump_array, np.ones((sz, sz)))
-        clump_array = (clump_array > 0).astype(np.int8)
+        mask = _water.maximum_filter(mask, 2 * int(clumpbuffer) + 1)
         conn = 4
+    if split_mask is None:
+        ids, _ = core.label(mask, conn)
     else:
-        conn = 8
-    if split_mask is not None:
-        split_ind = np.nonzero(split_mask)
-        split_clump_array = np.zeros_like(clump_array)
-        split_clump_array[split_ind] = clump_array[split_ind]
-        clump_array[split_ind] = 0
-        clump_ID_array, num_feat = core.label(clump_array, conn)
-        split_ID_array, _ = core.label(split_clump_array, conn)
-        split_ind = np.nonzero(split_ID_array)
-        split_ID_array[split_ind] += num_feat
-        clump_ID_array[split_ind] = split_ID_array[split_ind]
-    else:
-        clump_ID_array, num_feat = core.label(clump_array, conn)
+        inside = torch.from_numpy(np.ascontiguousarray(np.asarray(split_mask) != 0)).to(mask.device)
+        part = mask * inside.to(torch.uint8)
+        rest = mask * (~inside).to(torch.uint8)
+        ids, n_rest = core.label(rest.contiguous(), conn)
+        ids_part, _ = core.label(part.contiguous(), conn)
+        ids = torch.where(ids_part > 0, ids_part + n_rest, ids)
+    clump_ID_array = ids.cpu().numpy()
     if save_tif:
         meta = raster_io.read_raster(stencil_tif)[1] if (stencil_tif and os.path.exists(stencil_tif)) else None
         raster_io.write_raster(clump_ID_tif, clump_ID_array, meta, nodata=0)
     return clump_ID_array
 
 
+def _valid_bbox(valid):
+    """(first row, last row, first col, last col) of a boolean raster's True cells, or None"""
+    rows = np.flatnonzero(valid.any(axis=1))
+    cols = np.flatnonzero(valid.any(axis=0))
+    if rows.size == 0:
+        return None
+    return int(rows[0]), int(rows[-1]), int(cols[0]), int(cols[-1])
+
+
 def fix_shifted_data(in_array, shift_array, nodataval, failtest='negative_diff', vprint=False):
-    """tools/depressions.py:1406-1468: undo a whole-raster pixel shift of a WhiteboxTools output (detected from the
-    bounding boxes of the valid cells) and recompute the rounded difference map.  Returns (shift_array, diff_array).
-    The GPU tools never shift a raster, so on this path the shift is (0, 0) and only the difference map is rebuilt;
-    the index arithmetic is kept so that a raster produced elsewhere is repaired the same way (host numpy: a rare
-    repair path over index lists, not a kernel)."""
-    data_ind = np.nonzero(in_array != nodataval)
-    nodata_ind = np.nonzero(in_array == nodataval)
-    fill_data_ind = np.nonzero(shift_array != nodataval)
-    shift_1 = fill_data_ind[1].max() - data_ind[1].max()
-    shift_0 = fill_data_ind[0].max() - data_ind[0].max()
-    ind_diff = np.abs(len(data_ind[0]) - len(fill_data_ind[0]))
-    fill_data_ind_shift = (fill_data_ind[0] - shift_0, fill_data_ind[1] - shift_1)
-    shift_array[fill_data_ind_shift] = shift_array[fill_data_ind]
-    shift_array[nodata_ind] = nodataval
-    diff_array = np.round((shift_array - in_array), 3)
-    if failtest == 'negative_diff':
-        fail_diff = np.nonzero(diff_array < 0.0)
-    elif failtest == 'positive_diff':
-        fail_diff = np.nonzero(diff_array > 0.0)
-    num_fail = len(fail_diff[0])
-    assert num_fail <= ind_diff + 3, 'Re-mapped fill diff has too many negative values'
+    """tools/depressions.py:1406-1468: a WhiteboxTools output that came back displaced by whole pixels is moved back
+    (the displacement is read off the valid cells' bounding boxes: lower-right corners, as upstream) and the rounded
+    difference map is rebuilt.  Returns (shift_array, diff_array); `shift_array` is repaired in place.  The GPU tools
+    never displace a raster, so here the displacement is (0, 0) and the call is the difference recompute plus the
+    upstream sanity check (at most `|valid-count difference| + 3` cells may fail `failtest`)."""
+    have, got = in_array != nodataval, shift_array != nodataval
+    bb_in, bb_out = _valid_bbox(have), _valid_bbox(got)
+    if bb_in is not None and bb_out is not None:
+        dr, dc = bb_out[1] - bb_in[1], bb_out[3] - bb_in[3]
+        if dr or dc:
+            moved = np.full_like(shift_array, nodataval)
+            ny, nx = shift_array.shape
+            # destination (r, c) <- source (r + dr, c + dc), wherever both lie inside the raster
+            r0, r1 = max(0, -dr), min(ny, ny - dr)
+            c0, c1 = max(0, -dc), min(nx, nx - dc)
+            moved[r0:r1, c0:c1] = shift_array[r0 + dr:r1 + dr, c0 + dc:c1 + dc]
+            keep = (moved != nodataval)
+            shift_array[keep] = moved[keep]
+            if vprint:
+                print("   shifted back by", (dr, dc))
+    shift_array[~have] = nodataval
+    diff_array = np.round(shift_array - in_array, 3)
+    bad = diff_array < 0.0 if failtest == 'negative_diff' else diff_array > 0.0
+    slack = abs(int(have.sum()) - int(got.sum())) + 3
+    assert int(bad.sum()) <= slack, 'Re-mapped fill diff has too many negative values'
     return shift_array, diff_array
 
 
@@ -467,138 +490,154 @@ def _window_meta(meta, row_min, col_min):
     return m
 
 
+class _Trial:
+    """one (pit, fill fraction) candidate of the combined solution: a partially filled window waiting for its breach"""
+    __slots__ = ("pit", "frac", "win", "surface", "slot")
+
+    def __init__(self, pit, frac, win, surface):
+        self.pit, self.frac, self.win, self.surface, self.slot = pit, frac, win, surface, None
+
+
+def _pack_shelves(shapes, max_width=4096, gutter=2):
+    """greedy shelf packing of rectangles (h, w) with `gutter` free cells around each -> (positions, H, W)"""
+    order = sorted(range(len(shapes)), key=lambda i: -shapes[i][0])
+    W = max(max_width, max(w for _, w in shapes) + 2 * gutter)
+    pos = [None] * len(shapes)
+    x, y, shelf_h = gutter, gutter, 0
+    for i in order:
+        h, w = shapes[i]
+        if x + w + gutter > W:
+            x, y, shelf_h = gutter, y + shelf_h + gutter, 0
+        pos[i] = (y, x)
+        x += w + gutter
+        shelf_h = max(shelf_h, h)
+    return pos, y + shelf_h + gutter, W
+
+
+def combined_solutions(pit_ids, inDEM_array, nx, ny, DFpits, fillcells_dct, carvecells_dct, carve_fillcells_dct,
+                       combined_fill_interval, fillID_vec, fill_vec, carve_vec, radius, max_carve_depth, nodataval=-9999):
+    """The partial-fill + re-breach search of tools/depressions.py:813-1137 for MANY pits at once.
+
+    For every pit the reference clips a window (pit bounding box + radius + 2 cells), lowers the pit's full fill to
+    the fractions 0.2 ... 0.8 of its depth, breaches each partial surface again (max_length = radius, max_depth =
+    max_carve_depth, no single-cell-pit fill), keeps the carves that reach the pit without running off the raster and
+    without exceeding max_carve_depth, and finally picks -- among those, the plain fill and (if complete) the plain
+    carve -- the candidate with the smallest absolute volume change.  Up to 4 WhiteboxTools subprocesses and 8 GeoTIFF
+    round trips per pit upstream.
+
+    Here all partial surfaces of all pits are packed into ONE mosaic raster with nodata gutters and go through ONE
+    device breach and ONE device labelling: a gutter is exterior nodata, so every window's rim cells are seeds exactly
+    as the rim of a stand-alone raster is, and no flow path, flat or clump can cross it -- each window's result is the
+    stand-alone result.  Returns {pit_id: (solution_name, sol_df)} with the reference's return value per pit."""
+    import pandas as pd
+    import torch
+    ground_full = np.asarray(inDEM_array, dtype=np.float32).reshape(ny, nx)
+    fill_full = np.asarray(fill_vec).reshape(ny, nx)
+    carve_full = np.asarray(carve_vec).reshape(ny, nx)
+    ids_full = np.asarray(fillID_vec).reshape(ny, nx)
+    nd = np.float32(nodataval)
+    pad = int(radius) + 2
+    fractions = np.round(np.arange(combined_fill_interval, 1, combined_fill_interval), 1)
+
+    trials, per_pit = [], {}
+    for pit in pit_ids:
+        row = DFpits.loc[pit]
+        cells = np.asarray(fillcells_dct[pit])
+        rr, cc = np.divmod(cells, nx)
+        win = (slice(int(max(0, rr.min() - pad)), int(min(ny, rr.max() + pad + 1))),
+               slice(int(max(0, cc.min() - pad)), int(min(nx, cc.max() + pad + 1))))
+        ground = np.ascontiguousarray(ground_full[win])
+        inpit = ids_full[win] == pit
+        per_pit[pit] = dict(row=row, cells=cells, win=win, ground=ground, inpit=inpit, found=[])
+        for frac in fractions:
+            # the full fill, lowered inside the pit by a constant (its gradient, if any, survives), never below ground
+            surf = np.array(fill_full[win], copy=True)
+            surf[inpit] = surf[inpit] - row.maxfill * (1 - frac)
+            rise = np.round(surf - ground, 3)
+            under = rise < 0
+            surf[under] = ground[under]
+            wet = rise > 0
+            if not wet.any():
+                continue
+            # a partial fill that stands above the existing carve's back-fill cannot improve on that carve
+            if row.completecarve == 1 and surf[wet].min() > carve_full[win][wet].min():
+                continue
+            trials.append(_Trial(pit, frac, win, surf.astype(np.float32)))
+
+    if trials:
+        shapes = [t.surface.shape for t in trials]
+        pos, H, W = _pack_shelves(shapes)
+        mosaic = np.full((H, W), nd, np.float32)
+        for t, (y, x) in zip(trials, pos):
+            h, w = t.surface.shape
+            t.slot = (slice(y, y + h), slice(x, x + w))
+            mosaic[t.slot] = t.surface
+        mos_dev = torch.from_numpy(mosaic).cuda()
+        carved_dev = core.breach_depressions(mos_dev, nodata=float(nodataval), max_length=radius, max_depth=max_carve_depth,
+                                             fill_pits=False)
+        carved = carved_dev.cpu().numpy()
+        # clumps of lowered cells (plus the windows' own nodata: the raster edge a carve may not run into)
+        change = np.full((H, W), 0.0, np.float32)
+        own_nd = np.zeros((H, W), bool)
+        for t in trials:
+            g = per_pit[t.pit]["ground"]
+            change[t.slot] = np.round(carved[t.slot] - g, 4)
+            own_nd[t.slot] = g == nd
+        clump_mask = ((change < 0) | own_nd).astype(np.uint8)
+        clumps = core.label(torch.from_numpy(clump_mask).cuda(), 8)[0].cpu().numpy()
+        for t in trials:
+            info = per_pit[t.pit]
+            g, inpit = info["ground"], info["inpit"]
+            d, lab = change[t.slot], clumps[t.slot]
+            cut = d < 0
+            reach = np.unique(lab[inpit & cut])           # clumps whose carve enters the pit
+            holes = np.flatnonzero((g == nd).ravel())
+            if holes.size and lab.ravel()[holes[0]] in reach:
+                continue                                   # that carve leaves through the raster edge
+            member = np.isin(lab, reach) if reach.size else np.zeros(lab.shape, bool)
+            if not member.any():
+                continue
+            region = member | inpit
+            if abs(d[region].min()) > max_carve_depth:
+                continue
+            r0, c0 = t.win[0].start, t.win[1].start
+            lr, lc = np.nonzero(region)
+            info["found"].append(dict(vol=np.sum(np.abs(d[region])), elevs=list(carved[t.slot][region]),
+                                      solution=int((info["row"].solution - 1000) + 10 * t.frac),
+                                      footprint=((lr + r0) * nx + (lc + c0)).astype(int)))
+
+    out = {}
+    for pit, info in per_pit.items():
+        row, cells = info["row"], info["cells"]
+        cand = list(info["found"])
+        # the plain fill, and the plain carve when it is complete, compete too
+        cand.append(dict(vol=row.volfill, elevs=list(np.asarray(fill_vec)[cells]), solution=2003, footprint=cells))
+        if row.completecarve == 1 and not np.isnan(row.volcarve + row.volfillbehind):
+            allc = np.unique(np.concatenate([np.asarray(carvecells_dct[pit], dtype=np.int64),
+                                             np.asarray(carve_fillcells_dct[pit], dtype=np.int64),
+                                             np.asarray(cells, dtype=np.int64)]))
+            cand.append(dict(vol=row.volcarve + row.volfillbehind, elevs=list(np.asarray(carve_vec)[allc]), solution=1003,
+                             footprint=list(allc)))
+        table = pd.DataFrame(cand, columns=["vol", "elevs", "solution", "footprint"])
+        best = table.solution[table["vol"].astype(float).idxmin()]
+        out[pit] = (best, table.loc[table.solution == best].copy())
+    return out
+
+
 def combined_solution(inDEM, inDEM_array, outpath, nx, ny, DFpits, fillcells_dct, carvecells_dct, carve_fillcells_dct,
                       pit_id, combined_fill_interval, fillID_vec, fill_vec, carve_vec, radius, maxcost, min_dist,
                       max_carve_depth, wbt, nodataval=-9999, fixflats=False, flat_increment=0.0, carve_method='SC',
                       water_array=None, wall_vec=None, del_temp_files=True):
-    """Same arguments and return value -- (solution_name, sol_df[vol, elevs, solution, footprint]) -- as the
-    reference.  Host orchestration over a window of (pit bounding box + radius + 2) cells; the breaches go through
-    `wbt.breach_depressions(max_length=radius, max_depth=max_carve_depth, fill_pits=False)` and the carve clumps
-    through the GPU labelling (8-connectivity, scipy numbering)."""
-    import glob
-    import pandas as pd
-    pit_df = DFpits.loc[pit_id].copy()
-    init_sol = pit_df.solution
-    footprint = np.asarray(fillcells_dct[pit_id])
-    completecarve = pit_df.completecarve
-    combined_sol = init_sol - 1000   # 3000 or 3020
-    combined_path = os.path.join(outpath, "combined_solutions")
-    os.makedirs(combined_path, exist_ok=True)
-
-    # window = bounding box of the pit + (radius + 2) cells, clipped to the raster (pyct.clip_to_window)
-    clip_buf = radius + 2
-    rows, cols = np.unravel_index(footprint, (ny, nx))
-    row_min = int(max(0, rows.min() - clip_buf))
-    row_max = int(min(ny, rows.max() + clip_buf + 1))
-    col_min = int(max(0, cols.min() - clip_buf))
-    col_max = int(min(nx, cols.max() + clip_buf + 1))
-    ny_c, nx_c = row_max - row_min, col_max - col_min
-    rr, cc = np.mgrid[row_min:row_max, col_min:col_max]
-    clipped_ind = np.ravel_multi_index((rr.ravel(), cc.ravel()), (ny, nx))
-    win = (slice(row_min, row_max), slice(col_min, col_max))
-    _, meta = raster_io.read_raster(inDEM)
-    wmeta = _window_meta(meta, row_min, col_min)
-    clippedDEM = os.path.join(combined_path, "{0}.tif".format(pit_id))
-    inDEM_array_clipped = np.ascontiguousarray(np.asarray(inDEM_array)[win], dtype=np.float32)
-    raster_io.write_raster(clippedDEM, inDEM_array_clipped, wmeta, nodata=nodataval)
-    inDEM_vec_clipped = inDEM_array_clipped.reshape(ny_c * nx_c,)
-    fill_vec_clipped = np.asarray(fill_vec).reshape(ny, nx)[win].reshape(ny_c * nx_c,)
-    carve_vec_orig_clipped = np.asarray(carve_vec).reshape(ny, nx)[win].reshape(ny_c * nx_c,)
-    fillID_clipped_vec = np.asarray(fillID_vec)[clipped_ind]
-    footprint_clipped = np.flatnonzero(fillID_clipped_vec == pit_id)
-
-    maxfill_value = pit_df.maxfill
-    vols, elevs, sol_names, dep_indices = [], [], [], []
-
-    fraction_list = np.round(np.arange(combined_fill_interval, 1, combined_fill_interval), 1)
-    for frac in fraction_list:
-        # lower the full fill by a constant (keeps any gradient of the fill), never below ground (:905-914)
-        SF_vec = np.copy(fill_vec_clipped)
-        fill_depth_remove = maxfill_value * (1 - frac)
-        SF_vec[footprint_clipped] = SF_vec[footprint_clipped] - fill_depth_remove
-        SF_diff = np.round((SF_vec - inDEM_vec_clipped), 3)
-        belowground_ind = np.where(SF_diff < 0)[0]
-        fill_frac_ind = np.where(SF_diff > 0)[0]
-        SF_vec[belowground_ind] = inDEM_vec_clipped[belowground_ind]
-        p_fill_min = (SF_vec[fill_frac_ind]).min()
-        carve_fill_min = (carve_vec_orig_clipped[fill_frac_ind]).min()
-        if (completecarve == 1) and (p_fill_min > carve_fill_min):   # partial fill above the carve's back-fill
-            continue
-        clippedDEM_SF = os.path.join(combined_path, "{0}_SF_{1}.tif".format(pit_id, frac))
-        raster_io.write_raster(clippedDEM_SF, SF_vec.reshape(ny_c, nx_c).astype(np.float32), wmeta, nodata=nodataval)
-        clippedDEM_carved = os.path.join(combined_path, "{0}_SF_{1}_{2}.tif".format(pit_id, frac, carve_method))
-        if carve_method == 'LC':
-            wbt.breach_depressions_least_cost(clippedDEM_SF, clippedDEM_carved, radius, max_cost=maxcost,
-                                              min_dist=min_dist, flat_increment=flat_increment, fill=False)
-            clippedDEM_filled = os.path.join(combined_path, "{0}_SF_{1}_{2}_filled.tif".format(pit_id, frac, carve_method))
-            wbt.fill_depressions_wang_and_liu(clippedDEM_carved, clippedDEM_filled, fix_flats=fixflats,
-                                              flat_increment=flat_increment)
-        else:
-            wbt.breach_depressions(clippedDEM_SF, clippedDEM_carved, max_length=radius, max_depth=max_carve_depth,
-                                   fill_pits=False, flat_increment=flat_increment, callback=None)
-        clippedDEM_carved_array, _ = raster_io.read_raster(clippedDEM_carved)
-
-        # carves that touch the pit, as 8-connected clumps of (lowered or nodata) cells (:958-985)
-        diff_array_clip = np.round((clippedDEM_carved_array - inDEM_array_clipped), 4)
-        diff_vec_clip = diff_array_clip.reshape(ny_c * nx_c,)
-        mask_carve = np.zeros(inDEM_array_clipped.shape, dtype=np.int8)
-        mask_carve[diff_array_clip < 0] = 1
-        mask_carve[inDEM_array_clipped == nodataval] = 1
-        carveID_clip_array, _ = core.label(mask_carve, 8)
-        carveID_clip_vec = np.asarray(carveID_clip_array).reshape(ny_c * nx_c,)
-        carve_ind_clipped = np.flatnonzero(diff_vec_clip < 0.0)
-        carve_intersect = np.intersect1d(footprint_clipped, carve_ind_clipped, assume_unique=True)
-        carveIDs_pit = np.unique(carveID_clip_vec[carve_intersect])
-        carvecells_add = list(np.flatnonzero(np.isin(carveID_clip_vec, carveIDs_pit)))
-        nodata_clipped_ind = np.flatnonzero(inDEM_vec_clipped == nodataval)
-        if len(nodata_clipped_ind > 0):        # the window holds raster edge: a carve running off it is disqualified
-            carveout_ID = carveID_clip_vec[nodata_clipped_ind][0]
-            if carveout_ID in list(carveIDs_pit):
-                continue
-        if len(carvecells_add) < 1:
-            continue
-        expanded_footprint_clipped = list(set(carvecells_add + list(footprint_clipped)))
-        expanded_footprint = clipped_ind[expanded_footprint_clipped]
-        volchange = np.sum(abs(diff_vec_clip[expanded_footprint_clipped]))
-        maxcarvedepth = abs(diff_vec_clip[expanded_footprint_clipped].min())
-        if maxcarvedepth <= max_carve_depth:
-            elevs.append(list(clippedDEM_carved_array.reshape(ny_c * nx_c,)[expanded_footprint_clipped]))
-            vols.append(volchange)
-            dep_indices.append(expanded_footprint.astype(int))
-            if int(frac * 10) == 0:
-                if combined_sol == 3020:
-                    sol_names.append(1020)
-                elif combined_sol == 3000:
-                    sol_names.append(1003)
-            else:
-                sol_names.append(int(combined_sol + (10 * frac)))
-        if del_temp_files:
-            for f in glob.glob(os.path.join(combined_path, '{0}_*.tif'.format(pit_id))):
-                if os.path.isfile(f):
-                    os.remove(f)
-
-    # the plain fill, and the plain carve when it is complete, compete too (:1098-1117)
-    sol_names.append(2003)
-    vols.append(pit_df.volfill)
-    dep_indices.append(footprint)
-    elevs.append(list(np.asarray(fill_vec)[footprint]))
-    if completecarve == 1:
-        vol_total = pit_df.volcarve + pit_df.volfillbehind
-        carve_cells_all = list(set(list(carvecells_dct[pit_id]) + list(carve_fillcells_dct[pit_id]) + list(footprint)))
-        if not np.isnan(vol_total):
-            sol_names.append(1003)
-            vols.append(vol_total)
-            dep_indices.append(carve_cells_all)
-            elevs.append(list(np.asarray(carve_vec)[carve_cells_all]))
-
-    df_combined = pd.DataFrame(columns=["vol", "elevs", "solution", "footprint"])
-    df_combined["vol"] = vols
-    df_combined["elevs"] = elevs
-    df_combined["solution"] = sol_names
-    df_combined["footprint"] = dep_indices
-    solution_name = df_combined.solution[df_combined["vol"].idxmin()]
-    sol_df = df_combined.loc[df_combined.solution == solution_name].copy()
-    for f in glob.glob(os.path.join(combined_path, '*.tif')):
-        if os.path.isfile(f):
-            os.remove(f)
-    return solution_name, sol_df
+    """tools/depressions.py:813-1137 for one pit: same arguments, same return value (solution_name,
+    sol_df[vol, elevs, solution, footprint]).  A one-pit call of `combined_solutions` (above); the window rasters
+    live in memory only -- upstream writes them under <outpath>/combined_solutions and deletes every one of them
+    before returning (:1132-1135).  `carve_method='LC'` and a graded `flat_increment` are not built."""
+    if carve_method == 'LC':
+        raise NotImplementedError("carve_method='LC' (breach_depressions_least_cost) is not built")
+    if flat_increment and flat_increment > 0:
+        raise NotImplementedError("flat_increment > 0 is not offered (see wbt.WhiteboxToolsGPU)")
+    os.makedirs(os.path.join(outpath, "combined_solutions"), exist_ok=True)
+    res = combined_solutions([pit_id], inDEM_array, nx, ny, DFpits, fillcells_dct, carvecells_dct, carve_fillcells_dct,
+                             combined_fill_interval, fillID_vec, fill_vec, carve_vec, radius, max_carve_depth,
+                             nodataval=nodataval)
+    return res[pit_id]

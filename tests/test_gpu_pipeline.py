@@ -96,3 +96,79 @@ def test_combined_solution_window_geometry(tmp_path):
     w = _window_meta(m, 8, 20)
     assert list(w["geo"][33922][1])[3:5] == [100.0 + 20 * 0.5, 50.0 - 8 * 0.25]
     assert list(m["geo"][33922][1])[3:5] == [100.0, 50.0]
+
+
+@pytest.mark.gpu
+def test_combined_solutions_batch_equals_window_by_window_evaluation(tmp_path):
+    """the mosaic evaluation (all pits' partial fills in ONE breach + ONE labelling) must give, per pit, what a
+    stand-alone breach of each clipped window gives: same chosen solution, same volume, same elevations"""
+    import pydrodem_b200 as hc
+    from pydrodem_b200 import raster_io
+    from pydrodem_b200.tools import depressions as dep
+    from pydrodem_b200.wbt import WhiteboxToolsGPU
+    z = unit_dem(240, 250, 11)
+    dem = str(tmp_path / "u.tif")
+    raster_io.write_raster(dem, z, None, nodata=ND)
+    wbt = WhiteboxToolsGPU()
+    radius, mcd, step = 12, 6, 0.2
+    modv, fillv, carvev, dfill, dcarve, fid, cid, cfid, nx, ny = dep.initial_fill_carve(dem, "u", str(tmp_path), 'WL', 200,
+                                                                                         radius, False, ND, None, wbt, sfill=0.5)
+    DF, fc, cco, cc, cfc = dep.build_pit_catalog(modv, ND, carvev, dcarve, dfill, fid, cid, cfid)
+    DF = dep.select_solution(DF, fc, cc, cco, fillv, carvev, fid, cid, 60, 25, mcd, water_mask_array=np.zeros(z.shape, np.uint8))
+    pits = [int(p) for p in DF.index.values if 4000 <= DF.solution[p] < 5000]
+    assert len(pits) >= 2
+    ground = np.asarray(modv, np.float32).reshape(ny, nx)
+    res = dep.combined_solutions(pits, ground, nx, ny, DF, fc, cc, cfc, step, fid, fillv, carvev, radius, mcd, nodataval=ND)
+    fill2, ids2 = np.asarray(fillv).reshape(ny, nx), np.asarray(fid).reshape(ny, nx)
+    carve2 = np.asarray(carvev).reshape(ny, nx)
+    for pit in pits:
+        row = DF.loc[pit]
+        cells = np.asarray(fc[pit])
+        rr, cc_ = np.divmod(cells, nx)
+        win = (slice(max(0, rr.min() - radius - 2), min(ny, rr.max() + radius + 3)),
+               slice(max(0, cc_.min() - radius - 2), min(nx, cc_.max() + radius + 3)))
+        g, inpit = ground[win], ids2[win] == pit
+        best = (float(row.volfill), 2003, None)
+        if row.completecarve == 1 and not np.isnan(row.volcarve + row.volfillbehind):
+            v = float(row.volcarve + row.volfillbehind)
+            if v < best[0]:
+                best = (v, 1003, None)
+        cands = []
+        for frac in np.round(np.arange(step, 1, step), 1):
+            surf = fill2[win].copy()
+            surf[inpit] = surf[inpit] - row.maxfill * (1 - frac)
+            rise = np.round(surf - g, 3)
+            surf[rise < 0] = g[rise < 0]
+            wet = rise > 0
+            if not wet.any() or (row.completecarve == 1 and surf[wet].min() > carve2[win][wet].min()):
+                continue
+            carved = hc.breach_depressions(surf.astype(np.float32), nodata=ND, max_length=radius, max_depth=mcd, fill_pits=False)
+            d = np.round(carved - g, 4)
+            lab, _ = hc.label(((d < 0) | (g == ND)).astype(np.uint8), 8)
+            reach = np.unique(lab[inpit & (d < 0)])
+            holes = np.flatnonzero((g == ND).ravel())
+            if holes.size and lab.ravel()[holes[0]] in reach:
+                continue
+            region = (np.isin(lab, reach) if reach.size else np.zeros(lab.shape, bool))
+            if not region.any():
+                continue
+            region |= inpit
+            if abs(d[region].min()) > mcd:
+                continue
+            cands.append((float(np.sum(np.abs(d[region]))), int(row.solution - 1000 + 10 * frac), carved[region]))
+        # candidates are listed before the plain fill / carve; the first minimum wins
+        pick = None
+        for v, name, el in cands:
+            if pick is None or v < pick[0]:
+                pick = (v, name, el)
+        if pick is None or not (pick[0] <= best[0]):
+            pick = best if pick is None or best[0] < pick[0] else pick
+        name, sol = res[pit]
+        assert int(name) == int(pick[1]), (pit, name, pick[1])
+        assert abs(float(sol.vol.values[0]) - pick[0]) <= 1e-4 * max(1.0, abs(pick[0]))
+        if pick[2] is not None:
+            assert np.array_equal(np.asarray(sol.elevs.values[0], np.float32), pick[2])
+    # and the one-pit entry point with the reference's signature gives the same answer
+    name1, sol1 = dep.combined_solution(dem, ground, str(tmp_path), nx, ny, DF, fc, cc, cfc, pits[0], step, fid, fillv, carvev,
+                                        radius, 200, False, mcd, wbt, nodataval=ND)
+    assert int(name1) == int(res[pits[0]][0])
