@@ -528,7 +528,7 @@ def run_c1(args, world, rank, local, dev):
         synth.make_dem(n, n, 1001 + rank, nodata_frame=True, device=dev).cpu().numpy()
     stage = {}
     for name in ("fill_pits", "create_clump_array", "fill_shallow_pits", "breach_pits", "build_pit_catalog",
-                 "select_solution", "apply_solution", "combined_solution"):
+                 "select_solution", "apply_solution", "combined_solutions"):
         fn = getattr(dep, name)
 
         def wrap(*a, __fn=fn, __name=name, **k):

@@ -49,7 +49,12 @@ enum hc_status {
 const char *hc_last_error(void);
 int hc_version(void);
 
-/* one context per (process, device): owns the workspace arena and scratch events */
+/* A context owns the workspace arena, a pinned mailbox, the *_host staging buffers and the band state.
+ * Threading contract: every entry point that takes a context holds the context's (recursive) lock for the
+ * duration of the call, so concurrent callers of ONE context serialise; the device work a call enqueues runs on the
+ * stream it was given.  Calls on different streams through one context are therefore safe but not concurrent (each
+ * public call rewinds the one arena): use one context per thread / stream for concurrency (hc_create is cheap).
+ * hc_fill_host / hc_label_host share staging buffers with hc_fill_d8_accum_host_begin and wait for its copies. */
 int hc_create(hc_ctx **ctx, int device);
 int hc_destroy(hc_ctx *ctx);
 /* bytes of device workspace currently held */

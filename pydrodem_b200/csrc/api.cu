@@ -19,6 +19,7 @@ extern "C" int hc_version(void) { return 100; }
 
 extern "C" int hc_debug_read(hc_ctx *ctx, unsigned long long *out16) {
   if (!ctx || !out16) return HC_ERR_ARG;
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   HC_CUDA(cudaDeviceSynchronize());
   HC_CUDA(cudaMemcpy(out16, ctx->d_dbg, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
@@ -129,6 +130,7 @@ void prof_end(hc_ctx *ctx) {
 
 extern "C" int hc_profile_enable(hc_ctx *ctx, int on, int max_records) {
   if (!ctx) return HC_ERR_ARG;
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   if (on && !ctx->prof_ev) {
     int cap = max_records > 0 ? max_records : 8192;
@@ -147,6 +149,7 @@ extern "C" int hc_profile_enable(hc_ctx *ctx, int on, int max_records) {
 // Writes "name count total_ms max_ms\n" per kernel name into buf (NUL terminated); resets the log.
 extern "C" int hc_profile_read(hc_ctx *ctx, char *buf, int64_t buflen) {
   if (!ctx || !buf || buflen < 2) return HC_ERR_ARG;
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   HC_CUDA(cudaDeviceSynchronize());
   struct agg { const char *name; int64_t cnt; double tot, mx; };
@@ -187,6 +190,13 @@ extern "C" int hc_create(hc_ctx **out, int device) {
   hc_ctx *ctx = (hc_ctx *)calloc(1, sizeof(hc_ctx));
   if (!ctx) return HC_ERR_NOMEM;
   ctx->device = device;
+  {
+    pthread_mutexattr_t at;
+    pthread_mutexattr_init(&at);
+    pthread_mutexattr_settype(&at, PTHREAD_MUTEX_RECURSIVE);
+    pthread_mutex_init(&ctx->mu, &at);
+    pthread_mutexattr_destroy(&at);
+  }
   cudaDeviceProp prop;
   HC_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
@@ -224,6 +234,7 @@ extern "C" int hc_destroy(hc_ctx *ctx) {
   if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  pthread_mutex_destroy(&ctx->mu);
   free(ctx);
   return HC_OK;
 }
@@ -240,11 +251,7 @@ extern "C" int hc_fill_stats(const hc_ctx *ctx, int64_t *n_basins, int32_t *n_ro
   return HC_OK;
 }
 
-#define CHECK_CTX(ctx)                                             \
-  do {                                                             \
-    if (!(ctx)) { hc_set_error("null context"); return HC_ERR_ARG; } \
-    HC_CUDA(cudaSetDevice((ctx)->device));                         \
-  } while (0)
+#define CHECK_CTX(ctx) HC_ENTER(ctx)
 
 static int check_shape(int64_t ny, int64_t nx) {
   if (ny < 0 || nx < 0) { hc_set_error("negative shape"); return HC_ERR_ARG; }
@@ -374,6 +381,10 @@ extern "C" int hc_fill_host(hc_ctx *ctx, const float *z, float *out, int64_t ny,
   size_t n = (size_t)ny * nx;
   if (!n) return HC_OK;
   if (!z || !out) { hc_set_error("hc_fill_host: null pointer"); return HC_ERR_ARG; }
+  // shares the staging buffers of hc_fill_d8_accum_host_begin(slot 0): wait until that call's copies have landed
+  HC_CUDA(cudaEventSynchronize(ctx->ev_done[0]));
+  HC_CUDA(cudaEventSynchronize(ctx->ev_done[1]));
+  HC_CUDA(cudaStreamSynchronize(ctx->s_compute));
   dev_buf dz(ctx, 0), dout(ctx, 1);
   HC_TRY(dz.alloc(n * 4));
   HC_TRY(dout.alloc(n * 4));
@@ -465,6 +476,9 @@ extern "C" int hc_label_host(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int
   if (nlab) *nlab = 0;
   if (!n) return HC_OK;
   if (!mask || !lab) { hc_set_error("hc_label_host: null pointer"); return HC_ERR_ARG; }
+  HC_CUDA(cudaEventSynchronize(ctx->ev_done[0]));
+  HC_CUDA(cudaEventSynchronize(ctx->ev_done[1]));
+  HC_CUDA(cudaStreamSynchronize(ctx->s_compute));
   dev_buf dm(ctx, 2), dl(ctx, 4);
   HC_TRY(dm.alloc(n));
   HC_TRY(dl.alloc(n * 4));

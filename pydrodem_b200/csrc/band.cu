@@ -4,11 +4,7 @@
 // pydrodem_b200/bands.py) — the library never talks to another rank.
 #include "common.cuh"
 
-#define CHECK_CTX(ctx)                                             \
-  do {                                                             \
-    if (!(ctx)) { hc_set_error("null context"); return HC_ERR_ARG; } \
-    HC_CUDA(cudaSetDevice((ctx)->device));                         \
-  } while (0)
+#define CHECK_CTX(ctx) HC_ENTER(ctx)
 
 static int check_band(int64_t nb, int64_t nx, int flags) {
   if (nb <= 0 || nx <= 0) { hc_set_error("band: empty shape"); return HC_ERR_ARG; }

@@ -401,6 +401,7 @@ extern "C" int hc_breach_flowpath_dev(hc_ctx *ctx, const float *w, float *out, f
                                       uint8_t *seed, int64_t ny, int64_t nx, float nodata, double dx, double dy,
                                       int64_t max_length, double max_depth, int64_t *stats, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   if (stats) memset(stats, 0, sizeof(int64_t) * 4);
   if (ny <= 0 || nx <= 0) return HC_OK;

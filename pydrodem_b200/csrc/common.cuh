@@ -1,6 +1,7 @@
 // common.cuh — context, workspace arena, error plumbing shared by every pass of libhydrocore.
 #pragma once
 #include <cuda_runtime.h>
+#include <pthread.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -80,6 +81,10 @@ struct hc_block { char *p; size_t cap, off; };
 
 struct hc_ctx {
   int device;
+  // one call at a time per context: every entry point holds this (recursive) lock while it touches the arena, the
+  // mailbox, the staging buffers or the band state; concurrent callers of ONE context serialise instead of
+  // overwriting each other's workspace.  Use one context per thread / stream for concurrency.
+  pthread_mutex_t mu;
   int sm_count;
   // chunked bump arena: blocks are only ever ADDED inside a pass (pointers handed out stay
   // valid); arena_reset() at the start of a public call coalesces them into one block, so a
@@ -116,6 +121,19 @@ struct hc_ctx {
   const char **prof_name;
   cudaStream_t prof_stream;
 };
+
+struct hc_guard {
+  hc_ctx *c;
+  explicit hc_guard(hc_ctx *ctx) : c(ctx) { pthread_mutex_lock(&c->mu); }
+  ~hc_guard() { pthread_mutex_unlock(&c->mu); }
+  hc_guard(const hc_guard &) = delete;
+  hc_guard &operator=(const hc_guard &) = delete;
+};
+// first statement of every extern "C" entry point that takes a context
+#define HC_ENTER(ctx)                                                \
+  if (!(ctx)) { hc_set_error("null context"); return HC_ERR_ARG; }  \
+  hc_guard hc_guard__(ctx);                                          \
+  HC_CUDA(cudaSetDevice((ctx)->device))
 
 void prof_begin(hc_ctx *ctx, cudaStream_t st, const char *name);
 void prof_end(hc_ctx *ctx);

@@ -353,6 +353,7 @@ k_band_lab_out(const u32 *__restrict__ L, const u32 *__restrict__ G, const u32 *
 extern "C" int hc_band_label_local_dev(hc_ctx *ctx, const uint8_t *mask, int64_t nb, int64_t nx, int conn, int64_t row0,
                                        uint32_t *seam_out, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   if (!mask || !seam_out || nb <= 0 || nx <= 0 || (conn != 4 && conn != 8)) { hc_set_error("hc_band_label_local: bad argument"); return HC_ERR_ARG; }
   if ((double)(row0 + nb) * (double)nx >= 2147483632.0) { hc_set_error("labelled raster exceeds the 31-bit cell index"); return HC_ERR_TOO_LARGE; }
@@ -378,6 +379,7 @@ extern "C" int hc_band_label_local_dev(hc_ctx *ctx, const uint8_t *mask, int64_t
 extern "C" int hc_band_label_relax_dev(hc_ctx *ctx, const uint32_t *all_seams, int64_t nbands, int64_t band_index,
                                        uint32_t *seam_out, int *changed, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   band_label_state *s = &ctx->band_label;
   if (!s->ready || !all_seams || !seam_out) { hc_set_error("hc_band_label_relax: local phase first"); return HC_ERR_ARG; }
@@ -396,6 +398,7 @@ extern "C" int hc_band_label_relax_dev(hc_ctx *ctx, const uint32_t *all_seams, i
 // rank the owned roots locally; *n_owned (host) = components whose first cell lies in this band
 extern "C" int hc_band_label_rank_dev(hc_ctx *ctx, int64_t *n_owned, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   band_label_state *s = &ctx->band_label;
   if (!s->ready) { hc_set_error("hc_band_label_rank: local phase first"); return HC_ERR_ARG; }
@@ -422,6 +425,7 @@ extern "C" int hc_band_label_rank_dev(hc_ctx *ctx, int64_t *n_owned, void *strea
 // pairs_out[2][nx][2]: (global root, id) of the seam cells of owned components (id = offset + local rank)
 extern "C" int hc_band_label_pairs_dev(hc_ctx *ctx, int64_t offset, uint32_t *pairs_out, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   band_label_state *s = &ctx->band_label;
   if (!s->ready || !pairs_out) { hc_set_error("hc_band_label_pairs: rank phase first"); return HC_ERR_ARG; }
@@ -434,6 +438,7 @@ extern "C" int hc_band_label_pairs_dev(hc_ctx *ctx, int64_t offset, uint32_t *pa
 extern "C" int hc_band_label_finish_dev(hc_ctx *ctx, int64_t offset, const uint32_t *keys, const uint32_t *vals,
                                         int64_t nkeys, int32_t *lab, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   band_label_state *s = &ctx->band_label;
   if (!s->ready || !lab) { hc_set_error("hc_band_label_finish: rank phase first"); return HC_ERR_ARG; }
@@ -453,6 +458,7 @@ __global__ void k_gather_flag(const int32_t *__restrict__ lab, const uint8_t *__
 }
 extern "C" int hc_gather_flag_dev(hc_ctx *ctx, const int32_t *lab, const uint8_t *flag, uint8_t *out, int64_t n, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   if (n <= 0) return HC_OK;
   if (!lab || !flag || !out) { hc_set_error("hc_gather_flag: null pointer"); return HC_ERR_ARG; }

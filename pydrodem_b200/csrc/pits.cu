@@ -156,11 +156,7 @@ int taudem_fix_run(hc_ctx *ctx, const float *dem, const uint8_t *flat, float *ou
 }
 
 // ---- C ABI -----------------------------------------------------------------------------------------
-#define PITS_CTX(ctx)                                                \
-  do {                                                               \
-    if (!(ctx)) { hc_set_error("null context"); return HC_ERR_ARG; } \
-    HC_CUDA(cudaSetDevice((ctx)->device));                           \
-  } while (0)
+#define PITS_CTX(ctx) HC_ENTER(ctx)
 
 extern "C" int hc_fill_single_cell_pits_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx,
                                             float nodata, void *stream) {

@@ -177,6 +177,7 @@ extern "C" int hc_seg_stats_dev(hc_ctx *ctx, const int32_t *ids, const float *va
                                 int32_t nseg, int32_t lo_id, float *vmax, float *vmin, double *vsum, int64_t *count,
                                 void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   if (n < 0 || nseg < 0 || !ids) { hc_set_error("hc_seg_stats: bad argument"); return HC_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -208,6 +209,7 @@ extern "C" int hc_pit_catalog_dev(hc_ctx *ctx, const float *dem, float nodata, c
                                   int64_t *pairs_out, int64_t pair_cap, uint8_t *pair_included, int64_t *npairs,
                                   void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   if (n <= 0 || n >= 0x7FFFFFF0ll || npits < 0 || ncarves < 0) { hc_set_error("hc_pit_catalog: bad shape"); return HC_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -348,6 +350,7 @@ extern "C" int hc_pit_select_dev(hc_ctx *ctx, const int32_t *fillID, const int32
                                  double max_carve_depth, double maxcarve_factor, int apply_shallow_fill,
                                  int float32_scalars, int32_t *solution, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   if (!water) { hc_set_error("select_solution: water_mask_array is None (the reference raises NameError here, tools/depressions.py:606-647)"); return HC_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -439,6 +442,7 @@ extern "C" int hc_pit_apply_dev(hc_ctx *ctx, const float *dem, const float *fill
                                 const uint8_t *pit_out, const int64_t *ncarvecells, const int64_t *pairs,
                                 const uint8_t *pair_included, int64_t npairs, float *out, int16_t *mask, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   HC_TRY(arena_reset(ctx));
@@ -482,6 +486,7 @@ extern "C" int hc_fill_shallow_pits_dev(hc_ctx *ctx, float *mod, float sfill, co
                                         const float *fillv, const float *water, int64_t n, int32_t npits,
                                         int64_t *n_shallow, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   HC_TRY(arena_reset(ctx));
@@ -498,8 +503,13 @@ extern "C" int hc_fill_shallow_pits_dev(hc_ctx *ctx, float *mod, float sfill, co
     // number of labels (background included) that were filled, as the reference prints it
     uint8_t *h = (uint8_t *)malloc((size_t)npits + 1);
     if (!h) return HC_ERR_NOMEM;
-    HC_CUDA(cudaMemcpyAsync(h, keep, (size_t)npits + 1, cudaMemcpyDeviceToHost, st));
-    HC_CUDA(cudaStreamSynchronize(st));
+    cudaError_t e1 = cudaMemcpyAsync(h, keep, (size_t)npits + 1, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = e1 == cudaSuccess ? cudaStreamSynchronize(st) : e1;
+    if (e2 != cudaSuccess) {
+      free(h);
+      hc_set_error("hc_fill_shallow_pits: read-back -> %s", cudaGetErrorString(e2));
+      return HC_ERR_CUDA;
+    }
     int64_t c = 0;
     for (int32_t p = 0; p <= npits; p++) c += h[p] ? 0 : 1;
     free(h);
@@ -528,6 +538,7 @@ k_radix_hist(const float *__restrict__ x, size_t n, u32 prefix, u32 prefix_mask,
 // value of the k-th smallest element (0-based) of x[0..n); x must not contain NaN.  Host pointer out.
 extern "C" int hc_kth_value_dev(hc_ctx *ctx, const float *x, int64_t n, int64_t k, float *value, void *stream) {
   if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   if (!x || !value || n <= 0 || k < 0 || k >= n) { hc_set_error("hc_kth_value: bad argument"); return HC_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;

@@ -300,11 +300,7 @@ k_dtm_select(const float *__restrict__ dem, const float *__restrict__ z9, const 
 }
 
 // ---- C ABI --------------------------------------------------------------------------------------------
-#define ST_CTX(ctx)                                                  \
-  do {                                                               \
-    if (!(ctx)) { hc_set_error("null context"); return HC_ERR_ARG; } \
-    HC_CUDA(cudaSetDevice((ctx)->device));                           \
-  } while (0)
+#define ST_CTX(ctx) HC_ENTER(ctx)
 
 static grad_prm make_grad(double dx, double dy) {
   grad_prm p;

@@ -160,11 +160,7 @@ static int mm_filter(hc_ctx *ctx, const T *in, T *out, T *tmp, int ny, int nx, i
   return HC_OK;
 }
 
-#define W_CTX(ctx)                                                   \
-  do {                                                               \
-    if (!(ctx)) { hc_set_error("null context"); return HC_ERR_ARG; } \
-    HC_CUDA(cudaSetDevice((ctx)->device));                           \
-  } while (0)
+#define W_CTX(ctx) HC_ENTER(ctx)
 
 static bool w_dims_ok(int64_t ny, int64_t nx, int size) {
   return ny > 0 && nx > 0 && ny <= 65535 && nx < (1 << 30) && size >= 1 && size <= 1025;

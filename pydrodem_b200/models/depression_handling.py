@@ -108,11 +108,14 @@ class DepHandleCore:
     def run_depression_core(self, inDEM, outpath, water_mask_array=None, wall_array=None, sink_mask=None):
         """depression_core + the final fill of run_depression_handling (:470-484).  Returns (ffill_array,
         modDEMoutput_array, DFpits, solution_mask_array); ffill_array is the conditioned DEM."""
-        _, meta = raster_io.read_raster(inDEM)
-        outDEM_array, DFpits, solution_mask_array = self.depression_core(inDEM, outpath, water_mask_array, wall_array,
-                                                                        sink_mask)
-        outDEM_tif_temp = inDEM.replace('.tif', '_conditionedTEMP.tif')
-        raster_io.write_raster(outDEM_tif_temp, outDEM_array.astype(np.float32), meta, nodata=self.nodataval)
-        ffill_array, _ = dep.fill_pits(outDEM_tif_temp, self.wbt, save_tif=False, nodataval=self.nodataval)
-        raster_io.write_raster(outDEM_tif_temp, ffill_array.astype(np.float32), meta, nodata=self.nodataval)
+        # (rasters nobody reads back at once -- difference maps, id rasters, masks -- are written behind the pipeline's
+        #  back; every file is complete when this method returns)
+        with raster_io.write_behind():
+            _, meta = raster_io.read_raster(inDEM)
+            outDEM_array, DFpits, solution_mask_array = self.depression_core(inDEM, outpath, water_mask_array, wall_array,
+                                                                            sink_mask)
+            outDEM_tif_temp = inDEM.replace('.tif', '_conditionedTEMP.tif')
+            raster_io.write_raster(outDEM_tif_temp, outDEM_array.astype(np.float32), meta, nodata=self.nodataval)
+            ffill_array, _ = dep.fill_pits(outDEM_tif_temp, self.wbt, save_tif=False, nodataval=self.nodataval)
+            raster_io.write_raster(outDEM_tif_temp, ffill_array.astype(np.float32), meta, nodata=self.nodataval)
         return ffill_array, outDEM_array, DFpits, solution_mask_array

@@ -13,6 +13,7 @@ are carried through verbatim.  Anything else raises.  `.npy` paths are accepted 
 import json
 import os
 import struct
+import threading
 
 import numpy as np
 
@@ -74,6 +75,11 @@ def _tag_values(f, big, entry):
 
 
 def read_raster(path):
+    _WB.wait_for(path)
+    return _read_raster_now(path)
+
+
+def _read_raster_now(path):
     """-> (2-D numpy array, RasterMeta)."""
     if path.endswith(".npy"):
         arr = np.load(path)
@@ -182,10 +188,84 @@ def _unpredict(b, pred, rows, cols, dtype):
     return np.ascontiguousarray(planes.transpose(0, 2, 1)).view(dtype).reshape(rows, cols)
 
 
+class _WriteBehind:
+    """Write-behind for a unit pipeline: inside `with write_behind():` a write_raster() call snapshots the array, creates
+    the (empty) file at once -- os.path.exists() is true from then on -- and hands the encoding + file write to one
+    background thread; read_raster() of such a path waits for its write; leaving the block waits for all of them and
+    re-raises the first failure.  The pipeline's own kernels and numpy work overlap the ~50-120 ms a 3601^2 raster takes
+    to reach the page cache.  Off by default: outside the block every write is synchronous."""
+
+    def __init__(self):
+        self.depth = 0
+        self.pool = None
+        self.pending = {}
+        self.lock = threading.Lock()
+
+    def __enter__(self):
+        with self.lock:
+            if self.depth == 0:
+                from concurrent.futures import ThreadPoolExecutor
+                self.pool = ThreadPoolExecutor(max_workers=1)
+            self.depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        with self.lock:
+            self.depth -= 1
+            last = self.depth == 0
+        if last:
+            self.flush()
+            self.pool.shutdown(wait=True)
+            self.pool = None
+        return False
+
+    def flush(self):
+        with self.lock:
+            futs = list(self.pending.values())
+            self.pending.clear()
+        err = None
+        for f in futs:
+            try:
+                f.result()
+            except Exception as e:  # noqa: BLE001  (re-raised below)
+                err = err or e
+        if err is not None:
+            raise err
+
+    def wait_for(self, path):
+        with self.lock:
+            f = self.pending.pop(os.path.abspath(path), None)
+        if f is not None:
+            f.result()
+
+
+_WB = _WriteBehind()
+
+
+def write_behind():
+    """context manager: see _WriteBehind"""
+    return _WB
+
+
 def write_raster(path, arr, meta=None, nodata=None, compress=None, tiled=False):
     """Write a 2-D array as a single-band GeoTIFF (BigTIFF above 3.9 GB): uncompressed strips by default,
     `compress='lzw'` (what pyct.tifcompress produces, tools/convert.py:312) or `'deflate'`; `tiled=True` lays the
-    raster out in 256 x 256 tiles (GDAL's TILED=YES block size; `["COMPRESS=LZW", "TILED=YES"]`, tools/convert.py:202)."""
+    raster out in 256 x 256 tiles (GDAL's TILED=YES block size; `["COMPRESS=LZW", "TILED=YES"]`, tools/convert.py:202).
+    Inside `with write_behind():` the write is queued (see _WriteBehind)."""
+    if _WB.depth > 0 and _WB.pool is not None:
+        snap = np.array(arr, copy=True, order="C")
+        if snap.ndim != 2:
+            raise ValueError("write_raster needs a 2-D array")
+        _WB.wait_for(path)                       # an earlier queued write of the same path goes first
+        open(path, "wb").close()
+        fut = _WB.pool.submit(_write_raster_now, path, snap, meta, nodata, compress, tiled)
+        with _WB.lock:
+            _WB.pending[os.path.abspath(path)] = fut
+        return
+    _write_raster_now(path, arr, meta, nodata, compress, tiled)
+
+
+def _write_raster_now(path, arr, meta=None, nodata=None, compress=None, tiled=False):
     arr = np.ascontiguousarray(arr)
     if arr.ndim != 2:
         raise ValueError("write_raster needs a 2-D array")

@@ -464,6 +464,7 @@ def initial_fill_carve(inDEM_tif, basename, outpath, fill_method, maxcost, radiu
     carvefillID_vec = carvefillID_array.reshape(ny * nx,)
 
     if del_temp_files:                                                                        # :236-238 (ft.erase_files)
+        raster_io.write_behind().flush()     # (queued writes of the files about to be erased must have landed)
         basename_mod = os.path.splitext(os.path.basename(modDEM_tif))[0]
         for f in glob.glob(os.path.join(outpath, '{0}_*.tif'.format(basename_mod))):
             if os.path.isfile(f):

@@ -31,6 +31,11 @@ def run_units(fn, unit_ids, *args, group=None, gather=False, sort_descending=Tru
             break
         mine[_key(ids[i])] = fn(ids[i], *args, **kwargs)
     dist.barrier(group)
+    if dist.get_rank(group) == 0:
+        try:
+            store.delete_key(key)      # every member has drawn its last index: the counter is garbage
+        except (RuntimeError, NotImplementedError):
+            pass                       # (a store without delete support keeps the few bytes)
     if not gather:
         return mine
     parts = [None] * dist.get_world_size(group)
@@ -45,10 +50,13 @@ _calls = {}
 
 
 def _call_index(store, group):
-    """every rank makes the same sequence of run_units calls, so a per-process call count names the shared counter"""
-    k = id(group) if group is not None else 0
-    _calls[k] = _calls.get(k, 0) + 1
-    return f"{k and 'g'}{_calls[k]}"
+    """Name of the shared counter of this run_units call: the group's global ranks (identical on all its members, distinct
+    between disjoint groups) + how many run_units calls this process has made on that group (every member makes the
+    same sequence of calls)."""
+    import torch.distributed as dist
+    ranks = tuple(dist.get_process_group_ranks(group)) if group is not None else ("world",)
+    _calls[ranks] = _calls.get(ranks, 0) + 1
+    return "-".join(str(r) for r in ranks) + f"/{_calls[ranks]}"
 
 
 def _key(u):

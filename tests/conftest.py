@@ -13,13 +13,20 @@ def pytest_configure(config):
 
 
 def pytest_sessionstart(session):
-    """A fresh checkout has no libhydrocore.so (built artefacts are git-ignored): build it once, the way
-    __graft_entry__.build() does (nvcc cross-compiles sm_100a without a GPU).  An existing library is never rebuilt here."""
+    """Built artefacts are git-ignored, and a stale libhydrocore.so would silently test yesterday's kernels: run the
+    (incremental) make at every session start -- an up-to-date library costs a fraction of a second; nvcc cross-compiles
+    sm_100a without a GPU.  Without nvcc (a box that only received the built library) an existing .so is used as is."""
+    import shutil
+    import subprocess
     lib = os.path.join(ROOT, "pydrodem_b200", "libhydrocore.so")
-    if not os.path.exists(lib):
-        import subprocess
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "pydrodem_b200", "csrc"), "-j8"],
-                              stdout=subprocess.DEVNULL)
+    if shutil.which("nvcc") is None:
+        if not os.path.exists(lib):
+            print("conftest: nvcc not found and no libhydrocore.so: GPU and ABI tests will fail loudly", file=sys.stderr)
+        return
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "pydrodem_b200", "csrc"), "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-4000:] + r.stderr[-8000:])
+        raise RuntimeError("building libhydrocore.so failed")
 
 
 @pytest.fixture(scope="session")
