@@ -75,6 +75,9 @@ def _tag_values(f, big, entry):
 
 
 def read_raster(path):
+    hit = _WB.snapshot_of(path) if _WB.depth > 0 else None
+    if hit is not None:
+        return hit
     _WB.wait_for(path)
     return _read_raster_now(path)
 
@@ -190,9 +193,10 @@ def _unpredict(b, pred, rows, cols, dtype):
 
 class _WriteBehind:
     """Write-behind for a unit pipeline: inside `with write_behind():` a write_raster() call snapshots the array, creates
-    the (empty) file at once -- os.path.exists() is true from then on -- and hands the encoding + file write to one
-    background thread; read_raster() of such a path waits for its write; leaving the block waits for all of them and
-    re-raises the first failure.  The pipeline's own kernels and numpy work overlap the ~50-120 ms a 3601^2 raster takes
+    the (empty) file at once -- os.path.exists() is true from then on -- and hands the encoding + file write to a small
+    pool of background threads; read_raster() of a path whose write is still queued is served from the snapshot (a copy, with the
+    metadata a read of the finished file would give); leaving the block waits for all writes and re-raises the first
+    failure.  The pipeline's own kernels and numpy work overlap the ~50-120 ms a 3601^2 raster takes
     to reach the page cache.  Off by default: outside the block every write is synchronous."""
 
     def __init__(self):
@@ -205,7 +209,7 @@ class _WriteBehind:
         with self.lock:
             if self.depth == 0:
                 from concurrent.futures import ThreadPoolExecutor
-                self.pool = ThreadPoolExecutor(max_workers=1)
+                self.pool = ThreadPoolExecutor(max_workers=4)
             self.depth += 1
         return self
 
@@ -221,7 +225,7 @@ class _WriteBehind:
 
     def flush(self):
         with self.lock:
-            futs = list(self.pending.values())
+            futs = [e[0] for e in self.pending.values()]
             self.pending.clear()
         err = None
         for f in futs:
@@ -234,9 +238,19 @@ class _WriteBehind:
 
     def wait_for(self, path):
         with self.lock:
-            f = self.pending.pop(os.path.abspath(path), None)
-        if f is not None:
-            f.result()
+            e = self.pending.pop(os.path.abspath(path), None)
+        if e is not None:
+            e[0].result()
+
+    def snapshot_of(self, path):
+        """(array copy, RasterMeta) of a queued write, or None"""
+        with self.lock:
+            e = self.pending.get(os.path.abspath(path))
+        if e is None:
+            return None
+        if e[0].done():
+            e[0].result()          # surfaces a failed write here rather than at the end of the block
+        return e[1].copy(), RasterMeta({"nodata": e[2].get("nodata"), "geo": dict(e[2].get("geo", {}))})
 
 
 _WB = _WriteBehind()
@@ -258,9 +272,15 @@ def write_raster(path, arr, meta=None, nodata=None, compress=None, tiled=False):
             raise ValueError("write_raster needs a 2-D array")
         _WB.wait_for(path)                       # an earlier queued write of the same path goes first
         open(path, "wb").close()
+        m = RasterMeta(meta or {})
+        seen = {"nodata": float(nodata) if nodata is not None else m.get("nodata"),
+                "geo": {int(t): (int(v[0]), tuple(v[1]) if not isinstance(v[1], str) else v[1])
+                        for t, v in m.get("geo", {}).items() if int(t) in _GEO_TAGS}}
+        if snap.dtype.byteorder == ">":
+            snap = snap.astype(snap.dtype.newbyteorder("<"))
         fut = _WB.pool.submit(_write_raster_now, path, snap, meta, nodata, compress, tiled)
         with _WB.lock:
-            _WB.pending[os.path.abspath(path)] = fut
+            _WB.pending[os.path.abspath(path)] = (fut, snap, seen)
         return
     _write_raster_now(path, arr, meta, nodata, compress, tiled)
 
@@ -358,7 +378,7 @@ def _write_raster_now(path, arr, meta=None, nodata=None, compress=None, tiled=Fa
         else:
             f.write(b"II" + struct.pack("<HI", 42, ifd_off))
         if blobs is None:
-            f.write(arr.tobytes() if arr.nbytes < (1 << 30) else memoryview(arr).cast("B"))
+            f.write(memoryview(arr).cast("B"))
         else:
             for b in blobs:
                 f.write(b)

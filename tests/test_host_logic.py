@@ -190,3 +190,19 @@ def test_clipbuffer_arr_matches_the_reference_semantics():
     assert np.array_equal(stencils.clipbuffer_arr(a, 2, set_nodata=-9999), np.where(mask == 1, a, -9999))
     u = np.arange(56, dtype=np.uint8).reshape(7, 8)
     assert np.array_equal(stencils.clipbuffer_arr(u, 1, set_nodata=99)[0], np.full(8, 99, np.uint8)) and u[0, 0] == 0
+
+
+def test_unit_discovery_helpers(tmp_path):
+    """tools/log.py: which `<unit>_<id>` directories exist / are unfinished (reference tools/log.py:66-106, 189-195)"""
+    import os
+    from pydrodem_b200.tools import log as logt
+    for name in ("basin_6010", "basin_6020", "tile_N10E020", "notes"):
+        os.makedirs(tmp_path / name)
+    open(tmp_path / "basin_6010" / "DEMcompleted.txt", "w").close()
+    open(tmp_path / "basin_stray.txt", "w").close()
+    assert logt.find_all_ids(str(tmp_path), unit="basin", dir_search="basin_") == [6010, 6020]
+    assert logt.find_unfinished_ids(str(tmp_path), unit="basin", dir_search="basin_", tifname="DEMcompleted.txt") == [6020]
+    assert logt.find_all_ids(str(tmp_path), unit="tile", dir_search="tile_") == ["N10E020"]
+    assert logt.find_all_basins_IDs(str(tmp_path)) == [6010, 6020]
+    import time
+    assert logt.log_time("X", time.time() - 3725).startswith("X COMPLETE -- elapsed 01:02:0")
