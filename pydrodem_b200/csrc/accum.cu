@@ -75,11 +75,14 @@ template <int TABLE>
 __global__ void __launch_bounds__(NTHREADS)
 k_acc_tile_local(const uint8_t *__restrict__ dir, u64 *__restrict__ pstate, unsigned short *__restrict__ pexit,
                  u32 *__restrict__ pdown, u32 *__restrict__ pinflow, uint32_t *__restrict__ acc, int ny, int nx,
-                 hc_rows rw) {
+                 hc_rows rw, const uint8_t *__restrict__ tile_class, int only_class) {
   __shared__ uint8_t sd[TH * TH];
   __shared__ u32 st[T * T];
 
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  // (the whole-raster chain runs the tiles without pending flat cells while the flats' slow tier is still relaxing,
+  //  and the other tiles afterwards: tile_class = the flat pass's per-tile "pending" flag)
+  if (tile_class && (int)tile_class[tile] != only_class) return;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int hr = min(T, ny - r0), hc = min(T, nx - c0);
   const int tid = threadIdx.x;
@@ -363,7 +366,7 @@ static int accum_local_impl(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int6
   dim3 tg(tx, ty);
   unsigned sb = (unsigned)((nslots + 255) / 256);
   HC_PROF(ctx, st, "k_acc_tile_local");
-  k_acc_tile_local<TABLE><<<tg, NTHREADS, 0, st>>>(dir, pstate, pexit, pdown, pinflow, acc, (int)ny, (int)nx, rw);
+  k_acc_tile_local<TABLE><<<tg, NTHREADS, 0, st>>>(dir, pstate, pexit, pdown, pinflow, acc, (int)ny, (int)nx, rw, nullptr, 0);
   HC_LAUNCH_CHECK(ctx);
   HC_PROF(ctx, st, "k_acc_link_count");
   k_acc_link_count<<<sb, 256, 0, st>>>(pstate, pexit, pdown, nslots);
@@ -387,6 +390,56 @@ static int accum_final_impl(hc_ctx *ctx, uint32_t *acc, hc_rows rw, cudaStream_t
   k_acc_tile_final<TABLE><<<tg, NTHREADS, 0, st>>>(bs->dir, bs->pinflow, acc, (int)ny, (int)nx);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
+}
+
+// ---- split form for the whole-raster chain (fill.cu fill_d8_flats_accum_run): phase A per tile class on any stream,
+// ---- then links + phase C.  No arena_reset: the workspace is taken from the current arena generation.
+template <int TABLE>
+static int accum_tiles_impl(hc_ctx *ctx, const uint8_t *tile_class, int only_class, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  const int64_t ny = bs->nb, nx = bs->nx;
+  dim3 tg((unsigned)((nx + T - 1) / T), (unsigned)((ny + T - 1) / T));
+  HC_PROF(ctx, st, "k_acc_tile_local");
+  k_acc_tile_local<TABLE><<<tg, NTHREADS, 0, st>>>(bs->dir, bs->pstate, bs->pexit, bs->pdown, bs->pinflow, bs->acc_out, (int)ny,
+                                                   (int)nx, hc_make_rows(ny, 0), tile_class, only_class);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+int accum_split_prepare(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_t nx) {
+  hc_band_state *bs = &ctx->band;
+  const size_t nslots = (size_t)((nx + T - 1) / T) * ((ny + T - 1) / T) * PSLOTS;
+  bs->pstate = (u64 *)arena_take(ctx, nslots * 8);
+  bs->pexit = (unsigned short *)arena_take(ctx, nslots * 2);
+  bs->pdown = (u32 *)arena_take(ctx, nslots * 4);
+  bs->pinflow = (u32 *)arena_take(ctx, nslots * 4);
+  bs->bout = (u32 *)arena_take(ctx, (size_t)2 * nx * 4);
+  if (!bs->pstate || !bs->pexit || !bs->pdown || !bs->pinflow || !bs->bout) return HC_ERR_NOMEM;
+  bs->dir = dir; bs->nb = ny; bs->nx = nx; bs->acc_out = acc;
+  return HC_OK;
+}
+
+int accum_split_tiles(hc_ctx *ctx, int table, const uint8_t *tile_class, int only_class, cudaStream_t st) {
+  return table == HC_TABLE_WBT ? accum_tiles_impl<HC_TABLE_WBT>(ctx, tile_class, only_class, st)
+                               : accum_tiles_impl<HC_TABLE_TAUDEM>(ctx, tile_class, only_class, st);
+}
+
+int accum_split_finish(hc_ctx *ctx, int table, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  const size_t nslots = (size_t)((bs->nx + T - 1) / T) * ((bs->nb + T - 1) / T) * PSLOTS;
+  unsigned sb = (unsigned)((nslots + 255) / 256);
+  HC_PROF(ctx, st, "k_acc_link_count");
+  k_acc_link_count<<<sb, 256, 0, st>>>(bs->pstate, bs->pexit, bs->pdown, nslots);
+  HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_acc_link_mark");
+  k_acc_link_mark<<<sb, 256, 0, st>>>(bs->pstate, bs->pdown, nslots);
+  HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_acc_link_walk");
+  k_acc_link_walk<<<sb, 256, 0, st>>>(bs->pstate, bs->pexit, bs->pdown, bs->pinflow, nslots, bs->bout, (int)bs->nx);
+  HC_LAUNCH_CHECK(ctx);
+  hc_rows rw = hc_make_rows(bs->nb, 0);
+  return table == HC_TABLE_WBT ? accum_final_impl<HC_TABLE_WBT>(ctx, bs->acc_out, rw, st)
+                               : accum_final_impl<HC_TABLE_TAUDEM>(ctx, bs->acc_out, rw, st);
 }
 
 int accum_run(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_t nx, int table,

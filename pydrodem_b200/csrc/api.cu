@@ -211,9 +211,16 @@ extern "C" int hc_create(hc_ctx **out, int device) {
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_acc, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[0], cudaEventDisableTiming));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[1], cudaEventDisableTiming));
-  HC_CUDA(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+  // the flat pass's slow tier runs latency-bound rounds beside full-grid work of the chain: its streams get the highest
+  // priority so that their (few) CTAs are scheduled ahead of the queued CTAs of the big kernel
+  int prio_least = 0, prio_greatest = 0;
+  HC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  HC_CUDA(cudaStreamCreateWithPriority(&ctx->s_aux, cudaStreamNonBlocking, prio_greatest));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  HC_CUDA(cudaStreamCreateWithPriority(&ctx->s_aux2, cudaStreamNonBlocking, prio_greatest));
+  HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
+  HC_CUDA(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
   *out = ctx;
   return HC_OK;
 }
@@ -234,6 +241,9 @@ extern "C" int hc_destroy(hc_ctx *ctx) {
   if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->s_aux2) cudaStreamDestroy(ctx->s_aux2);
+  if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+  if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
   pthread_mutex_destroy(&ctx->mu);
   free(ctx);
   return HC_OK;
@@ -304,8 +314,7 @@ extern "C" int hc_fill_d8_accum_dev(hc_ctx *ctx, const float *z, float *filled, 
   if (ny && nx && (!z || !filled || !dir || !acc)) { hc_set_error("hc_fill_d8_accum: null pointer"); return HC_ERR_ARG; }
   if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("bad seed_mode"); return HC_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  HC_TRY(fill_d8_flats_run(ctx, z, filled, dir, slope, ny, nx, nodata, dx, dy, seed_mode, table, resolve_flats, st));
-  HC_TRY(accum_run(ctx, dir, acc, ny, nx, table, st));
+  HC_TRY(fill_d8_flats_accum_run(ctx, z, filled, dir, slope, acc, ny, nx, nodata, dx, dy, seed_mode, table, resolve_flats, st));
   return HC_OK;
 }
 
@@ -341,10 +350,9 @@ extern "C" int hc_fill_d8_accum_ld_dev(hc_ctx *ctx, float *z, float *filled, uin
     HC_LAUNCH_CHECK(ctx);
   }
   ctx->pad_from = ld > nx ? (int)nx : 0;   // (the WBT seed rule's exterior-nodata search need not label the padding)
-  int rc = fill_d8_flats_run(ctx, z, filled, dir, slope, ny, ld, nodata, dx, dy, seed_mode, table, resolve_flats, st);
+  int rc = fill_d8_flats_accum_run(ctx, z, filled, dir, slope, acc, ny, ld, nodata, dx, dy, seed_mode, table, resolve_flats, st);
   ctx->pad_from = 0;
   HC_TRY(rc);
-  HC_TRY(accum_run(ctx, dir, acc, ny, ld, table, st));
   return HC_OK;
 }
 
@@ -436,8 +444,8 @@ extern "C" int hc_fill_d8_accum_host_begin(hc_ctx *ctx, int slot, const float *z
     HC_LAUNCH_CHECK(ctx);
   }
   ctx->pad_from = ld > nx ? (int)nx : 0;
-  int rc = fill_d8_flats_run(ctx, (const float *)dz.p, (float *)df.p, (uint8_t *)dd.p, (float *)ds.p, ny, ld, nodata, dx, dy,
-                             seed_mode, table, resolve_flats, sc);
+  int rc = fill_d8_flats_accum_run(ctx, (const float *)dz.p, (float *)df.p, (uint8_t *)dd.p, (float *)ds.p, (uint32_t *)da.p, ny, ld,
+                                   nodata, dx, dy, seed_mode, table, resolve_flats, sc);
   ctx->pad_from = 0;
   HC_TRY(rc);
   HC_CUDA(cudaEventRecord(ctx->ev_dir, sc));
@@ -445,7 +453,6 @@ extern "C" int hc_fill_d8_accum_host_begin(hc_ctx *ctx, int slot, const float *z
   HC_CUDA(cudaMemcpy2DAsync(filled, (size_t)nx * 4, df.p, (size_t)ld * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost, sx));
   HC_CUDA(cudaMemcpy2DAsync(dir, (size_t)nx, dd.p, (size_t)ld, (size_t)nx, (size_t)ny, cudaMemcpyDeviceToHost, sx));
   if (slope) HC_CUDA(cudaMemcpy2DAsync(slope, (size_t)nx * 4, ds.p, (size_t)ld * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost, sx));
-  HC_TRY(accum_run(ctx, (const uint8_t *)dd.p, (uint32_t *)da.p, ny, ld, table, sc));
   HC_CUDA(cudaEventRecord(ctx->ev_acc, sc));
   HC_CUDA(cudaStreamWaitEvent(sx, ctx->ev_acc, 0));
   HC_CUDA(cudaMemcpy2DAsync(acc, (size_t)nx * 4, da.p, (size_t)ld * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost, sx));

@@ -70,7 +70,7 @@ struct hc_band_state {
   uint8_t *pending, *active, *nf, *visited, *tmask; u32 *dlo, *dhi, *flag, *tcount; unsigned short *tlist; int n_pending;
   u32 *qA, *qB, *queued;   // dirty-tile queues of the slow tier (current / next) and the per-tile "already queued" marks
   // accumulation
-  int acc_ready; const uint8_t *dir; unsigned long long *pstate; unsigned short *pexit; u32 *pdown, *pinflow, *bout, *acc_err;
+  int acc_ready; uint32_t *acc_out; const uint8_t *dir; unsigned long long *pstate; unsigned short *pexit; u32 *pdown, *pinflow, *bout, *acc_err;
 };
 
 // banded labelling: state between the phases (pointers into the arena)
@@ -97,6 +97,7 @@ struct hc_ctx {
   // stats of the last fill
   int64_t fill_basins;
   int32_t fill_rounds;
+  uint32_t *chain_acc;   // accumulation raster of the running hc_fill_d8_accum_* chain (fill_d8_flats_accum_run)
   int pad_from;   // > 0: columns >= pad_from are the nodata padding of a pitched raster (hc_fill_d8_accum_ld_dev)
   // band diagnostics: terminal-graph edges emitted, MSF rounds, global seam-graph rounds
   int64_t band_term_edges;
@@ -113,6 +114,9 @@ struct hc_ctx {
   // auxiliary stream of the flat pass (light and window relaxation kernels run side by side)
   cudaStream_t s_aux;
   cudaEvent_t ev_fork, ev_join;
+  // second auxiliary stream: accumulation of the tiles without pending flats beside the flats' slow tier
+  cudaStream_t s_aux2;
+  cudaEvent_t ev_fork2, ev_join2;
   unsigned long long *d_dbg;  // 16 device work counters
   // per-kernel event timing (off by default)
   int prof_on, prof_open;
@@ -175,6 +179,9 @@ __device__ __forceinline__ int d_code_to_k(int table, int code) {
 int fill_run(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata, int seed_mode,
              cudaStream_t st);
 size_t fill_workspace(int64_t ny, int64_t nx);
+int fill_d8_flats_accum_run(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope, uint32_t *acc, int64_t ny,
+                            int64_t nx, float nodata, double dx, double dy, int seed_mode, int table, int resolve_flats,
+                            cudaStream_t st);
 int fill_d8_flats_run(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope, int64_t ny, int64_t nx,
                       float nodata, double dx, double dy, int seed_mode, int table, int resolve_flats, cudaStream_t st);
 // exterior-nodata raster of the WBT seed rule (label.cu); ext comes from the arena, no arena_reset inside
@@ -190,6 +197,13 @@ int d8_flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, float *slope, int64_
 int accum_run(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_t nx, int table,
               cudaStream_t st);
 size_t accum_workspace(int64_t ny, int64_t nx);
+int accum_split_prepare(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t ny, int64_t nx);
+int accum_split_tiles(hc_ctx *ctx, int table, const uint8_t *tile_class, int only_class, cudaStream_t st);
+int accum_split_finish(hc_ctx *ctx, int table, cudaStream_t st);
+// flat pass in two halves (whole raster): fast tier, then the slow tier for what it left pending
+int flats_whole_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx, float nodata,
+                      int table, cudaStream_t st, const uint8_t **tile_pending, int *n_pending);
+int flats_whole_finish(hc_ctx *ctx, cudaStream_t st);
 int label_run(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn, int32_t *nlab,
               cudaStream_t st);
 size_t label_workspace(int64_t ny, int64_t nx);

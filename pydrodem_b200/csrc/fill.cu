@@ -1340,7 +1340,42 @@ int fill_d8_flats_run(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, 
     else HC_TRY((apply_d8_launch<HC_TABLE_TAUDEM, false>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st)));
   }
   if (!resolve_flats) return HC_OK;
-  return flats_core(ctx, filled, dirA, dir, ny, nx, nodata, table, st);
+  if (resolve_flats != 2) return flats_core(ctx, filled, dirA, dir, ny, nx, nodata, table, st);
+  // chain form: flats in two halves with the accumulation's tile phase split around the slow tier
+  const uint8_t *tile_pending = nullptr;
+  int n_pending = 0;
+  HC_TRY(flats_whole_begin(ctx, filled, dirA, dir, ny, nx, nodata, table, st, &tile_pending, &n_pending));
+  HC_TRY(accum_split_prepare(ctx, dir, ctx->chain_acc, ny, nx));
+  if (!n_pending) {
+    HC_TRY(accum_split_tiles(ctx, table, nullptr, 0, st));
+    return accum_split_finish(ctx, table, st);
+  }
+  // the tile phase of the settled tiles is queued first, on the caller's stream; the slow tier follows on the context's
+  // HIGH-PRIORITY stream, so its small kernels overtake the queued CTAs of the big one instead of waiting behind them
+  HC_CUDA(cudaEventRecord(ctx->ev_fork2, st));
+  HC_CUDA(cudaStreamWaitEvent(ctx->s_aux2, ctx->ev_fork2, 0));
+  HC_TRY(accum_split_tiles(ctx, table, tile_pending, 0, st));
+  HC_TRY(flats_whole_finish(ctx, ctx->s_aux2));
+  HC_CUDA(cudaEventRecord(ctx->ev_join2, ctx->s_aux2));
+  HC_CUDA(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+  HC_TRY(accum_split_tiles(ctx, table, tile_pending, 1, st));
+  return accum_split_finish(ctx, table, st);
+}
+
+// The whole chain (hc_fill_d8_accum_*): as above, but the accumulation's tile-local phase of every tile WITHOUT pending
+// flat cells (84 % of the tiles on the C2 recipe) runs on a second stream beside the flats' slow tier -- whose rounds are
+// latency bound and leave most SMs idle -- and only the remaining tiles wait for the final directions.  A pending cell
+// holds code 254 until then, which the tile-local phase of a neighbouring tile reads only as "not nodata".
+int fill_d8_flats_accum_run(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope, uint32_t *acc, int64_t ny,
+                            int64_t nx, float nodata, double dx, double dy, int seed_mode, int table, int resolve_flats,
+                            cudaStream_t st) {
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!resolve_flats || getenv("HC_NO_ACC_OVERLAP")) {
+    HC_TRY(fill_d8_flats_run(ctx, z, filled, dir, slope, ny, nx, nodata, dx, dy, seed_mode, table, resolve_flats, st));
+    return accum_run(ctx, dir, acc, ny, nx, table, st);
+  }
+  ctx->chain_acc = acc;
+  return fill_d8_flats_run(ctx, z, filled, dir, slope, ny, nx, nodata, dx, dy, seed_mode, table, 2, st);
 }
 
 // =============================================================================================

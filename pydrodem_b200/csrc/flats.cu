@@ -1121,6 +1121,22 @@ int flats_core(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, 
   return flats_dirs(ctx, rw, st);
 }
 
+int flats_whole_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx, float nodata,
+                      int table, cudaStream_t st, const uint8_t **tile_pending, int *n_pending) {
+  HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, ny, nx, nodata, table, hc_make_rows(ny, 0), st));
+  *tile_pending = ctx->band.pending;
+  *n_pending = ctx->band.n_pending;
+  return HC_OK;
+}
+
+int flats_whole_finish(hc_ctx *ctx, cudaStream_t st) {
+  hc_rows rw = hc_make_rows(ctx->band.nb, 0);
+  if (!ctx->band.n_pending) return HC_OK;
+  HC_TRY(flats_slow_init(ctx, rw, st));
+  HC_TRY(flats_relax_loop(ctx, rw, st));
+  return flats_dirs(ctx, rw, st);
+}
+
 // in-place public form: dir is copied aside first
 int flats_run(hc_ctx *ctx, const float *z, uint8_t *dir, int64_t ny, int64_t nx, float nodata, int table,
               cudaStream_t st) {
