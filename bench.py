@@ -41,7 +41,7 @@ BYTES_PER_CELL = {"fill": 8, "d8": 5, "flats": 0, "accum": 5}  # SURVEY.md §8(d
 KERNEL_PASS = {
     "k_ptr": "fill", "k_perim": "fill", "k_flatten": "fill", "k_minedge": "fill", "k_tab_init": "fill",
     "k_hook": "fill", "k_mutual": "fill", "k_jump": "fill", "k_merge": "fill", "k_repflat": "fill",
-    "k_levels": "fill", "k_apply": "fill", "k_nodata_mask": "fill", "k_lab_init": "fill", "k_lab_merge": "fill",
+    "k_levels": "fill", "k_apply": "fill", "k_nodata_mask": "fill", "k_lab_tile": "label", "k_lab_border": "label",
     "k_lab_compress": "fill", "k_ext_flag_border": "fill", "k_ext_out": "fill",
     "k_d8": "d8", "k_flat_init": "flats", "k_flat_relax": "flats", "k_flat_dirs": "flats",
     "k_acc_init": "accum", "k_acc_walk": "accum", "k_acc_out": "accum",
@@ -594,6 +594,66 @@ def run_c1(args, world, rank, local, dev):
     return 0
 
 
+def run_label(args, world, rank, local, dev):
+    """Connected-component labelling (scipy.ndimage.label's numbering; dep.create_clump_array, tools/depressions.py:
+    1646-1669) on a 10801^2 random mask at the 8-connected site-percolation threshold (p = 0.407: components of every size
+    up to raster-spanning ones).  Algorithmic bytes: 1 (mask in) + 4 (int32 labels out) = 5 B/cell."""
+    import torch
+    import pydrodem_b200 as hc
+    from pydrodem_b200 import _lib
+    n = args.size
+    g = torch.Generator(device=dev).manual_seed(4077 + rank)
+    mask = (torch.rand((n, n), device=dev, generator=g) < 0.407).to(torch.uint8)
+    for _ in range(args.warmup):
+        lab, nlab = hc.label(mask, 8)
+    torch.cuda.synchronize()
+    _lib.profile_enable(True, local)
+    launches0 = _lib.launch_count(local)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lab, nlab = hc.label(mask, 8)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = _lib.launch_count(local) - launches0
+    prof = _lib.profile_read(local)
+    _lib.profile_enable(False, local)
+    peak, peak_src = peaks()
+    cells = n * n
+    kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t_ / args.steps} for k, (c, t_, m) in
+               sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    name, (cnt, tot, mx) = max(prof.items(), key=lambda kv: kv[1][1])
+    per_launch_bytes = {"k_lab_tile": 5, "k_lab_compress": 8, "k_lab_out": 12, "k_root_rank": 8, "k_root_count": 4, "k_lab_border": 5}
+    b = per_launch_bytes.get(name, 5) * cells
+    roof = {"bound": "hbm", "kernel": name, "pass": "label", "achieved": b / (tot / cnt * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": b / (tot / cnt * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "avg_launch_ms": tot / cnt,
+            "algorithmic_bytes_per_launch": b, "launches_per_step": cnt / args.steps}
+    line = {"metric": "Mcells/s connected-component labelling", "value": cells / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8->i32", "data": "synthetic",
+            "config": {"workload": f"label: {n}x{n} uint8 random mask, density 0.407 (8-connected site-percolation threshold), "
+                                   "8-connectivity, scipy.ndimage.label numbering", "components": int(nlab),
+                       "algorithmic_bytes_per_cell": 5},
+            "roofline": roof, "cpu_baseline": None, "e2e": None, "gpu_launches": launches // args.steps, "clocks": clocks,
+            "hbm_frac_algorithmic_whole_step": 5 * cells / (ms * 1e-3) / 1e9 / peak, "kernels": kernels}
+    if args.cpu_sample > 0:
+        from scipy import ndimage
+        import numpy as np
+        s_ = min(3000, n)
+        crop = mask[:s_, :s_].cpu().numpy()
+        t0 = time.perf_counter()
+        ndimage.label(crop, structure=np.ones((3, 3)))
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": crop.size / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "reference", "seconds": dt,
+                                "sample": f"scipy.ndimage.label (the reference's own call) on the top-left {s_}x{s_} crop"}
+    print(json.dumps(line))
+    return 0
+
+
 def run_c5(args, world, rank, local, dev):
     """BASELINE.json configs[4]: dem_noise_removal smoothing core (4 DW smoothings 9/7/5/3, slope_D4 + curvature_D2 of
     the 5x5 result, global sigma, filter selection, final slope; models/dem_noise_removal.py:397-476) on a 20000^2 DEM,
@@ -698,7 +758,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=5400, help="edge of the crop timed on the CPU (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flats", type=int, default=1)
-    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "bands", "c3", "c4", "c5"],
+    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "bands", "c3", "c4", "c5", "label"],
                     help="auto: c2 (one 10801^2 DEM) at N=1; at N>1 c3 (the 40000^2 DEM row-band-sharded over the N GPUs, "
                          "strong scaling) as the headline with the weak-scaling bands run (one 10801 x 10801*N DEM, a band "
                          "per GPU) reported inside the same line; c1: the per-unit depression pipeline on 3601^2")
@@ -742,6 +802,8 @@ def main():
         return run_banded(args, world, rank, local, dev)
     if args.workload == "c1":
         return run_c1(args, world, rank, local, dev)
+    if args.workload == "label":
+        return run_label(args, world, rank, local, dev)
     if args.workload == "c5":
         return run_c5(args, world, rank, local, dev)
 

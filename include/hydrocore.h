@@ -246,6 +246,9 @@ int hc_band_flats_begin_dev(hc_ctx *ctx, const float *z, const uint8_t *dirA, ui
                             int64_t nx, float nodata, int table, int flags, void *stream);
 int hc_band_flats_get_seams_dev(hc_ctx *ctx, uint32_t *out, void *stream);
 int hc_band_flats_put_halos_dev(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int *changed, void *stream);
+/* Same, without any read-back: `flag_dev` (device int32) is set to 1 when a halo row changed (never cleared here), and the
+ * seam tile rows are re-queued on the device.  The caller all-reduces the ranks' flag words once per exchange round. */
+int hc_band_flats_put_halos_flag_dev(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int32_t *flag_dev, void *stream);
 int hc_band_flats_relax_dev(hc_ctx *ctx, void *stream);
 int hc_band_flats_finish_dev(hc_ctx *ctx, void *stream);
 /* accumulation: local writes the band-local counts into acc and publishes uint32

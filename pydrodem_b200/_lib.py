@@ -86,6 +86,7 @@ SIGNATURES = {
                                                c_vp]),
     "hc_band_flats_get_seams_dev": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "hc_band_flats_put_halos_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(ctypes.c_int), c_vp]),
+    "hc_band_flats_put_halos_flag_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hc_band_flats_relax_dev": (ctypes.c_int, [c_vp, c_vp]),
     "hc_band_flats_finish_dev": (ctypes.c_int, [c_vp, c_vp]),
     "hc_band_accum_local_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),

@@ -108,6 +108,7 @@ class BandedChain:
         self.edges = torch.zeros((nl, self.cap, 3), dtype=i32, device=self.device)
         self.fseam = torch.zeros((nl, 2, 3, self.nx), dtype=i32, device=self.device)
         self.aseam = torch.zeros((nl, 2, 2, self.nx), dtype=i32, device=self.device)
+        self.fchanged = torch.zeros(1, dtype=i32, device=self.device)
         self.flat_rounds = 0
         self.timing = False      # set True to collect per-phase device times of run() in self.phase_ms
         self.phase_ms = {}
@@ -259,16 +260,19 @@ class BandedChain:
                         self._chk(lib.hc_band_flats_get_seams_dev(self.ctx[i], ctypes.c_void_p(self.fseam[i].data_ptr()), st),
                                   "hc_band_flats_get_seams_dev")
                     allf = self.comm.gather(self.fseam)
-                    changed = False
+                    # halo rows in, seam tile rows re-queued, "something changed" accumulated -- all on the device; the
+                    # ranks then agree on convergence with ONE all_reduce + read-back per round
+                    self.fchanged.zero_()
                     for i in range(nl):
                         g = self.first + i
                         top = ctypes.c_void_p(allf[g - 1, 1].data_ptr()) if g > 0 else None
                         bot = ctypes.c_void_p(allf[g + 1, 0].data_ptr()) if g < self.nbands - 1 else None
-                        ch = ctypes.c_int(0)
-                        self._chk(lib.hc_band_flats_put_halos_dev(self.ctx[i], top, bot, ctypes.byref(ch), st),
-                                  "hc_band_flats_put_halos_dev")
-                        changed = changed or bool(ch.value)
-                    changed = self.comm.any(changed, self.device)
+                        self._chk(lib.hc_band_flats_put_halos_flag_dev(self.ctx[i], top, bot,
+                                                                       ctypes.c_void_p(self.fchanged.data_ptr()), st),
+                                  "hc_band_flats_put_halos_flag_dev")
+                    if self.comm.world > 1:
+                        self.comm.dist.all_reduce(self.fchanged, op=self.comm.dist.ReduceOp.MAX, group=self.comm.group)
+                    changed = bool(self.fchanged.item())
                     if not first and not changed:
                         break
                     first = False

@@ -55,6 +55,11 @@ extern "C" int hc_band_flats_put_halos_dev(hc_ctx *ctx, const uint32_t *top, con
   CHECK_CTX(ctx);
   return band_flats_put_halos(ctx, top, bot, changed, (cudaStream_t)stream);
 }
+extern "C" int hc_band_flats_put_halos_flag_dev(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int32_t *flag_dev, void *stream) {
+  CHECK_CTX(ctx);
+  if (!flag_dev) { hc_set_error("hc_band_flats_put_halos_flag: null flag"); return HC_ERR_ARG; }
+  return band_flats_put_halos_flag(ctx, top, bot, (int *)flag_dev, (cudaStream_t)stream);
+}
 extern "C" int hc_band_flats_relax_dev(hc_ctx *ctx, void *stream) {
   CHECK_CTX(ctx);
   return band_flats_relax(ctx, (cudaStream_t)stream);

@@ -218,6 +218,7 @@ int band_flats_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *
                      float nodata, int table, int flags, cudaStream_t st);
 int band_flats_get_seams(hc_ctx *ctx, uint32_t *out, cudaStream_t st);
 int band_flats_put_halos(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int *changed, cudaStream_t st);
+int band_flats_put_halos_flag(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int *flag_dev, cudaStream_t st);
 int band_flats_relax(hc_ctx *ctx, cudaStream_t st);
 int band_flats_finish(hc_ctx *ctx, cudaStream_t st);
 int band_accum_local(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t nb, int64_t nx, int table, int flags,

@@ -1249,6 +1249,43 @@ int band_flats_put_halos(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, 
   return HC_OK;
 }
 
+// device-flag form of put_halos: nothing is read back.  `flag_dev[0]` is OR-ed with "some halo row changed"; the seam tile
+// rows are re-queued by a kernel that looks at the change flags itself, so the host learns about convergence from ONE
+// all_reduce of the ranks' flag words per exchange round instead of a read-back per band plus that all_reduce.
+__global__ void k_flat_queue_tiles_if(const uint8_t *__restrict__ active, u32 first, u32 count, u32 *queued, u32 *list, u32 *n,
+                                      const u32 *__restrict__ changed, int *__restrict__ flag_out) {
+  if (!*changed) return;
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && flag_out) *flag_out = 1;
+  if (i >= count) return;
+  u32 t = first + i;
+  if (active[t] && atomicExch(&queued[t], 1u) == 0u) list[atomicAdd(n, 1u)] = t;
+}
+
+int band_flats_put_halos_flag(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, int *flag_dev, cudaStream_t st) {
+  hc_band_state *bs = &ctx->band;
+  if (!bs->flats_ready) { hc_set_error("band flats: begin first"); return HC_ERR_ARG; }
+  const int64_t ny = bs->nb, nx = bs->nx;
+  const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
+  HC_CUDA(cudaMemsetAsync(bs->flag + 2, 0, 8, st));
+  unsigned gb = (unsigned)((nx + 255) / 256), gt = (unsigned)((tx + 255) / 256);
+  if (top && (bs->flags & 1)) {
+    HC_PROF(ctx, st, "k_flat_put_halo");
+    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, -1ll, (int)nx, top, bs->flag + 2);
+    HC_LAUNCH_CHECK(ctx);
+    k_flat_queue_tiles_if<<<gt, 256, 0, st>>>(bs->active, 0u, (u32)tx, bs->queued, bs->qA, bs->flag + 8, bs->flag + 2, flag_dev);
+    HC_LAUNCH_CHECK(ctx);
+  }
+  if (bot && (bs->flags & 2)) {
+    HC_PROF(ctx, st, "k_flat_put_halo");
+    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, (long long)ny, (int)nx, bot, bs->flag + 3);
+    HC_LAUNCH_CHECK(ctx);
+    k_flat_queue_tiles_if<<<gt, 256, 0, st>>>(bs->active, (u32)((ty - 1) * tx), (u32)tx, bs->queued, bs->qA, bs->flag + 8, bs->flag + 3, flag_dev);
+    HC_LAUNCH_CHECK(ctx);
+  }
+  return HC_OK;
+}
+
 int band_flats_relax(hc_ctx *ctx, cudaStream_t st) {
   hc_band_state *bs = &ctx->band;
   if (!bs->flats_ready) { hc_set_error("band flats: begin first"); return HC_ERR_ARG; }

@@ -5,8 +5,11 @@
 // and endo.find_sink (tools/endo.py:323): 8- or 4-connectivity, ids 1..n in raster-scan order of
 // each component's first cell.
 //
-// Union-find on the pixel grid (each cell links to the smaller root, so a component's root is its
-// first cell in raster order), then the roots are ranked by a three-kernel exclusive scan.
+// Block-based union-find (each cell links to the smaller root, so a component's root is its first cell in
+// raster order): k_lab_tile merges every 64 x 64 tile in SHARED memory (16-bit-local ids, shared atomicMin, a
+// cell looks at W / N and only at the diagonals its row neighbours do not already cover) and writes each
+// cell's tile-local root as a global index; k_lab_border then unions across tile borders (3 % of the cells) in
+// global memory, k_lab_compress flattens.  The roots are ranked by a three-kernel exclusive scan.
 #include "common.cuh"
 
 __device__ __forceinline__ u32 uf_find(volatile u32 *L, u32 i) {
@@ -28,20 +31,139 @@ __device__ __forceinline__ void uf_union(u32 *L, u32 a, u32 b) {
   }
 }
 
-__global__ void __launch_bounds__(256)
-k_lab_init(const uint8_t *__restrict__ mask, u32 *__restrict__ L, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) L[i] = mask[i] ? (u32)i : HC_NONE;
+#define LT 64   // labelling tile edge
+
+__device__ __forceinline__ u32 suf_find(volatile u32 *L, u32 i) {
+  u32 p = L[i];
+  while (p != i) { i = p; p = L[i]; }
+  return i;
+}
+__device__ __forceinline__ void suf_union(u32 *L, u32 a, u32 b) {
+  volatile u32 *VL = L;
+  for (;;) {
+    a = suf_find(VL, a);
+    b = suf_find(VL, b);
+    if (a == b) return;
+    if (a < b) { u32 t = a; a = b; b = t; }
+    u32 old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// Tile-local components in shared memory; L[g] = global index of the cell's tile-local root (HC_NONE off the mask).
+// Horizontal connectivity needs no union at all: a row of the tile is one 64-bit word, and a cell's run start comes
+// out of a count-leading-ones on that word.  Union-find then works on RUN STARTS only, with one union per pair of
+// touching runs in consecutive rows (a cell asks for a union only where a new upper run begins), finds halve paths.
+__device__ __forceinline__ u32 suf_find_h(u32 *L, u32 i) {
+  volatile u32 *VL = L;
+  u32 p = VL[i];
+  while (p != i) {
+    const u32 gp = VL[p];
+    if (gp != p) VL[i] = gp;   // path halving (a plain store of an ancestor: links only ever move towards the root)
+    i = p;
+    p = gp;
+  }
+  return i;
+}
+__device__ __forceinline__ void suf_union_h(u32 *L, u32 a, u32 b) {
+  for (;;) {
+    a = suf_find_h(L, a);
+    b = suf_find_h(L, b);
+    if (a == b) return;
+    if (a < b) { u32 t = a; a = b; b = t; }
+    u32 old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+// start column of the run of ones that contains bit c of `bits`
+__device__ __forceinline__ int run_start(unsigned long long bits, int c) {
+  const unsigned long long upto = bits << (63 - c);          // bit c moved to bit 63
+  return c - __clzll((long long)~upto) + 1;                    // ones ending at c: leading ones of upto
 }
 
 __global__ void __launch_bounds__(256)
-k_lab_merge(const uint8_t *__restrict__ mask, u32 *L, int ny, int nx, int conn8) {
-  size_t n = (size_t)ny * nx;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !mask[i]) return;
-  int r = (int)(i / (size_t)nx), c = (int)(i - (size_t)r * nx);
-  if (c > 0 && mask[i - 1]) uf_union(L, (u32)i, (u32)(i - 1));
+k_lab_tile(const uint8_t *__restrict__ mask, u32 *__restrict__ L, int ny, int nx, int conn8) {
+  __shared__ unsigned long long rowbits[LT];
+  __shared__ u32 sl[LT * LT];
+  const int r0 = blockIdx.y * LT, c0 = blockIdx.x * LT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // row words by warp ballots: warp w builds rows w, w + 8, ...
+  for (int lr = warp; lr < LT; lr += 8) {
+    const int r = r0 + lr;
+    const int ca = c0 + lane, cb = c0 + 32 + lane;
+    const bool ma = r < ny && ca < nx && mask[(size_t)r * nx + ca] != 0;
+    const bool mb = r < ny && cb < nx && mask[(size_t)r * nx + cb] != 0;
+    const unsigned lo = __ballot_sync(0xFFFFFFFFu, ma), hi = __ballot_sync(0xFFFFFFFFu, mb);
+    if (lane == 0) rowbits[lr] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+  }
+  for (int i = tid; i < LT * LT; i += 256) sl[i] = (u32)i;
+  __syncthreads();
+  for (int i = tid; i < LT * LT; i += 256) {
+    const int lr = i >> 6, lc = i & (LT - 1);
+    const unsigned long long cur = rowbits[lr];
+    if (!((cur >> lc) & 1ull) || lr == 0) continue;
+    const unsigned long long up = rowbits[lr - 1];
+    const bool start = lc == 0 || !((cur >> (lc - 1)) & 1ull);
+    const bool u_m = (up >> lc) & 1ull;
+    const bool u_l = lc > 0 && ((up >> (lc - 1)) & 1ull);
+    const bool u_r = lc < LT - 1 && ((up >> (lc + 1)) & 1ull);
+    const u32 me = (u32)(lr * LT + run_start(cur, lc));
+    const u32 upbase = (u32)((lr - 1) * LT);
+    if (!conn8) {
+      if (u_m && (start || !u_l)) suf_union_h(sl, me, upbase + (u32)run_start(up, lc));
+    } else if (start) {
+      if (u_m) suf_union_h(sl, me, upbase + (u32)run_start(up, lc));
+      else {
+        if (u_l) suf_union_h(sl, me, upbase + (u32)run_start(up, lc - 1));
+        if (u_r) suf_union_h(sl, me, upbase + (u32)(lc + 1));
+      }
+    } else if (u_r && !u_m) {
+      suf_union_h(sl, me, upbase + (u32)(lc + 1));       // a new upper run begins right of this cell
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < LT * LT; i += 256) {
+    const int lr = i >> 6, lc = i & (LT - 1);
+    const int r = r0 + lr, c = c0 + lc;
+    if (r >= ny || c >= nx) continue;
+    u32 out = HC_NONE;
+    const unsigned long long cur = rowbits[lr];
+    if ((cur >> lc) & 1ull) {
+      const u32 root = suf_find((volatile u32 *)sl, (u32)(lr * LT + run_start(cur, lc)));
+      out = (u32)((size_t)(r0 + (int)(root >> 6)) * nx + (c0 + (int)(root & (LT - 1))));
+    }
+    L[(size_t)r * nx + c] = out;
+  }
+}
+
+// unions across tile borders: cells of a tile's top row / left / right column with their W, NW, N, NE neighbours that lie
+// in another tile (every cross-tile pair is seen from its later cell)
+__global__ void __launch_bounds__(256)
+k_lab_border(const uint8_t *__restrict__ mask, u32 *L, int ny, int nx, int conn8) {
+  const int r0 = blockIdx.y * LT, c0 = blockIdx.x * LT;
+  const int side = threadIdx.x >> 6, j = threadIdx.x & (LT - 1);
+  int lr, lc;
+  if (side == 0) { lr = 0; lc = j; }                       // top row
+  else if (side == 1) { lr = j; lc = 0; if (j == 0) return; }        // left column (corner belongs to the top row)
+  else if (side == 2) { lr = j; lc = LT - 1; if (j == 0) return; }   // right column: only its NE neighbour leaves the tile
+  else return;
+  const int r = r0 + lr, c = c0 + lc;
+  if (r >= ny || c >= nx) return;
+  const size_t i = (size_t)r * nx + c;
+  if (!mask[i]) return;
+  if (side == 2) {
+    if (conn8 && r > 0 && c < nx - 1 && mask[i - nx + 1]) uf_union(L, (u32)i, (u32)(i - nx + 1));
+    return;
+  }
+  if (side == 1) {
+    if (c > 0 && mask[i - 1]) uf_union(L, (u32)i, (u32)(i - 1));
+    if (conn8 && r > 0 && c > 0 && mask[i - nx - 1]) uf_union(L, (u32)i, (u32)(i - nx - 1));
+    return;
+  }
+  // top row
+  if (lc == 0 && c > 0 && mask[i - 1]) uf_union(L, (u32)i, (u32)(i - 1));
   if (r > 0) {
     if (mask[i - nx]) uf_union(L, (u32)i, (u32)(i - nx));
     if (conn8) {
@@ -136,6 +258,12 @@ k_lab_out(const u32 *__restrict__ L, const u32 *__restrict__ R, int32_t *__restr
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     u32 p = L[i];
+    if (p != HC_NONE) {
+      // (L is not flattened for this caller: a cell points at its tile-local root, which the border pass hung under
+      //  the component's first cell -- one or two hops)
+      u32 q = __ldg(&L[p]);
+      while (q != p) { p = q; q = __ldg(&L[p]); }
+    }
     lab[i] = p == HC_NONE ? 0 : (int32_t)__ldg(&R[p]);
   }
 }
@@ -145,18 +273,22 @@ size_t label_workspace(int64_t ny, int64_t nx) {
   return 2 * hc_align(n * 4) + hc_align(((n + SCAN_CHUNK - 1) / SCAN_CHUNK) * 4) + hc_align(256);
 }
 
-static int label_roots(hc_ctx *ctx, const uint8_t *mask, u32 *L, int64_t ny, int64_t nx, int conn, cudaStream_t st) {
+static int label_roots(hc_ctx *ctx, const uint8_t *mask, u32 *L, int64_t ny, int64_t nx, int conn, cudaStream_t st,
+                       bool flatten = true) {
   size_t n = (size_t)ny * nx;
   unsigned nb = (unsigned)((n + 255) / 256);
-  HC_PROF(ctx, st, "k_lab_init");
-  k_lab_init<<<ctx->sm_count * 8, 256, 0, st>>>(mask, L, n);
+  dim3 tg((unsigned)((nx + LT - 1) / LT), (unsigned)((ny + LT - 1) / LT));
+  HC_PROF(ctx, st, "k_lab_tile");
+  k_lab_tile<<<tg, 256, 0, st>>>(mask, L, (int)ny, (int)nx, conn == 8);
   HC_LAUNCH_CHECK(ctx);
-  HC_PROF(ctx, st, "k_lab_merge");
-  k_lab_merge<<<nb, 256, 0, st>>>(mask, L, (int)ny, (int)nx, conn == 8);
+  HC_PROF(ctx, st, "k_lab_border");
+  k_lab_border<<<tg, 256, 0, st>>>(mask, L, (int)ny, (int)nx, conn == 8);
   HC_LAUNCH_CHECK(ctx);
-  HC_PROF(ctx, st, "k_lab_compress");
-  k_lab_compress<<<nb, 256, 0, st>>>(L, n);
-  HC_LAUNCH_CHECK(ctx);
+  if (flatten) {
+    HC_PROF(ctx, st, "k_lab_compress");
+    k_lab_compress<<<nb, 256, 0, st>>>(L, n);
+    HC_LAUNCH_CHECK(ctx);
+  }
   return HC_OK;
 }
 
@@ -174,7 +306,7 @@ int label_run(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_
   u32 *bsum = (u32 *)arena_take(ctx, (size_t)nchunks * 4);
   u32 *total = (u32 *)arena_take(ctx, 256);
   if (!L || !R || !bsum || !total) return HC_ERR_NOMEM;
-  HC_TRY(label_roots(ctx, mask, L, ny, nx, conn, st));
+  HC_TRY(label_roots(ctx, mask, L, ny, nx, conn, st, false));   // (k_lab_out chases the one or two remaining hops itself)
   HC_PROF(ctx, st, "k_root_count");
   k_root_count<<<nchunks, 256, 0, st>>>(L, bsum, n);
   HC_LAUNCH_CHECK(ctx);
