@@ -140,6 +140,11 @@ int hc_conv2d_symm_dw4_dev(hc_ctx *ctx, const float *in, const float *kernels_ho
                            float *out5, float *out3, int64_t ny, int64_t nx, void *stream);
 int hc_slope_dev(hc_ctx *ctx, const float *z, int8_t *deg, float *mag, int64_t ny, int64_t nx, double dx,
                  double dy, int d4, void *stream);
+/* Optional: the 90 float32 slopes at which np.rad2deg(np.arctan(x)).astype(int8) steps to 1, 2, ..., 90 degrees, as the
+ * caller's own arctan places them (pydrodem_b200.stencils.degree_thresholds derives them from numpy by bisection).
+ * With them hc_slope_dev's degree output is a binary search and bit-identical to that numpy; n = 0 restores atanf.
+ * (tools/derive.py:128,203: `.astype(np.int8)` of the degree array.) */
+int hc_slope_thresholds_set(hc_ctx *ctx, const float *thr, int32_t n);
 int hc_curvature_d2_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, double dx, double dy,
                         int geometric, void *stream);
 int hc_mean_std_dev(hc_ctx *ctx, const float *x, int64_t n, double *mean, double *std, void *stream);

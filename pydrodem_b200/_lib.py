@@ -42,6 +42,7 @@ SIGNATURES = {
     "hc_conv2d_symm_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_i64, c_vp]),
     "hc_conv2d_symm_dw4_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "hc_slope_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_f64, ctypes.c_int, c_vp]),
+    "hc_slope_thresholds_set": (ctypes.c_int, [c_vp, c_vp, c_i32]),
     "hc_curvature_d2_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_f64, ctypes.c_int, c_vp]),
     "hc_mean_std_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_vp]),
     "hc_sum_shifted_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_f64, ctypes.POINTER(c_f64), c_vp]),

@@ -97,6 +97,7 @@ struct hc_ctx {
   // stats of the last fill
   int64_t fill_basins;
   int32_t fill_rounds;
+  float deg_thr[90]; int deg_thr_n;   // slope -> truncated-degree thresholds (hc_slope_thresholds_set), 0 = atanf form
   uint32_t *chain_acc;   // accumulation raster of the running hc_fill_d8_accum_* chain (fill_d8_flats_accum_run)
   int pad_from;   // > 0: columns >= pad_from are the nodata padding of a pitched raster (hc_fill_d8_accum_ld_dev)
   // band diagnostics: terminal-graph edges emitted, MSF rounds, global seam-graph rounds

@@ -172,27 +172,86 @@ __device__ __forceinline__ int8_t to_deg_i8(float slope) {
   float deg = atanf(slope) * 57.29577951308232f;  // np.rad2deg(np.arctan(.)) in float32
   return (int8_t)(int)deg;                       // astype(int8): truncation toward zero
 }
+// The int8 truncation keeps 91 distinct answers, so the transcendental is not needed at all: thr[k - 1] = smallest
+// float32 slope whose truncated degree is >= k (k = 1..90), found on the host by bisection over the float32 bit patterns
+// WITH THE CALLER'S OWN arctan (numpy's, see stencils.degree_thresholds) -- the result is then bit-identical to
+// np.rad2deg(np.arctan(x)).astype(int8) of that numpy, where the atanf form is off by one at a few truncation
+// boundaries -- and a 7-step binary search replaces ~40 instructions of atanf.
+struct deg_thr { float t[90]; int n; };
+__device__ __forceinline__ int8_t to_deg_i8_thr(float slope, const deg_thr &d) {
+  int lo = 0, hi = 90;   // answer in [lo, hi]: number of thresholds <= slope
+#pragma unroll
+  for (int it = 0; it < 7; it++) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (mid <= hi && mid >= 1 && slope >= d.t[mid - 1]) lo = mid; else hi = mid - 1;
+  }
+  return (int8_t)lo;
+}
 
-// mode 0: slope_D2, mode 1: slope_D4 (max |central difference| over x, y and the two diagonals)
+// mode 0: slope_D2, mode 1: slope_D4 (max |central difference| over x, y and the two diagonals).
+// Column strips: a thread walks SL_RS rows of one column with the 3 x 3 window in registers (three coalesced loads
+// per cell instead of eight with reflected index arithmetic); raster-border cells take the general path.  The degree
+// thresholds sit in shared memory (a per-lane index into kernel parameters would serialise in the constant cache).
+#define SL_RS 32
 __global__ void __launch_bounds__(256)
 k_slope(const float *__restrict__ z, int8_t *__restrict__ out, float *__restrict__ mag, int ny, int nx, grad_prm p,
-        int mode) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+        int mode, const __grid_constant__ deg_thr thr) {
+  __shared__ float sthr[90];
+  if (threadIdx.x < 90) sthr[threadIdx.x] = thr.t[threadIdx.x];
+  __syncthreads();
+  const bool use_thr = thr.n == 90;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nx) return;
-  float dy = gy(z, r, c, ny, nx, p), dx = gx(z, r, c, ny, nx, p);
-  float s;
-  if (mode == 0) {
-    s = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
-  } else {
-    // diagonal kernels are convolved in float64 and narrowed to float32 (tools/derive.py:226-241)
-    int ru = symm(r - 1, ny), rd = symm(r + 1, ny), cl = symm(c - 1, nx), cr = symm(c + 1, nx);
-    const double dxy = p.dxy;
-    float dnw = (float)__dadd_rn(__dmul_rn(dxy, (double)z[(size_t)rd * nx + cr]), __dmul_rn(-dxy, (double)z[(size_t)ru * nx + cl]));
-    float dne = (float)__dadd_rn(__dmul_rn(dxy, (double)z[(size_t)rd * nx + cl]), __dmul_rn(-dxy, (double)z[(size_t)ru * nx + cr]));
-    s = fmaxf(fmaxf(fabsf(dx), fabsf(dne)), fmaxf(fabsf(dy), fabsf(dnw)));
+  const int rbeg = blockIdx.y * SL_RS, rend = min(rbeg + SL_RS, ny);
+  const bool cin = c > 0 && c < nx - 1;
+  auto to_deg = [&](float s_) -> int8_t {
+    if (!use_thr) return to_deg_i8(s_);
+    int lo = 0, hi = 90;
+#pragma unroll
+    for (int it = 0; it < 7; it++) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (mid >= 1 && mid <= hi && s_ >= sthr[mid - 1]) lo = mid; else hi = mid - 1;
+    }
+    return (int8_t)lo;
+  };
+  float w0[3], w1[3], w2[3];
+  auto ld3 = [&](int r, float *w) {
+    w[0] = w[1] = w[2] = 0.f;
+    if (r < 0 || r >= ny || !cin) return;
+    const float *row = z + (size_t)r * nx + c;
+    w[0] = __ldg(row - 1); w[1] = __ldg(row); w[2] = __ldg(row + 1);
+  };
+  ld3(rbeg - 1, w0);
+  ld3(rbeg, w1);
+  for (int r = rbeg; r < rend; r++) {
+    ld3(r + 1, w2);
+    float s;
+    if (cin && r > 0 && r < ny - 1) {
+      const float dy = __fdiv_rn(__fsub_rn(w2[1], w0[1]), p.h2y), dx = __fdiv_rn(__fsub_rn(w1[2], w1[0]), p.h2x);
+      if (mode == 0) s = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+      else {
+        const double dxy = p.dxy;
+        const float dnw = (float)__dadd_rn(__dmul_rn(dxy, (double)w2[2]), __dmul_rn(-dxy, (double)w0[0]));
+        const float dne = (float)__dadd_rn(__dmul_rn(dxy, (double)w2[0]), __dmul_rn(-dxy, (double)w0[2]));
+        s = fmaxf(fmaxf(fabsf(dx), fabsf(dne)), fmaxf(fabsf(dy), fabsf(dnw)));
+      }
+    } else {
+      const float dy = gy(z, r, c, ny, nx, p), dx = gx(z, r, c, ny, nx, p);
+      if (mode == 0) s = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+      else {
+        // diagonal kernels are convolved in float64 and narrowed to float32 (tools/derive.py:226-241)
+        int ru = symm(r - 1, ny), rd = symm(r + 1, ny), cl = symm(c - 1, nx), cr = symm(c + 1, nx);
+        const double dxy = p.dxy;
+        float dnw = (float)__dadd_rn(__dmul_rn(dxy, (double)z[(size_t)rd * nx + cr]), __dmul_rn(-dxy, (double)z[(size_t)ru * nx + cl]));
+        float dne = (float)__dadd_rn(__dmul_rn(dxy, (double)z[(size_t)rd * nx + cl]), __dmul_rn(-dxy, (double)z[(size_t)ru * nx + cr]));
+        s = fmaxf(fmaxf(fabsf(dx), fabsf(dne)), fmaxf(fabsf(dy), fabsf(dnw)));
+      }
+    }
+    if (out) out[(size_t)r * nx + c] = to_deg(s);
+    if (mag) mag[(size_t)r * nx + c] = s;
+#pragma unroll
+    for (int j = 0; j < 3; j++) { w0[j] = w1[j]; w1[j] = w2[j]; }
   }
-  if (out) out[(size_t)r * nx + c] = to_deg_i8(s);
-  if (mag) mag[(size_t)r * nx + c] = s;
 }
 
 __device__ __forceinline__ void norm_grad(const float *z, int r, int c, int ny, int nx, const grad_prm &p, float *ny_,
@@ -359,13 +418,28 @@ extern "C" int hc_slope_dev(hc_ctx *ctx, const float *z, int8_t *deg, float *mag
                             double dy, int d4, void *stream) {
   ST_CTX(ctx);
   if (ny <= 0 || nx <= 0) return HC_OK;
-  if (!z || (!deg && !mag) || ny > 65535) { hc_set_error("hc_slope: bad argument"); return HC_ERR_ARG; }
+  if (!z || (!deg && !mag)) { hc_set_error("hc_slope: bad argument"); return HC_ERR_ARG; }
   grad_prm p = make_grad(dx, dy);
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((nx + 255) / 256), (unsigned)ny);
+  dim3 grid((unsigned)((nx + 255) / 256), (unsigned)((ny + SL_RS - 1) / SL_RS));
   HC_PROF(ctx, st, "k_slope");
-  k_slope<<<grid, 256, 0, st>>>(z, deg, mag, (int)ny, (int)nx, p, d4 ? 1 : 0);
+  deg_thr thr;
+  thr.n = ctx->deg_thr_n;
+  memcpy(thr.t, ctx->deg_thr, sizeof(thr.t));
+  k_slope<<<grid, 256, 0, st>>>(z, deg, mag, (int)ny, (int)nx, p, d4 ? 1 : 0, thr);
   HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+extern "C" int hc_slope_thresholds_set(hc_ctx *ctx, const float *thr, int32_t n) {
+  ST_CTX(ctx);
+  if (n == 0) { ctx->deg_thr_n = 0; return HC_OK; }   // back to the atanf form
+  if (!thr || n != 90) { hc_set_error("hc_slope_thresholds_set: need the 90 degree thresholds (or n = 0)"); return HC_ERR_ARG; }
+  for (int k = 0; k < 90; k++) {
+    if (!(thr[k] == thr[k]) || (k && thr[k] < thr[k - 1])) { hc_set_error("hc_slope_thresholds_set: thresholds must ascend"); return HC_ERR_ARG; }
+    ctx->deg_thr[k] = thr[k];
+  }
+  ctx->deg_thr_n = 90;
   return HC_OK;
 }
 

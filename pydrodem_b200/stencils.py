@@ -76,10 +76,54 @@ def dw_smooth4(array, kernels):
     return [o.cpu().numpy() for o in outs] if host else outs
 
 
+_DEG_THR = None
+_DEG_THR_SET = set()
+
+
+def degree_thresholds():
+    """thr[k - 1] = the smallest float32 slope s with np.rad2deg(np.arctan(s)).astype(int8) >= k, k = 1..90, found by
+    bisection over the float32 bit patterns with numpy's own float32 arctan: what tools/derive.py:128,203 computes, as
+    91 comparable intervals instead of a transcendental per cell."""
+    global _DEG_THR
+    if _DEG_THR is None:
+        def deg(bits):
+            x = np.array([bits], np.uint32).view(np.float32)
+            with np.errstate(all="ignore"):
+                return int(np.rad2deg(np.arctan(x)).astype(np.int8)[0])
+        top = int(np.array([np.inf], np.float32).view(np.uint32)[0])
+        thr = np.empty(90, np.float32)
+        lo_prev = 0
+        for k in range(1, 91):
+            lo, hi = lo_prev, top          # deg(lo) < k (or lo == 0), deg(hi) >= k
+            if deg(hi) < k:
+                thr[k - 1] = np.inf
+                continue
+            while hi - lo > 1:
+                mid = (lo + hi) // 2
+                if deg(mid) >= k:
+                    hi = mid
+                else:
+                    lo = mid
+            thr[k - 1] = np.array([hi], np.uint32).view(np.float32)[0]
+            lo_prev = lo
+        _DEG_THR = thr
+    return _DEG_THR
+
+
+def _ensure_thresholds(dev_index):
+    if dev_index not in _DEG_THR_SET:
+        t = np.ascontiguousarray(degree_thresholds(), np.float32)
+        _lib.check(_lib.load().hc_slope_thresholds_set(_lib.context(dev_index), ctypes.c_void_p(t.ctypes.data), 90),
+                   "hc_slope_thresholds_set")
+        _DEG_THR_SET.add(dev_index)
+
+
 def _slope(array, dx, dy, d4, unit):
     import torch
     a, host = _to_dev(array, np.float32)
     a = _tdev(a, torch.float32, "slope")
+    if unit == 'degree':
+        _ensure_thresholds(a.device.index or 0)
     deg = torch.empty(a.shape, dtype=torch.int8, device=a.device) if unit == 'degree' else None
     mag = torch.empty_like(a) if unit != 'degree' else None
     with torch.cuda.device(a.device):
