@@ -69,6 +69,14 @@ int64_t hc_launch_count(const hc_ctx *ctx);
 int hc_fill_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
                 int seed_mode, void *stream);
 
+/* Priority-Flood + epsilon (WhiteboxTools fill with fix_flats / flat_increment > 0; dep.fill_pits' second fill,
+ * tools/depressions.py:195-198, :1271-1286): float64 surface W = the unique solution of
+ * W(c) = max(z(c), min over neighbours W(n) + eps), W = z on the seeds, reached by monotone sweeps from the eps = 0
+ * fill.  `sweeps` (optional) receives the number of raster sweeps.  Tolerance class: the serial flood makes the same
+ * float64 additions, WhiteboxTools' own heap order is unknown (parity unpinned). */
+int hc_fill_eps_dev(hc_ctx *ctx, const float *z, double *out, int64_t ny, int64_t nx, float nodata, int seed_mode,
+                    double eps, int64_t *sweeps, void *stream);
+
 /* D8 direction (uint8 code, HC_DIR_NODATA on nodata / TauDEM-contaminated cells) and optional
  * slope (float32, may be NULL).  Replaces wbt.d8_pointer (run_aws.py:539) and the steepest-
  * descent half of TauDEM D8FlowDir -p -sd8 (run_aws.py:594-603). */

@@ -26,6 +26,7 @@ SIGNATURES = {
     "hc_workspace_bytes": (c_i64, [c_vp]),
     "hc_launch_count": (c_i64, [c_vp]),
     "hc_fill_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, c_vp]),
+    "hc_fill_eps_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, c_f64, ctypes.POINTER(c_i64), c_vp]),
     "hc_d8_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64, c_f64, ctypes.c_int, c_vp]),
     "hc_resolve_flats_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, c_vp]),
     "hc_accum_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_vp]),

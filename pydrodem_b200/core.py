@@ -64,6 +64,23 @@ def fill(z, nodata=-9999.0, seed_mode=SEED_WBT):
     return out
 
 
+def fill_eps(z, eps, nodata=-9999.0, seed_mode=SEED_WBT, return_sweeps=False):
+    """Priority-Flood + epsilon: the fill with an imposed gradient `eps` per step over filled areas (WhiteboxTools'
+    fix_flats / flat_increment > 0; tools/depressions.py:195-198, :1271-1286).  float64 out (WhiteboxTools writes
+    float64; dep.fill_pits narrows it unless downcast=False).  numpy in -> numpy out, CUDA tensor in -> CUDA tensor."""
+    import torch
+    lib = _lib.load()
+    host = not _is_torch(z)
+    zt = torch.from_numpy(_np2d(z, np.float32)).cuda() if host else _tdev(z, torch.float32, "fill_eps")
+    out = torch.empty(zt.shape, dtype=torch.float64, device=zt.device)
+    n = ctypes.c_int64(0)
+    with torch.cuda.device(zt.device):
+        _lib.check(lib.hc_fill_eps_dev(_lib.context(zt.device.index or 0), _tp(zt), _tp(out), zt.shape[0], zt.shape[1],
+                                       nodata, seed_mode, float(eps), ctypes.byref(n), _stream(zt)), "hc_fill_eps_dev")
+    res = out.cpu().numpy() if host else out
+    return (res, int(n.value)) if return_sweeps else res
+
+
 def d8(z, nodata=-9999.0, dx=1.0, dy=1.0, table=TABLE_WBT, want_slope=True):
     """D8 code (uint8) and optional slope (float32) — wbt.d8_pointer run_aws.py:539 /
     TauDEM D8FlowDir run_aws.py:594-603.  Device tensors only (numpy: use fill_d8_accum)."""
@@ -285,7 +302,8 @@ def breach_depressions(z, nodata=-9999.0, max_length=None, max_depth=None, fill_
                        return_stats=False, method='flowpath_dev'):
     """wbt.breach_depressions (Lindsay 2016) as dep.breach_pits calls it (tools/depressions.py:1376-1380): constrained
     breaching, then the depressions that could not be breached are filled with WhiteboxTools' seed rule.
-    float32 in, float32 out (numpy in -> numpy out, CUDA tensor in -> CUDA tensor out).
+    float32 in, float32 out (numpy in -> numpy out, CUDA tensor in -> CUDA tensor out); with flat_increment > 0 the closing
+    fill is Priority-Flood + epsilon (core.fill_eps) and the result is float64.
 
     method='flowpath_dev' (default): the order-independent flow-path formulation, every pass on the GPU
     (specification: oracle/breach_flowpath.py).  'flowpath': the same formulation with the pointer walks
@@ -293,15 +311,16 @@ def breach_depressions(z, nodata=-9999.0, max_length=None, max_depth=None, fill_
     WhiteboxTools itself is unavailable, so all three are restatements of Lindsay (2016): parity unpinned."""
     import ctypes
     import numpy as np
-    if flat_increment is not None and flat_increment > 0:
-        raise NotImplementedError("flat_increment > 0 (graded breach channels / Priority-Flood+epsilon) is order "
-                                  "dependent in WhiteboxTools and is not offered; pydrodem's default is 0.0")
+    eps = float(flat_increment) if (flat_increment is not None and flat_increment > 0) else 0.0
+    if eps > 0.0 and method != 'flowpath_dev':
+        raise NotImplementedError("flat_increment > 0 is served by the default method only")
     if method not in ('flood', 'flowpath', 'flowpath_dev'):
         raise ValueError("method must be 'flowpath_dev' (default), 'flowpath' or 'flood'")
     host = not _is_torch(z)
     if method == 'flowpath_dev':
         cut, st = _breach_flowpath_dev(z if not host else _np2d(z, np.float32), nodata, max_length, max_depth, fill_pits)
-        out = fill(cut, nodata=nodata, seed_mode=SEED_WBT)
+        # what could not be breached is filled; with flat_increment > 0 by the epsilon fill (float64 out, like WhiteboxTools)
+        out = fill_eps(cut, eps, nodata=nodata, seed_mode=SEED_WBT) if eps > 0.0 else fill(cut, nodata=nodata, seed_mode=SEED_WBT)
         if host:
             out = out.cpu().numpy()
         if return_stats:

@@ -447,3 +447,146 @@ extern "C" int hc_breach_flowpath_dev(hc_ctx *ctx, const float *w, float *out, f
   if (stats) { stats[0] = (int64_t)h[0]; stats[1] = (int64_t)h[1]; stats[2] = (int64_t)h[2]; stats[3] = (int64_t)h[4]; }
   return HC_OK;
 }
+
+
+// =================================================================================================
+// Priority-Flood + epsilon (fix_flats / flat_increment > 0: dep.fill_pits' second fill, tools/depressions.py:195-198,
+// :1271-1286; config_files/config_local.ini:161 leaves it at 0.0).  WhiteboxTools raises every cell to at least
+// (the level of the cell it was reached from) + eps, in float64.  Cells are reached in non-decreasing order of level, so
+// the parent is the neighbour with the lowest level and the surface is the UNIQUE solution of
+//       W(c) = max(z(c), min over 8-neighbours n of W(n) + eps),   W = z on the seeds
+// (every dependency points at a strictly lower level, so there is no cycle to make the heap's tie order matter).  It is
+// computed here as the limit of the monotone iteration W <- max(W, F(W)) from the eps = 0 fill, which lies below it: the
+// same float64 additions, one per step of a cell's chain, as the serial flood makes, hence the same doubles.  Jacobi
+// sweeps over the raster, as many as the longest raised chain is long (a lake's diameter): a tolerance-class option, not
+// a hot path -- what matters is that the key gives a result instead of an exception.
+// =================================================================================================
+// TauDEM seed rule: frame cells and cells 8-adjacent to any nodata cell
+__global__ void __launch_bounds__(256)
+k_bf_seed_any(const float *__restrict__ w, uint8_t *__restrict__ seed, int ny, int nx, float nodata) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= nx) return;
+  size_t i = (size_t)r * nx + c;
+  uint8_t s = 0;
+  if (!d_is_nodata(w[i], nodata)) {
+    if (r == 0 || c == 0 || r == ny - 1 || c == nx - 1) s = 1;
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) s |= d_is_nodata(w[(size_t)(r + c_dr[0][k]) * nx + c + c_dc[0][k]], nodata) ? 1 : 0;
+    }
+  }
+  seed[i] = s;
+}
+
+__global__ void __launch_bounds__(256)
+k_eps_init(const float *__restrict__ z, const float *__restrict__ filled, double *__restrict__ W, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    (void)z;
+    W[i] = (double)filled[i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_eps_sweep(const float *__restrict__ z, const uint8_t *__restrict__ seed, const double *__restrict__ A, double *__restrict__ B,
+            int ny, int nx, float nodata, double eps, u32 *__restrict__ changed) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  int ch = 0;
+  if (c < nx) {
+    const size_t i = (size_t)r * nx + c;
+    double w = A[i];
+    const float zc = z[i];
+    if (!d_is_nodata(zc, nodata) && !seed[i]) {
+      double m = INFINITY;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int rr = r + c_dr[0][k], cc = c + c_dc[0][k];
+        if (rr < 0 || rr >= ny || cc < 0 || cc >= nx) continue;
+        const size_t j = (size_t)rr * nx + cc;
+        if (d_is_nodata(z[j], nodata)) continue;
+        const double wn = A[j];
+        m = wn < m ? wn : m;
+      }
+      if (m < INFINITY) {
+        const double cand = fmax((double)zc, m + eps);
+        if (cand > w) { w = cand; ch = 1; }
+      }
+    }
+    B[i] = w;
+  }
+  ch = __syncthreads_or(ch);
+  if (ch && threadIdx.x == 0) *changed = 1u;
+}
+
+extern "C" int hc_fill_eps_dev(hc_ctx *ctx, const float *z, double *out, int64_t ny, int64_t nx, float nodata,
+                               int seed_mode, double eps, int64_t *sweeps, void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (sweeps) *sweeps = 0;
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!z || !out || !(eps >= 0.0)) { hc_set_error("hc_fill_eps: bad argument"); return HC_ERR_ARG; }
+  if (seed_mode != HC_SEED_WBT && seed_mode != HC_SEED_TAUDEM) { hc_set_error("hc_fill_eps: bad seed_mode"); return HC_ERR_ARG; }
+  if (ny > 65535) { hc_set_error("hc_fill_eps: more than 65535 rows"); return HC_ERR_TOO_LARGE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)ny * nx;
+  float *filled = nullptr;
+  double *B = nullptr;
+  uint8_t *seed = nullptr, *ext = nullptr;
+  u32 *flag = nullptr;
+  HC_CUDA(cudaMalloc(&filled, n * 4));
+  cudaError_t e = cudaMalloc(&B, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&seed, n);
+  if (e == cudaSuccess) e = cudaMalloc(&ext, n);
+  if (e == cudaSuccess) e = cudaMalloc(&flag, 256);
+  int rc = HC_OK;
+  auto cleanup = [&]() { cudaFree(filled); cudaFree(B); cudaFree(seed); cudaFree(ext); cudaFree(flag); };
+  if (e != cudaSuccess) { cudaGetLastError(); cleanup(); hc_set_error("hc_fill_eps: out of device memory"); return HC_ERR_NOMEM; }
+  // the eps = 0 surface (a lower bound), and the seed mask of the chosen rule
+  rc = fill_run(ctx, z, filled, ny, nx, nodata, seed_mode, st);
+  if (rc == HC_OK && seed_mode == HC_SEED_WBT) {
+    // WBT rule: only EXTERIOR nodata seeds its neighbours.  ext_nodata_mask leaves the plain nodata mask in `ext` when
+    // no nodata cell lies off the frame (then all of it is exterior) and the exterior subset otherwise.
+    rc = arena_reset(ctx);
+    int has_interior = 0;
+    if (rc == HC_OK) rc = ext_nodata_mask(ctx, z, ext, ny, nx, nodata, &has_interior, st);
+  }
+  if (rc != HC_OK) { cleanup(); return rc; }
+  dim3 g2((unsigned)((nx + 255) / 256), (unsigned)ny);
+  if (seed_mode == HC_SEED_TAUDEM) {
+    // seeds = frame cells + cells 8-adjacent to ANY nodata: a one-pass predicate on z itself
+    k_bf_seed_any<<<g2, 256, 0, st>>>(z, seed, (int)ny, (int)nx, nodata);
+  } else {
+    k_bf_seed<<<g2, 256, 0, st>>>(z, ext, seed, (int)ny, (int)nx, nodata);
+  }
+  k_eps_init<<<ctx->sm_count * 8, 256, 0, st>>>(z, filled, out, n);
+  ctx->launches += 2;
+  double *A = out;
+  int64_t nsweeps = 0;
+  if (eps > 0.0) {
+    for (;;) {
+      // 8 sweeps per read-back; the ping-pong ends in `out` (an even number of sweeps per batch)
+      cudaMemsetAsync(flag, 0, 4, st);
+      for (int k = 0; k < 8; k++) {
+        k_eps_sweep<<<g2, 256, 0, st>>>(z, seed, A, B, (int)ny, (int)nx, nodata, eps, flag);
+        double *t = A; A = B; B = t;
+        ctx->launches++;
+      }
+      nsweeps += 8;
+      u32 h = 0;
+      if (cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaError_t e2 = cudaGetLastError();
+        cleanup();
+        hc_set_error("hc_fill_eps: %s", cudaGetErrorString(e2));
+        return HC_ERR_CUDA;
+      }
+      if (!h) break;
+      if (nsweeps > 4 * (ny + nx) + 64) { cleanup(); hc_set_error("hc_fill_eps: no fixed point after %lld sweeps", (long long)nsweeps); return HC_ERR_INTERNAL; }
+    }
+  }
+  // (8 sweeps per batch: A is `out` again)
+  cudaError_t e3 = cudaStreamSynchronize(st);
+  cleanup();
+  if (e3 != cudaSuccess) { hc_set_error("hc_fill_eps: %s", cudaGetErrorString(e3)); return HC_ERR_CUDA; }
+  if (sweeps) *sweeps = nsweeps;
+  return HC_OK;
+}

@@ -16,7 +16,7 @@ from .. import core, raster_io, stencils
 def fill_pits(inDEM, wbt, fill_method='WL', nodataval=-9999, fixflats=False, flat_increment=0.0, save_tif=True,
               downcast=True):
     """tools/depressions.py:1236-1316.  Returns (fill_array, diff_fill_array), writes `<in>_<method>.tif`
-    and (save_tif) `<in>_<method>_DIFF.tif`.  `downcast` is moot: the fill is written as float32 already."""
+    and (save_tif) `<in>_<method>_DIFF.tif`.  `downcast` only matters for the float64 epsilon fill (flat_increment > 0)."""
     fill_tif = inDEM.replace('.tif', '_{0}.tif'.format(fill_method))
     if flat_increment > 0.0:
         fixflats = True
@@ -27,7 +27,11 @@ def fill_pits(inDEM, wbt, fill_method='WL', nodataval=-9999, fixflats=False, fla
     else:
         raise ValueError("   Improper fill method specified")
     inDEM_array, meta = raster_io.read_raster(inDEM)
-    fill_array, _ = raster_io.read_raster(fill_tif)
+    fill_array, fmeta = raster_io.read_raster(fill_tif)
+    if downcast and fill_array.dtype == np.float64:
+        # the epsilon fill is written in float64 (as WhiteboxTools writes everything); pyct.tifdowncast narrows it (:1306)
+        fill_array = fill_array.astype(np.float32)
+        raster_io.write_raster(fill_tif, fill_array, fmeta, nodata=nodataval)
     diff_fill_array = np.round((fill_array - inDEM_array), 3)  # :1308
     if save_tif:
         diff_tif_fill = fill_tif.replace('.tif', '_DIFF.tif')

@@ -9,8 +9,8 @@ success; unlike it, it raises on failure (the reference ignores return codes and
 missing output file).
 
 Deliberate differences, all stated where they apply:
-  * `fix_flats=True` / `flat_increment>0` (Priority-Flood+epsilon) is order dependent inside
-    WhiteboxTools itself and is not offered on the GPU path: NotImplementedError.
+  * `flat_increment > 0` (Priority-Flood+epsilon) is served by `hc_fill_eps_dev` (float64 out, as WhiteboxTools
+    writes): a stated-tolerance mode, WhiteboxTools' own heap order on ties being unknown.
   * outputs are float32 GeoTIFFs (WhiteboxTools writes float64 and pydrodem narrows them right
     away with `pyct.tifdowncast`, tools/depressions.py:1306); D8 pointers are int16 with -32768 on
     nodata cells as WhiteboxTools writes them.
@@ -49,18 +49,27 @@ class WhiteboxToolsGPU:
         return arr, meta, float(nodata)
 
     @staticmethod
-    def _no_eps(fix_flats, flat_increment):
-        if fix_flats or (flat_increment is not None and flat_increment > 0):
-            raise NotImplementedError(
-                "fix_flats / flat_increment > 0 (Priority-Flood+epsilon) is order dependent in WhiteboxTools and is "
-                "not reproduced on the GPU path; pydrodem's default is flat_increment = 0.0 "
-                "(config_files/config_local.ini:161)")
+    def _eps(fix_flats, flat_increment):
+        """the gradient WhiteboxTools imposes on filled areas: `flat_increment` when given (> 0), nothing when fix_flats is
+        off.  fix_flats=True WITHOUT an increment lets WhiteboxTools derive one from the raster's resolution and
+        elevation range (its own heuristic, not reproducible without the binary): refused."""
+        if flat_increment is not None and flat_increment > 0:
+            return float(flat_increment)
+        if fix_flats:
+            raise NotImplementedError("fix_flats=True needs an explicit flat_increment here (WhiteboxTools' automatic "
+                                      "increment is its own heuristic); pydrodem passes fix_flats only together with "
+                                      "flat_increment > 0 (tools/depressions.py:1271-1273)")
+        return 0.0
 
     # -- fills (tools/depressions.py:1277-1286, :1006, :1385) ---------------------------------------
     def fill_depressions_wang_and_liu(self, dem, output, fix_flats=True, flat_increment=None, callback=None):
-        self._no_eps(fix_flats, flat_increment)
+        eps = self._eps(fix_flats, flat_increment)
         z, meta, nodata = self._load(dem)
-        out = core.fill(np.asarray(z, np.float32), nodata=nodata, seed_mode=SEED_WBT)
+        if eps > 0.0:
+            # Priority-Flood + epsilon, float64 like WhiteboxTools' own output (tolerance class, see core.fill_eps)
+            out = core.fill_eps(np.asarray(z, np.float32), eps, nodata=nodata, seed_mode=SEED_WBT)
+        else:
+            out = core.fill(np.asarray(z, np.float32), nodata=nodata, seed_mode=SEED_WBT)
         raster_io.write_raster(output, out, meta, nodata=nodata)
         self._say("fill_depressions_wang_and_liu ->", output)
         return 0

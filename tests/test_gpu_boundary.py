@@ -65,8 +65,12 @@ def test_wbt_duck_type_fill_and_d8(tmp_path, oracle, cuda):
     sf_tif = dem_tif.replace(".tif", "_SF.tif")
     wbt.fill_depressions(dem_tif, sf_tif, max_depth=None, fix_flats=False, flat_increment=0.0)
     assert np.array_equal(raster_io.read_raster(sf_tif)[0], got)
+    eps_tif = dem_tif.replace(".tif", "_WLeps.tif")
+    assert wbt.fill_depressions_wang_and_liu(dem_tif, eps_tif, fix_flats=True, flat_increment=1e-5) == 0
+    eps_fill = raster_io.read_raster(eps_tif)[0]
+    assert eps_fill.dtype == np.float64 and np.array_equal(eps_fill[z != N], oracle.fill_eps(z, 1e-5, N, oracle.SEED_WBT)[z != N])
     with pytest.raises(NotImplementedError):
-        wbt.fill_depressions_wang_and_liu(dem_tif, fill_tif, fix_flats=True, flat_increment=1e-5)
+        wbt.fill_depressions_wang_and_liu(dem_tif, fill_tif, fix_flats=True, flat_increment=None)
     d8_tif, acc_tif = str(tmp_path / "d8.tif"), str(tmp_path / "acc.tif")
     wbt.d8_pointer(fill_tif, d8_tif)
     wbt.d8_flow_accumulation(d8_tif, acc_tif, pntr=True)

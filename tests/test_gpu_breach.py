@@ -45,7 +45,13 @@ def test_flood_method_gpu_fill_of_the_cut_surface_equals_host_fill(ny, nx, seed,
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), want)
     assert np.array_equal(hc.fill(got, nodata=ND, seed_mode=hc.SEED_WBT), got)       # depression free
     with pytest.raises(NotImplementedError):
-        hc.breach_depressions(z, flat_increment=0.001)
+        hc.breach_depressions(z, flat_increment=0.001, method='flood')
+    # default method + flat_increment: the breached surface closed by the epsilon fill (float64, like WhiteboxTools' output)
+    from oracle import breach_flowpath as bf
+    from oracle import hydro_oracle as ho
+    cut, _ = bf.breach_flowpath(z, ND, max_length=ml, fill_pits=True, do_fill=False)
+    graded = hc.breach_depressions(z, nodata=ND, max_length=ml or None, fill_pits=True, flat_increment=1e-4)
+    assert graded.dtype == np.float64 and np.array_equal(graded[z != ND], ho.fill_eps(cut, 1e-4, ND, ho.SEED_WBT)[z != ND])
 
 
 @pytest.mark.gpu

@@ -161,3 +161,45 @@ def test_chain_pitched_rasters_equal_dense(case, seed_mode, table, oracle, cuda)
     assert np.array_equal(gd.cpu().numpy(), d)
     assert np.array_equal(gs.cpu().numpy(), s)
     assert np.array_equal(ga.cpu().numpy().view(np.uint32), a)
+
+
+@pytest.mark.parametrize("case", [CASES[7], CASES[9], CASES[10], CASES[11]], ids=lambda c: f"{c[0]}x{c[1]}-{c[2]}-{c[3]}")
+@pytest.mark.parametrize("seed_mode", [0, 1], ids=["wbt", "taudem"])
+def test_fill_eps_equals_priority_flood_plus_epsilon(case, seed_mode, oracle, cuda):
+    """flat_increment > 0: hc_fill_eps_dev against the oracle's serial Priority-Flood + epsilon (float64).  The surface is
+    the unique solution of W = max(z, min_n W(n) + eps), and both make one float64 addition per step of a chain, so the
+    comparison is exact here; the stated tolerance towards WhiteboxTools itself (unknown heap order, parity unpinned) is
+    eps times the longest chain."""
+    import pydrodem_b200 as hc
+    z = _dem(case)
+    for eps in (1e-5, 1e-3):
+        want = oracle.fill_eps(z, eps, seed_mode=seed_mode)
+        got, sweeps = hc.fill_eps(z, eps, seed_mode=seed_mode, return_sweeps=True)
+        assert got.dtype == np.float64 and got.shape == z.shape and sweeps >= 8
+        valid = z != np.float32(-9999.0)
+        assert np.array_equal(got[valid], want[valid]), f"eps={eps}: max |diff| {np.abs(got[valid] - want[valid]).max()}"
+        assert np.all(got[valid] >= hc.fill(z, seed_mode=seed_mode)[valid])          # never below the eps = 0 surface
+    assert np.array_equal(hc.fill_eps(z, 0.0, seed_mode=seed_mode)[valid], hc.fill(z, seed_mode=seed_mode)[valid].astype(np.float64))
+
+
+@pytest.mark.gpu
+def test_wbt_fill_with_flat_increment_writes_float64_and_fill_pits_downcasts(tmp_path, oracle, cuda):
+    import pydrodem_b200 as hc
+    from pydrodem_b200 import raster_io
+    from pydrodem_b200.tools import depressions as dep
+    from pydrodem_b200.wbt import WhiteboxToolsGPU
+    z = _dem(CASES[11])
+    dem = str(tmp_path / "u.tif")
+    raster_io.write_raster(dem, z, None, nodata=-9999.0)
+    wbt = WhiteboxToolsGPU()
+    fill32, diff = dep.fill_pits(dem, wbt, flat_increment=1e-4)
+    assert fill32.dtype == np.float32
+    want = oracle.fill_eps(z, 1e-4, seed_mode=0).astype(np.float32)
+    valid = z != np.float32(-9999.0)
+    assert np.array_equal(fill32[valid], want[valid])
+    on_disk, _ = raster_io.read_raster(str(tmp_path / "u_WL.tif"))
+    assert on_disk.dtype == np.float32
+    fill64, _ = dep.fill_pits(dem, wbt, flat_increment=1e-4, downcast=False)
+    assert fill64.dtype == np.float64
+    with pytest.raises(NotImplementedError):
+        wbt.fill_depressions_wang_and_liu(dem, str(tmp_path / "x.tif"), fix_flats=True, flat_increment=None)
