@@ -112,7 +112,7 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -132,13 +132,18 @@ class ClockSampler:
                 except (AttributeError, OSError):
                     pass
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL, preexec_fn=_unpin)
         except OSError:
             self.p = None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    def stop(self, window=None):
+        """window = (t0, t1) in time.time() seconds: the timed region.  Samples are taken every 20 ms from start() on (the
+        sampler is started before the warm-up so that it is up when the timed region begins); `sm_mhz` is the median over
+        the samples INSIDE the window when there are any (else over all samples under the same load), `samples` says how
+        many those were and `samples_total` how many were taken in all."""
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "samples_total": 0}
         if self.p is None:
             return out
         self.p.terminate()
@@ -148,25 +153,31 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                sm, mx = float(parts[2]), float(parts[3])
             except ValueError:
                 continue
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+            rows.append((ts, sm, mx, [nm for nm, val in zip(names, parts[6:10]) if val.lower().startswith("active")]))
         self.f.close()
         os.unlink(self.f.name)
-        if sm:
-            s = sorted(sm)
-            out.update(sm_mhz=s[len(s) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        if not rows:
+            return out
+        inside = [r for r in rows if window and window[0] - 0.02 <= r[0] <= window[1] + 0.02]
+        use = inside if inside else rows
+        sms = sorted(r[1] for r in use)
+        reasons = set()
+        for r in use:
+            reasons.update(r[3])
+        out.update(sm_mhz=sms[len(sms) // 2], sm_max_mhz=max(r[2] for r in use), reasons=sorted(reasons),
+                   samples=len(inside), samples_total=len(rows),
+                   window="timed region" if inside else "warm-up + timed region (no sample fell inside the timed region)")
         return out
 
 
@@ -288,22 +299,25 @@ def measure_banded(args, world, rank, local, dev, workload, steps, warmup, want_
         torch.cuda.synchronize()
 
     out = None
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
     for _ in range(warmup):
         out = chain.run()
     barrier()
     for c in chain.ctx:
         _lib.profile_enable(True, ctx=c)
     launches0 = chain.launches()
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    tw0 = time.time()
     e0.record()
     for _ in range(steps):
         out = chain.run()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    tw1 = time.time()
+    clocks = sampler.stop((tw0, tw1))
     ms = e0.elapsed_time(e1)
     launches = chain.launches() - launches0
     prof = {}
@@ -835,25 +849,37 @@ def main():
         torch.cuda.synchronize()
 
     out = None
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)        # nvidia-smi needs a moment to come up; it then samples every 20 ms
     for _ in range(args.warmup):
         out = hc.fill_d8_accum(z, **kw)
     barrier()
-    _lib.profile_enable(True, local)
     launches0 = _lib.launch_count(local)
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    tw0 = time.time()
     e0.record()
     for _ in range(args.steps):
         out = hc.fill_d8_accum(z, **kw)
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    tw1 = time.time()
+    clocks = sampler.stop((tw0, tw1))
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count(local) - launches0
-    prof = _lib.profile_read(local)
+    # per-kernel times: a profiled pass of the same steps right after the timed region (the library brackets every launch
+    # with CUDA events on the launching stream).  The chain's one concurrency -- the accumulation's tile phase beside the
+    # flats' slow tier -- is switched off for this pass, so that each kernel's events time that kernel alone.
+    os.environ["HC_NO_ACC_OVERLAP"] = "1"
+    _lib.profile_enable(True, local)
+    psteps = max(3, min(args.steps, 10))
+    for _ in range(psteps):
+        hc.fill_d8_accum(z, **kw)
+    torch.cuda.synchronize()
+    prof = {k: (c * args.steps / psteps, t_ * args.steps / psteps, m) for k, (c, t_, m) in _lib.profile_read(local).items()}
     _lib.profile_enable(False, local)
+    del os.environ["HC_NO_ACC_OVERLAP"]
     basins, rounds = hc.core.fill_stats(local)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -967,6 +993,8 @@ def main():
                    "cells_per_gpu": cells, "l2": "inputs (467 MB z + outputs) exceed the 126 MB L2; no explicit flush",
                    "device_raster": "dense" if args.dense else "pitched (core.empty_raster, hc_fill_d8_accum_ld_dev): TMA path",
                    "flats": bool(args.flats), "basins": basins, "boruvka_rounds": rounds,
+                   "kernel_times": "profiled pass right after the timed region (same inputs, per-launch CUDA events, "
+                                   "accumulation / flats overlap off); the timed region itself runs unprofiled",
                    "algorithmic_bytes_per_cell": 18},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "hbm_frac_algorithmic_whole_step": 18 * cells / (ms_max / args.steps * 1e-3) / 1e9 / peak,
