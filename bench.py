@@ -806,9 +806,21 @@ def main():
         except (AttributeError, OSError):
             pass
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's version banner / debug output goes to stderr
+        # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout when the first communicator comes up,
+        # so file descriptor 1 points at stderr until that has happened
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     if args.workload == "auto":
         args.workload = "c2" if world == 1 and args.local_bands == 1 else ("auto_n" if world > 1 else "bands")
