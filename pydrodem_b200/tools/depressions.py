@@ -397,6 +397,44 @@ def fill_shallow_pits(modDEM_vec, sfill, fillID_vec, diff_fill_array, fill_array
     return out
 
 
+def raise_lake_connected_pits(watermask, fillID_vec, modDEM_vec, inDEM_vec, starttime=None, verbose_print=True):
+    """tools/depressions.py:1534-1590 as its docstring and comments describe it: every pit that holds large-waterbody
+    cells (`watermask` raster == 1) is raised, where it lies below the lowest water cell inside the pit, to that level
+    + 1 cm.  Returns (modDEM_vec, DEMdiff_vec = inDEM_vec - modDEM_vec).  Nothing happens with 20 or fewer lake cells.
+
+    Upstream computes the lake/pit intersection as `np.intersect1d(np.where(water_array == 1), flat indices)`, i.e. it
+    intersects the ROW and COLUMN numbers of the lake cells with flat cell indices, so its result is unrelated to the
+    lake (and the option, `fill_h20_adjacent`, is off in every shipped configuration).  This is the documented
+    behaviour, not that accident: one segmented minimum per pit over its lake cells (`hc_seg_stats_dev`), one
+    elementwise raise.  `watermask`: a GeoTIFF path, or the 2-D mask itself."""
+    torch = _torch()
+    water = raster_io.read_raster(watermask)[0] if isinstance(watermask, str) else np.asarray(watermask)
+    lake = _dev(water == 1, torch.int32)
+    dem_in = _dev(inDEM_vec, torch.float32)
+    n = dem_in.numel()
+    mod_is_torch = type(modDEM_vec).__module__.startswith("torch")
+    mod = _dev(modDEM_vec, torch.float32).clone()
+    if int(lake.sum()) > 20:
+        fid = _dev(fillID_vec, torch.int32)
+        npits = int(fid.max()) if n else 0
+        if npits > 0:
+            lowest = torch.full((npits + 1,), float("inf"), dtype=torch.float32, device=dem_in.device)
+            cnt = torch.zeros(npits + 1, dtype=torch.int64, device=dem_in.device)
+            _L.check(_L.load().hc_seg_stats_dev(_L.context(dem_in.device.index or 0), _p(fid), _p(dem_in), _p(lake), n, npits, 1,
+                                                None, _p(lowest), None, _p(cnt), _stream()), "hc_seg_stats_dev")
+            lowest[cnt == 0] = float("-inf")          # pits without lake cells: nothing lies below
+            lowest[0] = float("-inf")
+            lvl = lowest[fid.long()]
+            raise_it = (fid > 0) & (dem_in < lvl)
+            mod = torch.where(raise_it, lvl + 0.01, mod)
+    diff = dem_in - mod
+    if verbose_print:
+        print(f"      number of cells adjusted: {int((diff < 0).sum())} Max change: {float(diff.abs().max()) if n else 0.0:.2f}")
+    if mod_is_torch:
+        return mod, diff
+    return mod.cpu().numpy(), diff.cpu().numpy()
+
+
 # ==================================================================================================
 # initial_fill_carve (tools/depressions.py:41-264): the orchestration that turns one DEM GeoTIFF into the eight
 # vectors the pit catalog consumes -- two fills, four clump rasters, one breach.
@@ -406,11 +444,9 @@ def initial_fill_carve(inDEM_tif, basename, outpath, fill_method, maxcost, radiu
                        carve_method='SC', verbose_print=True, del_temp_files=False):
     """Same signature, file names and return tuple as the reference:
     (modDEM_vec, fill_vec, carve_vec, diff_vec_fill, diff_vec_carve, fillID_vec, carveID_vec, carvefillID_vec, nx, ny).
-    `watermask` (the lake raise of :163-176) is refused: `raise_lake_connected_pits` is broken upstream."""
+    `watermask` (path or array of the large-waterbody mask) switches on the lake raise of :163-176, see
+    raise_lake_connected_pits."""
     import glob
-    if watermask is not None:
-        raise NotImplementedError("initial_fill_carve(watermask=...) calls raise_lake_connected_pits, which cannot run "
-                                  "in the reference either (tools/depressions.py:1536-1590; DESIGN.md 7)")
     inDEM_array, meta = raster_io.read_raster(inDEM_tif)
     ny, nx = inDEM_array.shape
     water_mask_vec = np.ravel(water_mask_array) if water_mask_array is not None else None
@@ -432,9 +468,15 @@ def initial_fill_carve(inDEM_tif, basename, outpath, fill_method, maxcost, radiu
         modDEM_vec = fill_shallow_pits(modDEM_vec, sfill, fillID_vec, diff_fill_array, fill_array,
                                        water_vec=water_mask_vec, verbose_print=verbose_print)
 
-    if sfill is None:                                                                         # :160-162
+    if watermask is not None:                                                                 # :163-180
+        modDEM_vec, DEMdiff_lake_vec = raise_lake_connected_pits(watermask, fillID_vec, modDEM_vec, inDEM_vec,
+                                                                 starttime=starttime, verbose_print=verbose_print)
+        raster_io.write_raster(os.path.join(outpath, f"{basename}_lakefill_DIFF.tif"),
+                               np.asarray(DEMdiff_lake_vec, np.float32).reshape(ny, nx), meta, nodata=nodataval)
+
+    if sfill is None and watermask is None:                                                   # :183-186
         modDEM_tif = inDEM_tif
-    else:                                                                                     # :163-185
+    else:                                                                                     # :187-199
         modDEM_array = np.asarray(modDEM_vec).reshape(ny, nx)
         modDEM_tif = os.path.join(outpath, f"{basename}_shallowfill.tif")
         raster_io.write_raster(modDEM_tif, modDEM_array.astype(np.float32), meta, nodata=nodataval)

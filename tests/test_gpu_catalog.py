@@ -113,3 +113,100 @@ def test_seg_stats_large_random(cuda):
     np.minimum.at(wmn, ids, vals)
     assert np.array_equal(mx.cpu().numpy(), wmx) and np.array_equal(mn.cpu().numpy(), wmn)
     np.testing.assert_allclose(sm.cpu().numpy(), np.bincount(ids, weights=vals.astype(np.float64), minlength=nseg + 1), rtol=1e-9, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_raise_lake_connected_pits_documented_semantics(tmp_path):
+    """tools/depressions.py:1534-1590 as documented: pits holding lake cells are raised to (lowest lake cell in the pit)
+    + 1 cm where they lie below it; pits without lake cells and cells outside pits stay; nothing happens with <= 20 lake
+    cells.  (Upstream's own intersection is accidental -- see the function's docstring -- so the check is against the
+    definition, written out in numpy.)"""
+    from pydrodem_b200 import raster_io
+    from pydrodem_b200.tools import depressions as dep
+    rng = np.random.default_rng(3)
+    ny, nx = 90, 120
+    dem = (rng.random((ny, nx)) * 5 + 100).astype(np.float32)
+    fid = np.zeros((ny, nx), np.int32)
+    fid[10:30, 10:40] = 1
+    fid[40:70, 20:60] = 2
+    fid[75:85, 90:110] = 3                      # no lake inside
+    water = np.zeros((ny, nx), np.uint8)
+    water[15:22, 15:30] = 1                     # inside pit 1
+    water[50:60, 30:50] = 1                     # inside pit 2
+    water[2:5, 100:110] = 1                     # outside every pit
+    water[60, 5] = 2                            # a river code: not a lake
+    dem[water == 1] += np.float32(2.5)          # water surfaces stand above much of the pits' ground
+    mod0 = dem.copy()
+    mod0[12, 12] += 50.0                        # an earlier stage already raised this cell: must be kept
+    want = mod0.ravel().copy()
+    d = dem.ravel()
+    for pit in (1, 2, 3):
+        cells = np.flatnonzero(fid.ravel() == pit)
+        lake_cells = cells[water.ravel()[cells] == 1]
+        if lake_cells.size == 0:
+            continue
+        lvl = d[lake_cells].min()
+        below = cells[d[cells] < lvl]
+        want[below] = lvl + np.float32(0.01)
+    got, diff = dep.raise_lake_connected_pits(water, fid.ravel(), mod0.ravel().copy(), dem.ravel(), verbose_print=False)
+    assert np.array_equal(got, want) and np.array_equal(diff, dem.ravel() - want)
+    assert (got != mod0.ravel()).sum() > 50 and got[12 * nx + 12] in (mod0[12, 12], want[12 * nx + 12])
+    assert np.array_equal(got.reshape(ny, nx)[75:85, 90:110], mod0[75:85, 90:110])
+    # the same through a GeoTIFF path, as initial_fill_carve passes it
+    p = str(tmp_path / "lakes.tif")
+    raster_io.write_raster(p, water, None, nodata=0)
+    got2, _ = dep.raise_lake_connected_pits(p, fid.ravel(), mod0.ravel().copy(), dem.ravel(), verbose_print=False)
+    assert np.array_equal(got2, want)
+    few = np.zeros((ny, nx), np.uint8)
+    few[15:17, 15:20] = 1                       # 10 lake cells: below the threshold of 20
+    got3, diff3 = dep.raise_lake_connected_pits(few, fid.ravel(), mod0.ravel().copy(), dem.ravel(), verbose_print=False)
+    assert np.array_equal(got3, mod0.ravel())
+
+
+GOLD_C4 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "catalog_c4_reference.npz")
+
+
+@pytest.mark.gpu
+def test_c4_recipe_catalog_selection_with_water_mask_matches_reference(oracle, cuda):
+    """BASELINE.json configs[3] at 1201^2 (synth.make_c4: flattened lakes, burned rivers and their water mask): the
+    reference's own build_pit_catalog / select_solution / apply_solution / fill_shallow_pits outputs
+    (tests/golden/make_catalog_c4_golden.py, 5254 pits, two threshold sets) against the GPU segmented reductions."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_catalog_c4_golden import derive
+    from pydrodem_b200.tools import depressions as dep
+    g = np.load(GOLD_C4)
+    z, water = g["z"], g["water"]
+    carve = z.copy().ravel()
+    carve[g["carve_idx"]] = g["carve_val"]
+    carve = carve.reshape(z.shape)
+    d = derive(z, carve)                       # oracle fill + scipy labels: what initial_fill_carve derives
+    v = {k: np.ravel(a) for k, a in d.items()}
+    DF, fillcells, carveonly, carvecells, carvefill = dep.build_pit_catalog(
+        z.ravel(), NODATA, carve.ravel(), v["diff_carve"], v["diff_fill"], v["fillID"], v["carveID"], v["carvefillID"],
+        verbose_print=False, carveout=False)
+    assert len(DF) == len(g["cat_maxfill"]) == 5254
+    for col in ("maxfill", "maxcarve", "maxfillbehind", "completecarve"):
+        assert np.array_equal(DF[col].to_numpy(), g[f"cat_{col}"]), col
+    for col in ("volfill", "volcarve", "volfillbehind"):
+        np.testing.assert_allclose(DF[col].to_numpy(), g[f"cat_{col}"], rtol=1e-5, atol=1e-5, err_msg=col)
+    for tag in ("a", "b"):
+        fvt, cvt, mcd = (float(x) for x in g[f"{tag}_thresholds"])
+        D2 = dep.select_solution(DF.copy(), fillcells, carvecells, carveonly, v["fill"], carve.ravel(), v["fillID"], v["carveID"],
+                                 fvt, cvt, mcd, maxcarve_factor=1.25, apply_shallow_fill=False, wall_array=None,
+                                 water_mask_array=water, sink_array=None)
+        got = D2["solution"].to_numpy()
+        want = g[f"{tag}_solution"]
+        assert np.array_equal(got, want), (tag, np.flatnonzero(got != want)[:10], got[got != want][:10], want[got != want][:10])
+        D3 = D2[D2.solution < 3000]
+        mod, mask = dep.apply_solution(D3, fillcells, carvecells, carvefill, z.ravel().copy(), v["fill"], carve.ravel())
+        want_mod = z.ravel().copy()
+        want_mod[g[f"{tag}_mod_idx"]] = g[f"{tag}_mod_val"]
+        want_mask = np.zeros(z.size, np.int16)
+        want_mask[g[f"{tag}_mask_idx"]] = g[f"{tag}_mask_val"]
+        assert np.array_equal(np.asarray(mod), want_mod) and np.array_equal(np.asarray(mask), want_mask), tag
+    shallow = dep.fill_shallow_pits(z.ravel().copy(), 1.0, v["fillID"], d["diff_fill"], d["fill"], water_vec=water.ravel(),
+                                    verbose_print=False)
+    want_sh = z.ravel().copy()
+    want_sh[g["shallow_idx"]] = g["shallow_val"]
+    assert np.array_equal(np.asarray(shallow), want_sh)
