@@ -28,16 +28,17 @@
 //         started only if it holds part of an open flat (first visits wake unvisited neighbours that
 //         share flat cells) and re-queued only if one of its rim cells can improve.
 #include <stdlib.h>
+#include <cooperative_groups.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 #define T HC_TILE
 #define TH (T + 2)
 #define NTHREADS 256
 #define HC_DIR_PENDING 254
 #define FL_LCAP 1024  // NOFLOW cells a tile may hold to take the light relaxation path
-#define FLAT_BATCH 3  // relaxation rounds enqueued per host read-back
-#define FL_LT 256     // threads of a light-path CTA
 
 // ================================================================================================
 // fast tier
@@ -582,60 +583,85 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
   }
 }
 
-// smem: z f32 | lo u32 (bit 31 = NOFLOW flag) | hi u32, pitch TP (odd)
+// Slow-tier visits.  Shared-memory window of a lake tile: z f32 | lo u32 | hi u32 | mask u16, pitch TP (odd).  Inside a
+// visit "not reached" is R_INF instead of 0, so that a distance can be lowered with one shared atomicMin.
 #define TP (TH + 1)
-#define R_NF 0x80000000u
-#define R_CHG 0x40000000u   // set when this visit changed the cell (write-back then needs no global re-read)
-#define R_VAL 0x3FFFFFFFu
-#define FLAT_SMEM (TH * TP * 12 + T * T * 2 + 16)
+#define R_INF 0x3FFFFFFFu
+#define M_NF 0x100u    // mask bits 0..7: equal-elevation neighbour k of the 3x3 window (row-major, centre skipped)
+#define M_CHG 0x200u   // set when this visit lowered the cell (write-back then needs no global re-read)
+#define FLAT_SMEM (TH * TP * 14 + 16)
 
-__device__ __forceinline__ int slow_relax(const float *sz, u32 *slo, u32 *shi, int ci) {
-  u32 w = slo[ci];
-  if (!(w & R_NF)) return 0;
-  float v = sz[ci];
-  u32 lo = w & R_VAL, hi = shi[ci];
-  u32 blo = lo ? lo : 0x7FFFFFFFu, bhi = hi ? hi : 0x7FFFFFFFu;
-#pragma unroll
-  for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-    for (int dc = -1; dc <= 1; dc++) {
-      if (!dr && !dc) continue;
-      int ni = ci + dr * TP + dc;
-      if (sz[ni] != v) continue;
-      u32 nw = slo[ni];
-      u32 nlo = nw & R_VAL;
-      if (nlo && nlo + 1 < blo) blo = nlo + 1;
-      if (nw & R_NF) {
-        u32 nhi = shi[ni];
-        if (nhi && nhi + 1 < bhi) bhi = nhi + 1;
-      }
-    }
+// One directional sweep of one distance field over the tile window (one warp, two lines per lane).  Direction D walks
+// the 64 lines of the tile (0: rows downwards, 1: rows upwards, 2: columns rightwards, 3: columns leftwards) and lowers
+// every cell of a line from its three neighbours on the PREVIOUS line, whose values the warp still holds in registers
+// (neighbouring lanes by shuffle, the two halo ends from shared memory).  The four directions together cover all eight
+// neighbours, so an iteration of all four that lowers nothing proves the fixed point; on an obstacle-free tile a
+// geodesic between two cells is a chessboard path that stays inside one direction's cone, so ONE iteration already
+// carries every halo value to every cell (the old whole-line Gauss-Seidel needed the same iterations at 27 shared
+// loads per cell and step).  Concurrent sweeps only ever lower a value (atomicMin), so none is lost.
+template <int D>
+__device__ __forceinline__ int cone_sweep(u32 *val, unsigned short *smk, const int lane) {
+  constexpr bool vert = D < 2;
+  constexpr int step = (D == 0 || D == 2) ? 1 : -1;
+  constexpr int bA = D == 0 ? 0 : (D == 1 ? 5 : (D == 2 ? 0 : 2));
+  constexpr int bB = D == 0 ? 1 : (D == 1 ? 6 : (D == 2 ? 3 : 4));
+  constexpr int bC = D == 0 ? 2 : (D == 1 ? 7 : (D == 2 ? 5 : 7));
+  const int j0 = 1 + 2 * lane, j1 = j0 + 1;
+  volatile u32 *v = val;
+  volatile unsigned short *mk = smk;
+#define CS_IDX(s_, j_) (vert ? (s_) * TP + (j_) : (j_) * TP + (s_))
+  int s = step > 0 ? 1 : T;
+  u32 p0 = v[CS_IDX(s - step, j0)], p1 = v[CS_IDX(s - step, j1)];
   int changed = 0;
-  if (blo == 0x7FFFFFFFu) blo = lo;
-  if (bhi != 0x7FFFFFFFu && bhi != hi) { shi[ci] = bhi; changed = 1; }
-  if (blo != lo) changed = 1;
-  if (changed) slo[ci] = R_NF | R_CHG | blo;
+  // the line's own values, masks and the previous line's two halo ends are fetched one step ahead, so that their
+  // shared-memory latency hides behind the shuffle / min chain of the step before (a value another sweep lowers in
+  // between is only seen a step late, which costs at most one more iteration)
+  u32 n_c0 = v[CS_IDX(s, j0)], n_c1 = v[CS_IDX(s, j1)], n_m0 = mk[CS_IDX(s, j0)], n_m1 = mk[CS_IDX(s, j1)];
+  u32 n_e0 = v[CS_IDX(s - step, 0)], n_e1 = v[CS_IDX(s - step, T + 1)];
+  for (int k = 0; k < T; k++, s += step) {
+    const int i0 = CS_IDX(s, j0), i1 = CS_IDX(s, j1);
+    u32 c0 = n_c0, c1 = n_c1;
+    const u32 m0 = n_m0, m1 = n_m1, e0 = n_e0, e1 = n_e1;
+    if (k + 1 < T) {
+      const int sn = s + step;
+      n_c0 = v[CS_IDX(sn, j0)]; n_c1 = v[CS_IDX(sn, j1)];
+      n_m0 = mk[CS_IDX(sn, j0)]; n_m1 = mk[CS_IDX(sn, j1)];
+      n_e0 = v[CS_IDX(s, 0)]; n_e1 = v[CS_IDX(s, T + 1)];
+    }
+    u32 lft = __shfl_up_sync(0xFFFFFFFFu, p1, 1), rgt = __shfl_down_sync(0xFFFFFFFFu, p0, 1);
+    if (lane == 0) lft = e0;
+    if (lane == 31) rgt = e1;
+    const u32 a = min(min(((m0 >> bA) & 1u) ? lft : R_INF, ((m0 >> bB) & 1u) ? p0 : R_INF), ((m0 >> bC) & 1u) ? p1 : R_INF) + 1u;
+    const u32 b = min(min(((m1 >> bA) & 1u) ? p0 : R_INF, ((m1 >> bB) & 1u) ? p1 : R_INF), ((m1 >> bC) & 1u) ? rgt : R_INF) + 1u;
+    if ((m0 & M_NF) && a < c0) { atomicMin(&val[i0], a); mk[i0] = (unsigned short)(m0 | M_CHG); c0 = a; changed = 1; }
+    if ((m1 & M_NF) && b < c1) { atomicMin(&val[i1], b); mk[i1] = (unsigned short)(m1 | M_CHG); c1 = b; changed = 1; }
+    p0 = c0;
+    p1 = c1;
+  }
+#undef CS_IDX
   return changed;
 }
 
-// one visit of tile (by, bx): load, relax to the local fixed point, write back, queue the neighbours that can improve
+// one visit of a lake tile (by, bx): load the window, relax to the local fixed point, write back, queue the neighbours
+// that can improve
 __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
                                            const uint8_t *__restrict__ active, u32 *__restrict__ list_out,
-                                           u32 *__restrict__ n_out, u32 *__restrict__ queued, uint8_t *__restrict__ visited,
-                                           int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw, int by, int bx,
-                                           int tx, int ty, unsigned char *smem) {
+                                           u32 *__restrict__ n_out, u32 *__restrict__ queued, const u32 stamp,
+                                           uint8_t *__restrict__ visited, int ny, int nx, float nodata,
+                                           unsigned long long *dbg, hc_rows rw, int by, int bx, int tx, int ty,
+                                           unsigned char *smem) {
   float *sz = (float *)smem;
   u32 *slo = (u32 *)(smem + TH * TP * 4);
   u32 *shi = (u32 *)(smem + TH * TP * 8);
-  unsigned short *list = (unsigned short *)(smem + TH * TP * 12);
+  unsigned short *smk = (unsigned short *)(smem + TH * TP * 12);
   __shared__ int s_side;
-  __shared__ u32 s_n;
   const int r0 = by * T, c0 = bx * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
   __shared__ uint8_t s_act[9], s_vis[9];
-  __syncthreads();  // the previous tile of this CTA is completely done with the shared arrays
-  if (tid == 0) { s_side = 0; s_n = 0; }
+  __syncthreads();  // the previous visit of this CTA is completely done with the shared arrays
+  const long long t_begin = clock64();
+  if (tid == 0) s_side = 0;
   if (tid < 9) {
     int yy = by + tid / 3 - 1, xx = bx + tid % 3 - 1;
     bool in = yy >= 0 && yy < ty && xx >= 0 && xx < tx;
@@ -648,72 +674,60 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
   const bool first = s_vis[4] == 0;
   if (tid == 0) visited[by * tx + bx] = 1;
 #pragma unroll 4
-  for (int i0 = 0; i0 < TH * TH; i0 += NTHREADS) {
-    const int i = i0 + tid;
-    const bool ivalid = i < TH * TH;
-    int lr = ivalid ? i / TH : 0, lc = ivalid ? i - lr * TH : 0;
-    int r = r0 + lr - 1, c = c0 + lc - 1;
+  for (int i = tid; i < TH * TH; i += NTHREADS) {
+    const int lr = i / TH, lc = i - lr * TH;
+    const int r = r0 + lr - 1, c = c0 + lc - 1;
     // halo cells of tiles outside the active set hold no state: treat as not in any flat
-    int ay = lr == 0 ? 0 : (lr == TH - 1 ? 2 : 1), ax = lc == 0 ? 0 : (lc == TH - 1 ? 2 : 1);
+    const int ay = lr == 0 ? 0 : (lr == TH - 1 ? 2 : 1), ax = lc == 0 ? 0 : (lc == TH - 1 ? 2 : 1);
     // (a band's halo rows hold the neighbouring band's state, refreshed between relaxations)
-    bool halo_row = (r == -1 && rw.top) || (r == ny && rw.bot);
-    bool inb = ivalid && c >= 0 && c < nx && ((r >= 0 && r < ny && s_act[ay * 3 + ax]) || halo_row);
-    long long g = inb ? (long long)r * nx + c : 0;
-    float v = __ldg(z + g);
+    const bool halo_row = (r == -1 && rw.top) || (r == ny && rw.bot);
+    const bool inb = c >= 0 && c < nx && ((r >= 0 && r < ny && s_act[ay * 3 + ax]) || halo_row);
+    const long long g = inb ? (long long)r * nx + c : 0;
+    const float v = __ldg(z + g);
     u32 lo = __ldcg(dlo + g);
     u32 hi = __ldcg(dhi + g);
     uint8_t f = __ldcg(nf + g);
-    if (!inb || !ivalid) { lo = 0; hi = 0; f = 0; }
-    if (f) lo |= R_NF;
-    // warp-aggregated append to the work list (one shared atomic per warp)
-    const bool want = f && lr >= 1 && lr <= T && lc >= 1 && lc <= T && r < ny;
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, want);
-    if (bal) {
-      const int lane = tid & 31;
-      u32 base = 0;
-      if (lane == 0) base = atomicAdd(&s_n, (u32)__popc(bal));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (want) list[base + (u32)__popc(bal & ((1u << lane) - 1u))] = (unsigned short)(lr * TP + lc);
-    }
-    if (ivalid) {
-      sz[lr * TP + lc] = (inb && v != nodata) ? v : qnan;
-      slo[lr * TP + lc] = lo;
-      shi[lr * TP + lc] = hi;
-    }
+    if (!inb) { lo = 0; hi = 0; f = 0; }
+    sz[lr * TP + lc] = (inb && v != nodata) ? v : qnan;
+    slo[lr * TP + lc] = lo ? lo : R_INF;
+    shi[lr * TP + lc] = hi ? hi : R_INF;
+    smk[lr * TP + lc] = (unsigned short)(f ? M_NF : 0u);
   }
   __syncthreads();
-  const u32 nlist = s_n;
-  if (!nlist) return;
-  int ever = 0, nsweeps = 0;
-  if (nlist * 4 > T * T) {
-    // dense flat (lake): Gauss-Seidel along whole lines, all four directions at once (thread t walks line
-    // t % T in direction t / T: rows ->, columns v, rows <-, columns ^), so one pass carries the distance
-    // front across the full tile in every axis direction; concurrent writers only ever lower a value.
-    const int line = 1 + tid % T, dirn = tid / T;
-    // a pass that changes nothing proves the fixed point (every cell was just re-evaluated)
-    for (;;) {
-      int changed = 0;
-      switch (dirn) {
-        case 0: for (int c = 1; c <= T; c++) changed |= slow_relax(sz, slo, shi, line * TP + c); break;
-        case 1: for (int r = 1; r <= T; r++) changed |= slow_relax(sz, slo, shi, r * TP + line); break;
-        case 2: for (int c = T; c >= 1; c--) changed |= slow_relax(sz, slo, shi, line * TP + c); break;
-        default: for (int r = T; r >= 1; r--) changed |= slow_relax(sz, slo, shi, r * TP + line); break;
+  // equal-elevation links of the own cells (NaN never compares equal: nodata and absent cells link to nothing)
+  for (int i = tid; i < T * T; i += NTHREADS) {
+    const int ci = ((i >> 6) + 1) * TP + (i & (T - 1)) + 1;
+    const float v = sz[ci];
+    u32 m = 0;
+    int k = 0;
+#pragma unroll
+    for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+      for (int dc = -1; dc <= 1; dc++) {
+        if (!dr && !dc) continue;
+        if (sz[ci + dr * TP + dc] == v) m |= 1u << k;
+        k++;
       }
-      nsweeps += 4;
-      if (!__syncthreads_or(changed)) break;
-      ever = 1;
-    }
-  } else {
-    // sparse: Jacobi over the compact list of pending cells
-    for (;;) {
-      int changed = 0;
-      for (u32 k = tid; k < nlist; k += NTHREADS) changed |= slow_relax(sz, slo, shi, list[k]);
-      nsweeps++;
-      if (!__syncthreads_or(changed)) break;
-      ever = 1;
-    }
+    smk[ci] = (unsigned short)(smk[ci] | m);
   }
-  if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); if (nlist * 4 > T * T) HC_DBG(5, 1); }
+  __syncthreads();
+  // warp w: field w & 1 (lo / hi), direction w >> 1
+  const int warp = tid >> 5, lane = tid & 31;
+  u32 *val = (warp & 1) ? shi : slo;
+  int ever = 0, nsweeps = 0;
+  for (;;) {
+    int changed;
+    switch (warp >> 1) {
+      case 0: changed = cone_sweep<0>(val, smk, lane); break;
+      case 1: changed = cone_sweep<1>(val, smk, lane); break;
+      case 2: changed = cone_sweep<2>(val, smk, lane); break;
+      default: changed = cone_sweep<3>(val, smk, lane); break;
+    }
+    nsweeps += 4;
+    if (!__syncthreads_or(changed)) break;
+    ever = 1;
+  }
+  if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); HC_DBG(5, 1); HC_DBG(10, clock64() - t_begin); HC_DBG(11, nsweeps / 4); }
   if (!ever && !first) return;
   // write back; a neighbouring tile is re-queued only if one of ITS rim cells (my halo) can actually improve
   // from a rim cell of mine that changed (distances only ever decrease, so a stale halo value can cause a
@@ -721,39 +735,37 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
   // moves on in any neighbour.
   int nb9 = 0;  // bit (dy+1)*3 + (dx+1)
   for (int i = tid; i < T * T; i += NTHREADS) {
-    int lr = i / T, lc = i - lr * T;
-    int r = r0 + lr, c = c0 + lc;
+    const int lr = i / T, lc = i - lr * T;
+    const int r = r0 + lr, c = c0 + lc;
     if (r >= ny || c >= nx) continue;
-    int ci = (lr + 1) * TP + lc + 1;
-    u32 w = slo[ci];
-    if (!(w & R_NF)) continue;
-    const bool chg = (w & R_CHG) != 0;
+    const int ci = (lr + 1) * TP + lc + 1;
+    const u32 m = smk[ci];
+    if (!(m & M_NF)) continue;
+    const bool chg = (m & M_CHG) != 0;
     if (!chg && !first) continue;
-    size_t g = (size_t)r * nx + c;
-    u32 lo = w & R_VAL, hi = shi[ci];
-    {
-      if (chg) {
-        dlo[g] = lo;
-        dhi[g] = hi;
-      }
-      if (lr == 0 || lc == 0 || lr == T - 1 || lc == T - 1) {
-        const float v = sz[ci];
+    const size_t g = (size_t)r * nx + c;
+    const u32 lo = slo[ci], hi = shi[ci];
+    if (chg) {
+      dlo[g] = lo == R_INF ? 0u : lo;
+      dhi[g] = hi == R_INF ? 0u : hi;
+    }
+    if (lr == 0 || lc == 0 || lr == T - 1 || lc == T - 1) {
+      int k = 0;
 #pragma unroll
-        for (int dr = -1; dr <= 1; dr++)
+      for (int dr = -1; dr <= 1; dr++)
 #pragma unroll
-          for (int dc = -1; dc <= 1; dc++) {
-            const int hr = lr + 1 + dr, hc = lc + 1 + dc;
-            if (!(hr == 0 || hr == TH - 1 || hc == 0 || hc == TH - 1)) continue;  // not a halo cell
-            const int ni = hr * TP + hc;
-            if (sz[ni] != v) continue;
-            const u32 nw = slo[ni];
-            if (!(nw & R_NF)) continue;
-            const u32 nlo = nw & R_VAL, nhi = shi[ni];
-            const int nb = (hr == 0 ? 0 : (hr == TH - 1 ? 2 : 1)) * 3 + (hc == 0 ? 0 : (hc == TH - 1 ? 2 : 1));
-            if ((chg && ((lo && (nlo == 0 || lo + 1 < nlo)) || (hi && (nhi == 0 || hi + 1 < nhi)))) || (first && !s_vis[nb]))
-              nb9 |= 1 << nb;
-          }
-      }
+        for (int dc = -1; dc <= 1; dc++) {
+          if (!dr && !dc) continue;
+          const int kk = k++;
+          const int hr = lr + 1 + dr, hc = lc + 1 + dc;
+          if (!(hr == 0 || hr == TH - 1 || hc == 0 || hc == TH - 1)) continue;  // not a halo cell
+          if (!((m >> kk) & 1u)) continue;                                      // not the same elevation
+          const int ni = hr * TP + hc;
+          if (!(smk[ni] & M_NF)) continue;
+          const u32 nlo = slo[ni], nhi = shi[ni];
+          const int nb = (hr == 0 ? 0 : (hr == TH - 1 ? 2 : 1)) * 3 + (hc == 0 ? 0 : (hc == TH - 1 ? 2 : 1));
+          if ((chg && (lo + 1u < nlo || hi + 1u < nhi)) || (first && !s_vis[nb])) nb9 |= 1 << nb;
+        }
     }
   }
   if (nb9) atomicOr(&s_side, nb9);
@@ -764,136 +776,238 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
     if (yy >= 0 && yy < ty && xx >= 0 && xx < tx && active[yy * tx + xx]) {
       // the first one to flag a tile appends it to the next round's queue
       const u32 t = (u32)(yy * tx + xx);
-      if (atomicExch(&queued[t], 1u) == 0u) list_out[atomicAdd(n_out, 1u)] = t;
+      if (atomicExch(&queued[t], stamp) != stamp) list_out[atomicAdd(n_out, 1u)] = t;
     }
   }
 }
 
-// Light path for tiles with at most FL_LCAP NOFLOW cells (most visits): no shared-memory window at all.  The
-// tile's compact cell list and neighbour masks were built at init; a 64-thread CTA relaxes those cells straight on
-// the L2-resident distance rasters (Jacobi sweeps with block votes), so a visit touches a few KB instead of staging
-// 57 KB, and 16+ CTAs per SM hide the L2 latency.  Same re-queue / wake rules as the window path.
-__global__ void __launch_bounds__(FL_LT)
-k_flat_relax_light(const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi, const uint8_t *__restrict__ active,
-                   const unsigned short *__restrict__ tlist, const uint8_t *__restrict__ tmask, const u32 *__restrict__ tcount,
-                   const u32 *__restrict__ list_in, const u32 *__restrict__ n_in, u32 *__restrict__ list_out,
-                   u32 *__restrict__ n_out, u32 *__restrict__ queued, u32 *__restrict__ next, uint8_t *visited, int ny, int nx,
-                   int tx, int ty, unsigned long long *dbg) {
-  __shared__ u32 s_q;
+// Light visit for tiles with at most FL_LCAP NOFLOW cells (most visits): no window.  The tile's compact cell list and
+// neighbour masks were built at init; the visit copies those cells' two distances into shared memory, resolves every
+// in-tile neighbour to its list position through a 64 x 64 position grid (an equal-elevation neighbour that is not
+// listed has a direction, i.e. it is a low edge: constant 1), folds the neighbours in other tiles -- fixed for the
+// visit -- into one constant per cell, and then runs the Jacobi sweeps entirely on shared memory (the first version
+// swept on the L2-resident rasters: eight dependent L2 round trips per cell and sweep).  Same re-queue / wake rules as
+// the window path.
+#define FL_PER (FL_LCAP / NTHREADS)
+__device__ __forceinline__ void relax_light(const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi, const uint8_t *__restrict__ active,
+                                            const unsigned short *__restrict__ tlist, const uint8_t *__restrict__ tmask,
+                                            const u32 cnt, u32 *__restrict__ list_out, u32 *__restrict__ n_out,
+                                            u32 *__restrict__ queued, const u32 stamp, uint8_t *visited, int ny, int nx, int tx,
+                                            int ty, unsigned long long *dbg, const u32 t, unsigned char *smem) {
+  unsigned short *grid = (unsigned short *)smem;        // [T * T] list position + 1 of a NOFLOW cell, else 0
+  volatile u32 *vlo = (volatile u32 *)(smem + T * T * 2);   // [FL_LCAP]
+  volatile u32 *vhi = vlo + FL_LCAP;
+  __shared__ u32 s_want;
   const int tid = threadIdx.x;
-  const u32 n = *n_in;
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_q = atomicAdd(next, 1u);
-    __syncthreads();
-    const u32 q = s_q;
-    if (q >= n) break;
-    const u32 t = list_in[q];
-    const u32 cnt = tcount[t];
-    if (cnt > FL_LCAP || cnt == 0) continue;   // the window kernel takes the big ones
-    const int by = (int)(t / tx), bx = (int)(t % tx);
-    const int r0 = by * T, c0 = bx * T;
-    const bool first = visited[t] == 0;
-    long long g[FL_LCAP / FL_LT];
-    u32 lo[FL_LCAP / FL_LT], hi[FL_LCAP / FL_LT], msk[FL_LCAP / FL_LT], li[FL_LCAP / FL_LT];
-    u32 chg = 0;
-#pragma unroll
-    for (int j = 0; j < FL_LCAP / FL_LT; j++) {
-      const u32 k = tid + j * FL_LT;
-      msk[j] = 0; li[j] = 0; g[j] = 0; lo[j] = hi[j] = 0;
-      if (k < cnt) {
-        li[j] = tlist[(size_t)t * FL_LCAP + k];
-        msk[j] = tmask[(size_t)t * FL_LCAP + k] | 0x100u;   // bit 8 = "this slot holds a cell"
-        g[j] = (long long)(r0 + (int)(li[j] >> 6)) * nx + (c0 + (int)(li[j] & 63u));
-        lo[j] = __ldcg(dlo + g[j]);
-        hi[j] = __ldcg(dhi + g[j]);
-      }
-    }
-    int nsweeps = 0;
-    for (;;) {
-      int changed = 0;
-#pragma unroll
-      for (int j = 0; j < FL_LCAP / FL_LT; j++) {
-        if (!(msk[j] & 0x100u)) continue;
-        u32 blo = lo[j] ? lo[j] : 0x7FFFFFFFu, bhi = hi[j] ? hi[j] : 0x7FFFFFFFu;
-        // all neighbour loads are issued before any is used: a visit is a chain of L2 round trips otherwise
-        u32 nlo[8], nhi[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const int kk = k + (k >= 4);                               // position in the 3x3 window
-          const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
-          const bool on = (msk[j] >> k) & 1u;
-          nlo[k] = on ? __ldcg(dlo + gn) : 0u;
-          nhi[k] = on ? __ldcg(dhi + gn) : 0u;                       // (dhi of a cell with a direction is 0)
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          if (nlo[k] && nlo[k] + 1 < blo) blo = nlo[k] + 1;
-          if (nhi[k] && nhi[k] + 1 < bhi) bhi = nhi[k] + 1;
-        }
-        if (blo != 0x7FFFFFFFu && blo != lo[j]) { lo[j] = blo; __stcg(dlo + g[j], blo); chg |= 1u << j; changed = 1; }
-        if (bhi != 0x7FFFFFFFu && bhi != hi[j]) { hi[j] = bhi; __stcg(dhi + g[j], bhi); chg |= 1u << j; changed = 1; }
-      }
-      nsweeps++;
-      if (!__syncthreads_or(changed)) break;
-    }
-    if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); HC_DBG(6, 1); }
-    // re-queue neighbours that can improve from a changed rim cell; on the first visit also wake the unvisited
-    // neighbours that hold more of this tile's flats
-    __threadfence();
-#pragma unroll
-    for (int j = 0; j < FL_LCAP / FL_LT; j++) {
-      if (!(msk[j] & 0x100u)) continue;
-      const bool c = (chg >> j) & 1u;
-      if (!c && !first) continue;
-      const int lr = (int)(li[j] >> 6), lc = (int)(li[j] & 63u);
-      if (lr != 0 && lc != 0 && lr != T - 1 && lc != T - 1) continue;
-      u32 m = msk[j] & 0xFFu;
-      while (m) {
-        const int k = __ffs(m) - 1;
-        m &= m - 1;
-        const int kk = k + (k >= 4);
-        const int nr = lr + kk / 3 - 1, nc = lc + kk % 3 - 1;
-        if (nr >= 0 && nr < T && nc >= 0 && nc < T) continue;   // inside this tile
-        const int yy = by + (nr < 0 ? -1 : (nr >= T ? 1 : 0)), xx = bx + (nc < 0 ? -1 : (nc >= T ? 1 : 0));
-        if (yy < 0 || yy >= ty || xx < 0 || xx >= tx) continue;  // a band's halo row: the exchange handles it
-        const u32 tt = (u32)(yy * tx + xx);
-        if (!active[tt]) continue;
-        const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
-        if (!__ldcg(nf + gn)) continue;
-        const u32 nlo = __ldcg(dlo + gn), nhi = __ldcg(dhi + gn);
-        const bool benefit = c && ((lo[j] && (nlo == 0 || lo[j] + 1 < nlo)) || (hi[j] && (nhi == 0 || hi[j] + 1 < nhi)));
-        if (benefit || (first && !visited[tt])) {
-          if (atomicExch(&queued[tt], 1u) == 0u) list_out[atomicAdd(n_out, 1u)] = tt;
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) visited[t] = 1;
+  const int by = (int)(t / tx), bx = (int)(t % tx);
+  const int r0 = by * T, c0 = bx * T;
+  __syncthreads();  // the previous visit of this CTA is completely done with the shared arrays
+  const long long t_begin = clock64();
+  {
+    uint4 *q = (uint4 *)grid;
+    for (int i = tid; i < T * T * 2 / 16; i += NTHREADS) q[i] = make_uint4(0, 0, 0, 0);
   }
+  if (tid == 0) s_want = 0;
+  const bool first = visited[t] == 0;
+  __syncthreads();
+  long long g[FL_PER];
+  u32 lo[FL_PER], hi[FL_PER], msk[FL_PER], ref[FL_PER][4];
+#pragma unroll
+  for (int j = 0; j < FL_PER; j++) {
+    const u32 k = tid + j * NTHREADS;
+    msk[j] = 0; g[j] = 0; lo[j] = hi[j] = R_INF;
+    if (k < cnt) {
+      const u32 li = tlist[(size_t)t * FL_LCAP + k];
+      msk[j] = tmask[(size_t)t * FL_LCAP + k] | 0x100u | (li << 16);   // bit 8 = "this slot holds a cell"
+      g[j] = (long long)(r0 + (int)(li >> 6)) * nx + (c0 + (int)(li & 63u));
+      const u32 a = __ldcg(dlo + g[j]), b = __ldcg(dhi + g[j]);
+      lo[j] = a ? a : R_INF;
+      hi[j] = b ? b : R_INF;
+      grid[li] = (unsigned short)(k + 1);
+      vlo[k] = lo[j];
+      vhi[k] = hi[j];
+    }
+  }
+  __syncthreads();
+  const long long t_l1 = clock64();
+  // neighbours: listed cells of the tile go to a packed queue of list positions (eight 16-bit slots, first free slot
+  // = 0xFFFF); everything else is constant during the visit and is folded into the cell's own value right away
+  u32 chg = 0;
+#pragma unroll
+  for (int j = 0; j < FL_PER; j++) {
+    ref[j][0] = ref[j][1] = ref[j][2] = ref[j][3] = 0xFFFFFFFFu;
+    if (!(msk[j] & 0x100u)) continue;
+    u32 elo = R_INF, ehi = R_INF;
+    const int lr = (int)(msk[j] >> 22), lc = (int)((msk[j] >> 16) & 63u);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (!((msk[j] >> k) & 1u)) continue;
+      const int kk = k + (k >= 4);                               // position in the 3x3 window
+      const int nr = lr + kk / 3 - 1, nc = lc + kk % 3 - 1;
+      // (a band's halo row can lie inside the tile's footprint: that cell belongs to the other band, it is not listed)
+      if (nr >= 0 && nr < T && nc >= 0 && nc < T && r0 + nr < ny) {
+        const u32 pos = grid[nr * T + nc];
+        if (pos) {
+          ref[j][3] = __funnelshift_l(ref[j][2], ref[j][3], 16);
+          ref[j][2] = __funnelshift_l(ref[j][1], ref[j][2], 16);
+          ref[j][1] = __funnelshift_l(ref[j][0], ref[j][1], 16);
+          ref[j][0] = (ref[j][0] << 16) | (pos - 1u);
+        } else elo = min(elo, 2u);                               // a low edge (lo = 1) of the same elevation
+      } else {
+        const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
+        const u32 a = __ldcg(dlo + gn), b = __ldcg(dhi + gn);    // (dhi of a cell with a direction is 0)
+        if (a) elo = min(elo, a + 1u);
+        if (b) ehi = min(ehi, b + 1u);
+      }
+    }
+    const u32 k = tid + j * NTHREADS;
+    if (elo < lo[j]) { lo[j] = elo; vlo[k] = elo; chg |= 1u << j; }
+    if (ehi < hi[j]) { hi[j] = ehi; vhi[k] = ehi; chg |= 1u << j; }
+    if ((ref[j][0] & 0xFFFFu) == 0xFFFFu) msk[j] |= 0x200u;     // bit 9: no listed neighbour, nothing left to relax
+  }
+  int nsweeps = 0;
+  const long long t_l2 = clock64();
+  __syncthreads();
+  // Push relaxation: a cell whose value dropped offers value + 1 to its listed neighbours (shared atomicMin, only when it
+  // lowers them), so a sweep costs work only where the front is; the first sweep offers every reached cell once.  (The
+  // pull form re-read all eight neighbours of every cell in every sweep: 16 shared loads per cell and sweep.)  A sweep
+  // that lowers nothing ends the visit: cells that did not offer have not changed since their last offer, and their
+  // neighbours only ever decrease.
+  u32 push = 0;
+#pragma unroll
+  for (int j = 0; j < FL_PER; j++)
+    if ((msk[j] & 0x300u) == 0x100u && (lo[j] != R_INF || hi[j] != R_INF)) push |= 1u << j;
+  for (;;) {
+    int changed = 0;
+#pragma unroll
+    for (int j = 0; j < FL_PER; j++) {
+      if (!((push >> j) & 1u)) continue;
+      const u32 nl = lo[j] + 1u, nh = hi[j] + 1u;
+      const u32 own = tid + j * NTHREADS;
+      // all sixteen loads are issued before any is looked at (absent slots read the cell's own slot)
+      u32 rk[8], cl[8], ch[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        rk[i] = (ref[j][i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+        const u32 at = rk[i] == 0xFFFFu ? own : rk[i];
+        cl[i] = vlo[at];
+        ch[i] = vhi[at];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (rk[i] == 0xFFFFu) continue;
+        if (cl[i] > nl) { atomicMin((u32 *)&vlo[rk[i]], nl); changed = 1; }
+        if (ch[i] > nh) { atomicMin((u32 *)&vhi[rk[i]], nh); changed = 1; }
+      }
+    }
+    nsweeps++;
+    if (!__syncthreads_or(changed)) break;
+    push = 0;
+#pragma unroll
+    for (int j = 0; j < FL_PER; j++) {
+      if (!(msk[j] & 0x100u)) continue;
+      const u32 k = tid + j * NTHREADS;
+      const u32 a = vlo[k], b = vhi[k];
+      if (a < lo[j] || b < hi[j]) {
+        lo[j] = a; hi[j] = b;
+        chg |= 1u << j;
+        if (!(msk[j] & 0x200u)) push |= 1u << j;
+      }
+    }
+  }
+  const long long t_l3 = clock64();
+  if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); HC_DBG(6, 1); HC_DBG(12, cnt <= 64); HC_DBG(13, cnt <= 128); HC_DBG(14, cnt <= 256); HC_DBG(15, cnt); }
+#pragma unroll
+  for (int j = 0; j < FL_PER; j++)
+    if ((chg >> j) & 1u) {
+      __stcg(dlo + g[j], lo[j] == R_INF ? 0u : lo[j]);
+      __stcg(dhi + g[j], hi[j] == R_INF ? 0u : hi[j]);
+    }
+  // re-queue neighbours that can improve from a changed rim cell; on the first visit also wake the unvisited
+  // neighbours that hold more of this tile's flats (votes are collected in shared memory, one thread per neighbour
+  // tile then does the global queue operation)
+  u32 want = 0;
+#pragma unroll
+  for (int j = 0; j < FL_PER; j++) {
+    if (!(msk[j] & 0x100u)) continue;
+    const bool c = (chg >> j) & 1u;
+    if (!c && !first) continue;
+    const int lr = (int)(msk[j] >> 22), lc = (int)((msk[j] >> 16) & 63u);
+    if (lr != 0 && lc != 0 && lr != T - 1 && lc != T - 1) continue;
+    u32 m = msk[j] & 0xFFu;
+    while (m) {
+      const int k = __ffs(m) - 1;
+      m &= m - 1;
+      const int kk = k + (k >= 4);
+      const int nr = lr + kk / 3 - 1, nc = lc + kk % 3 - 1;
+      if (nr >= 0 && nr < T && nc >= 0 && nc < T) continue;   // inside this tile
+      const int dy = nr < 0 ? -1 : (nr >= T ? 1 : 0), dx = nc < 0 ? -1 : (nc >= T ? 1 : 0);
+      const int yy = by + dy, xx = bx + dx;
+      if (yy < 0 || yy >= ty || xx < 0 || xx >= tx) continue;  // a band's halo row: the exchange handles it
+      const u32 tt = (u32)(yy * tx + xx);
+      if (!active[tt]) continue;
+      const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
+      const u32 f = __ldcg(nf + gn), a = __ldcg(dlo + gn), b = __ldcg(dhi + gn);
+      if (!f) continue;
+      const u32 nlo = a ? a : R_INF, nhi = b ? b : R_INF;
+      const bool benefit = c && (lo[j] + 1u < nlo || hi[j] + 1u < nhi);
+      if (benefit || (first && !visited[tt])) want |= 1u << ((dy + 1) * 3 + dx + 1);
+    }
+  }
+  if (want) atomicOr(&s_want, want);
+  __syncthreads();
+  if (tid < 9 && ((s_want >> tid) & 1u)) {
+    const u32 tt = (u32)((by + tid / 3 - 1) * tx + bx + tid % 3 - 1);
+    if (atomicExch(&queued[tt], stamp) != stamp) list_out[atomicAdd(n_out, 1u)] = tt;
+  }
+  if (tid == 0) { visited[t] = 1; HC_DBG(9, clock64() - t_begin); }
 }
 
-// persistent form: the CTAs walk the queue of dirty tiles (a full-grid launch spends most of its time on
-// CTAs that find their tile clean)
-__global__ void __launch_bounds__(NTHREADS)
+// The slow tier's round loop, on the device: persistent CTAs (cooperative launch) walk the queue of dirty tiles with
+// dynamic fetch (tile costs differ by orders of magnitude), a grid-wide barrier ends the round, the queue the visits
+// filled becomes the next round's input, until a round queues nothing.  ctl: [0] n(qA) [1] n(qB) [2..3] fetch counters.
+// A tile is appended to the next queue by the first visit that stamps it with the round's number (`queued` holds 0 or 1
+// on entry -- 1 for tiles the caller queued -- and rounds stamp from 2 on, so no per-round clearing is needed).
+__global__ void __launch_bounds__(NTHREADS, 3)
 k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
-             const uint8_t *__restrict__ active, const u32 *__restrict__ list_in, const u32 *__restrict__ n_in,
-             u32 *__restrict__ list_out, u32 *__restrict__ n_out, u32 *__restrict__ queued, u32 *__restrict__ next,
-             uint8_t *__restrict__ visited, const u32 *__restrict__ tcount, int ny, int nx, float nodata,
-             unsigned long long *dbg, hc_rows rw, int tx, int ty) {
+             const uint8_t *__restrict__ active, u32 *qA, u32 *qB, u32 *ctl, u32 *__restrict__ queued,
+             uint8_t *visited, const unsigned short *__restrict__ tlist, const uint8_t *__restrict__ tmask,
+             const u32 *__restrict__ tcount, int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw, int tx, int ty) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ u32 s_q;
-  const u32 n = *n_in;
-  for (;;) {
-    // dynamic fetch: tile costs differ by orders of magnitude (a lake tile vs one with a few pits)
-    __syncthreads();
-    if (threadIdx.x == 0) s_q = atomicAdd(next, 1u);
-    __syncthreads();
-    const u32 q = s_q;
-    if (q >= n) break;
-    const u32 t = list_in[q];
-    if (tcount[t] <= FL_LCAP) continue;   // the light kernel takes the small ones
-    relax_tile(z, nf, dlo, dhi, active, list_out, n_out, queued, visited, ny, nx, nodata, dbg, rw, (int)(t / tx), (int)(t % tx), tx, ty, smem);
+  cg::grid_group grid = cg::this_grid();
+  u32 *lin = qA, *lout = qB;
+  for (u32 it = 0;; it++) {
+    // three rotating counter slots: this round's input count, the count the visits build for the next round, and the
+    // slot after that, which nobody touches during this round and which is cleared here for the round after
+    volatile u32 *nin = ctl + it % 3u;
+    u32 *nout = ctl + (it + 1u) % 3u, *fetch = ctl + 3 + it % 3u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[(it + 2u) % 3u] = 0u; ctl[3 + (it + 2u) % 3u] = 0u; }
+    const u32 n = *nin;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && it < 23u) {   // trace (HC_TRACE): tiles and start time of every round
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      ctl[8 + 2 * it] = n;
+      ctl[9 + 2 * it] = (u32)ns;
+    }
+    if (!n) break;
+    const u32 stamp = it + 2u;
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_q = atomicAdd(fetch, 1u);
+      __syncthreads();
+      const u32 q = s_q;
+      if (q >= n) break;
+      const u32 t = __ldcg(lin + q);
+      const u32 cnt = tcount[t];
+      if (!cnt) continue;
+      if (cnt <= FL_LCAP)
+        relax_light(nf, dlo, dhi, active, tlist, tmask, cnt, lout, nout, queued, stamp, visited, ny, nx, tx, ty, dbg, t, smem);
+      else
+        relax_tile(z, nf, dlo, dhi, active, lout, nout, queued, stamp, visited, ny, nx, nodata, dbg, rw, (int)(t / tx), (int)(t % tx), tx, ty, smem);
+    }
+    grid.sync();
+    u32 *sw = lin; lin = lout; lout = sw;
   }
 }
 
@@ -1053,45 +1167,40 @@ static int flats_slow_init(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   return HC_OK;
 }
 
-// relax until the queue runs dry; on return queue A (the next call's input) is empty and clean
+// relax until the queue runs dry (all rounds in ONE cooperative launch, no host read-back); on return queue A (the next
+// call's input) is empty and clean
 static int flats_relax_loop(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   hc_band_state *bs = &ctx->band;
   const int64_t ny = bs->nb, nx = bs->nx;
-  const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
+  int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t tiles = (size_t)tx * ty;
-  const unsigned grid = (unsigned)(tiles < (size_t)ctx->sm_count * 3 ? tiles : (size_t)ctx->sm_count * 3);
-  const unsigned lgrid = (unsigned)(tiles < (size_t)ctx->sm_count * 24 ? tiles : (size_t)ctx->sm_count * 24);
-  for (int it = 0;; it++) {
-    if (it > 1000000) { hc_set_error("flats: relaxation did not converge"); return HC_ERR_INTERNAL; }
-    // FLAT_BATCH rounds are enqueued back to back before the host looks at the queue length again (a round on an
-    // empty queue costs a few microseconds; a read-back costs a synchronisation — and, on a multi-GPU run, a point
-    // where one delayed rank stalls all the others)
-    for (int sub = 0; sub < FLAT_BATCH; sub++) {
-      // queue A holds this round's tiles, queue B collects the next round's
-      HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
-      HC_CUDA(cudaMemsetAsync(bs->flag + 9, 0, 12, st));   // n(qB) and the two fetch counters [10], [11]
-      // small tiles (<= FL_LCAP NOFLOW cells) on the light path, the rest through the shared-memory window; the two
-      // kernels share the queue and run side by side (the light one on the context's auxiliary stream)
-      HC_CUDA(cudaEventRecord(ctx->ev_fork, st));
-      HC_CUDA(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
-      k_flat_relax_light<<<lgrid, FL_LT, 0, ctx->s_aux>>>(bs->nf, bs->dlo, bs->dhi, bs->active, bs->tlist, bs->tmask, bs->tcount,
-                                                          bs->qA, bs->flag + 8, bs->qB, bs->flag + 9, bs->queued, bs->flag + 11,
-                                                          bs->visited, (int)ny, (int)nx, tx, ty, ctx->d_dbg);
-      ctx->launches++;
-      HC_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_aux));
-      HC_PROF(ctx, st, "k_flat_relax");
-      k_flat_relax<<<grid, NTHREADS, FLAT_SMEM, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->active, bs->qA, bs->flag + 8, bs->qB,
-                                                      bs->flag + 9, bs->queued, bs->flag + 10, bs->visited, bs->tcount, (int)ny,
-                                                      (int)nx, bs->nodata, ctx->d_dbg, rw, tx, ty);
-      HC_LAUNCH_CHECK(ctx);
-      HC_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-      // next round: B becomes A
-      HC_CUDA(cudaMemcpyAsync(bs->flag + 8, bs->flag + 9, 4, cudaMemcpyDeviceToDevice, st));
-      u32 *t = bs->qA; bs->qA = bs->qB; bs->qB = t;
-    }
-    HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag + 8, 4, cudaMemcpyDeviceToHost, st));
+  static int max_blocks = 0;
+  if (!max_blocks) {
+    int per_sm = 0;
+    HC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_relax, NTHREADS, FLAT_SMEM));
+    max_blocks = per_sm * ctx->sm_count;
+    if (max_blocks < 1) { hc_set_error("flats: cooperative launch: no resident block"); return HC_ERR_CUDA; }
+  }
+  const unsigned grid = (unsigned)(tiles < (size_t)max_blocks ? tiles : (size_t)max_blocks);
+  int iny = (int)ny, inx = (int)nx;
+  u32 *ctl = bs->flag + 8;
+  void *args[] = {(void *)&bs->fz, (void *)&bs->nf, (void *)&bs->dlo, (void *)&bs->dhi, (void *)&bs->active, (void *)&bs->qA,
+                  (void *)&bs->qB, (void *)&ctl, (void *)&bs->queued, (void *)&bs->visited, (void *)&bs->tlist,
+                  (void *)&bs->tmask, (void *)&bs->tcount, (void *)&iny, (void *)&inx, (void *)&bs->nodata, (void *)&ctx->d_dbg,
+                  (void *)&rw, (void *)&tx, (void *)&ty};
+  HC_PROF(ctx, st, "k_flat_relax");
+  HC_CUDA(cudaLaunchCooperativeKernel((void *)k_flat_relax, dim3(grid), dim3(NTHREADS), args, FLAT_SMEM, st));
+  HC_LAUNCH_CHECK(ctx);
+  if (getenv("HC_TRACE")) {
+    u32 h[48];
+    HC_CUDA(cudaMemcpyAsync(h, ctl + 8, sizeof h, cudaMemcpyDeviceToHost, st));
     HC_CUDA(cudaStreamSynchronize(st));
-    if (!ctx->h_mail[0]) break;
+    fprintf(stderr, "[flats] rounds (tiles @ us):");
+    for (int i = 0; i < 24; i++) {
+      fprintf(stderr, " %u@%.0f", h[2 * i], (double)(h[2 * i + 1] - h[1]) * 1e-3);
+      if (!h[2 * i]) break;
+    }
+    fprintf(stderr, "\n");
   }
   HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));  // put_halos may queue seam tiles for the next call
   return HC_OK;
