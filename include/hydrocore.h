@@ -226,6 +226,19 @@ int hc_dtm_select_dev(hc_ctx *ctx, const float *dem, const float *z9, const floa
                       const float *z3, const int8_t *slope0, const float *curv, const uint8_t *swo,
                       const uint8_t *edm, const uint8_t *tx, const uint8_t *artifact, float *zf, int8_t *filt,
                       int64_t n, float cbreak0, float cbreak1, const int *slopebreaks5, void *stream);
+/* The same block fused (models/dem_noise_removal.py:397-471): two tile passes over the DEM, no smoothed raster in HBM.
+ * hc_dtm_pre_dev: curvature_D2 (geometric, float32) and slope_D4 / slope_D2 (int8 degrees) of the 5x5-smoothed DEM
+ * (:405-410) plus sums[0] = sum, sums[1] = sum of squares (float64, HOST) of the curvature over rows [row_lo, row_hi)
+ * -- np.std(curvature) of :413; curv / slope0 may be NULL (sums only).  hc_dtm_apply_dev: the four DW smoothings
+ * (:399-402) and the selection (:414-471) -> Zf and the filter code.  kernels_host = the 9x9, 7x7, 5x5 and 3x3 kernels
+ * back to back (81 + 49 + 25 + 9 float32, HOST pointer); cbreak0/1 = c * sigma as np.float32.  Results are bit-identical
+ * to the unfused calls above. */
+int hc_dtm_pre_dev(hc_ctx *ctx, const float *dem, const float *kernels_host, float *curv, int8_t *slope0, int64_t ny,
+                   int64_t nx, double dx, double dy, int d4, int64_t row_lo, int64_t row_hi, double *sums, void *stream);
+int hc_dtm_apply_dev(hc_ctx *ctx, const float *dem, const float *kernels_host, const float *curv, const int8_t *slope0,
+                     const uint8_t *swo, const uint8_t *edm, const uint8_t *tx, const uint8_t *artifact, float *zf,
+                     int8_t *filt, int64_t ny, int64_t nx, float cbreak0, float cbreak1, const int *slopebreaks5,
+                     void *stream);
 
 /* ---- Row-band sharding (BASELINE.json configs[2]: one 40000^2 DEM over 2/4/8 GPUs) ----
  * A band owns rows [0, nb) of its slice; its rasters carry ONE halo row above (row -1) when

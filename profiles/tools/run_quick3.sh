@@ -1,3 +1,6 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bands.py -m gpu -x -q > gpurun_out/t_par.log 2>&1; tail -n 3 gpurun_out/t_par.log
-HC_NO_ACC_OVERLAP=1 timeout 300 python profiles/tools/chain_profile.py 10801 2 > gpurun_out/prof_c2_noov.json 2> gpurun_out/prof_c2.err; cat gpurun_out/prof_c2_noov.json | cut -c1-800; tail -n 3 gpurun_out/prof_c2.err
-HC_NO_ACC_OVERLAP=1 timeout 300 python profiles/tools/chain_profile.py 10801 2 c4 > gpurun_out/prof_c4_noov.json 2> gpurun_out/prof_c4.err; cat gpurun_out/prof_c4_noov.json | cut -c1-800; tail -n 3 gpurun_out/prof_c4.err
+timeout 600 python -m pytest tests/test_gpu_stencils.py tests/test_gpu_veg.py tests/test_gpu_water.py -m gpu -x -q > gpurun_out/t_st.log 2>&1; tail -n 5 gpurun_out/t_st.log
+timeout 600 python bench.py --workload c5 > gpurun_out/bench_c5.json 2> gpurun_out/c5.err; tail -c 400 gpurun_out/c5.err; python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench_c5.json").read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","ms_per_step")}, d.get("kernels"))
+PY

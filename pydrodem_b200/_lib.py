@@ -71,6 +71,9 @@ SIGNATURES = {
                                            ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(ctypes.c_int),
                                            c_vp]),
     "hc_dtm_select_dev": (ctypes.c_int, [c_vp] + [c_vp] * 13 + [c_i64, c_f32, c_f32, c_vp, c_vp]),
+    "hc_dtm_pre_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_f64, ctypes.c_int, c_i64, c_i64,
+                                      ctypes.POINTER(c_f64), c_vp]),
+    "hc_dtm_apply_dev": (ctypes.c_int, [c_vp] + [c_vp] * 10 + [c_i64, c_i64, c_f32, c_f32, c_vp, c_vp]),
     "hc_fill_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int]),
     "hc_fill_d8_accum_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64,
                                              c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),

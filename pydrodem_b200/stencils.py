@@ -194,12 +194,57 @@ def dtm_select(dem, z9, z7, z5, z3, slope0, curv, sigma, curvebreaks=(1.0, 2.5),
     return zf, filt
 
 
-def smooth_core(dem, dx, dy, gdir=4, fweights=None, slopebreaks=(0, 2, 6, 15, 30), curvebreaks=(1.0, 2.5), swo=None,
-                edm=None, tx=None, artifact=None):
-    """Smoothing core of CreateDTM.run_tile (models/dem_noise_removal.py:397-476), device resident:
-    four DW smoothings, slope/curvature of the 5x5 result, global sigma, filter selection, final slope.
-    Returns (Zf float32, filter_array int8, slope_array int8)."""
+def _dw_kernels32(fweights=None):
+    fweights = fweights or [DW_WEIGHTS[9], DW_WEIGHTS[7], DW_WEIGHTS[5], DW_WEIGHTS[3]]
+    ks = [build_kernel(w, dtype=np.float32, normalize=True) for w in fweights]
+    if [k.shape for k in ks] != [(9, 9), (7, 7), (5, 5), (3, 3)]:
+        return None, ks
+    return np.ascontiguousarray(np.concatenate([np.asarray(k, dtype=np.float64).astype(np.float32).ravel() for k in ks])), ks
+
+
+def dtm_pre(dem, k32, dx, dy, gdir=4, row_lo=0, row_hi=None, rasters=True):
+    """First fused pass (hc_dtm_pre_dev): curvature_D2 and slope_D4 / slope_D2 of the 5x5-smoothed DEM without the
+    smoothed raster, and the float64 (sum, sum of squares) of the curvature over rows [row_lo, row_hi) that
+    np.std(curvature) of models/dem_noise_removal.py:413 needs.  Returns (curv, slope0, s1, s2)."""
     import torch
+    _ensure_thresholds(dem.device.index or 0)
+    out = (ctypes.c_double * 2)()
+    ny, nx = dem.shape
+    curv = torch.empty_like(dem) if rasters else None
+    slope0 = torch.empty(dem.shape, dtype=torch.int8, device=dem.device) if rasters else None
+    with torch.cuda.device(dem.device):
+        _lib.check(_lib.load().hc_dtm_pre_dev(_lib.context(dem.device.index or 0), _tp(dem), ctypes.c_void_p(k32.ctypes.data),
+                                              _tp(curv), _tp(slope0), ny, nx, float(dx), float(dy), 1 if gdir == 4 else 0,
+                                              int(row_lo), int(ny if row_hi is None else row_hi), out, _stream(dem)),
+                   "hc_dtm_pre_dev")
+    return curv, slope0, float(out[0]), float(out[1])
+
+
+def dtm_apply(dem, k32, curv, slope0, sigma, curvebreaks=(1.0, 2.5), slopebreaks=(0, 2, 6, 15, 30), swo=None, edm=None,
+              tx=None, artifact=None):
+    """Second fused pass (hc_dtm_apply_dev): the four smoothings and the selection block of CreateDTM.run_tile
+    (:399-402, :414-471) in one tile pass -> (Zf, filter code)."""
+    import torch
+    masks = [None if m is None else _to_dev(np.asarray(m, np.uint8) if not _is_torch(m) else m, np.uint8)[0]
+             for m in (swo, edm, tx, artifact)]
+    zf = torch.empty_like(dem)
+    filt = torch.empty(dem.shape, dtype=torch.int8, device=dem.device)
+    cb = [np.float32(c) * np.float32(sigma) for c in curvebreaks]  # np.float32 scalars, as in the reference
+    sb = (ctypes.c_int * 5)(*[int(v) for v in slopebreaks])
+    with torch.cuda.device(dem.device):
+        _lib.check(_lib.load().hc_dtm_apply_dev(_lib.context(dem.device.index or 0), _tp(dem), ctypes.c_void_p(k32.ctypes.data),
+                                                _tp(curv), _tp(slope0), _tp(masks[0]), _tp(masks[1]), _tp(masks[2]),
+                                                _tp(masks[3]), _tp(zf), _tp(filt), dem.shape[0], dem.shape[1],
+                                                float(cb[0]), float(cb[1]), ctypes.cast(sb, ctypes.c_void_p), _stream(dem)),
+                   "hc_dtm_apply_dev")
+        torch.cuda.current_stream(dem.device).synchronize()  # k32 is host memory read by the async copy
+    return zf, filt
+
+
+def smooth_core_unfused(dem, dx, dy, gdir=4, fweights=None, slopebreaks=(0, 2, 6, 15, 30), curvebreaks=(1.0, 2.5), swo=None,
+                        edm=None, tx=None, artifact=None):
+    """The core as a chain of the single-purpose calls (every intermediate raster in HBM): the form the fused path is
+    checked against, and the path for filter sets other than the four DW kernels."""
     host = not _is_torch(dem)
     d = _to_dev(dem, np.float32)[0]
     fweights = fweights or [DW_WEIGHTS[9], DW_WEIGHTS[7], DW_WEIGHTS[5], DW_WEIGHTS[3]]
@@ -211,6 +256,30 @@ def smooth_core(dem, dx, dy, gdir=4, fweights=None, slopebreaks=(0, 2, 6, 15, 30
     sigma32 = np.float32(sigma)
     zf, filt = dtm_select(d, zs[0], zs[1], zs[2], zs[3], slope0, curv, sigma32, curvebreaks, slopebreaks, swo, edm, tx,
                           artifact)
+    slope = (slope_D4 if gdir == 4 else slope_D2)(zf, dx, dy)
+    if host:
+        return zf.cpu().numpy(), filt.cpu().numpy(), slope.cpu().numpy()
+    return zf, filt, slope
+
+
+def smooth_core(dem, dx, dy, gdir=4, fweights=None, slopebreaks=(0, 2, 6, 15, 30), curvebreaks=(1.0, 2.5), swo=None,
+                edm=None, tx=None, artifact=None):
+    """Smoothing core of CreateDTM.run_tile (models/dem_noise_removal.py:397-476), device resident:
+    four DW smoothings, slope/curvature of the 5x5 result, global sigma, filter selection, final slope -- as two fused
+    tile passes over the DEM (curvature + slope of the 5x5 smoothing with the sigma sums; then the smoothings + selection)
+    and the slope of Zf.
+    Returns (Zf float32, filter_array int8, slope_array int8)."""
+    import torch
+    k32, _ = _dw_kernels32(fweights)
+    if k32 is None:
+        return smooth_core_unfused(dem, dx, dy, gdir, fweights, slopebreaks, curvebreaks, swo, edm, tx, artifact)
+    host = not _is_torch(dem)
+    d = _to_dev(dem, np.float32)[0]
+    d = _tdev(d, torch.float32, "smooth_core")
+    curv, slope0, s1, s2 = dtm_pre(d, k32, dx, dy, gdir)
+    sigma = _sigma_from_sums(d.numel(), s1, s2)
+    zf, filt = dtm_apply(d, k32, curv, slope0, np.float32(sigma), curvebreaks, slopebreaks, swo, edm, tx, artifact)
+    del curv, slope0
     slope = (slope_D4 if gdir == 4 else slope_D2)(zf, dx, dy)
     if host:
         return zf.cpu().numpy(), filt.cpu().numpy(), slope.cpu().numpy()
@@ -246,22 +315,17 @@ class BandSmoother:
         self.hi = dem_h.shape[0] - (SMOOTH_HALO if self.bot else 0)
 
     def stage1(self):
-        d = self.d
-        ws = [DW_WEIGHTS[9], DW_WEIGHTS[7], DW_WEIGHTS[5], DW_WEIGHTS[3]]
-        self.zs = dw_smooth4(d, [build_kernel(w, dtype=np.float32, normalize=True) for w in ws])
-        sl = slope_D4 if self.gdir == 4 else slope_D2
-        self.slope0 = sl(self.zs[2], self.dx, self.dy)
-        self.curv = curvature_D2(self.zs[2], self.dx, self.dy)
-        own = self.curv[self.lo:self.hi]
-        s1, _ = _sum_shifted(own, 0.0)
-        return own.numel(), s1
+        self.k32, _ = _dw_kernels32()
+        self.curv, self.slope0, self.s1, self.s2 = dtm_pre(self.d, self.k32, self.dx, self.dy, self.gdir, self.lo, self.hi)
+        self.n = (self.hi - self.lo) * self.d.shape[1]
+        return self.n, self.s1
 
     def stage2(self, mean):
-        return _sum_shifted(self.curv[self.lo:self.hi], mean)
+        # sum(x - m), sum((x - m)^2) from the unshifted float64 sums
+        return self.s1 - self.n * mean, self.s2 - 2.0 * mean * self.s1 + self.n * mean * mean
 
     def finish(self, sigma):
-        zf, filt = dtm_select(self.d, self.zs[0], self.zs[1], self.zs[2], self.zs[3], self.slope0, self.curv,
-                              np.float32(sigma), self.cb, self.sb)
+        zf, filt = dtm_apply(self.d, self.k32, self.curv, self.slope0, np.float32(sigma), self.cb, self.sb)
         sl = slope_D4 if self.gdir == 4 else slope_D2
         slope = sl(zf, self.dx, self.dy)
         return zf[self.lo:self.hi], filt[self.lo:self.hi], slope[self.lo:self.hi]

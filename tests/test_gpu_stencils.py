@@ -111,3 +111,25 @@ def test_smoothing_core_row_bands_match_whole_raster(gold, cuda, nbands):
     assert np.array_equal(bfilt, filt)
     assert np.array_equal(bzf, zf)
     assert np.array_equal(bslope, slope)
+
+
+@pytest.mark.parametrize("shape", [(230, 190), (64, 64), (65, 129), (1, 40), (37, 1), (5, 5), (300, 517)])
+@pytest.mark.parametrize("gdir", [4, 2])
+def test_fused_core_equals_unfused_chain(cuda, shape, gdir):
+    """hc_dtm_pre_dev + hc_dtm_apply_dev (two tile passes over the DEM, no smoothed raster in HBM) against the chain of
+    single-purpose kernels (dw4 -> slope -> curvature -> sigma -> select): Zf, filter code and final slope bit for bit,
+    masks included; sigma within float64 summation noise."""
+    from pydrodem_b200 import stencils, synth
+    ny, nx = shape
+    rng = np.random.default_rng(ny * 1000 + nx)
+    dem = synth.make_dem_numpy(max(ny, 8), max(nx, 8), 1005, quantise=False)[:ny, :nx]
+    dem = (dem + rng.normal(0, 1.5, dem.shape)).astype(np.float32)
+    swo = (rng.random(dem.shape) < 0.05).astype(np.uint8)
+    edm = rng.integers(0, 7, dem.shape).astype(np.uint8)
+    tx = (rng.random(dem.shape) < 0.03).astype(np.uint8)
+    art = (rng.random(dem.shape) < 0.03).astype(np.uint8)
+    for masks in ({}, dict(swo=swo, edm=edm, tx=tx, artifact=art)):
+        a = stencils.smooth_core_unfused(dem, 30.0, 25.0, gdir=gdir, **masks)
+        b = stencils.smooth_core(dem, 30.0, 25.0, gdir=gdir, **masks)
+        for x, y, name in zip(a, b, ("zf", "filter", "slope")):
+            assert np.array_equal(x, y), f"{name}: {(x != y).sum()} cells differ"
