@@ -208,6 +208,12 @@ int hc_raise_small_streams_dev(hc_ctx *ctx, const float *dem, float *burn, const
 int hc_smooth_rivers_dev(hc_ctx *ctx, const float *dem, float *burn, const uint8_t *wm, const int16_t *swo,
                          float nodata, int swo_cut, float max_lower, int filter_size, int64_t ny, int64_t nx,
                          void *stream);
+/* wbt.fill_missing_data(i, output, filter, weight) (tools/water.py:1396,1774; models/burn_rivers.py:1283,1582;
+ * models/dem_noise_removal.py:739): a nodata cell takes the inverse-distance-weighted (1 / d^weight) mean of the valid
+ * cells that border nodata within filter / 2 cells; stays nodata when none is in reach.  out != z.  Restated from the
+ * tool's documentation (WhiteboxTools unavailable: parity unpinned). */
+int hc_fill_missing_data_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata, int filter,
+                             double weight, void *stream);
 /* Vegetation-bias lookup of CreateDTM.compute_veg_bias_3D (models/dem_noise_removal.py:764-805; the 2-D table of
  * compute_veg_bias_2D :620-629 is n1 == 1 with i1 NULL).
  * box3_index: inputs first capped at in_max (:777) and zeroed where in_zero != 0 (nullable; the ocean mask, :687);

@@ -666,7 +666,7 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
     int yy = by + tid / 3 - 1, xx = bx + tid % 3 - 1;
     bool in = yy >= 0 && yy < ty && xx >= 0 && xx < tx;
     s_act[tid] = in ? active[yy * tx + xx] : 0;
-    s_vis[tid] = in ? visited[yy * tx + xx] : 1;
+    s_vis[tid] = in ? __ldcg(visited + yy * tx + xx) : 1;   // L2: a persistent CTA's L1 may hold a stale 0
   }
   __syncthreads();
   // first visit of this tile: it must wake the not-yet-visited neighbours that hold more of its flats (they may
@@ -808,7 +808,7 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ nf, u32 
     for (int i = tid; i < T * T * 2 / 16; i += NTHREADS) q[i] = make_uint4(0, 0, 0, 0);
   }
   if (tid == 0) s_want = 0;
-  const bool first = visited[t] == 0;
+  const bool first = __ldcg(visited + t) == 0;   // (L2: a persistent CTA's L1 may hold a stale 0)
   __syncthreads();
   long long g[FL_PER];
   u32 lo[FL_PER], hi[FL_PER], msk[FL_PER], ref[FL_PER][4];
@@ -854,6 +854,10 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ nf, u32 
           ref[j][0] = (ref[j][0] << 16) | (pos - 1u);
         } else elo = min(elo, 2u);                               // a low edge (lo = 1) of the same elevation
       } else {
+        // a cell of a tile outside the active set holds no state (its rasters were never initialised): not in any flat,
+        // as in the window path; rows -1 / ny are a band's halo rows, whose state the exchange maintains
+        const int rn = r0 + nr;
+        if (rn >= 0 && rn < ny && !active[(rn >> 6) * tx + ((c0 + nc) >> 6)]) continue;
         const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
         const u32 a = __ldcg(dlo + gn), b = __ldcg(dhi + gn);    // (dhi of a cell with a direction is 0)
         if (a) elo = min(elo, a + 1u);
@@ -951,7 +955,7 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ nf, u32 
       if (!f) continue;
       const u32 nlo = a ? a : R_INF, nhi = b ? b : R_INF;
       const bool benefit = c && (lo[j] + 1u < nlo || hi[j] + 1u < nhi);
-      if (benefit || (first && !visited[tt])) want |= 1u << ((dy + 1) * 3 + dx + 1);
+      if (benefit || (first && !__ldcg(visited + tt))) want |= 1u << ((dy + 1) * 3 + dx + 1);
     }
   }
   if (want) atomicOr(&s_want, want);
@@ -989,8 +993,13 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
       ctl[8 + 2 * it] = n;
       ctl[9 + 2 * it] = (u32)ns;
+      if (it >= 14u && n == 1u) { const u32 t0 = __ldcg(lin); ctl[9 + 2 * it] = t0 | (tcount[t0] > FL_LCAP ? 0x80000000u : 0u); }
     }
     if (!n) break;
+    if (it >= (1u << 16)) {   // cannot happen on a consistent state (distances only decrease); never spin forever on a broken one
+      if (blockIdx.x == 0 && threadIdx.x == 0) { HC_DBG(7, 1); *nin = 0u; }
+      break;
+    }
     const u32 stamp = it + 2u;
     for (;;) {
       __syncthreads();
@@ -1197,7 +1206,8 @@ static int flats_relax_loop(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
     HC_CUDA(cudaStreamSynchronize(st));
     fprintf(stderr, "[flats] rounds (tiles @ us):");
     for (int i = 0; i < 24; i++) {
-      fprintf(stderr, " %u@%.0f", h[2 * i], (double)(h[2 * i + 1] - h[1]) * 1e-3);
+      if (i >= 14 && h[2 * i] == 1) fprintf(stderr, " 1@tile(%u,%u)%s", (h[2 * i + 1] & 0x7FFFFFFFu) / (u32)tx, (h[2 * i + 1] & 0x7FFFFFFFu) % (u32)tx, (h[2 * i + 1] >> 31) ? "L" : "l");
+      else fprintf(stderr, " %u@%.0f", h[2 * i], (double)(h[2 * i + 1] - h[1]) * 1e-3);
       if (!h[2 * i]) break;
     }
     fprintf(stderr, "\n");

@@ -437,3 +437,82 @@ extern "C" int hc_smooth_rivers_dev(hc_ctx *ctx, const float *dem, float *burn, 
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// wbt.fill_missing_data(i, output, filter, weight) as pydrodem calls it after blanking cells it wants re-interpolated
+// (tools/water.py:1396 filter=11, :1774 filter=17, weight=2; models/burn_rivers.py:1283,1582; models/dem_noise_removal.py:739).
+// WhiteboxTools' FillMissingData is not available here; restated from its documentation (parity unpinned): the sample
+// points are the valid cells on the EDGE of nodata areas (a valid cell with a nodata 8-neighbour); a nodata cell takes
+// the inverse-distance-weighted mean (weight 1 / d^w, d in cells) of the sample points within filter / 2 cells of it and
+// stays nodata when there is none.  Sums in float64, result narrowed to float32.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fmd_edges(const float *__restrict__ z, uint8_t *__restrict__ edge, int ny, int nx, float nodata) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)ny * nx) return;
+  const int r = (int)(i / nx), c = (int)(i - (long long)r * nx);
+  const float v = z[i];
+  uint8_t e = 0;
+  if (!(v == nodata || v != v)) {
+    for (int dr = -1; dr <= 1 && !e; dr++)
+      for (int dc = -1; dc <= 1; dc++) {
+        const int rr = r + dr, cc = c + dc;
+        if (rr < 0 || rr >= ny || cc < 0 || cc >= nx) continue;
+        const float w = z[(size_t)rr * nx + cc];
+        if (w == nodata || w != w) { e = 1; break; }
+      }
+  }
+  edge[i] = e;
+}
+
+// one warp per nodata cell would be overkill for the few thousand cells pydrodem blanks: one thread per cell, the
+// window walked row by row (edge flags are bytes, the window of a 17-cell filter is 289 of them)
+__global__ void __launch_bounds__(256)
+k_fmd_fill(const float *__restrict__ z, const uint8_t *__restrict__ edge, float *__restrict__ out, int ny, int nx,
+           float nodata, int half, double radius, double weight) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)ny * nx) return;
+  const float v = z[i];
+  if (!(v == nodata || v != v)) { out[i] = v; return; }
+  const int r = (int)(i / nx), c = (int)(i - (long long)r * nx);
+  double sw = 0.0, sz = 0.0;
+  for (int dr = -half; dr <= half; dr++) {
+    const int rr = r + dr;
+    if (rr < 0 || rr >= ny) continue;
+    for (int dc = -half; dc <= half; dc++) {
+      const int cc = c + dc;
+      if (cc < 0 || cc >= nx) continue;
+      const size_t g = (size_t)rr * nx + cc;
+      if (!edge[g]) continue;
+      const double d = sqrt((double)(dr * dr + dc * dc));
+      if (d > radius) continue;
+      const double w = 1.0 / pow(d, weight);
+      sw += w;
+      sz += w * (double)z[g];
+    }
+  }
+  out[i] = sw > 0.0 ? (float)(sz / sw) : v;
+}
+
+extern "C" int hc_fill_missing_data_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata,
+                                        int filter, double weight, void *stream) {
+  W_CTX(ctx);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!z || !out || z == out || filter < 1 || filter > 1001 || ny * nx >= 2147483647LL) {
+    hc_set_error("hc_fill_missing_data: bad argument");
+    return HC_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)ny * nx;
+  HC_TRY(arena_reset(ctx));
+  uint8_t *edge = (uint8_t *)arena_take(ctx, n);
+  if (!edge) return HC_ERR_NOMEM;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  HC_PROF(ctx, st, "k_fmd_edges");
+  k_fmd_edges<<<grid, 256, 0, st>>>(z, edge, (int)ny, (int)nx, nodata);
+  HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_fmd_fill");
+  k_fmd_fill<<<grid, 256, 0, st>>>(z, edge, out, (int)ny, (int)nx, nodata, filter / 2, (double)filter / 2.0, weight);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
