@@ -214,6 +214,15 @@ int hc_smooth_rivers_dev(hc_ctx *ctx, const float *dem, float *burn, const uint8
  * tool's documentation (WhiteboxTools unavailable: parity unpinned). */
 int hc_fill_missing_data_dev(hc_ctx *ctx, const float *z, float *out, int64_t ny, int64_t nx, float nodata, int filter,
                              double weight, void *stream);
+/* Raster halves of wtr.enforce_monotonic_rivers (tools/water.py:1407-1779) for one water level h.  hc_mono_mask_dev: the
+ * candidate cells (:1488-1496): river classes 4..7 with left != 0, above h or 8-adjacent to a river cell above h, not
+ * exactly on h.  hc_mono_stats_dev: per label 1..nlab of the 4-connected clumps of that mask, stats[6 * id + k] =
+ * {cells (with inner == 1 when inner is given), touches donut == 1, row min, row max, col min, col max} (:1505-1538);
+ * the caller presets stats to {0, 0, INT_MAX, -1, INT_MAX, -1}.  donut / inner may be NULL. */
+int hc_mono_mask_dev(hc_ctx *ctx, const float *dem, const uint8_t *wm, const uint8_t *left, float h, uint8_t *out,
+                     int64_t ny, int64_t nx, void *stream);
+int hc_mono_stats_dev(hc_ctx *ctx, const int32_t *lab, const uint8_t *donut, const uint8_t *inner, int32_t nlab,
+                      int32_t *stats, int64_t ny, int64_t nx, void *stream);
 /* Vegetation-bias lookup of CreateDTM.compute_veg_bias_3D (models/dem_noise_removal.py:764-805; the 2-D table of
  * compute_veg_bias_2D :620-629 is n1 == 1 with i1 NULL).
  * box3_index: inputs first capped at in_max (:777) and zeroed where in_zero != 0 (nullable; the ocean mask, :687);

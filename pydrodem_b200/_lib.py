@@ -65,6 +65,8 @@ SIGNATURES = {
     "hc_raise_small_streams_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, ctypes.c_int, c_i64,
                                                   c_i64, c_vp]),
     "hc_fill_missing_data_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, ctypes.c_int, c_f64, c_vp]),
+    "hc_mono_mask_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_i64, c_vp]),
+    "hc_mono_stats_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp, c_i64, c_i64, c_vp]),
     "hc_smooth_rivers_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, ctypes.c_int, c_f32, ctypes.c_int,
                                             c_i64, c_i64, c_vp]),
     "hc_box3_index_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_f32, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp]),

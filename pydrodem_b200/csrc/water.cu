@@ -486,7 +486,7 @@ k_fmd_fill(const float *__restrict__ z, const uint8_t *__restrict__ edge, float 
       if (!edge[g]) continue;
       const double d = sqrt((double)(dr * dr + dc * dc));
       if (d > radius) continue;
-      const double w = 1.0 / pow(d, weight);
+      const double w = 1.0 / (weight == 2.0 ? d * d : pow(d, weight));
       sw += w;
       sz += w * (double)z[g];
     }
@@ -513,6 +513,78 @@ extern "C" int hc_fill_missing_data_dev(hc_ctx *ctx, const float *z, float *out,
   HC_LAUNCH_CHECK(ctx);
   HC_PROF(ctx, st, "k_fmd_fill");
   k_fmd_fill<<<grid, 256, 0, st>>>(z, edge, out, (int)ny, (int)nx, nodata, filter / 2, (double)filter / 2.0, weight);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Raster halves of wtr.enforce_monotonic_rivers (tools/water.py:1407-1779), one water level h at a time:
+//   k_mono_mask    the candidate cells of level h: flattened-river cells (classes 4..7) still "left", standing above h
+//                  or 8-adjacent to a river cell that does, but not exactly on h (:1488-1496)
+//   k_mono_stats   per 4-connected clump of that mask: cell count (inside the inner boundary when one is given), whether
+//                  it touches the boundary "donut", bounding box (:1505-1524, :1535-1538)
+// The per-clump geometry tests that follow are host logic on small windows (pydrodem_b200/tools/water.py).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mono_mask(const float *__restrict__ dem, const uint8_t *__restrict__ wm, const uint8_t *__restrict__ left, float h,
+            uint8_t *__restrict__ out, int ny, int nx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)ny * nx) return;
+  const int r = (int)(i / nx), c = (int)(i - (long long)r * nx);
+  uint8_t o = 0;
+  const uint8_t w = wm[i];
+  if (w > 3 && w < 8 && left[i]) {
+    const float d = __fsub_rn(dem[i], h);
+    if (d != 0.f) {   // (NaN counts as "not zero", like numpy's ==)
+      for (int dr = -1; dr <= 1 && !o; dr++)
+        for (int dc = -1; dc <= 1; dc++) {
+          const int rr = r + dr, cc = c + dc;
+          if (rr < 0 || rr >= ny || cc < 0 || cc >= nx) continue;   // (symmetric padding only repeats cells of the window)
+          const size_t g = (size_t)rr * nx + cc;
+          const uint8_t wn = wm[g];
+          if (wn > 3 && wn < 8 && __fsub_rn(dem[g], h) > 0.f) { o = 1; break; }
+        }
+    }
+  }
+  out[i] = o;
+}
+
+// stats[id] = {count, touches donut, rmin, rmax, cmin, cmax} (int32 x 6), ids 1..nlab; rmin / cmin start at INT_MAX
+__global__ void __launch_bounds__(256)
+k_mono_stats(const int32_t *__restrict__ lab, const uint8_t *__restrict__ donut, const uint8_t *__restrict__ inner,
+             int32_t *__restrict__ stats, int ny, int nx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)ny * nx) return;
+  const int32_t id = lab[i];
+  if (id <= 0) return;
+  const int r = (int)(i / nx), c = (int)(i - (long long)r * nx);
+  int32_t *s = stats + (size_t)id * 6;
+  if (!inner || inner[i] == 1) atomicAdd(&s[0], 1);
+  if (donut && donut[i] == 1) atomicOr(&s[1], 1);
+  atomicMin(&s[2], r); atomicMax(&s[3], r);
+  atomicMin(&s[4], c); atomicMax(&s[5], c);
+}
+
+extern "C" int hc_mono_mask_dev(hc_ctx *ctx, const float *dem, const uint8_t *wm, const uint8_t *left, float h,
+                                uint8_t *out, int64_t ny, int64_t nx, void *stream) {
+  W_CTX(ctx);
+  if (ny <= 0 || nx <= 0) return HC_OK;
+  if (!dem || !wm || !left || !out || ny * nx >= 2147483647LL) { hc_set_error("hc_mono_mask: bad argument"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_PROF(ctx, st, "k_mono_mask");
+  k_mono_mask<<<(unsigned)(((size_t)ny * nx + 255) / 256), 256, 0, st>>>(dem, wm, left, h, out, (int)ny, (int)nx);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
+extern "C" int hc_mono_stats_dev(hc_ctx *ctx, const int32_t *lab, const uint8_t *donut, const uint8_t *inner,
+                                 int32_t nlab, int32_t *stats, int64_t ny, int64_t nx, void *stream) {
+  W_CTX(ctx);
+  if (ny <= 0 || nx <= 0 || nlab <= 0) return HC_OK;
+  if (!lab || !stats || ny * nx >= 2147483647LL) { hc_set_error("hc_mono_stats: bad argument"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_PROF(ctx, st, "k_mono_stats");
+  k_mono_stats<<<(unsigned)(((size_t)ny * nx + 255) / 256), 256, 0, st>>>(lab, donut, inner, stats, (int)ny, (int)nx);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }

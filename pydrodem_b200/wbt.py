@@ -129,6 +129,21 @@ class WhiteboxToolsGPU:
         self._say("breach_depressions ->", output)
         return 0
 
+    # -- gap interpolation (tools/water.py:1396, :1774; models/burn_rivers.py:1283, :1582; dem_noise_removal.py:739) --
+    def fill_missing_data(self, i, output, filter=11, weight=2.0, no_edges=False, callback=None):
+        """IDW infill of the cells pydrodem blanks before re-interpolating them (hc_fill_missing_data_dev): a nodata
+        cell takes the 1 / d^weight weighted mean of the valid cells bordering nodata within filter / 2 cells.  Restated
+        from the tool's documentation (parity unpinned).  no_edges=True (skip nodata connected to the raster frame) is
+        not what pydrodem passes and is not built."""
+        if no_edges:
+            raise NotImplementedError("fill_missing_data(no_edges=True) is not used by pydrodem")
+        from .tools import water
+        z, meta, nodata = self._load(i)
+        out = water.fill_missing_data(np.asarray(z, np.float32), nodata, int(filter), float(weight))
+        raster_io.write_raster(output, out, meta, nodata=nodata)
+        self._say("fill_missing_data ->", output)
+        return 0
+
     # -- not built ----------------------------------------------------------------------------------
     def breach_depressions_least_cost(self, dem, output, dist, max_cost=None, min_dist=True, flat_increment=None,
                                       fill=True, callback=None):

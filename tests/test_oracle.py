@@ -239,3 +239,21 @@ def test_golden_hashes(oracle):
         assert _digest(f) == golden[name]["fill"], name
         assert _digest(d) == golden[name]["dir"], name
         assert _digest(a) == golden[name]["acc"], name
+
+
+def test_fill_missing_oracle_hand_case():
+    """oracle/fill_missing_oracle.py on a hand-worked gap: one nodata cell between two edge cells takes their
+    inverse-distance-weighted mean; a cell out of reach stays nodata; valid cells never change"""
+    from oracle.fill_missing_oracle import fill_missing_data
+    nd = -9999.0
+    z = np.full((1, 7), nd, np.float32)
+    z[0, 0], z[0, 2] = 10.0, 20.0
+    out = fill_missing_data(z, nd, filter=3, weight=2.0)      # reach 1.5 cells
+    assert out[0, 0] == 10.0 and out[0, 2] == 20.0
+    assert out[0, 1] == np.float32(15.0)                       # two samples at distance 1
+    assert out[0, 3] == np.float32(20.0)                       # one sample at distance 1
+    assert (out[0, 4:] == nd).all()
+    z2 = np.array([[1.0, nd, nd, 4.0]], np.float32)
+    out2 = fill_missing_data(z2, nd, filter=7, weight=2.0)    # reach 3.5: both samples, weights 1 and 1/4
+    assert out2[0, 1] == np.float32((1.0 * 1.0 + 0.25 * 4.0) / 1.25)
+    assert out2[0, 2] == np.float32((0.25 * 1.0 + 1.0 * 4.0) / 1.25)
