@@ -133,6 +133,9 @@ int hc_taudem_check_dev(hc_ctx *ctx, const uint8_t *p, const float *fel, const u
                         float nodata, void *stream);
 int hc_taudem_fix_dev(hc_ctx *ctx, const float *dem, const uint8_t *flat, float *out, int64_t ny,
                       int64_t nx, float nodata, float bump, void *stream);
+/* np.round(a - b, decimals) on float32 rasters, numpy's float32 rule rint(x * 10^d) / 10^d (the fill / carve
+ * difference maps of tools/depressions.py:1308, :1395); out may alias a or b. */
+int hc_diff_round_dev(hc_ctx *ctx, const float *a, const float *b, float *out, int64_t n, int decimals, void *stream);
 
 /* Smoothing stencils of CreateDTM (models/dem_noise_removal.py:397-487) and dep.create_clump_array.
  * conv2d_symm = scipy.signal.convolve2d(boundary='symm', mode='same') as pdt.apply_convolve_filter

@@ -39,6 +39,7 @@ SIGNATURES = {
     "hc_breach_single_cell_pits_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp]),
     "hc_taudem_check_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_i64), c_i64, c_i64,
                                            c_f32, c_vp]),
+    "hc_diff_round_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp]),
     "hc_taudem_fix_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f32, c_vp]),
     "hc_conv2d_symm_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_i64, c_vp]),
     "hc_conv2d_symm_dw4_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),

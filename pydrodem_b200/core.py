@@ -391,3 +391,23 @@ def taudem_fix(dem, flat_mask, nodata=-9999.0, bump=0.10):
         _lib.check(lib.hc_taudem_fix_dev(_lib.context(dem.device.index or 0), _tp(dem), _tp(flat_mask), _tp(out),
                                          dem.shape[0], dem.shape[1], nodata, bump, _stream(dem)), "hc_taudem_fix_dev")
     return out.cpu().numpy() if host else out
+
+
+def diff_round(a, b, decimals=3):
+    """np.round(a - b, decimals) for float32 rasters on the GPU (hc_diff_round_dev): the difference maps of
+    dep.fill_pits / dep.breach_pits (tools/depressions.py:1308, :1395).  numpy in -> numpy out, tensor in -> tensor out."""
+    import torch
+    lib = _lib.load()
+    host = not _is_torch(a)
+    if host:
+        a = torch.from_numpy(_np2d(a, np.float32)).cuda()
+        b = torch.from_numpy(_np2d(b, np.float32)).cuda()
+    a = _tdev(a, torch.float32, "diff_round")
+    b = _tdev(b, torch.float32, "diff_round")
+    if a.shape != b.shape:
+        raise ValueError("diff_round: shapes differ")
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.hc_diff_round_dev(_lib.context(a.device.index or 0), _tp(a), _tp(b), _tp(out), a.numel(), int(decimals),
+                                         _stream(a)), "hc_diff_round_dev")
+    return out.cpu().numpy() if host else out

@@ -186,3 +186,26 @@ extern "C" int hc_taudem_fix_dev(hc_ctx *ctx, const float *dem, const uint8_t *f
   if (ny < 0 || nx < 0 || (ny && nx && (!dem || !flat || !out))) { hc_set_error("hc_taudem_fix: bad argument"); return HC_ERR_ARG; }
   return taudem_fix_run(ctx, dem, flat, out, ny, nx, nodata, bump, (cudaStream_t)stream);
 }
+
+// np.round(a - b, 3) on float32 rasters (tools/depressions.py:1308, :1395: the fill / carve difference maps): numpy
+// rounds float32 to `decimals` places as rint(x * 10^d) / 10^d in float32, every step rounded.
+__global__ void __launch_bounds__(256)
+k_diff_round(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, size_t n, float scale) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __fdiv_rn(rintf(__fmul_rn(__fsub_rn(a[i], b[i]), scale)), scale);
+}
+
+extern "C" int hc_diff_round_dev(hc_ctx *ctx, const float *a, const float *b, float *out, int64_t n, int decimals,
+                                 void *stream) {
+  HC_ENTER(ctx);
+  if (n <= 0) return HC_OK;
+  if (!a || !b || !out || decimals < 0 || decimals > 6) { hc_set_error("hc_diff_round: bad argument"); return HC_ERR_ARG; }
+  float scale = 1.f;
+  for (int k = 0; k < decimals; k++) scale *= 10.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_PROF(ctx, st, "k_diff_round");
+  k_diff_round<<<ctx->sm_count * 8, 256, 0, st>>>(a, b, out, (size_t)n, scale);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}

@@ -13,6 +13,13 @@ import numpy as np
 from .. import core, raster_io, stencils
 
 
+def _diff3(a, b):
+    """np.round(a - b, 3): on the GPU for float32 rasters (bit-identical, core.diff_round), numpy's own otherwise"""
+    if a.dtype == np.float32 and b.dtype == np.float32 and a.shape == b.shape and a.ndim == 2:
+        return core.diff_round(a, b, 3)
+    return np.round((a - b), 3)
+
+
 def fill_pits(inDEM, wbt, fill_method='WL', nodataval=-9999, fixflats=False, flat_increment=0.0, save_tif=True,
               downcast=True):
     """tools/depressions.py:1236-1316.  Returns (fill_array, diff_fill_array), writes `<in>_<method>.tif`
@@ -32,7 +39,7 @@ def fill_pits(inDEM, wbt, fill_method='WL', nodataval=-9999, fixflats=False, fla
         # the epsilon fill is written in float64 (as WhiteboxTools writes everything); pyct.tifdowncast narrows it (:1306)
         fill_array = fill_array.astype(np.float32)
         raster_io.write_raster(fill_tif, fill_array, fmeta, nodata=nodataval)
-    diff_fill_array = np.round((fill_array - inDEM_array), 3)  # :1308
+    diff_fill_array = _diff3(fill_array, inDEM_array)  # :1308
     if save_tif:
         diff_tif_fill = fill_tif.replace('.tif', '_DIFF.tif')
         raster_io.write_raster(diff_tif_fill, diff_fill_array.astype(np.float32), meta, nodata=nodataval)
@@ -60,7 +67,7 @@ def breach_pits(inDEM_tif, radius, maxcost, wbt, min_dist=False, flat_increment=
         carvefill_path = carve_path
     inDEM_array, meta = raster_io.read_raster(inDEM_tif)
     carve_array, _ = raster_io.read_raster(carvefill_path)
-    diff_carve_array = np.round((carve_array - inDEM_array), 3)  # :1395
+    diff_carve_array = _diff3(carve_array, inDEM_array)  # :1395
     if save_tif:
         diff_tif_carve = carvefill_path.replace('.tif', '_DIFF.tif')
         raster_io.write_raster(diff_tif_carve, diff_carve_array.astype(np.float32), meta, nodata=nodataval)

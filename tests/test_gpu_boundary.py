@@ -129,3 +129,21 @@ def test_taudem_cli(tmp_path, oracle, cuda):
     assert np.array_equal(raster_io.read_raster(sd8)[0], s)
     aa = raster_io.read_raster(ad8)[0]
     assert np.array_equal(np.where(aa < 0, 0, aa).astype(np.uint32), a)
+
+
+def test_diff_round_equals_numpy(cuda):
+    """hc_diff_round_dev = np.round(a - b, 3) on float32, bit for bit (ties, negatives, nodata-sized values, NaN)"""
+    import pydrodem_b200 as hc
+    rng = np.random.default_rng(5)
+    a = (rng.normal(0, 30, (257, 301))).astype(np.float32)
+    b = (a + rng.normal(0, 2, a.shape)).astype(np.float32)
+    b.ravel()[::7] = a.ravel()[::7]                       # zeros
+    a.ravel()[3::11] = b.ravel()[3::11] + np.float32(0.0005)   # ties at the third decimal
+    a[0, 0], b[0, 0] = -9999.0, -9999.0
+    a[0, 1], b[0, 1] = np.nan, 1.0
+    a[0, 2], b[0, 2] = 3.0e6, -9999.0
+    want = np.round((a - b), 3)
+    got = hc.core.diff_round(a, b, 3)
+    assert got.dtype == np.float32
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.array_equal(np.signbit(got), np.signbit(want))
