@@ -13,6 +13,8 @@
 #define HC_TAG 0x80000000u     // top bit marks a resolved basin id in the pointer/label array
 #define HC_LAB_NODATA 0x7FFFFFFFu
 #define HC_NONE 0xFFFFFFFFu
+#define HC_NFCAP 1024          // NOFLOW cells listed per 64 x 64 tile (flat pass); a tile holding more is "dense"
+#define HC_NF_HI 0x8000u       // list entry = local index (12 bits) | HC_NF_HI when the cell touches higher ground
 
 typedef unsigned int u32;
 typedef unsigned long long u64;
@@ -67,7 +69,7 @@ struct hc_band_state {
   int fill_ready; const float *z; u32 *P; float *level0; u32 *troot; u32 K1, nopen; u32 *cnt;
   // flats
   int flats_ready, table; float nodata; const float *fz; const uint8_t *dirA; uint8_t *dirB;
-  uint8_t *pending, *active, *nf, *visited, *tmask; u32 *dlo, *dhi, *flag, *tcount; unsigned short *tlist; int n_pending;
+  uint8_t *pending, *active, *visited, *tmask; u32 *dlo, *dhi, *flag, *tcount; unsigned short *tlist; int n_pending;
   u32 *qA, *qB, *queued;   // dirty-tile queues of the slow tier (current / next) and the per-tile "already queued" marks
   // accumulation
   int acc_ready; uint32_t *acc_out; const uint8_t *dir; unsigned long long *pstate; unsigned short *pexit; u32 *pdown, *pinflow, *bout, *acc_err;
@@ -202,8 +204,12 @@ int accum_split_prepare(hc_ctx *ctx, const uint8_t *dir, uint32_t *acc, int64_t 
 int accum_split_tiles(hc_ctx *ctx, int table, const uint8_t *tile_class, int only_class, cudaStream_t st);
 int accum_split_finish(hc_ctx *ctx, int table, cudaStream_t st);
 // flat pass in two halves (whole raster): fast tier, then the slow tier for what it left pending
+// per-tile lists of the NOFLOW cells of a D8 raster, as the flat pass consumes them: entries[tile * HC_NFCAP + k] = local
+// index | HC_NF_HI, eq[...] = which of the 8 neighbours (3 x 3 row-major, centre skipped) have the same elevation,
+// counts[tile] = NOFLOW cells in the tile (entries beyond HC_NFCAP are not stored)
+struct hc_nf_lists { unsigned short *entries; uint8_t *eq; u32 *counts; };
 int flats_whole_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx, float nodata,
-                      int table, cudaStream_t st, const uint8_t **tile_pending, int *n_pending);
+                      int table, cudaStream_t st, const uint8_t **tile_pending, int *n_pending, const hc_nf_lists *pre = nullptr);
 int flats_whole_finish(hc_ctx *ctx, cudaStream_t st);
 int label_run(hc_ctx *ctx, const uint8_t *mask, int32_t *lab, int64_t ny, int64_t nx, int conn, int32_t *nlab,
               cudaStream_t st);

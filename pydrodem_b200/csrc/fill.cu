@@ -1185,10 +1185,12 @@ __global__ void __launch_bounds__(NTHREADS)
 k_apply_d8(const float *__restrict__ z, const u32 *__restrict__ P, const __grid_constant__ CUtensorMap mz,
            const __grid_constant__ CUtensorMap mp, const float *__restrict__ level0, float *__restrict__ filled,
            uint8_t *__restrict__ dir, uint8_t *__restrict__ dir2, float *__restrict__ slope, int ny, int nx, float nodata,
-           fd8_params prm) {
+           fd8_params prm, hc_nf_lists nfl) {
   __shared__ __align__(128) float sf_box[TH * WP];
   __shared__ __align__(128) u32 sp_box[TH * WP];
   __shared__ __align__(8) uint64_t mbar;
+  __shared__ u32 s_nf;   // NOFLOW cells of the tile (listed for the flat pass while their 3 x 3 window is in registers)
+  if (threadIdx.x == 0) s_nf = 0;
   float *sf = sf_box + WXO;
   u32 *sp = sp_box + WXO;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
@@ -1232,7 +1234,8 @@ k_apply_d8(const float *__restrict__ z, const u32 *__restrict__ P, const __grid_
   // column walk: thread -> column lc = tid % 64, rows [16 * (tid / 64), +16), 3x3 window in registers
   const int lc = tid & (T - 1), lr0 = (tid >> 6) * (T / 4);
   const int c = c0 + lc;
-  if (c >= nx) return;
+  const size_t tile = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  if (c < nx) {
   float w[3][3];
   {
     const float *row = &sf[lr0 * WP + lc];
@@ -1284,29 +1287,55 @@ k_apply_d8(const float *__restrict__ z, const u32 *__restrict__ P, const __grid_
     dir[g] = code;
     if (dir2) dir2[g] = code;
     if (SLOPE) slope[g] = sl;
+    if (code == HC_DIR_NOFLOW && nfl.entries) {
+      // the flat pass's record of this cell: equal-elevation neighbours, "touches higher ground"
+      u32 eq = 0, hi = 0;
+      int kb = 0;
+#pragma unroll
+      for (int dr = 0; dr < 3; dr++)
+#pragma unroll
+        for (int dc = 0; dc < 3; dc++) {
+          if (dr == 1 && dc == 1) continue;
+          const float zn = w[dr][dc];
+          if (zn == v) eq |= 1u << kb;
+          else if (zn > v) hi = HC_NF_HI;
+          kb++;
+        }
+      const u32 pos = atomicAdd(&s_nf, 1u);
+      if (pos < HC_NFCAP) {
+        nfl.entries[tile * HC_NFCAP + pos] = (unsigned short)((u32)(lr * T + lc) | hi);
+        nfl.eq[tile * HC_NFCAP + pos] = (uint8_t)eq;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 3; j++) { w[0][j] = w[1][j]; w[1][j] = w[2][j]; }
+  }
+  }
+  if (nfl.counts) {
+    __syncthreads();
+    if (tid == 0) nfl.counts[tile] = s_nf;
   }
 }
 
 template <int TABLE, bool SLOPE>
 static int apply_d8_launch(hc_ctx *ctx, const float *z, const fill_state &fs, float *filled, uint8_t *dir, uint8_t *dir2,
-                           float *slope, int64_t ny, int64_t nx, float nodata, const fd8_params &prm, cudaStream_t st) {
+                           float *slope, int64_t ny, int64_t nx, float nodata, const fd8_params &prm, cudaStream_t st,
+                           hc_nf_lists nfl) {
   dim3 tg((unsigned)((nx + T - 1) / T), (unsigned)((ny + T - 1) / T));
   hc_tmap mz, mp;
   hc_tmap_2d(&mz, z, 4, 1, (uint64_t)nx, (uint64_t)ny, (uint64_t)nx * 4, WP, TH);
   hc_tmap_2d(&mp, fs.P, 4, 0, (uint64_t)nx, (uint64_t)ny, (uint64_t)nx * 4, WP, TH);
   HC_PROF(ctx, st, "k_apply_d8");
   if (mz.ok && mp.ok)
-    k_apply_d8<TABLE, SLOPE, true><<<tg, NTHREADS, 0, st>>>(z, fs.P, mz.map, mp.map, fs.level0, filled, dir, dir2, slope, (int)ny, (int)nx, nodata, prm);
+    k_apply_d8<TABLE, SLOPE, true><<<tg, NTHREADS, 0, st>>>(z, fs.P, mz.map, mp.map, fs.level0, filled, dir, dir2, slope, (int)ny, (int)nx, nodata, prm, nfl);
   else
-    k_apply_d8<TABLE, SLOPE, false><<<tg, NTHREADS, 0, st>>>(z, fs.P, mz.map, mp.map, fs.level0, filled, dir, dir2, slope, (int)ny, (int)nx, nodata, prm);
+    k_apply_d8<TABLE, SLOPE, false><<<tg, NTHREADS, 0, st>>>(z, fs.P, mz.map, mp.map, fs.level0, filled, dir, dir2, slope, (int)ny, (int)nx, nodata, prm, nfl);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
 
 int flats_core(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx, float nodata,
-               int table, cudaStream_t st);
+               int table, cudaStream_t st, const hc_nf_lists *pre = nullptr);
 
 // fill -> (apply + D8 fused) -> flat resolution, one arena generation: the head of hc_fill_d8_accum_*
 int fill_d8_flats_run(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, float *slope, int64_t ny, int64_t nx,
@@ -1332,19 +1361,28 @@ int fill_d8_flats_run(hc_ctx *ctx, const float *z, float *filled, uint8_t *dir, 
   }
   // with flats: D8 writes dirA (kept as the flat pass's read-only input) and dir; the flat pass rewrites NOFLOW cells of dir
   uint8_t *d1 = resolve_flats ? dirA : dir, *d2 = resolve_flats ? dir : nullptr;
+  // ... and lists the NOFLOW cells per tile for the flat pass while it has their windows in registers
+  hc_nf_lists nfl = {nullptr, nullptr, nullptr};
+  if (resolve_flats) {
+    const size_t tiles = (size_t)((nx + T - 1) / T) * ((ny + T - 1) / T);
+    nfl.entries = (unsigned short *)arena_take(ctx, tiles * HC_NFCAP * 2);
+    nfl.eq = (uint8_t *)arena_take(ctx, tiles * HC_NFCAP);
+    nfl.counts = (u32 *)arena_take(ctx, tiles * 4);
+    if (!nfl.entries || !nfl.eq || !nfl.counts) return HC_ERR_NOMEM;
+  }
   if (table == HC_TABLE_WBT) {
-    if (slope) HC_TRY((apply_d8_launch<HC_TABLE_WBT, true>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st)));
-    else HC_TRY((apply_d8_launch<HC_TABLE_WBT, false>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st)));
+    if (slope) HC_TRY((apply_d8_launch<HC_TABLE_WBT, true>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st, nfl)));
+    else HC_TRY((apply_d8_launch<HC_TABLE_WBT, false>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st, nfl)));
   } else {
-    if (slope) HC_TRY((apply_d8_launch<HC_TABLE_TAUDEM, true>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st)));
-    else HC_TRY((apply_d8_launch<HC_TABLE_TAUDEM, false>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st)));
+    if (slope) HC_TRY((apply_d8_launch<HC_TABLE_TAUDEM, true>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st, nfl)));
+    else HC_TRY((apply_d8_launch<HC_TABLE_TAUDEM, false>(ctx, z, fs, filled, d1, d2, slope, ny, nx, nodata, prm, st, nfl)));
   }
   if (!resolve_flats) return HC_OK;
-  if (resolve_flats != 2) return flats_core(ctx, filled, dirA, dir, ny, nx, nodata, table, st);
+  if (resolve_flats != 2) return flats_core(ctx, filled, dirA, dir, ny, nx, nodata, table, st, &nfl);
   // chain form: flats in two halves with the accumulation's tile phase split around the slow tier
   const uint8_t *tile_pending = nullptr;
   int n_pending = 0;
-  HC_TRY(flats_whole_begin(ctx, filled, dirA, dir, ny, nx, nodata, table, st, &tile_pending, &n_pending));
+  HC_TRY(flats_whole_begin(ctx, filled, dirA, dir, ny, nx, nodata, table, st, &tile_pending, &n_pending, &nfl));
   HC_TRY(accum_split_prepare(ctx, dir, ctx->chain_acc, ny, nx));
   if (!n_pending) {
     HC_TRY(accum_split_tiles(ctx, table, nullptr, 0, st));

@@ -13,20 +13,20 @@
 // in every comparison the masked D8 makes, and a flat without a low edge is exactly one whose
 // cells the "towards lower" field never reaches.
 //
-// Two tiers:
-//   fast  k_flat_fast: one CTA per 64x64 tile loads the tile plus an 8-cell apron (80x80) into
-//         shared memory, classifies, relaxes to the fixed point over a compact list of the NOFLOW
-//         cells and writes final directions for every flat that lies completely inside the apron
-//         (on a filled DEM that is nearly all of them: each filled pit is a flat a few cells
-//         wide).  One read of z and dir, one write of dir.
-//   slow  flats that reach the apron's rim are marked pending (code 254) and solved by tile
-//         relaxation against global distance arrays (k_flat_init / k_flat_relax[_light] / k_flat_dirs)
-//         on the tiles that hold pending cells and their neighbours.  A device queue holds the dirty
-//         tiles of a round; tiles with <= 1024 NOFLOW cells relax straight on the L2-resident rasters
-//         from compact per-tile lists (k_flat_relax_light), lake tiles through a shared-memory window
-//         with whole-line Gauss-Seidel sweeps (k_flat_relax), side by side on two streams.  A tile is
-//         started only if it holds part of an open flat (first visits wake unvisited neighbours that
-//         share flat cells) and re-queued only if one of its rim cells can improve.
+// Two tiers, both driven by per-tile RECORDS of the NOFLOW cells (hc_nf_lists: local index, which of the 8 neighbours
+// share the elevation, "touches higher ground") that the fused apply + D8 pass writes while it has each cell's 3 x 3
+// window in registers (k_flat_list builds them for a D8 raster handed in by a caller / a row band):
+//   fast  k_flat_fast_sparse: one CTA per 64x64 tile gathers the records of its tile plus an 8-cell apron (80x80
+//         region), relaxes to the fixed point in shared memory and writes final directions for every flat that lies
+//         completely inside the apron (on a filled DEM nearly all of them).  No elevation is read.
+//   slow  flats that reach the apron's rim are marked pending (code 254) and solved by tile relaxation against two
+//         global distance rasters that hold state only at NOFLOW cells (k_flat_init_lists / k_flat_init, k_flat_relax,
+//         k_flat_dirs) on the tiles that hold pending cells and their neighbours.  A cell WITH a direction next to an
+//         equal NOFLOW cell is a low edge: constant 1, asked of the D8 raster, never stored.  A device queue holds the
+//         dirty tiles of a round (one cooperative launch runs all rounds); tiles with <= 1024 NOFLOW cells relax from
+//         their records in shared memory (relax_light), lake tiles through a shared-memory window with directional
+//         cone sweeps (relax_tile).  A tile is started only if it holds part of an open flat and re-queued only if
+//         one of its rim cells can improve.
 #include <stdlib.h>
 #include <cooperative_groups.h>
 
@@ -50,174 +50,6 @@ namespace cg = cooperative_groups;
 #define F_LO 0x3FFFu
 #define FLCAP 1536           // NOFLOW cells a tile may hold before it is left to the slow tier
 #define FSWEEPS 40           // sweep cap: a flat that fits the apron converges well inside it
-#define FAST_SMEM (FR * FR * (4 + 2 + 2) + FLCAP * 2 + 16)
-
-template <int TABLE>
-__global__ void __launch_bounds__(NTHREADS)
-k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB,
-            uint8_t *__restrict__ tile_pending, int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  float *sz = (float *)smem;
-  unsigned short *slo = (unsigned short *)(smem + FR * FR * 4);  // [OPEN | NF | lo:14]
-  unsigned short *shi = (unsigned short *)(smem + FR * FR * 6);
-  unsigned short *list = (unsigned short *)(smem + FR * FR * 8);
-  u32 *s_n = (u32 *)(smem + FR * FR * 8 + FLCAP * 2);
-
-  const int tid = threadIdx.x;
-  const int r0 = blockIdx.y * T - FH, c0 = blockIdx.x * T - FH;
-  const float qnan = __int_as_float(0x7fc00000);
-  if (tid == 0) s_n[0] = 0;
-  __syncthreads();
-  // 1. load + classify in one pass: NOFLOW flag, "open" on the region's rim, work list of the rest
-  //    (FR*FR is a multiple of NTHREADS: warps stay whole for the ballot)
-#pragma unroll 5
-  for (int i0 = 0; i0 < FR * FR; i0 += NTHREADS) {
-    const int i = i0 + tid;
-    int lr = i / FR, lc = i - lr * FR;
-    int r = r0 + lr, c = c0 + lc;
-    bool inb = r >= rw.rlo && r < rw.rhi && c >= 0 && c < nx;
-    long long g = inb ? (long long)r * nx + c : 0;  // r = -1 / ny: a band's halo rows
-    float v = __ldg(z + g);
-    uint8_t d = __ldg(dirA + g);
-    const bool valid = inb && v != nodata && v == v;
-    u32 w = 0;
-    bool want = false;
-    if (valid && d == HC_DIR_NOFLOW) {
-      // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
-      // (conservatively also when the rim coincides with the raster border)
-      // ... and a NOFLOW cell of a band's halo row belongs to the neighbouring band: open too
-      if (lr == 0 || lc == 0 || lr == FR - 1 || lc == FR - 1 || r < 0 || r >= ny) w = F_NF | F_OPEN;
-      else { w = F_NF; want = true; }
-    }
-    // warp-aggregated append: one shared atomic per warp instead of one per NOFLOW cell
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, want);
-    if (bal) {
-      const int lane = tid & 31;
-      u32 base = 0;
-      if (lane == 0) base = atomicAdd(&s_n[0], (u32)__popc(bal));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (want) {
-        u32 k = base + (u32)__popc(bal & ((1u << lane) - 1u));
-        if (k < FLCAP) list[k] = (unsigned short)i;
-      }
-    }
-    sz[i] = valid ? v : qnan;
-    slo[i] = (unsigned short)w;
-    shi[i] = 0;
-  }
-  __syncthreads();
-  const u32 nlist = s_n[0];
-  bool giveup = nlist > FLCAP;
-  if (!giveup && nlist) {
-    // 2. edges: a NOFLOW cell next to higher ground is a high edge (hi = 1); a cell WITH a
-    //    direction next to an equal NOFLOW cell is a low edge (lo = 1).  All writers store 1.
-    for (u32 k = tid; k < nlist; k += NTHREADS) {
-      int ci = list[k];
-      float v = sz[ci];
-      u32 hi = 0;
-#pragma unroll
-      for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-        for (int dc = -1; dc <= 1; dc++) {
-          if (!dr && !dc) continue;
-          int ni = ci + dr * FR + dc;
-          float zn = sz[ni];
-          if (zn > v) hi = 1;
-          else if (zn == v && !(slo[ni] & F_NF)) slo[ni] = 1;
-        }
-      shi[ci] = (unsigned short)hi;
-    }
-    __syncthreads();
-    // 3. relax the two distance fields and the "open" flag to their fixed point
-    int sweeps = 0;
-    for (;;) {
-      int changed = 0;
-      for (u32 k = tid; k < nlist; k += NTHREADS) {
-        int ci = list[k];
-        u32 w = slo[ci];
-        float v = sz[ci];
-        u32 lo = w & F_LO, hi = shi[ci];
-        u32 blo = lo ? lo : 0xFFFFu, bhi = hi ? hi : 0xFFFFu;
-        u32 open = w & F_OPEN;
-#pragma unroll
-        for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-          for (int dc = -1; dc <= 1; dc++) {
-            if (!dr && !dc) continue;
-            int ni = ci + dr * FR + dc;
-            if (sz[ni] != v) continue;
-            u32 nw = slo[ni];
-            u32 nlo = nw & F_LO;
-            if (nlo && nlo + 1 < blo) blo = nlo + 1;
-            if (nw & F_NF) {
-              u32 nhi = shi[ni];
-              if (nhi && nhi + 1 < bhi) bhi = nhi + 1;
-              open |= nw & F_OPEN;
-            }
-          }
-        if (blo == 0xFFFFu) blo = 0;
-        if (bhi == 0xFFFFu) bhi = 0;
-        u32 nw2 = F_NF | open | blo;
-        if (nw2 != w) { slo[ci] = (unsigned short)nw2; changed = 1; }
-        if (bhi != hi) { shi[ci] = (unsigned short)bhi; changed = 1; }
-      }
-      sweeps++;
-      if (!__syncthreads_or(changed)) break;
-      if (sweeps >= FSWEEPS) { giveup = true; break; }
-    }
-    if (tid == 0) { HC_DBG(0, sweeps); HC_DBG(1, 1); }
-  }
-  // 4. write: dirB already holds dirA's codes, so only the NOFLOW cells of the own tile are touched —
-  //    closed flats get their direction, open ones are marked pending
-  int pend = 0;
-  auto resolve = [&](int ci, int lr, int lc) {
-    int r = r0 + lr, c = c0 + lc;
-    if (lr < FH || lr >= FH + T || lc < FH || lc >= FH + T || r >= ny || c >= nx) return;  // not an own cell
-    u32 w = slo[ci];
-    uint8_t d = HC_DIR_NOFLOW;
-    if (giveup || (w & F_OPEN)) { d = HC_DIR_PENDING; pend = 1; }
-    else if (w & F_LO) {
-      float v = sz[ci];
-      int own = 2 * (int)(w & F_LO) - (int)shi[ci];
-      int mn = own, best = -1;
-      bool bdiag = false;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        int ni = ci + c_dr[TABLE][k] * FR + c_dc[TABLE][k];
-        if (sz[ni] != v) continue;
-        u32 nw = slo[ni];
-        int key;
-        if (nw & F_NF) {
-          if (!(nw & F_LO)) continue;
-          key = 2 * (int)(nw & F_LO) - (int)shi[ni];
-        } else {
-          key = -0x40000000;
-        }
-        bool kdiag = (c_dr[TABLE][k] != 0) && (c_dc[TABLE][k] != 0);
-        if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = k; bdiag = kdiag; }
-      }
-      if (best >= 0) d = (uint8_t)c_code[TABLE][best];
-    }
-    if (d != HC_DIR_NOFLOW) dirB[(size_t)r * nx + c] = d;
-  };
-  if (!giveup) {
-    for (u32 k = tid; k < nlist; k += NTHREADS) {
-      int ci = list[k];
-      int lr = ci / FR;
-      resolve(ci, lr, ci - lr * FR);
-    }
-  } else {
-    // the work list overflowed: every NOFLOW cell of the tile goes to the slow tier
-    for (int i = tid; i < T * T; i += NTHREADS) {
-      int lr = i / T + FH, lc = i % T + FH;
-      int ci = lr * FR + lc;
-      if (slo[ci] & F_NF) resolve(ci, lr, lc);
-    }
-  }
-  pend = __syncthreads_or(pend);
-  if (tid == 0 && pend) HC_DBG(2, 1);  // pending tiles
-  if (tid == 0) tile_pending[blockIdx.y * gridDim.x + blockIdx.x] = (uint8_t)(pend ? 1 : 0);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Sparse form of the fast tier.  On a filled DEM only a few percent of the cells are NOFLOW (3.4 % on the C2
@@ -227,11 +59,17 @@ k_flat_fast(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8
 // 3 x 3 elevations of just those cells, and keeps the per-cell state in the same 80 x 80 shared grid — same
 // rules, same result, a small fraction of the instructions.
 // ------------------------------------------------------------------------------------------------
-#define NFCAP 1024   // listed NOFLOW cells per tile; a tile with more is "dense": its region is left to the slow tier
+#define NFCAP HC_NFCAP   // listed NOFLOW cells per tile; a tile with more is "dense": its region is left to the slow tier
 
+__constant__ const int c_k_of_j[2][8] = {{2, 4, 7, 6, 5, 3, 0, 1}, {4, 2, 1, 0, 3, 5, 6, 7}};   // 3 x 3 slot of table neighbour j
+
+// generic entry points (a D8 raster handed in by the caller, row bands): the lists k_apply_d8 builds on the fly in the
+// whole-raster chain.  One CTA per tile: compact the NOFLOW cells (one byte read per cell), then look at the 3 x 3
+// elevations of just those cells for the record (equal-elevation neighbours, "touches higher ground").
 __global__ void __launch_bounds__(256)
-k_flat_list(const uint8_t *__restrict__ dir, int ny, int nx, unsigned short *__restrict__ lists, u32 *__restrict__ counts) {
+k_flat_list(const float *__restrict__ z, const uint8_t *__restrict__ dir, int ny, int nx, float nodata, hc_nf_lists nfl, hc_rows rw) {
   __shared__ u32 s_w[8];
+  __shared__ unsigned short s_li[NFCAP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = tid >> 2, lc0 = (tid & 3) * 16;
   const int r = blockIdx.y * T + lr, c0 = blockIdx.x * T + lc0;
@@ -257,17 +95,43 @@ k_flat_list(const uint8_t *__restrict__ dir, int ny, int nx, unsigned short *__r
   for (int o = 1; o < 32; o <<= 1) { u32 t_ = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t_; }
   if (lane == 31) s_w[warp] = inc;
   __syncthreads();
-  u32 base = 0;
-  for (int w = 0; w < warp; w++) base += s_w[w];
+  u32 base = 0, total = 0;
+  for (int w = 0; w < 8; w++) { if (w < warp) base += s_w[w]; total += s_w[w]; }
   u32 off = base + inc - cnt;
   const size_t tile = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
   while (m) {
     const int j = __ffs(m) - 1;
     m &= m - 1;
-    if (off < NFCAP) lists[tile * NFCAP + off] = (unsigned short)(lr * T + lc0 + j);
+    if (off < NFCAP) s_li[off] = (unsigned short)(lr * T + lc0 + j);
     off++;
   }
-  if (tid == 255) counts[tile] = base + inc;
+  if (tid == 0) nfl.counts[tile] = total;
+  __syncthreads();
+  const u32 nl = total < NFCAP ? total : NFCAP;
+  for (u32 k = tid; k < nl; k += 256) {
+    const int li = s_li[k];
+    const int rr = blockIdx.y * T + (li >> 6), cc = blockIdx.x * T + (li & (T - 1));
+    const float v = __ldg(z + (long long)rr * nx + cc);
+    u32 eq = 0, hi = 0;
+    int kb = 0;
+#pragma unroll
+    for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+      for (int dc = -1; dc <= 1; dc++) {
+        if (!dr && !dc) continue;
+        const int nr = rr + dr, nc = cc + dc;
+        if (nr >= rw.rlo && nr < rw.rhi && nc >= 0 && nc < nx) {
+          const float zn = __ldg(z + (long long)nr * nx + nc);
+          if (zn != nodata) {
+            if (zn == v) eq |= 1u << kb;
+            else if (zn > v) hi = HC_NF_HI;
+          }
+        }
+        kb++;
+      }
+    nfl.entries[tile * NFCAP + k] = (unsigned short)((u32)li | hi);
+    nfl.eq[tile * NFCAP + k] = (uint8_t)eq;
+  }
 }
 
 #define FS_THREADS 128
@@ -275,14 +139,13 @@ k_flat_list(const uint8_t *__restrict__ dir, int ny, int nx, unsigned short *__r
 
 template <int TABLE>
 __global__ void __launch_bounds__(FS_THREADS)
-k_flat_fast_sparse(const float *__restrict__ z, const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB,
-                   const unsigned short *__restrict__ lists, const u32 *__restrict__ counts,
-                   uint8_t *__restrict__ tile_pending, int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw) {
+k_flat_fast_sparse(const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB, const hc_nf_lists nfl,
+                   uint8_t *__restrict__ tile_pending, int ny, int nx, unsigned long long *dbg, hc_rows rw) {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned short *slo = (unsigned short *)smem;                          // [OPEN | NF | lo:14] per region cell
   unsigned short *shi = (unsigned short *)(smem + FR * FR * 2);
   unsigned short *list = (unsigned short *)(smem + FR * FR * 4);         // region index of the work cells
-  unsigned short *lmask = (unsigned short *)(smem + FR * FR * 4 + FLCAP * 2);   // [low-edge neighbours : 8 | NOFLOW neighbours : 8]
+  unsigned short *lmask = (unsigned short *)(smem + FR * FR * 4 + FLCAP * 2);   // [low-edge neighbours : 8 | NOFLOW neighbours : 8], 3 x 3 slots
   u32 *s_n = (u32 *)(smem + FR * FR * 4 + FLCAP * 4);                    // [0] work cells, [1] give up
   const int tid = threadIdx.x;
   const int by = blockIdx.y, bx = blockIdx.x, ty = gridDim.y, tx = gridDim.x;
@@ -293,16 +156,18 @@ k_flat_fast_sparse(const float *__restrict__ z, const uint8_t *__restrict__ dirA
     for (int i = tid; i < FR * FR * 4 / 16; i += FS_THREADS) q[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
-  // 1. the region's NOFLOW cells from the lists of the 3 x 3 tiles around
+  // 1. the region's NOFLOW cells from the records of the 3 x 3 tiles around: flags into the grid, the record (equal-
+  //    elevation neighbours, high edge) beside the work list -- no elevation is read here at all
   for (int t9 = 0; t9 < 9; t9++) {
     const int dy = t9 / 3 - 1, dx = t9 % 3 - 1;
     const int yy = by + dy, xx = bx + dx;
     if (yy < 0 || yy >= ty || xx < 0 || xx >= tx) continue;
     const size_t tile = (size_t)yy * tx + xx;
-    const u32 cnt = counts[tile];
+    const u32 cnt = nfl.counts[tile];
     if (cnt > NFCAP) { if (tid == 0) s_n[1] = 1; continue; }
     for (u32 k = tid; k < cnt; k += FS_THREADS) {
-      const int li = lists[tile * NFCAP + k];
+      const u32 e = nfl.entries[tile * NFCAP + k];
+      const int li = (int)(e & 0x0FFFu);
       const int rr = (li >> 6) + T * dy + FH, cc = (li & (T - 1)) + T * dx + FH;
       if (rr < 0 || rr >= FR || cc < 0 || cc >= FR) continue;
       const int ri = rr * FR + cc;
@@ -311,7 +176,10 @@ k_flat_fast_sparse(const float *__restrict__ z, const uint8_t *__restrict__ dirA
       else {
         slo[ri] = (unsigned short)F_NF;
         const u32 pos = atomicAdd(&s_n[0], 1u);
-        if (pos < FLCAP) list[pos] = (unsigned short)ri;
+        if (pos < FLCAP) {
+          list[pos] = (unsigned short)ri;
+          lmask[pos] = (unsigned short)(nfl.eq[tile * NFCAP + k] | ((e & HC_NF_HI) ? 0x100u : 0u));   // (record, resolved below)
+        }
       }
     }
   }
@@ -339,25 +207,16 @@ k_flat_fast_sparse(const float *__restrict__ z, const uint8_t *__restrict__ dirA
     //    direction (a low edge) it starts at lo = 2; equal NOFLOW neighbours are remembered as a mask
     for (u32 k = tid; k < nlist; k += FS_THREADS) {
       const int ri = list[k];
-      const int rr = ri / FR, cc = ri - rr * FR;
-      const int r = r0 + rr, c = c0 + cc;
-      const float v = __ldg(z + (long long)r * nx + c);
-      u32 mnf = 0, mlow = 0, hi = 0;
+      const u32 rec = lmask[k];
+      u32 mnf = 0;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const int dr = c_dr[TABLE][j], dc = c_dc[TABLE][j];
-        const int nr = r + dr, nc = c + dc;
-        if (nr < rw.rlo || nr >= rw.rhi || nc < 0 || nc >= nx) continue;
-        const float zn = __ldg(z + (long long)nr * nx + nc);
-        if (zn == nodata) continue;
-        if (zn > v) hi = 1;
-        else if (zn == v) {
-          if (slo[ri + dr * FR + dc] & F_NF) mnf |= 1u << j;
-          else mlow |= 1u << j;
-        }
+        const int kk = j + (j >= 4);
+        if (((rec >> j) & 1u) && (slo[ri + (kk / 3 - 1) * FR + (kk % 3 - 1)] & F_NF)) mnf |= 1u << j;
       }
+      const u32 mlow = (rec & 0xFFu) & ~mnf;
       lmask[k] = (unsigned short)((mlow << 8) | mnf);
-      shi[ri] = (unsigned short)hi;
+      shi[ri] = (unsigned short)((rec >> 8) & 1u);
       if (mlow) slo[ri] = (unsigned short)(F_NF | 2u);
     }
     __syncthreads();
@@ -376,7 +235,8 @@ k_flat_fast_sparse(const float *__restrict__ z, const uint8_t *__restrict__ dirA
         while (mnf) {
           const int j = __ffs(mnf) - 1;
           mnf &= mnf - 1;
-          const int ni = ri + c_dr[TABLE][j] * FR + c_dc[TABLE][j];
+          const int kk = j + (j >= 4);
+          const int ni = ri + (kk / 3 - 1) * FR + (kk % 3 - 1);
           const u32 nw = slo[ni];
           const u32 nlo = nw & F_LO;
           if (nlo && nlo + 1 < blo) blo = nlo + 1;
@@ -415,13 +275,14 @@ k_flat_fast_sparse(const float *__restrict__ z, const uint8_t *__restrict__ dirA
         bool bdiag = false;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
+          const int ks = c_k_of_j[TABLE][j];
           int key;
-          if ((mk >> j) & 1u) {
+          if ((mk >> ks) & 1u) {
             const int ni = ri + c_dr[TABLE][j] * FR + c_dc[TABLE][j];
             const u32 nw = slo[ni];
             if (!(nw & F_LO)) continue;
             key = 2 * (int)(nw & F_LO) - (int)shi[ni];
-          } else if ((mk >> (8 + j)) & 1u) {
+          } else if ((mk >> (8 + ks)) & 1u) {
             key = -0x40000000;
           } else continue;
           const bool kdiag = (c_dr[TABLE][j] != 0) && (c_dc[TABLE][j] != 0);
@@ -434,7 +295,7 @@ k_flat_fast_sparse(const float *__restrict__ z, const uint8_t *__restrict__ dirA
   } else {
     // dense / overflowing region: every NOFLOW cell of the own tile goes to the slow tier
     const size_t tile = (size_t)by * tx + bx;
-    const u32 cnt = counts[tile];
+    const u32 cnt = nfl.counts[tile];
     if (cnt > NFCAP) {
       for (int i = tid; i < T * T; i += FS_THREADS) {
         const int r = by * T + i / T, c = bx * T + i % T;
@@ -442,7 +303,7 @@ k_flat_fast_sparse(const float *__restrict__ z, const uint8_t *__restrict__ dirA
       }
     } else {
       for (u32 k = tid; k < cnt; k += FS_THREADS) {
-        const int li = lists[tile * NFCAP + k];
+        const int li = nfl.entries[tile * NFCAP + k] & 0x0FFFu;
         dirB[(size_t)(by * T + (li >> 6)) * nx + (bx * T + (li & (T - 1)))] = HC_DIR_PENDING;
         pend = 1;
       }
@@ -474,22 +335,67 @@ __global__ void k_flat_dilate(const uint8_t *__restrict__ pending, uint8_t *__re
 // ================================================================================================
 // slow tier (general: any flat size), restricted to `active` tiles
 // ================================================================================================
-// nf[c]  = 1 if c is valid and has no direction (NOFLOW)
-// dlo[c] = 1 for low edges (valid, has a direction, touches an equal-elevation NOFLOW cell)
-// dhi[c] = 1 for high edges (NOFLOW, touches a higher valid cell); 0 = not reached yet
+// State lives in two rasters that only ever mean something AT NOFLOW CELLS of active tiles:
+//   dlo[c] = 1 + geodesic distance to the nearest low edge through the flat (a cell next to a low edge starts at 2)
+//   dhi[c] = 1 + geodesic distance to the nearest high edge (a NOFLOW cell touching higher ground is 1); 0 = not reached
+// A valid cell WITH a direction that touches an equal NOFLOW cell is a low edge: constant 1, never stored -- whoever
+// looks at an equal-elevation neighbour asks the D8 raster (dirA) whether it is NOFLOW first.
+//
+// k_flat_init_lists: tiles with at most NFCAP NOFLOW cells start from their records (no elevation, no window): the
+// record says which neighbours share the elevation and whether the cell is a high edge; dirA says which of those
+// neighbours have a direction.  Also decides whether the tile must be relaxed before anyone asks for it: yes if it
+// holds pending cells itself, or if one of its NOFLOW cells touches a PENDING cell of the same elevation in a
+// neighbouring tile (it then holds part of a flat that is open over there, possibly with that flat's only sources).
+__global__ void __launch_bounds__(256)
+k_flat_init_lists(const uint8_t *__restrict__ dirA, const uint8_t *__restrict__ dirB, u32 *__restrict__ dlo, u32 *__restrict__ dhi,
+                  const uint8_t *__restrict__ active, const uint8_t *__restrict__ pending, uint8_t *__restrict__ startq,
+                  const hc_nf_lists nfl, int ny, int nx, hc_rows rw, int start_all) {
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  if (!active[tile]) { if (threadIdx.x == 0) startq[tile] = 0; return; }
+  const u32 cnt = nfl.counts[tile];
+  if (cnt > NFCAP) return;   // the window form below takes the dense tiles
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  int touch = 0;
+  for (u32 k = threadIdx.x; k < cnt; k += 256) {
+    const u32 e = nfl.entries[(size_t)tile * NFCAP + k];
+    const u32 eq = nfl.eq[(size_t)tile * NFCAP + k];
+    const int lr = (int)((e & 0x0FFFu) >> 6), lc = (int)(e & 63u);
+    const long long g = (long long)(r0 + lr) * nx + (c0 + lc);
+    u32 lo = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (!((eq >> j) & 1u)) continue;
+      const int kk = j + (j >= 4);
+      const int dr = kk / 3 - 1, dc = kk % 3 - 1;
+      const long long gn = g + (long long)dr * nx + dc;
+      if (__ldg(dirA + gn) != HC_DIR_NOFLOW) lo = 2;
+      else {
+        const int nr = lr + dr, nc = lc + dc;
+        if ((nr < 0 || nr >= T || nc < 0 || nc >= T) && r0 + nr >= 0 && r0 + nr < ny && __ldcg(dirB + gn) == HC_DIR_PENDING) touch = 1;
+      }
+    }
+    dlo[g] = lo;
+    dhi[g] = (e & HC_NF_HI) ? 1u : 0u;
+  }
+  touch = __syncthreads_or(touch);
+  if (threadIdx.x == 0) {
+    // a band cannot see the neighbouring band's pending marks: its seam tile rows always start
+    const bool seam = (rw.top && blockIdx.y == 0) || (rw.bot && blockIdx.y == gridDim.y - 1);
+    startq[tile] = (uint8_t)((pending[tile] || touch || seam || start_all) ? 1 : 0);
+  }
+}
+
+// window form for the dense tiles (more than NFCAP NOFLOW cells: lakes): same initial state from the staged tile
 __global__ void __launch_bounds__(NTHREADS)
 k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const uint8_t *__restrict__ dirB,
-            uint8_t *__restrict__ nf, u32 *__restrict__ dlo, u32 *__restrict__ dhi,
-            const uint8_t *__restrict__ active, const uint8_t *__restrict__ pending, uint8_t *__restrict__ startq,
-            unsigned short *__restrict__ tlist, uint8_t *__restrict__ tmask, u32 *__restrict__ tcount,
-            int ny, int nx, float nodata, hc_rows rw, int start_all, unsigned long long *dbgp) {
-  __shared__ u32 s_cnt;
+            u32 *__restrict__ dlo, u32 *__restrict__ dhi, const uint8_t *__restrict__ active,
+            const uint8_t *__restrict__ pending, uint8_t *__restrict__ startq, const u32 *__restrict__ counts,
+            int ny, int nx, float nodata, hc_rows rw, int start_all) {
   __shared__ float sz[TH * TH];
   __shared__ uint8_t sd[TH * TH];
   __shared__ uint8_t sp[TH * TH];   // dirB: the fast tier's PENDING marks, looked at on the halo ring only
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (!active[tile]) { if (threadIdx.x == 0) { startq[tile] = 0; tcount[tile] = 0; } return; }
-  if (threadIdx.x == 0) s_cnt = 0;
+  if (!active[tile] || counts[tile] <= NFCAP) return;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
@@ -510,10 +416,6 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
     sp[i] = pb;
   }
   __syncthreads();
-  // Does this tile have to be relaxed before anyone asks for it?  Yes if it holds pending cells itself, or if one
-  // of its NOFLOW cells touches a PENDING cell of the same elevation in a neighbouring tile (it then holds part of
-  // a flat that is open over there, possibly with that flat's only sources).  Every other active tile just keeps
-  // its initial values until a neighbour's rim shows it something better.
   int touch = 0;
   for (int i = tid; i < T * T; i += NTHREADS) {
     int lr = i / T, lc = i - lr * T;
@@ -521,65 +423,31 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
     if (r >= ny || c >= nx) continue;
     int ci = (lr + 1) * TH + lc + 1;
     float v = sz[ci];
-    uint8_t isnf = 0;
+    if (!(v == v) || sd[ci] != HC_DIR_NOFLOW) continue;
     u32 lo = 0, hi = 0;
-    if (v == v) {
-      isnf = sd[ci] == HC_DIR_NOFLOW;
-      if (isnf && (lr == 0 || lc == 0 || lr == T - 1 || lc == T - 1 || r == ny - 1 || c == nx - 1)) {
 #pragma unroll
-        for (int dr = -1; dr <= 1; dr++)
+    for (int dr = -1; dr <= 1; dr++)
 #pragma unroll
-          for (int dc = -1; dc <= 1; dc++) {
-            const int hr = lr + 1 + dr, hc = lc + 1 + dc;
-            if (hr >= 1 && hr <= T && hc >= 1 && hc <= T) continue;   // own cell
-            const int ni = hr * TH + hc;
-            if (sz[ni] == v && sp[ni] == HC_DIR_PENDING) touch = 1;
-          }
-      }
-#pragma unroll
-      for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-        for (int dc = -1; dc <= 1; dc++) {
-          if (!dr && !dc) continue;
-          int ni = ci + dr * TH + dc;
-          float zn = sz[ni];
-          if (zn != zn) continue;
-          if (isnf) { if (zn > v) hi = 1; }
-          else { if (zn == v && sd[ni] == HC_DIR_NOFLOW) lo = 1; }
+      for (int dc = -1; dc <= 1; dc++) {
+        if (!dr && !dc) continue;
+        const int hr = lr + 1 + dr, hc = lc + 1 + dc;
+        const int ni = hr * TH + hc;
+        const float zn = sz[ni];
+        if (zn != zn) continue;
+        if (zn > v) hi = 1;
+        else if (zn == v) {
+          if (sd[ni] != HC_DIR_NOFLOW) lo = 2;
+          else if (!(hr >= 1 && hr <= T && hc >= 1 && hc <= T) && r + dr >= 0 && r + dr < ny && sp[ni] == HC_DIR_PENDING) touch = 1;
         }
-    }
-    size_t g = (size_t)r * nx + c;
-    // every NOFLOW cell of an active tile takes part: a flat can be resolved in one tile (it fits
-    // that tile's apron) and pending in the next, and its distances must still flow through both
-    nf[g] = isnf;
+      }
+    const size_t g = (size_t)r * nx + c;
     dlo[g] = lo;
     dhi[g] = hi;
-    if (isnf) {
-      // compact list for the light relaxation path: local index + mask of the equal-elevation neighbours
-      // (bit k = k-th neighbour of the 3x3 window in row-major order, centre skipped)
-      u32 m = 0;
-      int k = 0;
-#pragma unroll
-      for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-        for (int dc = -1; dc <= 1; dc++) {
-          if (!dr && !dc) continue;
-          if (sz[ci + dr * TH + dc] == v) m |= 1u << k;
-          k++;
-        }
-      u32 pos = atomicAdd(&s_cnt, 1u);
-      if (pos < FL_LCAP) {
-        tlist[(size_t)tile * FL_LCAP + pos] = (unsigned short)(lr * T + lc);
-        tmask[(size_t)tile * FL_LCAP + pos] = (uint8_t)m;
-      }
-    }
   }
   touch = __syncthreads_or(touch);
   if (tid == 0) {
-    // a band cannot see the neighbouring band's pending marks: its seam tile rows always start
     const bool seam = (rw.top && blockIdx.y == 0) || (rw.bot && blockIdx.y == gridDim.y - 1);
     startq[tile] = (uint8_t)((pending[tile] || touch || seam || start_all) ? 1 : 0);
-    tcount[tile] = s_cnt;
   }
 }
 
@@ -644,7 +512,7 @@ __device__ __forceinline__ int cone_sweep(u32 *val, unsigned short *smk, const i
 
 // one visit of a lake tile (by, bx): load the window, relax to the local fixed point, write back, queue the neighbours
 // that can improve
-__device__ __forceinline__ void relax_tile(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
+__device__ __forceinline__ void relax_tile(const float *__restrict__ z, const uint8_t *__restrict__ dirA, u32 *dlo, u32 *dhi,
                                            const uint8_t *__restrict__ active, u32 *__restrict__ list_out,
                                            u32 *__restrict__ n_out, u32 *__restrict__ queued, const u32 stamp,
                                            uint8_t *__restrict__ visited, int ny, int nx, float nodata,
@@ -677,17 +545,19 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
   for (int i = tid; i < TH * TH; i += NTHREADS) {
     const int lr = i / TH, lc = i - lr * TH;
     const int r = r0 + lr - 1, c = c0 + lc - 1;
-    // halo cells of tiles outside the active set hold no state: treat as not in any flat
     const int ay = lr == 0 ? 0 : (lr == TH - 1 ? 2 : 1), ax = lc == 0 ? 0 : (lc == TH - 1 ? 2 : 1);
     // (a band's halo rows hold the neighbouring band's state, refreshed between relaxations)
     const bool halo_row = (r == -1 && rw.top) || (r == ny && rw.bot);
-    const bool inb = c >= 0 && c < nx && ((r >= 0 && r < ny && s_act[ay * 3 + ax]) || halo_row);
-    const long long g = inb ? (long long)r * nx + c : 0;
+    const bool inr = c >= 0 && c < nx && ((r >= 0 && r < ny) || halo_row);
+    const long long g = inr ? (long long)r * nx + c : 0;
     const float v = __ldg(z + g);
-    u32 lo = __ldcg(dlo + g);
-    u32 hi = __ldcg(dhi + g);
-    uint8_t f = __ldcg(nf + g);
-    if (!inb) { lo = 0; hi = 0; f = 0; }
+    const bool nfc = __ldg(dirA + g) == HC_DIR_NOFLOW;
+    // NOFLOW cells of tiles outside the active set hold no state: not in any flat (they cannot share a flat with a pending
+    // cell); a cell WITH a direction needs no state -- it only matters as the low edge of an equal NOFLOW neighbour: constant 1
+    const bool f = inr && nfc && (halo_row || s_act[ay * 3 + ax]);
+    const bool inb = inr && (f || !nfc);
+    u32 lo = 1, hi = 0;
+    if (f) { lo = __ldcg(dlo + g); hi = __ldcg(dhi + g); }
     sz[lr * TP + lc] = (inb && v != nodata) ? v : qnan;
     slo[lr * TP + lc] = lo ? lo : R_INF;
     shi[lr * TP + lc] = hi ? hi : R_INF;
@@ -789,7 +659,7 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
 // swept on the L2-resident rasters: eight dependent L2 round trips per cell and sweep).  Same re-queue / wake rules as
 // the window path.
 #define FL_PER (FL_LCAP / NTHREADS)
-__device__ __forceinline__ void relax_light(const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi, const uint8_t *__restrict__ active,
+__device__ __forceinline__ void relax_light(const uint8_t *__restrict__ dirA, u32 *dlo, u32 *dhi, const uint8_t *__restrict__ active,
                                             const unsigned short *__restrict__ tlist, const uint8_t *__restrict__ tmask,
                                             const u32 cnt, u32 *__restrict__ list_out, u32 *__restrict__ n_out,
                                             u32 *__restrict__ queued, const u32 stamp, uint8_t *visited, int ny, int nx, int tx,
@@ -817,7 +687,7 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ nf, u32 
     const u32 k = tid + j * NTHREADS;
     msk[j] = 0; g[j] = 0; lo[j] = hi[j] = R_INF;
     if (k < cnt) {
-      const u32 li = tlist[(size_t)t * FL_LCAP + k];
+      const u32 li = tlist[(size_t)t * FL_LCAP + k] & 0x0FFFu;
       msk[j] = tmask[(size_t)t * FL_LCAP + k] | 0x100u | (li << 16);   // bit 8 = "this slot holds a cell"
       g[j] = (long long)(r0 + (int)(li >> 6)) * nx + (c0 + (int)(li & 63u));
       const u32 a = __ldcg(dlo + g[j]), b = __ldcg(dhi + g[j]);
@@ -857,9 +727,10 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ nf, u32 
         // a cell of a tile outside the active set holds no state (its rasters were never initialised): not in any flat,
         // as in the window path; rows -1 / ny are a band's halo rows, whose state the exchange maintains
         const int rn = r0 + nr;
-        if (rn >= 0 && rn < ny && !active[(rn >> 6) * tx + ((c0 + nc) >> 6)]) continue;
         const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
-        const u32 a = __ldcg(dlo + gn), b = __ldcg(dhi + gn);    // (dhi of a cell with a direction is 0)
+        if (__ldg(dirA + gn) != HC_DIR_NOFLOW) { elo = min(elo, 2u); continue; }   // a low edge of the same elevation (needs no state)
+        if (rn >= 0 && rn < ny && !active[(rn >> 6) * tx + ((c0 + nc) >> 6)]) continue;
+        const u32 a = __ldcg(dlo + gn), b = __ldcg(dhi + gn);
         if (a) elo = min(elo, a + 1u);
         if (b) ehi = min(ehi, b + 1u);
       }
@@ -951,7 +822,7 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ nf, u32 
       const u32 tt = (u32)(yy * tx + xx);
       if (!active[tt]) continue;
       const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
-      const u32 f = __ldcg(nf + gn), a = __ldcg(dlo + gn), b = __ldcg(dhi + gn);
+      const u32 f = __ldg(dirA + gn) == HC_DIR_NOFLOW, a = __ldcg(dlo + gn), b = __ldcg(dhi + gn);
       if (!f) continue;
       const u32 nlo = a ? a : R_INF, nhi = b ? b : R_INF;
       const bool benefit = c && (lo[j] + 1u < nlo || hi[j] + 1u < nhi);
@@ -973,7 +844,7 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ nf, u32 
 // A tile is appended to the next queue by the first visit that stamps it with the round's number (`queued` holds 0 or 1
 // on entry -- 1 for tiles the caller queued -- and rounds stamp from 2 on, so no per-round clearing is needed).
 __global__ void __launch_bounds__(NTHREADS, 3)
-k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *dlo, u32 *dhi,
+k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ dirA, u32 *dlo, u32 *dhi,
              const uint8_t *__restrict__ active, u32 *qA, u32 *qB, u32 *ctl, u32 *__restrict__ queued,
              uint8_t *visited, const unsigned short *__restrict__ tlist, const uint8_t *__restrict__ tmask,
              const u32 *__restrict__ tcount, int ny, int nx, float nodata, unsigned long long *dbg, hc_rows rw, int tx, int ty) {
@@ -1011,9 +882,9 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ nf, u32 *d
       const u32 cnt = tcount[t];
       if (!cnt) continue;
       if (cnt <= FL_LCAP)
-        relax_light(nf, dlo, dhi, active, tlist, tmask, cnt, lout, nout, queued, stamp, visited, ny, nx, tx, ty, dbg, t, smem);
+        relax_light(dirA, dlo, dhi, active, tlist, tmask, cnt, lout, nout, queued, stamp, visited, ny, nx, tx, ty, dbg, t, smem);
       else
-        relax_tile(z, nf, dlo, dhi, active, lout, nout, queued, stamp, visited, ny, nx, nodata, dbg, rw, (int)(t / tx), (int)(t % tx), tx, ty, smem);
+        relax_tile(z, dirA, dlo, dhi, active, lout, nout, queued, stamp, visited, ny, nx, nodata, dbg, rw, (int)(t / tx), (int)(t % tx), tx, ty, smem);
     }
     grid.sync();
     u32 *sw = lin; lin = lout; lout = sw;
@@ -1031,7 +902,7 @@ __global__ void k_flat_queue_tiles(const uint8_t *__restrict__ active, u32 first
 // masked D8 for the pending cells
 template <int TABLE>
 __global__ void __launch_bounds__(256)
-k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ nf, const u32 *__restrict__ dlo,
+k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ dirA, const u32 *__restrict__ dlo,
             const u32 *__restrict__ dhi, uint8_t *__restrict__ dirB, const uint8_t *__restrict__ pending,
             int ny, int nx, float nodata, hc_rows rw) {
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
@@ -1059,7 +930,7 @@ k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ nf, const u
         float zn = z[gn];
         if (zn != v) continue;  // also drops nodata / NaN
         long long key;
-        if (nf[gn]) {
+        if (dirA[gn] == HC_DIR_NOFLOW) {
           u32 nlo = dlo[gn];
           if (!nlo) continue;
           key = 2ll * (long long)nlo - (long long)dhi[gn];
@@ -1076,15 +947,16 @@ k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ nf, const u
 }
 
 size_t flats_workspace(int64_t ny, int64_t nx) {
-  size_t n = (size_t)ny * nx;
+  size_t n = (size_t)(ny + 2) * nx;
   size_t tiles = (size_t)((ny + T - 1) / T) * ((nx + T - 1) / T);
-  return 2 * hc_align(n) + 2 * hc_align(n * 4) + 4 * hc_align(tiles) + hc_align(256);
+  // NOFLOW records (3 B x NFCAP per tile), two distance rasters, per-tile maps and queues
+  return hc_align(tiles * NFCAP * 2) + hc_align(tiles * NFCAP) + 2 * hc_align(n * 4) + 4 * hc_align(tiles) + 4 * hc_align(tiles * 4) + hc_align(256);
 }
 
 // ---- the pass in pieces (the whole-raster call runs them back to back; a band interleaves the
 // ---- relaxation with seam exchanges).  State lives in ctx->band.
 static int flats_fast_tier(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx,
-                           float nodata, int table, hc_rows rw, cudaStream_t st) {
+                           float nodata, int table, hc_rows rw, cudaStream_t st, const hc_nf_lists *pre) {
   hc_band_state *bs = &ctx->band;
   const int tx = (int)((nx + T - 1) / T), ty = (int)((ny + T - 1) / T);
   const size_t tiles = (size_t)tx * ty;
@@ -1096,38 +968,32 @@ static int flats_fast_tier(hc_ctx *ctx, const float *z, const uint8_t *dirA, uin
   bs->flag = (u32 *)arena_take(ctx, 256);   // [1] pending tiles, [2..3] halo changed, [8] n(qA), [9] n(qB)
   if (!bs->pending || !bs->active || !bs->qA || !bs->qB || !bs->queued || !bs->flag) return HC_ERR_NOMEM;
   bs->fz = z; bs->dirA = dirA; bs->dirB = dirB; bs->nb = ny; bs->nx = nx; bs->nodata = nodata; bs->table = table;
-  bs->nf = nullptr;
 
   static bool attr_set = false;
   if (!attr_set) {
     HC_CUDA(cudaFuncSetAttribute(k_flat_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, FLAT_SMEM));
-    HC_CUDA(cudaFuncSetAttribute(k_flat_fast<HC_TABLE_WBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
-    HC_CUDA(cudaFuncSetAttribute(k_flat_fast<HC_TABLE_TAUDEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
     attr_set = true;
   }
   dim3 tg(tx, ty);
-  if (getenv("HC_FLAT_DENSE_FAST")) {
-    HC_PROF(ctx, st, "k_flat_fast");
-    if (table == HC_TABLE_WBT)
-      k_flat_fast<HC_TABLE_WBT><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
-    else
-      k_flat_fast<HC_TABLE_TAUDEM><<<tg, NTHREADS, FAST_SMEM, st>>>(z, dirA, dirB, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
-    HC_LAUNCH_CHECK(ctx);
-  } else {
-    // sparse fast tier: per-tile lists of the NOFLOW cells, then only those cells are looked at
-    unsigned short *lists = (unsigned short *)arena_take(ctx, tiles * NFCAP * 2);
-    u32 *counts = (u32 *)arena_take(ctx, tiles * 4);
-    if (!lists || !counts) return HC_ERR_NOMEM;
+  // per-tile records of the NOFLOW cells: handed in by the fused apply + D8 pass, or listed here from the D8 raster
+  hc_nf_lists nfl;
+  if (pre && pre->entries) nfl = *pre;
+  else {
+    nfl.entries = (unsigned short *)arena_take(ctx, tiles * NFCAP * 2);
+    nfl.eq = (uint8_t *)arena_take(ctx, tiles * NFCAP);
+    nfl.counts = (u32 *)arena_take(ctx, tiles * 4);
+    if (!nfl.entries || !nfl.eq || !nfl.counts) return HC_ERR_NOMEM;
     HC_PROF(ctx, st, "k_flat_list");
-    k_flat_list<<<tg, 256, 0, st>>>(dirA, (int)ny, (int)nx, lists, counts);
-    HC_LAUNCH_CHECK(ctx);
-    HC_PROF(ctx, st, "k_flat_fast_sparse");
-    if (table == HC_TABLE_WBT)
-      k_flat_fast_sparse<HC_TABLE_WBT><<<tg, FS_THREADS, FS_SMEM, st>>>(z, dirA, dirB, lists, counts, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
-    else
-      k_flat_fast_sparse<HC_TABLE_TAUDEM><<<tg, FS_THREADS, FS_SMEM, st>>>(z, dirA, dirB, lists, counts, bs->pending, (int)ny, (int)nx, nodata, ctx->d_dbg, rw);
+    k_flat_list<<<tg, 256, 0, st>>>(z, dirA, (int)ny, (int)nx, nodata, nfl, rw);
     HC_LAUNCH_CHECK(ctx);
   }
+  bs->tlist = nfl.entries; bs->tmask = nfl.eq; bs->tcount = nfl.counts;
+  HC_PROF(ctx, st, "k_flat_fast_sparse");
+  if (table == HC_TABLE_WBT)
+    k_flat_fast_sparse<HC_TABLE_WBT><<<tg, FS_THREADS, FS_SMEM, st>>>(dirA, dirB, nfl, bs->pending, (int)ny, (int)nx, ctx->d_dbg, rw);
+  else
+    k_flat_fast_sparse<HC_TABLE_TAUDEM><<<tg, FS_THREADS, FS_SMEM, st>>>(dirA, dirB, nfl, bs->pending, (int)ny, (int)nx, ctx->d_dbg, rw);
+  HC_LAUNCH_CHECK(ctx);
   HC_CUDA(cudaMemsetAsync(bs->flag, 0, 64, st));
   HC_PROF(ctx, st, "k_flat_dilate");
   k_flat_dilate<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(bs->pending, bs->active, tx, ty, bs->flag + 1, rw);
@@ -1145,28 +1011,27 @@ static int flats_slow_init(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   const size_t tiles = (size_t)tx * ty;
   // state rasters carry the band's halo rows (row -1 and row ny) like z and dir do
   const size_t nh = (size_t)(ny + 2) * nx;
-  uint8_t *nf = (uint8_t *)arena_take(ctx, nh);
   u32 *dlo = (u32 *)arena_take(ctx, nh * 4);
   u32 *dhi = (u32 *)arena_take(ctx, nh * 4);
-  if (!nf || !dlo || !dhi) return HC_ERR_NOMEM;
-  HC_CUDA(cudaMemsetAsync(nf, 0, (size_t)nx, st));
-  HC_CUDA(cudaMemsetAsync(nf + (size_t)(ny + 1) * nx, 0, (size_t)nx, st));
+  if (!dlo || !dhi) return HC_ERR_NOMEM;
   HC_CUDA(cudaMemsetAsync(dlo, 0, (size_t)nx * 4, st));
   HC_CUDA(cudaMemsetAsync(dlo + (size_t)(ny + 1) * nx, 0, (size_t)nx * 4, st));
   HC_CUDA(cudaMemsetAsync(dhi, 0, (size_t)nx * 4, st));
   HC_CUDA(cudaMemsetAsync(dhi + (size_t)(ny + 1) * nx, 0, (size_t)nx * 4, st));
-  bs->nf = nf + nx; bs->dlo = dlo + nx; bs->dhi = dhi + nx;
+  bs->dlo = dlo + nx; bs->dhi = dhi + nx;
   dim3 tg(tx, ty);
-  HC_PROF(ctx, st, "k_flat_init");
   uint8_t *startq = (uint8_t *)arena_take(ctx, tiles);
   bs->visited = (uint8_t *)arena_take(ctx, tiles);   // per-tile "visited" map of the slow tier
-  bs->tlist = (unsigned short *)arena_take(ctx, tiles * FL_LCAP * 2);
-  bs->tmask = (uint8_t *)arena_take(ctx, tiles * FL_LCAP);
-  bs->tcount = (u32 *)arena_take(ctx, tiles * 4);
-  if (!startq || !bs->visited || !bs->tlist || !bs->tmask || !bs->tcount) return HC_ERR_NOMEM;
+  if (!startq || !bs->visited) return HC_ERR_NOMEM;
   HC_CUDA(cudaMemsetAsync(bs->visited, 0, tiles, st));
-  k_flat_init<<<tg, NTHREADS, 0, st>>>(bs->fz, bs->dirA, bs->dirB, bs->nf, bs->dlo, bs->dhi, bs->active, bs->pending, startq,
-                                       bs->tlist, bs->tmask, bs->tcount, (int)ny, (int)nx, bs->nodata, rw, getenv("HC_FLAT_START_ALL") ? 1 : 0, ctx->d_dbg);
+  const int start_all = getenv("HC_FLAT_START_ALL") ? 1 : 0;
+  const hc_nf_lists nfl = {bs->tlist, bs->tmask, bs->tcount};
+  HC_PROF(ctx, st, "k_flat_init_lists");
+  k_flat_init_lists<<<tg, 256, 0, st>>>(bs->dirA, bs->dirB, bs->dlo, bs->dhi, bs->active, bs->pending, startq, nfl, (int)ny, (int)nx, rw, start_all);
+  HC_LAUNCH_CHECK(ctx);
+  HC_PROF(ctx, st, "k_flat_init");
+  k_flat_init<<<tg, NTHREADS, 0, st>>>(bs->fz, bs->dirA, bs->dirB, bs->dlo, bs->dhi, bs->active, bs->pending, startq, bs->tcount,
+                                       (int)ny, (int)nx, bs->nodata, rw, start_all);
   HC_LAUNCH_CHECK(ctx);
   // first relaxation visits every active tile: queue A
   HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
@@ -1193,7 +1058,7 @@ static int flats_relax_loop(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   const unsigned grid = (unsigned)(tiles < (size_t)max_blocks ? tiles : (size_t)max_blocks);
   int iny = (int)ny, inx = (int)nx;
   u32 *ctl = bs->flag + 8;
-  void *args[] = {(void *)&bs->fz, (void *)&bs->nf, (void *)&bs->dlo, (void *)&bs->dhi, (void *)&bs->active, (void *)&bs->qA,
+  void *args[] = {(void *)&bs->fz, (void *)&bs->dirA, (void *)&bs->dlo, (void *)&bs->dhi, (void *)&bs->active, (void *)&bs->qA,
                   (void *)&bs->qB, (void *)&ctl, (void *)&bs->queued, (void *)&bs->visited, (void *)&bs->tlist,
                   (void *)&bs->tmask, (void *)&bs->tcount, (void *)&iny, (void *)&inx, (void *)&bs->nodata, (void *)&ctx->d_dbg,
                   (void *)&rw, (void *)&tx, (void *)&ty};
@@ -1222,18 +1087,18 @@ static int flats_dirs(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   dim3 tg((unsigned)((nx + T - 1) / T), (unsigned)((ny + T - 1) / T));
   HC_PROF(ctx, st, "k_flat_dirs");
   if (bs->table == HC_TABLE_WBT)
-    k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->dirB, bs->pending, (int)ny, (int)nx, bs->nodata, rw);
+    k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, (int)ny, (int)nx, bs->nodata, rw);
   else
-    k_flat_dirs<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(bs->fz, bs->nf, bs->dlo, bs->dhi, bs->dirB, bs->pending, (int)ny, (int)nx, bs->nodata, rw);
+    k_flat_dirs<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, (int)ny, (int)nx, bs->nodata, rw);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
 
 // dirA: D8 codes with NOFLOW on flats (read only); dirB: output (may not alias dirA).
 int flats_core(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx,
-               float nodata, int table, cudaStream_t st) {
+               float nodata, int table, cudaStream_t st, const hc_nf_lists *pre = nullptr) {
   hc_rows rw = hc_make_rows(ny, 0);
-  HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, ny, nx, nodata, table, rw, st));
+  HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, ny, nx, nodata, table, rw, st, pre));
   if (!ctx->band.n_pending) return HC_OK;  // every flat was resolved inside its apron
   HC_TRY(flats_slow_init(ctx, rw, st));
   HC_TRY(flats_relax_loop(ctx, rw, st));
@@ -1241,8 +1106,8 @@ int flats_core(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, 
 }
 
 int flats_whole_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *dirB, int64_t ny, int64_t nx, float nodata,
-                      int table, cudaStream_t st, const uint8_t **tile_pending, int *n_pending) {
-  HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, ny, nx, nodata, table, hc_make_rows(ny, 0), st));
+                      int table, cudaStream_t st, const uint8_t **tile_pending, int *n_pending, const hc_nf_lists *pre) {
+  HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, ny, nx, nodata, table, hc_make_rows(ny, 0), st, pre));
   *tile_pending = ctx->band.pending;
   *n_pending = ctx->band.n_pending;
   return HC_OK;
@@ -1295,34 +1160,36 @@ int band_flats_begin(hc_ctx *ctx, const float *z, const uint8_t *dirA, uint8_t *
   HC_TRY(arena_reset(ctx));
   ctx->band.flags = flags;
   HC_CUDA(cudaMemcpyAsync(dirB, dirA, (size_t)nb * nx, cudaMemcpyDeviceToDevice, st));  // the fast tier only rewrites NOFLOW cells
-  HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, nb, nx, nodata, table, rw, st));
+  HC_TRY(flats_fast_tier(ctx, z, dirA, dirB, nb, nx, nodata, table, rw, st, nullptr));
   HC_TRY(flats_slow_init(ctx, rw, st));
   ctx->band.flats_ready = 1;
   return HC_OK;
 }
 
-// out[side][field][nx] (u32): side 0 = first own row, 1 = last own row; fields nf, dlo, dhi
-__global__ void k_flat_get_seams(const uint8_t *__restrict__ nf, const u32 *__restrict__ dlo, const u32 *__restrict__ dhi,
+// out[side][field][nx] (u32): side 0 = first own row, 1 = last own row; fields NOFLOW flag (informational: the
+// receiver has the row's D8 codes in its halo already), dlo, dhi
+__global__ void k_flat_get_seams(const uint8_t *__restrict__ dirA, const u32 *__restrict__ dlo, const u32 *__restrict__ dhi,
                                  int ny, int nx, u32 *__restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * nx) return;
   int side = i / nx, c = i - side * nx;
   size_t g = (size_t)(side ? ny - 1 : 0) * nx + c;
   u32 *o = out + (size_t)side * 3 * nx;
-  o[c] = nf[g];
-  o[nx + c] = dlo[g];
-  o[2 * (size_t)nx + c] = dhi[g];
+  const u32 f = dirA[g] == HC_DIR_NOFLOW ? 1u : 0u;
+  o[c] = f;
+  o[nx + c] = f ? dlo[g] : 0u;
+  o[2 * (size_t)nx + c] = f ? dhi[g] : 0u;
 }
 
 // write a halo row from the neighbour's seam record; flag[2] != 0 if anything differed
-__global__ void k_flat_put_halo(uint8_t *nf, u32 *dlo, u32 *dhi, long long row, int nx, const u32 *__restrict__ in,
-                                u32 *flag) {
+__global__ void k_flat_put_halo(u32 *dlo, u32 *dhi, long long row, int nx, const u32 *__restrict__ in, u32 *flag) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nx) return;
   long long g = row * nx + c;
-  u32 f = in[c], lo = in[nx + c], hi = in[2 * (size_t)nx + c];
-  if (nf[g] != (uint8_t)f || dlo[g] != lo || dhi[g] != hi) {
-    nf[g] = (uint8_t)f; dlo[g] = lo; dhi[g] = hi;
+  // (only NOFLOW cells carry state; a cell with a direction is a constant low edge on both sides of the seam)
+  u32 f = in[c], lo = f ? in[nx + c] : 0u, hi = f ? in[2 * (size_t)nx + c] : 0u;
+  if (dlo[g] != lo || dhi[g] != hi) {
+    dlo[g] = lo; dhi[g] = hi;
     *flag = 1u;
   }
 }
@@ -1331,7 +1198,7 @@ int band_flats_get_seams(hc_ctx *ctx, uint32_t *out, cudaStream_t st) {
   hc_band_state *bs = &ctx->band;
   if (!bs->flats_ready) { hc_set_error("band flats: begin first"); return HC_ERR_ARG; }
   HC_PROF(ctx, st, "k_flat_get_seams");
-  k_flat_get_seams<<<(unsigned)((2 * bs->nx + 255) / 256), 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, (int)bs->nb, (int)bs->nx, out);
+  k_flat_get_seams<<<(unsigned)((2 * bs->nx + 255) / 256), 256, 0, st>>>(bs->dirA, bs->dlo, bs->dhi, (int)bs->nb, (int)bs->nx, out);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
@@ -1345,12 +1212,12 @@ int band_flats_put_halos(hc_ctx *ctx, const uint32_t *top, const uint32_t *bot, 
   unsigned gb = (unsigned)((nx + 255) / 256);
   if (top && (bs->flags & 1)) {
     HC_PROF(ctx, st, "k_flat_put_halo");
-    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, -1ll, (int)nx, top, bs->flag + 2);
+    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->dlo, bs->dhi, -1ll, (int)nx, top, bs->flag + 2);
     HC_LAUNCH_CHECK(ctx);
   }
   if (bot && (bs->flags & 2)) {
     HC_PROF(ctx, st, "k_flat_put_halo");
-    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, (long long)ny, (int)nx, bot, bs->flag + 3);
+    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->dlo, bs->dhi, (long long)ny, (int)nx, bot, bs->flag + 3);
     HC_LAUNCH_CHECK(ctx);
   }
   HC_CUDA(cudaMemcpyAsync(ctx->h_mail, bs->flag + 2, 8, cudaMemcpyDeviceToHost, st));
@@ -1390,14 +1257,14 @@ int band_flats_put_halos_flag(hc_ctx *ctx, const uint32_t *top, const uint32_t *
   unsigned gb = (unsigned)((nx + 255) / 256), gt = (unsigned)((tx + 255) / 256);
   if (top && (bs->flags & 1)) {
     HC_PROF(ctx, st, "k_flat_put_halo");
-    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, -1ll, (int)nx, top, bs->flag + 2);
+    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->dlo, bs->dhi, -1ll, (int)nx, top, bs->flag + 2);
     HC_LAUNCH_CHECK(ctx);
     k_flat_queue_tiles_if<<<gt, 256, 0, st>>>(bs->active, 0u, (u32)tx, bs->queued, bs->qA, bs->flag + 8, bs->flag + 2, flag_dev);
     HC_LAUNCH_CHECK(ctx);
   }
   if (bot && (bs->flags & 2)) {
     HC_PROF(ctx, st, "k_flat_put_halo");
-    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->nf, bs->dlo, bs->dhi, (long long)ny, (int)nx, bot, bs->flag + 3);
+    k_flat_put_halo<<<gb, 256, 0, st>>>(bs->dlo, bs->dhi, (long long)ny, (int)nx, bot, bs->flag + 3);
     HC_LAUNCH_CHECK(ctx);
     k_flat_queue_tiles_if<<<gt, 256, 0, st>>>(bs->active, (u32)((ty - 1) * tx), (u32)tx, bs->queued, bs->qA, bs->flag + 8, bs->flag + 3, flag_dev);
     HC_LAUNCH_CHECK(ctx);

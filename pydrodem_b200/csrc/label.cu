@@ -124,6 +124,17 @@ k_lab_tile(const uint8_t *__restrict__ mask, u32 *__restrict__ L, int ny, int nx
     }
   }
   __syncthreads();
+  // every run start chases its chain ONCE and keeps the root (a store of an ancestor never misleads a concurrent chase);
+  // the cells of the run then read it with one shared load (before, each cell walked its run's chain by itself)
+  for (int i = tid; i < LT * LT; i += 256) {
+    const int lr = i >> 6, lc = i & (LT - 1);
+    const unsigned long long cur = rowbits[lr];
+    if (((cur >> lc) & 1ull) && (lc == 0 || !((cur >> (lc - 1)) & 1ull))) {
+      const u32 root = suf_find((volatile u32 *)sl, (u32)i);
+      ((volatile u32 *)sl)[i] = root;
+    }
+  }
+  __syncthreads();
   for (int i = tid; i < LT * LT; i += 256) {
     const int lr = i >> 6, lc = i & (LT - 1);
     const int r = r0 + lr, c = c0 + lc;
@@ -131,7 +142,7 @@ k_lab_tile(const uint8_t *__restrict__ mask, u32 *__restrict__ L, int ny, int nx
     u32 out = HC_NONE;
     const unsigned long long cur = rowbits[lr];
     if ((cur >> lc) & 1ull) {
-      const u32 root = suf_find((volatile u32 *)sl, (u32)(lr * LT + run_start(cur, lc)));
+      const u32 root = sl[lr * LT + run_start(cur, lc)];
       out = (u32)((size_t)(r0 + (int)(root >> 6)) * nx + (c0 + (int)(root & (LT - 1))));
     }
     L[(size_t)r * nx + c] = out;
