@@ -881,9 +881,8 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count(local) - launches0
     # per-kernel times: a profiled pass of the same steps right after the timed region (the library brackets every launch
-    # with CUDA events on the launching stream).  The chain's one concurrency -- the accumulation's tile phase beside the
-    # flats' slow tier -- is switched off for this pass, so that each kernel's events time that kernel alone.
-    os.environ["HC_NO_ACC_OVERLAP"] = "1"
+    # with CUDA events on the launching stream; the chain runs its kernels in sequence on one stream, so each kernel's
+    # events time that kernel alone)
     _lib.profile_enable(True, local)
     psteps = max(3, min(args.steps, 10))
     for _ in range(psteps):
@@ -891,7 +890,6 @@ def main():
     torch.cuda.synchronize()
     prof = {k: (c * args.steps / psteps, t_ * args.steps / psteps, m) for k, (c, t_, m) in _lib.profile_read(local).items()}
     _lib.profile_enable(False, local)
-    del os.environ["HC_NO_ACC_OVERLAP"]
     basins, rounds = hc.core.fill_stats(local)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -1005,8 +1003,8 @@ def main():
                    "cells_per_gpu": cells, "l2": "inputs (467 MB z + outputs) exceed the 126 MB L2; no explicit flush",
                    "device_raster": "dense" if args.dense else "pitched (core.empty_raster, hc_fill_d8_accum_ld_dev): TMA path",
                    "flats": bool(args.flats), "basins": basins, "boruvka_rounds": rounds,
-                   "kernel_times": "profiled pass right after the timed region (same inputs, per-launch CUDA events, "
-                                   "accumulation / flats overlap off); the timed region itself runs unprofiled",
+                   "kernel_times": "profiled pass right after the timed region (same inputs, per-launch CUDA events); "
+                                   "the timed region itself runs unprofiled",
                    "algorithmic_bytes_per_cell": 18},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "hbm_frac_algorithmic_whole_step": 18 * cells / (ms_max / args.steps * 1e-3) / 1e9 / peak,

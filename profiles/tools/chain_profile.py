@@ -47,7 +47,7 @@ torch.cuda.synchronize()
 dbg = [int(x) for x in _lib.debug_read(0)]
 dbg_names = {0: "fast_sweeps", 1: "fast_tiles_with_work", 2: "pending_tiles", 3: "slow_sweeps", 4: "slow_visits",
              5: "lake_visits", 6: "light_visits", 8: "edges_general_path_tiles", 9: "light_cycles", 10: "lake_cycles",
-             11: "lake_iterations", 12: "light_le64", 13: "light_le128", 14: "light_le256", 15: "light_cells"}
+             11: "lake_iterations", 12: "light_cycles_load", 13: "light_cycles_fold", 14: "light_cycles_sweeps", 15: "light_cells"}
 rows = sorted(((k, c / steps, t / steps) for k, (c, t, m) in prof.items()), key=lambda r: -r[2])
 print(json.dumps({"size": n, "workload": wl, "ms_per_step": ms_plain, "kernel_ms_sum": sum(r[2] for r in rows),
                   "fill_stats": hc.core.fill_stats(0), "debug": {v: dbg[k] for k, v in dbg_names.items()},

@@ -1408,7 +1408,9 @@ int fill_d8_flats_accum_run(hc_ctx *ctx, const float *z, float *filled, uint8_t 
                             int64_t nx, float nodata, double dx, double dy, int seed_mode, int table, int resolve_flats,
                             cudaStream_t st) {
   if (ny <= 0 || nx <= 0) return HC_OK;
-  if (!resolve_flats || getenv("HC_NO_ACC_OVERLAP")) {
+  // (measured on B200: the slow tier's persistent CTAs hold most of every SM's shared memory, so the accumulation's tile
+  // phase gains nothing beside it -- C2 6.91 ms in sequence, 7.04 ms overlapped; the split form stays behind HC_ACC_OVERLAP)
+  if (!resolve_flats || !getenv("HC_ACC_OVERLAP")) {
     HC_TRY(fill_d8_flats_run(ctx, z, filled, dir, slope, ny, nx, nodata, dx, dy, seed_mode, table, resolve_flats, st));
     return accum_run(ctx, dir, acc, ny, nx, table, st);
   }

@@ -150,37 +150,63 @@ k_flat_fast_sparse(const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB,
   const int tid = threadIdx.x;
   const int by = blockIdx.y, bx = blockIdx.x, ty = gridDim.y, tx = gridDim.x;
   const int r0 = by * T - FH, c0 = bx * T - FH;
+  // the nine tiles' counts and every thread's first two records of each tile are requested before anything is looked
+  // at: the gather is a handful of dependent round trips to L2 / HBM, and with one tile after the other (count ->
+  // records -> next tile's count ...) those round trips were most of the kernel's time
+  u32 cnt9[9];
+#pragma unroll
+  for (int t9 = 0; t9 < 9; t9++) {
+    const int yy = by + t9 / 3 - 1, xx = bx + t9 % 3 - 1;
+    cnt9[t9] = (yy >= 0 && yy < ty && xx >= 0 && xx < tx) ? __ldg(nfl.counts + (size_t)yy * tx + xx) : 0u;
+  }
   if (tid < 2) s_n[tid] = 0;
   {
     uint4 *q = (uint4 *)smem;
     for (int i = tid; i < FR * FR * 4 / 16; i += FS_THREADS) q[i] = make_uint4(0, 0, 0, 0);
   }
+  bool dense = false;   // (every thread sees the same counts: no shared flag needed)
+#pragma unroll
+  for (int t9 = 0; t9 < 9; t9++)
+    if (cnt9[t9] > NFCAP) { dense = true; cnt9[t9] = 0; }
+  u32 rec9[9][2];
+#pragma unroll
+  for (int t9 = 0; t9 < 9; t9++) {
+    const size_t base = ((size_t)(by + t9 / 3 - 1) * tx + (bx + t9 % 3 - 1)) * NFCAP;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const u32 k = tid + h * FS_THREADS;
+      rec9[t9][h] = k < cnt9[t9] ? ((u32)__ldg(nfl.entries + base + k) | ((u32)__ldg(nfl.eq + base + k) << 16)) : 0xFFFFFFFFu;
+    }
+  }
   __syncthreads();
   // 1. the region's NOFLOW cells from the records of the 3 x 3 tiles around: flags into the grid, the record (equal-
   //    elevation neighbours, high edge) beside the work list -- no elevation is read here at all
-  for (int t9 = 0; t9 < 9; t9++) {
+  auto put = [&](const int t9, const u32 rec) {
     const int dy = t9 / 3 - 1, dx = t9 % 3 - 1;
-    const int yy = by + dy, xx = bx + dx;
-    if (yy < 0 || yy >= ty || xx < 0 || xx >= tx) continue;
-    const size_t tile = (size_t)yy * tx + xx;
-    const u32 cnt = nfl.counts[tile];
-    if (cnt > NFCAP) { if (tid == 0) s_n[1] = 1; continue; }
-    for (u32 k = tid; k < cnt; k += FS_THREADS) {
-      const u32 e = nfl.entries[tile * NFCAP + k];
-      const int li = (int)(e & 0x0FFFu);
-      const int rr = (li >> 6) + T * dy + FH, cc = (li & (T - 1)) + T * dx + FH;
-      if (rr < 0 || rr >= FR || cc < 0 || cc >= FR) continue;
-      const int ri = rr * FR + cc;
-      // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
-      if (rr == 0 || cc == 0 || rr == FR - 1 || cc == FR - 1) slo[ri] = (unsigned short)(F_NF | F_OPEN);
-      else {
-        slo[ri] = (unsigned short)F_NF;
-        const u32 pos = atomicAdd(&s_n[0], 1u);
-        if (pos < FLCAP) {
-          list[pos] = (unsigned short)ri;
-          lmask[pos] = (unsigned short)(nfl.eq[tile * NFCAP + k] | ((e & HC_NF_HI) ? 0x100u : 0u));   // (record, resolved below)
-        }
+    const int li = (int)(rec & 0x0FFFu);
+    const int rr = (li >> 6) + T * dy + FH, cc = (li & (T - 1)) + T * dx + FH;
+    if (rr < 0 || rr >= FR || cc < 0 || cc >= FR) return;
+    const int ri = rr * FR + cc;
+    // a NOFLOW cell on the region's rim may continue outside the region: its flat is "open"
+    if (rr == 0 || cc == 0 || rr == FR - 1 || cc == FR - 1) slo[ri] = (unsigned short)(F_NF | F_OPEN);
+    else {
+      slo[ri] = (unsigned short)F_NF;
+      const u32 pos = atomicAdd(&s_n[0], 1u);
+      if (pos < FLCAP) {
+        list[pos] = (unsigned short)ri;
+        lmask[pos] = (unsigned short)(((rec >> 16) & 0xFFu) | ((rec & HC_NF_HI) ? 0x100u : 0u));   // (record, resolved below)
       }
+    }
+  };
+#pragma unroll
+  for (int t9 = 0; t9 < 9; t9++) {
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+      if (rec9[t9][h] != 0xFFFFFFFFu) put(t9, rec9[t9][h]);
+    if (cnt9[t9] > 2 * FS_THREADS) {
+      const size_t base = ((size_t)(by + t9 / 3 - 1) * tx + (bx + t9 % 3 - 1)) * NFCAP;
+      for (u32 k = tid + 2 * FS_THREADS; k < cnt9[t9]; k += FS_THREADS)
+        put(t9, (u32)__ldg(nfl.entries + base + k) | ((u32)__ldg(nfl.eq + base + k) << 16));
     }
   }
   // ... and a NOFLOW cell of a band's halo row belongs to the neighbouring band: open too (no tile lists them)
@@ -201,7 +227,7 @@ k_flat_fast_sparse(const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB,
   }
   __syncthreads();
   const u32 nlist = s_n[0];
-  bool giveup = nlist > FLCAP || s_n[1];
+  bool giveup = nlist > FLCAP || dense;
   if (!giveup && nlist) {
     // 2. edges: a NOFLOW cell next to higher ground is a high edge (hi = 1); next to an equal cell that HAS a
     //    direction (a low edge) it starts at lo = 2; equal NOFLOW neighbours are remembered as a mask
@@ -659,27 +685,61 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
 // swept on the L2-resident rasters: eight dependent L2 round trips per cell and sweep).  Same re-queue / wake rules as
 // the window path.
 #define FL_PER (FL_LCAP / NTHREADS)
+#define FL_RING (4 * T + 4)   // ring cells: row -1 (T + 2, corners included), row T (T + 2), column -1 (T), column T (T)
+#define RING_IDX(nr_, nc_) ((nr_) < 0 ? (nc_) + 1 : ((nr_) >= T ? (T + 2) + (nc_) + 1 : ((nc_) < 0 ? 2 * (T + 2) + (nr_) : 2 * (T + 2) + T + (nr_))))
+#define RING_TILE(nr_, nc_) (((nr_) < 0 ? 0 : ((nr_) >= T ? 2 : 1)) * 3 + ((nc_) < 0 ? 0 : ((nc_) >= T ? 2 : 1)))
 __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ dirA, u32 *dlo, u32 *dhi, const uint8_t *__restrict__ active,
                                             const unsigned short *__restrict__ tlist, const uint8_t *__restrict__ tmask,
                                             const u32 cnt, u32 *__restrict__ list_out, u32 *__restrict__ n_out,
                                             u32 *__restrict__ queued, const u32 stamp, uint8_t *visited, int ny, int nx, int tx,
-                                            int ty, unsigned long long *dbg, const u32 t, unsigned char *smem) {
+                                            int ty, unsigned long long *dbg, const u32 t, const hc_rows rw, unsigned char *smem) {
   unsigned short *grid = (unsigned short *)smem;        // [T * T] list position + 1 of a NOFLOW cell, else 0
   volatile u32 *vlo = (volatile u32 *)(smem + T * T * 2);   // [FL_LCAP]
   volatile u32 *vhi = vlo + FL_LCAP;
+  // snapshot of the one-cell ring around the tile (4 x 64 + 4 corners; RING_IDX), taken once at the start of the visit
+  // with one load per thread: 0 = no cell there, 1 = a cell with a direction, 2 = a NOFLOW cell (+ its two distances)
+  u32 *h_lo = (u32 *)(smem + T * T * 2 + FL_LCAP * 8);
+  u32 *h_hi = h_lo + FL_RING;
+  uint8_t *h_nf = (uint8_t *)(h_hi + FL_RING);
   __shared__ u32 s_want;
+  __shared__ uint8_t s_lact[9], s_lvis[9];   // the 3 x 3 tiles around: takes part in the slow tier / has been visited
   const int tid = threadIdx.x;
   const int by = (int)(t / tx), bx = (int)(t % tx);
   const int r0 = by * T, c0 = bx * T;
   __syncthreads();  // the previous visit of this CTA is completely done with the shared arrays
   const long long t_begin = clock64();
+  // every global read of the visit that does not depend on another one is issued here, side by side: the cell list,
+  // the ring, the neighbour tiles' flags (chains of dependent reads per rim cell were most of a visit's time)
+  for (int i = tid; i < FL_RING; i += NTHREADS) {
+    int nr, nc;
+    if (i < 2 * (T + 2)) { nr = i < T + 2 ? -1 : T; nc = (i < T + 2 ? i : i - (T + 2)) - 1; }
+    else { const int k = i - 2 * (T + 2); nc = k < T ? -1 : T; nr = k < T ? k : k - T; }
+    const int r = r0 + nr, c = c0 + nc;
+    u32 f = 0, a = 0, b = 0;
+    if (c >= 0 && c < nx && r >= rw.rlo && r < rw.rhi) {
+      const long long g = (long long)r * nx + c;
+      f = __ldg(dirA + g) == HC_DIR_NOFLOW ? 2u : 1u;
+      a = __ldcg(dlo + g);    // (meaningless unless f == 2 and the cell's tile takes part: looked at under those tests only)
+      b = __ldcg(dhi + g);
+    }
+    h_nf[i] = (uint8_t)f; h_lo[i] = a; h_hi[i] = b;
+  }
+  if (tid < 9) {
+    const int yy = by + tid / 3 - 1, xx = bx + tid % 3 - 1;
+    uint8_t a = 0, v = 1;
+    if (xx >= 0 && xx < tx) {
+      if (yy >= 0 && yy < ty) { a = active[yy * tx + xx]; v = __ldcg(visited + yy * tx + xx); }   // (L2: a persistent CTA's L1 may hold a stale 0)
+      else a = (yy < 0 ? rw.top : rw.bot) ? 1 : 0;   // a band's halo row: the exchange maintains its state
+    }
+    s_lact[tid] = a; s_lvis[tid] = v;
+  }
   {
     uint4 *q = (uint4 *)grid;
     for (int i = tid; i < T * T * 2 / 16; i += NTHREADS) q[i] = make_uint4(0, 0, 0, 0);
   }
   if (tid == 0) s_want = 0;
-  const bool first = __ldcg(visited + t) == 0;   // (L2: a persistent CTA's L1 may hold a stale 0)
   __syncthreads();
+  const bool first = s_lvis[4] == 0;
   long long g[FL_PER];
   u32 lo[FL_PER], hi[FL_PER], msk[FL_PER], ref[FL_PER][4];
 #pragma unroll
@@ -723,14 +783,21 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ dirA, u3
           ref[j][1] = __funnelshift_l(ref[j][0], ref[j][1], 16);
           ref[j][0] = (ref[j][0] << 16) | (pos - 1u);
         } else elo = min(elo, 2u);                               // a low edge (lo = 1) of the same elevation
-      } else {
-        // a cell of a tile outside the active set holds no state (its rasters were never initialised): not in any flat,
-        // as in the window path; rows -1 / ny are a band's halo rows, whose state the exchange maintains
-        const int rn = r0 + nr;
+      } else if (nr >= 0 && nr < T && nc >= 0 && nc < T) {
+        // a band's halo row inside the tile's footprint (ny not a multiple of the tile size): not on the ring
         const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
-        if (__ldg(dirA + gn) != HC_DIR_NOFLOW) { elo = min(elo, 2u); continue; }   // a low edge of the same elevation (needs no state)
-        if (rn >= 0 && rn < ny && !active[(rn >> 6) * tx + ((c0 + nc) >> 6)]) continue;
+        if (__ldg(dirA + gn) != HC_DIR_NOFLOW) { elo = min(elo, 2u); continue; }
         const u32 a = __ldcg(dlo + gn), b = __ldcg(dhi + gn);
+        if (a) elo = min(elo, a + 1u);
+        if (b) ehi = min(ehi, b + 1u);
+      } else {
+        const int ri = RING_IDX(nr, nc);
+        const u32 f = h_nf[ri];
+        if (f == 1u) { elo = min(elo, 2u); continue; }   // a low edge of the same elevation (needs no state)
+        // a NOFLOW cell of a tile outside the active set holds no state (its rasters were never initialised): not in
+        // any flat, as in the window path
+        if (f != 2u || !s_lact[RING_TILE(nr, nc)]) continue;
+        const u32 a = h_lo[ri], b = h_hi[ri];
         if (a) elo = min(elo, a + 1u);
         if (b) ehi = min(ehi, b + 1u);
       }
@@ -791,7 +858,7 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ dirA, u3
     }
   }
   const long long t_l3 = clock64();
-  if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); HC_DBG(6, 1); HC_DBG(12, cnt <= 64); HC_DBG(13, cnt <= 128); HC_DBG(14, cnt <= 256); HC_DBG(15, cnt); }
+  if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); HC_DBG(6, 1); HC_DBG(12, t_l1 - t_begin); HC_DBG(13, t_l2 - t_l1); HC_DBG(14, t_l3 - t_l2); HC_DBG(15, cnt); }
 #pragma unroll
   for (int j = 0; j < FL_PER; j++)
     if ((chg >> j) & 1u) {
@@ -819,14 +886,16 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ dirA, u3
       const int dy = nr < 0 ? -1 : (nr >= T ? 1 : 0), dx = nc < 0 ? -1 : (nc >= T ? 1 : 0);
       const int yy = by + dy, xx = bx + dx;
       if (yy < 0 || yy >= ty || xx < 0 || xx >= tx) continue;  // a band's halo row: the exchange handles it
-      const u32 tt = (u32)(yy * tx + xx);
-      if (!active[tt]) continue;
-      const long long gn = g[j] + (long long)(kk / 3 - 1) * nx + (kk % 3 - 1);
-      const u32 f = __ldg(dirA + gn) == HC_DIR_NOFLOW, a = __ldcg(dlo + gn), b = __ldcg(dhi + gn);
-      if (!f) continue;
+      const int t9 = (dy + 1) * 3 + dx + 1;
+      if (!s_lact[t9]) continue;
+      // (the ring is the snapshot from the start of the visit: distances only ever decrease, so a stale value can cause a
+      // spurious visit, never a missed one -- as in the window path)
+      const int ri = RING_IDX(nr, nc);
+      if (h_nf[ri] != 2u) continue;
+      const u32 a = h_lo[ri], b = h_hi[ri];
       const u32 nlo = a ? a : R_INF, nhi = b ? b : R_INF;
       const bool benefit = c && (lo[j] + 1u < nlo || hi[j] + 1u < nhi);
-      if (benefit || (first && !__ldcg(visited + tt))) want |= 1u << ((dy + 1) * 3 + dx + 1);
+      if (benefit || (first && !s_lvis[t9])) want |= 1u << t9;
     }
   }
   if (want) atomicOr(&s_want, want);
@@ -882,7 +951,7 @@ k_flat_relax(const float *__restrict__ z, const uint8_t *__restrict__ dirA, u32 
       const u32 cnt = tcount[t];
       if (!cnt) continue;
       if (cnt <= FL_LCAP)
-        relax_light(dirA, dlo, dhi, active, tlist, tmask, cnt, lout, nout, queued, stamp, visited, ny, nx, tx, ty, dbg, t, smem);
+        relax_light(dirA, dlo, dhi, active, tlist, tmask, cnt, lout, nout, queued, stamp, visited, ny, nx, tx, ty, dbg, t, rw, smem);
       else
         relax_tile(z, dirA, dlo, dhi, active, lout, nout, queued, stamp, visited, ny, nx, nodata, dbg, rw, (int)(t / tx), (int)(t % tx), tx, ty, smem);
     }
@@ -899,14 +968,57 @@ __global__ void k_flat_queue_tiles(const uint8_t *__restrict__ active, u32 first
   if (active[t] && atomicExch(&queued[t], 1u) == 0u) list[atomicAdd(n, 1u)] = t;
 }
 
-// masked D8 for the pending cells
+// masked D8 for the pending cells of the tiles that have records: only the NOFLOW cells are visited, and of their
+// neighbours only the equal-elevation ones the record names (no elevation is read)
+template <int TABLE>
+__global__ void __launch_bounds__(256)
+k_flat_dirs_lists(const uint8_t *__restrict__ dirA, const u32 *__restrict__ dlo, const u32 *__restrict__ dhi,
+                  uint8_t *__restrict__ dirB, const uint8_t *__restrict__ pending, const hc_nf_lists nfl, int nx) {
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  if (!pending[tile]) return;
+  const u32 cnt = nfl.counts[tile];
+  if (cnt > NFCAP) return;
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  for (u32 k = threadIdx.x; k < cnt; k += 256) {
+    const u32 li = nfl.entries[(size_t)tile * NFCAP + k] & 0x0FFFu;
+    const u32 eq = nfl.eq[(size_t)tile * NFCAP + k];
+    const long long g = (long long)(r0 + (int)(li >> 6)) * nx + (c0 + (int)(li & 63u));
+    if (dirB[g] != HC_DIR_PENDING) continue;
+    uint8_t out = HC_DIR_NOFLOW;
+    const u32 lo = dlo[g];
+    if (lo) {
+      long long mn = 2ll * (long long)lo - (long long)dhi[g];
+      int best = -1;
+      bool bdiag = false;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (!((eq >> c_k_of_j[TABLE][j]) & 1u)) continue;
+        const long long gn = g + (long long)c_dr[TABLE][j] * nx + c_dc[TABLE][j];
+        long long key;
+        if (dirA[gn] == HC_DIR_NOFLOW) {
+          const u32 nlo = dlo[gn];
+          if (!nlo) continue;
+          key = 2ll * (long long)nlo - (long long)dhi[gn];
+        } else {
+          key = -0x4000000000000000ll;  // low edge: below every mask value
+        }
+        const bool kdiag = (c_dr[TABLE][j] != 0) && (c_dc[TABLE][j] != 0);
+        if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = j; bdiag = kdiag; }
+      }
+      if (best >= 0) out = (uint8_t)c_code[TABLE][best];
+    }
+    dirB[g] = out;
+  }
+}
+
+// masked D8 for the pending cells (window form: the dense tiles)
 template <int TABLE>
 __global__ void __launch_bounds__(256)
 k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ dirA, const u32 *__restrict__ dlo,
             const u32 *__restrict__ dhi, uint8_t *__restrict__ dirB, const uint8_t *__restrict__ pending,
-            int ny, int nx, float nodata, hc_rows rw) {
+            const u32 *__restrict__ counts, int ny, int nx, float nodata, hc_rows rw) {
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (!pending[tile]) return;
+  if (!pending[tile] || counts[tile] <= NFCAP) return;   // (tiles with records: k_flat_dirs_lists)
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   for (int i = threadIdx.x; i < T * T; i += 256) {
     int lr = i / T, lc = i - lr * T;
@@ -1052,6 +1164,7 @@ static int flats_relax_loop(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   if (!max_blocks) {
     int per_sm = 0;
     HC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_relax, NTHREADS, FLAT_SMEM));
+    if (const char *e = getenv("HC_FLAT_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // (experiments)
     max_blocks = per_sm * ctx->sm_count;
     if (max_blocks < 1) { hc_set_error("flats: cooperative launch: no resident block"); return HC_ERR_CUDA; }
   }
@@ -1085,11 +1198,16 @@ static int flats_dirs(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   hc_band_state *bs = &ctx->band;
   const int64_t ny = bs->nb, nx = bs->nx;
   dim3 tg((unsigned)((nx + T - 1) / T), (unsigned)((ny + T - 1) / T));
+  const hc_nf_lists nfl = {bs->tlist, bs->tmask, bs->tcount};
+  HC_PROF(ctx, st, "k_flat_dirs_lists");
+  if (bs->table == HC_TABLE_WBT) k_flat_dirs_lists<HC_TABLE_WBT><<<tg, 256, 0, st>>>(bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, nfl, (int)nx);
+  else k_flat_dirs_lists<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, nfl, (int)nx);
+  HC_LAUNCH_CHECK(ctx);
   HC_PROF(ctx, st, "k_flat_dirs");
   if (bs->table == HC_TABLE_WBT)
-    k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, (int)ny, (int)nx, bs->nodata, rw);
+    k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, bs->tcount, (int)ny, (int)nx, bs->nodata, rw);
   else
-    k_flat_dirs<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, (int)ny, (int)nx, bs->nodata, rw);
+    k_flat_dirs<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, bs->tcount, (int)ny, (int)nx, bs->nodata, rw);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
