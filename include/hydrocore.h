@@ -182,12 +182,22 @@ int hc_breach_depressions_host(const float *z, float *out, int64_t ny, int64_t n
 int hc_breach_flowpath_host(const float *w, const float *filled, const uint8_t *dir, float *out, int64_t ny, int64_t nx,
                             float nodata, int64_t max_length, double max_depth, int64_t *stats);
 int hc_wbt_seed_mask_host(const float *w, uint8_t *seed_out, int64_t ny, int64_t nx, float nodata);
-/* EXPERIMENTAL, NOT YET RUN ON A GPU -- the whole flow-path breach on the device: seeds, fill, seeds lowered by one
+/* The whole flow-path breach on the device (the default of wbt.breach_depressions; GPU-checked against its specification): seeds, fill, seeds lowered by one
  * ulp, D8 + flats, one walk per pit (atomic min on the cut surface).  w -> out (fill it afterwards); filled / dir / seed
  * are caller-provided device rasters that receive the intermediates; dx, dy as for hc_d8_dev.  stats as above (host). */
 int hc_breach_flowpath_dev(hc_ctx *ctx, const float *w, float *out, float *filled, uint8_t *dir, uint8_t *seed,
                            int64_t ny, int64_t nx, float nodata, double dx, double dy, int64_t max_length,
                            double max_depth, int64_t *stats, void *stream);
+/* Least-cost breaching on the device (csrc/leastcost.cu): replaces WhiteboxTools breach_depressions_least_cost as
+ * tools/depressions.py:1370-1374 (breach_pits, method 'LC') and :996-1000 (combined_solution, carve_method 'LC') call
+ * it -- wbt.breach_depressions_least_cost(dem, output, dist, max_cost=, min_dist=, flat_increment=, fill=False).
+ * Order-independent restatement of Lindsay & Dhun (2015), specification oracle/breach_leastcost.py (parity unpinned:
+ * the tool itself is not in the reference tree).  w -> out = the cut surface (fill it afterwards with hc_fill_dev for
+ * fill=True / the caller's closing Wang & Liu fill).  dist 1..65 cells; max_cost <= 0: no limit; min_dist != 0: shortest
+ * breach first, then cheapest; flat_increment <= 0: level channels.  stats (4 x int64, host, nullable): pits, breached,
+ * left, cells lowered. */
+int hc_breach_least_cost_dev(hc_ctx *ctx, const float *w, float *out, int64_t ny, int64_t nx, float nodata, int64_t dist,
+                             double max_cost, int min_dist, double flat_increment, int64_t *stats, void *stream);
 /* Water stencils of tools/water.py (called from models/depression_handling.py:647,889,898 and
  * models/burn_rivers.py:841,856).  wm = water_mask_array as uint8, swo = SWO_array as int16, dem/burn float32;
  * `burn` (DEM_burn_arr) is updated in place and may alias `dem`, as in the reference's own calls.

@@ -52,6 +52,8 @@ SIGNATURES = {
     "hc_wbt_seed_mask_host": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32]),
     "hc_breach_flowpath_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f64, c_f64,
                                               c_i64, c_f64, c_vp, c_vp]),
+    "hc_breach_least_cost_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_i64, c_f64, ctypes.c_int, c_f64,
+                                                c_vp, c_vp]),
     "hc_lzw_decode_host": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64)]),
     "hc_lzw_encode_host": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64)]),
     "hc_breach_depressions_host": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32, c_i64, c_f64, ctypes.c_int,

@@ -352,6 +352,38 @@ def breach_depressions(z, nodata=-9999.0, max_length=None, max_depth=None, fill_
     return out
 
 
+def breach_depressions_least_cost(z, dist, nodata=-9999.0, max_cost=None, min_dist=True, flat_increment=None, fill=True,
+                                  return_stats=False):
+    """wbt.breach_depressions_least_cost (Lindsay & Dhun 2015) as dep.breach_pits(method='LC') and
+    dep.combined_solution(carve_method='LC') call it (tools/depressions.py:1370-1374, :996-1000): every pit is breached
+    along the cheapest path (cost = elevation removed) to a lower cell or the raster's edge inside a (2 dist + 1)^2
+    window, unless that costs more than max_cost; min_dist prefers the shortest breach; flat_increment is the channel's
+    gradient; fill=True fills what is left (WhiteboxTools' seed rule).  One CTA per pit on the GPU
+    (`hc_breach_least_cost_dev`), order-independent form, specification oracle/breach_leastcost.py -- the tool itself is
+    not in the reference tree: parity unpinned.  float32 in, float32 out (numpy -> numpy, CUDA tensor -> CUDA tensor)."""
+    import ctypes
+    import torch
+    host = not _is_torch(z)
+    zt = torch.from_numpy(np.ascontiguousarray(_np2d(z, np.float32))).cuda() if host else z
+    zt = _tdev(zt, torch.float32, "breach_depressions_least_cost")
+    out = torch.empty_like(zt)
+    st = (ctypes.c_int64 * 4)()
+    with torch.cuda.device(zt.device):
+        _lib.check(_lib.load().hc_breach_least_cost_dev(_lib.context(zt.device.index or 0), _tp(zt), _tp(out), zt.shape[0],
+                                                       zt.shape[1], float(nodata), int(dist),
+                                                       float(max_cost) if max_cost is not None else 0.0,
+                                                       int(bool(min_dist)),
+                                                       float(flat_increment) if flat_increment else 0.0, st, _stream(zt)),
+                   "hc_breach_least_cost_dev")
+    if fill:
+        out = globals()["fill"](out, nodata=nodata, seed_mode=SEED_WBT)   # (the keyword shadows the module's fill)
+    if host:
+        out = out.cpu().numpy()
+    if return_stats:
+        return out, dict(pits=st[0], breached=st[1], left=st[2], cells_lowered=st[3])
+    return out
+
+
 def taudem_check(p, fel, flat_mask, edm, nodata=-9999.0):
     """TaudemCheck.check_basin's problem mask (models/taudem_check.py:143-147): returns (mask uint8, count).
     `p` is the uint8 D8 raster with 255 = nodata."""

@@ -82,12 +82,12 @@ class DepHandleCore:
             modDEM_array, _ = raster_io.read_raster(modDEM_tif)
             # every pit's partial-fill candidates are evaluated from the same pre-combination surface (the reference's
             # loop reads modDEM_array once, :768), so all of them go through one batched device pass
-            if self.carvemethod == 'LC':
-                raise NotImplementedError("carve_method='LC' (breach_depressions_least_cost) is not built")
             results = dep.combined_solutions(list(DFpits_3.index.values), modDEM_array, nx, ny, DFpits, fillcells_dct,
                                              carvecells_dct, carve_fillcells_dct, self.combined_fill_interval, fillID_vec,
                                              fill_vec, carve_vec, self.radius, self.max_carve_depth,
-                                             nodataval=self.nodataval)
+                                             nodataval=self.nodataval, carve_method=self.carvemethod,
+                                             maxcost=self.maxcost, min_dist=self.min_dist,
+                                             flat_increment=self.flat_increment if self.carvemethod == 'LC' else 0.0)
             for pit_id in DFpits_3.index.values:
                 solution_name, sol_df = results[pit_id]
                 DFpits.at[pit_id, 'solution'] = solution_name

@@ -569,7 +569,8 @@ def _pack_shelves(shapes, max_width=4096, gutter=2):
 
 
 def combined_solutions(pit_ids, inDEM_array, nx, ny, DFpits, fillcells_dct, carvecells_dct, carve_fillcells_dct,
-                       combined_fill_interval, fillID_vec, fill_vec, carve_vec, radius, max_carve_depth, nodataval=-9999):
+                       combined_fill_interval, fillID_vec, fill_vec, carve_vec, radius, max_carve_depth, nodataval=-9999,
+                       carve_method='SC', maxcost=None, min_dist=False, flat_increment=0.0):
     """The partial-fill + re-breach search of tools/depressions.py:813-1137 for MANY pits at once.
 
     For every pit the reference clips a window (pit bounding box + radius + 2 cells), lowers the pit's full fill to
@@ -582,7 +583,9 @@ def combined_solutions(pit_ids, inDEM_array, nx, ny, DFpits, fillcells_dct, carv
     Here all partial surfaces of all pits are packed into ONE mosaic raster with nodata gutters and go through ONE
     device breach and ONE device labelling: a gutter is exterior nodata, so every window's rim cells are seeds exactly
     as the rim of a stand-alone raster is, and no flow path, flat or clump can cross it -- each window's result is the
-    stand-alone result.  Returns {pit_id: (solution_name, sol_df)} with the reference's return value per pit."""
+    stand-alone result.  carve_method='LC' re-breaches with the least-cost breach instead (:996-1000: dist = radius,
+    max_cost = maxcost, min_dist, flat_increment, no fill).  Returns {pit_id: (solution_name, sol_df)} with the
+    reference's return value per pit."""
     import pandas as pd
     import torch
     ground_full = np.asarray(inDEM_array, dtype=np.float32).reshape(ny, nx)
@@ -627,8 +630,12 @@ def combined_solutions(pit_ids, inDEM_array, nx, ny, DFpits, fillcells_dct, carv
             t.slot = (slice(y, y + h), slice(x, x + w))
             mosaic[t.slot] = t.surface
         mos_dev = torch.from_numpy(mosaic).cuda()
-        carved_dev = core.breach_depressions(mos_dev, nodata=float(nodataval), max_length=radius, max_depth=max_carve_depth,
-                                             fill_pits=False)
+        if carve_method == 'LC':
+            carved_dev = core.breach_depressions_least_cost(mos_dev, int(radius), nodata=float(nodataval), max_cost=maxcost,
+                                                            min_dist=min_dist, flat_increment=flat_increment, fill=False)
+        else:
+            carved_dev = core.breach_depressions(mos_dev, nodata=float(nodataval), max_length=radius,
+                                                 max_depth=max_carve_depth, fill_pits=False)
         carved = carved_dev.cpu().numpy()
         # clumps of lowered cells (plus the windows' own nodata: the raster edge a carve may not run into)
         change = np.full((H, W), 0.0, np.float32)
@@ -685,13 +692,13 @@ def combined_solution(inDEM, inDEM_array, outpath, nx, ny, DFpits, fillcells_dct
     """tools/depressions.py:813-1137 for one pit: same arguments, same return value (solution_name,
     sol_df[vol, elevs, solution, footprint]).  A one-pit call of `combined_solutions` (above); the window rasters
     live in memory only -- upstream writes them under <outpath>/combined_solutions and deletes every one of them
-    before returning (:1132-1135).  `carve_method='LC'` and a graded `flat_increment` are not built."""
-    if carve_method == 'LC':
-        raise NotImplementedError("carve_method='LC' (breach_depressions_least_cost) is not built")
-    if flat_increment and flat_increment > 0:
-        raise NotImplementedError("flat_increment > 0 is not offered (see wbt.WhiteboxToolsGPU)")
+    before returning (:1132-1135).  A graded `flat_increment` is served for carve_method='LC' only (there it is the
+    channel's gradient)."""
+    if carve_method != 'LC' and flat_increment and flat_increment > 0:
+        raise NotImplementedError("flat_increment > 0 in the partial-fill search is served for carve_method='LC' only")
     os.makedirs(os.path.join(outpath, "combined_solutions"), exist_ok=True)
     res = combined_solutions([pit_id], inDEM_array, nx, ny, DFpits, fillcells_dct, carvecells_dct, carve_fillcells_dct,
                              combined_fill_interval, fillID_vec, fill_vec, carve_vec, radius, max_carve_depth,
-                             nodataval=nodataval)
+                             nodataval=nodataval, carve_method=carve_method, maxcost=maxcost, min_dist=min_dist,
+                             flat_increment=flat_increment)
     return res[pit_id]

@@ -144,8 +144,15 @@ class WhiteboxToolsGPU:
         self._say("fill_missing_data ->", output)
         return 0
 
-    # -- not built ----------------------------------------------------------------------------------
+    # -- least-cost breach (tools/depressions.py:1370-1374, :996-1000: carve_method 'LC') ----------------
     def breach_depressions_least_cost(self, dem, output, dist, max_cost=None, min_dist=True, flat_increment=None,
                                       fill=True, callback=None):
-        raise NotImplementedError("breach_depressions_least_cost (Lindsay & Dhun 2015) is not built; pydrodem's "
-                                  "default carve method is 'SC' = breach_depressions (tools/depressions.py:1320)")
+        """Lindsay & Dhun (2015) least-cost breaching, one CTA per pit on the GPU; see core.breach_depressions_least_cost
+        (order-independent restatement, parity unpinned).  dist is the search radius in cells (at most 65 here: the
+        window lives in shared memory; the reference passes radius = 50, config_files/config_local.ini:162)."""
+        z, meta, nodata = self._load(dem)
+        out = core.breach_depressions_least_cost(np.asarray(z, np.float32), int(dist), nodata=nodata, max_cost=max_cost,
+                                                 min_dist=min_dist, flat_increment=flat_increment, fill=fill)
+        raster_io.write_raster(output, out, meta, nodata=nodata)
+        self._say("breach_depressions_least_cost ->", output)
+        return 0

@@ -109,5 +109,4 @@ def test_wbt_and_breach_pits_file_protocol(tmp_path):
     raster_io.write_raster(str(tmp_path / "unit_SC_12.tif"), z, None, nodata=ND)
     carve2, diff2 = dep.breach_pits(dem_tif, 12, 200, wbt, nodataval=ND)
     assert np.array_equal(carve2, z) and not diff2.any()
-    with pytest.raises(NotImplementedError):
-        dep.breach_pits(dem_tif, 13, 200, wbt, method='LC')
+    # (method='LC': tests/test_gpu_breach_leastcost.py)
