@@ -20,8 +20,8 @@
 //         region), relaxes to the fixed point in shared memory and writes final directions for every flat that lies
 //         completely inside the apron (on a filled DEM nearly all of them).  No elevation is read.
 //   slow  flats that reach the apron's rim are marked pending (code 254) and solved by tile relaxation against two
-//         global distance rasters that hold state only at NOFLOW cells (k_flat_init_lists / k_flat_init, k_flat_relax,
-//         k_flat_dirs) on the tiles that hold pending cells and their neighbours.  A cell WITH a direction next to an
+//         global distance rasters that hold state only at NOFLOW cells (k_flat_init_lists, k_flat_relax,
+//         k_flat_dirs_lists) on the tiles that hold pending cells and their neighbours.  A cell WITH a direction next to an
 //         equal NOFLOW cell is a low edge: constant 1, asked of the D8 raster, never stored.  A device queue holds the
 //         dirty tiles of a round (one cooperative launch runs all rounds); tiles with <= 1024 NOFLOW cells relax from
 //         their records in shared memory (relax_light), lake tiles through a shared-memory window with directional
@@ -361,67 +361,15 @@ __global__ void k_flat_dilate(const uint8_t *__restrict__ pending, uint8_t *__re
 // ================================================================================================
 // slow tier (general: any flat size), restricted to `active` tiles
 // ================================================================================================
-// State lives in two rasters that only ever mean something AT NOFLOW CELLS of active tiles:
-//   dlo[c] = 1 + geodesic distance to the nearest low edge through the flat (a cell next to a low edge starts at 2)
-//   dhi[c] = 1 + geodesic distance to the nearest high edge (a NOFLOW cell touching higher ground is 1); 0 = not reached
-// A valid cell WITH a direction that touches an equal NOFLOW cell is a low edge: constant 1, never stored -- whoever
-// looks at an equal-elevation neighbour asks the D8 raster (dirA) whether it is NOFLOW first.
-//
-// k_flat_init_lists: tiles with at most NFCAP NOFLOW cells start from their records (no elevation, no window): the
-// record says which neighbours share the elevation and whether the cell is a high edge; dirA says which of those
-// neighbours have a direction.  Also decides whether the tile must be relaxed before anyone asks for it: yes if it
-// holds pending cells itself, or if one of its NOFLOW cells touches a PENDING cell of the same elevation in a
-// neighbouring tile (it then holds part of a flat that is open over there, possibly with that flat's only sources).
-__global__ void __launch_bounds__(256)
-k_flat_init_lists(const uint8_t *__restrict__ dirA, const uint8_t *__restrict__ dirB, u32 *__restrict__ dlo, u32 *__restrict__ dhi,
-                  const uint8_t *__restrict__ active, const uint8_t *__restrict__ pending, uint8_t *__restrict__ startq,
-                  const hc_nf_lists nfl, int ny, int nx, hc_rows rw, int start_all) {
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (!active[tile]) { if (threadIdx.x == 0) startq[tile] = 0; return; }
-  const u32 cnt = nfl.counts[tile];
-  if (cnt > NFCAP) return;   // the window form below takes the dense tiles
-  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
-  int touch = 0;
-  for (u32 k = threadIdx.x; k < cnt; k += 256) {
-    const u32 e = nfl.entries[(size_t)tile * NFCAP + k];
-    const u32 eq = nfl.eq[(size_t)tile * NFCAP + k];
-    const int lr = (int)((e & 0x0FFFu) >> 6), lc = (int)(e & 63u);
-    const long long g = (long long)(r0 + lr) * nx + (c0 + lc);
-    u32 lo = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      if (!((eq >> j) & 1u)) continue;
-      const int kk = j + (j >= 4);
-      const int dr = kk / 3 - 1, dc = kk % 3 - 1;
-      const long long gn = g + (long long)dr * nx + dc;
-      if (__ldg(dirA + gn) != HC_DIR_NOFLOW) lo = 2;
-      else {
-        const int nr = lr + dr, nc = lc + dc;
-        if ((nr < 0 || nr >= T || nc < 0 || nc >= T) && r0 + nr >= 0 && r0 + nr < ny && __ldcg(dirB + gn) == HC_DIR_PENDING) touch = 1;
-      }
-    }
-    dlo[g] = lo;
-    dhi[g] = (e & HC_NF_HI) ? 1u : 0u;
-  }
-  touch = __syncthreads_or(touch);
-  if (threadIdx.x == 0) {
-    // a band cannot see the neighbouring band's pending marks: its seam tile rows always start
-    const bool seam = (rw.top && blockIdx.y == 0) || (rw.bot && blockIdx.y == gridDim.y - 1);
-    startq[tile] = (uint8_t)((pending[tile] || touch || seam || start_all) ? 1 : 0);
-  }
-}
-
 // window form for the dense tiles (more than NFCAP NOFLOW cells: lakes): same initial state from the staged tile
-__global__ void __launch_bounds__(NTHREADS)
-k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const uint8_t *__restrict__ dirB,
-            u32 *__restrict__ dlo, u32 *__restrict__ dhi, const uint8_t *__restrict__ active,
-            const uint8_t *__restrict__ pending, uint8_t *__restrict__ startq, const u32 *__restrict__ counts,
-            int ny, int nx, float nodata, hc_rows rw, int start_all) {
+__device__ __noinline__ void
+flat_init_window(const float *__restrict__ z, const uint8_t *__restrict__ dir, const uint8_t *__restrict__ dirB,
+                 u32 *__restrict__ dlo, u32 *__restrict__ dhi, const uint8_t *__restrict__ pending,
+                 uint8_t *__restrict__ startq, int ny, int nx, float nodata, hc_rows rw, int start_all) {
   __shared__ float sz[TH * TH];
   __shared__ uint8_t sd[TH * TH];
   __shared__ uint8_t sp[TH * TH];   // dirB: the fast tier's PENDING marks, looked at on the halo ring only
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (!active[tile] || counts[tile] <= NFCAP) return;
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   const int tid = threadIdx.x;
   const float qnan = __int_as_float(0x7fc00000);
@@ -472,6 +420,60 @@ k_flat_init(const float *__restrict__ z, const uint8_t *__restrict__ dir, const 
   }
   touch = __syncthreads_or(touch);
   if (tid == 0) {
+    const bool seam = (rw.top && blockIdx.y == 0) || (rw.bot && blockIdx.y == gridDim.y - 1);
+    startq[tile] = (uint8_t)((pending[tile] || touch || seam || start_all) ? 1 : 0);
+  }
+}
+
+// State lives in two rasters that only ever mean something AT NOFLOW CELLS of active tiles:
+//   dlo[c] = 1 + geodesic distance to the nearest low edge through the flat (a cell next to a low edge starts at 2)
+//   dhi[c] = 1 + geodesic distance to the nearest high edge (a NOFLOW cell touching higher ground is 1); 0 = not reached
+// A valid cell WITH a direction that touches an equal NOFLOW cell is a low edge: constant 1, never stored -- whoever
+// looks at an equal-elevation neighbour asks the D8 raster (dirA) whether it is NOFLOW first.
+//
+// k_flat_init_lists: tiles with at most NFCAP NOFLOW cells start from their records (no elevation, no window): the
+// record says which neighbours share the elevation and whether the cell is a high edge; dirA says which of those
+// neighbours have a direction.  Also decides whether the tile must be relaxed before anyone asks for it: yes if it
+// holds pending cells itself, or if one of its NOFLOW cells touches a PENDING cell of the same elevation in a
+// neighbouring tile (it then holds part of a flat that is open over there, possibly with that flat's only sources).
+__global__ void __launch_bounds__(256)
+k_flat_init_lists(const float *__restrict__ z, const uint8_t *__restrict__ dirA, const uint8_t *__restrict__ dirB,
+                  u32 *__restrict__ dlo, u32 *__restrict__ dhi, const uint8_t *__restrict__ active,
+                  const uint8_t *__restrict__ pending, uint8_t *__restrict__ startq, const hc_nf_lists nfl, int ny, int nx,
+                  float nodata, hc_rows rw, int start_all) {
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  if (!active[tile]) { if (threadIdx.x == 0) startq[tile] = 0; return; }
+  const u32 cnt = nfl.counts[tile];
+  if (cnt > NFCAP) {   // a dense tile (lake): the window form
+    flat_init_window(z, dirA, dirB, dlo, dhi, pending, startq, ny, nx, nodata, rw, start_all);
+    return;
+  }
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  int touch = 0;
+  for (u32 k = threadIdx.x; k < cnt; k += 256) {
+    const u32 e = nfl.entries[(size_t)tile * NFCAP + k];
+    const u32 eq = nfl.eq[(size_t)tile * NFCAP + k];
+    const int lr = (int)((e & 0x0FFFu) >> 6), lc = (int)(e & 63u);
+    const long long g = (long long)(r0 + lr) * nx + (c0 + lc);
+    u32 lo = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (!((eq >> j) & 1u)) continue;
+      const int kk = j + (j >= 4);
+      const int dr = kk / 3 - 1, dc = kk % 3 - 1;
+      const long long gn = g + (long long)dr * nx + dc;
+      if (__ldg(dirA + gn) != HC_DIR_NOFLOW) lo = 2;
+      else {
+        const int nr = lr + dr, nc = lc + dc;
+        if ((nr < 0 || nr >= T || nc < 0 || nc >= T) && r0 + nr >= 0 && r0 + nr < ny && __ldcg(dirB + gn) == HC_DIR_PENDING) touch = 1;
+      }
+    }
+    dlo[g] = lo;
+    dhi[g] = (e & HC_NF_HI) ? 1u : 0u;
+  }
+  touch = __syncthreads_or(touch);
+  if (threadIdx.x == 0) {
+    // a band cannot see the neighbouring band's pending marks: its seam tile rows always start
     const bool seam = (rw.top && blockIdx.y == 0) || (rw.bot && blockIdx.y == gridDim.y - 1);
     startq[tile] = (uint8_t)((pending[tile] || touch || seam || start_all) ? 1 : 0);
   }
@@ -968,57 +970,11 @@ __global__ void k_flat_queue_tiles(const uint8_t *__restrict__ active, u32 first
   if (active[t] && atomicExch(&queued[t], 1u) == 0u) list[atomicAdd(n, 1u)] = t;
 }
 
-// masked D8 for the pending cells of the tiles that have records: only the NOFLOW cells are visited, and of their
-// neighbours only the equal-elevation ones the record names (no elevation is read)
-template <int TABLE>
-__global__ void __launch_bounds__(256)
-k_flat_dirs_lists(const uint8_t *__restrict__ dirA, const u32 *__restrict__ dlo, const u32 *__restrict__ dhi,
-                  uint8_t *__restrict__ dirB, const uint8_t *__restrict__ pending, const hc_nf_lists nfl, int nx) {
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (!pending[tile]) return;
-  const u32 cnt = nfl.counts[tile];
-  if (cnt > NFCAP) return;
-  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
-  for (u32 k = threadIdx.x; k < cnt; k += 256) {
-    const u32 li = nfl.entries[(size_t)tile * NFCAP + k] & 0x0FFFu;
-    const u32 eq = nfl.eq[(size_t)tile * NFCAP + k];
-    const long long g = (long long)(r0 + (int)(li >> 6)) * nx + (c0 + (int)(li & 63u));
-    if (dirB[g] != HC_DIR_PENDING) continue;
-    uint8_t out = HC_DIR_NOFLOW;
-    const u32 lo = dlo[g];
-    if (lo) {
-      long long mn = 2ll * (long long)lo - (long long)dhi[g];
-      int best = -1;
-      bool bdiag = false;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        if (!((eq >> c_k_of_j[TABLE][j]) & 1u)) continue;
-        const long long gn = g + (long long)c_dr[TABLE][j] * nx + c_dc[TABLE][j];
-        long long key;
-        if (dirA[gn] == HC_DIR_NOFLOW) {
-          const u32 nlo = dlo[gn];
-          if (!nlo) continue;
-          key = 2ll * (long long)nlo - (long long)dhi[gn];
-        } else {
-          key = -0x4000000000000000ll;  // low edge: below every mask value
-        }
-        const bool kdiag = (c_dr[TABLE][j] != 0) && (c_dc[TABLE][j] != 0);
-        if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = j; bdiag = kdiag; }
-      }
-      if (best >= 0) out = (uint8_t)c_code[TABLE][best];
-    }
-    dirB[g] = out;
-  }
-}
-
 // masked D8 for the pending cells (window form: the dense tiles)
 template <int TABLE>
-__global__ void __launch_bounds__(256)
-k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ dirA, const u32 *__restrict__ dlo,
-            const u32 *__restrict__ dhi, uint8_t *__restrict__ dirB, const uint8_t *__restrict__ pending,
-            const u32 *__restrict__ counts, int ny, int nx, float nodata, hc_rows rw) {
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  if (!pending[tile] || counts[tile] <= NFCAP) return;   // (tiles with records: k_flat_dirs_lists)
+__device__ __noinline__ void
+flat_dirs_window(const float *__restrict__ z, const uint8_t *__restrict__ dirA, const u32 *__restrict__ dlo,
+                 const u32 *__restrict__ dhi, uint8_t *__restrict__ dirB, int ny, int nx, float nodata, hc_rows rw) {
   const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
   for (int i = threadIdx.x; i < T * T; i += 256) {
     int lr = i / T, lc = i - lr * T;
@@ -1051,6 +1007,50 @@ k_flat_dirs(const float *__restrict__ z, const uint8_t *__restrict__ dirA, const
         }
         bool kdiag = (c_dr[TABLE][k] != 0) && (c_dc[TABLE][k] != 0);
         if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = k; bdiag = kdiag; }
+      }
+      if (best >= 0) out = (uint8_t)c_code[TABLE][best];
+    }
+    dirB[g] = out;
+  }
+}
+
+// masked D8 for the pending cells of the tiles that have records: only the NOFLOW cells are visited, and of their
+// neighbours only the equal-elevation ones the record names (no elevation is read)
+template <int TABLE>
+__global__ void __launch_bounds__(256)
+k_flat_dirs_lists(const float *__restrict__ z, const uint8_t *__restrict__ dirA, const u32 *__restrict__ dlo,
+                  const u32 *__restrict__ dhi, uint8_t *__restrict__ dirB, const uint8_t *__restrict__ pending,
+                  const hc_nf_lists nfl, int ny, int nx, float nodata, hc_rows rw) {
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  if (!pending[tile]) return;
+  const u32 cnt = nfl.counts[tile];
+  if (cnt > NFCAP) { flat_dirs_window<TABLE>(z, dirA, dlo, dhi, dirB, ny, nx, nodata, rw); return; }   // a dense tile
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  for (u32 k = threadIdx.x; k < cnt; k += 256) {
+    const u32 li = nfl.entries[(size_t)tile * NFCAP + k] & 0x0FFFu;
+    const u32 eq = nfl.eq[(size_t)tile * NFCAP + k];
+    const long long g = (long long)(r0 + (int)(li >> 6)) * nx + (c0 + (int)(li & 63u));
+    if (dirB[g] != HC_DIR_PENDING) continue;
+    uint8_t out = HC_DIR_NOFLOW;
+    const u32 lo = dlo[g];
+    if (lo) {
+      long long mn = 2ll * (long long)lo - (long long)dhi[g];
+      int best = -1;
+      bool bdiag = false;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (!((eq >> c_k_of_j[TABLE][j]) & 1u)) continue;
+        const long long gn = g + (long long)c_dr[TABLE][j] * nx + c_dc[TABLE][j];
+        long long key;
+        if (dirA[gn] == HC_DIR_NOFLOW) {
+          const u32 nlo = dlo[gn];
+          if (!nlo) continue;
+          key = 2ll * (long long)nlo - (long long)dhi[gn];
+        } else {
+          key = -0x4000000000000000ll;  // low edge: below every mask value
+        }
+        const bool kdiag = (c_dr[TABLE][j] != 0) && (c_dc[TABLE][j] != 0);
+        if (key < mn || (key == mn && best >= 0 && bdiag && !kdiag)) { mn = key; best = j; bdiag = kdiag; }
       }
       if (best >= 0) out = (uint8_t)c_code[TABLE][best];
     }
@@ -1139,11 +1139,8 @@ static int flats_slow_init(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   const int start_all = getenv("HC_FLAT_START_ALL") ? 1 : 0;
   const hc_nf_lists nfl = {bs->tlist, bs->tmask, bs->tcount};
   HC_PROF(ctx, st, "k_flat_init_lists");
-  k_flat_init_lists<<<tg, 256, 0, st>>>(bs->dirA, bs->dirB, bs->dlo, bs->dhi, bs->active, bs->pending, startq, nfl, (int)ny, (int)nx, rw, start_all);
-  HC_LAUNCH_CHECK(ctx);
-  HC_PROF(ctx, st, "k_flat_init");
-  k_flat_init<<<tg, NTHREADS, 0, st>>>(bs->fz, bs->dirA, bs->dirB, bs->dlo, bs->dhi, bs->active, bs->pending, startq, bs->tcount,
-                                       (int)ny, (int)nx, bs->nodata, rw, start_all);
+  k_flat_init_lists<<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dirB, bs->dlo, bs->dhi, bs->active, bs->pending, startq, nfl, (int)ny,
+                                        (int)nx, bs->nodata, rw, start_all);
   HC_LAUNCH_CHECK(ctx);
   // first relaxation visits every active tile: queue A
   HC_CUDA(cudaMemsetAsync(bs->queued, 0, tiles * 4, st));
@@ -1200,14 +1197,10 @@ static int flats_dirs(hc_ctx *ctx, hc_rows rw, cudaStream_t st) {
   dim3 tg((unsigned)((nx + T - 1) / T), (unsigned)((ny + T - 1) / T));
   const hc_nf_lists nfl = {bs->tlist, bs->tmask, bs->tcount};
   HC_PROF(ctx, st, "k_flat_dirs_lists");
-  if (bs->table == HC_TABLE_WBT) k_flat_dirs_lists<HC_TABLE_WBT><<<tg, 256, 0, st>>>(bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, nfl, (int)nx);
-  else k_flat_dirs_lists<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, nfl, (int)nx);
-  HC_LAUNCH_CHECK(ctx);
-  HC_PROF(ctx, st, "k_flat_dirs");
   if (bs->table == HC_TABLE_WBT)
-    k_flat_dirs<HC_TABLE_WBT><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, bs->tcount, (int)ny, (int)nx, bs->nodata, rw);
+    k_flat_dirs_lists<HC_TABLE_WBT><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, nfl, (int)ny, (int)nx, bs->nodata, rw);
   else
-    k_flat_dirs<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, bs->tcount, (int)ny, (int)nx, bs->nodata, rw);
+    k_flat_dirs_lists<HC_TABLE_TAUDEM><<<tg, 256, 0, st>>>(bs->fz, bs->dirA, bs->dlo, bs->dhi, bs->dirB, bs->pending, nfl, (int)ny, (int)nx, bs->nodata, rw);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
 }
