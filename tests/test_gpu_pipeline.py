@@ -172,3 +172,55 @@ def test_combined_solutions_batch_equals_window_by_window_evaluation(tmp_path):
     name1, sol1 = dep.combined_solution(dem, ground, str(tmp_path), nx, ny, DF, fc, cc, cfc, pits[0], step, fid, fillv, carvev,
                                         radius, 200, False, mcd, wbt, nodataval=ND)
     assert int(name1) == int(res[pits[0]][0])
+
+
+@pytest.mark.gpu
+def test_initial_fill_carve_equals_its_cpu_specification(tmp_path):
+    """dep.initial_fill_carve (tools/depressions.py:41-264) against a CPU restatement that uses nothing of the product:
+    the reference's own numpy / scipy statements for the masks, the shallow fill and the clumps (:1471-1531, :1625-1669),
+    the C oracle for the two fills and the flow-path specification for the breach.  Every returned vector, bit for bit."""
+    from scipy import ndimage
+    from scipy.signal import convolve2d
+    from oracle import breach_flowpath as bf
+    from oracle import hydro_oracle as ho
+    from pydrodem_b200 import raster_io
+    from pydrodem_b200.tools import depressions as dep
+    from pydrodem_b200.wbt import WhiteboxToolsGPU
+    z = unit_dem(120, 140, 21)
+    sfill, radius = 0.5, 10
+    dem = str(tmp_path / "u.tif")
+    raster_io.write_raster(dem, z, None, nodata=ND)
+    got = dep.initial_fill_carve(dem, "u", str(tmp_path), 'WL', 200, radius, False, ND, None, WhiteboxToolsGPU(),
+                                 sfill=sfill, verbose_print=False)
+    modv, fillv, carvev, dfill, dcarve, fid, cid, cfid, nx, ny = got
+    assert (ny, nx) == z.shape
+
+    eight, four = np.ones((3, 3), int), np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+    f0 = ho.fill(z, ND, ho.SEED_WBT)
+    d0 = np.round(f0 - z, 3)
+    id0 = ndimage.label(d0 > 0, structure=eight)[0].ravel()
+    deep = np.unique(id0[np.flatnonzero(d0.ravel() > sfill)])                      # fill_shallow_pits :1509-1523
+    take = np.isin(id0, deep, invert=True)
+    mod = z.ravel().copy()
+    mod[take] = f0.ravel()[take]
+    mod2 = mod.reshape(z.shape)
+    f1 = ho.fill(mod2, ND, ho.SEED_WBT)
+    d1 = np.round(f1 - mod2, 3)
+    grown = convolve2d((d1 > 0).astype(np.float32), np.ones((3, 3), np.float32), mode='same', boundary='symm') > 0
+    want_fid = ndimage.label(grown, structure=four)[0]                            # clumpbuffer=1 -> 4-connected
+    carve, _ = bf.breach_flowpath(mod2, ND, max_length=radius, fill_pits=True, do_fill=True)
+    dc = np.round(carve - mod2, 3)
+    dcm = dc.copy()
+    dcm[z == ND] = -1.0
+    want_cid = ndimage.label(dcm < 0, structure=eight)[0]
+    want_cfid = ndimage.label(dcm > 0, structure=eight)[0]
+
+    assert np.array_equal(np.asarray(modv, np.float32), mod)
+    assert np.array_equal(np.asarray(fillv, np.float32), f1.ravel())
+    assert np.array_equal(np.asarray(dfill, np.float32), d1.ravel())
+    assert np.array_equal(np.asarray(carvev, np.float32), carve.ravel())
+    assert np.array_equal(np.asarray(fid), want_fid.ravel()) and want_fid.max() > 3
+    assert np.array_equal(np.asarray(cid), want_cid.ravel()) and want_cid.max() > 1
+    assert np.array_equal(np.asarray(cfid), want_cfid.ravel())
+    dcv = np.asarray(dcarve, np.float32).reshape(z.shape)
+    assert np.array_equal(dcv[z != ND], dc[z != ND])
