@@ -351,6 +351,45 @@ int hc_pit_catalog_dev(hc_ctx *ctx, const float *dem, float nodata, const float 
                        int8_t *complete, uint8_t *pit_out, int64_t *carve_amax, int64_t *carve_amin,
                        float *carve_min, double *carve_sum, int64_t *carve_n, int64_t *pairs_out, int64_t pair_cap,
                        uint8_t *pair_included, int64_t *npairs, void *stream);
+/* The catalog over ROW BANDS of one raster (SURVEY.md 8e "Catalog / select / apply: AllReduce of per-label partial
+ * max / sum"; pydrodem_b200/bands.py pit_catalog_banded).  Label rasters hold whole-raster ids (hc_band_label_*).
+ * (1) hc_band_catalog_local_dev on every band: cell0 = whole-raster index of the band's first cell; partial tables out
+ *     (per pit: maxfill, volfill64, nfill, fb_max, fb_sum, fb_n; per carve: carve_min, carve_sum, carve_n and the
+ *     arg-extreme keys kmax / kmin, which carry whole-raster cell indices) + the band's distinct (pit, carve) pairs.
+ *     The caller reduces across the bands: max (maxfill, fb_max, kmax as UNSIGNED), min (carve_min, kmin as unsigned),
+ *     sum (the float64 sums, the counts); pair lists are concatenated and made unique.
+ * (2) hc_band_catalog_owner_ids_dev on every band with the reduced keys: the pit id at each carve's first highest /
+ *     first lowest cell where this band owns that cell (0 elsewhere, -1 for an empty carve): max-reduce.
+ * (3) hc_catalog_finish_dev on the reduced tables (every rank, redundantly): the catalog's columns, pair_included,
+ *     pit_out.  hc_pit_catalog_dev is exactly (1)-(3) on one raster. */
+int hc_band_catalog_local_dev(hc_ctx *ctx, const float *dem, float nodata, const float *carve, const float *diff_carve,
+                              const float *diff_fill, const int32_t *fillID, const int32_t *carveID,
+                              const int32_t *carvefillID, int64_t n, int64_t cell0, int32_t npits, int32_t ncarves,
+                              int32_t *carve_bound, float *maxfill, double *volfill64, int64_t *nfill, float *fb_max,
+                              double *fb_sum, int64_t *fb_n, float *carve_min, double *carve_sum, int64_t *carve_n,
+                              uint64_t *kmax, uint64_t *kmin, int64_t *pairs_out, int64_t pair_cap, int64_t *npairs,
+                              void *stream);
+int hc_band_catalog_owner_ids_dev(hc_ctx *ctx, const int32_t *fillID, int64_t n, int64_t cell0, int32_t ncarves,
+                                  const uint64_t *kmax, const uint64_t *kmin, int32_t *fid_amax, int32_t *fid_amin,
+                                  void *stream);
+int hc_catalog_finish_dev(hc_ctx *ctx, int32_t npits, int32_t ncarves, const int64_t *pairs, int64_t npairs,
+                          const int32_t *fid_amax, const int32_t *fid_amin, int carveout, int32_t carveout_id,
+                          const double *volfill64, const float *fb_max, const double *fb_sum, const int64_t *fb_n,
+                          const float *carve_min, const double *carve_sum, const int64_t *carve_n, float *volfill,
+                          float *maxcarve, float *volcarve, int64_t *ncarvecells, float *volfb, float *maxfb,
+                          int8_t *complete, uint8_t *pit_out, uint8_t *pair_included, void *stream);
+/* select_solution over row bands: per-band partial tables (min-reduce wall_min, max-reduce sink_max, sum carve_water),
+ * then the decision tree on the reduced tables.  wall / sink (and then wall_min / sink_max) may be NULL. */
+int hc_band_select_partials_dev(hc_ctx *ctx, const int32_t *fillID, const int32_t *carve_bound, int64_t n, int32_t npits,
+                                int32_t ncarves, const float *wall, const float *water, const float *sink, float *wall_min,
+                                float *sink_max, int64_t *carve_water, void *stream);
+int hc_pit_select_tables_dev(hc_ctx *ctx, int32_t npits, const float *maxfill, const float *volfill, const float *maxcarve,
+                             const float *volcarve, const float *volfb, const float *maxfb, const int8_t *complete,
+                             const int64_t *nfill, const int64_t *ncarvecells, const uint8_t *pit_out, const int64_t *pairs,
+                             const uint8_t *pair_included, int64_t npairs, const float *wall_min, const float *sink_max,
+                             const int64_t *carve_water, double fill_vol_thresh, double carve_vol_thresh,
+                             double max_carve_depth, double maxcarve_factor, int apply_shallow_fill, int float32_scalars,
+                             int32_t *solution, void *stream);
 /* dep.select_solution (:517-810): decision tree per pit -> 4-digit codes.  wall / sink may be NULL; water
  * must not be (the reference raises NameError without a water mask, :606-647).  float32_scalars selects
  * the arithmetic numpy gives the reference's scalar expressions: 1 = float32 (numpy >= 2, weak Python

@@ -54,6 +54,14 @@ SIGNATURES = {
                                               c_i64, c_f64, c_vp, c_vp]),
     "hc_breach_least_cost_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_i64, c_f64, ctypes.c_int, c_f64,
                                                 c_vp, c_vp]),
+    "hc_band_catalog_local_dev": (ctypes.c_int, [c_vp, c_vp, c_f32] + [c_vp] * 6 + [c_i64, c_i64, ctypes.c_int32, ctypes.c_int32]
+                                  + [c_vp] * 13 + [c_i64, ctypes.POINTER(c_i64), c_vp]),
+    "hc_band_catalog_owner_ids_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hc_catalog_finish_dev": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_vp, c_i64, c_vp, c_vp, ctypes.c_int,
+                                             ctypes.c_int32] + [c_vp] * 16 + [c_vp]),
+    "hc_band_select_partials_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int32, ctypes.c_int32] + [c_vp] * 6 + [c_vp]),
+    "hc_pit_select_tables_dev": (ctypes.c_int, [c_vp, ctypes.c_int32] + [c_vp] * 12 + [c_i64] + [c_vp] * 3
+                                 + [c_f64] * 4 + [ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "hc_lzw_decode_host": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64)]),
     "hc_lzw_encode_host": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64)]),
     "hc_breach_depressions_host": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_f32, c_i64, c_f64, ctypes.c_int,

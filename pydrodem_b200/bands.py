@@ -499,3 +499,228 @@ def apply_rank(fn, own_rasters, halo, comm=None):
     top = halo if rank > 0 else 0
     crop = lambda o: o[top:top + nb]  # noqa: E731
     return tuple(crop(o) for o in res) if isinstance(res, tuple) else crop(res)
+
+
+# ---- pit catalog / selection / apply over row bands (SURVEY.md §8e "Catalog / select / apply": AllReduce of per-label
+# ---- partial max / sum).  The per-cell reductions run band by band (hc_band_catalog_local_dev, hc_band_select_partials_dev),
+# ---- the per-label tables are reduced across the bands (torch.distributed all_reduce over NCCL; plain tensor ops between the
+# ---- bands one process holds), the small table logic runs redundantly on every rank, and apply_solution is per cell.
+class BandedCatalog:
+    """dep.build_pit_catalog / select_solution / apply_solution (tools/depressions.py:272-810, :1140-1228) for one raster
+    cut into row bands.  `bands`: this process's consecutive bands, each a dict of flat device tensors
+    dem, carve, dcarve, dfill (float32) and fid, cid, cfid (int32 label rasters with WHOLE-RASTER ids, e.g. from
+    BandedLabel) plus `cell0`, the whole-raster index of the band's first cell.  Results equal the whole-raster calls
+    (counts, maxima, codes and the applied surface exactly; the float64-accumulated volume columns to the last ulp of
+    their float32 value, since partial sums are added in a different order)."""
+
+    def __init__(self, bands, nodataval, carveout=False, comm=None):
+        import torch
+        self.torch = torch
+        self.comm = comm if comm is not None else SeamComm()
+        self.bands = bands
+        self.nodata = float(nodataval)
+        self.carveout = bool(carveout)
+        self.lib = _lib.load()
+        self.dev = bands[0]["dem"].device
+        self.ctx = _lib.context(self.dev.index or 0)
+        self.state = None
+
+    # -- reductions: between this process's bands by tensor ops, between the ranks by all_reduce ----------------------
+    def _reduce(self, parts, op):
+        torch, dist = self.torch, self.comm.dist
+        fn = {"max": torch.maximum, "min": torch.minimum, "sum": torch.add}[op]
+        out = parts[0].clone()
+        for p in parts[1:]:
+            out = fn(out, p)
+        if self.comm.world > 1:
+            rop = {"max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN, "sum": dist.ReduceOp.SUM}[op]
+            dist.all_reduce(out, op=rop, group=self.comm.group)
+        return out
+
+    def _reduce_u64(self, parts, op):
+        """unsigned 64-bit max / min of keys held in int64 tensors: flip the sign bit, reduce signed, flip back"""
+        flip = -(1 << 63)
+        return self._reduce([p ^ flip for p in parts], op) ^ flip
+
+    def _p(self, t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def build(self):
+        """-> DFpits (the reference's columns), replicated on every rank"""
+        import numpy as np
+        import pandas as pd
+        torch = self.torch
+        f32, f64, i32, i64 = torch.float32, torch.float64, torch.int32, torch.int64
+        dv = self.dev
+        big = torch.iinfo(i64).max
+        # label counts and the carve that holds the first nodata cell of the WHOLE raster (:335)
+        loc = []
+        for b in self.bands:
+            nd = torch.nonzero(b["dem"] == self.nodata).reshape(-1)
+            first = big if nd.numel() == 0 else ((int(b["cell0"]) + int(nd[0])) << 32) | max(int(b["cid"][nd[0]]), 0)
+            loc.append(torch.tensor([int(b["fid"].max()), max(int(b["cid"].max()), 0), -first], dtype=i64, device=dv))
+        g = self._reduce(loc, "max")
+        npits, ncarves, first = int(g[0]), int(g[1]), -int(g[2])
+        carveout_id = 0
+        if not self.carveout:
+            if first == big:
+                raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # as the reference (:335)
+            carveout_id = first & 0xFFFFFFFF
+        P1, C1 = npits + 1, ncarves + 1
+        names = (("maxfill", P1, f32, "max"), ("volfill64", P1, f64, "sum"), ("nfill", P1, i64, "sum"), ("fb_max", P1, f32, "max"),
+                 ("fb_sum", P1, f64, "sum"), ("fb_n", P1, i64, "sum"), ("carve_min", C1, f32, "min"), ("carve_sum", C1, f64, "sum"),
+                 ("carve_n", C1, i64, "sum"), ("kmax", C1, i64, "umax"), ("kmin", C1, i64, "umin"))
+        parts = {k: [] for k, *_ in names}
+        pair_parts = []
+        with torch.cuda.device(dv):
+            for b in self.bands:
+                n = b["dem"].numel()
+                b["carve_bound"] = torch.empty(n, dtype=i32, device=dv)
+                t = {k: torch.empty(m, dtype=dt, device=dv) for k, m, dt, _ in names}
+                cap = max(1024, 4 * (npits + ncarves) + 1024)
+                npairs = ctypes.c_int64(0)
+                while True:
+                    pairs = torch.empty(cap, dtype=i64, device=dv)
+                    rc = self.lib.hc_band_catalog_local_dev(
+                        self.ctx, self._p(b["dem"]), self.nodata, self._p(b["carve"]), self._p(b["dcarve"]), self._p(b["dfill"]),
+                        self._p(b["fid"]), self._p(b["cid"]), self._p(b["cfid"]), n, int(b["cell0"]), npits, ncarves,
+                        self._p(b["carve_bound"]), *[self._p(t[k]) for k, *_ in names], self._p(pairs), cap,
+                        ctypes.byref(npairs), self._stream())
+                    if rc == -4 and cap < (1 << 28):   # HC_ERR_TOO_LARGE: more distinct pairs than the table holds
+                        cap *= 8
+                        continue
+                    _lib.check(rc, "hc_band_catalog_local_dev")
+                    break
+                for k, *_ in names:
+                    parts[k].append(t[k])
+                pair_parts.append(pairs[: int(npairs.value)])
+            red = {}
+            for k, _, _, op in names:
+                red[k] = self._reduce_u64(parts[k], op[1:]) if op[0] == "u" else self._reduce(parts[k], op)
+            # the distinct pairs of all bands
+            mine = torch.cat(pair_parts) if pair_parts else torch.empty(0, dtype=i64, device=dv)
+            if self.comm.world > 1:
+                cnt = torch.tensor([mine.numel()], dtype=i64, device=dv)
+                allc = self.comm.gather(cnt)
+                width = int(allc.max())
+                padded = torch.zeros((1, max(width, 1)), dtype=i64, device=dv)
+                padded[0, : mine.numel()] = mine
+                mine = self.comm.gather(padded).reshape(-1)
+                mine = mine[mine != 0]
+            pairs = torch.unique(mine)
+            np_ = int(pairs.numel())
+            pairs = pairs.contiguous() if np_ else torch.zeros(1, dtype=i64, device=dv)
+            # pit ids at the carves' extreme cells: every band answers for the cells it owns
+            fa, fb = [], []
+            for b in self.bands:
+                a = torch.empty(C1, dtype=i32, device=dv)
+                c = torch.empty(C1, dtype=i32, device=dv)
+                _lib.check(self.lib.hc_band_catalog_owner_ids_dev(self.ctx, self._p(b["fid"]), b["fid"].numel(), int(b["cell0"]),
+                                                                   ncarves, self._p(red["kmax"]), self._p(red["kmin"]),
+                                                                   self._p(a), self._p(c), self._stream()),
+                           "hc_band_catalog_owner_ids_dev")
+                fa.append(a)
+                fb.append(c)
+            fid_amax, fid_amin = self._reduce(fa, "max"), self._reduce(fb, "max")
+            out = {k: torch.empty(P1, dtype=f32, device=dv) for k in ("volfill", "maxcarve", "volcarve", "volfb", "maxfb")}
+            ncarvecells = torch.empty(P1, dtype=i64, device=dv)
+            complete = torch.empty(P1, dtype=torch.int8, device=dv)
+            pit_out = torch.empty(P1, dtype=torch.uint8, device=dv)
+            included = torch.zeros(max(np_, 1), dtype=torch.uint8, device=dv)
+            _lib.check(self.lib.hc_catalog_finish_dev(
+                self.ctx, npits, ncarves, self._p(pairs), np_, self._p(fid_amax), self._p(fid_amin), int(self.carveout),
+                carveout_id, self._p(red["volfill64"]), self._p(red["fb_max"]), self._p(red["fb_sum"]), self._p(red["fb_n"]),
+                self._p(red["carve_min"]), self._p(red["carve_sum"]), self._p(red["carve_n"]), self._p(out["volfill"]),
+                self._p(out["maxcarve"]), self._p(out["volcarve"]), self._p(ncarvecells), self._p(out["volfb"]),
+                self._p(out["maxfb"]), self._p(complete), self._p(pit_out), self._p(included), self._stream()),
+                "hc_catalog_finish_dev")
+        self.state = dict(npits=npits, ncarves=ncarves, pairs=pairs, npairs=np_, included=included, pit_out=pit_out,
+                          ncarvecells=ncarvecells, nfill=red["nfill"], maxfill=red["maxfill"], complete=complete, **out)
+        cols = {k: v[1:].cpu().numpy() for k, v in out.items()}
+        DFpits = pd.DataFrame({'fillcarveID': np.arange(1, npits + 1), 'maxfill': red["maxfill"][1:].cpu().numpy(),
+                               'volfill': cols["volfill"], 'maxcarve': cols["maxcarve"], 'volcarve': cols["volcarve"],
+                               'volfillbehind': cols["volfb"], 'maxfillbehind': cols["maxfb"],
+                               'completecarve': complete[1:].cpu().numpy()})
+        DFpits.index = DFpits['fillcarveID']
+        DFpits.drop(labels=['fillcarveID'], axis=1, inplace=True)
+        return DFpits
+
+    def select(self, DFpits, fill_vol_thresh, carve_vol_thresh, max_carve_depth, maxcarve_factor=1.25, apply_shallow_fill=False,
+               wall=None, water=None, sink=None, numpy_scalars=None):
+        """dep.select_solution: `wall` / `water` / `sink` are lists with one flat float32 device tensor per local band
+        (wall / sink may be None); adds the 'solution' and 'downstream_pit' columns."""
+        import numpy as np
+        torch = self.torch
+        if water is None:
+            raise NameError("name 'water_mask_vec' is not defined")  # the reference's latent bug, kept (SURVEY.md §3.6)
+        if numpy_scalars is None:
+            numpy_scalars = "weak" if int(np.__version__.split(".")[0]) >= 2 else "legacy"
+        s = self.state
+        npits, ncarves = s["npits"], s["ncarves"]
+        P1, C1 = npits + 1, ncarves + 1
+        dv = self.dev
+        wm, sx, cw = [], [], []
+        with torch.cuda.device(dv):
+            for i, b in enumerate(self.bands):
+                w_ = torch.empty(P1, dtype=torch.float32, device=dv) if wall is not None else None
+                s_ = torch.empty(P1, dtype=torch.float32, device=dv) if sink is not None else None
+                c_ = torch.empty(C1, dtype=torch.int64, device=dv)
+                _lib.check(self.lib.hc_band_select_partials_dev(
+                    self.ctx, self._p(b["fid"]), self._p(b["carve_bound"]), b["fid"].numel(), npits, ncarves,
+                    self._p(wall[i]) if wall is not None else None, self._p(water[i]),
+                    self._p(sink[i]) if sink is not None else None, self._p(w_), self._p(s_), self._p(c_), self._stream()),
+                    "hc_band_select_partials_dev")
+                wm.append(w_)
+                sx.append(s_)
+                cw.append(c_)
+            wall_min = self._reduce(wm, "min") if wall is not None else None
+            sink_max = self._reduce(sx, "max") if sink is not None else None
+            carve_water = self._reduce(cw, "sum")
+            sol = torch.zeros(P1, dtype=torch.int32, device=dv)
+            _lib.check(self.lib.hc_pit_select_tables_dev(
+                self.ctx, npits, self._p(s["maxfill"]), self._p(s["volfill"]), self._p(s["maxcarve"]), self._p(s["volcarve"]),
+                self._p(s["volfb"]), self._p(s["maxfb"]), self._p(s["complete"]), self._p(s["nfill"]), self._p(s["ncarvecells"]),
+                self._p(s["pit_out"]), self._p(s["pairs"]), self._p(s["included"]), s["npairs"], self._p(wall_min),
+                self._p(sink_max), self._p(carve_water), float(fill_vol_thresh), float(carve_vol_thresh), float(max_carve_depth),
+                float(maxcarve_factor), int(bool(apply_shallow_fill)), 1 if numpy_scalars == "weak" else 0, self._p(sol),
+                self._stream()), "hc_pit_select_tables_dev")
+        s["solution"] = sol
+        DFpits["solution"] = sol[1:].cpu().numpy().astype(np.int64)
+        DFpits["downstream_pit"] = np.zeros(npits, dtype=np.int64)
+        return DFpits
+
+    def apply(self, DFpits, fill, carve=None, excludedpits=None):
+        """dep.apply_solution on every local band: `fill` = list of the bands' filled surfaces (flat float32 device
+        tensors), `carve` defaults to the bands' own carve rasters.  Pits absent from DFpits are left alone (the
+        reference loops over DFpits.index only).  -> (list of modified DEM bands, list of int16 solution masks)"""
+        import numpy as np
+        torch = self.torch
+        s = self.state
+        npits, ncarves = s["npits"], s["ncarves"]
+        dv = self.dev
+        solh = np.full(npits + 1, -1, np.int32)
+        solh[DFpits.index.to_numpy().astype(np.int64)] = DFpits["solution"].to_numpy().astype(np.int32)
+        sol = torch.from_numpy(solh).to(dv)
+        excl = None
+        if excludedpits is not None:
+            excl = torch.zeros(npits + 1, dtype=torch.uint8, device=dv)
+            if len(excludedpits):
+                excl[torch.as_tensor(list(excludedpits), dtype=torch.int64, device=dv)] = 1
+        outs, masks = [], []
+        with torch.cuda.device(dv):
+            for i, b in enumerate(self.bands):
+                n = b["dem"].numel()
+                out = torch.empty_like(b["dem"])
+                mask = torch.zeros(n, dtype=torch.int16, device=dv)
+                cv = b["carve"] if carve is None else carve[i]
+                _lib.check(self.lib.hc_pit_apply_dev(
+                    self.ctx, self._p(b["dem"]), self._p(fill[i]), self._p(cv), self._p(b["fid"]), self._p(b["carve_bound"]),
+                    self._p(b["cfid"]), n, npits, ncarves, self._p(sol), self._p(excl), self._p(s["pit_out"]),
+                    self._p(s["ncarvecells"]), self._p(s["pairs"]), self._p(s["included"]), s["npairs"], self._p(out),
+                    self._p(mask), self._stream()), "hc_pit_apply_dev")
+                outs.append(out)
+                masks.append(mask)
+        return outs, masks

@@ -67,17 +67,36 @@ k_seg_stats(const int32_t *__restrict__ ids, const float *__restrict__ vals, con
 // first index of the maximum / minimum per segment: key = (orderable(v), index) packed in 64 bits
 __global__ void __launch_bounds__(256)
 k_seg_argext(const int32_t *__restrict__ ids, const float *__restrict__ vals, size_t n, int nseg,
-             u64 *kmax, u64 *kmin) {
+             u64 *kmax, u64 *kmin, u32 cell0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int id = ids[i];
   if (id < 1 || id > nseg) return;
   u32 o = d_ford(vals[i]);
+  const u32 gi = cell0 + (u32)i;   // index in the whole raster (cell0: a row band's first cell)
   // max value, smallest index on ties  <=> max of (o, ~index)
-  u64 k1 = ((u64)o << 32) | (u64)(0xFFFFFFFFu - (u32)i);
+  u64 k1 = ((u64)o << 32) | (u64)(0xFFFFFFFFu - gi);
   if (k1 > kmax[id]) atomicMax(&kmax[id], k1);
-  u64 k2 = ((u64)o << 32) | (u64)(u32)i;
+  u64 k2 = ((u64)o << 32) | (u64)gi;
   if (k2 < kmin[id]) atomicMin(&kmin[id], k2);
+}
+// pit id at every carve's first highest / first lowest cell, as far as this band owns that cell (else 0): the two
+// look-ups of the inclusion test (:435-439).  -1: the carve has no cell at all.
+__global__ void k_argext_owner_ids(const u64 *kmax, const u64 *kmin, int nseg, const int32_t *__restrict__ fillID, u32 cell0,
+                                   size_t n, int32_t *fid_amax, int32_t *fid_amin) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nseg) return;
+  int32_t a = -1, b = -1;
+  if (kmax[s] != 0ull) {
+    const u32 g = 0xFFFFFFFFu - (u32)(kmax[s] & 0xFFFFFFFFu);
+    a = (g >= cell0 && (size_t)(g - cell0) < n) ? fillID[g - cell0] : 0;
+  }
+  if (kmin[s] != ~0ull) {
+    const u32 g = (u32)(kmin[s] & 0xFFFFFFFFu);
+    b = (g >= cell0 && (size_t)(g - cell0) < n) ? fillID[g - cell0] : 0;
+  }
+  fid_amax[s] = a;
+  fid_amin[s] = b;
 }
 __global__ void k_argext_decode(const u64 *kmax, const u64 *kmin, int nseg, long long *amax, long long *amin) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,17 +143,16 @@ __global__ void k_pairs_compact(const u64 *table, u32 tsize, long long *out, lon
 }
 
 // pair-level logic of build_pit_catalog (:412-441)
-__global__ void k_pair_flags(const long long *pairs, u32 np, const int32_t *__restrict__ fillID,
-                             const long long *carve_amax, const long long *carve_amin, int carveout, int carveout_id,
+__global__ void k_pair_flags(const long long *pairs, u32 np, const int32_t *__restrict__ fid_amax,
+                             const int32_t *__restrict__ fid_amin, int carveout, int carveout_id,
                              uint8_t *included, uint8_t *pit_out) {
   u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= np) return;
   int p = (int)((u64)pairs[j] >> 32), c = (int)((u64)pairs[j] & 0xFFFFFFFFu);
   // "does carve leave basin?": the carve that contains the nodata pixels touches this pit
   if (!carveout && c == carveout_id) pit_out[p] = 1;
-  long long imax = carve_amax[c], imin = carve_amin[c];
   bool inc = false;
-  if (imax >= 0) inc = (fillID[imax] == p) || (fillID[imin] != p);
+  if (fid_amax[c] >= 0) inc = (fid_amax[c] == p) || (fid_amin[c] != p);
   included[j] = inc ? 1 : 0;
 }
 // per pit: aggregate its included carves
@@ -194,53 +212,36 @@ extern "C" int hc_seg_stats_dev(hc_ctx *ctx, const int32_t *ids, const float *va
   return HC_OK;
 }
 
-// build_pit_catalog (tools/depressions.py:272-509).  All pointers are device pointers; per-pit
-// outputs have npits+1 entries (entry 0 unused), per-carve outputs ncarves+1.  pairs_out receives the
-// distinct (pit << 32 | carve) pairs, pair_included the reference's inclusion test per pair;
-// *npairs (host) their number.  carveout_id = carveID at the first nodata cell (:335), ignored when
-// carveout != 0.
-extern "C" int hc_pit_catalog_dev(hc_ctx *ctx, const float *dem, float nodata, const float *carve, const float *diff_carve,
-                                  const float *diff_fill, const int32_t *fillID, const int32_t *carveID,
-                                  const int32_t *carvefillID, int64_t n, int32_t npits, int32_t ncarves, int carveout,
-                                  int32_t carveout_id, int32_t *carve_bound, float *maxfill, float *volfill,
-                                  int64_t *nfill, float *maxcarve, float *volcarve, int64_t *ncarvecells, float *volfb,
-                                  float *maxfb, int8_t *complete, uint8_t *pit_out, int64_t *carve_amax,
-                                  int64_t *carve_amin, float *carve_min, double *carve_sum, int64_t *carve_n,
-                                  int64_t *pairs_out, int64_t pair_cap, uint8_t *pair_included, int64_t *npairs,
-                                  void *stream) {
-  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
-  hc_guard hc_guard__(ctx);
-  HC_CUDA(cudaSetDevice(ctx->device));
-  if (n <= 0 || n >= 0x7FFFFFF0ll || npits < 0 || ncarves < 0) { hc_set_error("hc_pit_catalog: bad shape"); return HC_ERR_ARG; }
-  cudaStream_t st = (cudaStream_t)stream;
-  HC_TRY(arena_reset(ctx));
-  const size_t P1 = (size_t)npits + 1, C1 = (size_t)ncarves + 1;
-  double *volfill64 = (double *)arena_take(ctx, P1 * 8);
-  double *fb_sum = (double *)arena_take(ctx, P1 * 8);
-  float *fb_max = (float *)arena_take(ctx, P1 * 4);
-  long long *fb_n = (long long *)arena_take(ctx, P1 * 8);
-  float *pit_mincarve = (float *)arena_take(ctx, P1 * 4);
-  double *pit_sumcarve = (double *)arena_take(ctx, P1 * 8);
-  u64 *kmax = (u64 *)arena_take(ctx, C1 * 8);
-  u64 *kmin = (u64 *)arena_take(ctx, C1 * 8);
-  u32 *cnt = (u32 *)arena_take(ctx, 256);
-  if (!volfill64 || !fb_sum || !fb_max || !fb_n || !pit_mincarve || !pit_sumcarve || !kmax || !kmin || !cnt) return HC_ERR_NOMEM;
+// build_pit_catalog (tools/depressions.py:272-509) in three steps, so that a raster cut into row bands can run the
+// first on every band, reduce the per-label tables across the bands (max / min / sum; the arg-extreme keys carry whole-
+// raster cell indices) and run the other two on the reduced tables ("AllReduce of per-label partial
+// max / sum").  hc_pit_catalog_dev is the three back to back on one raster.
+struct catalog_partials {
+  float *maxfill; double *volfill64; long long *nfill;          // per pit: diff_fill over its cells (:392-394)
+  float *fb_max; double *fb_sum; long long *fb_n;               // per pit: fill behind the carve (:395,449,457)
+  float *carve_min; double *carve_sum; long long *carve_n;      // per carve: diff_carve over its bounded cells
+  u64 *kmax, *kmin;                                             // per carve: first arg-max / arg-min of carve_vec (:421-424)
+};
 
+// step 1: everything that is a reduction over cells.  *npairs (host) = distinct (pit, carve) pairs of these cells.
+static int catalog_local(hc_ctx *ctx, const float *dem, float nodata, const float *carve, const float *diff_carve,
+                         const float *diff_fill, const int32_t *fillID, const int32_t *carveID, const int32_t *carvefillID,
+                         int64_t n, u32 cell0, int32_t npits, int32_t ncarves, int32_t *carve_bound, const catalog_partials &t,
+                         int64_t *pairs_out, int64_t pair_cap, int64_t *npairs, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t C1 = (size_t)ncarves + 1;
+  u32 *cnt = (u32 *)arena_take(ctx, 256);
+  if (!cnt) return HC_ERR_NOMEM;
   HC_PROF(ctx, st, "k_carve_bound");
   k_carve_bound<<<nblk((size_t)n), 256, 0, st>>>(carveID, dem, nodata, (size_t)n, carve_bound);
   HC_LAUNCH_CHECK(ctx);
-  // per pit: max / sum / count of diff_fill (:392-394)
-  HC_TRY(hc_seg_stats_dev(ctx, fillID, diff_fill, nullptr, n, npits, 1, maxfill, nullptr, volfill64, nfill, stream));
-  // per pit: fill behind the carve = pit cells with carvefillID > 0 (:395,449,457)
-  HC_TRY(hc_seg_stats_dev(ctx, fillID, diff_carve, carvefillID, n, npits, 1, fb_max, nullptr, fb_sum, (int64_t *)fb_n, stream));
-  // per carve: min / sum / count of diff_carve over its (bounded) cells, first argmax / argmin of carve_vec (:421-424)
-  HC_TRY(hc_seg_stats_dev(ctx, carve_bound, diff_carve, nullptr, n, ncarves, 1, nullptr, carve_min, carve_sum, carve_n, stream));
-  HC_CUDA(cudaMemsetAsync(kmax, 0, C1 * 8, st));
-  HC_CUDA(cudaMemsetAsync(kmin, 0xFF, C1 * 8, st));
+  HC_TRY(hc_seg_stats_dev(ctx, fillID, diff_fill, nullptr, n, npits, 1, t.maxfill, nullptr, t.volfill64, (int64_t *)t.nfill, stream));
+  HC_TRY(hc_seg_stats_dev(ctx, fillID, diff_carve, carvefillID, n, npits, 1, t.fb_max, nullptr, t.fb_sum, (int64_t *)t.fb_n, stream));
+  HC_TRY(hc_seg_stats_dev(ctx, carve_bound, diff_carve, nullptr, n, ncarves, 1, nullptr, t.carve_min, t.carve_sum, (int64_t *)t.carve_n, stream));
+  HC_CUDA(cudaMemsetAsync(t.kmax, 0, C1 * 8, st));
+  HC_CUDA(cudaMemsetAsync(t.kmin, 0xFF, C1 * 8, st));
   HC_PROF(ctx, st, "k_seg_argext");
-  k_seg_argext<<<nblk((size_t)n), 256, 0, st>>>(carve_bound, carve, (size_t)n, ncarves, kmax, kmin);
-  HC_LAUNCH_CHECK(ctx);
-  k_argext_decode<<<nblk(C1), 256, 0, st>>>(kmax, kmin, ncarves, (long long *)carve_amax, (long long *)carve_amin);
+  k_seg_argext<<<nblk((size_t)n), 256, 0, st>>>(carve_bound, carve, (size_t)n, ncarves, t.kmax, t.kmin, cell0);
   HC_LAUNCH_CHECK(ctx);
   // distinct (pit, carve) pairs
   u32 tsize = 1024;
@@ -260,26 +261,130 @@ extern "C" int hc_pit_catalog_dev(hc_ctx *ctx, const float *dem, float nodata, c
     hc_set_error("hc_pit_catalog: more than %lld distinct (pit, carve) pairs", (long long)pair_cap);
     return HC_ERR_TOO_LARGE;
   }
-  const u32 np = ctx->h_mail[0];
-  if (npairs) *npairs = np;
+  if (npairs) *npairs = ctx->h_mail[0];
+  return HC_OK;
+}
+
+// step 3: pair-level logic and the per-pit carve columns from the (reduced) tables
+static int catalog_finish(hc_ctx *ctx, int32_t npits, int32_t ncarves, const int64_t *pairs, int64_t np, const int32_t *fid_amax,
+                          const int32_t *fid_amin, int carveout, int32_t carveout_id, const catalog_partials &t,
+                          float *volfill, float *maxcarve, float *volcarve, int64_t *ncarvecells, float *volfb, float *maxfb,
+                          int8_t *complete, uint8_t *pit_out, uint8_t *pair_included, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t P1 = (size_t)npits + 1;
+  float *pit_mincarve = (float *)arena_take(ctx, P1 * 4);
+  double *pit_sumcarve = (double *)arena_take(ctx, P1 * 8);
+  if (!pit_mincarve || !pit_sumcarve) return HC_ERR_NOMEM;
   HC_CUDA(cudaMemsetAsync(pit_out, 0, P1, st));
   k_fill_f32<<<nblk(P1), 256, 0, st>>>(pit_mincarve, INFINITY, P1);
   HC_LAUNCH_CHECK(ctx);
   HC_CUDA(cudaMemsetAsync(pit_sumcarve, 0, P1 * 8, st));
   HC_CUDA(cudaMemsetAsync(ncarvecells, 0, P1 * 8, st));
   if (np) {
-    k_pair_flags<<<nblk(np), 256, 0, st>>>((const long long *)pairs_out, np, fillID, (const long long *)carve_amax,
-                                            (const long long *)carve_amin, carveout, carveout_id, pair_included, pit_out);
+    k_pair_flags<<<nblk((size_t)np), 256, 0, st>>>((const long long *)pairs, (u32)np, fid_amax, fid_amin, carveout, carveout_id,
+                                                   pair_included, pit_out);
     HC_LAUNCH_CHECK(ctx);
-    k_pair_reduce<<<nblk(np), 256, 0, st>>>((const long long *)pairs_out, np, pair_included, pit_out, carve_min, carve_sum,
-                                             (const long long *)carve_n, nullptr, pit_mincarve, pit_sumcarve,
-                                             (long long *)ncarvecells, nullptr);
+    k_pair_reduce<<<nblk((size_t)np), 256, 0, st>>>((const long long *)pairs, (u32)np, pair_included, pit_out, t.carve_min, t.carve_sum,
+                                                    t.carve_n, nullptr, pit_mincarve, pit_sumcarve, (long long *)ncarvecells, nullptr);
     HC_LAUNCH_CHECK(ctx);
   }
-  k_catalog_finish<<<nblk(P1), 256, 0, st>>>(npits, pit_out, pit_mincarve, pit_sumcarve, (const long long *)ncarvecells, fb_sum,
-                                             fb_max, fb_n, maxcarve, volcarve, volfb, maxfb, complete, volfill64, volfill);
+  k_catalog_finish<<<nblk(P1), 256, 0, st>>>(npits, pit_out, pit_mincarve, pit_sumcarve, (const long long *)ncarvecells, t.fb_sum,
+                                             t.fb_max, t.fb_n, maxcarve, volcarve, volfb, maxfb, complete, t.volfill64, volfill);
+  HC_LAUNCH_CHECK(ctx);
+  (void)ncarves;
+  return HC_OK;
+}
+
+// All pointers are device pointers; per-pit outputs have npits+1 entries (entry 0 unused), per-carve outputs
+// ncarves+1.  pairs_out receives the distinct (pit << 32 | carve) pairs, pair_included the reference's inclusion
+// test per pair; *npairs (host) their number.  carveout_id = carveID at the first nodata cell (:335), ignored when
+// carveout != 0.
+extern "C" int hc_pit_catalog_dev(hc_ctx *ctx, const float *dem, float nodata, const float *carve, const float *diff_carve,
+                                  const float *diff_fill, const int32_t *fillID, const int32_t *carveID,
+                                  const int32_t *carvefillID, int64_t n, int32_t npits, int32_t ncarves, int carveout,
+                                  int32_t carveout_id, int32_t *carve_bound, float *maxfill, float *volfill,
+                                  int64_t *nfill, float *maxcarve, float *volcarve, int64_t *ncarvecells, float *volfb,
+                                  float *maxfb, int8_t *complete, uint8_t *pit_out, int64_t *carve_amax,
+                                  int64_t *carve_amin, float *carve_min, double *carve_sum, int64_t *carve_n,
+                                  int64_t *pairs_out, int64_t pair_cap, uint8_t *pair_included, int64_t *npairs,
+                                  void *stream) {
+  if (!ctx) { hc_set_error("null context"); return HC_ERR_ARG; }
+  hc_guard hc_guard__(ctx);
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (n <= 0 || n >= 0x7FFFFFF0ll || npits < 0 || ncarves < 0) { hc_set_error("hc_pit_catalog: bad shape"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HC_TRY(arena_reset(ctx));
+  const size_t P1 = (size_t)npits + 1, C1 = (size_t)ncarves + 1;
+  catalog_partials t;
+  t.maxfill = maxfill; t.nfill = (long long *)nfill;
+  t.carve_min = carve_min; t.carve_sum = carve_sum; t.carve_n = (long long *)carve_n;
+  t.volfill64 = (double *)arena_take(ctx, P1 * 8);
+  t.fb_sum = (double *)arena_take(ctx, P1 * 8);
+  t.fb_max = (float *)arena_take(ctx, P1 * 4);
+  t.fb_n = (long long *)arena_take(ctx, P1 * 8);
+  t.kmax = (u64 *)arena_take(ctx, C1 * 8);
+  t.kmin = (u64 *)arena_take(ctx, C1 * 8);
+  int32_t *fid_amax = (int32_t *)arena_take(ctx, C1 * 4), *fid_amin = (int32_t *)arena_take(ctx, C1 * 4);
+  if (!t.volfill64 || !t.fb_sum || !t.fb_max || !t.fb_n || !t.kmax || !t.kmin || !fid_amax || !fid_amin) return HC_ERR_NOMEM;
+  int64_t np = 0;
+  HC_TRY(catalog_local(ctx, dem, nodata, carve, diff_carve, diff_fill, fillID, carveID, carvefillID, n, 0u, npits, ncarves,
+                       carve_bound, t, pairs_out, pair_cap, &np, stream));
+  if (npairs) *npairs = np;
+  k_argext_decode<<<nblk(C1), 256, 0, st>>>(t.kmax, t.kmin, ncarves, (long long *)carve_amax, (long long *)carve_amin);
+  HC_LAUNCH_CHECK(ctx);
+  k_argext_owner_ids<<<nblk(C1), 256, 0, st>>>(t.kmax, t.kmin, ncarves, fillID, 0u, (size_t)n, fid_amax, fid_amin);
+  HC_LAUNCH_CHECK(ctx);
+  return catalog_finish(ctx, npits, ncarves, pairs_out, np, fid_amax, fid_amin, carveout, carveout_id, t, volfill, maxcarve,
+                        volcarve, ncarvecells, volfb, maxfb, complete, pit_out, pair_included, stream);
+}
+
+// ---- the same over row bands (pydrodem_b200/bands.py pit_catalog_banded) ------------------------------------------------
+// step 1 on one band: `cell0` = whole-raster index of the band's first cell, label rasters hold WHOLE-RASTER ids
+// (bands.label_banded).  Outputs are this band's partial tables, to be reduced across the bands by the caller: max for
+// maxfill / fb_max / kmax (unsigned), min for carve_min / kmin (unsigned), sum for the float64 sums and the counts; the
+// pair lists are concatenated and made unique.
+extern "C" int hc_band_catalog_local_dev(hc_ctx *ctx, const float *dem, float nodata, const float *carve, const float *diff_carve,
+                                         const float *diff_fill, const int32_t *fillID, const int32_t *carveID,
+                                         const int32_t *carvefillID, int64_t n, int64_t cell0, int32_t npits, int32_t ncarves,
+                                         int32_t *carve_bound, float *maxfill, double *volfill64, int64_t *nfill, float *fb_max,
+                                         double *fb_sum, int64_t *fb_n, float *carve_min, double *carve_sum, int64_t *carve_n,
+                                         uint64_t *kmax, uint64_t *kmin, int64_t *pairs_out, int64_t pair_cap, int64_t *npairs,
+                                         void *stream) {
+  HC_ENTER(ctx);
+  if (n <= 0 || cell0 < 0 || cell0 + n >= 0x7FFFFFF0ll || npits < 0 || ncarves < 0) { hc_set_error("hc_band_catalog_local: bad shape"); return HC_ERR_ARG; }
+  HC_TRY(arena_reset(ctx));
+  catalog_partials t = {maxfill, volfill64, (long long *)nfill, fb_max, fb_sum, (long long *)fb_n, carve_min, carve_sum,
+                        (long long *)carve_n, (u64 *)kmax, (u64 *)kmin};
+  return catalog_local(ctx, dem, nodata, carve, diff_carve, diff_fill, fillID, carveID, carvefillID, n, (u32)cell0, npits, ncarves,
+                       carve_bound, t, pairs_out, pair_cap, npairs, stream);
+}
+// step 2 on one band, after kmax / kmin were reduced: the pit ids at the carves' extreme cells this band owns (0
+// elsewhere, -1 for an empty carve): max-reduce across the bands.
+extern "C" int hc_band_catalog_owner_ids_dev(hc_ctx *ctx, const int32_t *fillID, int64_t n, int64_t cell0, int32_t ncarves,
+                                             const uint64_t *kmax, const uint64_t *kmin, int32_t *fid_amax, int32_t *fid_amin,
+                                             void *stream) {
+  HC_ENTER(ctx);
+  if (n <= 0 || cell0 < 0 || ncarves < 0 || !fillID || !kmax || !kmin || !fid_amax || !fid_amin) { hc_set_error("hc_band_catalog_owner_ids: bad argument"); return HC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  k_argext_owner_ids<<<nblk((size_t)ncarves + 1), 256, 0, st>>>((const u64 *)kmax, (const u64 *)kmin, ncarves, fillID, (u32)cell0, (size_t)n,
+                                                               fid_amax, fid_amin);
   HC_LAUNCH_CHECK(ctx);
   return HC_OK;
+}
+// step 3 on the reduced tables (every rank, redundantly: the tables are small): the catalog's columns
+extern "C" int hc_catalog_finish_dev(hc_ctx *ctx, int32_t npits, int32_t ncarves, const int64_t *pairs, int64_t npairs,
+                                     const int32_t *fid_amax, const int32_t *fid_amin, int carveout, int32_t carveout_id,
+                                     const double *volfill64, const float *fb_max, const double *fb_sum, const int64_t *fb_n,
+                                     const float *carve_min, const double *carve_sum, const int64_t *carve_n, float *volfill,
+                                     float *maxcarve, float *volcarve, int64_t *ncarvecells, float *volfb, float *maxfb,
+                                     int8_t *complete, uint8_t *pit_out, uint8_t *pair_included, void *stream) {
+  HC_ENTER(ctx);
+  if (npits < 0 || ncarves < 0 || npairs < 0) { hc_set_error("hc_catalog_finish: bad shape"); return HC_ERR_ARG; }
+  HC_TRY(arena_reset(ctx));
+  catalog_partials t = {nullptr, (double *)volfill64, nullptr, (float *)fb_max, (double *)fb_sum, (long long *)fb_n,
+                        (float *)carve_min, (double *)carve_sum, (long long *)carve_n, nullptr, nullptr};
+  return catalog_finish(ctx, npits, ncarves, pairs, npairs, fid_amax, fid_amin, carveout, carveout_id, t, volfill, maxcarve, volcarve,
+                        ncarvecells, volfb, maxfb, complete, pit_out, pair_included, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -340,6 +445,55 @@ __global__ void k_nonzero_sel(const float *w, size_t n, int32_t *o) {
   if (i < n) o[i] = w[i] != 0.f ? 1 : 0;
 }
 
+// select_solution in two steps, split like the catalog: the reductions over cells (per pit: is it inside the wall, does
+// it hold a sink; per carve: how many of its cells lie in the water mask), then the decision tree on the tables.
+static int select_partials(hc_ctx *ctx, const int32_t *fillID, const int32_t *carve_bound, int64_t n, int32_t npits,
+                           int32_t ncarves, const float *wall, const float *water, const float *sink, float *wall_min,
+                           float *sink_max, int64_t *carve_water, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t *wsel = (int32_t *)arena_take(ctx, (size_t)n * 4);
+  if (!wsel) return HC_ERR_NOMEM;
+  if (wall) HC_TRY(hc_seg_stats_dev(ctx, fillID, wall, nullptr, n, npits, 1, nullptr, wall_min, nullptr, nullptr, stream));
+  if (sink) HC_TRY(hc_seg_stats_dev(ctx, fillID, sink, nullptr, n, npits, 1, sink_max, nullptr, nullptr, nullptr, stream));
+  // np.count_nonzero(water_mask_vec[carve_cells]) per carve
+  k_nonzero_sel<<<nblk((size_t)n), 256, 0, st>>>(water, (size_t)n, wsel);
+  HC_LAUNCH_CHECK(ctx);
+  return hc_seg_stats_dev(ctx, carve_bound, nullptr, wsel, n, ncarves, 1, nullptr, nullptr, nullptr, carve_water, stream);
+}
+
+static int select_tables(hc_ctx *ctx, int32_t npits, const float *maxfill, const float *volfill, const float *maxcarve,
+                         const float *volcarve, const float *volfb, const float *maxfb, const int8_t *complete,
+                         const int64_t *nfill, const int64_t *ncarvecells, const uint8_t *pit_out, const int64_t *pairs,
+                         const uint8_t *pair_included, int64_t npairs, const float *wall_min, const float *sink_max,
+                         const int64_t *carve_water, double fill_vol_thresh, double carve_vol_thresh, double max_carve_depth,
+                         double maxcarve_factor, int apply_shallow_fill, int float32_scalars, int32_t *solution, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t P1 = (size_t)npits + 1;
+  long long *pit_water = (long long *)arena_take(ctx, P1 * 8);
+  if (!pit_water) return HC_ERR_NOMEM;
+  HC_CUDA(cudaMemsetAsync(pit_water, 0, P1 * 8, st));
+  if (npairs) {   // ... summed over a pit's included carves
+    k_pair_reduce<<<nblk((size_t)npairs), 256, 0, st>>>((const long long *)pairs, (u32)npairs, pair_included, pit_out, nullptr,
+                                                         nullptr, nullptr, (const long long *)carve_water, nullptr, nullptr, nullptr,
+                                                         pit_water);
+    HC_LAUNCH_CHECK(ctx);
+  }
+  select_params prm = {fill_vol_thresh, carve_vol_thresh, max_carve_depth, maxcarve_factor, apply_shallow_fill,
+                       wall_min ? 1 : 0, sink_max ? 1 : 0};
+  HC_CUDA(cudaMemsetAsync(solution, 0, 4, st));
+  HC_PROF(ctx, st, "k_select");
+  if (float32_scalars)
+    k_select<float><<<nblk(P1), 256, 0, st>>>(npits, maxfill, volfill, maxcarve, volcarve, volfb, maxfb, complete,
+                                              (const long long *)nfill, (const long long *)ncarvecells, pit_water, wall_min,
+                                              sink_max, prm, solution);
+  else
+    k_select<double><<<nblk(P1), 256, 0, st>>>(npits, maxfill, volfill, maxcarve, volcarve, volfb, maxfb, complete,
+                                               (const long long *)nfill, (const long long *)ncarvecells, pit_water, wall_min,
+                                               sink_max, prm, solution);
+  HC_LAUNCH_CHECK(ctx);
+  return HC_OK;
+}
+
 // wall / water / sink rasters arrive as float32 (host converts); any of them may be NULL
 extern "C" int hc_pit_select_dev(hc_ctx *ctx, const int32_t *fillID, const int32_t *carve_bound, int64_t n, int32_t npits,
                                  int32_t ncarves, const float *maxfill, const float *volfill, const float *maxcarve,
@@ -353,41 +507,46 @@ extern "C" int hc_pit_select_dev(hc_ctx *ctx, const int32_t *fillID, const int32
   hc_guard hc_guard__(ctx);
   HC_CUDA(cudaSetDevice(ctx->device));
   if (!water) { hc_set_error("select_solution: water_mask_array is None (the reference raises NameError here, tools/depressions.py:606-647)"); return HC_ERR_ARG; }
-  cudaStream_t st = (cudaStream_t)stream;
   HC_TRY(arena_reset(ctx));
   const size_t P1 = (size_t)npits + 1, C1 = (size_t)ncarves + 1;
   float *wall_min = (float *)arena_take(ctx, P1 * 4);
   float *sink_max = (float *)arena_take(ctx, P1 * 4);
-  long long *carve_water = (long long *)arena_take(ctx, C1 * 8);
-  long long *pit_water = (long long *)arena_take(ctx, P1 * 8);
-  int32_t *wsel = (int32_t *)arena_take(ctx, (size_t)n * 4);
-  if (!wall_min || !sink_max || !carve_water || !pit_water || !wsel) return HC_ERR_NOMEM;
-  if (wall) HC_TRY(hc_seg_stats_dev(ctx, fillID, wall, nullptr, n, npits, 1, nullptr, wall_min, nullptr, nullptr, stream));
-  if (sink) HC_TRY(hc_seg_stats_dev(ctx, fillID, sink, nullptr, n, npits, 1, sink_max, nullptr, nullptr, nullptr, stream));
-  // np.count_nonzero(water_mask_vec[carve_cells]) per carve, then summed over a pit's included carves
-  k_nonzero_sel<<<nblk((size_t)n), 256, 0, st>>>(water, (size_t)n, wsel);
-  HC_LAUNCH_CHECK(ctx);
-  HC_TRY(hc_seg_stats_dev(ctx, carve_bound, nullptr, wsel, n, ncarves, 1, nullptr, nullptr, nullptr, (int64_t *)carve_water, stream));
-  HC_CUDA(cudaMemsetAsync(pit_water, 0, P1 * 8, st));
-  if (npairs) {
-    k_pair_reduce<<<nblk((size_t)npairs), 256, 0, st>>>((const long long *)pairs, (u32)npairs, pair_included, pit_out, nullptr,
-                                                         nullptr, nullptr, carve_water, nullptr, nullptr, nullptr, pit_water);
-    HC_LAUNCH_CHECK(ctx);
+  int64_t *carve_water = (int64_t *)arena_take(ctx, C1 * 8);
+  if (!wall_min || !sink_max || !carve_water) return HC_ERR_NOMEM;
+  HC_TRY(select_partials(ctx, fillID, carve_bound, n, npits, ncarves, wall, water, sink, wall_min, sink_max, carve_water, stream));
+  return select_tables(ctx, npits, maxfill, volfill, maxcarve, volcarve, volfb, maxfb, complete, nfill, ncarvecells, pit_out, pairs,
+                       pair_included, npairs, wall ? wall_min : nullptr, sink ? sink_max : nullptr, carve_water, fill_vol_thresh,
+                       carve_vol_thresh, max_carve_depth, maxcarve_factor, apply_shallow_fill, float32_scalars, solution, stream);
+}
+
+// over row bands: the per-band partial tables (min-reduce wall_min, max-reduce sink_max, sum carve_water across the
+// bands), then the tree on the reduced tables (every rank, redundantly).  wall / sink may be NULL (then the table is
+// left untouched and NULL must be passed to hc_pit_select_tables_dev too).
+extern "C" int hc_band_select_partials_dev(hc_ctx *ctx, const int32_t *fillID, const int32_t *carve_bound, int64_t n, int32_t npits,
+                                           int32_t ncarves, const float *wall, const float *water, const float *sink,
+                                           float *wall_min, float *sink_max, int64_t *carve_water, void *stream) {
+  HC_ENTER(ctx);
+  if (!water) { hc_set_error("select_solution: water_mask_array is None (the reference raises NameError here, tools/depressions.py:606-647)"); return HC_ERR_ARG; }
+  if (n <= 0 || npits < 0 || ncarves < 0 || !fillID || !carve_bound || !carve_water || (wall && !wall_min) || (sink && !sink_max)) {
+    hc_set_error("hc_band_select_partials: bad argument");
+    return HC_ERR_ARG;
   }
-  select_params prm = {fill_vol_thresh, carve_vol_thresh, max_carve_depth, maxcarve_factor, apply_shallow_fill,
-                       wall ? 1 : 0, sink ? 1 : 0};
-  HC_CUDA(cudaMemsetAsync(solution, 0, 4, st));
-  HC_PROF(ctx, st, "k_select");
-  if (float32_scalars)
-    k_select<float><<<nblk(P1), 256, 0, st>>>(npits, maxfill, volfill, maxcarve, volcarve, volfb, maxfb, complete,
-                                              (const long long *)nfill, (const long long *)ncarvecells, pit_water, wall_min,
-                                              sink_max, prm, solution);
-  else
-    k_select<double><<<nblk(P1), 256, 0, st>>>(npits, maxfill, volfill, maxcarve, volcarve, volfb, maxfb, complete,
-                                               (const long long *)nfill, (const long long *)ncarvecells, pit_water, wall_min,
-                                               sink_max, prm, solution);
-  HC_LAUNCH_CHECK(ctx);
-  return HC_OK;
+  HC_TRY(arena_reset(ctx));
+  return select_partials(ctx, fillID, carve_bound, n, npits, ncarves, wall, water, sink, wall_min, sink_max, carve_water, stream);
+}
+extern "C" int hc_pit_select_tables_dev(hc_ctx *ctx, int32_t npits, const float *maxfill, const float *volfill, const float *maxcarve,
+                                        const float *volcarve, const float *volfb, const float *maxfb, const int8_t *complete,
+                                        const int64_t *nfill, const int64_t *ncarvecells, const uint8_t *pit_out,
+                                        const int64_t *pairs, const uint8_t *pair_included, int64_t npairs, const float *wall_min,
+                                        const float *sink_max, const int64_t *carve_water, double fill_vol_thresh,
+                                        double carve_vol_thresh, double max_carve_depth, double maxcarve_factor,
+                                        int apply_shallow_fill, int float32_scalars, int32_t *solution, void *stream) {
+  HC_ENTER(ctx);
+  if (npits < 0 || npairs < 0 || !carve_water || !solution) { hc_set_error("hc_pit_select_tables: bad argument"); return HC_ERR_ARG; }
+  HC_TRY(arena_reset(ctx));
+  return select_tables(ctx, npits, maxfill, volfill, maxcarve, volcarve, volfb, maxfb, complete, nfill, ncarvecells, pit_out, pairs,
+                       pair_included, npairs, wall_min, sink_max, carve_water, fill_vol_thresh, carve_vol_thresh, max_carve_depth,
+                       maxcarve_factor, apply_shallow_fill, float32_scalars, solution, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
