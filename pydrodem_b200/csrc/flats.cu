@@ -50,6 +50,7 @@ namespace cg = cooperative_groups;
 #define F_LO 0x3FFFu
 #define FLCAP 1536           // NOFLOW cells a tile may hold before it is left to the slow tier
 #define FSWEEPS 40           // sweep cap: a flat that fits the apron converges well inside it
+#define FS_BATCH 1           // relaxation passes between two block-wide votes (4 measured slower: 0.78 vs 0.63 ms, most flats settle in 2-3 passes)
 
 // ------------------------------------------------------------------------------------------------
 // Sparse form of the fast tier.  On a filled DEM only a few percent of the cells are NOFLOW (3.4 % on the C2
@@ -247,15 +248,21 @@ k_flat_fast_sparse(const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB,
     }
     __syncthreads();
     // 3. relax the two distance fields and the "open" flag to their fixed point
+    //    (FS_BATCH passes between two block-wide votes: every update is a monotone step -- distances only fall, the
+    //    open flag is only ever set -- so the passes need no barrier between them, and a batch without any change is a
+    //    full pass over stable values)
     int sweeps = 0;
+    volatile unsigned short *vslo = slo, *vshi = shi;
     for (;;) {
       int changed = 0;
+#pragma unroll 1
+      for (int it = 0; it < FS_BATCH; it++)
       for (u32 k = tid; k < nlist; k += FS_THREADS) {
         const int ri = list[k];
         u32 mnf = lmask[k] & 0xFFu;
         if (!mnf) continue;
-        const u32 w = slo[ri];
-        const u32 lo = w & F_LO, hi = shi[ri];
+        const u32 w = vslo[ri];
+        const u32 lo = w & F_LO, hi = vshi[ri];
         u32 blo = lo ? lo : 0xFFFFu, bhi = hi ? hi : 0xFFFFu;
         u32 open = w & F_OPEN;
         while (mnf) {
@@ -263,20 +270,20 @@ k_flat_fast_sparse(const uint8_t *__restrict__ dirA, uint8_t *__restrict__ dirB,
           mnf &= mnf - 1;
           const int kk = j + (j >= 4);
           const int ni = ri + (kk / 3 - 1) * FR + (kk % 3 - 1);
-          const u32 nw = slo[ni];
+          const u32 nw = vslo[ni];
           const u32 nlo = nw & F_LO;
           if (nlo && nlo + 1 < blo) blo = nlo + 1;
-          const u32 nhi = shi[ni];
+          const u32 nhi = vshi[ni];
           if (nhi && nhi + 1 < bhi) bhi = nhi + 1;
           open |= nw & F_OPEN;
         }
         if (blo == 0xFFFFu) blo = 0;
         if (bhi == 0xFFFFu) bhi = 0;
         const u32 nw2 = F_NF | open | blo;
-        if (nw2 != w) { slo[ri] = (unsigned short)nw2; changed = 1; }
-        if (bhi != hi) { shi[ri] = (unsigned short)bhi; changed = 1; }
+        if (nw2 != w) { vslo[ri] = (unsigned short)nw2; changed = 1; }
+        if (bhi != hi) { vshi[ri] = (unsigned short)bhi; changed = 1; }
       }
-      sweeps++;
+      sweeps += FS_BATCH;
       if (!__syncthreads_or(changed)) break;
       if (sweeps >= FSWEEPS) { giveup = true; break; }
     }
@@ -687,6 +694,10 @@ __device__ __forceinline__ void relax_tile(const float *__restrict__ z, const ui
 // swept on the L2-resident rasters: eight dependent L2 round trips per cell and sweep).  Same re-queue / wake rules as
 // the window path.
 #define FL_PER (FL_LCAP / NTHREADS)
+#ifndef HC_LIGHT_ASYNC
+#define HC_LIGHT_ASYNC 1
+#endif
+#define FL_BATCH 3            // relaxation passes between two block-wide votes (light visits)
 #define FL_RING (4 * T + 4)   // ring cells: row -1 (T + 2, corners included), row T (T + 2), column -1 (T), column T (T)
 #define RING_IDX(nr_, nc_) ((nr_) < 0 ? (nc_) + 1 : ((nr_) >= T ? (T + 2) + (nc_) + 1 : ((nc_) < 0 ? 2 * (T + 2) + (nr_) : 2 * (T + 2) + T + (nr_))))
 #define RING_TILE(nr_, nc_) (((nr_) < 0 ? 0 : ((nr_) >= T ? 2 : 1)) * 3 + ((nc_) < 0 ? 0 : ((nc_) >= T ? 2 : 1)))
@@ -812,6 +823,36 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ dirA, u3
   int nsweeps = 0;
   const long long t_l2 = clock64();
   __syncthreads();
+#if HC_LIGHT_ASYNC
+  // Asynchronous pull relaxation: every thread lowers ITS cells from their listed neighbours, FL_BATCH times in a row
+  // without any barrier in between -- chaotic iteration of a monotone operator converges to the same fixed point in any
+  // interleaving, so warps need not wait for each other -- and one block-wide vote per batch decides whether anything
+  // still moved.  A batch in which no thread changed anything is a full pass over stable values: the fixed point.  (The
+  // barrier-per-sweep forms, pull or push, spent half of a visit waiting at ~14 block barriers with 7 of 8 warps idle.)
+  for (;;) {
+    int changed = 0;
+#pragma unroll 1
+    for (int it = 0; it < FL_BATCH; it++) {
+#pragma unroll
+      for (int j = 0; j < FL_PER; j++) {
+        if ((msk[j] & 0x300u) != 0x100u) continue;
+        u32 bl = lo[j], bh = hi[j];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const u32 rk = (ref[j][i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+          if (rk == 0xFFFFu) break;   // (slots fill from the low end)
+          bl = min(bl, vlo[rk] + 1u);
+          bh = min(bh, vhi[rk] + 1u);
+        }
+        const u32 k = tid + j * NTHREADS;
+        if (bl < lo[j]) { lo[j] = bl; vlo[k] = bl; chg |= 1u << j; changed = 1; }
+        if (bh < hi[j]) { hi[j] = bh; vhi[k] = bh; chg |= 1u << j; changed = 1; }
+      }
+    }
+    nsweeps += FL_BATCH;
+    if (!__syncthreads_or(changed)) break;
+  }
+#else
   // Push relaxation: a cell whose value dropped offers value + 1 to its listed neighbours (shared atomicMin, only when it
   // lowers them), so a sweep costs work only where the front is; the first sweep offers every reached cell once.  (The
   // pull form re-read all eight neighbours of every cell in every sweep: 16 shared loads per cell and sweep.)  A sweep
@@ -859,6 +900,7 @@ __device__ __forceinline__ void relax_light(const uint8_t *__restrict__ dirA, u3
       }
     }
   }
+#endif
   const long long t_l3 = clock64();
   if (tid == 0) { HC_DBG(3, nsweeps); HC_DBG(4, 1); HC_DBG(6, 1); HC_DBG(12, t_l1 - t_begin); HC_DBG(13, t_l2 - t_l1); HC_DBG(14, t_l3 - t_l2); HC_DBG(15, cnt); }
 #pragma unroll
