@@ -505,6 +505,12 @@ def apply_rank(fn, own_rasters, halo, comm=None):
 # ---- partial max / sum).  The per-cell reductions run band by band (hc_band_catalog_local_dev, hc_band_select_partials_dev),
 # ---- the per-label tables are reduced across the bands (torch.distributed all_reduce over NCCL; plain tensor ops between the
 # ---- bands one process holds), the small table logic runs redundantly on every rank, and apply_solution is per cell.
+def u64_order_flip(t):
+    """int64 view of uint64 keys <-> int64 values whose SIGNED order is the keys' UNSIGNED order (flip the sign bit;
+    the map is its own inverse): lets a signed MAX / MIN all_reduce stand in for the unsigned one"""
+    return t ^ (-(1 << 63))
+
+
 class BandedCatalog:
     """dep.build_pit_catalog / select_solution / apply_solution (tools/depressions.py:272-810, :1140-1228) for one raster
     cut into row bands.  `bands`: this process's consecutive bands, each a dict of flat device tensors
@@ -538,9 +544,8 @@ class BandedCatalog:
         return out
 
     def _reduce_u64(self, parts, op):
-        """unsigned 64-bit max / min of keys held in int64 tensors: flip the sign bit, reduce signed, flip back"""
-        flip = -(1 << 63)
-        return self._reduce([p ^ flip for p in parts], op) ^ flip
+        """unsigned 64-bit max / min of keys held in int64 tensors (torch.distributed has no unsigned reduction)"""
+        return u64_order_flip(self._reduce([u64_order_flip(p) for p in parts], op))
 
     def _p(self, t):
         return ctypes.c_void_p(t.data_ptr()) if t is not None else None

@@ -206,3 +206,22 @@ def test_unit_discovery_helpers(tmp_path):
     assert logt.find_all_basins_IDs(str(tmp_path)) == [6010, 6020]
     import time
     assert logt.log_time("X", time.time() - 3725).startswith("X COMPLETE -- elapsed 01:02:0")
+
+
+def test_u64_order_flip_turns_signed_reductions_into_unsigned_ones():
+    """bands.BandedCatalog reduces 64-bit (value, cell index) keys across ranks with signed int64 MAX / MIN all_reduces"""
+    import torch
+    from pydrodem_b200.bands import u64_order_flip
+    keys = [0, 1, 0x7FFFFFFFFFFFFFFF, 0x8000000000000000, 0x8000000000000001, 0xFFFFFFFFFFFFFFFE, 0xFFFFFFFFFFFFFFFF,
+            (0xC2F00000 << 32) | 12345, (0x3D100000 << 32) | 0xFFFFFFFF]
+    as_i64 = torch.tensor([k - (1 << 64) if k >= (1 << 63) else k for k in keys], dtype=torch.int64)
+    flipped = u64_order_flip(as_i64)
+    order_unsigned = sorted(range(len(keys)), key=lambda i: keys[i])
+    order_flipped = sorted(range(len(keys)), key=lambda i: int(flipped[i]))
+    assert order_unsigned == order_flipped
+    assert torch.equal(u64_order_flip(flipped), as_i64)
+    a, b = as_i64[:5], as_i64[4:9]
+    n = min(len(a), len(b))
+    got = u64_order_flip(torch.maximum(u64_order_flip(a[:n]), u64_order_flip(b[:n])))
+    want = [max(keys[i], keys[4 + i]) for i in range(n)]
+    assert [int(v) % (1 << 64) for v in got] == want
