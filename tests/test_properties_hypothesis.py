@@ -65,3 +65,30 @@ def test_breach_equals_restatement_and_drains(ny, nx, seed, max_length, fill_pit
     assert [st_[0], st_[1], st_[2], st_[3]] == [sw["pits"], sw["breached"], sw["left"], sw["cut"]]
     assert np.array_equal(ho.fill(out, ND, ho.SEED_WBT), out)    # depression free
     assert np.array_equal(out == ND, z == ND)
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(6, 16), st.integers(6, 18), st.integers(0, 2 ** 31 - 1), st.integers(2, 12), st.booleans(),
+       st.sampled_from([None, 0.5, 3.0, 40.0]), st.sampled_from([None, 0.01]))
+def test_least_cost_breach_specification_properties(ny, nx, seed, levels, min_dist, max_cost, eps):
+    """oracle/breach_leastcost.py on random small surfaces: never raises a cell, accounts for every pit, can only reduce
+    what a fill has to add, respects the cost limit, and with a window that sees the whole raster and no limit every pit
+    drains (a fill adds nothing afterwards)"""
+    from oracle import breach_leastcost as lc
+    rng = np.random.default_rng(seed)
+    z = rng.integers(0, levels, (ny, nx)).astype(np.float32)
+    if seed % 3 == 0:
+        z[ny // 2, nx // 2] = ND
+    out, st_ = lc.breach_least_cost(z, ND, dist=4, max_cost=max_cost, min_dist=min_dist, flat_increment=eps, return_stats=True)
+    valid = z != ND
+    assert (out[valid] <= z[valid]).all() and np.array_equal(out[~valid], z[~valid])
+    assert st_["pits"] == st_["breached"] + st_["left"] and st_["cells_lowered"] == int((out < z).sum())
+    v0 = float((ho.fill(z, ND, ho.SEED_TAUDEM) - z)[valid].sum())
+    v1 = float((ho.fill(out, ND, ho.SEED_TAUDEM) - out)[valid].sum())
+    assert v1 <= v0 + 1e-4
+    if max_cost is not None and eps is None:
+        # level channels: what one breach removes is at most its cost limit; all of them together at most pits x limit
+        assert float((z - out)[valid].sum()) <= st_["breached"] * max_cost * (1 + 1e-6) + 1e-3
+    if eps is None:
+        full = lc.breach_least_cost(z, ND, dist=max(ny, nx), min_dist=min_dist)
+        assert np.array_equal(ho.fill(full, ND, ho.SEED_TAUDEM), full)
